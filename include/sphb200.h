@@ -1,0 +1,183 @@
+/* ============================================================================
+ * sphb200.h -- C ABI of the B200-native SPH hydro-derivative engine.
+ *
+ * This is the drop-in boundary: a host-side Spheral `Physics<Dim>` package (or the Python
+ * mirror in spheral_b200/) calls these entry points instead of running the reference's CPU loops.
+ * Plain pointers and sizes only; no C++/torch types.  Every entry point cites the reference interface it
+ * replaces (llnl/spheral @ c64796e1, paths relative to src/).
+ *
+ * Conventions
+ *   - One context per GPU / rank.  Not re-entrant per context.  All work is stream-ordered on the context's
+ *     stream; functions that return data to the host synchronise that stream.
+ *   - All functions return 0 on success, non-zero on error; sphb200_last_error() gives the message
+ *     (the reference throws VERIFYError -> Python exception, Utilities/DBC.hh:28-45; the host wrapper re-raises).
+ *   - Host field layout is the reference's Field<DataType> AoS (Field/Field.hh:213):
+ *       Vector ndim doubles | SymTensor 3-D xx,xy,xz,yy,yz,zz / 2-D xx,xy,yy | Tensor ndim*ndim row-major,
+ *     nodes [0,nInternal) internal then [nInternal,nInternal+nGhost) ghost (FieldView.hh:64-66).
+ *   - Derivatives are defined on internal nodes only (the reference's thread reduction covers internal nodes
+ *     only, Utilities/OpenMP_wrapper.hh:69-117); ghost entries are written as 0.
+ * ==========================================================================*/
+#ifndef SPHB200_H
+#define SPHB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHB200_ABI_VERSION 1
+
+typedef struct sphb200_ctx sphb200_ctx;
+
+/* ArtificialViscosity flavour (ArtificialViscosity/MonaghanGingoldViscosity.cc:41-101,
+   LimitedMonaghanGingoldViscosity.cc:120-219) */
+enum { SPHB200_Q_MG = 0, SPHB200_Q_LIMITED_MG = 1 };
+/* smoothing-scale sub-package run after the hydro (SPH/SPHHydros.py:129-140):
+   SPHSmoothingScale.cc:101-275 | ASPHSmoothingScale.cc:110-147 | none */
+enum { SPHB200_H_SPH = 0, SPHB200_H_ASPH = 1, SPHB200_H_NONE = 2 };
+/* analytic kernels for sphb200_table_kernel_build (Kernel/*KernelInline.hh) */
+enum { SPHB200_KERNEL_BSPLINE = 0, SPHB200_KERNEL_WENDLANDC4 = 1, SPHB200_KERNEL_WENDLANDC2 = 2 };
+/* which TableKernel a table upload refers to (SPHBase.hh:182-183: kernel() / PiKernel()) */
+enum { SPHB200_TABLE_W = 0, SPHB200_TABLE_WPI = 1 };
+
+/* Constructor arguments of SPH<Dim> (SPH/SPH.hh:40-56, SPH/SPHHydros.py:9-33) that the derivative path
+   reads, plus the Q parameters (ArtificialViscosityHandle.cc:37-53) and NodeList bounds used by the
+   smoothing-scale package (NodeList hmin/hmax/nodesPerSmoothingScale). */
+typedef struct {
+  int    ndim;                      /* 2 | 3 */
+  int    compatibleEnergy;          /* compatibleEnergyEvolution */
+  int    evolveTotalEnergy;
+  int    XSPH;
+  int    correctVelocityGradient;
+  double epsTensile;
+  double nTensile;
+  double nPerh;                     /* nodesPerSmoothingScale of NodeList 0 */
+  int    Qkind;                     /* SPHB200_Q_* */
+  double Cl, Cq, eps2, negligibleSoundSpeed;
+  int    balsara, linearInExpansion, quadraticInExpansion;
+  double etaCritFrac, etaFoldFrac;
+  int    hEvolution;                /* SPHB200_H_* */
+  double hmin, hmax;
+} sphb200_options;
+
+/* State fields read by the path (SPH.cc:206-216; Appendix B of SURVEY.md). Bits for fieldMask. */
+enum {
+  SPHB200_F_POSITION = 1u << 0,  SPHB200_F_VELOCITY = 1u << 1,  SPHB200_F_H = 1u << 2,
+  SPHB200_F_MASS = 1u << 3,      SPHB200_F_RHO = 1u << 4,       SPHB200_F_EPS = 1u << 5,
+  SPHB200_F_PRESSURE = 1u << 6,  SPHB200_F_SOUNDSPEED = 1u << 7, SPHB200_F_OMEGA = 1u << 8,
+  SPHB200_F_DVDXQ = 1u << 9,     SPHB200_F_FCL = 1u << 10,      SPHB200_F_FCQ = 1u << 11,
+  SPHB200_F_ALL_BASIC = 0x1FFu
+};
+typedef struct {
+  const double *position, *velocity, *H, *mass, *massDensity, *specificThermalEnergy,
+               *pressure, *soundSpeed, *omegaGradh, *DvDxQ, *fCl, *fCq;
+} sphb200_host_state;
+
+/* Derivative fields written by the path (SPH.cc:230-245, SPHSmoothingScale.cc:130-137). Bits for fieldMask. */
+enum {
+  SPHB200_D_DXDT = 1u << 0,   SPHB200_D_DRHODT = 1u << 1,  SPHB200_D_DVDT = 1u << 2,   SPHB200_D_DEPSDT = 1u << 3,
+  SPHB200_D_DVDX = 1u << 4,   SPHB200_D_LOCALDVDX = 1u << 5, SPHB200_D_GRADRHO = 1u << 6, SPHB200_D_M = 1u << 7,
+  SPHB200_D_LOCALM = 1u << 8, SPHB200_D_RHOSUM = 1u << 9,  SPHB200_D_NORM = 1u << 10,  SPHB200_D_MAXQ = 1u << 11,
+  SPHB200_D_EFFQ = 1u << 12,  SPHB200_D_XSPHW = 1u << 13,  SPHB200_D_XSPHDV = 1u << 14, SPHB200_D_DHDT = 1u << 15,
+  SPHB200_D_HIDEAL = 1u << 16, SPHB200_D_M0 = 1u << 17,    SPHB200_D_M1 = 1u << 18,
+  SPHB200_D_ALL = 0x7FFFFu
+};
+typedef struct {
+  double *DxDt, *DrhoDt, *DvDt, *DepsDt, *DvDx, *localDvDx, *gradRho, *M, *localM,
+         *rhoSum, *normalization, *maxViscousPressure, *effViscousPressure, *XSPHWeightSum, *XSPHDeltaV,
+         *DHDt, *Hideal, *massZerothMoment, *massFirstMoment;
+} sphb200_host_derivs;
+
+/* ---- life cycle --------------------------------------------------------------------------------------
+   replaces: SPH<Dim>::SPH(...) (SPH/SPH.cc:43-80) + SPHBase::initializeProblemStartup (SPHBase.cc:116-142) */
+int  sphb200_abi_version(void);
+int  sphb200_create(sphb200_ctx** ctx, int device, const sphb200_options* opts);
+void sphb200_destroy(sphb200_ctx* ctx);
+int  sphb200_set_options(sphb200_ctx* ctx, const sphb200_options* opts);   /* property setters, SPHBase.hh:131-176 */
+const char* sphb200_last_error(const sphb200_ctx* ctx);                     /* NULL ctx -> last global error */
+int  sphb200_sync(sphb200_ctx* ctx);
+
+/* ---- TableKernel ---------------------------------------------------------------------------------------
+   Upload the coefficients of a host TableKernel: three QuadraticInterpolators sharing (xmin,xstep,n1), each
+   3*(n1+1) doubles (Kernel/TableKernel.cc:169-209; readable from a real Spheral through
+   PYB11/Kernel/Kernel.py:432-434 + PYB11/Utilities/QuadraticInterpolator.py:53-102).  nperhVals/wsumVals are the
+   CubicHermite lookups (n values then n gradients; may be NULL when hEvolution != SPHB200_H_SPH). */
+int  sphb200_set_kernel_table(sphb200_ctx* ctx, int which, double kext, double xmin, double xstep, size_t n1,
+                              const double* Wcoef, const double* gradWcoef, const double* grad2Wcoef,
+                              size_t nperhN, double nperhXmin, double nperhXmax, const double* nperhVals,
+                              size_t wsumN, double wsumXmin, double wsumXmax, const double* wsumVals);
+/* Stand-alone host-side TableKernel construction (no GPU needed; used when no Spheral TableKernel exists):
+   TableKernel<Dim>::TableKernel(kernel, numPoints, minNperh, maxNperh), Kernel/TableKernel.cc:169-209.
+   Coefficient arrays must hold sphb200_table_ncoef(numPoints) doubles, lookup arrays 2*numPoints doubles. */
+size_t sphb200_table_ncoef(size_t numPoints);
+int  sphb200_table_kernel_build(int kind, int ndim, size_t numPoints, double minNperh, double maxNperh,
+                                double* kext, double* xstep, size_t* n1,
+                                double* Wcoef, double* gradWcoef, double* grad2Wcoef,
+                                double* nperhVals, double* nperhRange /*[2]*/,
+                                double* wsumVals, double* wsumRange /*[2]*/);
+
+/* ---- node data -------------------------------------------------------------------------------------------
+   replaces: State<Dim>::fields(name) reads at SPH.cc:206-216 (device-resident copies keep their values across
+   Integrator stages until re-uploaded). */
+int  sphb200_set_nodes(sphb200_ctx* ctx, size_t nInternal, size_t nGhost);
+int  sphb200_upload_state(sphb200_ctx* ctx, unsigned fieldMask, const sphb200_host_state* s);
+int  sphb200_download_state(sphb200_ctx* ctx, unsigned fieldMask, double* const* fields /* same order as struct */);
+
+/* ---- neighbour pairs ---------------------------------------------------------------------------------------
+   replaces: Neighbor::updateNodes (TreeNeighbor.cc:370-455 / NestedGridNeighbor.cc:209-560) +
+             ConnectivityMap::computeConnectivity (ConnectivityMap.cc:747-1152).
+   Uses the positions/H currently on the device.  npairs = size of the NodePairList (i<j once). */
+int  sphb200_build_pairs(sphb200_ctx* ctx, size_t* npairs);
+/* NodePairList in the reference order (NodePairIdxType::operator<, NodePairIdxType.hh:34-58): sorted (i,j), i<j. */
+int  sphb200_download_pairs(sphb200_ctx* ctx, uint32_t* i, uint32_t* j, size_t cap);
+/* ConnectivityMap::numNeighborsForNode for internal nodes (ConnectivityMapInline.hh) */
+int  sphb200_download_neighbor_counts(sphb200_ctx* ctx, uint32_t* counts);
+
+/* ---- derivatives ---------------------------------------------------------------------------------------------
+   replaces: SPH<Dim>::evaluateDerivatives (SPH.cc:141-555) followed by the smoothing-scale package's
+   evaluateDerivatives; derivatives are zeroed first (CheapSynchronousRK2.cc:87 derivs.Zero()). Asynchronous. */
+int  sphb200_evaluate_derivatives(sphb200_ctx* ctx, double time, double dt);
+int  sphb200_download_derivs(sphb200_ctx* ctx, unsigned fieldMask, const sphb200_host_derivs* d);
+/* PairwiseField "pair-wise accelerations" (SPH.cc:129-133, :430) in NodePairList order, npairs*ndim doubles. */
+int  sphb200_download_pair_accelerations(sphb200_ctx* ctx, double* pairAccelerations, size_t cap);
+/* ArtificialViscosityHandle::postStateUpdate copy DvDx -> Q velocity gradient (ArtificialViscosityHandle.cc:165-180) */
+int  sphb200_copy_DvDx_to_Q(sphb200_ctx* ctx);
+
+/* ---- compatible energy -----------------------------------------------------------------------------------------
+   replaces: SpecificThermalEnergyPolicy::update (Hydro/SpecificThermalEnergyPolicy.cc:47-174):
+   eps += multiplier * (pair-wise discrete work), using the velocity/mass/eps currently on the device and the
+   DvDt, DepsDt and pair accelerations of the last sphb200_evaluate_derivatives call. */
+int  sphb200_update_energy_compatible(sphb200_ctx* ctx, double multiplier);
+
+/* ---- multi-GPU halo (Distributed/DistributedBoundary.cc:565-753, 1256-1353) ---------------------------------------
+   The exchange itself is NCCL send/recv issued by the host plumbing on device staging buffers; these two calls
+   are the device-side pack (gather the listed send nodes of the masked fields into one staging buffer) and the
+   ghost landing (copy a received staging buffer into ghost slots [firstGhost, firstGhost+count)).
+   Staging layout: field-major, each field count*width doubles, fields in ascending mask-bit order. */
+size_t sphb200_halo_bytes_per_node(const sphb200_ctx* ctx, unsigned fieldMask);
+int  sphb200_halo_pack(sphb200_ctx* ctx, unsigned fieldMask, const uint32_t* sendNodesDevice, size_t count,
+                       void* stagingDevice);
+int  sphb200_halo_unpack(sphb200_ctx* ctx, unsigned fieldMask, size_t firstGhost, size_t count,
+                         const void* stagingDevice);
+/* raw stream handle (cudaStream_t) so the plumbing can order NCCL calls after pack / before unpack */
+void* sphb200_stream(sphb200_ctx* ctx);
+
+/* ---- instrumentation ----------------------------------------------------------------------------------------------
+   Number of kernels of this library launched on the context since creation, and device time (ms, CUDA events on the
+   context's stream) of the last build_pairs / evaluate_derivatives / update_energy calls and of their dominant kernels. */
+typedef struct {
+  uint64_t launches;
+  float ms_build_pairs, ms_evaluate, ms_energy;
+  float ms_pair_kernel;        /* the K3 pair-loop kernel alone */
+  float ms_neighbor_kernels;   /* K2 count+fill */
+  uint64_t directed_edges;     /* sum of neighbour counts (2*internal-internal + internal-ghost pairs) */
+} sphb200_stats;
+int  sphb200_get_stats(sphb200_ctx* ctx, sphb200_stats* out);
+/* FP64 FMA throughput microbenchmark on the context's device (roofline denominator; returns TFLOP/s). */
+int  sphb200_measure_fp64_peak(sphb200_ctx* ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,262 @@
+"""ctypes front-end of the CPU ORACLE (test infrastructure, NOT product code).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference`` legs may import
+this module.  Nothing under spheral_b200/ does.  See oracle/sph_oracle.h for what is restated and how the
+restatement is pinned.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libsph_oracle.so")
+
+KERNEL_BSPLINE, KERNEL_WENDLANDC4, KERNEL_WENDLANDC2 = 0, 1, 2
+Q_MG, Q_LIMITED_MG = 0, 1
+H_SPH, H_ASPH, H_NONE = 0, 1, 2
+
+
+def build(force=False):
+    """Compile the C restatement (gcc only)."""
+    if force or not os.path.exists(_LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+class Options(C.Structure):
+    _fields_ = [("ndim", C.c_int), ("compatibleEnergy", C.c_int), ("evolveTotalEnergy", C.c_int),
+                ("XSPH", C.c_int), ("correctVelocityGradient", C.c_int),
+                ("epsTensile", C.c_double), ("nTensile", C.c_double), ("nPerh", C.c_double),
+                ("Qkind", C.c_int), ("Cl", C.c_double), ("Cq", C.c_double), ("eps2", C.c_double),
+                ("negligibleSoundSpeed", C.c_double),
+                ("balsara", C.c_int), ("linearInExpansion", C.c_int), ("quadraticInExpansion", C.c_int),
+                ("etaCritFrac", C.c_double), ("etaFoldFrac", C.c_double),
+                ("hEvolution", C.c_int), ("hmin", C.c_double), ("hmax", C.c_double)]
+
+
+_dp = C.POINTER(C.c_double)
+
+
+class Table(C.Structure):
+    _fields_ = [("kext", C.c_double), ("xmin", C.c_double), ("xstep", C.c_double), ("n1", C.c_size_t),
+                ("Wcoef", _dp), ("gradWcoef", _dp), ("grad2Wcoef", _dp),
+                ("nperhN", C.c_size_t), ("nperhXmin", C.c_double), ("nperhXmax", C.c_double),
+                ("nperhXstep", C.c_double), ("nperhVals", _dp),
+                ("wsumN", C.c_size_t), ("wsumXmin", C.c_double), ("wsumXmax", C.c_double),
+                ("wsumXstep", C.c_double), ("wsumVals", _dp)]
+
+
+class State(C.Structure):
+    _fields_ = [(k, _dp) for k in ("pos", "vel", "H", "mass", "rho", "P", "cs", "omega", "DvDxQ", "fCl", "fCq")]
+
+
+DERIV_FIELDS = ("DxDt", "DrhoDt", "DvDt", "DepsDt", "DvDx", "localDvDx", "gradRho", "M", "localM",
+                "rhoSum", "normalization", "maxViscousPressure", "effViscousPressure",
+                "XSPHWeightSum", "XSPHDeltaV", "DHDt", "Hideal", "massZerothMoment", "massFirstMoment",
+                "pairAccelerations")
+
+
+class Derivs(C.Structure):
+    _fields_ = [(k, _dp) for k in DERIV_FIELDS]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.orc_kernel_extent.restype = C.c_double
+        L.orc_kernel_extent.argtypes = [C.c_int, C.c_int]
+        L.orc_kernel_analytic.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp]
+        L.orc_table_ncoef.restype = C.c_size_t
+        L.orc_table_ncoef.argtypes = [C.c_size_t]
+        L.orc_table_build.argtypes = [C.c_int, C.c_int, C.c_size_t, _dp, _dp, _dp, _dp, C.POINTER(C.c_size_t), _dp]
+        L.orc_table_build_nperh.argtypes = [C.POINTER(Table), C.c_int, C.c_size_t, C.c_double, C.c_double,
+                                            _dp, _dp, _dp, _dp]
+        L.orc_table_eval.argtypes = [C.POINTER(Table), C.c_double, C.c_double, _dp, _dp]
+        L.orc_cubic_hermite_eval.restype = C.c_double
+        L.orc_cubic_hermite_eval.argtypes = [C.c_size_t, C.c_double, C.c_double, C.c_double, _dp, C.c_double]
+        u32p = C.POINTER(C.c_uint32)
+        for f in (L.orc_pairs_bruteforce, L.orc_pairs_cells):
+            f.restype = C.c_size_t
+            f.argtypes = [C.c_int, C.c_size_t, C.c_size_t, _dp, _dp, C.c_double, u32p, u32p, C.c_size_t, u32p]
+        L.orc_evaluate_derivatives.argtypes = [C.POINTER(Options), C.POINTER(Table), C.POINTER(Table),
+                                               C.c_size_t, C.c_size_t, C.POINTER(State), C.c_size_t, u32p, u32p,
+                                               u32p, C.POINTER(Derivs), C.c_int]
+        L.orc_update_energy_compatible.argtypes = [C.c_int, C.c_size_t, C.c_size_t, _dp, _dp, _dp, _dp, C.c_size_t,
+                                                   u32p, u32p, _dp, C.c_double, _dp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _u(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+def _c(a, dtype=np.float64):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+def nsym(ndim):
+    return 6 if ndim == 3 else 3
+
+
+class TableKernel:
+    """TableKernel(kind, numPoints) restated (Kernel/TableKernel.cc:169-209)."""
+
+    def __init__(self, kind, ndim, numPoints=100, minNperh=0.25, maxNperh=64.0, with_nperh=True):
+        L = lib()
+        nc = L.orc_table_ncoef(numPoints)
+        self.kind, self.ndim, self.numPoints = kind, ndim, numPoints
+        self.Wcoef = np.zeros(nc)
+        self.gradWcoef = np.zeros(nc)
+        self.grad2Wcoef = np.zeros(nc)
+        kext = C.c_double()
+        n1 = C.c_size_t()
+        xstep = C.c_double()
+        rc = L.orc_table_build(kind, ndim, numPoints, _p(self.Wcoef), _p(self.gradWcoef), _p(self.grad2Wcoef),
+                               C.byref(kext), C.byref(n1), C.byref(xstep))
+        assert rc == 0
+        self.kext, self.n1, self.xstep, self.xmin = kext.value, n1.value, xstep.value, 0.0
+        self.wsumVals = self.nperhVals = None
+        self.wsumRange = self.nperhRange = None
+        if with_nperh:
+            self.wsumVals = np.zeros(2*numPoints)
+            self.nperhVals = np.zeros(2*numPoints)
+            self.wsumRange = np.zeros(2)
+            self.nperhRange = np.zeros(2)
+            t = self.ctable()
+            L.orc_table_build_nperh(C.byref(t), ndim, numPoints, minNperh, maxNperh,
+                                    _p(self.wsumVals), _p(self.wsumRange), _p(self.nperhVals), _p(self.nperhRange))
+
+    @classmethod
+    def from_arrays(cls, ndim, kext, xmin, xstep, n1, Wcoef, gradWcoef, grad2Wcoef=None,
+                    nperh=None, wsum=None):
+        """Wrap an externally built table (e.g. the product's) so GPU and oracle share ONE table."""
+        self = cls.__new__(cls)
+        self.kind, self.ndim = -1, ndim
+        self.kext, self.xmin, self.xstep, self.n1 = kext, xmin, xstep, n1
+        self.Wcoef, self.gradWcoef = _c(Wcoef), _c(gradWcoef)
+        self.grad2Wcoef = _c(grad2Wcoef) if grad2Wcoef is not None else np.zeros_like(self.Wcoef)
+        self.numPoints = 0
+        self.wsumVals = self.nperhVals = self.wsumRange = self.nperhRange = None
+        if nperh is not None:       # (vals[2n], xmin, xmax)
+            self.nperhVals, self.nperhRange = _c(nperh[0]), np.array(nperh[1:3], dtype=float)
+            self.numPoints = len(self.nperhVals)//2
+        if wsum is not None:
+            self.wsumVals, self.wsumRange = _c(wsum[0]), np.array(wsum[1:3], dtype=float)
+        return self
+
+    def ctable(self):
+        t = Table()
+        t.kext, t.xmin, t.xstep, t.n1 = self.kext, self.xmin, self.xstep, self.n1
+        t.Wcoef, t.gradWcoef, t.grad2Wcoef = _p(self.Wcoef), _p(self.gradWcoef), _p(self.grad2Wcoef)
+        if self.nperhVals is not None and self.nperhRange is not None and self.nperhRange[1] != self.nperhRange[0]:
+            n = len(self.nperhVals)//2
+            t.nperhN, t.nperhXmin, t.nperhXmax = n, self.nperhRange[0], self.nperhRange[1]
+            t.nperhXstep = (self.nperhRange[1] - self.nperhRange[0])/(n - 1)
+            t.nperhVals = _p(self.nperhVals)
+        if self.wsumVals is not None and self.wsumRange is not None and self.wsumRange[1] != self.wsumRange[0]:
+            n = len(self.wsumVals)//2
+            t.wsumN, t.wsumXmin, t.wsumXmax = n, self.wsumRange[0], self.wsumRange[1]
+            t.wsumXstep = (self.wsumRange[1] - self.wsumRange[0])/(n - 1)
+            t.wsumVals = _p(self.wsumVals)
+        return t
+
+    def kernelAndGradValue(self, eta, Hdet=1.0):
+        W, g = C.c_double(), C.c_double()
+        t = self.ctable()
+        lib().orc_table_eval(C.byref(t), eta, Hdet, C.byref(W), C.byref(g))
+        return W.value, g.value
+
+    def equivalentNodesPerSmoothingScale(self, Wsum):
+        t = self.ctable()
+        return max(0.0, lib().orc_cubic_hermite_eval(t.nperhN, t.nperhXmin, t.nperhXmax, t.nperhXstep,
+                                                     t.nperhVals, Wsum))
+
+    def equivalentWsum(self, nPerh):
+        t = self.ctable()
+        return max(0.0, lib().orc_cubic_hermite_eval(t.wsumN, t.wsumXmin, t.wsumXmax, t.wsumXstep,
+                                                     t.wsumVals, nPerh))
+
+
+def kernel_analytic(kind, ndim, eta):
+    W, g, g2 = C.c_double(), C.c_double(), C.c_double()
+    lib().orc_kernel_analytic(kind, ndim, eta, C.byref(W), C.byref(g), C.byref(g2))
+    return W.value, g.value, g2.value
+
+
+def pairs(ndim, nInt, nGhost, pos, H, kext, method="cells"):
+    """Sorted (i<j) pair list + numNeighborsForNode for internal nodes."""
+    L = lib()
+    pos, H = _c(pos), _c(H)
+    f = L.orc_pairs_bruteforce if method == "brute" else L.orc_pairs_cells
+    counts = np.zeros(nInt, dtype=np.uint32)
+    dummy = np.zeros(1, dtype=np.uint32)
+    npairs = f(ndim, nInt, nGhost, _p(pos), _p(H), kext, _u(dummy), _u(dummy), 0, _u(counts))
+    pi = np.zeros(max(npairs, 1), dtype=np.uint32)
+    pj = np.zeros(max(npairs, 1), dtype=np.uint32)
+    n2 = f(ndim, nInt, nGhost, _p(pos), _p(H), kext, _u(pi), _u(pj), npairs, _u(counts))
+    assert n2 == npairs
+    return pi[:npairs], pj[:npairs], counts
+
+
+def default_options(ndim, **kw):
+    o = Options()
+    o.ndim = ndim
+    o.compatibleEnergy, o.evolveTotalEnergy, o.XSPH, o.correctVelocityGradient = 1, 0, 1, 1
+    o.epsTensile, o.nTensile, o.nPerh = 0.0, 4.0, 2.01
+    o.Qkind, o.Cl, o.Cq, o.eps2, o.negligibleSoundSpeed = Q_MG, 1.0, 1.0, 1.0e-2, 1.0e-10
+    o.balsara = o.linearInExpansion = o.quadraticInExpansion = 0
+    o.etaCritFrac, o.etaFoldFrac = 1.0, 0.2
+    o.hEvolution, o.hmin, o.hmax = H_SPH, 1.0e-20, 1.0e20
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise KeyError(k)
+        setattr(o, k, v)
+    return o
+
+
+def evaluate_derivatives(opts, W, state, nInt, nGhost, pi, pj, counts, WQ=None, nthreads=1):
+    """state: dict of AoS numpy arrays (pos, vel, H, mass, rho, P, cs, omega[, DvDxQ, fCl, fCq]).
+    Returns dict of derivative arrays (DERIV_FIELDS)."""
+    L = lib()
+    nd = opts.ndim
+    n = nInt + nGhost
+    ns, nt = nsym(nd), nd*nd
+    keep = {k: _c(state.get(k)) for k in ("pos", "vel", "H", "mass", "rho", "P", "cs", "omega", "DvDxQ", "fCl", "fCq")}
+    s = State(**{k: _p(v) for k, v in keep.items()})
+    npairs = len(pi)
+    shapes = dict(DxDt=nd, DrhoDt=1, DvDt=nd, DepsDt=1, DvDx=nt, localDvDx=nt, gradRho=nd, M=nt, localM=nt,
+                  rhoSum=1, normalization=1, maxViscousPressure=1, effViscousPressure=1, XSPHWeightSum=1,
+                  XSPHDeltaV=nd, DHDt=ns, Hideal=ns, massZerothMoment=1, massFirstMoment=nd)
+    out = {k: np.zeros((n, w) if w > 1 else n) for k, w in shapes.items()}
+    out["pairAccelerations"] = np.zeros((npairs, nd))
+    d = Derivs(**{k: _p(v) for k, v in out.items()})
+    pi, pj, counts = _c(pi, np.uint32), _c(pj, np.uint32), _c(counts, np.uint32)
+    tW = W.ctable()
+    tQ = WQ.ctable() if WQ is not None else None
+    rc = L.orc_evaluate_derivatives(C.byref(opts), C.byref(tW), C.byref(tQ) if tQ is not None else None,
+                                    nInt, nGhost, C.byref(s), npairs, _u(pi), _u(pj), _u(counts), C.byref(d),
+                                    nthreads)
+    if rc != 0:
+        raise RuntimeError("SPH error : you cannot simultaneously use both compatibleEnergyEvolution and "
+                           "evolveTotalEnergy" if rc == 2 else "oracle error %d" % rc)
+    return out
+
+
+def update_energy_compatible(ndim, nInt, nGhost, mass, vel, DvDt, DepsDt0, pi, pj, pacc, multiplier, eps):
+    eps = np.array(eps, dtype=np.float64, copy=True)
+    mass, vel, DvDt, DepsDt0, pacc = map(_c, (mass, vel, DvDt, DepsDt0, pacc))
+    pi, pj = _c(pi, np.uint32), _c(pj, np.uint32)
+    lib().orc_update_energy_compatible(ndim, nInt, nGhost, _p(mass), _p(vel), _p(DvDt), _p(DepsDt0), len(pi),
+                                       _u(pi), _u(pj), _p(pacc), multiplier, _p(eps))
+    return eps

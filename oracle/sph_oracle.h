@@ -1,0 +1,131 @@
+/* ----------------------------------------------------------------------------
+ * sph_oracle.h -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A plain-C, FP64 restatement of the reference (llnl/spheral @ c64796e1)
+ * algorithm for the SPH hydro-derivative hot path.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may build, load or call anything in oracle/.  The product path
+ * (spheral_b200/, include/) never links or imports it.
+ *
+ * The reference itself cannot be compiled in this image (needs Eigen 5, RAJA,
+ * CHAI, axom, boost, polytope, silo, MPI -- none vendored), so
+ * this restatement is pinned by the reference's own known-answer *properties*
+ * (tests/unit/Neighbor/NeighborTestBase.py:192-258 brute-force neighbour sets,
+ * tests/unit/SPH/testLinearVelocityGradient.py linear-field DvDx to 5e-5,
+ * tests/unit/Kernel/testTableKernel.py:74-90 table vs analytic 1e-3/1e-2,
+ * tests/functional/Hydro/Noh/Noh-cylindrical-2d.py:803-808 |dE/E|<1e-13).
+ * No per-node golden derivative vectors exist in the reference tree, so
+ * bit-level derivative values are "parity unpinned"; see DESIGN.md.
+ *
+ * Layout conventions (the reference's Field<DataType> AoS):
+ *   Vector     : ndim doubles            (x,y[,z])
+ *   SymTensor  : 3-D xx,xy,xz,yy,yz,zz   2-D xx,xy,yy   (GeomSymmetricTensorBase.hh:43-70)
+ *   Tensor     : ndim*ndim doubles, row major
+ *   nodes      : [0,nInternal) internal, [nInternal,nInternal+nGhost) ghost
+ * --------------------------------------------------------------------------*/
+#ifndef SPH_ORACLE_H
+#define SPH_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* analytic kernel ids */
+enum { ORC_KERNEL_BSPLINE = 0, ORC_KERNEL_WENDLANDC4 = 1, ORC_KERNEL_WENDLANDC2 = 2, ORC_KERNEL_GAUSSIAN = 3 };
+/* artificial viscosity ids */
+enum { ORC_Q_MG = 0, ORC_Q_LIMITED_MG = 1 };
+/* smoothing scale package */
+enum { ORC_H_SPH = 0, ORC_H_ASPH = 1, ORC_H_NONE = 2 };
+
+typedef struct {
+  int    ndim;                      /* 2 | 3 */
+  int    compatibleEnergy;          /* SPHBase.hh:136 */
+  int    evolveTotalEnergy;
+  int    XSPH;
+  int    correctVelocityGradient;
+  double epsTensile;                /* SPH.cc:190 */
+  double nTensile;                  /* unused by SPH.cc (pow4 hard-wired), kept for API parity */
+  double nPerh;                     /* NodeList::nodesPerSmoothingScale */
+  /* artificial viscosity (ArtificialViscosityHandle.cc:37-53) */
+  int    Qkind;
+  double Cl, Cq, eps2, negligibleSoundSpeed;
+  int    balsara, linearInExpansion, quadraticInExpansion;
+  double etaCritFrac, etaFoldFrac;  /* LimitedMonaghanGingoldViscosity */
+  /* smoothing scale */
+  int    hEvolution;                /* ORC_H_SPH | ORC_H_ASPH | ORC_H_NONE */
+  double hmin, hmax;
+} orc_options;
+
+/* TableKernel payload: three QuadraticInterpolators sharing xmin/xstep/n1
+   (Kernel/TableKernel.cc:169-209) + the two CubicHermite nperh lookups. */
+typedef struct {
+  double kext;
+  double xmin, xstep;
+  size_t n1;                        /* max interval index; 3*(n1+1) coeffs per table */
+  const double* Wcoef;
+  const double* gradWcoef;
+  const double* grad2Wcoef;
+  /* CubicHermite lookups (n values then n gradients), may be NULL/0 if unused */
+  size_t nperhN;  double nperhXmin,  nperhXmax,  nperhXstep;  const double* nperhVals;   /* Wsum -> nperh */
+  size_t wsumN;   double wsumXmin,   wsumXmax,   wsumXstep;   const double* wsumVals;    /* nperh -> Wsum */
+} orc_table;
+
+typedef struct {                    /* inputs, AoS, length nInternal+nGhost */
+  const double *pos, *vel, *H, *mass, *rho, *P, *cs, *omega;
+  const double *DvDxQ;              /* optional (LimitedMG / Balsara), Tensor */
+  const double *fCl, *fCq;          /* optional multipliers */
+} orc_state;
+
+typedef struct {                    /* outputs, AoS, length nInternal+nGhost (ghost entries left 0) */
+  double *DxDt, *DrhoDt, *DvDt, *DepsDt, *DvDx, *localDvDx, *gradRho, *M, *localM;
+  double *rhoSum, *normalization, *maxViscousPressure, *effViscousPressure;
+  double *XSPHWeightSum, *XSPHDeltaV;
+  double *DHDt, *Hideal, *massZerothMoment, *massFirstMoment;
+  double *pairAccelerations;        /* npairs * ndim, may be NULL unless compatibleEnergy */
+} orc_derivs;
+
+/* ---- kernels and tables --------------------------------------------------*/
+double orc_kernel_extent(int kind, int ndim);
+void   orc_kernel_analytic(int kind, int ndim, double eta, double* W, double* gradW, double* grad2W);
+/* QuadraticInterpolator::initialize (Utilities/QuadraticInterpolator.cc:59-100) */
+void   orc_quadratic_fit(double xmin, double xmax, size_t n, const double* yvals, double* coeffs, size_t* n1, double* xstep);
+/* table sizes: returns number of coefficients per table ( 3*(n1+1) ) for numPoints */
+size_t orc_table_ncoef(size_t numPoints);
+int    orc_table_build(int kind, int ndim, size_t numPoints, double* Wc, double* gWc, double* g2Wc,
+                       double* kext, size_t* n1, double* xstep);
+/* nperh lookups (TableKernel.cc:196-208): vals arrays each 2*numPoints doubles */
+int    orc_table_build_nperh(const orc_table* t, int ndim, size_t numPoints, double minNperh, double maxNperh,
+                             double* wsumVals, double* wsumRange /*[xmin,xmax]*/,
+                             double* nperhVals, double* nperhRange);
+void   orc_table_eval(const orc_table* t, double eta, double Hdet, double* W, double* gW);
+double orc_cubic_hermite_eval(size_t n, double xmin, double xmax, double xstep, const double* vals, double x);
+
+/* ---- neighbour pairs (ConnectivityMap.cc:912-931, 1023-1029) ---------------*/
+/* returns npairs; writes up to cap sorted (i<j) pairs; counts[i] = numNeighborsForNode (internal i) */
+size_t orc_pairs_bruteforce(int ndim, size_t nInt, size_t nGhost, const double* pos, const double* H,
+                            double kext, uint32_t* pi, uint32_t* pj, size_t cap, uint32_t* counts);
+size_t orc_pairs_cells(int ndim, size_t nInt, size_t nGhost, const double* pos, const double* H,
+                       double kext, uint32_t* pi, uint32_t* pj, size_t cap, uint32_t* counts);
+
+/* ---- derivatives ------------------------------------------------------------*/
+/* SPH<Dim>::evaluateDerivativesImpl (SPH/SPH.cc:165-555) followed by the
+   smoothing-scale sub-package (SPHSmoothingScale.cc:101-275 | ASPHSmoothingScale.cc:110-147).
+   nthreads<=1: serial, pair order; else OpenMP with per-thread scratch copies
+   (the reference's threadCopy/threadReduce strategy, FieldListInline.hh:1394-1443). */
+int orc_evaluate_derivatives(const orc_options* o, const orc_table* W, const orc_table* WQ,
+                             size_t nInt, size_t nGhost, const orc_state* s,
+                             size_t npairs, const uint32_t* pi, const uint32_t* pj,
+                             const uint32_t* numNeighbors, orc_derivs* d, int nthreads);
+
+/* SpecificThermalEnergyPolicy::update (Hydro/SpecificThermalEnergyPolicy.cc:47-174) : eps += ... */
+int orc_update_energy_compatible(int ndim, size_t nInt, size_t nGhost, const double* mass, const double* vel,
+                                 const double* DvDt, const double* DepsDt0, size_t npairs,
+                                 const uint32_t* pi, const uint32_t* pj, const double* pairAccelerations,
+                                 double multiplier, double* eps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

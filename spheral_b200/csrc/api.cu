@@ -1,0 +1,486 @@
+// api.cu -- the C ABI of libsphb200 (include/sphb200.h): context life cycle, field movement, and the drivers that
+// string the kernels of neighbors.cu / derivs.cu / energy.cu together.  No CPU fallback exists: every compute entry
+// point runs CUDA kernels on the context's device or fails with an error.
+#include "sphb200_internal.cuh"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+static std::string g_lastError;
+static std::mutex g_errMutex;
+
+int sphb200_fail(sphb200_ctx* c, const std::string& msg) {
+  if (c) c->err = msg;
+  std::lock_guard<std::mutex> lk(g_errMutex);
+  g_lastError = msg;
+  return 1;
+}
+
+namespace {
+
+constexpr int RB = 256;
+
+// sorted SoA (component-major) -> host AoS order, for downloads
+__global__ void __launch_bounds__(RB) k_unpermute(const double* __restrict__ src, size_t cap, const uint32_t* __restrict__ perm,
+                                                  size_t n, int width, double* __restrict__ dst) {
+  const size_t s = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (s >= n) return;
+  const size_t o = perm[s];
+  for (int q = 0; q < width; ++q) dst[o*width + q] = src[(size_t)q*cap + s];
+}
+// DvDx (sorted SoA) -> api DvDxQ (AoS, original order)
+__global__ void __launch_bounds__(RB) k_copy_dvdx(const double* __restrict__ src, size_t cap, const uint32_t* __restrict__ perm,
+                                                  size_t n, int width, double* __restrict__ dst) {
+  const size_t s = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (s >= n) return;
+  const size_t o = perm[s];
+  for (int q = 0; q < width; ++q) dst[o*width + q] = src[(size_t)q*cap + s];
+}
+__global__ void __launch_bounds__(RB) k_counts_by_orig(const uint32_t* __restrict__ nbrCount, const uint32_t* __restrict__ perm,
+                                                       size_t n, uint32_t nInt, uint32_t* __restrict__ out) {
+  const size_t s = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (s >= n) return;
+  const uint32_t o = perm[s];
+  if (o < nInt) out[o] = nbrCount[s];
+}
+// halo: gather listed nodes of one field into a staging block / scatter a block into a contiguous ghost range
+__global__ void __launch_bounds__(RB) k_halo_pack(const double* __restrict__ field, int width, const uint32_t* __restrict__ nodes,
+                                                  size_t count, double* __restrict__ out) {
+  const size_t t = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (t >= count*(size_t)width) return;
+  const size_t k = t/width; const int q = (int)(t % width);
+  out[t] = field[(size_t)nodes[k]*width + q];
+}
+// dependent-chain FP64 FMA throughput probe: 8 independent chains per thread
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x*1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int k = 0; k < iters; ++k) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 12345.678) out[blockIdx.x*blockDim.x + threadIdx.x] = s;
+}
+
+int alloc_nodes(sphb200_ctx* c, size_t n) {
+  if (n <= c->cap) return 0;
+  const size_t cap = n + n/32 + 32;
+  auto reall = [&](double*& p, size_t cnt) -> int {
+    if (p) cudaFree(p);
+    p = nullptr;
+    CU_CHECK(c, cudaMalloc((void**)&p, cnt*sizeof(double)));
+    return 0;
+  };
+  for (int s = 0; s < S_COUNT; ++s) {
+    if (reall(c->api[s], cap*(size_t)sphb200_state_width(c->ndim, s))) return 1;
+    c->have[s] = false;
+  }
+  if (reall(c->rows, cap*(size_t)(c->ndim == 3 ? 16 : 12))) return 1;
+  for (int s = 0; s < DV_COUNT; ++s) if (reall(c->deriv[s], cap*(size_t)sphb200_deriv_width(c->ndim, s))) return 1;
+  auto reall32 = [&](uint32_t*& p, size_t cnt) -> int {
+    if (p) cudaFree(p);
+    p = nullptr;
+    CU_CHECK(c, cudaMalloc((void**)&p, cnt*sizeof(uint32_t)));
+    return 0;
+  };
+  if (reall32(c->cellKeyApi, cap) || reall32(c->perm, cap) || reall32(c->skey, cap) || reall32(c->nbrCount, cap)) return 1;
+  const size_t nt = (cap + SPHB200_TILE - 1)/SPHB200_TILE + 1;
+  if (reall32(c->tileRows, nt)) return 1;
+  if (c->tileOff) cudaFree(c->tileOff);
+  c->tileOff = nullptr;
+  CU_CHECK(c, cudaMalloc((void**)&c->tileOff, (nt + 1)*sizeof(unsigned long long)));
+  // aux arrays are sized lazily from cap
+  for (double** p : {&c->auxPneg, &c->auxSomr2, &c->auxDvDxQ, &c->auxfCl, &c->auxfCq}) { if (*p) cudaFree(*p); *p = nullptr; }
+  c->cap = cap;
+  return 0;
+}
+
+int ensure_stage(sphb200_ctx* c, size_t bytes) {
+  if (bytes <= c->stageBytes) return 0;
+  if (c->stage) cudaFree(c->stage);
+  c->stage = nullptr; c->stageBytes = 0;
+  CU_CHECK(c, cudaMalloc((void**)&c->stage, bytes + bytes/8));
+  c->stageBytes = bytes + bytes/8;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sphb200_abi_version(void) { return SPHB200_ABI_VERSION; }
+
+const char* sphb200_last_error(const sphb200_ctx* c) {
+  if (c) return c->err.c_str();
+  return g_lastError.c_str();
+}
+
+static int check_options(sphb200_ctx* c, const sphb200_options* o) {
+  if (!o) return sphb200_fail(c, "null options");
+  if (o->ndim != 2 && o->ndim != 3) return sphb200_fail(c, "ndim must be 2 or 3");
+  // SPH.cc:97-98
+  if (o->compatibleEnergy && o->evolveTotalEnergy)
+    return sphb200_fail(c, "SPH error : you cannot simultaneously use both compatibleEnergyEvolution and evolveTotalEnergy");
+  if (!(o->nPerh > 0.0)) return sphb200_fail(c, "nPerh must be positive");
+  if (o->Qkind != SPHB200_Q_MG && o->Qkind != SPHB200_Q_LIMITED_MG) return sphb200_fail(c, "unknown Qkind");
+  if (o->hEvolution < SPHB200_H_SPH || o->hEvolution > SPHB200_H_NONE) return sphb200_fail(c, "unknown hEvolution");
+  return 0;
+}
+
+int sphb200_create(sphb200_ctx** out, int device, const sphb200_options* opts) {
+  if (!out) return sphb200_fail(nullptr, "null ctx pointer");
+  *out = nullptr;
+  if (check_options(nullptr, opts)) return 1;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return sphb200_fail(nullptr, std::string("no CUDA device available (libsphb200 has no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return sphb200_fail(nullptr, "device index out of range");
+  sphb200_ctx* c = new sphb200_ctx();
+  c->device = device; c->ndim = opts->ndim; c->opt = *opts;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return sphb200_fail(nullptr, "cudaSetDevice/cudaStreamCreate failed");
+  }
+  for (auto& ev : c->ev) cudaEventCreate(&ev);
+  cudaMalloc((void**)&c->reduceBuf, (296*9 + 16)*sizeof(double));
+  cudaMallocHost((void**)&c->reduceHost, 16*sizeof(double));
+  cudaMalloc((void**)&c->counters, 4*sizeof(unsigned long long));
+  cudaMallocHost((void**)&c->countersHost, 4*sizeof(unsigned long long));
+  if (cudaGetLastError() != cudaSuccess) { sphb200_destroy(c); return sphb200_fail(nullptr, "context allocation failed"); }
+  *out = c;
+  return 0;
+}
+
+void sphb200_destroy(sphb200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int s = 0; s < S_COUNT; ++s) cudaFree(c->api[s]);
+  for (int s = 0; s < DV_COUNT; ++s) cudaFree(c->deriv[s]);
+  for (void* p : {(void*)c->W.coef, (void*)c->W.nperhVals, (void*)c->WQ.coef, (void*)c->WQ.nperhVals, (void*)c->cellKeyApi, (void*)c->cellStart,
+                  (void*)c->cellCursor, (void*)c->perm, (void*)c->skey, (void*)c->reduceBuf, (void*)c->rows, (void*)c->auxPneg, (void*)c->auxSomr2,
+                  (void*)c->auxDvDxQ, (void*)c->auxfCl, (void*)c->auxfCq, (void*)c->nbrCount, (void*)c->tileRows, (void*)c->tileOff, (void*)c->nbr,
+                  (void*)c->counters, (void*)c->scanTmp, (void*)c->pacc, (void*)c->stage}) cudaFree(p);
+  cudaFreeHost(c->reduceHost); cudaFreeHost(c->countersHost);
+  for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int sphb200_set_options(sphb200_ctx* c, const sphb200_options* o) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  if (check_options(c, o)) return 1;
+  if (o->ndim != c->ndim) return sphb200_fail(c, "ndim cannot change after creation");
+  const bool repack = (o->epsTensile != c->opt.epsTensile) || (o->Qkind != c->opt.Qkind) || (o->balsara != c->opt.balsara);
+  c->opt = *o;
+  if (repack) c->rowsValid = false;
+  return 0;
+}
+
+int sphb200_sync(sphb200_ctx* c) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+void* sphb200_stream(sphb200_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int sphb200_set_kernel_table(sphb200_ctx* c, int which, double kext, double xmin, double xstep, size_t n1,
+                             const double* Wc, const double* gWc, const double* /*g2Wc*/,
+                             size_t nperhN, double nperhXmin, double nperhXmax, const double* nperhVals,
+                             size_t /*wsumN*/, double /*wsumXmin*/, double /*wsumXmax*/, const double* /*wsumVals*/) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  if (which != SPHB200_TABLE_W && which != SPHB200_TABLE_WPI) return sphb200_fail(c, "set_kernel_table: bad table id");
+  if (!Wc || !gWc || !(kext > 0.0) || !(xstep > 0.0)) return sphb200_fail(c, "set_kernel_table: bad arguments");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  TableDev& t = (which == SPHB200_TABLE_W) ? c->W : c->WQ;
+  const size_t nint = n1 + 1;
+  std::vector<double> inter(6*nint);
+  for (size_t k = 0; k < nint; ++k) for (int q = 0; q < 3; ++q) { inter[6*k + q] = Wc[3*k + q]; inter[6*k + 3 + q] = gWc[3*k + q]; }
+  if (t.coef) cudaFree(t.coef);
+  t.coef = nullptr;
+  CU_CHECK(c, cudaMalloc((void**)&t.coef, inter.size()*sizeof(double)));
+  CU_CHECK(c, cudaMemcpyAsync(t.coef, inter.data(), inter.size()*sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  t.kext = kext; t.xmin = xmin; t.xstep = xstep; t.n1 = (uint32_t)n1;
+  t.hostW.assign(Wc, Wc + 3*nint); t.hostG.assign(gWc, gWc + 3*nint);
+  if (t.nperhVals) { cudaFree(t.nperhVals); t.nperhVals = nullptr; }
+  t.nperhN = 0;
+  if (nperhVals && nperhN >= 2) {
+    CU_CHECK(c, cudaMalloc((void**)&t.nperhVals, 2*nperhN*sizeof(double)));
+    CU_CHECK(c, cudaMemcpyAsync(t.nperhVals, nperhVals, 2*nperhN*sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    t.nperhN = (uint32_t)nperhN; t.nperhXmin = nperhXmin; t.nperhXmax = nperhXmax; t.nperhXstep = (nperhXmax - nperhXmin)/double(nperhN - 1);
+  }
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));     // inter is a local buffer
+  t.set = true;
+  // oneKernel = (W == WQ), SPH.cc:185 / TableKernelViewInline.hh:104-112
+  c->oneKernel = !c->WQ.set || (c->WQ.kext == c->W.kext && c->WQ.n1 == c->W.n1 && c->WQ.xstep == c->W.xstep &&
+                                c->WQ.hostW == c->W.hostW && c->WQ.hostG == c->W.hostG);
+  c->pairsValid = false;
+  return 0;
+}
+
+int sphb200_set_nodes(sphb200_ctx* c, size_t nInternal, size_t nGhost) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  const size_t n = nInternal + nGhost;
+  if (n >= 0x7fffffffull) return sphb200_fail(c, "set_nodes: more than 2^31-1 nodes per GPU is not supported");
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (alloc_nodes(c, n)) return 1;
+  if (n != c->n || nInternal != c->nInt) { c->sortValid = c->rowsValid = c->pairsValid = c->derivsValid = false; }
+  c->nInt = nInternal; c->nGhost = nGhost; c->n = n;
+  return 0;
+}
+
+static const double* state_ptr(const sphb200_host_state* s, int slot) {
+  switch (slot) {
+    case S_POS: return s->position; case S_VEL: return s->velocity; case S_H: return s->H; case S_MASS: return s->mass;
+    case S_RHO: return s->massDensity; case S_EPS: return s->specificThermalEnergy; case S_P: return s->pressure;
+    case S_CS: return s->soundSpeed; case S_OMEGA: return s->omegaGradh; case S_DVDXQ: return s->DvDxQ;
+    case S_FCL: return s->fCl; case S_FCQ: return s->fCq;
+  }
+  return nullptr;
+}
+
+int sphb200_upload_state(sphb200_ctx* c, unsigned mask, const sphb200_host_state* s) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  if (!s) return sphb200_fail(c, "upload_state: null state");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  for (int slot = 0; slot < S_COUNT; ++slot) {
+    if (!(mask & (1u << slot))) continue;
+    const double* src = state_ptr(s, slot);
+    if (!src) return sphb200_fail(c, "upload_state: field selected in mask but pointer is null");
+    const size_t bytes = c->n*(size_t)sphb200_state_width(c->ndim, slot)*sizeof(double);
+    if (bytes) CU_CHECK(c, cudaMemcpyAsync(c->api[slot], src, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->have[slot] = true;
+    if (slot == S_POS || slot == S_H) { c->sortValid = false; c->pairsValid = false; }
+    if (slot != S_EPS) c->rowsValid = false;
+  }
+  return 0;
+}
+
+int sphb200_download_state(sphb200_ctx* c, unsigned mask, double* const* fields) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  for (int slot = 0; slot < S_COUNT; ++slot) {
+    if (!(mask & (1u << slot))) continue;
+    if (!fields[slot]) return sphb200_fail(c, "download_state: null destination");
+    if (!c->have[slot]) return sphb200_fail(c, "download_state: field was never uploaded");
+    const size_t bytes = c->n*(size_t)sphb200_state_width(c->ndim, slot)*sizeof(double);
+    if (bytes) CU_CHECK(c, cudaMemcpyAsync(fields[slot], c->api[slot], bytes, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int sphb200_build_pairs(sphb200_ctx* c, size_t* npairs) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (c->n == 0) { c->npairs = c->nEdges = c->nSlots = 0; c->nTiles = 0; c->pairsValid = true; c->sortValid = true; c->rowsValid = true; if (npairs) *npairs = 0; return 0; }
+  cudaEventRecord(c->ev[0], c->stream);
+  if (sphb200_sort_and_pack(c)) return 1;
+  cudaEventRecord(c->ev[1], c->stream);
+  if (sphb200_neighbors(c)) return 1;
+  cudaEventRecord(c->ev[2], c->stream);
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->stats.ms_build_pairs, c->ev[0], c->ev[2]);
+  cudaEventElapsedTime(&c->stats.ms_neighbor_kernels, c->ev[1], c->ev[2]);
+  c->derivsValid = false;
+  if (npairs) *npairs = c->npairs;
+  return 0;
+}
+
+int sphb200_download_pairs(sphb200_ctx* c, uint32_t* i, uint32_t* j, size_t cap) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  if (!c->pairsValid) return sphb200_fail(c, "download_pairs: no valid pair list (call build_pairs after changing position/H)");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (c->npairs == 0) return 0;
+  return sphb200_pairs_to_host(c, i, j, cap, nullptr, 0);
+}
+
+int sphb200_download_pair_accelerations(sphb200_ctx* c, double* pacc, size_t cap) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  if (!c->pairsValid || !c->derivsValid) return sphb200_fail(c, "download_pair_accelerations: derivatives have not been evaluated for the current pair list");
+  if (!c->opt.compatibleEnergy) return sphb200_fail(c, "download_pair_accelerations: pair-wise accelerations exist only with compatibleEnergyEvolution (SPH.cc:129-133)");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (c->npairs == 0) return 0;
+  return sphb200_pairs_to_host(c, nullptr, nullptr, 0, pacc, cap);
+}
+
+int sphb200_download_neighbor_counts(sphb200_ctx* c, uint32_t* counts) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  if (!c->pairsValid) return sphb200_fail(c, "download_neighbor_counts: no valid pair list");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (c->nInt == 0) return 0;
+  if (ensure_stage(c, c->nInt*sizeof(uint32_t))) return 1;
+  k_counts_by_orig<<<(unsigned)((c->n + RB - 1)/RB), RB, 0, c->stream>>>(c->nbrCount, c->perm, c->n, (uint32_t)c->nInt, (uint32_t*)c->stage);
+  KERNEL_CHECK(c, "k_counts_by_orig");
+  CU_CHECK(c, cudaMemcpyAsync(counts, c->stage, c->nInt*sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int sphb200_evaluate_derivatives(sphb200_ctx* c, double /*time*/, double /*dt*/) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (!c->pairsValid) return sphb200_fail(c, "evaluateDerivatives: connectivity is stale or missing (requireConnectivity: call build_pairs first)");
+  if (c->n == 0) { c->derivsValid = true; return 0; }
+  for (int s : {S_POS, S_VEL, S_H, S_MASS, S_RHO, S_P, S_CS, S_OMEGA})
+    if (!c->have[s]) return sphb200_fail(c, "evaluateDerivatives: required state field missing on device (position, velocity, H, mass, mass density, pressure, sound speed, grad h corrections)");
+  if (!c->W.set) return sphb200_fail(c, "evaluateDerivatives: kernel table not set");
+  cudaEventRecord(c->ev[3], c->stream);
+  if (!c->rowsValid && sphb200_pack_rows(c)) return 1;
+  cudaEventRecord(c->ev[4], c->stream);
+  if (sphb200_launch_derivs(c)) return 1;
+  cudaEventRecord(c->ev[5], c->stream);
+  return 0;
+}
+
+static double* deriv_ptr(const sphb200_host_derivs* d, int slot) {
+  switch (slot) {
+    case DV_DXDT: return d->DxDt; case DV_DRHODT: return d->DrhoDt; case DV_DVDT: return d->DvDt; case DV_DEPSDT: return d->DepsDt;
+    case DV_DVDX: return d->DvDx; case DV_LOCALDVDX: return d->localDvDx; case DV_GRADRHO: return d->gradRho; case DV_M: return d->M;
+    case DV_LOCALM: return d->localM; case DV_RHOSUM: return d->rhoSum; case DV_NORM: return d->normalization;
+    case DV_MAXQ: return d->maxViscousPressure; case DV_EFFQ: return d->effViscousPressure; case DV_XSPHW: return d->XSPHWeightSum;
+    case DV_XSPHDV: return d->XSPHDeltaV; case DV_DHDT: return d->DHDt; case DV_HIDEAL: return d->Hideal;
+    case DV_M0: return d->massZerothMoment; case DV_M1: return d->massFirstMoment;
+  }
+  return nullptr;
+}
+
+int sphb200_download_derivs(sphb200_ctx* c, unsigned mask, const sphb200_host_derivs* d) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  if (!d) return sphb200_fail(c, "download_derivs: null destination struct");
+  if (!c->derivsValid) return sphb200_fail(c, "download_derivs: derivatives have not been evaluated");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (c->n == 0) return 0;
+  size_t total = 0;
+  for (int s = 0; s < DV_COUNT; ++s) if (mask & (1u << s)) total += c->n*(size_t)sphb200_deriv_width(c->ndim, s);
+  if (ensure_stage(c, total*sizeof(double))) return 1;
+  size_t off = 0;
+  const unsigned nb = (unsigned)((c->n + RB - 1)/RB);
+  for (int s = 0; s < DV_COUNT; ++s) {
+    if (!(mask & (1u << s))) continue;
+    double* dst = deriv_ptr(d, s);
+    if (!dst) return sphb200_fail(c, "download_derivs: field selected in mask but pointer is null");
+    const int w = sphb200_deriv_width(c->ndim, s);
+    k_unpermute<<<nb, RB, 0, c->stream>>>(c->deriv[s], c->cap, c->perm, c->n, w, c->stage + off);
+    KERNEL_CHECK(c, "k_unpermute");
+    CU_CHECK(c, cudaMemcpyAsync(dst, c->stage + off, c->n*(size_t)w*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    off += c->n*(size_t)w;
+  }
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int sphb200_copy_DvDx_to_Q(sphb200_ctx* c) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  if (!c->derivsValid) return sphb200_fail(c, "copy_DvDx_to_Q: derivatives have not been evaluated");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (c->n == 0) return 0;
+  k_copy_dvdx<<<(unsigned)((c->n + RB - 1)/RB), RB, 0, c->stream>>>(c->deriv[DV_DVDX], c->cap, c->perm, c->n, c->ndim*c->ndim, c->api[S_DVDXQ]);
+  KERNEL_CHECK(c, "k_copy_dvdx");
+  c->have[S_DVDXQ] = true;
+  c->rowsValid = false;
+  return 0;
+}
+
+int sphb200_update_energy_compatible(sphb200_ctx* c, double multiplier) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (!c->opt.compatibleEnergy) return sphb200_fail(c, "update_energy_compatible: compatibleEnergyEvolution is off");
+  if (!c->derivsValid || !c->pairsValid) return sphb200_fail(c, "update_energy_compatible: needs the derivatives and pair accelerations of the current pair list");
+  for (int s : {S_VEL, S_MASS, S_EPS}) if (!c->have[s]) return sphb200_fail(c, "update_energy_compatible: velocity, mass and specific thermal energy must be on the device");
+  if (c->n == 0) return 0;
+  cudaEventRecord(c->ev[6], c->stream);
+  if (sphb200_launch_energy(c, multiplier)) return 1;
+  cudaEventRecord(c->ev[7], c->stream);
+  return 0;
+}
+
+size_t sphb200_halo_bytes_per_node(const sphb200_ctx* c, unsigned mask) {
+  if (!c) return 0;
+  size_t w = 0;
+  for (int s = 0; s < S_COUNT; ++s) if (mask & (1u << s)) w += (size_t)sphb200_state_width(c->ndim, s);
+  return w*sizeof(double);
+}
+
+int sphb200_halo_pack(sphb200_ctx* c, unsigned mask, const uint32_t* nodes, size_t count, void* staging) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  double* out = (double*)staging;
+  for (int s = 0; s < S_COUNT; ++s) {
+    if (!(mask & (1u << s))) continue;
+    if (!c->have[s]) return sphb200_fail(c, "halo_pack: field not on device");
+    const int w = sphb200_state_width(c->ndim, s);
+    if (count) {
+      k_halo_pack<<<(unsigned)((count*w + RB - 1)/RB), RB, 0, c->stream>>>(c->api[s], w, nodes, count, out);
+      KERNEL_CHECK(c, "k_halo_pack");
+    }
+    out += count*(size_t)w;
+  }
+  return 0;
+}
+
+int sphb200_halo_unpack(sphb200_ctx* c, unsigned mask, size_t firstGhost, size_t count, const void* staging) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (firstGhost + count > c->n) return sphb200_fail(c, "halo_unpack: ghost range exceeds node count");
+  const double* in = (const double*)staging;
+  for (int s = 0; s < S_COUNT; ++s) {
+    if (!(mask & (1u << s))) continue;
+    const int w = sphb200_state_width(c->ndim, s);
+    // ghosts are a contiguous tail of the host-ordered arrays, so landing a field block is one D2D copy
+    if (count) CU_CHECK(c, cudaMemcpyAsync(c->api[s] + firstGhost*(size_t)w, in, count*(size_t)w*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    in += count*(size_t)w;
+    c->have[s] = true;
+    if (s == S_POS || s == S_H) { c->sortValid = false; c->pairsValid = false; }
+    if (s != S_EPS) c->rowsValid = false;
+  }
+  return 0;
+}
+
+int sphb200_get_stats(sphb200_ctx* c, sphb200_stats* out) {
+  if (!c || !out) return sphb200_fail(c, "get_stats: null argument");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (c->derivsValid && c->n) {
+    if (cudaEventElapsedTime(&c->stats.ms_evaluate, c->ev[3], c->ev[5]) != cudaSuccess) c->stats.ms_evaluate = 0;
+    if (cudaEventElapsedTime(&c->stats.ms_pair_kernel, c->ev[4], c->ev[5]) != cudaSuccess) c->stats.ms_pair_kernel = 0;
+  }
+  if (cudaEventElapsedTime(&c->stats.ms_energy, c->ev[6], c->ev[7]) != cudaSuccess) c->stats.ms_energy = 0;
+  cudaGetLastError();
+  *out = c->stats;
+  return 0;
+}
+
+int sphb200_measure_fp64_peak(sphb200_ctx* c, double* tflops) {
+  if (!c || !tflops) return sphb200_fail(c, "measure_fp64_peak: null argument");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  CU_CHECK(c, cudaGetDeviceProperties(&prop, c->device));
+  const int blocks = prop.multiProcessorCount*8, threads = 256, iters = 20000;
+  if (ensure_stage(c, (size_t)blocks*threads*sizeof(double))) return 1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, c->stream);
+    k_fp64_peak<<<blocks, threads, 0, c->stream>>>(c->stage, iters, 0.999999, 1.0e-7);
+    cudaEventRecord(e1, c->stream);
+    cudaStreamSynchronize(c->stream);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+    c->stats.launches++;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CU_CHECK(c, cudaGetLastError());
+  const double flops = 2.0*8.0*(double)iters*(double)blocks*(double)threads;
+  *tflops = flops/(best*1e-3)/1e12;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,511 @@
+// derivs.cu -- K3 (SPH pair loop), K4 (per-node finalize) and K5 (smoothing-scale derivatives), fused.
+//
+// Replaces SPH<Dim>::evaluateDerivativesImpl (SPH/SPH.cc:165-555) followed by
+// SPHSmoothingScale::evaluateDerivatives (SmoothingScale/SPHSmoothingScale.cc:101-275) or
+// ASPHSmoothingScale::evaluateDerivatives (SmoothingScale/ASPHSmoothingScale.cc:110-147).
+//
+// Formulation: i-centric gather.  The reference walks each pair (i<j) once and scatters into both nodes through
+// per-thread full-size scratch copies (SPH.cc:271-292, 473).  Here every internal node i walks its complete neighbour
+// list and accumulates only its own sums in registers, so there is no scatter, no atomic and the summation order of
+// a node is fixed by the list order (bitwise reproducible run to run).  Each pair is therefore evaluated twice; the
+// terms are the reference's (Appendix A of SURVEY.md) with i and j exchanged for the second visit.
+#include "sphb200_internal.cuh"
+#include <algorithm>
+#include <cmath>
+
+namespace {
+
+struct DerivArgs {
+  const double* rows; const uint32_t* perm;
+  const uint32_t* nbrCount; const uint32_t* tileRows; const unsigned long long* tileOff; const uint32_t* nbr;
+  const double *auxPneg, *auxSomr2, *auxDvDxQ, *auxfCl, *auxfCq;
+  const double* tabW; const double* tabQ;       // interleaved coefficient tables (6 per interval)
+  double kextW, xminW, xstepW; uint32_t n1W;
+  double kextQ, xminQ, xstepQ; uint32_t n1Q;
+  const double* nperhVals; uint32_t nperhN; double nperhXmin, nperhXmax, nperhXstep;
+  double W0, WnPerh;
+  size_t n, cap; uint32_t nInt;
+  sphb200_options o;
+  int oneKernel;
+  double* deriv[DV_COUNT];
+  double* pacc; size_t nSlots;
+};
+
+// TableKernelView::kernelAndGradValue (Kernel/TableKernelViewInline.hh:84-99) with
+// QuadraticInterpolatorView::lowerBound (Utilities/QuadraticInterpolatorViewInline.hh:71-77).  The interval index is
+// size_t(max(0,x-xmin)/xstep); a reciprocal multiply is used unless the quotient is within 1e-9 of an integer, where the
+// true division decides (an off-by-one interval would change W at the 1e-6 level).
+__device__ __forceinline__ void table_eval(const double* __restrict__ tab, double kext, double xmin, double xstep, double rxstep,
+                                           uint32_t n1, double eta, double Hdet, double& W, double& gW) {
+  if (eta < kext) {
+    const double x = fmax(0.0, eta - xmin);
+    double q = x*rxstep;
+    const double fl = floor(q);
+    if (q - fl < 1.0e-9 || fl + 1.0 - q < 1.0e-9) q = x/xstep;
+    uint32_t k = (uint32_t)q;
+    k = min(k, n1);
+    const double* c = tab + 6u*k;
+    W  = Hdet*(c[0] + (c[1] + c[2]*eta)*eta);
+    gW = Hdet*(c[3] + (c[4] + c[5]*eta)*eta);
+  } else {
+    W = 0.0; gW = 0.0;
+  }
+}
+
+template <int DIM> __device__ __forceinline__ double rootnu(double x) {
+  if (DIM == 3) return d_sgn(x)*pow(fabs(x), 0.3333333333333333);   // Dimension.hh:94, FastMath.hh:152-163
+  return sqrt(x);
+}
+template <int DIM> __device__ __forceinline__ double ten_det(const double* T) {
+  if (DIM == 3) return (T[0]*T[4]*T[8] + T[1]*T[5]*T[6] + T[2]*T[3]*T[7] - T[0]*T[5]*T[7] - T[1]*T[3]*T[8] - T[2]*T[4]*T[6]);
+  return T[0]*T[3] - T[1]*T[2];
+}
+template <int DIM> __device__ __forceinline__ void ten_inverse(const double* T, double* o) {
+  const double di = 1.0/ten_det<DIM>(T);
+  if (DIM == 3) {
+    const double xx = T[0], xy = T[1], xz = T[2], yx = T[3], yy = T[4], yz = T[5], zx = T[6], zy = T[7], zz = T[8];
+    o[0] = (yy*zz - yz*zy)*di; o[1] = (xz*zy - xy*zz)*di; o[2] = (xy*yz - xz*yy)*di;
+    o[3] = (yz*zx - yx*zz)*di; o[4] = (xx*zz - xz*zx)*di; o[5] = (xz*yx - xx*yz)*di;
+    o[6] = (yx*zy - yy*zx)*di; o[7] = (xy*zx - xx*zy)*di; o[8] = (xx*yy - xy*yx)*di;
+  } else {
+    const double xx = T[0], xy = T[1], yx = T[2], yy = T[3];
+    o[0] = yy*di; o[1] = -xy*di; o[2] = -yx*di; o[3] = xx*di;
+  }
+}
+template <int DIM> __device__ __forceinline__ void ten_mul(const double* A, const double* B, double* o) {
+  double t[DIM*DIM];
+#pragma unroll
+  for (int r = 0; r < DIM; ++r)
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) {
+      double s = A[r*DIM]*B[c];
+#pragma unroll
+      for (int k = 1; k < DIM; ++k) s += A[r*DIM + k]*B[k*DIM + c];
+      t[r*DIM + c] = s;
+    }
+#pragma unroll
+  for (int k = 0; k < DIM*DIM; ++k) o[k] = t[k];
+}
+template <int DIM> __device__ __forceinline__ double ten_trace(const double* T) { return DIM == 3 ? T[0] + T[4] + T[8] : T[0] + T[3]; }
+template <int DIM> __device__ __forceinline__ void ten_dot(const double* T, const double* v, double* o) {
+#pragma unroll
+  for (int r = 0; r < DIM; ++r) {
+    double s = T[r*DIM]*v[0];
+#pragma unroll
+    for (int k = 1; k < DIM; ++k) s += T[r*DIM + k]*v[k];
+    o[r] = s;
+  }
+}
+
+// ArtificialViscosityHandle::calcBalsaraShearCorrection (ArtificialViscosityHandleInline.hh:47-63)
+template <int DIM> __device__ __forceinline__ double balsara(const sphb200_options& o, const double* DvDx, double Hdet, double cs) {
+  const double div = fabs(ten_trace<DIM>(DvDx));
+  double curl;
+  if (DIM == 3) { const double a = DvDx[7] - DvDx[5], b = DvDx[2] - DvDx[6], c = DvDx[3] - DvDx[1]; curl = sqrt(a*a + b*b + c*c); }
+  else curl = fabs(DvDx[2] - DvDx[1]);
+  const double hmaxinverse = rootnu<DIM>(Hdet);
+  const double x = div + curl + o.eps2*fmax(o.negligibleSoundSpeed, cs)*hmaxinverse;
+  return div*(d_sgn(x)/fmax(1.0e-30, fabs(x)));
+}
+
+// smoothingScaleDerivative (SmoothingScale/SmoothingScaleUtilities.hh:46-85)
+template <int DIM> __device__ __forceinline__ void asph_DHDt(const double* H, const double* T, double* o) {
+  if (DIM == 3) {
+    const double Hxx = H[0], Hxy = H[1], Hxz = H[2], Hyy = H[3], Hyz = H[4], Hzz = H[5];
+    const double Txx = T[0], Txy = T[1], Txz = T[2], Tyx = T[3], Tyy = T[4], Tyz = T[5], Tzx = T[6], Tzy = T[7], Tzz = T[8];
+    const double AA = Hxx*Txy - Hxy*(Txx - Tyy) + Hxz*Tzy - Hyy*Tyx - Hyz*Tzx;
+    const double BB = Hxx*Txz + Hxy*Tyz - Hxz*(Txx - Tzz) - Hyz*Tyx - Hzz*Tzx;
+    const double CC = Hxy*Txz + Hyy*Tyz - Hyz*(Tyy - Tzz) - Hxz*Txy - Hzz*Tzy;
+    const double thpt = Hyy + Hzz;
+    const double Ga = (Hxx + Hyy)*thpt - Hxz*Hxz;
+    const double Gb = (Hyy + Hzz)*Hyz + Hxy*Hxz;
+    const double Gc = (Hxx + Hzz)*thpt - Hxy*Hxy;
+    const double Gd = thpt*AA + Hxz*CC;
+    const double Ge = thpt*BB - Hxy*CC;
+    const double ack = 1.0/(Ga*Gc - Gb*Gb);
+    const double Gdot = (Gc*Gd - Gb*Ge)*ack;
+    const double Tdot = (Gb*Gd - Ga*Ge)*ack;
+    const double Phidot = (Hxz*Gdot + Hxy*Tdot + CC)/thpt;
+    o[0] = -Hxx*Txx + Hxy*(Gdot - Tyx) - Hxz*(Tdot + Tzx);
+    o[1] = Hyy*Gdot - Hyz*Tdot - Hxx*Txy - Hxy*Tyy - Hxz*Tzy;
+    o[2] = Hyz*Gdot - Hzz*Tdot - Hxx*Txz - Hxy*Tyz - Hxz*Tzz;
+    o[3] = Hyz*(Phidot - Tzy) - Hxy*(Gdot + Txy) - Hyy*Tyy;
+    o[4] = Hxy*Tdot - Hyy*Phidot - Hxz*Txy - Hyz*Tyy - Hzz*Tzy;
+    o[5] = Hxz*(Tdot - Txz) - Hyz*(Phidot + Tyz) - Hzz*Tzz;
+  } else {
+    const double Hxx = H[0], Hyx = H[1], Hyy = H[2];
+    const double Txx = T[0], Txy = T[1], Tyx = T[2], Tyy = T[3];
+    const double thetaDot = (Hxx*Txy - Hyy*Tyx - Hyx*(Txx - Tyy))/(Hxx + Hyy);
+    o[0] = Hyx*(thetaDot - Tyx) - Hxx*Txx;
+    o[1] = -(Hxx*thetaDot + Hyx*Txx + Hyy*Tyx);
+    o[2] = -Hyx*(thetaDot + Txy) - Hyy*Tyy;
+  }
+}
+
+// CubicHermiteInterpolatorView::operator() (Utilities/CubicHermiteInterpolatorViewInline.hh:8-33,103-108)
+__device__ __forceinline__ double hermite_eval(const double* __restrict__ v, uint32_t n, double xmin, double xmax, double xstep, double x) {
+  if (x < xmin) return v[0] + v[n]*(x - xmin);
+  if (x > xmax) return v[n - 1u] + v[2u*n - 1u]*(x - xmin);
+  uint32_t i0 = (uint32_t)(fmax(0.0, x - xmin)/xstep);
+  i0 = min(i0, n - 2u);
+  const double t = fmax(0.0, fmin(1.0, (x - xmin - (double)i0*xstep)/xstep));
+  const double t2 = t*t, t3 = t*t2;
+  return ((2.0*t3 - 3.0*t2 + 1.0)*v[i0] + (-2.0*t3 + 3.0*t2)*v[i0 + 1u] +
+          xstep*((t3 - 2.0*t2 + t)*v[n + i0] + (t3 - t2)*v[n + i0 + 1u]));
+}
+
+// The pair-loop kernel: one warp per tile of 32 Morton-consecutive nodes, lane <-> node i.
+template <int DIM>
+__global__ void __launch_bounds__(128) k_sph_derivs(DerivArgs a) {
+  using D = Dm<DIM>;
+  constexpr int NS = D::NS, NT = D::NT, ROW = D::ROW;
+  extern __shared__ double smem[];
+  // stage the interleaved W/gradW table(s) in shared memory
+  const uint32_t nW = 6u*(a.n1W + 1u), nQ = a.oneKernel ? 0u : 6u*(a.n1Q + 1u);
+  for (uint32_t k = threadIdx.x; k < nW; k += blockDim.x) smem[k] = a.tabW[k];
+  for (uint32_t k = threadIdx.x; k < nQ; k += blockDim.x) smem[nW + k] = a.tabQ[k];
+  __syncthreads();
+  const double* tW = smem;
+  const double* tQ = smem + nW;
+  const double rxW = 1.0/a.xstepW, rxQ = a.oneKernel ? 0.0 : 1.0/a.xstepQ;
+
+  const int lane = threadIdx.x & 31;
+  const size_t tile = (size_t)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tile*SPHB200_TILE >= a.n) return;
+  const size_t i = tile*SPHB200_TILE + lane;
+  const bool inRange = i < a.n;
+  const bool active = inRange && a.perm[i] < a.nInt;
+  const sphb200_options& o = a.o;
+  const double tiny = 1.0e-30;
+
+  // ---- node i state
+  double ri[DIM], vi[DIM], Hi[NS];
+  double mi = 0, rhoi = 1, Prhoi0 = 0, ci = 0;
+  if (inRange) {
+    const double* r = a.rows + i*ROW;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) { ri[k] = r[D::R_POS + k]; vi[k] = r[D::R_VEL + k]; }
+#pragma unroll
+    for (int k = 0; k < NS; ++k) Hi[k] = r[D::R_H + k];
+    mi = r[D::R_M]; rhoi = r[D::R_RHO]; Prhoi0 = r[D::R_PRHO]; ci = r[D::R_CS];
+  } else {
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) { ri[k] = 0; vi[k] = 0; }
+#pragma unroll
+    for (int k = 0; k < NS; ++k) Hi[k] = 0;
+  }
+  const double Hdeti = sym_det<DIM>(Hi);
+  const bool tens = (o.epsTensile != 0.0);
+  const bool needQ = (o.Qkind == SPHB200_Q_LIMITED_MG) || o.balsara;
+  const bool mult = (a.auxfCl != nullptr);
+  const double Pnegi = (tens && inRange) ? a.auxPneg[i] : 0.0;
+  const double somr2i = (tens && inRange) ? a.auxSomr2[i] : 0.0;
+  double DvDxQi[NT];
+#pragma unroll
+  for (int k = 0; k < NT; ++k) DvDxQi[k] = (needQ && inRange) ? a.auxDvDxQ[i*NT + k] : 0.0;
+  const double fCli = (mult && inRange) ? a.auxfCl[i] : 1.0, fCqi = (mult && inRange) ? a.auxfCq[i] : 1.0;
+  const double balsi = (o.balsara && inRange) ? balsara<DIM>(o, DvDxQi, Hdeti, ci) : 1.0;
+  const double mi_over_rhoi = mi/rhoi;
+
+  // ---- accumulators
+  double rhoSum = 0, norm = 0, DepsDt = 0, maxQ = 0, effQ = 0, XW = 0, m0 = 0;
+  double DvDt[DIM], gradRho[DIM], XdV[DIM], m1[DIM], DvDx[NT], M[NT];
+#pragma unroll
+  for (int k = 0; k < DIM; ++k) { DvDt[k] = 0; gradRho[k] = 0; XdV[k] = 0; m1[k] = 0; }
+#pragma unroll
+  for (int k = 0; k < NT; ++k) { DvDx[k] = 0; M[k] = 0; }
+
+  const uint32_t cnt = active ? a.nbrCount[i] : 0u;
+  const uint32_t rows = a.tileRows[tile];
+  const unsigned long long base = a.tileOff[tile];
+
+  for (uint32_t k = 0; k < rows; ++k) {
+    if (k >= cnt) continue;
+    const unsigned long long slot = base + (unsigned long long)k*SPHB200_TILE + lane;
+    const uint32_t e = a.nbr[slot];
+    const uint32_t j = e & 0x7fffffffu;
+    // ---- node j state: one 128-byte row
+    double rw[ROW];
+    {
+      const double2* rp = reinterpret_cast<const double2*>(a.rows + (size_t)j*ROW);
+#pragma unroll
+      for (int q = 0; q < ROW/2; ++q) { const double2 t = __ldg(rp + q); rw[2*q] = t.x; rw[2*q + 1] = t.y; }
+    }
+    const double* rj = rw + D::R_POS; const double* vj = rw + D::R_VEL; const double* Hj = rw + D::R_H;
+    const double mj = rw[D::R_M], rhoj = rw[D::R_RHO], cj = rw[D::R_CS];
+    const double Hdetj = sym_det<DIM>(Hj);
+
+    // SPH.cc:363-369
+    double rij[DIM], etai[DIM], etaj[DIM];
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) rij[q] = ri[q] - rj[q];
+    sym_dot<DIM>(Hi, rij, etai);
+    sym_dot<DIM>(Hj, rij, etaj);
+    const double etaMagi = sqrt(vdot<DIM>(etai, etai));
+    const double etaMagj = sqrt(vdot<DIM>(etaj, etaj));
+    const double invi = d_sgn(etaMagi)/fmax(1.0e-30, fabs(etaMagi));     // safeInvVar
+    const double invj = d_sgn(etaMagj)/fmax(1.0e-30, fabs(etaMagj));
+    double etaiU[DIM], etajU[DIM];
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) { etaiU[q] = etai[q]*invi; etajU[q] = etaj[q]*invj; }
+
+    // SPH.cc:374-388
+    double Wi, gWi, Wj, gWj;
+    table_eval(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, etaMagi, Hdeti, Wi, gWi);
+    table_eval(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, etaMagj, Hdetj, Wj, gWj);
+    double gradWi[DIM], gradWj[DIM], gradWQi[DIM], gradWQj[DIM], WQi, WQj;
+    { double t[DIM];
+      sym_dot<DIM>(Hi, etaiU, t);
+#pragma unroll
+      for (int q = 0; q < DIM; ++q) gradWi[q] = gWi*t[q];
+      sym_dot<DIM>(Hj, etajU, t);
+#pragma unroll
+      for (int q = 0; q < DIM; ++q) gradWj[q] = gWj*t[q];
+      if (a.oneKernel) {
+        WQi = Wi; WQj = Wj;
+#pragma unroll
+        for (int q = 0; q < DIM; ++q) { gradWQi[q] = gradWi[q]; gradWQj[q] = gradWj[q]; }
+      } else {
+        double gWQi, gWQj;
+        table_eval(tQ, a.kextQ, a.xminQ, a.xstepQ, rxQ, a.n1Q, etaMagi, Hdeti, WQi, gWQi);
+        table_eval(tQ, a.kextQ, a.xminQ, a.xstepQ, rxQ, a.n1Q, etaMagj, Hdetj, WQj, gWQj);
+        sym_dot<DIM>(Hi, etaiU, t);
+#pragma unroll
+        for (int q = 0; q < DIM; ++q) gradWQi[q] = gWQi*t[q];
+        sym_dot<DIM>(Hj, etajU, t);
+#pragma unroll
+        for (int q = 0; q < DIM; ++q) gradWQj[q] = gWQj*t[q];
+      }
+    }
+
+    // SPH.cc:391-396 (i side)
+    rhoSum += mj*Wi;
+    norm += mi_over_rhoi*Wi;
+
+    // ---- artificial viscosity: MonaghanGingoldViscosity.cc:69-100 / LimitedMonaghanGingoldViscosity.cc:140-218
+    double vij[DIM];
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) vij[q] = vi[q] - vj[q];
+    double fshear = 1.0, fClj = 1.0, fCqj = 1.0;
+    double vijQ[DIM];
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) vijQ[q] = vij[q];
+    if (mult) { fClj = a.auxfCl[j]; fCqj = a.auxfCq[j]; }
+    if (needQ) {
+      double DvDxQj[NT];
+#pragma unroll
+      for (int q = 0; q < NT; ++q) DvDxQj[q] = a.auxDvDxQ[(size_t)j*NT + q];
+      if (o.balsara) fshear = 0.5*(balsi + balsara<DIM>(o, DvDxQj, Hdetj, cj));
+      if (o.Qkind == SPHB200_Q_LIMITED_MG) {
+        const double etaCrit = o.etaCritFrac/o.nPerh, etaFold = o.etaFoldFrac/o.nPerh;
+        double xij[DIM], t1[DIM], t2[DIM];
+#pragma unroll
+        for (int q = 0; q < DIM; ++q) xij[q] = 0.5*rij[q];
+        ten_dot<DIM>(DvDxQi, xij, t1); const double gradi = vdot<DIM>(t1, xij);
+        ten_dot<DIM>(DvDxQj, xij, t2); const double gradj = vdot<DIM>(t2, xij);
+        const double rri = gradi/(d_sgn(gradj)*fmax(1.0e-30, fabs(gradj)));
+        const double rrj = gradj/(d_sgn(gradi)*fmax(1.0e-30, fabs(gradi)));
+        const double x = fmin(rri, rrj);
+        double phi = (x > 0.0 ? 2.0/(1.0 + x)*2.0*x/(1.0 + x) : 0.0);       // van Leer
+        const double etaij = fmin(etaMagi, etaMagj);
+        if (etaij < etaCrit) { const double z = (etaij - etaCrit)/etaFold; phi *= exp(-z*z); }
+#pragma unroll
+        for (int q = 0; q < DIM; ++q) vijQ[q] = (vi[q] - phi*t1[q]) - (vj[q] + phi*t2[q]);
+      }
+    }
+    const double Clij = 0.5*(fCli + fClj)*fshear*o.Cl;
+    const double Cqij = 0.5*(fCqi + fCqj)*fshear*o.Cq;
+    const double mui = vdot<DIM>(vijQ, etai)/(vdot<DIM>(etai, etai) + o.eps2);
+    const double muj = vdot<DIM>(vijQ, etaj)/(vdot<DIM>(etaj, etaj) + o.eps2);
+    const double mui0 = fmin(0.0, mui), muj0 = fmin(0.0, muj);
+    const double ei = -Clij*ci*(o.linearInExpansion ? mui : mui0) + Cqij*(o.quadraticInExpansion ? -d_sgn(mui)*mui*mui : mui0*mui0);
+    const double ej = -Clij*cj*(o.linearInExpansion ? muj : muj0) + Cqij*(o.quadraticInExpansion ? -d_sgn(muj)*muj*muj : muj0*muj0);
+    const double QPiij = ei/rhoi, QPiji = ej/rhoj;
+    const double Qi = rhoi*ei;
+
+    // SPH.cc:405-414
+    double Qacci[DIM], Qaccj[DIM];
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) { Qacci[q] = 0.5*(QPiij*gradWQi[q]); Qaccj[q] = 0.5*(QPiji*gradWQj[q]); }
+    const double workQi = vdot<DIM>(vij, Qacci);
+    maxQ = fmax(maxQ, Qi);
+    effQ += mj*Qi*WQi/rhoj;
+
+    // SPH.cc:417-426
+    double Prhoi = Prhoi0, Prhoj = rw[D::R_PRHO];
+    if (tens) {
+      const double t = Wi/(Hdeti*a.WnPerh), u = Wj/(Hdetj*a.WnPerh);
+      const double Ri = o.epsTensile*(t*t*t*t)*Pnegi;
+      const double Rj = o.epsTensile*(u*u*u*u)*a.auxPneg[j];
+      Prhoi += somr2i*Ri;
+      Prhoj += a.auxSomr2[j]*Rj;
+    }
+    double delta[DIM];
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) delta[q] = Prhoi*gradWi[q] + Prhoj*gradWj[q] + Qacci[q] + Qaccj[q];
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) DvDt[q] -= mj*delta[q];
+    if (o.compatibleEnergy) {
+#pragma unroll
+      for (int q = 0; q < DIM; ++q) a.pacc[(size_t)q*a.nSlots + slot] = delta[q];
+    }
+
+    // SPH.cc:434
+    DepsDt += mj*(Prhoi*vdot<DIM>(vij, gradWi) + workQi);
+
+    // SPH.cc:438-445, 463-468
+#pragma unroll
+    for (int r = 0; r < DIM; ++r)
+#pragma unroll
+      for (int c2 = 0; c2 < DIM; ++c2) {
+        DvDx[r*DIM + c2] -= mj*(vij[r]*gradWi[c2]);
+        M[r*DIM + c2] -= mj*(rij[r]*gradWi[c2]);
+      }
+
+    // SPH.cc:448-454
+    if (o.XSPH) {
+      const double w = 0.5*(mi_over_rhoi*Wi + mj/rhoj*Wj);
+      XW += w;
+#pragma unroll
+      for (int q = 0; q < DIM; ++q) XdV[q] -= w*vij[q];
+    }
+
+    // SPH.cc:457-460
+    { const double f = mj*(rhoj - rhoi);
+#pragma unroll
+      for (int q = 0; q < DIM; ++q) gradRho[q] += f*gradWi[q]; }
+
+    // SPHSmoothingScale.cc:186-222 (i side; same NodeList, Cartesian => fweightij = 1)
+    if (o.hEvolution == SPHB200_H_SPH) {
+      double dW, gg;
+      table_eval(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, etaMagi, 1.0, dW, gg);
+      const double WSPHi = fabs(gg);
+      m0 += WSPHi;
+#pragma unroll
+      for (int q = 0; q < DIM; ++q) m1[q] -= WSPHi*etai[q];
+    }
+  }
+
+  if (!inRange) return;
+  // ---- K4: per-node finalize (SPH.cc:480-552); ghost nodes get zeros
+  const size_t cap = a.cap;
+  auto put = [&](int slot, int comp, double v) { a.deriv[slot][(size_t)comp*cap + i] = v; };
+  if (!active) {
+    for (int s = 0; s < DV_COUNT; ++s) { const int w = sphb200_deriv_width(DIM, s); for (int q = 0; q < w; ++q) put(s, q, 0.0); }
+    return;
+  }
+  rhoSum += mi*a.W0*Hdeti;
+  norm += mi_over_rhoi*a.W0*Hdeti;
+  double Minv[NT], DvDxF[NT];
+  const uint32_t pownu2 = (DIM == 3) ? 8u : 4u;
+  if (o.correctVelocityGradient && fabs(ten_det<DIM>(M)) > 1.0e-10 && cnt > pownu2) {
+    ten_inverse<DIM>(M, Minv);
+    ten_mul<DIM>(DvDx, Minv, DvDxF);
+  } else {
+    const double rinv = 1.0/rhoi;
+#pragma unroll
+    for (int q = 0; q < NT; ++q) { Minv[q] = M[q]; DvDxF[q] = DvDx[q]*rinv; }
+  }
+  { const double rinv = 1.0/rhoi;
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) put(DV_GRADRHO, q, gradRho[q]*rinv); }
+  put(DV_DRHODT, 0, -rhoi*ten_trace<DIM>(DvDxF));
+  if (o.evolveTotalEnergy) DepsDt = mi*(vdot<DIM>(vi, DvDt) + DepsDt);
+  put(DV_DEPSDT, 0, DepsDt);
+  if (o.XSPH) {
+    XW += Hdeti*mi/rhoi*a.W0;
+    const double deninv = 1.0/fmax(tiny, XW);
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) put(DV_DXDT, q, vi[q] + XdV[q]*deninv);
+  } else {
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) put(DV_DXDT, q, vi[q]);
+  }
+  put(DV_RHOSUM, 0, rhoSum); put(DV_NORM, 0, norm); put(DV_MAXQ, 0, maxQ); put(DV_EFFQ, 0, effQ); put(DV_XSPHW, 0, XW);
+#pragma unroll
+  for (int q = 0; q < DIM; ++q) { put(DV_DVDT, q, DvDt[q]); put(DV_XSPHDV, q, XdV[q]); }
+#pragma unroll
+  for (int q = 0; q < NT; ++q) { put(DV_DVDX, q, DvDxF[q]); put(DV_LOCALDVDX, q, DvDxF[q]); put(DV_M, q, Minv[q]); put(DV_LOCALM, q, Minv[q]); }
+
+  // ---- K5: smoothing scale
+  if (o.hEvolution == SPHB200_H_SPH) {
+    const double z0 = rootnu<DIM>(fmax(0.0, m0));
+    put(DV_M0, 0, z0);
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) put(DV_M1, q, m1[q]);
+    const double tr = ten_trace<DIM>(DvDxF);
+    const double dinv = 1.0/(double)DIM;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) put(DV_DHDT, q, ((-Hi[q])*dinv)*tr);
+    const bool isolated = fabs(z0 - 0.0) <= 1.0e-15*fmax(1.0, fabs(z0));                 // fuzzyEqual(z0, 0)
+    const double cur = isolated ? 0.5*o.nPerh : fmax(0.0, hermite_eval(a.nperhVals, a.nperhN, a.nperhXmin, a.nperhXmax, a.nperhXstep, z0));
+    const double sv = fmin(4.0, fmax(0.25, o.nPerh/(cur + 1.0e-30)));
+    const double aa = (sv < 1.0 ? 0.4*(1.0 + sv*sv) : 0.4*(1.0 + 1.0/(sv*sv*sv)));
+    const double hi0 = 1.0/Hi[0];
+    const double hi1 = fmin(o.hmax, fmax(o.hmin, hi0*(1.0 - aa + aa*sv)));
+    const double hinv = 1.0/hi1;
+    if (DIM == 3) { put(DV_HIDEAL, 0, hinv); put(DV_HIDEAL, 1, 0.0); put(DV_HIDEAL, 2, 0.0); put(DV_HIDEAL, 3, hinv); put(DV_HIDEAL, 4, 0.0); put(DV_HIDEAL, 5, hinv); }
+    else { put(DV_HIDEAL, 0, hinv); put(DV_HIDEAL, 1, 0.0); put(DV_HIDEAL, 2, hinv); }
+  } else {
+    put(DV_M0, 0, 0.0);
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) put(DV_M1, q, 0.0);
+    double dh[NS];
+    if (o.hEvolution == SPHB200_H_ASPH) asph_DHDt<DIM>(Hi, DvDxF, dh);
+    else {
+#pragma unroll
+      for (int q = 0; q < NS; ++q) dh[q] = 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < NS; ++q) { put(DV_DHDT, q, dh[q]); put(DV_HIDEAL, q, 0.0); }
+  }
+}
+
+}  // namespace
+
+static double host_table_eval(const TableDev& t, double eta, bool grad) {
+  if (!(eta < t.kext)) return 0.0;
+  double q = std::max(0.0, eta - t.xmin)/t.xstep;
+  size_t k = std::min<size_t>((size_t)q, t.n1);
+  const std::vector<double>& c = grad ? t.hostG : t.hostW;
+  return c[3*k] + (c[3*k + 1] + c[3*k + 2]*eta)*eta;
+}
+
+int sphb200_launch_derivs(sphb200_ctx* c) {
+  DerivArgs a{};
+  a.rows = c->rows; a.perm = c->perm; a.nbrCount = c->nbrCount; a.tileRows = c->tileRows; a.tileOff = c->tileOff; a.nbr = c->nbr;
+  const bool tens = c->opt.epsTensile != 0.0;
+  const bool needQ = (c->opt.Qkind == SPHB200_Q_LIMITED_MG) || c->opt.balsara;
+  const bool mult = c->have[S_FCL] && c->have[S_FCQ];
+  a.auxPneg = tens ? c->auxPneg : nullptr; a.auxSomr2 = tens ? c->auxSomr2 : nullptr;
+  a.auxDvDxQ = needQ ? c->auxDvDxQ : nullptr; a.auxfCl = mult ? c->auxfCl : nullptr; a.auxfCq = mult ? c->auxfCq : nullptr;
+  a.tabW = c->W.coef; a.kextW = c->W.kext; a.xminW = c->W.xmin; a.xstepW = c->W.xstep; a.n1W = c->W.n1;
+  a.oneKernel = c->oneKernel ? 1 : 0;
+  const TableDev& Q = c->oneKernel ? c->W : c->WQ;
+  a.tabQ = Q.coef; a.kextQ = Q.kext; a.xminQ = Q.xmin; a.xstepQ = Q.xstep; a.n1Q = Q.n1;
+  a.nperhVals = c->W.nperhVals; a.nperhN = c->W.nperhN; a.nperhXmin = c->W.nperhXmin; a.nperhXmax = c->W.nperhXmax; a.nperhXstep = c->W.nperhXstep;
+  if (c->opt.hEvolution == SPHB200_H_SPH && (!a.nperhVals || a.nperhN < 2))
+    return sphb200_fail(c, "evaluateDerivatives: SPHSmoothingScale needs the TableKernel nperh lookup (nperhVals) but none was set");
+  a.W0 = host_table_eval(c->W, 0.0, false);                       // SPH.cc:189
+  a.WnPerh = host_table_eval(c->W, 1.0/c->opt.nPerh, false);      // SPH.cc:264-266
+  a.n = c->n; a.cap = c->cap; a.nInt = (uint32_t)c->nInt; a.o = c->opt;
+  for (int s = 0; s < DV_COUNT; ++s) a.deriv[s] = c->deriv[s];
+  if (c->opt.compatibleEnergy) {
+    if (sphb200_ensure(c, c->pacc, c->paccCap, c->nSlots*(size_t)c->ndim)) return 1;
+  }
+  a.pacc = c->pacc; a.nSlots = c->nSlots;
+  const int wpb = 4;
+  const unsigned nb = (unsigned)((c->nTiles + wpb - 1)/wpb);
+  const size_t shm = (size_t)6*(c->W.n1 + 1)*sizeof(double) + (c->oneKernel ? 0 : (size_t)6*(c->WQ.n1 + 1)*sizeof(double));
+  if (shm > 200*1024) return sphb200_fail(c, "kernel table too large for shared memory");
+  if (c->ndim == 3) {
+    CU_CHECK(c, cudaFuncSetAttribute(k_sph_derivs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    k_sph_derivs<3><<<nb, wpb*32, shm, c->stream>>>(a);
+  } else {
+    CU_CHECK(c, cudaFuncSetAttribute(k_sph_derivs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    k_sph_derivs<2><<<nb, wpb*32, shm, c->stream>>>(a);
+  }
+  KERNEL_CHECK(c, "k_sph_derivs");
+  c->derivsValid = true;
+  return 0;
+}

@@ -1,0 +1,194 @@
+// sphb200_internal.cuh -- context layout and device helpers shared by the kernels of libsphb200.
+//
+// Data layout in HBM (DESIGN.md "Data layout"):
+//   api_*      : fields exactly as the host hands them (reference AoS, original node order) -- the landing
+//                zone of uploads / halo receives and the source of downloads.
+//   rows       : nodes re-ordered by Morton cell key, one 128-byte (3-D) / 96-byte (2-D) record per node
+//                   3-D: x y z vx vy vz Hxx Hxy Hxz Hyy Hyz Hzz m rho Prho cs
+//                   2-D: x y vx vy Hxx Hxy Hyy m rho Prho cs (pad)
+//                Prho = safeInv(omega)*P/(rho*rho) (SPH.cc:310,425 with epsTensile == 0) is folded per node.
+//   nbr        : neighbour lists of internal nodes, sliced-ELL: tile t = sorted slots [32t,32t+32),
+//                entry k of lane l at nbr[tileOff[t] + 32*k + l]; bit31 = "original index of j > original index of i".
+//   d_*        : derivative fields, SoA per component, sorted order.
+//   pacc[a]    : deltaDvDt of every directed edge (same indexing as nbr), component-major.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "sphb200.h"
+
+#define SPHB200_TILE 32
+
+enum StateSlot { S_POS = 0, S_VEL, S_H, S_MASS, S_RHO, S_EPS, S_P, S_CS, S_OMEGA, S_DVDXQ, S_FCL, S_FCQ, S_COUNT };
+enum DerivSlot { DV_DXDT = 0, DV_DRHODT, DV_DVDT, DV_DEPSDT, DV_DVDX, DV_LOCALDVDX, DV_GRADRHO, DV_M, DV_LOCALM,
+                 DV_RHOSUM, DV_NORM, DV_MAXQ, DV_EFFQ, DV_XSPHW, DV_XSPHDV, DV_DHDT, DV_HIDEAL, DV_M0, DV_M1, DV_COUNT };
+
+// width (doubles per node) of each field
+__host__ __device__ inline int sphb200_state_width(int ndim, int slot) {
+  switch (slot) {
+    case S_POS: case S_VEL: return ndim;
+    case S_H: return ndim == 3 ? 6 : 3;
+    case S_DVDXQ: return ndim*ndim;
+    default: return 1;
+  }
+}
+__host__ __device__ inline int sphb200_deriv_width(int ndim, int slot) {
+  switch (slot) {
+    case DV_DXDT: case DV_DVDT: case DV_GRADRHO: case DV_XSPHDV: case DV_M1: return ndim;
+    case DV_DVDX: case DV_LOCALDVDX: case DV_M: case DV_LOCALM: return ndim*ndim;
+    case DV_DHDT: case DV_HIDEAL: return ndim == 3 ? 6 : 3;
+    default: return 1;
+  }
+}
+
+struct TableDev {
+  double kext = 0, xmin = 0, xstep = 0;
+  uint32_t n1 = 0;
+  double* coef = nullptr;          // interleaved per interval: W a0 a1 a2, gradW g0 g1 g2  (6*(n1+1) doubles)
+  bool set = false;
+  // CubicHermite nperh lookup (Wsum -> nperh)
+  uint32_t nperhN = 0; double nperhXmin = 0, nperhXmax = 0, nperhXstep = 0; double* nperhVals = nullptr;
+  std::vector<double> hostW, hostG;   // host copies (W0, WnPerh evaluation, equality test)
+};
+
+struct GridDev {                    // uniform cell grid, Morton keyed
+  double lo[3], cs[3], invcs_unused[3];
+  int nc[3];
+  int bits[3];
+  uint32_t mask[3];                 // dilated bit masks per axis
+  uint8_t bitpos[3][16];            // output bit position of bit l of axis a
+  uint32_t tableSize;               // 2^(sum bits)
+};
+
+struct sphb200_ctx {
+  int device = 0;
+  int ndim = 3;
+  sphb200_options opt{};
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  size_t nInt = 0, nGhost = 0, n = 0, cap = 0;
+  double* api[S_COUNT] = {nullptr};
+  bool have[S_COUNT] = {false};
+
+  TableDev W, WQ;
+  bool oneKernel = true;
+
+  // grid + sort
+  GridDev grid{};
+  uint32_t* cellKeyApi = nullptr;   // key per node, original order
+  uint32_t* cellStart = nullptr;    // tableSize+1
+  uint32_t* cellCursor = nullptr;
+  size_t cellCap = 0;
+  uint32_t* perm = nullptr;         // sorted slot -> original index
+  uint32_t* skey = nullptr;         // sorted slot -> cell key
+  double* reduceBuf = nullptr;      // bbox partials
+  double* reduceHost = nullptr;     // pinned
+
+  // sorted rows + aux
+  double* rows = nullptr;
+  double* auxPneg = nullptr;        // max(-P,0)                      (tensile, SPH.cc:417)
+  double* auxSomr2 = nullptr;       // safeInv(omega)/(rho*rho)        (tensile)
+  double* auxDvDxQ = nullptr;       // ndim*ndim per node (sorted)     (LimitedMG / Balsara)
+  double* auxfCl = nullptr; double* auxfCq = nullptr;
+  bool rowsValid = false;           // rows reflect current api state for the current sort
+  bool sortValid = false;
+
+  // neighbour lists
+  size_t nTiles = 0;
+  uint32_t* nbrCount = nullptr;     // per sorted slot
+  uint32_t* tileRows = nullptr;     // per tile: max count
+  unsigned long long* tileOff = nullptr;  // nTiles+1, in entries
+  uint32_t* nbr = nullptr; size_t nbrCap = 0;
+  unsigned long long* counters = nullptr; // [0]=npairs [1]=directed edges
+  unsigned long long* countersHost = nullptr; // pinned
+  size_t npairs = 0, nEdges = 0, nSlots = 0;
+  bool pairsValid = false;
+  void* scanTmp = nullptr; size_t scanTmpBytes = 0;
+
+  // derivatives (sorted, SoA per component): deriv[slot] points at width*cap doubles, component c at + c*cap
+  double* deriv[DV_COUNT] = {nullptr};
+  double* pacc = nullptr; size_t paccCap = 0;   // ndim * nSlots
+  bool derivsValid = false;
+  double* stage = nullptr; size_t stageBytes = 0;   // download staging (device)
+
+  // instrumentation
+  sphb200_stats stats{};
+  cudaEvent_t ev[8] = {nullptr};
+};
+
+int  sphb200_fail(sphb200_ctx* c, const std::string& msg);
+#define CU_CHECK(c, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
+  return sphb200_fail((c), std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
+#define KERNEL_CHECK(c, name) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) \
+  return sphb200_fail((c), std::string("launch ") + name + ": " + cudaGetErrorString(e__)); (c)->stats.launches++; } while (0)
+
+template <typename T> int sphb200_ensure(sphb200_ctx* c, T*& p, size_t& cap, size_t need);
+
+// implemented in scan.cu: exclusive scans with the total written at out[n]
+int sphb200_scan_u32(sphb200_ctx* c, const uint32_t* in, uint32_t* out, size_t n);
+int sphb200_scan_tiles(sphb200_ctx* c, const uint32_t* rows, unsigned long long* out, size_t n);   // out = 32*rows prefix
+
+// implemented in neighbors.cu / derivs.cu / energy.cu
+int sphb200_sort_and_pack(sphb200_ctx* c);
+int sphb200_pack_rows(sphb200_ctx* c);
+int sphb200_neighbors(sphb200_ctx* c);
+int sphb200_launch_derivs(sphb200_ctx* c);
+int sphb200_launch_energy(sphb200_ctx* c, double multiplier);
+int sphb200_pairs_to_host(sphb200_ctx* c, uint32_t* pi, uint32_t* pj, size_t cap, double* pacc, size_t paccCap);
+
+// ---- device helpers ---------------------------------------------------------------------------------------
+template <int DIM> struct Dm;
+template <> struct Dm<3> { static constexpr int NS = 6, NT = 9, ROW = 16, R_POS = 0, R_VEL = 3, R_H = 6, R_M = 12, R_RHO = 13, R_PRHO = 14, R_CS = 15; };
+template <> struct Dm<2> { static constexpr int NS = 3, NT = 4, ROW = 12, R_POS = 0, R_VEL = 2, R_H = 4, R_M = 7, R_RHO = 8, R_PRHO = 9, R_CS = 10; };
+
+__device__ __forceinline__ double d_sgn(double x) { return x < 0.0 ? -1.0 : 1.0; }
+
+// Exactly-rounded, never-contracted H.r and |.|^2 for the pair predicate (ConnectivityMap.cc:912-925;
+// GeomSymmetricTensorInline.hh:1762-1777, GeomVectorInline.hh:1045-1055): the reference is built for generic
+// x86-64, i.e. without FMA, so every product and sum is rounded separately, left to right.
+template <int DIM> __device__ __forceinline__ double eta2_exact(const double* H, const double* r) {
+  if (DIM == 3) {
+    const double ex = __dadd_rn(__dadd_rn(__dmul_rn(H[0], r[0]), __dmul_rn(H[1], r[1])), __dmul_rn(H[2], r[2]));
+    const double ey = __dadd_rn(__dadd_rn(__dmul_rn(H[1], r[0]), __dmul_rn(H[3], r[1])), __dmul_rn(H[4], r[2]));
+    const double ez = __dadd_rn(__dadd_rn(__dmul_rn(H[2], r[0]), __dmul_rn(H[4], r[1])), __dmul_rn(H[5], r[2]));
+    return __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+  } else {
+    const double ex = __dadd_rn(__dmul_rn(H[0], r[0]), __dmul_rn(H[1], r[1]));
+    const double ey = __dadd_rn(__dmul_rn(H[1], r[0]), __dmul_rn(H[2], r[1]));
+    return __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
+  }
+}
+
+template <int DIM> __device__ __forceinline__ double sym_det(const double* H) {
+  if (DIM == 3) return (H[0]*H[3]*H[5] + H[1]*H[4]*H[2] + H[2]*H[1]*H[4] - H[0]*H[4]*H[4] - H[1]*H[1]*H[5] - H[2]*H[3]*H[2]);
+  return H[0]*H[2] - H[1]*H[1];
+}
+template <int DIM> __device__ __forceinline__ void sym_dot(const double* H, const double* r, double* o) {
+  if (DIM == 3) {
+    o[0] = H[0]*r[0] + H[1]*r[1] + H[2]*r[2];
+    o[1] = H[1]*r[0] + H[3]*r[1] + H[4]*r[2];
+    o[2] = H[2]*r[0] + H[4]*r[1] + H[5]*r[2];
+  } else {
+    o[0] = H[0]*r[0] + H[1]*r[1];
+    o[1] = H[1]*r[0] + H[2]*r[1];
+  }
+}
+template <int DIM> __device__ __forceinline__ double vdot(const double* a, const double* b) {
+  double s = a[0]*b[0];
+#pragma unroll
+  for (int k = 1; k < DIM; ++k) s += a[k]*b[k];
+  return s;
+}
+
+// cell coordinate of a position on the grid (shared by every kernel that needs it, so it is bit-identical)
+__device__ __forceinline__ int cell_coord(double x, double lo, double cs, int nc) {
+  int k = (int)floor((x - lo)/cs);
+  return k < 0 ? 0 : (k >= nc ? nc - 1 : k);
+}
+__device__ __forceinline__ uint32_t dilate(const GridDev& g, int axis, int c) {
+  uint32_t key = 0;
+  for (int l = 0; l < g.bits[axis]; ++l) key |= ((uint32_t)(c >> l) & 1u) << g.bitpos[axis][l];
+  return key;
+}

@@ -1,0 +1,205 @@
+"""Engine -- thin Python handle over the C ABI (one per GPU / rank).
+
+This is the device boundary of SURVEY.md 8b: everything below it is CUDA, everything above it is the host-side
+mirror of Spheral's Physics package interface (spheral_b200/physics.py).  Errors of the C ABI become
+RuntimeError (the reference raises VERIFYError -> Python exception, Utilities/DBC.hh:28-45).
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib as L
+
+
+class SPHB200Error(RuntimeError):
+    pass
+
+
+def make_options(ndim, **kw):
+    o = L.Options()
+    o.ndim = ndim
+    o.compatibleEnergy, o.evolveTotalEnergy, o.XSPH, o.correctVelocityGradient = 1, 0, 1, 1
+    o.epsTensile, o.nTensile, o.nPerh = 0.0, 4.0, 2.01
+    o.Qkind, o.Cl, o.Cq, o.eps2, o.negligibleSoundSpeed = L.Q_MG, 1.0, 1.0, 1.0e-2, 1.0e-10
+    o.balsara = o.linearInExpansion = o.quadraticInExpansion = 0
+    o.etaCritFrac, o.etaFoldFrac = 1.0, 0.2
+    o.hEvolution, o.hmin, o.hmax = L.H_SPH, 1.0e-20, 1.0e20
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise KeyError(k)
+        setattr(o, k, v)
+    return o
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Engine:
+    def __init__(self, ndim, device=0, options=None, **kw):
+        self._lib = L.lib()
+        self.ndim = ndim
+        self.options = options if options is not None else make_options(ndim, **kw)
+        self._h = C.c_void_p()
+        if self._lib.sphb200_create(C.byref(self._h), device, C.byref(self.options)) != 0:
+            raise SPHB200Error(self._lib.sphb200_last_error(None).decode())
+        self.nInternal = self.nGhost = 0
+        self.npairs = 0
+
+    # -- plumbing ------------------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise SPHB200Error(self._lib.sphb200_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.sphb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n(self):
+        return self.nInternal + self.nGhost
+
+    def set_options(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.options, k):
+                raise KeyError(k)
+            setattr(self.options, k, v)
+        self._check(self._lib.sphb200_set_options(self._h, C.byref(self.options)))
+
+    def sync(self):
+        self._check(self._lib.sphb200_sync(self._h))
+
+    @property
+    def stream(self):
+        return self._lib.sphb200_stream(self._h)
+
+    # -- kernel tables ---------------------------------------------------------------------------------------
+    def set_kernel_table(self, table, which=L.TABLE_W):
+        """table: spheral_b200.kernel.TableKernel (or anything with the same attributes)."""
+        nperh = getattr(table, "nperhVals", None)
+        wsum = getattr(table, "wsumVals", None)
+        keep = [np.ascontiguousarray(table.Wcoef), np.ascontiguousarray(table.gradWcoef),
+                np.ascontiguousarray(table.grad2Wcoef)]
+        nN = len(nperh)//2 if nperh is not None else 0
+        wN = len(wsum)//2 if wsum is not None else 0
+        self._check(self._lib.sphb200_set_kernel_table(
+            self._h, which, table.kernelExtent, table.xmin, table.xstep, table.n1,
+            _dp(keep[0]), _dp(keep[1]), _dp(keep[2]),
+            nN, table.nperhRange[0] if nN else 0.0, table.nperhRange[1] if nN else 0.0,
+            _dp(np.ascontiguousarray(nperh)) if nN else None,
+            wN, table.wsumRange[0] if wN else 0.0, table.wsumRange[1] if wN else 0.0,
+            _dp(np.ascontiguousarray(wsum)) if wN else None))
+
+    # -- nodes and state ---------------------------------------------------------------------------------------
+    def set_nodes(self, nInternal, nGhost=0):
+        self._check(self._lib.sphb200_set_nodes(self._h, nInternal, nGhost))
+        self.nInternal, self.nGhost = nInternal, nGhost
+
+    def upload_state(self, **fields):
+        """fields: name -> array in the reference AoS layout; names from _lib.STATE_FIELDS."""
+        hs = L.HostState()
+        mask = 0
+        keep = []
+        for k, v in fields.items():
+            if v is None:
+                continue
+            if k not in L.STATE_BITS:
+                raise KeyError(k)
+            a = np.ascontiguousarray(v, dtype=np.float64)
+            if a.size != self.n*L.state_width(self.ndim, k):
+                raise ValueError("field %s has %d values, expected %d" % (k, a.size, self.n*L.state_width(self.ndim, k)))
+            keep.append(a)
+            setattr(hs, k, _dp(a))
+            mask |= L.STATE_BITS[k]
+        self._check(self._lib.sphb200_upload_state(self._h, mask, C.byref(hs)))
+        self.sync()          # the numpy temporaries must outlive the async copies
+
+    def upload_state_pinned(self, mask, hs):
+        """Asynchronous variant used by bench.py: hs is a prepared HostState over pinned buffers."""
+        self._check(self._lib.sphb200_upload_state(self._h, mask, C.byref(hs)))
+
+    def download_state(self, *names):
+        arr = (C.POINTER(C.c_double)*len(L.STATE_FIELDS))()
+        out = {}
+        mask = 0
+        for k in names:
+            w = L.state_width(self.ndim, k)
+            out[k] = np.zeros((self.n, w) if w > 1 else self.n)
+            arr[L.STATE_FIELDS.index(k)] = _dp(out[k])
+            mask |= L.STATE_BITS[k]
+        self._check(self._lib.sphb200_download_state(self._h, mask, arr))
+        return out
+
+    # -- connectivity ----------------------------------------------------------------------------------------------
+    def build_pairs(self):
+        np_ = C.c_size_t()
+        self._check(self._lib.sphb200_build_pairs(self._h, C.byref(np_)))
+        self.npairs = np_.value
+        return self.npairs
+
+    def download_pairs(self):
+        pi = np.zeros(max(self.npairs, 1), dtype=np.uint32)
+        pj = np.zeros(max(self.npairs, 1), dtype=np.uint32)
+        self._check(self._lib.sphb200_download_pairs(self._h, pi.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                     pj.ctypes.data_as(C.POINTER(C.c_uint32)), self.npairs))
+        return pi[:self.npairs], pj[:self.npairs]
+
+    def download_neighbor_counts(self):
+        c = np.zeros(max(self.nInternal, 1), dtype=np.uint32)
+        self._check(self._lib.sphb200_download_neighbor_counts(self._h, c.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return c[:self.nInternal]
+
+    # -- derivatives ---------------------------------------------------------------------------------------------------
+    def evaluate_derivatives(self, time=0.0, dt=1.0):
+        self._check(self._lib.sphb200_evaluate_derivatives(self._h, time, dt))
+
+    def download_derivs(self, *names):
+        names = names or L.DERIV_FIELDS
+        hd = L.HostDerivs()
+        out = {}
+        mask = 0
+        for k in names:
+            w = L.deriv_width(self.ndim, k)
+            out[k] = np.zeros((self.n, w) if w > 1 else self.n)
+            setattr(hd, k, _dp(out[k]))
+            mask |= L.DERIV_BITS[k]
+        self._check(self._lib.sphb200_download_derivs(self._h, mask, C.byref(hd)))
+        return out
+
+    def download_pair_accelerations(self):
+        out = np.zeros((max(self.npairs, 1), self.ndim))
+        self._check(self._lib.sphb200_download_pair_accelerations(self._h, _dp(out), out.size))
+        return out[:self.npairs]
+
+    def copy_DvDx_to_Q(self):
+        self._check(self._lib.sphb200_copy_DvDx_to_Q(self._h))
+
+    def update_energy_compatible(self, multiplier):
+        self._check(self._lib.sphb200_update_energy_compatible(self._h, multiplier))
+
+    # -- halo ----------------------------------------------------------------------------------------------------------
+    def halo_bytes_per_node(self, mask):
+        return self._lib.sphb200_halo_bytes_per_node(self._h, mask)
+
+    def halo_pack(self, mask, send_nodes_ptr, count, staging_ptr):
+        self._check(self._lib.sphb200_halo_pack(self._h, mask, send_nodes_ptr, count, staging_ptr))
+
+    def halo_unpack(self, mask, first_ghost, count, staging_ptr):
+        self._check(self._lib.sphb200_halo_unpack(self._h, mask, first_ghost, count, staging_ptr))
+
+    # -- instrumentation -----------------------------------------------------------------------------------------------
+    def stats(self):
+        s = L.Stats()
+        self._check(self._lib.sphb200_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in L.Stats._fields_}
+
+    def measure_fp64_peak(self):
+        t = C.c_double()
+        self._check(self._lib.sphb200_measure_fp64_peak(self._h, C.byref(t)))
+        return t.value

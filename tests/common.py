@@ -1,0 +1,100 @@
+"""Shared problem builders and comparison helpers for the parity tests (tests only; may use the oracle)."""
+import math
+import numpy as np
+
+from spheral_b200 import nodegen as ng
+
+STATE_KEYS = ("position", "velocity", "H", "mass", "massDensity", "specificThermalEnergy", "pressure", "soundSpeed",
+              "omegaGradh", "DvDxQ", "fCl", "fCq")
+# product name -> oracle name
+ORC_STATE = dict(position="pos", velocity="vel", H="H", mass="mass", massDensity="rho", pressure="P", soundSpeed="cs",
+                 omegaGradh="omega", DvDxQ="DvDxQ", fCl="fCl", fCq="fCq")
+
+
+def smooth_velocity(pos, amp=1.0, seed=7):
+    rng = np.random.default_rng(seed)
+    nd = pos.shape[1]
+    k = rng.uniform(1.0, 4.0, size=(nd, nd))
+    ph = rng.uniform(0, 2*math.pi, size=nd)
+    v = np.stack([amp*np.sin((pos*k[a]).sum(axis=1) + ph[a]) for a in range(nd)], axis=1)
+    return v + 0.05*amp*rng.standard_normal(v.shape)
+
+
+def make_problem(ndim=3, n=10, nPerh=1.51, kind="lattice", seed=11, negP=False, gamma=5.0/3.0, ghosts=False, kext=2.0):
+    """Returns (state dict with product names, nInternal, nGhost)."""
+    rng = np.random.default_rng(seed)
+    if kind == "lattice":
+        pos, mass, H, d = ng.lattice(ndim, n, nPerh=nPerh)
+        pos = ng.jitter(pos, 0.2, d, seed=seed)
+    elif kind == "aniso":
+        N = n**ndim
+        pos, H = ng.random_anisotropic(ndim, N, [[0, 1]]*ndim, nPerh=nPerh, seed=seed)
+        mass = np.full(N, 1.0/N)
+    else:
+        raise ValueError(kind)
+    N = pos.shape[0]
+    rho = 1.0 + 0.3*np.sin(3.0*pos[:, 0])*np.cos(2.0*pos[:, 1]) + 0.02*rng.standard_normal(N)
+    mass = mass*rho if kind == "lattice" else mass*(1.0 + 0.1*rng.standard_normal(N))
+    eps = 1.0 + 0.5*np.cos(2.5*pos[:, 1]) + 0.05*rng.standard_normal(N)
+    vel = smooth_velocity(pos, seed=seed + 1)
+    P, cs = ng.gamma_law(rho, eps, gamma)
+    if negP:
+        P = P - 1.2*np.abs(P).mean()*(rng.uniform(size=N) < 0.3)
+    omega = 1.0 + 0.1*rng.standard_normal(N)
+    st = dict(position=pos, velocity=vel, H=H, mass=mass, massDensity=rho, specificThermalEnergy=eps, pressure=P,
+              soundSpeed=cs, omegaGradh=omega)
+    nInt, nGhost = N, 0
+    if ghosts:
+        planes = [(np.zeros(ndim), np.eye(ndim)[a]) for a in range(ndim)]
+        f = dict(pos=pos, H=H, vel=vel, mass=mass, rho=rho, eps=eps, P=P, cs=cs, omega=omega)
+        out, ctl, n0 = ng.reflect_ghosts(ndim, f, planes, kext)
+        st = dict(position=out["pos"], velocity=out["vel"], H=out["H"], mass=out["mass"], massDensity=out["rho"],
+                  specificThermalEnergy=out["eps"], pressure=out["P"], soundSpeed=out["cs"], omegaGradh=out["omega"])
+        nInt, nGhost = n0, out["pos"].shape[0] - n0
+    return {k: np.ascontiguousarray(v) for k, v in st.items()}, nInt, nGhost
+
+
+def add_q_fields(st, ndim, seed=3):
+    rng = np.random.default_rng(seed)
+    N = st["position"].shape[0]
+    st = dict(st)
+    st["DvDxQ"] = np.ascontiguousarray(0.8*rng.standard_normal((N, ndim*ndim)))
+    st["fCl"] = 1.0 + 0.2*rng.uniform(size=N)
+    st["fCq"] = 1.0 + 0.3*rng.uniform(size=N)
+    return st
+
+
+def to_oracle_state(st):
+    return {ORC_STATE[k]: v for k, v in st.items() if k in ORC_STATE}
+
+
+def oracle_table(orc, tk):
+    """Wrap the PRODUCT's table so that GPU and oracle evaluate one and the same table (SURVEY 7 hard part 2)."""
+    return orc.TableKernel.from_arrays(tk.ndim, tk.kernelExtent, tk.xmin, tk.xstep, tk.n1, tk.Wcoef, tk.gradWcoef,
+                                       tk.grad2Wcoef, nperh=(tk.nperhVals, tk.nperhRange[0], tk.nperhRange[1]),
+                                       wsum=(tk.wsumVals, tk.wsumRange[0], tk.wsumRange[1]))
+
+
+def opts_pair(orc, eng_mod, ndim, **kw):
+    """Identical option sets for the oracle and the product."""
+    return orc.default_options(ndim, **kw), eng_mod.make_options(ndim, **kw)
+
+
+def field_err(a, b, nInt, floor):
+    """SURVEY 8c metric: max-norm error over internal nodes, scaled by max(|ref|_inf, floor)."""
+    a = np.asarray(a)[:nInt]
+    b = np.asarray(b)[:nInt]
+    scale = max(float(np.abs(b).max()) if b.size else 0.0, floor)
+    return float(np.abs(a - b).max())/scale if b.size else 0.0
+
+
+def physical_floors(st, nInt, ndim):
+    """Per-field physical scales used as floors so that symmetric (near-zero) fields do not produce 0/0."""
+    h = 1.0/st["H"][:nInt, 0].mean()
+    cs = max(float(st["soundSpeed"][:nInt].max()), 1e-30)
+    v = max(float(np.abs(st["velocity"][:nInt]).max()), cs)
+    rho = float(st["massDensity"][:nInt].mean())
+    P = max(float(np.abs(st["pressure"][:nInt]).max()), 1e-30)
+    return dict(DxDt=v, DrhoDt=rho*v/h, DvDt=cs*cs/h, DepsDt=cs*cs*v/h, DvDx=v/h, localDvDx=v/h, gradRho=rho/h, M=1.0,
+                localM=1.0, rhoSum=rho, normalization=1.0, maxViscousPressure=P, effViscousPressure=P, XSPHWeightSum=1.0,
+                XSPHDeltaV=v, DHDt=v/(h*h), Hideal=1.0/h, massZerothMoment=1.0, massFirstMoment=1.0)
