@@ -352,15 +352,14 @@ int sphb200_sort_and_pack(sphb200_ctx* c) {
   KERNEL_CHECK(c, "k_bbox_final");
   CU_CHECK(c, cudaMemcpyAsync(c->reduceHost, c->reduceBuf + 296*9, 9*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU_CHECK(c, cudaStreamSynchronize(c->stream));
-  for (int k = 0; k < 3*c->ndim; ++k) if (!std::isfinite(c->reduceHost[k < c->ndim ? k : (k < 2*c->ndim ? 3 + k - c->ndim : 6 + k - 2*c->ndim)]))
-    return sphb200_fail(c, "build_pairs: non-finite position or H");
+  for (int a = 0; a < c->ndim; ++a)
+    if (!std::isfinite(c->reduceHost[a]) || !std::isfinite(c->reduceHost[3 + a]) || !std::isfinite(c->reduceHost[6 + a]))
+      return sphb200_fail(c, "build_pairs: non-finite position or H");
   if (build_grid(c, c->reduceHost)) return 1;
 
   const size_t tbl = (size_t)c->grid.tableSize + 1;
   if (sphb200_ensure(c, c->cellStart, c->cellCap, tbl)) return 1;
-  { size_t cap2 = c->cellCursor ? c->cellCap : 0;
-    if (c->cellCursor && cap2 < tbl) { cudaFree(c->cellCursor); c->cellCursor = nullptr; }
-    if (!c->cellCursor) CU_CHECK(c, cudaMalloc((void**)&c->cellCursor, c->cellCap*sizeof(uint32_t))); }
+  if (sphb200_ensure(c, c->cellCursor, c->cellCursorCap, tbl)) return 1;
   CU_CHECK(c, cudaMemsetAsync(c->cellStart, 0, tbl*sizeof(uint32_t), c->stream));
   const unsigned nb = (unsigned)((n + RB - 1)/RB);
   if (c->ndim == 3) k_cell_count<3><<<nb, RB, 0, c->stream>>>(c->api[S_POS], n, c->grid, c->cellKeyApi, c->cellStart);

@@ -80,7 +80,7 @@ struct sphb200_ctx {
   uint32_t* cellKeyApi = nullptr;   // key per node, original order
   uint32_t* cellStart = nullptr;    // tableSize+1
   uint32_t* cellCursor = nullptr;
-  size_t cellCap = 0;
+  size_t cellCap = 0, cellCursorCap = 0;
   uint32_t* perm = nullptr;         // sorted slot -> original index
   uint32_t* skey = nullptr;         // sorted slot -> cell key
   double* reduceBuf = nullptr;      // bbox partials

@@ -1,0 +1,230 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): neighbour pair sets bit-exact after sorting; per-node derivatives of one
+evaluateDerivatives call within 1e-10 relative (FP64, re-associated sums), measured with the field-wise max-norm
+metric of SURVEY.md 8c over internal nodes.
+"""
+import numpy as np
+import pytest
+
+import common
+from spheral_b200 import kernel as K, nodegen as ng
+
+pytestmark = pytest.mark.gpu
+TOL = 1.0e-10
+
+
+@pytest.fixture(scope="module")
+def eng_mod(sphlib):
+    from spheral_b200 import engine
+    return engine
+
+
+def run_both(oracle, eng_mod, ndim, st, nInt, nGhost, WT, WQ=None, **kw):
+    oo, po = common.opts_pair(oracle, eng_mod, ndim, **kw)
+    OT = common.oracle_table(oracle, WT)
+    OQ = common.oracle_table(oracle, WQ) if WQ is not None else None
+    s = common.to_oracle_state(st)
+    kext = max(WT.kernelExtent, WQ.kernelExtent if WQ is not None else 0.0)
+    pi, pj, cnt = oracle.pairs(ndim, nInt, nGhost, s["pos"], s["H"], kext)
+    ref = oracle.evaluate_derivatives(oo, OT, s, nInt, nGhost, pi, pj, cnt, WQ=OQ)
+    e = eng_mod.Engine(ndim, options=po)
+    e.set_kernel_table(WT)
+    if WQ is not None:
+        e.set_kernel_table(WQ, which=1)
+    e.set_nodes(nInt, nGhost)
+    e.upload_state(**st)
+    npairs = e.build_pairs()
+    gi, gj = e.download_pairs()
+    gc = e.download_neighbor_counts()
+    e.evaluate_derivatives(0.0, 1.0)
+    got = e.download_derivs()
+    if po.compatibleEnergy:
+        got["pairAccelerations"] = e.download_pair_accelerations()
+    return dict(ref=ref, got=got, pairs=(pi, pj, cnt), gpairs=(gi, gj, gc), npairs=npairs, engine=e)
+
+
+def assert_parity(r, st, nInt, ndim, skip=()):
+    pi, pj, cnt = r["pairs"]
+    gi, gj, gc = r["gpairs"]
+    assert r["npairs"] == len(pi)
+    assert np.array_equal(gi, pi) and np.array_equal(gj, pj), "pair set differs"
+    assert np.array_equal(gc, cnt), "numNeighborsForNode differs"
+    floors = common.physical_floors(st, nInt, ndim)
+    worst = {}
+    for k, f in floors.items():
+        if k in skip:
+            continue
+        worst[k] = common.field_err(r["got"][k], r["ref"][k], nInt, f)
+    bad = {k: v for k, v in worst.items() if not v <= TOL}
+    assert not bad, "fields out of tolerance: %s (all: %s)" % (bad, worst)
+    if "pairAccelerations" in r["got"]:
+        a, b = r["got"]["pairAccelerations"], r["ref"]["pairAccelerations"]
+        assert a.shape == b.shape
+        assert np.abs(a - b).max() <= TOL*max(np.abs(b).max(), floors["DvDt"]*1e-3)
+    # ghosts carry zeros
+    n = r["got"]["DvDt"].shape[0]
+    if n > nInt:
+        assert np.all(r["got"]["DvDt"][nInt:] == 0.0)
+    return worst
+
+
+@pytest.mark.parametrize("ndim,n,nPerh", [(3, 14, 1.51), (2, 40, 2.01)])
+def test_sph_lattice_default_flags(oracle, eng_mod, ndim, n, nPerh):
+    st, nInt, nGhost = common.make_problem(ndim, n, nPerh=nPerh)
+    WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    r = run_both(oracle, eng_mod, ndim, st, nInt, nGhost, WT, nPerh=nPerh, Cl=2.0, Cq=2.0)
+    assert_parity(r, st, nInt, ndim)
+
+
+@pytest.mark.parametrize("ndim,n", [(3, 11), (2, 36)])
+def test_asph_random_rotated_anisotropic_H(oracle, eng_mod, ndim, n):
+    st, nInt, nGhost = common.make_problem(ndim, n, nPerh=2.01 if ndim == 2 else 1.3, kind="aniso", seed=21)
+    WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    r = run_both(oracle, eng_mod, ndim, st, nInt, nGhost, WT, nPerh=2.01, hEvolution=1)
+    assert_parity(r, st, nInt, ndim)
+
+
+@pytest.mark.parametrize("flags", [
+    dict(XSPH=0), dict(compatibleEnergy=0), dict(compatibleEnergy=0, evolveTotalEnergy=1),
+    dict(correctVelocityGradient=0), dict(hEvolution=2), dict(linearInExpansion=1, quadraticInExpansion=1),
+])
+def test_flag_variants_3d(oracle, eng_mod, flags):
+    st, nInt, nGhost = common.make_problem(3, 10, nPerh=1.51, seed=5)
+    WT = K.TableKernel(K.BSplineKernel(3), 1000)
+    r = run_both(oracle, eng_mod, 3, st, nInt, nGhost, WT, nPerh=1.51, **flags)
+    assert_parity(r, st, nInt, 3)
+
+
+def test_tensile_correction_with_negative_pressure(oracle, eng_mod):
+    st, nInt, nGhost = common.make_problem(3, 10, nPerh=1.51, negP=True, seed=9)
+    assert (st["pressure"] < 0).any()
+    WT = K.TableKernel(K.BSplineKernel(3), 1000)
+    r = run_both(oracle, eng_mod, 3, st, nInt, nGhost, WT, nPerh=1.51, epsTensile=0.3)
+    assert_parity(r, st, nInt, 3)
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+@pytest.mark.parametrize("qflags", [dict(Qkind=1), dict(Qkind=1, balsara=1), dict(Qkind=0, balsara=1)])
+def test_limited_mg_and_balsara(oracle, eng_mod, ndim, qflags):
+    st, nInt, nGhost = common.make_problem(ndim, 10 if ndim == 3 else 30, nPerh=1.51 if ndim == 3 else 2.01, seed=13)
+    st = common.add_q_fields(st, ndim)
+    WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    r = run_both(oracle, eng_mod, ndim, st, nInt, nGhost, WT, nPerh=1.51, Cl=2.0, Cq=2.0, **qflags)
+    assert_parity(r, st, nInt, ndim)
+
+
+def test_separate_pi_kernel(oracle, eng_mod):
+    st, nInt, nGhost = common.make_problem(3, 10, nPerh=1.51, seed=17)
+    WT = K.TableKernel(K.BSplineKernel(3), 1000)
+    WQ = K.TableKernel(K.WendlandC4Kernel(3), 1000)
+    # make the supports comparable: WendlandC4 has kext 1, so only the closest neighbours feel Q
+    r = run_both(oracle, eng_mod, 3, st, nInt, nGhost, WT, WQ=WQ, nPerh=1.51)
+    assert_parity(r, st, nInt, 3)
+
+
+def test_config_C1_noh_cylindrical_2d_with_reflecting_ghosts(oracle, eng_mod):
+    """BASELINE.json configs[0]: Noh-cylindrical-2d SPH (scaled to nRadial=40 for test time), WendlandC4 nPerh=4.01,
+    two reflecting planes, v = -rhat, eps = 0."""
+    nPerh = 4.01
+    pos, mass, H = ng.constant_dtheta_2d(40, nPerh=nPerh)
+    N = len(pos)
+    r_ = np.linalg.norm(pos, axis=1)
+    vel = -pos/r_[:, None]
+    rho = np.ones(N); eps = np.zeros(N)
+    P, cs = ng.gamma_law(rho, eps)
+    f = dict(pos=pos, H=H, vel=vel, mass=mass, rho=rho, eps=eps, P=P, cs=cs, omega=np.ones(N))
+    out, ctl, n0 = ng.reflect_ghosts(2, f, [((0, 0), (1, 0)), ((0, 0), (0, 1))], 1.0)
+    st = dict(position=out["pos"], velocity=out["vel"], H=out["H"], mass=out["mass"], massDensity=out["rho"],
+              specificThermalEnergy=out["eps"], pressure=out["P"], soundSpeed=out["cs"], omegaGradh=out["omega"])
+    st = {k: np.ascontiguousarray(v) for k, v in st.items()}
+    nInt, nGhost = n0, len(out["pos"]) - n0
+    assert nGhost > 100
+    WT = K.TableKernel(K.WendlandC4Kernel(2), 1000)
+    r = run_both(oracle, eng_mod, 2, st, nInt, nGhost, WT, nPerh=nPerh, Cl=1.0, Cq=1.0)
+    # cs = 0 and P = 0: scale DvDt by v^2/h instead
+    assert_parity(r, dict(st, soundSpeed=np.ones_like(st["soundSpeed"]), pressure=np.ones_like(st["pressure"])), nInt, 2)
+
+
+def test_compatible_energy_update_matches_oracle_and_conserves(oracle, eng_mod):
+    st, nInt, nGhost = common.make_problem(3, 12, nPerh=1.51, seed=23)
+    WT = K.TableKernel(K.BSplineKernel(3), 1000)
+    r = run_both(oracle, eng_mod, 3, st, nInt, nGhost, WT, nPerh=1.51, compatibleEnergy=1)
+    pi, pj, _ = r["pairs"]
+    ref = r["ref"]
+    dt = 2.0e-3
+    eps_ref = oracle.update_energy_compatible(3, nInt, 0, st["mass"], st["velocity"], ref["DvDt"], ref["DepsDt"], pi, pj,
+                                              ref["pairAccelerations"], dt, st["specificThermalEnergy"])
+    e = r["engine"]
+    e.update_energy_compatible(dt)
+    eps_gpu = e.download_state("specificThermalEnergy")["specificThermalEnergy"]
+    d = np.abs(eps_gpu - eps_ref).max()
+    assert d <= 1e-12*np.abs(eps_ref).max()
+    m, v0 = st["mass"], st["velocity"]
+    v1 = v0 + dt*r["got"]["DvDt"]
+    E0 = (m*(0.5*(v0**2).sum(axis=1) + st["specificThermalEnergy"])).sum()
+    E1 = (m*(0.5*(v1**2).sum(axis=1) + eps_gpu)).sum()
+    assert abs(E1 - E0)/abs(E0) < 1e-13          # Noh-cylindrical-2d.py:803-808
+
+
+def test_edge_cases(oracle, eng_mod):
+    WT = K.TableKernel(K.BSplineKernel(3), 1000)
+    e = eng_mod.Engine(3, nPerh=1.51)
+    e.set_kernel_table(WT)
+    # stale connectivity is an error, like requireConnectivity
+    e.set_nodes(0, 0)
+    assert e.build_pairs() == 0
+    e.evaluate_derivatives()
+    # a single isolated node, and two far-apart nodes: no pairs, finite outputs
+    for pos in (np.array([[0.5, 0.5, 0.5]]), np.array([[0.1, 0.1, 0.1], [0.9, 0.9, 0.9]])):
+        n = len(pos)
+        H = ng.sym_from_diag(3, np.full((n, 3), 50.0))
+        st = dict(position=pos, velocity=np.zeros((n, 3)), H=H, mass=np.ones(n), massDensity=np.ones(n),
+                  specificThermalEnergy=np.ones(n), pressure=np.ones(n), soundSpeed=np.ones(n), omegaGradh=np.ones(n))
+        e.set_nodes(n, 0)
+        e.upload_state(**st)
+        assert e.build_pairs() == 0
+        e.evaluate_derivatives()
+        d = e.download_derivs()
+        assert np.all(np.isfinite(d["DvDt"])) and np.all(d["DvDt"] == 0.0)
+        s = common.to_oracle_state(st)
+        pi, pj, cnt = oracle.pairs(3, n, 0, s["pos"], s["H"], 2.0)
+        ref = oracle.evaluate_derivatives(oracle.default_options(3, nPerh=1.51), common.oracle_table(oracle, WT), s, n, 0, pi, pj, cnt)
+        for k in ("rhoSum", "normalization", "DrhoDt", "Hideal", "DHDt", "DxDt"):
+            assert np.allclose(d[k], ref[k], rtol=1e-12, atol=1e-300), k
+    # missing field / stale pairs raise
+    e2 = eng_mod.Engine(3, nPerh=1.51)
+    e2.set_kernel_table(WT)
+    e2.set_nodes(2, 0)
+    with pytest.raises(eng_mod.SPHB200Error, match="position and H"):
+        e2.build_pairs()
+    e2.upload_state(position=np.zeros((2, 3)), H=ng.sym_from_diag(3, np.ones((2, 3))))
+    e2.build_pairs()
+    with pytest.raises(eng_mod.SPHB200Error, match="required state field"):
+        e2.evaluate_derivatives()
+
+
+def test_neighbour_pairs_bit_exact_on_ragged_inputs(oracle, eng_mod):
+    """Pair sets only (cheap), over shapes the grid must cope with: ghosts, strongly varying h, a node count that is
+    not a multiple of the tile, coincident nodes."""
+    WT = K.TableKernel(K.BSplineKernel(3), 1000)
+    cases = []
+    st, nInt, nGhost = common.make_problem(3, 9, nPerh=1.51, ghosts=True, seed=31)
+    cases.append((3, st["position"], st["H"], nInt, nGhost))
+    pos, H = ng.random_anisotropic(3, 1500, [[0, 1]]*3, nPerh=1.2, seed=33)
+    H[:200] *= 0.35                       # a population of much larger ellipsoids
+    cases.append((3, pos, H, 1500, 0))
+    pos2, H2 = ng.random_anisotropic(2, 1111, [[0, 2], [0, 0.5]], nPerh=2.01, seed=35)
+    pos2[17] = pos2[16]                   # coincident nodes
+    cases.append((2, pos2, H2, 1111, 0))
+    for ndim, pos, H, nInt, nGhost in cases:
+        e = eng_mod.Engine(ndim, nPerh=1.51)
+        e.set_kernel_table(K.TableKernel(K.BSplineKernel(ndim), 100))
+        e.set_nodes(nInt, nGhost)
+        e.upload_state(position=pos, H=H)
+        npairs = e.build_pairs()
+        gi, gj = e.download_pairs()
+        gc = e.download_neighbor_counts()
+        pi, pj, cnt = oracle.pairs(ndim, nInt, nGhost, pos, H, 2.0, "brute")
+        assert npairs == len(pi)
+        assert np.array_equal(gi, pi) and np.array_equal(gj, pj) and np.array_equal(gc, cnt)
