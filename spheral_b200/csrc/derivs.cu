@@ -31,25 +31,49 @@ struct DerivArgs {
   double* pacc; size_t nSlots;
 };
 
+// Fast FP64 reciprocal / reciprocal square root for the pair loop: the hardware seed (MUFU.RCP64H / MUFU.RSQ64H) refined to
+// full double precision (relative error ~1e-16), without the IEEE corner-case slow path of `/` and sqrt() -- arguments in
+// the pair loop are finite, positive and far from the denormal range.  The 1e-10 parity bar leaves 6 digits of head room.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  e = fma(e, e, e);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double t = y*y;
+  const double e = fma(-t, x, 1.0);
+  const double p = fma(e, 0.375, 0.5);
+  const double q = e*y;
+  y = fma(p, q, y);
+  // one more Newton step: cheap insurance that the result is good to the last few ulps
+  const double e2 = fma(-(y*y), x, 1.0);
+  return fma(0.5*y, e2, y);
+}
+
 // TableKernelView::kernelAndGradValue (Kernel/TableKernelViewInline.hh:84-99) with
-// QuadraticInterpolatorView::lowerBound (Utilities/QuadraticInterpolatorViewInline.hh:71-77).  The interval index is
-// size_t(max(0,x-xmin)/xstep); a reciprocal multiply is used unless the quotient is within 1e-9 of an integer, where the
-// true division decides (an off-by-one interval would change W at the 1e-6 level).
-__device__ __forceinline__ void table_eval(const double* __restrict__ tab, double kext, double xmin, double xstep, double rxstep,
-                                           uint32_t n1, double eta, double Hdet, double& W, double& gW) {
-  if (eta < kext) {
-    const double x = fmax(0.0, eta - xmin);
-    double q = x*rxstep;
-    const double fl = floor(q);
-    if (q - fl < 1.0e-9 || fl + 1.0 - q < 1.0e-9) q = x/xstep;
-    uint32_t k = (uint32_t)q;
-    k = min(k, n1);
-    const double* c = tab + 6u*k;
-    W  = Hdet*(c[0] + (c[1] + c[2]*eta)*eta);
-    gW = Hdet*(c[3] + (c[4] + c[5]*eta)*eta);
-  } else {
-    W = 0.0; gW = 0.0;
-  }
+// QuadraticInterpolatorView::lowerBound (Utilities/QuadraticInterpolatorViewInline.hh:71-77), WITHOUT the Hdet factor
+// (the caller multiplies; the raw gradient value is also kernelValueSPH of TableKernelViewInline.hh:118-127).
+// The interval index is size_t(max(0,x-xmin)/xstep); a reciprocal multiply is used unless the quotient is within 1e-9
+// of an integer, where the true division decides (an off-by-one interval would change W at the 1e-6 level).
+__device__ __forceinline__ void table_eval_raw(const double* __restrict__ tab, double kext, double xmin, double xstep, double rxstep,
+                                               uint32_t n1, double eta, double& W, double& gW) {
+  const double x = fmax(0.0, eta - xmin);
+  double q = x*rxstep;
+  int k = __double2int_rz(q);
+  const double fr = q - (double)k;
+  if (fr < 1.0e-9 || fr > 1.0 - 1.0e-9) k = (int)(x/xstep);
+  k = min(k, (int)n1);
+  const double2* c = reinterpret_cast<const double2*>(tab + 6*k);
+  const double2 c01 = c[0], c23 = c[1], c45 = c[2];
+  const bool in = eta < kext;
+  W  = in ? fma(fma(c23.x, eta, c01.y), eta, c01.x) : 0.0;
+  gW = in ? fma(fma(c45.y, eta, c45.x), eta, c23.y) : 0.0;
 }
 
 template <int DIM> __device__ __forceinline__ double rootnu(double x) {
@@ -154,20 +178,29 @@ __device__ __forceinline__ double hermite_eval(const double* __restrict__ v, uin
           xstep*((t3 - 2.0*t2 + t)*v[n + i0] + (t3 - t2)*v[n + i0 + 1u]));
 }
 
+// 256-bit read-only row loads (LDG.E.256, sm_100): a 128-byte node row is four of them.
+__device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
 // The pair-loop kernel: one warp per tile of 32 Morton-consecutive nodes, lane <-> node i.
-template <int DIM>
+//   GEN    : general path -- every option of the reference is honoured at run time (LimitedMG, Balsara, Cl/Cq multipliers,
+//            tensile correction, separate Pi kernel, linear/quadraticInExpansion, any XSPH/compatible/smoothing-scale choice).
+//   !GEN   : the plain MonaghanGingold path named by BASELINE.json, with XSPH / SPH-moments / pair-acceleration storage
+//            fixed at compile time so that unused accumulators cost no registers.
+template <int DIM, bool GEN, bool XSPH_, bool HSPH_, bool COMPAT_>
 __global__ void __launch_bounds__(128) k_sph_derivs(DerivArgs a) {
   using D = Dm<DIM>;
   constexpr int NS = D::NS, NT = D::NT, ROW = D::ROW;
   extern __shared__ double smem[];
   // stage the interleaved W/gradW table(s) in shared memory
-  const uint32_t nW = 6u*(a.n1W + 1u), nQ = a.oneKernel ? 0u : 6u*(a.n1Q + 1u);
+  const uint32_t nW = 6u*(a.n1W + 1u), nQ = (GEN && !a.oneKernel) ? 6u*(a.n1Q + 1u) : 0u;
   for (uint32_t k = threadIdx.x; k < nW; k += blockDim.x) smem[k] = a.tabW[k];
   for (uint32_t k = threadIdx.x; k < nQ; k += blockDim.x) smem[nW + k] = a.tabQ[k];
   __syncthreads();
   const double* tW = smem;
   const double* tQ = smem + nW;
-  const double rxW = 1.0/a.xstepW, rxQ = a.oneKernel ? 0.0 : 1.0/a.xstepQ;
+  const double rxW = 1.0/a.xstepW, rxQ = (GEN && !a.oneKernel) ? 1.0/a.xstepQ : 0.0;
 
   const int lane = threadIdx.x & 31;
   const size_t tile = (size_t)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -177,6 +210,13 @@ __global__ void __launch_bounds__(128) k_sph_derivs(DerivArgs a) {
   const bool active = inRange && a.perm[i] < a.nInt;
   const sphb200_options& o = a.o;
   const double tiny = 1.0e-30;
+  const bool xsph = GEN ? (o.XSPH != 0) : XSPH_;
+  const bool hsph = GEN ? (o.hEvolution == SPHB200_H_SPH) : HSPH_;
+  const bool compat = GEN ? (o.compatibleEnergy != 0) : COMPAT_;
+  const bool tens = GEN && (o.epsTensile != 0.0);
+  const bool needQ = GEN && ((o.Qkind == SPHB200_Q_LIMITED_MG) || o.balsara);
+  const bool mult = GEN && (a.auxfCl != nullptr);
+  const bool twoK = GEN && !a.oneKernel;
 
   // ---- node i state
   double ri[DIM], vi[DIM], Hi[NS];
@@ -195,17 +235,18 @@ __global__ void __launch_bounds__(128) k_sph_derivs(DerivArgs a) {
     for (int k = 0; k < NS; ++k) Hi[k] = 0;
   }
   const double Hdeti = sym_det<DIM>(Hi);
-  const bool tens = (o.epsTensile != 0.0);
-  const bool needQ = (o.Qkind == SPHB200_Q_LIMITED_MG) || o.balsara;
-  const bool mult = (a.auxfCl != nullptr);
+  const double rhoiInv = 1.0/rhoi;
+  const double mi_over_rhoi = mi/rhoi;
   const double Pnegi = (tens && inRange) ? a.auxPneg[i] : 0.0;
   const double somr2i = (tens && inRange) ? a.auxSomr2[i] : 0.0;
-  double DvDxQi[NT];
+  double DvDxQi[GEN ? NT : 1];
+  if (GEN) {
 #pragma unroll
-  for (int k = 0; k < NT; ++k) DvDxQi[k] = (needQ && inRange) ? a.auxDvDxQ[i*NT + k] : 0.0;
+    for (int k = 0; k < NT; ++k) DvDxQi[k] = (needQ && inRange) ? a.auxDvDxQ[i*NT + k] : 0.0;
+  }
   const double fCli = (mult && inRange) ? a.auxfCl[i] : 1.0, fCqi = (mult && inRange) ? a.auxfCq[i] : 1.0;
-  const double balsi = (o.balsara && inRange) ? balsara<DIM>(o, DvDxQi, Hdeti, ci) : 1.0;
-  const double mi_over_rhoi = mi/rhoi;
+  const double balsi = (GEN && o.balsara && inRange) ? balsara<DIM>(o, DvDxQi, Hdeti, ci) : 1.0;
+  const double Cl0 = o.Cl, Cq0 = o.Cq, eps2 = o.eps2;
 
   // ---- accumulators
   double rhoSum = 0, norm = 0, DepsDt = 0, maxQ = 0, effQ = 0, XW = 0, m0 = 0;
@@ -217,172 +258,175 @@ __global__ void __launch_bounds__(128) k_sph_derivs(DerivArgs a) {
 
   const uint32_t cnt = active ? a.nbrCount[i] : 0u;
   const uint32_t rows = a.tileRows[tile];
-  const unsigned long long base = a.tileOff[tile];
+  const unsigned long long base = a.tileOff[tile] + lane;
 
   for (uint32_t k = 0; k < rows; ++k) {
-    if (k >= cnt) continue;
-    const unsigned long long slot = base + (unsigned long long)k*SPHB200_TILE + lane;
-    const uint32_t e = a.nbr[slot];
-    const uint32_t j = e & 0x7fffffffu;
-    // ---- node j state: one 128-byte row
+    if (k < cnt) {
+    const unsigned long long slot = base + (unsigned long long)k*SPHB200_TILE;
+    const uint32_t j = a.nbr[slot] & 0x7fffffffu;
+    // ---- node j state: one 128-byte (3-D) / 96-byte (2-D) row
     double rw[ROW];
     {
-      const double2* rp = reinterpret_cast<const double2*>(a.rows + (size_t)j*ROW);
+      const double* rp = a.rows + (size_t)j*ROW;
 #pragma unroll
-      for (int q = 0; q < ROW/2; ++q) { const double2 t = __ldg(rp + q); rw[2*q] = t.x; rw[2*q + 1] = t.y; }
+      for (int q = 0; q < ROW/4; ++q) ldg256(rp + 4*q, rw[4*q], rw[4*q + 1], rw[4*q + 2], rw[4*q + 3]);
     }
     const double* rj = rw + D::R_POS; const double* vj = rw + D::R_VEL; const double* Hj = rw + D::R_H;
     const double mj = rw[D::R_M], rhoj = rw[D::R_RHO], cj = rw[D::R_CS];
     const double Hdetj = sym_det<DIM>(Hj);
+    const double rhojInv = fast_rcp(rhoj);
 
-    // SPH.cc:363-369
+    // SPH.cc:363-369 : rij, eta = H.rij, |eta|, unit vectors (safeInvVar: 0 for coincident nodes)
     double rij[DIM], etai[DIM], etaj[DIM];
 #pragma unroll
     for (int q = 0; q < DIM; ++q) rij[q] = ri[q] - rj[q];
     sym_dot<DIM>(Hi, rij, etai);
     sym_dot<DIM>(Hj, rij, etaj);
-    const double etaMagi = sqrt(vdot<DIM>(etai, etai));
-    const double etaMagj = sqrt(vdot<DIM>(etaj, etaj));
-    const double invi = d_sgn(etaMagi)/fmax(1.0e-30, fabs(etaMagi));     // safeInvVar
-    const double invj = d_sgn(etaMagj)/fmax(1.0e-30, fabs(etaMagj));
-    double etaiU[DIM], etajU[DIM];
-#pragma unroll
-    for (int q = 0; q < DIM; ++q) { etaiU[q] = etai[q]*invi; etajU[q] = etaj[q]*invj; }
+    const double e2i = vdot<DIM>(etai, etai), e2j = vdot<DIM>(etaj, etaj);
+    const double invi = e2i > 0.0 ? fast_rsqrt(e2i) : 0.0;
+    const double invj = e2j > 0.0 ? fast_rsqrt(e2j) : 0.0;
+    const double etaMagi = e2i*invi, etaMagj = e2j*invj;
 
-    // SPH.cc:374-388
+    // SPH.cc:374-377 : W, gradW (table values carry no Hdet yet)
     double Wi, gWi, Wj, gWj;
-    table_eval(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, etaMagi, Hdeti, Wi, gWi);
-    table_eval(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, etaMagj, Hdetj, Wj, gWj);
-    double gradWi[DIM], gradWj[DIM], gradWQi[DIM], gradWQj[DIM], WQi, WQj;
-    { double t[DIM];
-      sym_dot<DIM>(Hi, etaiU, t);
+    table_eval_raw(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, etaMagi, Wi, gWi);
+    table_eval_raw(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, etaMagj, Wj, gWj);
+    const double gWiRaw = gWi;
+    Wi *= Hdeti; gWi *= Hdeti; Wj *= Hdetj; gWj *= Hdetj;
+    double Hei[DIM], Hej[DIM], gradWi[DIM], gradWj[DIM];
+    sym_dot<DIM>(Hi, etai, Hei);                 // gWi*Hi*etaiUnit == (gWi/|etai|) * (Hi.etai)
+    sym_dot<DIM>(Hj, etaj, Hej);
+    { const double si = gWi*invi, sj = gWj*invj;
 #pragma unroll
-      for (int q = 0; q < DIM; ++q) gradWi[q] = gWi*t[q];
-      sym_dot<DIM>(Hj, etajU, t);
+      for (int q = 0; q < DIM; ++q) { gradWi[q] = si*Hei[q]; gradWj[q] = sj*Hej[q]; } }
+    double WQi = Wi, WQj = Wj, gradWQi[DIM], gradWQj[DIM];
 #pragma unroll
-      for (int q = 0; q < DIM; ++q) gradWj[q] = gWj*t[q];
-      if (a.oneKernel) {
-        WQi = Wi; WQj = Wj;
+    for (int q = 0; q < DIM; ++q) { gradWQi[q] = gradWi[q]; gradWQj[q] = gradWj[q]; }
+    if (twoK) {                                   // SPH.cc:383-388
+      double gWQi, gWQj;
+      table_eval_raw(tQ, a.kextQ, a.xminQ, a.xstepQ, rxQ, a.n1Q, etaMagi, WQi, gWQi);
+      table_eval_raw(tQ, a.kextQ, a.xminQ, a.xstepQ, rxQ, a.n1Q, etaMagj, WQj, gWQj);
+      WQi *= Hdeti; WQj *= Hdetj;
+      const double si = gWQi*Hdeti*invi, sj = gWQj*Hdetj*invj;
 #pragma unroll
-        for (int q = 0; q < DIM; ++q) { gradWQi[q] = gradWi[q]; gradWQj[q] = gradWj[q]; }
-      } else {
-        double gWQi, gWQj;
-        table_eval(tQ, a.kextQ, a.xminQ, a.xstepQ, rxQ, a.n1Q, etaMagi, Hdeti, WQi, gWQi);
-        table_eval(tQ, a.kextQ, a.xminQ, a.xstepQ, rxQ, a.n1Q, etaMagj, Hdetj, WQj, gWQj);
-        sym_dot<DIM>(Hi, etaiU, t);
-#pragma unroll
-        for (int q = 0; q < DIM; ++q) gradWQi[q] = gWQi*t[q];
-        sym_dot<DIM>(Hj, etajU, t);
-#pragma unroll
-        for (int q = 0; q < DIM; ++q) gradWQj[q] = gWQj*t[q];
-      }
+      for (int q = 0; q < DIM; ++q) { gradWQi[q] = si*Hei[q]; gradWQj[q] = sj*Hej[q]; }
     }
 
     // SPH.cc:391-396 (i side)
-    rhoSum += mj*Wi;
-    norm += mi_over_rhoi*Wi;
+    rhoSum = fma(mj, Wi, rhoSum);
+    norm = fma(mi_over_rhoi, Wi, norm);
 
     // ---- artificial viscosity: MonaghanGingoldViscosity.cc:69-100 / LimitedMonaghanGingoldViscosity.cc:140-218
-    double vij[DIM];
+    double vij[DIM], vijQ[DIM];
 #pragma unroll
-    for (int q = 0; q < DIM; ++q) vij[q] = vi[q] - vj[q];
-    double fshear = 1.0, fClj = 1.0, fCqj = 1.0;
-    double vijQ[DIM];
+    for (int q = 0; q < DIM; ++q) { vij[q] = vi[q] - vj[q]; vijQ[q] = vij[q]; }
+    double Clij = Cl0, Cqij = Cq0;
+    if (GEN) {
+      double fshear = 1.0, fClj = 1.0, fCqj = 1.0;
+      if (mult) { fClj = a.auxfCl[j]; fCqj = a.auxfCq[j]; }
+      if (needQ) {
+        double DvDxQj[NT];
 #pragma unroll
-    for (int q = 0; q < DIM; ++q) vijQ[q] = vij[q];
-    if (mult) { fClj = a.auxfCl[j]; fCqj = a.auxfCq[j]; }
-    if (needQ) {
-      double DvDxQj[NT];
+        for (int q = 0; q < NT; ++q) DvDxQj[q] = a.auxDvDxQ[(size_t)j*NT + q];
+        if (o.balsara) fshear = 0.5*(balsi + balsara<DIM>(o, DvDxQj, Hdetj, cj));
+        if (o.Qkind == SPHB200_Q_LIMITED_MG) {
+          const double etaCrit = o.etaCritFrac/o.nPerh, etaFold = o.etaFoldFrac/o.nPerh;
+          double xij[DIM], t1[DIM], t2[DIM];
 #pragma unroll
-      for (int q = 0; q < NT; ++q) DvDxQj[q] = a.auxDvDxQ[(size_t)j*NT + q];
-      if (o.balsara) fshear = 0.5*(balsi + balsara<DIM>(o, DvDxQj, Hdetj, cj));
-      if (o.Qkind == SPHB200_Q_LIMITED_MG) {
-        const double etaCrit = o.etaCritFrac/o.nPerh, etaFold = o.etaFoldFrac/o.nPerh;
-        double xij[DIM], t1[DIM], t2[DIM];
+          for (int q = 0; q < DIM; ++q) xij[q] = 0.5*rij[q];
+          ten_dot<DIM>(DvDxQi, xij, t1); const double gradi = vdot<DIM>(t1, xij);
+          ten_dot<DIM>(DvDxQj, xij, t2); const double gradj = vdot<DIM>(t2, xij);
+          const double rri = gradi/(d_sgn(gradj)*fmax(1.0e-30, fabs(gradj)));
+          const double rrj = gradj/(d_sgn(gradi)*fmax(1.0e-30, fabs(gradi)));
+          const double x = fmin(rri, rrj);
+          double phi = (x > 0.0 ? 2.0/(1.0 + x)*2.0*x/(1.0 + x) : 0.0);       // van Leer
+          const double etaij = fmin(etaMagi, etaMagj);
+          if (etaij < etaCrit) { const double z = (etaij - etaCrit)/etaFold; phi *= exp(-z*z); }
 #pragma unroll
-        for (int q = 0; q < DIM; ++q) xij[q] = 0.5*rij[q];
-        ten_dot<DIM>(DvDxQi, xij, t1); const double gradi = vdot<DIM>(t1, xij);
-        ten_dot<DIM>(DvDxQj, xij, t2); const double gradj = vdot<DIM>(t2, xij);
-        const double rri = gradi/(d_sgn(gradj)*fmax(1.0e-30, fabs(gradj)));
-        const double rrj = gradj/(d_sgn(gradi)*fmax(1.0e-30, fabs(gradi)));
-        const double x = fmin(rri, rrj);
-        double phi = (x > 0.0 ? 2.0/(1.0 + x)*2.0*x/(1.0 + x) : 0.0);       // van Leer
-        const double etaij = fmin(etaMagi, etaMagj);
-        if (etaij < etaCrit) { const double z = (etaij - etaCrit)/etaFold; phi *= exp(-z*z); }
-#pragma unroll
-        for (int q = 0; q < DIM; ++q) vijQ[q] = (vi[q] - phi*t1[q]) - (vj[q] + phi*t2[q]);
+          for (int q = 0; q < DIM; ++q) vijQ[q] = (vi[q] - phi*t1[q]) - (vj[q] + phi*t2[q]);
+        }
       }
+      Clij = 0.5*(fCli + fClj)*fshear*Cl0;
+      Cqij = 0.5*(fCqi + fCqj)*fshear*Cq0;
     }
-    const double Clij = 0.5*(fCli + fClj)*fshear*o.Cl;
-    const double Cqij = 0.5*(fCqi + fCqj)*fshear*o.Cq;
-    const double mui = vdot<DIM>(vijQ, etai)/(vdot<DIM>(etai, etai) + o.eps2);
-    const double muj = vdot<DIM>(vijQ, etaj)/(vdot<DIM>(etaj, etaj) + o.eps2);
+    const double mui = vdot<DIM>(vijQ, etai)*fast_rcp(e2i + eps2);
+    const double muj = vdot<DIM>(vijQ, etaj)*fast_rcp(e2j + eps2);
     const double mui0 = fmin(0.0, mui), muj0 = fmin(0.0, muj);
-    const double ei = -Clij*ci*(o.linearInExpansion ? mui : mui0) + Cqij*(o.quadraticInExpansion ? -d_sgn(mui)*mui*mui : mui0*mui0);
-    const double ej = -Clij*cj*(o.linearInExpansion ? muj : muj0) + Cqij*(o.quadraticInExpansion ? -d_sgn(muj)*muj*muj : muj0*muj0);
-    const double QPiij = ei/rhoi, QPiji = ej/rhoj;
+    double ei, ej;
+    if (GEN && (o.linearInExpansion || o.quadraticInExpansion)) {
+      ei = -Clij*ci*(o.linearInExpansion ? mui : mui0) + Cqij*(o.quadraticInExpansion ? -d_sgn(mui)*mui*mui : mui0*mui0);
+      ej = -Clij*cj*(o.linearInExpansion ? muj : muj0) + Cqij*(o.quadraticInExpansion ? -d_sgn(muj)*muj*muj : muj0*muj0);
+    } else {
+      ei = fma(Cqij*mui0, mui0, -(Clij*ci)*mui0);
+      ej = fma(Cqij*muj0, muj0, -(Clij*cj)*muj0);
+    }
+    const double hQPiij = 0.5*(ei*rhoiInv), hQPiji = 0.5*(ej*rhojInv);     // 0.5*QPi (SPH.cc:405-406)
     const double Qi = rhoi*ei;
 
     // SPH.cc:405-414
-    double Qacci[DIM], Qaccj[DIM];
+    double Qacc[DIM];                                                     // Qacci + Qaccj
+    double workQi = 0.0;
 #pragma unroll
-    for (int q = 0; q < DIM; ++q) { Qacci[q] = 0.5*(QPiij*gradWQi[q]); Qaccj[q] = 0.5*(QPiji*gradWQj[q]); }
-    const double workQi = vdot<DIM>(vij, Qacci);
+    for (int q = 0; q < DIM; ++q) {
+      const double qi = hQPiij*gradWQi[q];
+      workQi = fma(vij[q], qi, workQi);
+      Qacc[q] = fma(hQPiji, gradWQj[q], qi);
+    }
     maxQ = fmax(maxQ, Qi);
-    effQ += mj*Qi*WQi/rhoj;
+    effQ = fma(mj*Qi, WQi*rhojInv, effQ);
 
     // SPH.cc:417-426
     double Prhoi = Prhoi0, Prhoj = rw[D::R_PRHO];
     if (tens) {
       const double t = Wi/(Hdeti*a.WnPerh), u = Wj/(Hdetj*a.WnPerh);
-      const double Ri = o.epsTensile*(t*t*t*t)*Pnegi;
-      const double Rj = o.epsTensile*(u*u*u*u)*a.auxPneg[j];
-      Prhoi += somr2i*Ri;
-      Prhoj += a.auxSomr2[j]*Rj;
+      Prhoi += somr2i*(o.epsTensile*(t*t*t*t)*Pnegi);
+      Prhoj += a.auxSomr2[j]*(o.epsTensile*(u*u*u*u)*a.auxPneg[j]);
     }
     double delta[DIM];
 #pragma unroll
-    for (int q = 0; q < DIM; ++q) delta[q] = Prhoi*gradWi[q] + Prhoj*gradWj[q] + Qacci[q] + Qaccj[q];
+    for (int q = 0; q < DIM; ++q) delta[q] = fma(Prhoi, gradWi[q], fma(Prhoj, gradWj[q], Qacc[q]));
 #pragma unroll
-    for (int q = 0; q < DIM; ++q) DvDt[q] -= mj*delta[q];
-    if (o.compatibleEnergy) {
+    for (int q = 0; q < DIM; ++q) DvDt[q] = fma(-mj, delta[q], DvDt[q]);
+    if (compat) {
 #pragma unroll
       for (int q = 0; q < DIM; ++q) a.pacc[(size_t)q*a.nSlots + slot] = delta[q];
     }
 
     // SPH.cc:434
-    DepsDt += mj*(Prhoi*vdot<DIM>(vij, gradWi) + workQi);
+    DepsDt = fma(mj, fma(Prhoi, vdot<DIM>(vij, gradWi), workQi), DepsDt);
 
-    // SPH.cc:438-445, 463-468
+    // SPH.cc:438-445, 463-468 : DvDx -= mj*vij (x) gradWi ; M -= mj*rij (x) gradWi
+    { double g[DIM];
 #pragma unroll
-    for (int r = 0; r < DIM; ++r)
+      for (int q = 0; q < DIM; ++q) g[q] = mj*gradWi[q];
 #pragma unroll
-      for (int c2 = 0; c2 < DIM; ++c2) {
-        DvDx[r*DIM + c2] -= mj*(vij[r]*gradWi[c2]);
-        M[r*DIM + c2] -= mj*(rij[r]*gradWi[c2]);
-      }
-
-    // SPH.cc:448-454
-    if (o.XSPH) {
-      const double w = 0.5*(mi_over_rhoi*Wi + mj/rhoj*Wj);
-      XW += w;
+      for (int r = 0; r < DIM; ++r)
 #pragma unroll
-      for (int q = 0; q < DIM; ++q) XdV[q] -= w*vij[q];
+        for (int c2 = 0; c2 < DIM; ++c2) {
+          DvDx[r*DIM + c2] = fma(-vij[r], g[c2], DvDx[r*DIM + c2]);
+          M[r*DIM + c2] = fma(-rij[r], g[c2], M[r*DIM + c2]);
+        }
+      // SPH.cc:457-460
+      const double f = rhoj - rhoi;
+#pragma unroll
+      for (int q = 0; q < DIM; ++q) gradRho[q] = fma(f, g[q], gradRho[q]);
     }
 
-    // SPH.cc:457-460
-    { const double f = mj*(rhoj - rhoi);
+    // SPH.cc:448-454
+    if (xsph) {
+      const double w = 0.5*fma(mi_over_rhoi, Wi, mj*rhojInv*Wj);
+      XW += w;
 #pragma unroll
-      for (int q = 0; q < DIM; ++q) gradRho[q] += f*gradWi[q]; }
+      for (int q = 0; q < DIM; ++q) XdV[q] = fma(-w, vij[q], XdV[q]);
+    }
 
-    // SPHSmoothingScale.cc:186-222 (i side; same NodeList, Cartesian => fweightij = 1)
-    if (o.hEvolution == SPHB200_H_SPH) {
-      double dW, gg;
-      table_eval(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, etaMagi, 1.0, dW, gg);
-      const double WSPHi = fabs(gg);
+    // SPHSmoothingScale.cc:186-222 (i side; same NodeList, Cartesian => fweightij = 1): WSPHi = |gradW table(eta_i)|
+    if (hsph) {
+      const double WSPHi = fabs(gWiRaw);
       m0 += WSPHi;
 #pragma unroll
-      for (int q = 0; q < DIM; ++q) m1[q] -= WSPHi*etai[q];
+      for (int q = 0; q < DIM; ++q) m1[q] = fma(-WSPHi, etai[q], m1[q]);
+    }
     }
   }
 
@@ -402,17 +446,15 @@ __global__ void __launch_bounds__(128) k_sph_derivs(DerivArgs a) {
     ten_inverse<DIM>(M, Minv);
     ten_mul<DIM>(DvDx, Minv, DvDxF);
   } else {
-    const double rinv = 1.0/rhoi;
 #pragma unroll
-    for (int q = 0; q < NT; ++q) { Minv[q] = M[q]; DvDxF[q] = DvDx[q]*rinv; }
+    for (int q = 0; q < NT; ++q) { Minv[q] = M[q]; DvDxF[q] = DvDx[q]*rhoiInv; }
   }
-  { const double rinv = 1.0/rhoi;
 #pragma unroll
-    for (int q = 0; q < DIM; ++q) put(DV_GRADRHO, q, gradRho[q]*rinv); }
+  for (int q = 0; q < DIM; ++q) put(DV_GRADRHO, q, gradRho[q]*rhoiInv);
   put(DV_DRHODT, 0, -rhoi*ten_trace<DIM>(DvDxF));
   if (o.evolveTotalEnergy) DepsDt = mi*(vdot<DIM>(vi, DvDt) + DepsDt);
   put(DV_DEPSDT, 0, DepsDt);
-  if (o.XSPH) {
+  if (xsph) {
     XW += Hdeti*mi/rhoi*a.W0;
     const double deninv = 1.0/fmax(tiny, XW);
 #pragma unroll
@@ -428,7 +470,7 @@ __global__ void __launch_bounds__(128) k_sph_derivs(DerivArgs a) {
   for (int q = 0; q < NT; ++q) { put(DV_DVDX, q, DvDxF[q]); put(DV_LOCALDVDX, q, DvDxF[q]); put(DV_M, q, Minv[q]); put(DV_LOCALM, q, Minv[q]); }
 
   // ---- K5: smoothing scale
-  if (o.hEvolution == SPHB200_H_SPH) {
+  if (hsph) {
     const double z0 = rootnu<DIM>(fmax(0.0, m0));
     put(DV_M0, 0, z0);
 #pragma unroll
@@ -458,6 +500,29 @@ __global__ void __launch_bounds__(128) k_sph_derivs(DerivArgs a) {
     }
 #pragma unroll
     for (int q = 0; q < NS; ++q) { put(DV_DHDT, q, dh[q]); put(DV_HIDEAL, q, 0.0); }
+  }
+}
+
+template <int DIM, bool GEN, bool X, bool H, bool C>
+int launch_one(sphb200_ctx* c, const DerivArgs& a, unsigned nb, int threads, size_t shm) {
+  CU_CHECK(c, cudaFuncSetAttribute(k_sph_derivs<DIM, GEN, X, H, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+  k_sph_derivs<DIM, GEN, X, H, C><<<nb, threads, shm, c->stream>>>(a);
+  return 0;
+}
+template <int DIM>
+int launch_dim(sphb200_ctx* c, const DerivArgs& a, unsigned nb, int threads, size_t shm, bool gen) {
+  const bool x = a.o.XSPH != 0, h = a.o.hEvolution == SPHB200_H_SPH, p = a.o.compatibleEnergy != 0;
+  if (gen) return launch_one<DIM, true, true, true, true>(c, a, nb, threads, shm);
+  const int code = (x ? 4 : 0) | (h ? 2 : 0) | (p ? 1 : 0);
+  switch (code) {
+    case 0: return launch_one<DIM, false, false, false, false>(c, a, nb, threads, shm);
+    case 1: return launch_one<DIM, false, false, false, true>(c, a, nb, threads, shm);
+    case 2: return launch_one<DIM, false, false, true, false>(c, a, nb, threads, shm);
+    case 3: return launch_one<DIM, false, false, true, true>(c, a, nb, threads, shm);
+    case 4: return launch_one<DIM, false, true, false, false>(c, a, nb, threads, shm);
+    case 5: return launch_one<DIM, false, true, false, true>(c, a, nb, threads, shm);
+    case 6: return launch_one<DIM, false, true, true, false>(c, a, nb, threads, shm);
+    default: return launch_one<DIM, false, true, true, true>(c, a, nb, threads, shm);
   }
 }
 
@@ -498,13 +563,10 @@ int sphb200_launch_derivs(sphb200_ctx* c) {
   const unsigned nb = (unsigned)((c->nTiles + wpb - 1)/wpb);
   const size_t shm = (size_t)6*(c->W.n1 + 1)*sizeof(double) + (c->oneKernel ? 0 : (size_t)6*(c->WQ.n1 + 1)*sizeof(double));
   if (shm > 200*1024) return sphb200_fail(c, "kernel table too large for shared memory");
-  if (c->ndim == 3) {
-    CU_CHECK(c, cudaFuncSetAttribute(k_sph_derivs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-    k_sph_derivs<3><<<nb, wpb*32, shm, c->stream>>>(a);
-  } else {
-    CU_CHECK(c, cudaFuncSetAttribute(k_sph_derivs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-    k_sph_derivs<2><<<nb, wpb*32, shm, c->stream>>>(a);
-  }
+  const bool gen = (c->opt.Qkind != SPHB200_Q_MG) || c->opt.balsara || mult || tens || !c->oneKernel ||
+                   c->opt.linearInExpansion || c->opt.quadraticInExpansion;
+  if (c->ndim == 3) { if (launch_dim<3>(c, a, nb, wpb*32, shm, gen)) return 1; }
+  else              { if (launch_dim<2>(c, a, nb, wpb*32, shm, gen)) return 1; }
   KERNEL_CHECK(c, "k_sph_derivs");
   c->derivsValid = true;
   return 0;
