@@ -86,12 +86,16 @@ int alloc_nodes(sphb200_ctx* c, size_t n) {
   };
   if (reall32(c->cellKeyApi, cap) || reall32(c->perm, cap) || reall32(c->skey, cap) || reall32(c->nbrCount, cap)) return 1;
   const size_t nt = (cap + SPHB200_TILE - 1)/SPHB200_TILE + 1;
-  if (reall32(c->tileRows, nt)) return 1;
+  if (reall32(c->tileRows, nt) || reall32(c->tileWords, nt)) return 1;
+  if (c->maskOff) cudaFree(c->maskOff);
+  c->maskOff = nullptr;
+  CU_CHECK(c, cudaMalloc((void**)&c->maskOff, (nt + 1)*sizeof(unsigned long long)));
   if (c->tileOff) cudaFree(c->tileOff);
   c->tileOff = nullptr;
   CU_CHECK(c, cudaMalloc((void**)&c->tileOff, (nt + 1)*sizeof(unsigned long long)));
   // aux arrays are sized lazily from cap
   for (double** p : {&c->auxPneg, &c->auxSomr2, &c->auxDvDxQ, &c->auxfCl, &c->auxfCq}) { if (*p) cudaFree(*p); *p = nullptr; }
+  if (c->frows) { cudaFree(c->frows); c->frows = nullptr; c->frowsCap = 0; }
   c->cap = cap;
   return 0;
 }
@@ -162,7 +166,7 @@ void sphb200_destroy(sphb200_ctx* c) {
   for (void* p : {(void*)c->W.coef, (void*)c->W.nperhVals, (void*)c->WQ.coef, (void*)c->WQ.nperhVals, (void*)c->cellKeyApi, (void*)c->cellStart,
                   (void*)c->cellCursor, (void*)c->perm, (void*)c->skey, (void*)c->reduceBuf, (void*)c->rows, (void*)c->auxPneg, (void*)c->auxSomr2,
                   (void*)c->auxDvDxQ, (void*)c->auxfCl, (void*)c->auxfCq, (void*)c->nbrCount, (void*)c->tileRows, (void*)c->tileOff, (void*)c->nbr,
-                  (void*)c->counters, (void*)c->scanTmp, (void*)c->pacc, (void*)c->stage}) cudaFree(p);
+                  (void*)c->counters, (void*)c->frows, (void*)c->tileWords, (void*)c->maskOff, (void*)c->mask, (void*)c->scanTmp, (void*)c->pacc, (void*)c->stage}) cudaFree(p);
   cudaFreeHost(c->reduceHost); cudaFreeHost(c->countersHost);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);

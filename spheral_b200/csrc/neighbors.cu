@@ -15,6 +15,10 @@ namespace {
 
 constexpr int RB = 256;   // threads for simple per-node kernels
 
+template <int DIM> struct Fr;                     // FP32 pre-filter row: relpos, H, lo2, hi2
+template <> struct Fr<3> { static constexpr int ROW = 12, R_H = 3, R_LO = 9, R_HI = 10; };
+template <> struct Fr<2> { static constexpr int ROW = 8,  R_H = 2, R_LO = 5, R_HI = 6; };
+
 // ---- K1a: bounding box + maximum per-axis kernel extent ---------------------------------------------------------
 // extent_a(i) = kext*sqrt((H^-2)_aa): half width along axis a of node i's ellipsoid |H r| <= kext
 // (the role of Neighbor::HExtent, NeighborInline.hh:52-64).
@@ -115,6 +119,7 @@ struct PackArgs {
   const uint32_t *perm, *keyApi;
   uint32_t* skey;
   size_t n;
+  float* frows; GridDev g; double kext; double csmax;
 };
 template <int DIM>
 __global__ void __launch_bounds__(RB) k_pack(PackArgs a) {
@@ -140,58 +145,53 @@ __global__ void __launch_bounds__(RB) k_pack(PackArgs a) {
   }
   if (a.auxfCl) { a.auxfCl[s] = a.fCl[o]; a.auxfCq[s] = a.fCq[o]; }
   if (a.skey) a.skey[s] = a.keyApi[o];
+  if (a.frows) {
+    // FP32 pre-filter row: position relative to the node's cell corner, H, and the squared thresholds of the error band.
+    // |eta_f32 - eta| <= B = ||H||_F * csmax * 2^-17 for candidates in the 3^DIM stencil (DESIGN.md "K2 error band"), so
+    //   eta_f32^2 <= (kext-B)^2  => certainly inside ;  eta_f32^2 > (kext+B)^2  => certainly outside.
+    using F = Fr<DIM>;
+    float* f = a.frows + s*F::ROW;
+    double hf = 0.0;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+      const double x = a.pos[o*DIM + k];
+      const int c = cell_coord(x, a.g.lo[k], a.g.cs[k], a.g.nc[k]);
+      f[k] = (float)(x - (a.g.lo[k] + (double)c*a.g.cs[k]));
+    }
+#pragma unroll
+    for (int k = 0; k < D::NS; ++k) { const double h = a.H[o*D::NS + k]; f[F::R_H + k] = (float)h; hf += h*h; }
+    if (DIM == 3) hf += a.H[o*6 + 1]*a.H[o*6 + 1] + a.H[o*6 + 2]*a.H[o*6 + 2] + a.H[o*6 + 4]*a.H[o*6 + 4];
+    else hf += a.H[o*3 + 1]*a.H[o*3 + 1];
+    const double B = sqrt(hf)*a.csmax*7.62939453125e-06;       // 2^-17
+    const double lo = fmax(a.kext - B, 0.0), hi = a.kext + B;
+    f[F::R_LO] = __double2float_rd(lo*lo*(1.0 - 1.0e-6));
+    f[F::R_HI] = __double2float_ru(hi*hi*(1.0 + 1.0e-6));
+    f[F::ROW - 1] = 0.f;
+  }
 }
 
 // ---- K2: neighbour build ----------------------------------------------------------------------------------------------------
 // One warp per tile of 32 consecutive Morton-sorted nodes; lane <-> node i.  The warp walks the union of the 3^DIM cell
-// stencils of the distinct cells its nodes live in; every candidate j is read once (uniform address -> broadcast) and
-// tested by all lanes.  FILL=false counts, FILL=true writes the sliced-ELL lists.
+// stencils of the distinct cells its nodes live in ("candidates", visited in a fixed order); every candidate j is read once
+// (uniform address -> broadcast) and tested by all lanes.
+//   k_nbr_count_candidates : integer walk, number of candidates per tile (sizes the hit-mask buffer)
+//   k_nbr_test             : the predicate, once per (i, candidate): FP32 pre-filter with a rigorous error band, exact FP64
+//                            evaluation (reference operation order, no FMA) for the rare in-band cases; emits one hit bit
+//                            per (lane, candidate) plus the per-node counts
+//   k_nbr_fill             : integer walk that expands the hit masks into the sliced-ELL lists (warp-shuffle lookups)
 struct NbrArgs {
-  const double* rows; const uint32_t* perm; const uint32_t* skey; const uint32_t* cellStart;
+  const double* rows; const float* frows; const uint32_t* perm; const uint32_t* skey; const uint32_t* cellStart;
   size_t n; uint32_t nInt; double kext2; GridDev g;
   uint32_t* nbrCount; uint32_t* tileRows; const unsigned long long* tileOff; uint32_t* nbr;
+  uint32_t* tileWords; const unsigned long long* maskOff; uint32_t* mask;
   unsigned long long* counters;
 };
 
-template <int DIM, bool FILL>
-__global__ void __launch_bounds__(128) k_neighbors(NbrArgs a) {
-  using D = Dm<DIM>;
-  const int lane = threadIdx.x & 31;
-  const size_t tile = (size_t)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
-  const size_t i = tile*SPHB200_TILE + lane;
-  if (tile*SPHB200_TILE >= a.n) return;
-  const bool inRange = i < a.n;
-  const uint32_t origi = inRange ? a.perm[i] : 0xffffffffu;
-  const bool active = inRange && origi < a.nInt;
 
-  double ri[DIM], Hi[D::NS];
-  int ci[3] = {0, 0, 0};
-  uint32_t keyi = 0xffffffffu;
-  if (inRange) {
-    const double* r = a.rows + i*D::ROW;
-#pragma unroll
-    for (int k = 0; k < DIM; ++k) ri[k] = r[D::R_POS + k];
-#pragma unroll
-    for (int k = 0; k < D::NS; ++k) Hi[k] = r[D::R_H + k];
-#pragma unroll
-    for (int k = 0; k < DIM; ++k) ci[k] = cell_coord(ri[k], a.g.lo[k], a.g.cs[k], a.g.nc[k]);
-    keyi = a.skey[i];
-  } else {
-#pragma unroll
-    for (int k = 0; k < DIM; ++k) ri[k] = 0.0;
-#pragma unroll
-    for (int k = 0; k < D::NS; ++k) Hi[k] = 0.0;
-  }
-
-  // leaders: first active lane of every distinct cell in the tile
-  const unsigned actMask = __ballot_sync(0xffffffffu, active);
-  unsigned same = __match_any_sync(0xffffffffu, active ? keyi : (0x80000000u | lane));
-  const bool leader = active && ((__ffs(same & actMask) - 1) == lane);
-  const unsigned leaders = __ballot_sync(0xffffffffu, leader);
-
-  uint32_t cnt = 0, hi = 0;
-  const unsigned long long base = FILL ? a.tileOff[tile] : 0ull;
-
+// Per-warp candidate walk shared by the three kernels: calls f(jb, je, sx, sy, sz) for every stencil cell, warp-uniformly.
+template <int DIM, typename F>
+__device__ __forceinline__ void walk_cells(const GridDev& g, const uint32_t* __restrict__ cellStart, unsigned leaders,
+                                           const int* ci, F&& f) {
   for (unsigned lm = leaders; lm; lm &= lm - 1) {
     const int L = __ffs(lm) - 1;
     int lc[3];
@@ -199,13 +199,13 @@ __global__ void __launch_bounds__(128) k_neighbors(NbrArgs a) {
     const int zlo = (DIM == 3) ? -1 : 0, zhi = (DIM == 3) ? 1 : 0;
     for (int dz = zlo; dz <= zhi; ++dz) {
       const int sz = lc[2] + dz;
-      if (DIM == 3 && (sz < 0 || sz >= a.g.nc[2])) continue;
+      if (DIM == 3 && (sz < 0 || sz >= g.nc[2])) continue;
       for (int dy = -1; dy <= 1; ++dy) {
         const int sy = lc[1] + dy;
-        if (sy < 0 || sy >= a.g.nc[1]) continue;
+        if (sy < 0 || sy >= g.nc[1]) continue;
         for (int dx = -1; dx <= 1; ++dx) {
           const int sx = lc[0] + dx;
-          if (sx < 0 || sx >= a.g.nc[0]) continue;
+          if (sx < 0 || sx >= g.nc[0]) continue;
           // skip cells already visited through an earlier leader's stencil
           bool seen = false;
           for (unsigned pm = leaders & ((1u << L) - 1u); pm && !seen; pm &= pm - 1) {
@@ -214,44 +214,181 @@ __global__ void __launch_bounds__(128) k_neighbors(NbrArgs a) {
             seen = (abs(px - sx) <= 1) && (abs(py - sy) <= 1) && (DIM == 2 || abs(pz - sz) <= 1);
           }
           if (seen) continue;
-          uint32_t key = dilate(a.g, 0, sx) | dilate(a.g, 1, sy);
-          if (DIM == 3) key |= dilate(a.g, 2, sz);
-          const uint32_t jb = a.cellStart[key], je = a.cellStart[key + 1];
-          for (uint32_t j = jb; j < je; ++j) {
-            const double* rj = a.rows + (size_t)j*D::ROW;     // uniform address: one broadcast transaction per load
-            double rij[DIM], Hj[D::NS];
-#pragma unroll
-            for (int k = 0; k < DIM; ++k) rij[k] = __dadd_rn(ri[k], -rj[D::R_POS + k]);
-#pragma unroll
-            for (int k = 0; k < D::NS; ++k) Hj[k] = rj[D::R_H + k];
-            const double e2i = eta2_exact<DIM>(Hi, rij);
-            const double e2j = eta2_exact<DIM>(Hj, rij);
-            const bool hit = active && (j != (uint32_t)i) && (e2i <= a.kext2 || e2j <= a.kext2);
-            if (hit) {
-              const uint32_t up = (a.perm[j] > origi) ? 1u : 0u;
-              if (FILL) a.nbr[base + (unsigned long long)cnt*SPHB200_TILE + lane] = j | (up << 31);
-              ++cnt; hi += up;
-            }
-          }
+          uint32_t key = dilate(g, 0, sx) | dilate(g, 1, sy);
+          if (DIM == 3) key |= dilate(g, 2, sz);
+          const uint32_t jb = cellStart[key], je = cellStart[key + 1];
+          if (je > jb) f(jb, je, sx, sy, sz);
         }
       }
     }
   }
+}
 
-  if (!FILL) {
-    if (inRange) a.nbrCount[i] = cnt;
-    uint32_t mx = cnt;
-    unsigned long long sHi = hi, sAll = cnt;
-    for (int d = 16; d; d >>= 1) {
-      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-      sHi += __shfl_xor_sync(0xffffffffu, sHi, d);
-      sAll += __shfl_xor_sync(0xffffffffu, sAll, d);
-    }
-    if (lane == 0) {
-      a.tileRows[tile] = mx;
-      if (sAll) { atomicAdd(&a.counters[0], sHi); atomicAdd(&a.counters[1], sAll); }
-    }
+// common per-lane prologue: identity, cell coordinates, leaders
+template <int DIM>
+__device__ __forceinline__ bool tile_prologue(const NbrArgs& a, size_t& tile, int& lane, size_t& i, bool& inRange, bool& active,
+                                              uint32_t& origi, int* ci, unsigned& leaders) {
+  using D = Dm<DIM>;
+  lane = threadIdx.x & 31;
+  tile = (size_t)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tile*SPHB200_TILE >= a.n) return false;
+  i = tile*SPHB200_TILE + lane;
+  inRange = i < a.n;
+  origi = inRange ? a.perm[i] : 0xffffffffu;
+  active = inRange && origi < a.nInt;
+  ci[0] = ci[1] = ci[2] = 0;
+  uint32_t keyi = 0xffffffffu;
+  if (inRange) {
+    const double* r = a.rows + i*D::ROW;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) ci[k] = cell_coord(r[D::R_POS + k], a.g.lo[k], a.g.cs[k], a.g.nc[k]);
+    keyi = a.skey[i];
   }
+  const unsigned actMask = __ballot_sync(0xffffffffu, active);
+  const unsigned same = __match_any_sync(0xffffffffu, active ? keyi : (0x80000000u | lane));
+  const bool leader = active && ((__ffs(same & actMask) - 1) == lane);
+  leaders = __ballot_sync(0xffffffffu, leader);
+  return true;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128) k_nbr_count_candidates(NbrArgs a) {
+  size_t tile, i; int lane, ci[3]; bool inRange, active; uint32_t origi; unsigned leaders;
+  if (!tile_prologue<DIM>(a, tile, lane, i, inRange, active, origi, ci, leaders)) return;
+  uint32_t T = 0;
+  walk_cells<DIM>(a.g, a.cellStart, leaders, ci, [&](uint32_t jb, uint32_t je, int, int, int) { T += je - jb; });
+  if (lane == 0) a.tileWords[tile] = (T + 31u)/32u;
+}
+
+// exact predicate (ConnectivityMap.cc:912-925) from the FP64 rows
+template <int DIM>
+__device__ __noinline__ bool exact_pair(const double* __restrict__ rows, size_t i, size_t j, double kext2) {
+  using D = Dm<DIM>;
+  const double* pi = rows + i*D::ROW; const double* pj = rows + j*D::ROW;
+  double rij[DIM], Hi[D::NS], Hj[D::NS];
+#pragma unroll
+  for (int k = 0; k < DIM; ++k) rij[k] = __dadd_rn(pi[D::R_POS + k], -pj[D::R_POS + k]);
+#pragma unroll
+  for (int k = 0; k < D::NS; ++k) { Hi[k] = pi[D::R_H + k]; Hj[k] = pj[D::R_H + k]; }
+  return eta2_exact<DIM>(Hi, rij) <= kext2 || eta2_exact<DIM>(Hj, rij) <= kext2;
+}
+
+template <int DIM> __device__ __forceinline__ float eta2_f32(const float* H, const float* r) {
+  if (DIM == 3) {
+    const float ex = fmaf(H[2], r[2], fmaf(H[1], r[1], H[0]*r[0]));
+    const float ey = fmaf(H[4], r[2], fmaf(H[3], r[1], H[1]*r[0]));
+    const float ez = fmaf(H[5], r[2], fmaf(H[4], r[1], H[2]*r[0]));
+    return fmaf(ez, ez, fmaf(ey, ey, ex*ex));
+  } else {
+    const float ex = fmaf(H[1], r[1], H[0]*r[0]);
+    const float ey = fmaf(H[2], r[1], H[1]*r[0]);
+    return fmaf(ey, ey, ex*ex);
+  }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128) k_nbr_test(NbrArgs a) {
+  using F = Fr<DIM>;
+  size_t tile, i; int lane, ci[3]; bool inRange, active; uint32_t origi; unsigned leaders;
+  if (!tile_prologue<DIM>(a, tile, lane, i, inRange, active, origi, ci, leaders)) return;
+  float reli[DIM], Hi[Dm<DIM>::NS], lo2i = 0.f, hi2i = 0.f;
+  if (inRange) {
+    const float* fr = a.frows + i*F::ROW;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) reli[k] = fr[k];
+#pragma unroll
+    for (int k = 0; k < Dm<DIM>::NS; ++k) Hi[k] = fr[F::R_H + k];
+    lo2i = fr[F::R_LO]; hi2i = fr[F::R_HI];
+  } else {
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) reli[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < Dm<DIM>::NS; ++k) Hi[k] = 0.f;
+  }
+  const float csf[3] = {(float)a.g.cs[0], (float)a.g.cs[1], (float)a.g.cs[2]};
+  uint32_t cnt = 0, word = 0, t = 0;
+  uint32_t* mrow = a.mask + a.maskOff[tile] + lane;
+
+  walk_cells<DIM>(a.g, a.cellStart, leaders, ci, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) {
+    // the error band of the FP32 filter is derived for candidates in the lane's own 3^DIM stencil; anything farther is a
+    // certain miss because every cell is at least one kernel extent wide
+    const int kx = ci[0] - sx, ky = ci[1] - sy, kz = (DIM == 3) ? ci[2] - sz : 0;
+    const bool near = active && abs(kx) <= 1 && abs(ky) <= 1 && abs(kz) <= 1;
+    float bse[DIM];
+    bse[0] = fmaf((float)kx, csf[0], reli[0]);
+    bse[1] = fmaf((float)ky, csf[1], reli[1]);
+    if (DIM == 3) bse[2] = fmaf((float)kz, csf[2], reli[2]);
+    for (uint32_t j = jb; j < je; ++j) {
+      const float4* fj = reinterpret_cast<const float4*>(a.frows + (size_t)j*F::ROW);   // uniform address: broadcast
+      float rw[F::ROW];
+#pragma unroll
+      for (int q = 0; q < F::ROW/4; ++q) { const float4 v = __ldg(fj + q); rw[4*q] = v.x; rw[4*q + 1] = v.y; rw[4*q + 2] = v.z; rw[4*q + 3] = v.w; }
+      float r[DIM];
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) r[k] = bse[k] - rw[k];
+      const float e2i = eta2_f32<DIM>(Hi, r);
+      const float e2j = eta2_f32<DIM>(rw + F::R_H, r);
+      const bool cand = near && (j != (uint32_t)i);
+      bool hit = cand && (e2i <= lo2i || e2j <= rw[F::R_LO]);
+      const bool amb = cand && !hit && !(e2i > hi2i && e2j > rw[F::R_HI]);
+      if (amb) hit = exact_pair<DIM>(a.rows, i, j, a.kext2);
+      word |= (hit ? 1u : 0u) << (t & 31u);
+      cnt += hit ? 1u : 0u;
+      ++t;
+      if ((t & 31u) == 0u) { mrow[(size_t)((t >> 5) - 1u)*SPHB200_TILE] = word; word = 0; }
+    }
+  });
+  if (t & 31u) mrow[(size_t)(t >> 5)*SPHB200_TILE] = word;
+
+  if (inRange) a.nbrCount[i] = cnt;
+  uint32_t mx = cnt;
+  unsigned long long sAll = cnt;
+  for (int d = 16; d; d >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    sAll += __shfl_xor_sync(0xffffffffu, sAll, d);
+  }
+  if (lane == 0) {
+    a.tileRows[tile] = mx;
+    if (sAll) atomicAdd(&a.counters[1], sAll);
+  }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128) k_nbr_fill(NbrArgs a) {
+  size_t tile, i; int lane, ci[3]; bool inRange, active; uint32_t origi; unsigned leaders;
+  if (!tile_prologue<DIM>(a, tile, lane, i, inRange, active, origi, ci, leaders)) return;
+  const uint32_t* mrow = a.mask + a.maskOff[tile] + lane;
+  uint32_t* out = a.nbr + a.tileOff[tile] + lane;
+  uint32_t cnt = 0, hi = 0, t = 0;
+  uint32_t candJ = 0, candO = 0;           // lane L holds candidate (32*w + L) of the current chunk
+  auto flush = [&](uint32_t w) {
+    uint32_t m = mrow[(size_t)w*SPHB200_TILE];
+    while (__any_sync(0xffffffffu, m != 0u)) {
+      const int b = m ? (__ffs(m) - 1) : 0;
+      const uint32_t j = __shfl_sync(0xffffffffu, candJ, b);
+      const uint32_t oj = __shfl_sync(0xffffffffu, candO, b);
+      if (m) {
+        const uint32_t up = (oj > origi) ? 1u : 0u;
+        out[(size_t)cnt*SPHB200_TILE] = j | (up << 31);
+        ++cnt; hi += up;
+        m &= m - 1u;
+      }
+    }
+  };
+  walk_cells<DIM>(a.g, a.cellStart, leaders, ci, [&](uint32_t jb, uint32_t je, int, int, int) {
+    uint32_t j = jb;
+    while (j < je) {
+      const uint32_t pos = t & 31u;                         // first free lane of the chunk
+      const uint32_t take = min(32u - pos, je - j);
+      if ((uint32_t)lane >= pos && (uint32_t)lane < pos + take) { candJ = j + ((uint32_t)lane - pos); candO = a.perm[candJ]; }
+      j += take; t += take;
+      if ((t & 31u) == 0u) flush((t >> 5) - 1u);
+    }
+  });
+  if (t & 31u) flush(t >> 5);
+  unsigned long long sHi = hi;
+  for (int d = 16; d; d >>= 1) sHi += __shfl_xor_sync(0xffffffffu, sHi, d);
+  if (lane == 0 && sHi) atomicAdd(&a.counters[0], sHi);
 }
 
 }  // namespace
@@ -269,6 +406,7 @@ template <typename T> int sphb200_ensure(sphb200_ctx* c, T*& p, size_t& cap, siz
 }
 template int sphb200_ensure<uint32_t>(sphb200_ctx*, uint32_t*&, size_t&, size_t);
 template int sphb200_ensure<double>(sphb200_ctx*, double*&, size_t&, size_t);
+template int sphb200_ensure<float>(sphb200_ctx*, float*&, size_t&, size_t);
 
 static int build_grid(sphb200_ctx* c, const double* bb /*lo3 hi3 ext3*/) {
   GridDev& g = c->grid;
@@ -331,6 +469,12 @@ int sphb200_pack_rows(sphb200_ctx* c) {
   a.rows = c->rows; a.auxPneg = tens ? c->auxPneg : nullptr; a.auxSomr2 = tens ? c->auxSomr2 : nullptr;
   a.auxDvDxQ = needQ ? c->auxDvDxQ : nullptr; a.auxfCl = mult ? c->auxfCl : nullptr; a.auxfCq = mult ? c->auxfCq : nullptr;
   a.perm = c->perm; a.keyApi = c->cellKeyApi; a.skey = c->skey; a.n = c->n;
+  { size_t fcap = c->frows ? c->frowsCap : 0;
+    if (sphb200_ensure(c, c->frows, fcap, c->cap*(size_t)(c->ndim == 3 ? 12 : 8))) return 1;
+    c->frowsCap = fcap; }
+  a.frows = c->frows; a.g = c->grid;
+  a.kext = std::max(c->W.kext, c->WQ.set ? c->WQ.kext : 0.0);
+  a.csmax = std::max(c->grid.cs[0], std::max(c->grid.cs[1], c->ndim == 3 ? c->grid.cs[2] : 0.0));
   const unsigned nb = (unsigned)((c->n + RB - 1)/RB);
   if (c->ndim == 3) k_pack<3><<<nb, RB, 0, c->stream>>>(a); else k_pack<2><<<nb, RB, 0, c->stream>>>(a);
   KERNEL_CHECK(c, "k_pack");
@@ -379,27 +523,39 @@ int sphb200_neighbors(sphb200_ctx* c) {
   const size_t n = c->n;
   c->nTiles = (n + SPHB200_TILE - 1)/SPHB200_TILE;
   NbrArgs a{};
-  a.rows = c->rows; a.perm = c->perm; a.skey = c->skey; a.cellStart = c->cellStart;
+  a.rows = c->rows; a.frows = c->frows; a.perm = c->perm; a.skey = c->skey; a.cellStart = c->cellStart;
   a.n = n; a.nInt = (uint32_t)c->nInt;
   const double kext = std::max(c->W.kext, c->WQ.set ? c->WQ.kext : 0.0);
   a.kext2 = kext*kext; a.g = c->grid;
   a.nbrCount = c->nbrCount; a.tileRows = c->tileRows; a.tileOff = c->tileOff; a.nbr = nullptr; a.counters = c->counters;
+  a.tileWords = c->tileWords; a.maskOff = c->maskOff; a.mask = nullptr;
   CU_CHECK(c, cudaMemsetAsync(c->counters, 0, 2*sizeof(unsigned long long), c->stream));
   const int wpb = 4;
   const unsigned nb = (unsigned)((c->nTiles + wpb - 1)/wpb);
-  if (c->ndim == 3) k_neighbors<3, false><<<nb, wpb*32, 0, c->stream>>>(a); else k_neighbors<2, false><<<nb, wpb*32, 0, c->stream>>>(a);
-  KERNEL_CHECK(c, "k_neighbors<count>");
+  // 1. candidates per tile -> hit-mask offsets
+  if (c->ndim == 3) k_nbr_count_candidates<3><<<nb, wpb*32, 0, c->stream>>>(a); else k_nbr_count_candidates<2><<<nb, wpb*32, 0, c->stream>>>(a);
+  KERNEL_CHECK(c, "k_nbr_count_candidates");
+  if (sphb200_scan_tiles(c, c->tileWords, c->maskOff, c->nTiles)) return 1;
+  CU_CHECK(c, cudaMemcpyAsync(c->countersHost + 3, c->maskOff + c->nTiles, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (sphb200_ensure(c, c->mask, c->maskCap, (size_t)c->countersHost[3] + 32)) return 1;
+  a.mask = c->mask;
+  // 2. the predicate, once per (node, candidate)
+  if (c->ndim == 3) k_nbr_test<3><<<nb, wpb*32, 0, c->stream>>>(a); else k_nbr_test<2><<<nb, wpb*32, 0, c->stream>>>(a);
+  KERNEL_CHECK(c, "k_nbr_test");
   if (sphb200_scan_tiles(c, c->tileRows, c->tileOff, c->nTiles)) return 1;
-  CU_CHECK(c, cudaMemcpyAsync(c->countersHost, c->counters, 2*sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   CU_CHECK(c, cudaMemcpyAsync(c->countersHost + 2, c->tileOff + c->nTiles, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  c->nSlots = (size_t)c->countersHost[2];
+  if (sphb200_ensure(c, c->nbr, c->nbrCap, c->nSlots + 32)) return 1;
+  a.nbr = c->nbr;
+  // 3. expand the masks into the sliced-ELL lists
+  if (c->ndim == 3) k_nbr_fill<3><<<nb, wpb*32, 0, c->stream>>>(a); else k_nbr_fill<2><<<nb, wpb*32, 0, c->stream>>>(a);
+  KERNEL_CHECK(c, "k_nbr_fill");
+  CU_CHECK(c, cudaMemcpyAsync(c->countersHost, c->counters, 2*sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   CU_CHECK(c, cudaStreamSynchronize(c->stream));
   c->npairs = (size_t)c->countersHost[0];
   c->nEdges = (size_t)c->countersHost[1];
-  c->nSlots = (size_t)c->countersHost[2];
-  if (sphb200_ensure(c, c->nbr, c->nbrCap, c->nSlots)) return 1;
-  a.nbr = c->nbr;
-  if (c->ndim == 3) k_neighbors<3, true><<<nb, wpb*32, 0, c->stream>>>(a); else k_neighbors<2, true><<<nb, wpb*32, 0, c->stream>>>(a);
-  KERNEL_CHECK(c, "k_neighbors<fill>");
   c->pairsValid = true;
   c->stats.directed_edges = c->nEdges;
   return 0;

@@ -88,6 +88,7 @@ struct sphb200_ctx {
 
   // sorted rows + aux
   double* rows = nullptr;
+  float* frows = nullptr; size_t frowsCap = 0;   // FP32 pre-filter rows of K2 (relpos, H, band thresholds)
   double* auxPneg = nullptr;        // max(-P,0)                      (tensile, SPH.cc:417)
   double* auxSomr2 = nullptr;       // safeInv(omega)/(rho*rho)        (tensile)
   double* auxDvDxQ = nullptr;       // ndim*ndim per node (sorted)     (LimitedMG / Balsara)
@@ -101,6 +102,9 @@ struct sphb200_ctx {
   uint32_t* tileRows = nullptr;     // per tile: max count
   unsigned long long* tileOff = nullptr;  // nTiles+1, in entries
   uint32_t* nbr = nullptr; size_t nbrCap = 0;
+  uint32_t* tileWords = nullptr;    // per tile: 32-candidate words of the hit mask
+  unsigned long long* maskOff = nullptr;
+  uint32_t* mask = nullptr; size_t maskCap = 0;
   unsigned long long* counters = nullptr; // [0]=npairs [1]=directed edges
   unsigned long long* countersHost = nullptr; // pinned
   size_t npairs = 0, nEdges = 0, nSlots = 0;
