@@ -183,16 +183,31 @@ __device__ __forceinline__ void ldg256(const double* p, double& a, double& b, do
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 
-// The pair-loop kernel: one warp per tile of 32 Morton-consecutive nodes, lane <-> node i.
+// Asynchronous global->shared copies (LDGSTS): a warp streams the 128-byte rows of its lanes' upcoming neighbours into a
+// shared-memory ring, PAIR_STAGES iterations ahead of their use, so the L2 latency of the gather is off the critical path
+// although only 2 warps per scheduler are resident (the accumulators cost ~200 registers per thread).
+__device__ __forceinline__ void cp_async16(void* smemDst, const void* gmemSrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmemSrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+constexpr int PAIR_STAGES = 4;          // depth of the neighbour-row ring
+constexpr int PAIR_WARPS = 4;           // warps (= tiles in flight) per CTA
+template <int DIM> struct RingGeom { static constexpr int ROWB = Dm<DIM>::ROW*8 + 16; };   // +16 B pad: conflict-free 128-bit LDS
+
+// The pair-loop kernel: one warp per tile of 32 Morton-consecutive nodes, lane <-> node i; persistent CTAs stride over tiles.
 //   GEN    : general path -- every option of the reference is honoured at run time (LimitedMG, Balsara, Cl/Cq multipliers,
 //            tensile correction, separate Pi kernel, linear/quadraticInExpansion, any XSPH/compatible/smoothing-scale choice).
 //   !GEN   : the plain MonaghanGingold path named by BASELINE.json, with XSPH / SPH-moments / pair-acceleration storage
 //            fixed at compile time so that unused accumulators cost no registers.
 template <int DIM, bool GEN, bool XSPH_, bool HSPH_, bool COMPAT_>
-__global__ void __launch_bounds__(128) k_sph_derivs(DerivArgs a) {
+__global__ void __launch_bounds__(32*PAIR_WARPS, 2) k_sph_derivs(DerivArgs a) {
   using D = Dm<DIM>;
   constexpr int NS = D::NS, NT = D::NT, ROW = D::ROW;
-  extern __shared__ double smem[];
+  constexpr int ROWB = RingGeom<DIM>::ROWB;
+  extern __shared__ __align__(16) double smem[];
   // stage the interleaved W/gradW table(s) in shared memory
   const uint32_t nW = 6u*(a.n1W + 1u), nQ = (GEN && !a.oneKernel) ? 6u*(a.n1Q + 1u) : 0u;
   for (uint32_t k = threadIdx.x; k < nW; k += blockDim.x) smem[k] = a.tabW[k];
@@ -203,12 +218,15 @@ __global__ void __launch_bounds__(128) k_sph_derivs(DerivArgs a) {
   const double rxW = 1.0/a.xstepW, rxQ = (GEN && !a.oneKernel) ? 1.0/a.xstepQ : 0.0;
 
   const int lane = threadIdx.x & 31;
-  const size_t tile = (size_t)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (tile*SPHB200_TILE >= a.n) return;
+  const int warp = threadIdx.x >> 5;
+  // ring of this warp: PAIR_STAGES stages x 32 lane slots of ROWB bytes
+  unsigned char* const warpRing = reinterpret_cast<unsigned char*>(smem + nW + nQ) + (size_t)warp*PAIR_STAGES*32*ROWB;
+  const sphb200_options& o = a.o;
+  const size_t nTiles = (a.n + SPHB200_TILE - 1)/SPHB200_TILE;
+  for (size_t tile = (size_t)blockIdx.x*PAIR_WARPS + warp; tile < nTiles; tile += (size_t)gridDim.x*PAIR_WARPS) {
   const size_t i = tile*SPHB200_TILE + lane;
   const bool inRange = i < a.n;
   const bool active = inRange && a.perm[i] < a.nInt;
-  const sphb200_options& o = a.o;
   const double tiny = 1.0e-30;
   const bool xsph = GEN ? (o.XSPH != 0) : XSPH_;
   const bool hsph = GEN ? (o.hEvolution == SPHB200_H_SPH) : HSPH_;
@@ -260,17 +278,54 @@ __global__ void __launch_bounds__(128) k_sph_derivs(DerivArgs a) {
   const uint32_t rows = a.tileRows[tile];
   const unsigned long long base = a.tileOff[tile] + lane;
 
+  // ---- software pipeline over the neighbour list: indices one iteration ahead of the row copies, row copies
+  //      PAIR_STAGES-1 iterations ahead of the arithmetic.  The copy of the 32 rows of one iteration is warp-cooperative:
+  //      CH lanes fetch the CH 16-byte chunks of one row, so a LDGSTS instruction touches 32/CH full lines instead of 32
+  //      partial ones (the per-lane gather was L1-wavefront bound: profiles/r01_notes.md).
+  constexpr int CH = ROW*8/16;                       // 16-byte chunks per row: 8 (3-D) / 6 (2-D)
+  constexpr uint32_t NOJ = 0xffffffffu;
+  auto issue_rows = [&](uint32_t p, uint32_t jraw) {  // jraw: this lane's neighbour at list position p, NOJ if none
+    unsigned char* const stage = warpRing + (size_t)(p % PAIR_STAGES)*32*ROWB;
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+      const int t = q*32 + lane;
+      const int row = t/CH, chunk = t - row*CH;
+      const uint32_t jr = __shfl_sync(0xffffffffu, jraw, row);
+      if (jr != NOJ)
+        cp_async16(stage + (size_t)row*ROWB + 16*chunk,
+                   reinterpret_cast<const unsigned char*>(a.rows + (size_t)(jr & 0x7fffffffu)*ROW) + 16*chunk);
+    }
+    cp_async_commit();
+  };
+  auto load_idx = [&](uint32_t p) -> uint32_t {
+    return (p < cnt) ? a.nbr[base + (unsigned long long)p*SPHB200_TILE] : NOJ;
+  };
+  uint32_t jn = load_idx(0u);
+#pragma unroll
+  for (uint32_t p = 0; p < (uint32_t)PAIR_STAGES - 1u; ++p) {
+    issue_rows(p, jn);
+    jn = load_idx(p + 1u);
+  }
+
   for (uint32_t k = 0; k < rows; ++k) {
-    if (k < cnt) {
-    const unsigned long long slot = base + (unsigned long long)k*SPHB200_TILE;
-    const uint32_t j = a.nbr[slot] & 0x7fffffffu;
-    // ---- node j state: one 128-byte (3-D) / 96-byte (2-D) row
+    cp_async_wait<PAIR_STAGES - 2>();                 // this lane's copies for position k have landed ...
+    __syncwarp();                                     // ... and so have every other lane's
+    // ---- node j state: one 128-byte (3-D) / 96-byte (2-D) row, from this lane's ring slot
     double rw[ROW];
     {
-      const double* rp = a.rows + (size_t)j*ROW;
+      const double2* rp = reinterpret_cast<const double2*>(warpRing + (size_t)(k % PAIR_STAGES)*32*ROWB + (size_t)lane*ROWB);
 #pragma unroll
-      for (int q = 0; q < ROW/4; ++q) ldg256(rp + 4*q, rw[4*q], rw[4*q + 1], rw[4*q + 2], rw[4*q + 3]);
+      for (int q = 0; q < ROW/2; ++q) { const double2 v = rp[q]; rw[2*q] = v.x; rw[2*q + 1] = v.y; }
     }
+    {
+      // refill the stage consumed in the previous iteration (every lane is past its reads: they precede the __syncwarp above)
+      const uint32_t p = k + (uint32_t)PAIR_STAGES - 1u;
+      issue_rows(p, jn);
+      jn = load_idx(p + 1u);
+    }
+    if (k < cnt) {
+    const unsigned long long slot = base + (unsigned long long)k*SPHB200_TILE;
+    const uint32_t j = GEN ? (a.nbr[slot] & 0x7fffffffu) : 0u;
     const double* rj = rw + D::R_POS; const double* vj = rw + D::R_VEL; const double* Hj = rw + D::R_H;
     const double mj = rw[D::R_M], rhoj = rw[D::R_RHO], cj = rw[D::R_CS];
     const double Hdetj = sym_det<DIM>(Hj);
@@ -430,13 +485,14 @@ __global__ void __launch_bounds__(128) k_sph_derivs(DerivArgs a) {
     }
   }
 
-  if (!inRange) return;
+  cp_async_wait<0>();
+  if (!inRange) continue;
   // ---- K4: per-node finalize (SPH.cc:480-552); ghost nodes get zeros
   const size_t cap = a.cap;
   auto put = [&](int slot, int comp, double v) { a.deriv[slot][(size_t)comp*cap + i] = v; };
   if (!active) {
     for (int s = 0; s < DV_COUNT; ++s) { const int w = sphb200_deriv_width(DIM, s); for (int q = 0; q < w; ++q) put(s, q, 0.0); }
-    return;
+    continue;
   }
   rhoSum += mi*a.W0*Hdeti;
   norm += mi_over_rhoi*a.W0*Hdeti;
@@ -501,6 +557,7 @@ __global__ void __launch_bounds__(128) k_sph_derivs(DerivArgs a) {
 #pragma unroll
     for (int q = 0; q < NS; ++q) { put(DV_DHDT, q, dh[q]); put(DV_HIDEAL, q, 0.0); }
   }
+  }   // tile loop
 }
 
 template <int DIM, bool GEN, bool X, bool H, bool C>
@@ -559,10 +616,14 @@ int sphb200_launch_derivs(sphb200_ctx* c) {
     if (sphb200_ensure(c, c->pacc, c->paccCap, c->nSlots*(size_t)c->ndim)) return 1;
   }
   a.pacc = c->pacc; a.nSlots = c->nSlots;
-  const int wpb = 4;
-  const unsigned nb = (unsigned)((c->nTiles + wpb - 1)/wpb);
-  const size_t shm = (size_t)6*(c->W.n1 + 1)*sizeof(double) + (c->oneKernel ? 0 : (size_t)6*(c->WQ.n1 + 1)*sizeof(double));
-  if (shm > 200*1024) return sphb200_fail(c, "kernel table too large for shared memory");
+  const int wpb = PAIR_WARPS;
+  const size_t ringBytes = (size_t)PAIR_WARPS*PAIR_STAGES*32*(c->ndim == 3 ? RingGeom<3>::ROWB : RingGeom<2>::ROWB);
+  const size_t shm = (size_t)6*(c->W.n1 + 1)*sizeof(double) + (c->oneKernel ? 0 : (size_t)6*(c->WQ.n1 + 1)*sizeof(double)) + ringBytes;
+  if (shm > 226*1024) return sphb200_fail(c, "kernel table too large for shared memory");
+  // persistent CTAs: 2 per SM (register-limited), each striding over the tiles
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+  const unsigned nb = (unsigned)std::min<size_t>((c->nTiles + wpb - 1)/wpb, (size_t)nsm*2);
   const bool gen = (c->opt.Qkind != SPHB200_Q_MG) || c->opt.balsara || mult || tens || !c->oneKernel ||
                    c->opt.linearInExpansion || c->opt.quadraticInExpansion;
   if (c->ndim == 3) { if (launch_dim<3>(c, a, nb, wpb*32, shm, gen)) return 1; }
