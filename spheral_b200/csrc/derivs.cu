@@ -56,21 +56,28 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
   return fma(0.5*y, e2, y);
 }
 
+__device__ __forceinline__ double2 lds128(unsigned addr) {      // 32-bit shared-window address: no generic->shared conversion per use
+  double2 v;
+  asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+
 // TableKernelView::kernelAndGradValue (Kernel/TableKernelViewInline.hh:84-99) with
 // QuadraticInterpolatorView::lowerBound (Utilities/QuadraticInterpolatorViewInline.hh:71-77), WITHOUT the Hdet factor
 // (the caller multiplies; the raw gradient value is also kernelValueSPH of TableKernelViewInline.hh:118-127).
 // The interval index is size_t(max(0,x-xmin)/xstep); a reciprocal multiply is used unless the quotient is within 1e-9
 // of an integer, where the true division decides (an off-by-one interval would change W at the 1e-6 level).
-__device__ __forceinline__ void table_eval_raw(const double* __restrict__ tab, double kext, double xmin, double xstep, double rxstep,
+__device__ __forceinline__ void table_eval_raw(unsigned tab, double kext, double xmin, double xstep, double rxstep,
                                                uint32_t n1, double eta, double& W, double& gW) {
-  const double x = fmax(0.0, eta - xmin);
-  double q = x*rxstep;
+  double x = eta - xmin;
+  x = x > 0.0 ? x : 0.0;
+  const double q = x*rxstep;
   int k = __double2int_rz(q);
   const double fr = q - (double)k;
   if (fr < 1.0e-9 || fr > 1.0 - 1.0e-9) k = (int)(x/xstep);
   k = min(k, (int)n1);
-  const double2* c = reinterpret_cast<const double2*>(tab + 6*k);
-  const double2 c01 = c[0], c23 = c[1], c45 = c[2];
+  const unsigned c = tab + 48u*(unsigned)k;
+  const double2 c01 = lds128(c), c23 = lds128(c + 16u), c45 = lds128(c + 32u);
   const bool in = eta < kext;
   W  = in ? fma(fma(c23.x, eta, c01.y), eta, c01.x) : 0.0;
   gW = in ? fma(fma(c45.y, eta, c45.x), eta, c23.y) : 0.0;
@@ -193,6 +200,10 @@ __device__ __forceinline__ void cp_async16(void* smemDst, const void* gmemSrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
+__device__ __forceinline__ void cp_async16_s(unsigned smemDst, const void* gmemSrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smemDst), "l"(gmemSrc) : "memory");
+}
+
 constexpr int PAIR_STAGES = 4;          // depth of the neighbour-row ring
 constexpr int PAIR_WARPS = 4;           // warps (= tiles in flight) per CTA
 template <int DIM> struct RingGeom { static constexpr int ROWB = Dm<DIM>::ROW*8 + 16; };   // +16 B pad: conflict-free 128-bit LDS
@@ -213,14 +224,14 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, 2) k_sph_derivs(DerivArgs a) {
   for (uint32_t k = threadIdx.x; k < nW; k += blockDim.x) smem[k] = a.tabW[k];
   for (uint32_t k = threadIdx.x; k < nQ; k += blockDim.x) smem[nW + k] = a.tabQ[k];
   __syncthreads();
-  const double* tW = smem;
-  const double* tQ = smem + nW;
+  const unsigned tW = (unsigned)__cvta_generic_to_shared(smem);
+  const unsigned tQ = tW + 8u*nW;
   const double rxW = 1.0/a.xstepW, rxQ = (GEN && !a.oneKernel) ? 1.0/a.xstepQ : 0.0;
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   // ring of this warp: PAIR_STAGES stages x 32 lane slots of ROWB bytes
-  unsigned char* const warpRing = reinterpret_cast<unsigned char*>(smem + nW + nQ) + (size_t)warp*PAIR_STAGES*32*ROWB;
+  const unsigned warpRing = tW + 8u*(nW + nQ) + (unsigned)warp*(PAIR_STAGES*32*ROWB);
   const sphb200_options& o = a.o;
   const size_t nTiles = (a.n + SPHB200_TILE - 1)/SPHB200_TILE;
   for (size_t tile = (size_t)blockIdx.x*PAIR_WARPS + warp; tile < nTiles; tile += (size_t)gridDim.x*PAIR_WARPS) {
@@ -278,27 +289,38 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, 2) k_sph_derivs(DerivArgs a) {
   const uint32_t rows = a.tileRows[tile];
   const unsigned long long base = a.tileOff[tile] + lane;
 
+  double* const paccTile = compat ? a.pacc + (size_t)DIM*a.tileOff[tile] + lane : nullptr;     // pacc_index<DIM>(slot, c)
   // ---- software pipeline over the neighbour list: indices one iteration ahead of the row copies, row copies
   //      PAIR_STAGES-1 iterations ahead of the arithmetic.  The copy of the 32 rows of one iteration is warp-cooperative:
   //      CH lanes fetch the CH 16-byte chunks of one row, so a LDGSTS instruction touches 32/CH full lines instead of 32
   //      partial ones (the per-lane gather was L1-wavefront bound: profiles/r01_notes.md).
   constexpr int CH = ROW*8/16;                       // 16-byte chunks per row: 8 (3-D) / 6 (2-D)
-  constexpr uint32_t NOJ = 0xffffffffu;
-  auto issue_rows = [&](uint32_t p, uint32_t jraw) {  // jraw: this lane's neighbour at list position p, NOJ if none
-    unsigned char* const stage = warpRing + (size_t)(p % PAIR_STAGES)*32*ROWB;
+  // positions past the end of a lane's list fetch row 0 (never read back): no predication in the copy
+  const unsigned char* const rowsB = reinterpret_cast<const unsigned char*>(a.rows);
+  auto issue_rows = [&](uint32_t p, uint32_t jraw) {  // jraw: this lane's list entry at position p (0 if none)
+    const uint32_t jrow = jraw & 0x7fffffffu;         // masked HERE, an iteration after the load was issued, not at the load
+    const unsigned stage = warpRing + (p % PAIR_STAGES)*(32u*ROWB);
+    if (CH == 8) {
+      const unsigned dst = stage + (unsigned)(lane >> 3)*ROWB + 16u*(lane & 7);
+      const unsigned char* const src = rowsB + 16*(lane & 7);
 #pragma unroll
-    for (int q = 0; q < CH; ++q) {
-      const int t = q*32 + lane;
-      const int row = t/CH, chunk = t - row*CH;
-      const uint32_t jr = __shfl_sync(0xffffffffu, jraw, row);
-      if (jr != NOJ)
-        cp_async16(stage + (size_t)row*ROWB + 16*chunk,
-                   reinterpret_cast<const unsigned char*>(a.rows + (size_t)(jr & 0x7fffffffu)*ROW) + 16*chunk);
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t jr = __shfl_sync(0xffffffffu, jrow, 4*q + (lane >> 3));
+        cp_async16_s(dst + (unsigned)q*(4u*ROWB), src + (size_t)jr*(ROW*8));
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        const int t = q*32 + lane;
+        const int row = t/CH, chunk = t - row*CH;
+        const uint32_t jr = __shfl_sync(0xffffffffu, jrow, row);
+        cp_async16_s(stage + (unsigned)row*ROWB + 16u*chunk, rowsB + (size_t)jr*(ROW*8) + 16*chunk);
+      }
     }
     cp_async_commit();
   };
   auto load_idx = [&](uint32_t p) -> uint32_t {
-    return (p < cnt) ? a.nbr[base + (unsigned long long)p*SPHB200_TILE] : NOJ;
+    return (p < cnt) ? a.nbr[base + (unsigned long long)p*SPHB200_TILE] : 0u;
   };
   uint32_t jn = load_idx(0u);
 #pragma unroll
@@ -313,9 +335,9 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, 2) k_sph_derivs(DerivArgs a) {
     // ---- node j state: one 128-byte (3-D) / 96-byte (2-D) row, from this lane's ring slot
     double rw[ROW];
     {
-      const double2* rp = reinterpret_cast<const double2*>(warpRing + (size_t)(k % PAIR_STAGES)*32*ROWB + (size_t)lane*ROWB);
+      const unsigned rp = warpRing + (k % PAIR_STAGES)*(32u*ROWB) + (unsigned)lane*ROWB;
 #pragma unroll
-      for (int q = 0; q < ROW/2; ++q) { const double2 v = rp[q]; rw[2*q] = v.x; rw[2*q + 1] = v.y; }
+      for (int q = 0; q < ROW/2; ++q) { const double2 v = lds128(rp + 16u*q); rw[2*q] = v.x; rw[2*q + 1] = v.y; }
     }
     {
       // refill the stage consumed in the previous iteration (every lane is past its reads: they precede the __syncwarp above)
@@ -323,6 +345,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, 2) k_sph_derivs(DerivArgs a) {
       issue_rows(p, jn);
       jn = load_idx(p + 1u);
     }
+    double* const paccRow = paccTile + (size_t)k*(DIM*32);
     if (k < cnt) {
     const unsigned long long slot = base + (unsigned long long)k*SPHB200_TILE;
     const uint32_t j = GEN ? (a.nbr[slot] & 0x7fffffffu) : 0u;
@@ -338,8 +361,10 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, 2) k_sph_derivs(DerivArgs a) {
     sym_dot<DIM>(Hi, rij, etai);
     sym_dot<DIM>(Hj, rij, etaj);
     const double e2i = vdot<DIM>(etai, etai), e2j = vdot<DIM>(etaj, etaj);
-    const double invi = e2i > 0.0 ? fast_rsqrt(e2i) : 0.0;
-    const double invj = e2j > 0.0 ? fast_rsqrt(e2j) : 0.0;
+    // coincident nodes (eta == 0): 1e-300 keeps the reciprocal finite; it multiplies exact zeros (H.eta, eta^2) below, which
+    // reproduces safeInvVar's 0 * 1e30 = 0 (SPH.cc:368-369); for every other pair the addend is below half an ulp
+    const double invi = fast_rsqrt(e2i + 1.0e-300);
+    const double invj = fast_rsqrt(e2j + 1.0e-300);
     const double etaMagi = e2i*invi, etaMagj = e2j*invj;
 
     // SPH.cc:374-377 : W, gradW (table values carry no Hdet yet)
@@ -406,7 +431,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, 2) k_sph_derivs(DerivArgs a) {
     }
     const double mui = vdot<DIM>(vijQ, etai)*fast_rcp(e2i + eps2);
     const double muj = vdot<DIM>(vijQ, etaj)*fast_rcp(e2j + eps2);
-    const double mui0 = fmin(0.0, mui), muj0 = fmin(0.0, muj);
+    const double mui0 = mui < 0.0 ? mui : 0.0, muj0 = muj < 0.0 ? muj : 0.0;
     double ei, ej;
     if (GEN && (o.linearInExpansion || o.quadraticInExpansion)) {
       ei = -Clij*ci*(o.linearInExpansion ? mui : mui0) + Cqij*(o.quadraticInExpansion ? -d_sgn(mui)*mui*mui : mui0*mui0);
@@ -427,7 +452,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, 2) k_sph_derivs(DerivArgs a) {
       workQi = fma(vij[q], qi, workQi);
       Qacc[q] = fma(hQPiji, gradWQj[q], qi);
     }
-    maxQ = fmax(maxQ, Qi);
+    maxQ = Qi > maxQ ? Qi : maxQ;
     effQ = fma(mj*Qi, WQi*rhojInv, effQ);
 
     // SPH.cc:417-426
@@ -444,7 +469,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, 2) k_sph_derivs(DerivArgs a) {
     for (int q = 0; q < DIM; ++q) DvDt[q] = fma(-mj, delta[q], DvDt[q]);
     if (compat) {
 #pragma unroll
-      for (int q = 0; q < DIM; ++q) a.pacc[(size_t)q*a.nSlots + slot] = delta[q];
+      for (int q = 0; q < DIM; ++q) paccRow[32*q] = delta[q];
     }
 
     // SPH.cc:434

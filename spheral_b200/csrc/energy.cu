@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(128) k_energy(const double* __restrict__ erow,
     const bool up = (e >> 31) != 0u;                   // original index of j > original index of i
     double vj[DIM], d[DIM];
 #pragma unroll
-    for (int q = 0; q < DIM; ++q) { vj[q] = erow[(size_t)j*ES + q]; d[q] = pacc[(size_t)q*nSlots + slot]; }
+    for (int q = 0; q < DIM; ++q) { vj[q] = erow[(size_t)j*ES + q]; d[q] = pacc[pacc_index<DIM>(slot, q)]; }
     const double Dj = erow[(size_t)j*ES + DIM], mj = erow[(size_t)j*ES + DIM + 1];
     if (up) {
       // i is the pair's i-node: paccij = -mj*deltaDvDt (SPH.cc:430); duij = (vj12 - vi12).paccij
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(RB) k_emit_pacc(const uint32_t* __restrict__ o
   const double mj = massApi[outJ[k]];
   const unsigned long long slot = outSlot[k];
 #pragma unroll
-  for (int q = 0; q < DIM; ++q) out[k*DIM + q] = -mj*pacc[(size_t)q*nSlots + slot];    // SPH.cc:430
+  for (int q = 0; q < DIM; ++q) out[k*DIM + q] = -mj*pacc[pacc_index<DIM>(slot, q)];    // SPH.cc:430
 }
 
 // u32 counts -> u64 exclusive offsets (single block serial-by-chunks; export path only, not on the hot path)

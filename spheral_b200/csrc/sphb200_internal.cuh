@@ -10,7 +10,8 @@
 //   nbr        : neighbour lists of internal nodes, sliced-ELL: tile t = sorted slots [32t,32t+32),
 //                entry k of lane l at nbr[tileOff[t] + 32*k + l]; bit31 = "original index of j > original index of i".
 //   d_*        : derivative fields, SoA per component, sorted order.
-//   pacc[a]    : deltaDvDt of every directed edge (same indexing as nbr), component-major.
+//   pacc       : deltaDvDt of every directed edge, blocked like nbr: component c of edge `slot` at pacc_index<DIM>(slot, c)
+//                = DIM*(slot & ~31) + 32*c + (slot & 31), i.e. one 32-lane line per (list row, component).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -146,6 +147,10 @@ int sphb200_pairs_to_host(sphb200_ctx* c, uint32_t* pi, uint32_t* pj, size_t cap
 template <int DIM> struct Dm;
 template <> struct Dm<3> { static constexpr int NS = 6, NT = 9, ROW = 16, R_POS = 0, R_VEL = 3, R_H = 6, R_M = 12, R_RHO = 13, R_PRHO = 14, R_CS = 15; };
 template <> struct Dm<2> { static constexpr int NS = 3, NT = 4, ROW = 12, R_POS = 0, R_VEL = 2, R_H = 4, R_M = 7, R_RHO = 8, R_PRHO = 9, R_CS = 10; };
+
+template <int DIM> __host__ __device__ __forceinline__ unsigned long long pacc_index(unsigned long long slot, int comp) {
+  return (unsigned long long)DIM*(slot & ~31ull) + 32ull*(unsigned)comp + (slot & 31ull);
+}
 
 __device__ __forceinline__ double d_sgn(double x) { return x < 0.0 ? -1.0 : 1.0; }
 
