@@ -86,7 +86,7 @@ int alloc_nodes(sphb200_ctx* c, size_t n) {
   };
   if (reall32(c->cellKeyApi, cap) || reall32(c->perm, cap) || reall32(c->skey, cap) || reall32(c->nbrCount, cap)) return 1;
   const size_t nt = (cap + SPHB200_TILE - 1)/SPHB200_TILE + 1;
-  if (reall32(c->tileRows, nt) || reall32(c->tileWords, nt)) return 1;
+  if (reall32(c->tileRows, nt) || reall32(c->tileWords, nt) || reall32(c->tileRunStart, nt) || reall32(c->tileRunCount, nt)) return 1;
   if (c->maskOff) cudaFree(c->maskOff);
   c->maskOff = nullptr;
   CU_CHECK(c, cudaMalloc((void**)&c->maskOff, (nt + 1)*sizeof(unsigned long long)));
@@ -151,7 +151,8 @@ int sphb200_create(sphb200_ctx** out, int device, const sphb200_options* opts) {
   cudaMalloc((void**)&c->reduceBuf, (296*9 + 16)*sizeof(double));
   cudaMallocHost((void**)&c->reduceHost, 16*sizeof(double));
   cudaMalloc((void**)&c->counters, 4*sizeof(unsigned long long));
-  cudaMallocHost((void**)&c->countersHost, 4*sizeof(unsigned long long));
+  cudaMalloc((void**)&c->dilTab, 3*SPHB200_DIL*sizeof(uint32_t));
+  cudaMallocHost((void**)&c->countersHost, 8*sizeof(unsigned long long));
   if (cudaGetLastError() != cudaSuccess) { sphb200_destroy(c); return sphb200_fail(nullptr, "context allocation failed"); }
   *out = c;
   return 0;
@@ -166,7 +167,8 @@ void sphb200_destroy(sphb200_ctx* c) {
   for (void* p : {(void*)c->W.coef, (void*)c->W.nperhVals, (void*)c->WQ.coef, (void*)c->WQ.nperhVals, (void*)c->cellKeyApi, (void*)c->cellStart,
                   (void*)c->cellCursor, (void*)c->perm, (void*)c->skey, (void*)c->reduceBuf, (void*)c->rows, (void*)c->auxPneg, (void*)c->auxSomr2,
                   (void*)c->auxDvDxQ, (void*)c->auxfCl, (void*)c->auxfCq, (void*)c->nbrCount, (void*)c->tileRows, (void*)c->tileOff, (void*)c->nbr,
-                  (void*)c->counters, (void*)c->frows, (void*)c->tileWords, (void*)c->maskOff, (void*)c->mask, (void*)c->scanTmp, (void*)c->pacc, (void*)c->stage}) cudaFree(p);
+                  (void*)c->counters, (void*)c->frows, (void*)c->tileWords, (void*)c->maskOff, (void*)c->mask, (void*)c->scanTmp, (void*)c->pacc, (void*)c->stage,
+                  (void*)c->runs, (void*)c->tileRunStart, (void*)c->tileRunCount, (void*)c->dilTab}) cudaFree(p);
   cudaFreeHost(c->reduceHost); cudaFreeHost(c->countersHost);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);

@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, 2) k_sph_derivs(DerivArgs a) {
   // positions past the end of a lane's list fetch row 0 (never read back): no predication in the copy
   const unsigned char* const rowsB = reinterpret_cast<const unsigned char*>(a.rows);
   auto issue_rows = [&](uint32_t p, uint32_t jraw) {  // jraw: this lane's list entry at position p (0 if none)
-    const uint32_t jrow = jraw & 0x7fffffffu;         // masked HERE, an iteration after the load was issued, not at the load
+    const uint32_t jrow = jraw;
     const unsigned stage = warpRing + (p % PAIR_STAGES)*(32u*ROWB);
     if (CH == 8) {
       const unsigned dst = stage + (unsigned)(lane >> 3)*ROWB + 16u*(lane & 7);
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, 2) k_sph_derivs(DerivArgs a) {
     double* const paccRow = paccTile + (size_t)k*(DIM*32);
     if (k < cnt) {
     const unsigned long long slot = base + (unsigned long long)k*SPHB200_TILE;
-    const uint32_t j = GEN ? (a.nbr[slot] & 0x7fffffffu) : 0u;
+    const uint32_t j = GEN ? a.nbr[slot] : 0u;
     const double* rj = rw + D::R_POS; const double* vj = rw + D::R_VEL; const double* Hj = rw + D::R_H;
     const double mj = rw[D::R_M], rhoj = rw[D::R_RHO], cj = rw[D::R_CS];
     const double Hdetj = sym_det<DIM>(Hj);

@@ -10,13 +10,13 @@ namespace {
 
 constexpr int RB = 256;
 
-// erow[s] = { v + DvDt*hdt (DIM), DepsDt0, m }   stride DIM+2 padded to even
+// erow[s] = { v + DvDt*hdt (DIM), DepsDt0, m, original index }   stride DIM+3
 template <int DIM>
 __global__ void __launch_bounds__(RB) k_energy_prep(const double* __restrict__ velApi, const double* __restrict__ massApi,
                                                     const uint32_t* __restrict__ perm, const double* __restrict__ DvDt,
                                                     const double* __restrict__ DepsDt, size_t n, size_t cap, double hdt,
                                                     double* __restrict__ erow) {
-  constexpr int ES = (DIM == 3) ? 6 : 4;
+  constexpr int ES = DIM + 3;
   const size_t s = (size_t)blockIdx.x*RB + threadIdx.x;
   if (s >= n) return;
   const size_t o = perm[s];
@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(RB) k_energy_prep(const double* __restrict__ v
   for (int q = 0; q < DIM; ++q) erow[s*ES + q] = velApi[o*DIM + q] + DvDt[(size_t)q*cap + s]*hdt;
   erow[s*ES + DIM] = DepsDt[s];
   erow[s*ES + DIM + 1] = massApi[o];
-  if (DIM == 3) erow[s*ES + 5] = 0.0;
+  erow[s*ES + DIM + 2] = (double)o;            // original index: orients the pair (i_node < j_node, NodePairIdxType.hh:34-58)
 }
 
 template <int DIM>
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(128) k_energy(const double* __restrict__ erow,
                                                 const unsigned long long* __restrict__ tileOff, const uint32_t* __restrict__ nbr,
                                                 const double* __restrict__ pacc, size_t nSlots, size_t n, uint32_t nInt,
                                                 double multiplier, double* __restrict__ epsApi) {
-  constexpr int ES = (DIM == 3) ? 6 : 4;
+  constexpr int ES = DIM + 3;
   const int lane = threadIdx.x & 31;
   const size_t tile = (size_t)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
   const size_t i = tile*SPHB200_TILE + lane;
@@ -57,13 +57,12 @@ __global__ void __launch_bounds__(128) k_energy(const double* __restrict__ erow,
   for (uint32_t k = 0; k < rows; ++k) {
     if (k >= cnt) continue;
     const unsigned long long slot = base + (unsigned long long)k*SPHB200_TILE + lane;
-    const uint32_t e = nbr[slot];
-    const uint32_t j = e & 0x7fffffffu;
-    const bool up = (e >> 31) != 0u;                   // original index of j > original index of i
+    const uint32_t j = nbr[slot];
     double vj[DIM], d[DIM];
 #pragma unroll
     for (int q = 0; q < DIM; ++q) { vj[q] = erow[(size_t)j*ES + q]; d[q] = pacc[pacc_index<DIM>(slot, q)]; }
     const double Dj = erow[(size_t)j*ES + DIM], mj = erow[(size_t)j*ES + DIM + 1];
+    const bool up = erow[(size_t)j*ES + DIM + 2] > (double)o;         // original index of j > original index of i
     if (up) {
       // i is the pair's i-node: paccij = -mj*deltaDvDt (SPH.cc:430); duij = (vj12 - vi12).paccij
       double du = 0.0;
@@ -98,7 +97,7 @@ __global__ void __launch_bounds__(128) k_hi_count(const uint32_t* __restrict__ p
   const unsigned long long base = tileOff[i/SPHB200_TILE] + (i % SPHB200_TILE);
   const uint32_t cnt = nbrCount[i];
   uint32_t h = 0;
-  for (uint32_t k = 0; k < cnt; ++k) h += nbr[base + (unsigned long long)k*SPHB200_TILE] >> 31;
+  for (uint32_t k = 0; k < cnt; ++k) h += (perm[nbr[base + (unsigned long long)k*SPHB200_TILE]] > o) ? 1u : 0u;
   hiByOrig[o] = h;
 }
 
@@ -117,9 +116,8 @@ __global__ void __launch_bounds__(128) k_emit_pairs(const uint32_t* __restrict__
   unsigned long long t = p0;
   for (uint32_t k = 0; k < cnt; ++k) {
     const unsigned long long slot = base + (unsigned long long)k*SPHB200_TILE;
-    const uint32_t e = nbr[slot];
-    if (e >> 31) {
-      const uint32_t jo = perm[e & 0x7fffffffu];
+    const uint32_t jo = perm[nbr[slot]];
+    if (jo > o) {
       unsigned long long q = t;                    // insertion sort by original j
       while (q > p0 && outJ[q - 1] > jo) { outJ[q] = outJ[q - 1]; outSlot[q] = outSlot[q - 1]; --q; }
       outJ[q] = jo; outSlot[q] = slot; outI[t] = o;
@@ -170,7 +168,7 @@ __global__ void k_scan64_small(const uint32_t* __restrict__ in, unsigned long lo
 
 int sphb200_launch_energy(sphb200_ctx* c, double multiplier) {
   const size_t n = c->n;
-  const int ES = (c->ndim == 3) ? 6 : 4;
+  const int ES = c->ndim + 3;
   size_t need = n*ES*sizeof(double);
   if (need > c->stageBytes) {
     if (c->stage) cudaFree(c->stage);

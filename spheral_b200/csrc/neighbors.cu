@@ -15,9 +15,41 @@ namespace {
 
 constexpr int RB = 256;   // threads for simple per-node kernels
 
-template <int DIM> struct Fr;                     // FP32 pre-filter row: relpos, H, lo2, hi2
-template <> struct Fr<3> { static constexpr int ROW = 12, R_H = 3, R_LO = 9, R_HI = 10; };
-template <> struct Fr<2> { static constexpr int ROW = 8,  R_H = 2, R_LO = 5, R_HI = 6; };
+// FP32 pre-filter row of K2, 16 floats = four float4 (both dimensions):
+//   q0 = { x-rel, y-rel, z-rel, r2lo }   position relative to the node's cell corner; |r|^2 <= r2lo  => certainly a neighbour
+//   q1 = { r2hi, e2lo, e2hi, - }         |r|^2 > r2hi => certainly not (this node's side);  eta^2 thresholds of the error band
+//   q2 = { Hxx, Hxy, Hxz, Hyy }  q3 = { Hyz, Hzz, -, - }      (2-D: Hxx, Hxy, Hyy in q2.xyz)
+struct Fr { static constexpr int ROW = 16, R_R2LO = 3, R_R2HI = 4, R_E2LO = 5, R_E2HI = 6, R_H = 8; };
+
+// Bounds on the extreme eigenvalues of a symmetric positive H: cyclic Jacobi rotations, then Gershgorin discs on the
+// (similar) rotated matrix, so lmin/lmax are true bounds up to the round-off of the rotations (the caller adds a 1e-9
+// relative margin).  Exact for diagonal H.  Needed only to turn the ellipsoid |H r| <= kext into an inner and an outer sphere.
+__device__ __forceinline__ void jacobi_rot(double& app, double& aqq, double& apq, double& arp, double& arq) {
+  if (apq == 0.0) return;
+  const double theta = (aqq - app)/(2.0*apq);
+  const double t = (theta < 0.0 ? -1.0 : 1.0)/(fabs(theta) + sqrt(theta*theta + 1.0));
+  const double c = 1.0/sqrt(t*t + 1.0), sn = t*c;
+  app -= t*apq; aqq += t*apq; apq = 0.0;
+  const double rp = c*arp - sn*arq, rq = sn*arp + c*arq;
+  arp = rp; arq = rq;
+}
+template <int DIM> __device__ __forceinline__ void sym_eig_bounds(const double* H, double& lmin, double& lmax) {
+  if (DIM == 2) {
+    const double m = 0.5*(H[0] + H[2]), d = sqrt(0.25*(H[0] - H[2])*(H[0] - H[2]) + H[1]*H[1]);
+    lmin = m - d; lmax = m + d;
+    return;
+  }
+  double a00 = H[0], a01 = H[1], a02 = H[2], a11 = H[3], a12 = H[4], a22 = H[5];
+  for (int sweep = 0; sweep < 10; ++sweep) {
+    if (fabs(a01) + fabs(a02) + fabs(a12) <= 1.0e-13*(fabs(a00) + fabs(a11) + fabs(a22))) break;
+    jacobi_rot(a00, a11, a01, a02, a12);
+    jacobi_rot(a00, a22, a02, a01, a12);
+    jacobi_rot(a11, a22, a12, a01, a02);
+  }
+  const double off = fabs(a01) + fabs(a02) + fabs(a12);
+  lmin = fmin(a00, fmin(a11, a22)) - off;
+  lmax = fmax(a00, fmax(a11, a22)) + off;
+}
 
 // ---- K1a: bounding box + maximum per-axis kernel extent ---------------------------------------------------------
 // extent_a(i) = kext*sqrt((H^-2)_aa): half width along axis a of node i's ellipsoid |H r| <= kext
@@ -81,13 +113,13 @@ __global__ void k_bbox_final(const double* __restrict__ partial, int nb, double*
 
 // ---- K1b: cell key + histogram --------------------------------------------------------------------------------------
 template <int DIM>
-__global__ void __launch_bounds__(RB) k_cell_count(const double* __restrict__ pos, size_t n, GridDev g,
+__global__ void __launch_bounds__(RB) k_cell_count(const double* __restrict__ pos, size_t n, GridDev g, const uint32_t* __restrict__ dilTab,
                                                    uint32_t* __restrict__ keyOut, uint32_t* __restrict__ cellCount) {
   const size_t i = (size_t)blockIdx.x*RB + threadIdx.x;
   if (i >= n) return;
   uint32_t key = 0;
 #pragma unroll
-  for (int a = 0; a < DIM; ++a) key |= dilate(g, a, cell_coord(pos[i*DIM + a], g.lo[a], g.cs[a], g.nc[a]));
+  for (int a = 0; a < DIM; ++a) key |= dilTab[a*SPHB200_DIL + cell_coord(pos[i*DIM + a], g.lo[a], g.cs[a], g.nc[a])];
   keyOut[i] = key;
   atomicAdd(&cellCount[key], 1u);
 }
@@ -146,52 +178,79 @@ __global__ void __launch_bounds__(RB) k_pack(PackArgs a) {
   if (a.auxfCl) { a.auxfCl[s] = a.fCl[o]; a.auxfCq[s] = a.fCq[o]; }
   if (a.skey) a.skey[s] = a.keyApi[o];
   if (a.frows) {
-    // FP32 pre-filter row: position relative to the node's cell corner, H, and the squared thresholds of the error band.
-    // |eta_f32 - eta| <= B = ||H||_F * csmax * 2^-17 for candidates in the 3^DIM stencil (DESIGN.md "K2 error band"), so
-    //   eta_f32^2 <= (kext-B)^2  => certainly inside ;  eta_f32^2 > (kext+B)^2  => certainly outside.
-    using F = Fr<DIM>;
-    float* f = a.frows + s*F::ROW;
-    double hf = 0.0;
+    // FP32 pre-filter row (layout: struct Fr).  Error model (DESIGN.md "K2 error bands"): every relative-position component
+    // is reconstructed in FP32 as k*cs + rel_i - rel_j with |error| <= 7*2^-24*cs, so for a pair at true distance <= R
+    //   | |r|^2_f32 - |r|^2 | <= 2e-6*R*cs + 1e-6*R^2 + 1e-11*cs^2 =: margin(R)            (spheres)
+    //   | eta_f32 - eta |     <= ||H||_F * cs * 2^-17 =: B                                     (ellipsoids, 3^DIM stencil)
+    float* f = a.frows + s*Fr::ROW;
+    double h[D::NS], hf = 0.0;
 #pragma unroll
-    for (int k = 0; k < DIM; ++k) {
-      const double x = a.pos[o*DIM + k];
-      const int c = cell_coord(x, a.g.lo[k], a.g.cs[k], a.g.nc[k]);
-      f[k] = (float)(x - (a.g.lo[k] + (double)c*a.g.cs[k]));
+    for (int k = 0; k < D::NS; ++k) { h[k] = a.H[o*D::NS + k]; hf += h[k]*h[k]; }
+    if (DIM == 3) hf += h[1]*h[1] + h[2]*h[2] + h[4]*h[4]; else hf += h[1]*h[1];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float rel = 0.f;
+      if (k < DIM) {
+        const double x = a.pos[o*DIM + k];
+        const int c = cell_coord(x, a.g.lo[k], a.g.cs[k], a.g.nc[k]);
+        rel = (float)(x - (a.g.lo[k] + (double)c*a.g.cs[k]));
+      }
+      f[k] = rel;
     }
-#pragma unroll
-    for (int k = 0; k < D::NS; ++k) { const double h = a.H[o*D::NS + k]; f[F::R_H + k] = (float)h; hf += h*h; }
-    if (DIM == 3) hf += a.H[o*6 + 1]*a.H[o*6 + 1] + a.H[o*6 + 2]*a.H[o*6 + 2] + a.H[o*6 + 4]*a.H[o*6 + 4];
-    else hf += a.H[o*3 + 1]*a.H[o*3 + 1];
-    const double B = sqrt(hf)*a.csmax*7.62939453125e-06;       // 2^-17
+    const double cs = a.csmax;
+    double lmin, lmax;
+    sym_eig_bounds<DIM>(h, lmin, lmax);
+    lmin -= 1.0e-9*lmax; lmax *= 1.0 + 1.0e-9;
+    float r2lo = -1.f, r2hi = 3.0e38f;
+    if (lmin > 0.0) {
+      const double Rmax = a.kext/lmin, Rmin = a.kext/lmax;
+      const double mhi = 2.0e-6*Rmax*cs + 1.0e-6*Rmax*Rmax + 1.0e-11*cs*cs;
+      const double mlo = 2.0e-6*Rmin*cs + 1.0e-6*Rmin*Rmin + 1.0e-11*cs*cs;
+      const double hi = (Rmax*Rmax + mhi)*(1.0 + 1.0e-7);
+      if (hi < 3.0e38) r2hi = __double2float_ru(hi);
+      if (Rmin > 1.0e-3*cs) r2lo = __double2float_rd((Rmin*Rmin - mlo)*(1.0 - 1.0e-7));
+    }
+    f[Fr::R_R2LO] = r2lo; f[Fr::R_R2HI] = r2hi;
+    const double B = sqrt(hf)*cs*7.62939453125e-06;       // 2^-17
     const double lo = fmax(a.kext - B, 0.0), hi = a.kext + B;
-    f[F::R_LO] = __double2float_rd(lo*lo*(1.0 - 1.0e-6));
-    f[F::R_HI] = __double2float_ru(hi*hi*(1.0 + 1.0e-6));
-    f[F::ROW - 1] = 0.f;
+    f[Fr::R_E2LO] = __double2float_rd(lo*lo*(1.0 - 1.0e-6));
+    f[Fr::R_E2HI] = __double2float_ru(hi*hi*(1.0 + 1.0e-6));
+    f[7] = __uint_as_float((uint32_t)o);                 // original index (bit pattern), for the pair orientation
+#pragma unroll
+    for (int k = 0; k < 6; ++k) f[Fr::R_H + k] = (k < D::NS) ? (float)h[k] : 0.f;
+    f[14] = 0.f; f[15] = 0.f;
   }
 }
 
 // ---- K2: neighbour build ----------------------------------------------------------------------------------------------------
-// One warp per tile of 32 consecutive Morton-sorted nodes; lane <-> node i.  The warp walks the union of the 3^DIM cell
-// stencils of the distinct cells its nodes live in ("candidates", visited in a fixed order); every candidate j is read once
-// (uniform address -> broadcast) and tested by all lanes.
-//   k_nbr_count_candidates : integer walk, number of candidates per tile (sizes the hit-mask buffer)
-//   k_nbr_test             : the predicate, once per (i, candidate): FP32 pre-filter with a rigorous error band, exact FP64
-//                            evaluation (reference operation order, no FMA) for the rare in-band cases; emits one hit bit
-//                            per (lane, candidate) plus the per-node counts
-//   k_nbr_fill             : integer walk that expands the hit masks into the sliced-ELL lists (warp-shuffle lookups)
+// One warp per tile of 32 consecutive Morton-sorted nodes; lane <-> node i.  The candidates of a tile are the nodes of the
+// union of the 3^DIM cell stencils of the distinct cells its nodes live in, visited in a fixed order, so every candidate j
+// is fetched once per tile and tested by all lanes.
+//   k_tile_runs : integer walk over the stencils; emits the tile's candidate runs (<= 32 consecutive sorted slots of one
+//                 cell: first slot, length, cell coordinates).  A run owns one 32-bit word per lane of the tile's hit mask.
+//   k_nbr_test  : the predicate, once per (i, candidate).  The 64-byte FP32 rows of a run are loaded coalesced (one lane
+//                 per candidate, one run ahead) and broadcast through shared memory.  Stage 1 is |r|^2 against the nodes'
+//                 inner and outer spheres (decisive for isotropic H); stage 2 the FP32 ellipsoid test with a rigorous error
+//                 band; the rare in-band cases are decided by the exact FP64 evaluation (reference operation order, no
+//                 FMA).  Emits one hit word per (lane, run); also counts the pairs (neighbours with a larger original index).
+//   k_nbr_fill  : expands the words into the sliced-ELL lists.
+// All three are launched back to back without a host round trip: buffer capacities come from the previous build and a
+// kernel that would overflow one skips its tile; the host checks the totals once at the end and redoes the build with
+// larger buffers if needed.
 struct NbrArgs {
   const double* rows; const float* frows; const uint32_t* perm; const uint32_t* skey; const uint32_t* cellStart;
+  const uint32_t* dilTab;
   size_t n; uint32_t nInt; double kext2; GridDev g;
-  uint32_t* nbrCount; uint32_t* tileRows; const unsigned long long* tileOff; uint32_t* nbr;
-  uint32_t* tileWords; const unsigned long long* maskOff; uint32_t* mask;
-  unsigned long long* counters;
+  uint32_t* nbrCount; uint32_t* tileRows; const unsigned long long* tileOff; uint32_t* nbr; unsigned long long nbrCap;
+  uint32_t* tileWords; const unsigned long long* maskOff; uint32_t* mask; unsigned long long maskCap;
+  uint4* runs; unsigned long long runsCap; uint32_t* tileRunStart; uint32_t* tileRunCount;
+  unsigned long long* counters;      // [0] npairs  [1] directed edges  [2] run cursor
 };
 
-
-// Per-warp candidate walk shared by the three kernels: calls f(jb, je, sx, sy, sz) for every stencil cell, warp-uniformly.
+// Per-warp candidate walk: calls f(jb, je, sx, sy, sz) for every non-empty stencil cell, warp-uniformly.
 template <int DIM, typename F>
-__device__ __forceinline__ void walk_cells(const GridDev& g, const uint32_t* __restrict__ cellStart, unsigned leaders,
-                                           const int* ci, F&& f) {
+__device__ __forceinline__ void walk_cells(const GridDev& g, const uint32_t* __restrict__ dilTab,
+                                           const uint32_t* __restrict__ cellStart, unsigned leaders, const int* ci, F&& f) {
   for (unsigned lm = leaders; lm; lm &= lm - 1) {
     const int L = __ffs(lm) - 1;
     int lc[3];
@@ -203,6 +262,7 @@ __device__ __forceinline__ void walk_cells(const GridDev& g, const uint32_t* __r
       for (int dy = -1; dy <= 1; ++dy) {
         const int sy = lc[1] + dy;
         if (sy < 0 || sy >= g.nc[1]) continue;
+        const uint32_t kyz = dilTab[SPHB200_DIL + sy] | ((DIM == 3) ? dilTab[2*SPHB200_DIL + sz] : 0u);
         for (int dx = -1; dx <= 1; ++dx) {
           const int sx = lc[0] + dx;
           if (sx < 0 || sx >= g.nc[0]) continue;
@@ -214,8 +274,7 @@ __device__ __forceinline__ void walk_cells(const GridDev& g, const uint32_t* __r
             seen = (abs(px - sx) <= 1) && (abs(py - sy) <= 1) && (DIM == 2 || abs(pz - sz) <= 1);
           }
           if (seen) continue;
-          uint32_t key = dilate(g, 0, sx) | dilate(g, 1, sy);
-          if (DIM == 3) key |= dilate(g, 2, sz);
+          const uint32_t key = dilTab[sx] | kyz;
           const uint32_t jb = cellStart[key], je = cellStart[key + 1];
           if (je > jb) f(jb, je, sx, sy, sz);
         }
@@ -224,10 +283,10 @@ __device__ __forceinline__ void walk_cells(const GridDev& g, const uint32_t* __r
   }
 }
 
-// common per-lane prologue: identity, cell coordinates, leaders
+// common per-lane prologue: identity, cell coordinates
 template <int DIM>
 __device__ __forceinline__ bool tile_prologue(const NbrArgs& a, size_t& tile, int& lane, size_t& i, bool& inRange, bool& active,
-                                              uint32_t& origi, int* ci, unsigned& leaders) {
+                                              uint32_t& origi, int* ci) {
   using D = Dm<DIM>;
   lane = threadIdx.x & 31;
   tile = (size_t)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -237,27 +296,53 @@ __device__ __forceinline__ bool tile_prologue(const NbrArgs& a, size_t& tile, in
   origi = inRange ? a.perm[i] : 0xffffffffu;
   active = inRange && origi < a.nInt;
   ci[0] = ci[1] = ci[2] = 0;
-  uint32_t keyi = 0xffffffffu;
   if (inRange) {
     const double* r = a.rows + i*D::ROW;
 #pragma unroll
     for (int k = 0; k < DIM; ++k) ci[k] = cell_coord(r[D::R_POS + k], a.g.lo[k], a.g.cs[k], a.g.nc[k]);
-    keyi = a.skey[i];
   }
-  const unsigned actMask = __ballot_sync(0xffffffffu, active);
-  const unsigned same = __match_any_sync(0xffffffffu, active ? keyi : (0x80000000u | lane));
-  const bool leader = active && ((__ffs(same & actMask) - 1) == lane);
-  leaders = __ballot_sync(0xffffffffu, leader);
   return true;
 }
 
+constexpr int RUN_CAP = 128;         // candidate runs per tile buffered in shared memory (typical: 40-70)
+
 template <int DIM>
-__global__ void __launch_bounds__(128) k_nbr_count_candidates(NbrArgs a) {
-  size_t tile, i; int lane, ci[3]; bool inRange, active; uint32_t origi; unsigned leaders;
-  if (!tile_prologue<DIM>(a, tile, lane, i, inRange, active, origi, ci, leaders)) return;
-  uint32_t T = 0;
-  walk_cells<DIM>(a.g, a.cellStart, leaders, ci, [&](uint32_t jb, uint32_t je, int, int, int) { T += je - jb; });
-  if (lane == 0) a.tileWords[tile] = (T + 31u)/32u;
+__global__ void __launch_bounds__(128) k_tile_runs(NbrArgs a) {
+  __shared__ uint4 sruns[4][RUN_CAP];
+  size_t tile, i; int lane, ci[3]; bool inRange, active; uint32_t origi;
+  if (!tile_prologue<DIM>(a, tile, lane, i, inRange, active, origi, ci)) return;
+  const int w = threadIdx.x >> 5;
+  // leaders: first internal lane of every distinct cell of the tile
+  const uint32_t keyi = inRange ? a.skey[i] : 0xffffffffu;
+  const unsigned actMask = __ballot_sync(0xffffffffu, active);
+  const unsigned same = __match_any_sync(0xffffffffu, active ? keyi : (0x80000000u | lane));
+  const bool leader = active && ((__ffs(same & actMask) - 1) == lane);
+  const unsigned leaders = __ballot_sync(0xffffffffu, leader);
+  uint32_t R = 0;
+  auto emit = [&](uint32_t jb, uint32_t je, int sx, int sy, int sz, uint32_t lo, bool toShared) {
+    // a cell with more than 32 nodes becomes several runs
+    for (uint32_t b = jb; b < je; b += 32u) {
+      const uint4 rec = make_uint4(b, min(32u, je - b), (uint32_t)sx | ((uint32_t)sy << 16), (uint32_t)sz);
+      if (lane == 0) {
+        if (toShared) { if (R < RUN_CAP) sruns[w][R] = rec; }
+        else if (R >= RUN_CAP) a.runs[lo + R] = rec;
+      }
+      ++R;
+    }
+  };
+  walk_cells<DIM>(a.g, a.dilTab, a.cellStart, leaders, ci, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) { emit(jb, je, sx, sy, sz, 0u, true); });
+  __syncwarp();
+  const uint32_t Rtot = R;
+  unsigned long long start = 0;
+  if (lane == 0) start = atomicAdd(&a.counters[2], (unsigned long long)Rtot);
+  start = __shfl_sync(0xffffffffu, start, 0);
+  if (lane == 0) { a.tileRunStart[tile] = (uint32_t)start; a.tileRunCount[tile] = Rtot; a.tileWords[tile] = Rtot; }
+  if (start + Rtot > a.runsCap) return;              // the host sees the cursor past the capacity and redoes the build
+  for (uint32_t k = lane; k < min(Rtot, (uint32_t)RUN_CAP); k += 32) a.runs[start + k] = sruns[w][k];
+  if (Rtot > RUN_CAP) {                              // rare: very ragged tile, walk again for the tail
+    R = 0;
+    walk_cells<DIM>(a.g, a.dilTab, a.cellStart, leaders, ci, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) { emit(jb, je, sx, sy, sz, (uint32_t)start, false); });
+  }
 }
 
 // exact predicate (ConnectivityMap.cc:912-925) from the FP64 rows
@@ -286,109 +371,130 @@ template <int DIM> __device__ __forceinline__ float eta2_f32(const float* H, con
   }
 }
 
+constexpr int CROW = 20;             // floats per candidate row in shared memory (16 + 4 pad: conflict-free 128-bit stores)
+
 template <int DIM>
 __global__ void __launch_bounds__(128) k_nbr_test(NbrArgs a) {
-  using F = Fr<DIM>;
-  size_t tile, i; int lane, ci[3]; bool inRange, active; uint32_t origi; unsigned leaders;
-  if (!tile_prologue<DIM>(a, tile, lane, i, inRange, active, origi, ci, leaders)) return;
-  float reli[DIM], Hi[Dm<DIM>::NS], lo2i = 0.f, hi2i = 0.f;
+  __shared__ __align__(16) float scand[4][32*CROW];
+  size_t tile, i; int lane, ci[3]; bool inRange, active; uint32_t origi;
+  if (!tile_prologue<DIM>(a, tile, lane, i, inRange, active, origi, ci)) return;
+  const uint32_t R = a.tileRunCount[tile];
+  const unsigned long long rs = a.tileRunStart[tile];
+  if (rs + R > a.runsCap || a.maskOff[tile + 1] > a.maskCap) {       // capacity miss: leave a consistent, empty tile
+    if (inRange) a.nbrCount[i] = 0;
+    if (lane == 0) a.tileRows[tile] = 0;
+    return;
+  }
+  float reli[3] = {0.f, 0.f, 0.f}, Hi[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, r2loi = -1.f, r2hii = 0.f, e2loi = 0.f, e2hii = 0.f;
+  const float4* __restrict__ frows4 = reinterpret_cast<const float4*>(a.frows);
   if (inRange) {
-    const float* fr = a.frows + i*F::ROW;
-#pragma unroll
-    for (int k = 0; k < DIM; ++k) reli[k] = fr[k];
-#pragma unroll
-    for (int k = 0; k < Dm<DIM>::NS; ++k) Hi[k] = fr[F::R_H + k];
-    lo2i = fr[F::R_LO]; hi2i = fr[F::R_HI];
-  } else {
-#pragma unroll
-    for (int k = 0; k < DIM; ++k) reli[k] = 0.f;
-#pragma unroll
-    for (int k = 0; k < Dm<DIM>::NS; ++k) Hi[k] = 0.f;
+    const float4 q0 = frows4[i*4], q1 = frows4[i*4 + 1], q2 = frows4[i*4 + 2], q3 = frows4[i*4 + 3];
+    reli[0] = q0.x; reli[1] = q0.y; reli[2] = q0.z; r2loi = q0.w;
+    r2hii = q1.x; e2loi = q1.y; e2hii = q1.z;
+    if (DIM == 3) { Hi[0] = q2.x; Hi[1] = q2.y; Hi[2] = q2.z; Hi[3] = q2.w; Hi[4] = q3.x; Hi[5] = q3.y; }
+    else { Hi[0] = q2.x; Hi[1] = q2.y; Hi[2] = q2.z; }
   }
   const float csf[3] = {(float)a.g.cs[0], (float)a.g.cs[1], (float)a.g.cs[2]};
-  uint32_t cnt = 0, word = 0, t = 0;
+  float* const sc = scand[threadIdx.x >> 5];
+  uint32_t cnt = 0, hiCnt = 0;                     // neighbours; neighbours with a larger original index (= pairs owned by i)
   uint32_t* mrow = a.mask + a.maskOff[tile] + lane;
 
-  walk_cells<DIM>(a.g, a.cellStart, leaders, ci, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) {
-    // the error band of the FP32 filter is derived for candidates in the lane's own 3^DIM stencil; anything farther is a
-    // certain miss because every cell is at least one kernel extent wide
-    const int kx = ci[0] - sx, ky = ci[1] - sy, kz = (DIM == 3) ? ci[2] - sz : 0;
+  // software pipeline: the rows of run r+1 travel to registers while run r is tested out of shared memory
+  uint4 rec = (R > 0u) ? __ldg(a.runs + rs) : make_uint4(0u, 0u, 0u, 0u);
+  float4 p0, p1, p2, p3;
+  p0 = p1 = p2 = p3 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if ((uint32_t)lane < rec.y) { const size_t c = (size_t)(rec.x + lane)*4; p0 = __ldg(frows4 + c); p1 = __ldg(frows4 + c + 1); p2 = __ldg(frows4 + c + 2); p3 = __ldg(frows4 + c + 3); }
+  for (uint32_t r = 0; r < R; ++r) {
+    const uint32_t jb = rec.x, len = rec.y;
+    const int kx = ci[0] - (int)(rec.z & 0xffffu), ky = ci[1] - (int)(rec.z >> 16), kz = (DIM == 3) ? ci[2] - (int)rec.w : 0;
+    __syncwarp();                                                   // every lane is done with the previous run's rows
+    { float4* d = reinterpret_cast<float4*>(sc + lane*CROW); d[0] = p0; d[1] = p1; d[2] = p2; d[3] = p3; }
+    __syncwarp();
+    if (r + 1u < R) {
+      rec = __ldg(a.runs + rs + r + 1u);
+      if ((uint32_t)lane < rec.y) { const size_t c = (size_t)(rec.x + lane)*4; p0 = __ldg(frows4 + c); p1 = __ldg(frows4 + c + 1); p2 = __ldg(frows4 + c + 2); p3 = __ldg(frows4 + c + 3); }
+    }
+    // a candidate outside the lane's own 3^DIM stencil is a certain miss (every cell is at least one kernel extent wide);
+    // the error bands are derived for candidates inside it
     const bool near = active && abs(kx) <= 1 && abs(ky) <= 1 && abs(kz) <= 1;
-    float bse[DIM];
+    float bse[3];
     bse[0] = fmaf((float)kx, csf[0], reli[0]);
     bse[1] = fmaf((float)ky, csf[1], reli[1]);
-    if (DIM == 3) bse[2] = fmaf((float)kz, csf[2], reli[2]);
-    for (uint32_t j = jb; j < je; ++j) {
-      const float4* fj = reinterpret_cast<const float4*>(a.frows + (size_t)j*F::ROW);   // uniform address: broadcast
-      float rw[F::ROW];
-#pragma unroll
-      for (int q = 0; q < F::ROW/4; ++q) { const float4 v = __ldg(fj + q); rw[4*q] = v.x; rw[4*q + 1] = v.y; rw[4*q + 2] = v.z; rw[4*q + 3] = v.w; }
-      float r[DIM];
-#pragma unroll
-      for (int k = 0; k < DIM; ++k) r[k] = bse[k] - rw[k];
-      const float e2i = eta2_f32<DIM>(Hi, r);
-      const float e2j = eta2_f32<DIM>(rw + F::R_H, r);
-      const bool cand = near && (j != (uint32_t)i);
-      bool hit = cand && (e2i <= lo2i || e2j <= rw[F::R_LO]);
-      const bool amb = cand && !hit && !(e2i > hi2i && e2j > rw[F::R_HI]);
-      if (amb) hit = exact_pair<DIM>(a.rows, i, j, a.kext2);
-      word |= (hit ? 1u : 0u) << (t & 31u);
-      cnt += hit ? 1u : 0u;
-      ++t;
-      if ((t & 31u) == 0u) { mrow[(size_t)((t >> 5) - 1u)*SPHB200_TILE] = word; word = 0; }
+    bse[2] = (DIM == 3) ? fmaf((float)kz, csf[2], reli[2]) : 0.f;
+    uint32_t word = 0, upw = 0;
+#pragma unroll 4
+    for (uint32_t c = 0; c < len; ++c) {
+      const float4 q0 = *reinterpret_cast<const float4*>(sc + c*CROW);          // broadcast
+      const float4 q1 = *reinterpret_cast<const float4*>(sc + c*CROW + 4);
+      float rv[3];
+      rv[0] = bse[0] - q0.x; rv[1] = bse[1] - q0.y; rv[2] = bse[2] - q0.z;
+      const float r2 = (DIM == 3) ? fmaf(rv[2], rv[2], fmaf(rv[1], rv[1], rv[0]*rv[0])) : fmaf(rv[1], rv[1], rv[0]*rv[0]);
+      bool hit = r2 <= fmaxf(r2loi, q0.w);                                       // inside an inner sphere: certain
+      if (!hit && near && (r2 <= fmaxf(r2hii, q1.x)) && (jb + c != (uint32_t)i)) {   // inside an outer sphere: ask the ellipsoids
+        const float4 q2 = *reinterpret_cast<const float4*>(sc + c*CROW + 8), q3 = *reinterpret_cast<const float4*>(sc + c*CROW + 12);
+        float Hj[6];
+        if (DIM == 3) { Hj[0] = q2.x; Hj[1] = q2.y; Hj[2] = q2.z; Hj[3] = q2.w; Hj[4] = q3.x; Hj[5] = q3.y; }
+        else { Hj[0] = q2.x; Hj[1] = q2.y; Hj[2] = q2.z; }
+        const float e2i = eta2_f32<DIM>(Hi, rv), e2j = eta2_f32<DIM>(Hj, rv);
+        hit = (e2i <= e2loi) || (e2j <= q1.y);
+        if (!hit && !(e2i > e2hii && e2j > q1.z)) hit = exact_pair<DIM>(a.rows, i, (size_t)jb + c, a.kext2);
+      }
+      word |= (hit ? 1u : 0u) << c;
+      upw |= ((__float_as_uint(q1.w) > origi) ? 1u : 0u) << c;
     }
-  });
-  if (t & 31u) mrow[(size_t)(t >> 5)*SPHB200_TILE] = word;
+    // self and out-of-stencil candidates are never neighbours
+    if (!near) word = 0u;
+    else if ((uint32_t)i - jb < len) word &= ~(1u << ((uint32_t)i - jb));
+    mrow[(size_t)r*SPHB200_TILE] = word;
+    cnt += __popc(word);
+    hiCnt += __popc(upw & word);
+  }
 
   if (inRange) a.nbrCount[i] = cnt;
   uint32_t mx = cnt;
-  unsigned long long sAll = cnt;
+  unsigned long long sAll = cnt, sHi = hiCnt;
   for (int d = 16; d; d >>= 1) {
     mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
     sAll += __shfl_xor_sync(0xffffffffu, sAll, d);
+    sHi += __shfl_xor_sync(0xffffffffu, sHi, d);
   }
   if (lane == 0) {
     a.tileRows[tile] = mx;
     if (sAll) atomicAdd(&a.counters[1], sAll);
+    if (sHi) atomicAdd(&a.counters[0], sHi);
   }
 }
 
 template <int DIM>
 __global__ void __launch_bounds__(128) k_nbr_fill(NbrArgs a) {
-  size_t tile, i; int lane, ci[3]; bool inRange, active; uint32_t origi; unsigned leaders;
-  if (!tile_prologue<DIM>(a, tile, lane, i, inRange, active, origi, ci, leaders)) return;
+  const int lane = threadIdx.x & 31;
+  const size_t tile = (size_t)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tile*SPHB200_TILE >= a.n) return;
+  const uint32_t R = a.tileRunCount[tile];
+  const unsigned long long rs = a.tileRunStart[tile];
+  if (rs + R > a.runsCap || a.maskOff[tile + 1] > a.maskCap || a.tileOff[tile + 1] > a.nbrCap) return;
   const uint32_t* mrow = a.mask + a.maskOff[tile] + lane;
   uint32_t* out = a.nbr + a.tileOff[tile] + lane;
-  uint32_t cnt = 0, hi = 0, t = 0;
-  uint32_t candJ = 0, candO = 0;           // lane L holds candidate (32*w + L) of the current chunk
-  auto flush = [&](uint32_t w) {
-    uint32_t m = mrow[(size_t)w*SPHB200_TILE];
-    while (__any_sync(0xffffffffu, m != 0u)) {
-      const int b = m ? (__ffs(m) - 1) : 0;
-      const uint32_t j = __shfl_sync(0xffffffffu, candJ, b);
-      const uint32_t oj = __shfl_sync(0xffffffffu, candO, b);
-      if (m) {
-        const uint32_t up = (oj > origi) ? 1u : 0u;
-        out[(size_t)cnt*SPHB200_TILE] = j | (up << 31);
-        ++cnt; hi += up;
-        m &= m - 1u;
-      }
+  uint32_t cnt = 0;
+  uint32_t m = 0, jb = 0;
+  if (R) { m = mrow[0]; jb = __ldg(&a.runs[rs].x); }
+  for (uint32_t r = 0; r < R; ++r) {
+    uint32_t mn = 0, jbn = 0;
+    if (r + 1u < R) { mn = mrow[(size_t)(r + 1u)*SPHB200_TILE]; jbn = __ldg(&a.runs[rs + r + 1u].x); }   // in flight during the expansion
+    while (m) {
+      out[(size_t)cnt*SPHB200_TILE] = jb + (uint32_t)(__ffs(m) - 1);
+      m &= m - 1u;
+      ++cnt;
     }
-  };
-  walk_cells<DIM>(a.g, a.cellStart, leaders, ci, [&](uint32_t jb, uint32_t je, int, int, int) {
-    uint32_t j = jb;
-    while (j < je) {
-      const uint32_t pos = t & 31u;                         // first free lane of the chunk
-      const uint32_t take = min(32u - pos, je - j);
-      if ((uint32_t)lane >= pos && (uint32_t)lane < pos + take) { candJ = j + ((uint32_t)lane - pos); candO = a.perm[candJ]; }
-      j += take; t += take;
-      if ((t & 31u) == 0u) flush((t >> 5) - 1u);
-    }
-  });
-  if (t & 31u) flush(t >> 5);
-  unsigned long long sHi = hi;
-  for (int d = 16; d; d >>= 1) sHi += __shfl_xor_sync(0xffffffffu, sHi, d);
-  if (lane == 0 && sHi) atomicAdd(&a.counters[0], sHi);
+    m = mn; jb = jbn;
+  }
+}
+
+// dilated (Morton) coordinate tables: dilTab[axis*SPHB200_DIL + c] = bits of c spread to the axis' key positions
+__global__ void __launch_bounds__(RB) k_dilate_table(GridDev g, uint32_t* __restrict__ tab) {
+  const int c = blockIdx.x*RB + threadIdx.x;
+  const int axis = blockIdx.y;
+  if (c < g.nc[axis]) tab[axis*SPHB200_DIL + c] = dilate(g, axis, c);
 }
 
 }  // namespace
@@ -407,6 +513,7 @@ template <typename T> int sphb200_ensure(sphb200_ctx* c, T*& p, size_t& cap, siz
 template int sphb200_ensure<uint32_t>(sphb200_ctx*, uint32_t*&, size_t&, size_t);
 template int sphb200_ensure<double>(sphb200_ctx*, double*&, size_t&, size_t);
 template int sphb200_ensure<float>(sphb200_ctx*, float*&, size_t&, size_t);
+template int sphb200_ensure<uint4>(sphb200_ctx*, uint4*&, size_t&, size_t);
 
 static int build_grid(sphb200_ctx* c, const double* bb /*lo3 hi3 ext3*/) {
   GridDev& g = c->grid;
@@ -470,7 +577,7 @@ int sphb200_pack_rows(sphb200_ctx* c) {
   a.auxDvDxQ = needQ ? c->auxDvDxQ : nullptr; a.auxfCl = mult ? c->auxfCl : nullptr; a.auxfCq = mult ? c->auxfCq : nullptr;
   a.perm = c->perm; a.keyApi = c->cellKeyApi; a.skey = c->skey; a.n = c->n;
   { size_t fcap = c->frows ? c->frowsCap : 0;
-    if (sphb200_ensure(c, c->frows, fcap, c->cap*(size_t)(c->ndim == 3 ? 12 : 8))) return 1;
+    if (sphb200_ensure(c, c->frows, fcap, c->cap*(size_t)Fr::ROW)) return 1;
     c->frowsCap = fcap; }
   a.frows = c->frows; a.g = c->grid;
   a.kext = std::max(c->W.kext, c->WQ.set ? c->WQ.kext : 0.0);
@@ -506,8 +613,13 @@ int sphb200_sort_and_pack(sphb200_ctx* c) {
   if (sphb200_ensure(c, c->cellCursor, c->cellCursorCap, tbl)) return 1;
   CU_CHECK(c, cudaMemsetAsync(c->cellStart, 0, tbl*sizeof(uint32_t), c->stream));
   const unsigned nb = (unsigned)((n + RB - 1)/RB);
-  if (c->ndim == 3) k_cell_count<3><<<nb, RB, 0, c->stream>>>(c->api[S_POS], n, c->grid, c->cellKeyApi, c->cellStart);
-  else              k_cell_count<2><<<nb, RB, 0, c->stream>>>(c->api[S_POS], n, c->grid, c->cellKeyApi, c->cellStart);
+  {
+    int ncmax = std::max(c->grid.nc[0], std::max(c->grid.nc[1], c->grid.nc[2]));
+    k_dilate_table<<<dim3((unsigned)((ncmax + RB - 1)/RB), (unsigned)c->ndim), RB, 0, c->stream>>>(c->grid, c->dilTab);
+    KERNEL_CHECK(c, "k_dilate_table");
+  }
+  if (c->ndim == 3) k_cell_count<3><<<nb, RB, 0, c->stream>>>(c->api[S_POS], n, c->grid, c->dilTab, c->cellKeyApi, c->cellStart);
+  else              k_cell_count<2><<<nb, RB, 0, c->stream>>>(c->api[S_POS], n, c->grid, c->dilTab, c->cellKeyApi, c->cellStart);
   KERNEL_CHECK(c, "k_cell_count");
   if (sphb200_scan_u32(c, c->cellStart, c->cellStart, c->grid.tableSize)) return 1;
   CU_CHECK(c, cudaMemcpyAsync(c->cellCursor, c->cellStart, (size_t)c->grid.tableSize*sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
@@ -522,41 +634,52 @@ int sphb200_sort_and_pack(sphb200_ctx* c) {
 int sphb200_neighbors(sphb200_ctx* c) {
   const size_t n = c->n;
   c->nTiles = (n + SPHB200_TILE - 1)/SPHB200_TILE;
-  NbrArgs a{};
-  a.rows = c->rows; a.frows = c->frows; a.perm = c->perm; a.skey = c->skey; a.cellStart = c->cellStart;
-  a.n = n; a.nInt = (uint32_t)c->nInt;
   const double kext = std::max(c->W.kext, c->WQ.set ? c->WQ.kext : 0.0);
-  a.kext2 = kext*kext; a.g = c->grid;
-  a.nbrCount = c->nbrCount; a.tileRows = c->tileRows; a.tileOff = c->tileOff; a.nbr = nullptr; a.counters = c->counters;
-  a.tileWords = c->tileWords; a.maskOff = c->maskOff; a.mask = nullptr;
-  CU_CHECK(c, cudaMemsetAsync(c->counters, 0, 2*sizeof(unsigned long long), c->stream));
   const int wpb = 4;
   const unsigned nb = (unsigned)((c->nTiles + wpb - 1)/wpb);
-  // 1. candidates per tile -> hit-mask offsets
-  if (c->ndim == 3) k_nbr_count_candidates<3><<<nb, wpb*32, 0, c->stream>>>(a); else k_nbr_count_candidates<2><<<nb, wpb*32, 0, c->stream>>>(a);
-  KERNEL_CHECK(c, "k_nbr_count_candidates");
-  if (sphb200_scan_tiles(c, c->tileWords, c->maskOff, c->nTiles)) return 1;
-  CU_CHECK(c, cudaMemcpyAsync(c->countersHost + 3, c->maskOff + c->nTiles, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-  CU_CHECK(c, cudaStreamSynchronize(c->stream));
-  if (sphb200_ensure(c, c->mask, c->maskCap, (size_t)c->countersHost[3] + 32)) return 1;
-  a.mask = c->mask;
-  // 2. the predicate, once per (node, candidate)
-  if (c->ndim == 3) k_nbr_test<3><<<nb, wpb*32, 0, c->stream>>>(a); else k_nbr_test<2><<<nb, wpb*32, 0, c->stream>>>(a);
-  KERNEL_CHECK(c, "k_nbr_test");
-  if (sphb200_scan_tiles(c, c->tileRows, c->tileOff, c->nTiles)) return 1;
-  CU_CHECK(c, cudaMemcpyAsync(c->countersHost + 2, c->tileOff + c->nTiles, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-  CU_CHECK(c, cudaStreamSynchronize(c->stream));
-  c->nSlots = (size_t)c->countersHost[2];
-  if (sphb200_ensure(c, c->nbr, c->nbrCap, c->nSlots + 32)) return 1;
-  a.nbr = c->nbr;
-  // 3. expand the masks into the sliced-ELL lists
-  if (c->ndim == 3) k_nbr_fill<3><<<nb, wpb*32, 0, c->stream>>>(a); else k_nbr_fill<2><<<nb, wpb*32, 0, c->stream>>>(a);
-  KERNEL_CHECK(c, "k_nbr_fill");
-  CU_CHECK(c, cudaMemcpyAsync(c->countersHost, c->counters, 2*sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-  CU_CHECK(c, cudaStreamSynchronize(c->stream));
-  c->npairs = (size_t)c->countersHost[0];
-  c->nEdges = (size_t)c->countersHost[1];
-  c->pairsValid = true;
-  c->stats.directed_edges = c->nEdges;
-  return 0;
+  // first guesses for the variable-size buffers; afterwards the capacities of the previous build are reused
+  if (!c->runs && sphb200_ensure(c, c->runs, c->runsCap, c->nTiles*72 + 1024)) return 1;
+  if (!c->mask && sphb200_ensure(c, c->mask, c->maskCap, c->nTiles*(size_t)(c->ndim == 3 ? 72 : 20)*32 + 1024)) return 1;
+  if (!c->nbr && sphb200_ensure(c, c->nbr, c->nbrCap, n*(size_t)(c->ndim == 3 ? 150 : 60) + 1024)) return 1;
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    NbrArgs a{};
+    a.rows = c->rows; a.frows = c->frows; a.perm = c->perm; a.skey = c->skey; a.cellStart = c->cellStart; a.dilTab = c->dilTab;
+    a.n = n; a.nInt = (uint32_t)c->nInt; a.kext2 = kext*kext; a.g = c->grid;
+    a.nbrCount = c->nbrCount; a.tileRows = c->tileRows; a.tileOff = c->tileOff; a.nbr = c->nbr; a.nbrCap = c->nbrCap;
+    a.tileWords = c->tileWords; a.maskOff = c->maskOff; a.mask = c->mask; a.maskCap = c->maskCap;
+    a.runs = c->runs; a.runsCap = c->runsCap; a.tileRunStart = c->tileRunStart; a.tileRunCount = c->tileRunCount;
+    a.counters = c->counters;
+    CU_CHECK(c, cudaMemsetAsync(c->counters, 0, 4*sizeof(unsigned long long), c->stream));
+    // 1. candidate runs per tile -> hit-mask offsets
+    if (c->ndim == 3) k_tile_runs<3><<<nb, wpb*32, 0, c->stream>>>(a); else k_tile_runs<2><<<nb, wpb*32, 0, c->stream>>>(a);
+    KERNEL_CHECK(c, "k_tile_runs");
+    if (sphb200_scan_tiles(c, c->tileWords, c->maskOff, c->nTiles)) return 1;
+    // 2. the predicate, once per (node, candidate)
+    if (c->ndim == 3) k_nbr_test<3><<<nb, wpb*32, 0, c->stream>>>(a); else k_nbr_test<2><<<nb, wpb*32, 0, c->stream>>>(a);
+    KERNEL_CHECK(c, "k_nbr_test");
+    if (sphb200_scan_tiles(c, c->tileRows, c->tileOff, c->nTiles)) return 1;
+    // 3. expand the masks into the sliced-ELL lists
+    if (c->ndim == 3) k_nbr_fill<3><<<nb, wpb*32, 0, c->stream>>>(a); else k_nbr_fill<2><<<nb, wpb*32, 0, c->stream>>>(a);
+    KERNEL_CHECK(c, "k_nbr_fill");
+    // one host round trip: totals and capacity check
+    CU_CHECK(c, cudaMemcpyAsync(c->countersHost, c->counters, 3*sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(c, cudaMemcpyAsync(c->countersHost + 3, c->maskOff + c->nTiles, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(c, cudaMemcpyAsync(c->countersHost + 4, c->tileOff + c->nTiles, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    const size_t needRuns = (size_t)c->countersHost[2], needMask = (size_t)c->countersHost[3], needNbr = (size_t)c->countersHost[4];
+    const bool okRuns = needRuns <= c->runsCap, okMask = needMask <= c->maskCap;
+    const bool okNbr = okRuns && okMask && needNbr <= c->nbrCap;     // the list size is only known once the test ran everywhere
+    if (okRuns && okMask && okNbr) {
+      c->npairs = (size_t)c->countersHost[0];
+      c->nEdges = (size_t)c->countersHost[1];
+      c->nSlots = needNbr;
+      c->pairsValid = true;
+      c->stats.directed_edges = c->nEdges;
+      return 0;
+    }
+    if (!okRuns && sphb200_ensure(c, c->runs, c->runsCap, needRuns + needRuns/8)) return 1;
+    if (!okMask && sphb200_ensure(c, c->mask, c->maskCap, needMask + needMask/8)) return 1;
+    if (okRuns && okMask && !okNbr && sphb200_ensure(c, c->nbr, c->nbrCap, needNbr + needNbr/8)) return 1;
+  }
+  return sphb200_fail(c, "build_pairs: neighbour buffers failed to converge");
 }

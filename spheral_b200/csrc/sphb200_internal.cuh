@@ -8,7 +8,7 @@
 //                   2-D: x y vx vy Hxx Hxy Hyy m rho Prho cs (pad)
 //                Prho = safeInv(omega)*P/(rho*rho) (SPH.cc:310,425 with epsTensile == 0) is folded per node.
 //   nbr        : neighbour lists of internal nodes, sliced-ELL: tile t = sorted slots [32t,32t+32),
-//                entry k of lane l at nbr[tileOff[t] + 32*k + l]; bit31 = "original index of j > original index of i".
+//                entry k of lane l at nbr[tileOff[t] + 32*k + l] = sorted slot of the neighbour.
 //   d_*        : derivative fields, SoA per component, sorted order.
 //   pacc       : deltaDvDt of every directed edge, blocked like nbr: component c of edge `slot` at pacc_index<DIM>(slot, c)
 //                = DIM*(slot & ~31) + 32*c + (slot & 31), i.e. one 32-lane line per (list row, component).
@@ -20,6 +20,7 @@
 #include "sphb200.h"
 
 #define SPHB200_TILE 32
+#define SPHB200_DIL 32768          /* entries per axis of the dilated-coordinate table (max cells per axis) */
 
 enum StateSlot { S_POS = 0, S_VEL, S_H, S_MASS, S_RHO, S_EPS, S_P, S_CS, S_OMEGA, S_DVDXQ, S_FCL, S_FCQ, S_COUNT };
 enum DerivSlot { DV_DXDT = 0, DV_DRHODT, DV_DVDT, DV_DEPSDT, DV_DVDX, DV_LOCALDVDX, DV_GRADRHO, DV_M, DV_LOCALM,
@@ -78,6 +79,7 @@ struct sphb200_ctx {
 
   // grid + sort
   GridDev grid{};
+  uint32_t* dilTab = nullptr;       // 3*SPHB200_DIL dilated cell coordinates
   uint32_t* cellKeyApi = nullptr;   // key per node, original order
   uint32_t* cellStart = nullptr;    // tableSize+1
   uint32_t* cellCursor = nullptr;
@@ -103,10 +105,13 @@ struct sphb200_ctx {
   uint32_t* tileRows = nullptr;     // per tile: max count
   unsigned long long* tileOff = nullptr;  // nTiles+1, in entries
   uint32_t* nbr = nullptr; size_t nbrCap = 0;
+  uint4* runs = nullptr; size_t runsCap = 0;   // candidate runs of all tiles: {first sorted slot, length, sx|sy<<16, sz}
+  uint32_t* tileRunStart = nullptr; // per tile: first run
+  uint32_t* tileRunCount = nullptr; // per tile: number of runs
   uint32_t* tileWords = nullptr;    // per tile: 32-candidate words of the hit mask
   unsigned long long* maskOff = nullptr;
   uint32_t* mask = nullptr; size_t maskCap = 0;
-  unsigned long long* counters = nullptr; // [0]=npairs [1]=directed edges
+  unsigned long long* counters = nullptr; // [0]=npairs [1]=directed edges [2]=run cursor
   unsigned long long* countersHost = nullptr; // pinned
   size_t npairs = 0, nEdges = 0, nSlots = 0;
   bool pairsValid = false;
