@@ -150,7 +150,7 @@ int sphb200_create(sphb200_ctx** out, int device, const sphb200_options* opts) {
   for (auto& ev : c->ev) cudaEventCreate(&ev);
   cudaMalloc((void**)&c->reduceBuf, (296*9 + 16)*sizeof(double));
   cudaMallocHost((void**)&c->reduceHost, 16*sizeof(double));
-  cudaMalloc((void**)&c->counters, 4*sizeof(unsigned long long));
+  cudaMalloc((void**)&c->counters, 8*sizeof(unsigned long long));
   cudaMalloc((void**)&c->dilTab, 3*SPHB200_DIL*sizeof(uint32_t));
   cudaMallocHost((void**)&c->countersHost, 8*sizeof(unsigned long long));
   if (cudaGetLastError() != cudaSuccess) { sphb200_destroy(c); return sphb200_fail(nullptr, "context allocation failed"); }

@@ -227,24 +227,23 @@ __global__ void __launch_bounds__(RB) k_pack(PackArgs a) {
 // union of the 3^DIM cell stencils of the distinct cells its nodes live in, visited in a fixed order, so every candidate j
 // is fetched once per tile and tested by all lanes.
 //   k_tile_runs : integer walk over the stencils; emits the tile's candidate runs (<= 32 consecutive sorted slots of one
-//                 cell: first slot, length, cell coordinates).  A run owns one 32-bit word per lane of the tile's hit mask.
-//   k_nbr_test  : the predicate, once per (i, candidate).  The 64-byte FP32 rows of a run are loaded coalesced (one lane
-//                 per candidate, one run ahead) and broadcast through shared memory.  Stage 1 is |r|^2 against the nodes'
-//                 inner and outer spheres (decisive for isotropic H); stage 2 the FP32 ellipsoid test with a rigorous error
-//                 band; the rare in-band cases are decided by the exact FP64 evaluation (reference operation order, no
-//                 FMA).  Emits one hit word per (lane, run); also counts the pairs (neighbours with a larger original index).
-//   k_nbr_fill  : expands the words into the sliced-ELL lists.
-// All three are launched back to back without a host round trip: buffer capacities come from the previous build and a
-// kernel that would overflow one skips its tile; the host checks the totals once at the end and redoes the build with
-// larger buffers if needed.
+//                 cell: first slot, length, cell coordinates)
+//   k_nbr_build : the predicate, once per (i, candidate), and the lists.  The 64-byte FP32 rows of a run are loaded
+//                 coalesced (one lane per candidate, one run ahead) and broadcast through shared memory.  Stage 1 is |r|^2
+//                 against the nodes' inner and outer spheres (decisive for isotropic H); stage 2 the FP32 ellipsoid test
+//                 with a rigorous error band; the rare in-band cases are decided by the exact FP64 evaluation (reference
+//                 operation order, no FMA).  Hits are appended to the lane's column of a shared-memory list, the tile's
+//                 block of the sliced-ELL array is allocated with one atomic and written as whole 128-byte rows.
+// Both are launched back to back without a host round trip: buffer capacities come from the previous build and a kernel
+// that would overflow one skips its tile; the host checks the totals once at the end and redoes the build with larger
+// buffers if needed.
 struct NbrArgs {
   const double* rows; const float* frows; const uint32_t* perm; const uint32_t* skey; const uint32_t* cellStart;
   const uint32_t* dilTab;
   size_t n; uint32_t nInt; double kext2; GridDev g;
-  uint32_t* nbrCount; uint32_t* tileRows; const unsigned long long* tileOff; uint32_t* nbr; unsigned long long nbrCap;
-  uint32_t* tileWords; const unsigned long long* maskOff; uint32_t* mask; unsigned long long maskCap;
+  uint32_t* nbrCount; uint32_t* tileRows; unsigned long long* tileOff; uint32_t* nbr; unsigned long long nbrCap;
   uint4* runs; unsigned long long runsCap; uint32_t* tileRunStart; uint32_t* tileRunCount;
-  unsigned long long* counters;      // [0] npairs  [1] directed edges  [2] run cursor
+  unsigned long long* counters;      // [0] hits on ghost candidates  [1] directed edges  [2] run cursor  [3] list cursor  [4] longest list
 };
 
 // Per-warp candidate walk: calls f(jb, je, sx, sy, sz) for every non-empty stencil cell, warp-uniformly.
@@ -336,7 +335,7 @@ __global__ void __launch_bounds__(128) k_tile_runs(NbrArgs a) {
   unsigned long long start = 0;
   if (lane == 0) start = atomicAdd(&a.counters[2], (unsigned long long)Rtot);
   start = __shfl_sync(0xffffffffu, start, 0);
-  if (lane == 0) { a.tileRunStart[tile] = (uint32_t)start; a.tileRunCount[tile] = Rtot; a.tileWords[tile] = Rtot; }
+  if (lane == 0) { a.tileRunStart[tile] = (uint32_t)start; a.tileRunCount[tile] = Rtot; }
   if (start + Rtot > a.runsCap) return;              // the host sees the cursor past the capacity and redoes the build
   for (uint32_t k = lane; k < min(Rtot, (uint32_t)RUN_CAP); k += 32) a.runs[start + k] = sruns[w][k];
   if (Rtot > RUN_CAP) {                              // rare: very ragged tile, walk again for the tail
@@ -372,17 +371,29 @@ template <int DIM> __device__ __forceinline__ float eta2_f32(const float* H, con
 }
 
 constexpr int CROW = 20;             // floats per candidate row in shared memory (16 + 4 pad: conflict-free 128-bit stores)
+constexpr int NB_WARPS = 4;          // warps (tiles) per CTA of k_nbr_build
+constexpr int JB_CAP = 128;          // runs per tile whose first slot is cached in shared memory for the flush
 
+// Shared memory of k_nbr_build per warp: candidate rows of the current run (32*CROW floats), first slots of the runs
+// (JB_CAP words) and the list under construction, `listRows` rows x 32 lanes of 16-bit codes (run << 5 | candidate).
+// The lists are assembled [row][lane] (conflict-free for any per-lane row) and written out as whole 128-byte rows; a
+// lane-private 4-byte global store per hit would cost a 32-byte L2 sector transaction each (profiles/r01_notes.md).
 template <int DIM>
-__global__ void __launch_bounds__(128) k_nbr_test(NbrArgs a) {
-  __shared__ __align__(16) float scand[4][32*CROW];
+__global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build(NbrArgs a, int listRows) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const int w = threadIdx.x >> 5;
+  const size_t perWarp = (size_t)32*CROW*4 + (size_t)JB_CAP*4 + (size_t)listRows*64;
+  float* const sc = reinterpret_cast<float*>(smemRaw + w*perWarp);
+  uint32_t* const sjb = reinterpret_cast<uint32_t*>(sc + 32*CROW);
+  unsigned short* const slist = reinterpret_cast<unsigned short*>(sjb + JB_CAP);
+
   size_t tile, i; int lane, ci[3]; bool inRange, active; uint32_t origi;
   if (!tile_prologue<DIM>(a, tile, lane, i, inRange, active, origi, ci)) return;
   const uint32_t R = a.tileRunCount[tile];
   const unsigned long long rs = a.tileRunStart[tile];
-  if (rs + R > a.runsCap || a.maskOff[tile + 1] > a.maskCap) {       // capacity miss: leave a consistent, empty tile
+  if (rs + R > a.runsCap) {                        // capacity miss: leave a consistent, empty tile; the host redoes the build
     if (inRange) a.nbrCount[i] = 0;
-    if (lane == 0) a.tileRows[tile] = 0;
+    if (lane == 0) { a.tileRows[tile] = 0; a.tileOff[tile] = 0; }
     return;
   }
   float reli[3] = {0.f, 0.f, 0.f}, Hi[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, r2loi = -1.f, r2hii = 0.f, e2loi = 0.f, e2hii = 0.f;
@@ -395,98 +406,107 @@ __global__ void __launch_bounds__(128) k_nbr_test(NbrArgs a) {
     else { Hi[0] = q2.x; Hi[1] = q2.y; Hi[2] = q2.z; }
   }
   const float csf[3] = {(float)a.g.cs[0], (float)a.g.cs[1], (float)a.g.cs[2]};
-  float* const sc = scand[threadIdx.x >> 5];
-  uint32_t cnt = 0, hiCnt = 0;                     // neighbours; neighbours with a larger original index (= pairs owned by i)
-  uint32_t* mrow = a.mask + a.maskOff[tile] + lane;
+  uint32_t cnt = 0, ghostHits = 0;
+  unsigned short* lp = slist + lane;               // next free entry of this lane's column
+  unsigned short* const lend = slist + (size_t)listRows*32;
 
   // software pipeline: the rows of run r+1 travel to registers while run r is tested out of shared memory
+  const float4 FAR0 = make_float4(-1.0e30f, 0.f, 0.f, -1.f), FAR1 = make_float4(-1.f, 0.f, 0.f, 0.f);   // padding candidate: at infinity
   uint4 rec = (R > 0u) ? __ldg(a.runs + rs) : make_uint4(0u, 0u, 0u, 0u);
-  float4 p0, p1, p2, p3;
-  p0 = p1 = p2 = p3 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 p0 = FAR0, p1 = FAR1, p2 = FAR1, p3 = FAR1;
   if ((uint32_t)lane < rec.y) { const size_t c = (size_t)(rec.x + lane)*4; p0 = __ldg(frows4 + c); p1 = __ldg(frows4 + c + 1); p2 = __ldg(frows4 + c + 2); p3 = __ldg(frows4 + c + 3); }
   for (uint32_t r = 0; r < R; ++r) {
     const uint32_t jb = rec.x, len = rec.y;
     const int kx = ci[0] - (int)(rec.z & 0xffffu), ky = ci[1] - (int)(rec.z >> 16), kz = (DIM == 3) ? ci[2] - (int)rec.w : 0;
     __syncwarp();                                                   // every lane is done with the previous run's rows
     { float4* d = reinterpret_cast<float4*>(sc + lane*CROW); d[0] = p0; d[1] = p1; d[2] = p2; d[3] = p3; }
+    if (lane == 0 && r < (uint32_t)JB_CAP) sjb[r] = jb;
+    // ghost candidates of the run (original index >= nInt): a hit on one of them is a pair counted once, not twice
+    const unsigned ghostWord = __ballot_sync(0xffffffffu, (uint32_t)lane < len && __float_as_uint(p1.w) >= a.nInt);
     __syncwarp();
+    p0 = FAR0; p1 = FAR1; p2 = FAR1; p3 = FAR1;
     if (r + 1u < R) {
       rec = __ldg(a.runs + rs + r + 1u);
       if ((uint32_t)lane < rec.y) { const size_t c = (size_t)(rec.x + lane)*4; p0 = __ldg(frows4 + c); p1 = __ldg(frows4 + c + 1); p2 = __ldg(frows4 + c + 2); p3 = __ldg(frows4 + c + 3); }
     }
-    // a candidate outside the lane's own 3^DIM stencil is a certain miss (every cell is at least one kernel extent wide);
-    // the error bands are derived for candidates inside it
+    // A candidate outside the lane's own 3^DIM stencil is a certain miss (every cell is at least one kernel extent wide)
+    // and the error bands are derived for candidates inside it: such lanes (and ghost / padding lanes) see the run at infinity.
     const bool near = active && abs(kx) <= 1 && abs(ky) <= 1 && abs(kz) <= 1;
     float bse[3];
-    bse[0] = fmaf((float)kx, csf[0], reli[0]);
+    bse[0] = near ? fmaf((float)kx, csf[0], reli[0]) : 1.0e30f;
     bse[1] = fmaf((float)ky, csf[1], reli[1]);
     bse[2] = (DIM == 3) ? fmaf((float)kz, csf[2], reli[2]) : 0.f;
-    uint32_t word = 0, upw = 0;
-#pragma unroll 4
-    for (uint32_t c = 0; c < len; ++c) {
-      const float4 q0 = *reinterpret_cast<const float4*>(sc + c*CROW);          // broadcast
-      const float4 q1 = *reinterpret_cast<const float4*>(sc + c*CROW + 4);
-      float rv[3];
-      rv[0] = bse[0] - q0.x; rv[1] = bse[1] - q0.y; rv[2] = bse[2] - q0.z;
-      const float r2 = (DIM == 3) ? fmaf(rv[2], rv[2], fmaf(rv[1], rv[1], rv[0]*rv[0])) : fmaf(rv[1], rv[1], rv[0]*rv[0]);
-      bool hit = r2 <= fmaxf(r2loi, q0.w);                                       // inside an inner sphere: certain
-      if (!hit && near && (r2 <= fmaxf(r2hii, q1.x)) && (jb + c != (uint32_t)i)) {   // inside an outer sphere: ask the ellipsoids
+
+    // stage 1, branch-free: |r|^2 against the inner spheres (certain hit) and the outer spheres (possible hit).  Rows past
+    // the end of the run are padding candidates at infinity, so the loop runs in groups of four.
+    uint32_t hitWord = 0, inWord = 0;
+    for (uint32_t c4 = 0; c4 < len; c4 += 4u) {
+      uint32_t hn = 0, in = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 q0 = *reinterpret_cast<const float4*>(sc + (c4 + u)*CROW);          // broadcast
+        const float4 q1 = *reinterpret_cast<const float4*>(sc + (c4 + u)*CROW + 4);
+        const float rx = bse[0] - q0.x, ry = bse[1] - q0.y, rz = bse[2] - q0.z;
+        const float r2 = (DIM == 3) ? fmaf(rz, rz, fmaf(ry, ry, rx*rx)) : fmaf(ry, ry, rx*rx);
+        if (r2 <= fmaxf(r2loi, q0.w)) hn |= 1u << u;
+        if (r2 <= fmaxf(r2hii, q1.x)) in |= 1u << u;
+      }
+      hitWord |= hn << c4; inWord |= in << c4;
+    }
+    // stage 2: candidates inside an outer sphere but no inner one ask the ellipsoids (FP32 with error band, else exact)
+    uint32_t amb = inWord & ~hitWord;
+    for (unsigned au = __reduce_or_sync(0xffffffffu, amb); au; au &= au - 1u) {
+      const uint32_t c = (uint32_t)(__ffs(au) - 1);
+      if ((amb >> c) & 1u) {
+        const float4 q0 = *reinterpret_cast<const float4*>(sc + c*CROW), q1 = *reinterpret_cast<const float4*>(sc + c*CROW + 4);
         const float4 q2 = *reinterpret_cast<const float4*>(sc + c*CROW + 8), q3 = *reinterpret_cast<const float4*>(sc + c*CROW + 12);
-        float Hj[6];
+        float rv[3], Hj[6];
+        rv[0] = bse[0] - q0.x; rv[1] = bse[1] - q0.y; rv[2] = bse[2] - q0.z;
         if (DIM == 3) { Hj[0] = q2.x; Hj[1] = q2.y; Hj[2] = q2.z; Hj[3] = q2.w; Hj[4] = q3.x; Hj[5] = q3.y; }
         else { Hj[0] = q2.x; Hj[1] = q2.y; Hj[2] = q2.z; }
         const float e2i = eta2_f32<DIM>(Hi, rv), e2j = eta2_f32<DIM>(Hj, rv);
-        hit = (e2i <= e2loi) || (e2j <= q1.y);
+        bool hit = (e2i <= e2loi) || (e2j <= q1.y);
         if (!hit && !(e2i > e2hii && e2j > q1.z)) hit = exact_pair<DIM>(a.rows, i, (size_t)jb + c, a.kext2);
+        if (hit) hitWord |= 1u << c;
       }
-      word |= (hit ? 1u : 0u) << c;
-      upw |= ((__float_as_uint(q1.w) > origi) ? 1u : 0u) << c;
     }
-    // self and out-of-stencil candidates are never neighbours
-    if (!near) word = 0u;
-    else if ((uint32_t)i - jb < len) word &= ~(1u << ((uint32_t)i - jb));
-    mrow[(size_t)r*SPHB200_TILE] = word;
-    cnt += __popc(word);
-    hiCnt += __popc(upw & word);
+    const uint32_t self = (uint32_t)i - jb;                        // this node's own position in the run, if any
+    if (self < len) hitWord &= ~(1u << self);
+    cnt += __popc(hitWord);
+    ghostHits += __popc(hitWord & ghostWord);
+    // append the hits to this lane's column of the list
+    for (uint32_t m = hitWord; m; m &= m - 1u) {
+      if (lp < lend) *lp = (unsigned short)((r << 5) | (uint32_t)(__ffs(m) - 1));
+      lp += 32;
+    }
   }
 
   if (inRange) a.nbrCount[i] = cnt;
   uint32_t mx = cnt;
-  unsigned long long sAll = cnt, sHi = hiCnt;
+  unsigned long long sAll = cnt, sGhost = ghostHits;
   for (int d = 16; d; d >>= 1) {
     mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
     sAll += __shfl_xor_sync(0xffffffffu, sAll, d);
-    sHi += __shfl_xor_sync(0xffffffffu, sHi, d);
+    sGhost += __shfl_xor_sync(0xffffffffu, sGhost, d);
   }
+  // allocate the tile's block of the sliced-ELL array (placement order is irrelevant; the content is deterministic)
+  unsigned long long off = 0;
   if (lane == 0) {
-    a.tileRows[tile] = mx;
+    off = atomicAdd(&a.counters[3], (unsigned long long)mx*SPHB200_TILE);
+    a.tileRows[tile] = mx; a.tileOff[tile] = off;
     if (sAll) atomicAdd(&a.counters[1], sAll);
-    if (sHi) atomicAdd(&a.counters[0], sHi);
+    if (sGhost) atomicAdd(&a.counters[0], sGhost);
+    atomicMax(&a.counters[4], (unsigned long long)mx);          // longest list: sizes the staging (too small -> host redoes)
   }
-}
-
-template <int DIM>
-__global__ void __launch_bounds__(128) k_nbr_fill(NbrArgs a) {
-  const int lane = threadIdx.x & 31;
-  const size_t tile = (size_t)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (tile*SPHB200_TILE >= a.n) return;
-  const uint32_t R = a.tileRunCount[tile];
-  const unsigned long long rs = a.tileRunStart[tile];
-  if (rs + R > a.runsCap || a.maskOff[tile + 1] > a.maskCap || a.tileOff[tile + 1] > a.nbrCap) return;
-  const uint32_t* mrow = a.mask + a.maskOff[tile] + lane;
-  uint32_t* out = a.nbr + a.tileOff[tile] + lane;
-  uint32_t cnt = 0;
-  uint32_t m = 0, jb = 0;
-  if (R) { m = mrow[0]; jb = __ldg(&a.runs[rs].x); }
-  for (uint32_t r = 0; r < R; ++r) {
-    uint32_t mn = 0, jbn = 0;
-    if (r + 1u < R) { mn = mrow[(size_t)(r + 1u)*SPHB200_TILE]; jbn = __ldg(&a.runs[rs + r + 1u].x); }   // in flight during the expansion
-    while (m) {
-      out[(size_t)cnt*SPHB200_TILE] = jb + (uint32_t)(__ffs(m) - 1);
-      m &= m - 1u;
-      ++cnt;
-    }
-    m = mn; jb = jbn;
+  off = __shfl_sync(0xffffffffu, off, 0);
+  if (off + (unsigned long long)mx*SPHB200_TILE > a.nbrCap || mx > (uint32_t)listRows) return;
+  __syncwarp();
+  uint32_t* out = a.nbr + off + lane;
+  for (uint32_t k = 0; k < mx; ++k) {
+    const uint32_t code = slist[k*32u + lane];
+    const uint32_t rr = code >> 5;
+    const uint32_t jb = (rr < (uint32_t)JB_CAP) ? sjb[rr] : __ldg(&a.runs[rs + rr].x);
+    out[(size_t)k*SPHB200_TILE] = (k < cnt) ? jb + (code & 31u) : 0u;        // padding entries point at slot 0 (never used)
   }
 }
 
@@ -635,51 +655,57 @@ int sphb200_neighbors(sphb200_ctx* c) {
   const size_t n = c->n;
   c->nTiles = (n + SPHB200_TILE - 1)/SPHB200_TILE;
   const double kext = std::max(c->W.kext, c->WQ.set ? c->WQ.kext : 0.0);
-  const int wpb = 4;
-  const unsigned nb = (unsigned)((c->nTiles + wpb - 1)/wpb);
+  const unsigned nb = (unsigned)((c->nTiles + 3)/4);
   // first guesses for the variable-size buffers; afterwards the capacities of the previous build are reused
   if (!c->runs && sphb200_ensure(c, c->runs, c->runsCap, c->nTiles*72 + 1024)) return 1;
-  if (!c->mask && sphb200_ensure(c, c->mask, c->maskCap, c->nTiles*(size_t)(c->ndim == 3 ? 72 : 20)*32 + 1024)) return 1;
   if (!c->nbr && sphb200_ensure(c, c->nbr, c->nbrCap, n*(size_t)(c->ndim == 3 ? 150 : 60) + 1024)) return 1;
-  for (int attempt = 0; attempt < 4; ++attempt) {
+  if (c->listRows <= 0) c->listRows = (c->ndim == 3) ? 192 : 96;
+  for (int attempt = 0; attempt < 5; ++attempt) {
     NbrArgs a{};
     a.rows = c->rows; a.frows = c->frows; a.perm = c->perm; a.skey = c->skey; a.cellStart = c->cellStart; a.dilTab = c->dilTab;
     a.n = n; a.nInt = (uint32_t)c->nInt; a.kext2 = kext*kext; a.g = c->grid;
     a.nbrCount = c->nbrCount; a.tileRows = c->tileRows; a.tileOff = c->tileOff; a.nbr = c->nbr; a.nbrCap = c->nbrCap;
-    a.tileWords = c->tileWords; a.maskOff = c->maskOff; a.mask = c->mask; a.maskCap = c->maskCap;
     a.runs = c->runs; a.runsCap = c->runsCap; a.tileRunStart = c->tileRunStart; a.tileRunCount = c->tileRunCount;
     a.counters = c->counters;
-    CU_CHECK(c, cudaMemsetAsync(c->counters, 0, 4*sizeof(unsigned long long), c->stream));
-    // 1. candidate runs per tile -> hit-mask offsets
-    if (c->ndim == 3) k_tile_runs<3><<<nb, wpb*32, 0, c->stream>>>(a); else k_tile_runs<2><<<nb, wpb*32, 0, c->stream>>>(a);
+    CU_CHECK(c, cudaMemsetAsync(c->counters, 0, 8*sizeof(unsigned long long), c->stream));
+    // 1. candidate runs per tile
+    if (c->ndim == 3) k_tile_runs<3><<<nb, 128, 0, c->stream>>>(a); else k_tile_runs<2><<<nb, 128, 0, c->stream>>>(a);
     KERNEL_CHECK(c, "k_tile_runs");
-    if (sphb200_scan_tiles(c, c->tileWords, c->maskOff, c->nTiles)) return 1;
-    // 2. the predicate, once per (node, candidate)
-    if (c->ndim == 3) k_nbr_test<3><<<nb, wpb*32, 0, c->stream>>>(a); else k_nbr_test<2><<<nb, wpb*32, 0, c->stream>>>(a);
-    KERNEL_CHECK(c, "k_nbr_test");
-    if (sphb200_scan_tiles(c, c->tileRows, c->tileOff, c->nTiles)) return 1;
-    // 3. expand the masks into the sliced-ELL lists
-    if (c->ndim == 3) k_nbr_fill<3><<<nb, wpb*32, 0, c->stream>>>(a); else k_nbr_fill<2><<<nb, wpb*32, 0, c->stream>>>(a);
-    KERNEL_CHECK(c, "k_nbr_fill");
+    // 2. the predicate, once per (node, candidate), and the sliced-ELL lists
+    {
+      const size_t perWarp = (size_t)32*CROW*4 + (size_t)JB_CAP*4 + (size_t)c->listRows*64;
+      int warps = NB_WARPS;
+      while (warps > 1 && warps*perWarp > 220*1024) warps >>= 1;     // very long lists: fewer tiles per CTA
+      if (perWarp > 220*1024)
+        return sphb200_fail(c, "build_pairs: a node has more neighbours than the list staging can hold (H far too large for the node spacing?)");
+      const size_t shm = warps*perWarp;
+      const unsigned nbb = (unsigned)((c->nTiles + warps - 1)/warps);
+      if (c->ndim == 3) { CU_CHECK(c, cudaFuncSetAttribute(k_nbr_build<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); k_nbr_build<3><<<nbb, 32*warps, shm, c->stream>>>(a, c->listRows); }
+      else              { CU_CHECK(c, cudaFuncSetAttribute(k_nbr_build<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); k_nbr_build<2><<<nbb, 32*warps, shm, c->stream>>>(a, c->listRows); }
+      KERNEL_CHECK(c, "k_nbr_build");
+    }
     // one host round trip: totals and capacity check
-    CU_CHECK(c, cudaMemcpyAsync(c->countersHost, c->counters, 3*sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-    CU_CHECK(c, cudaMemcpyAsync(c->countersHost + 3, c->maskOff + c->nTiles, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-    CU_CHECK(c, cudaMemcpyAsync(c->countersHost + 4, c->tileOff + c->nTiles, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(c, cudaMemcpyAsync(c->countersHost, c->counters, 8*sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
-    const size_t needRuns = (size_t)c->countersHost[2], needMask = (size_t)c->countersHost[3], needNbr = (size_t)c->countersHost[4];
-    const bool okRuns = needRuns <= c->runsCap, okMask = needMask <= c->maskCap;
-    const bool okNbr = okRuns && okMask && needNbr <= c->nbrCap;     // the list size is only known once the test ran everywhere
-    if (okRuns && okMask && okNbr) {
-      c->npairs = (size_t)c->countersHost[0];
+    const size_t needRuns = (size_t)c->countersHost[2], needNbr = (size_t)c->countersHost[3], needRows = (size_t)c->countersHost[4];
+    const bool okRuns = needRuns <= c->runsCap;
+    const bool okRows = needRows <= (size_t)c->listRows;
+    const bool okNbr = okRuns && needNbr <= c->nbrCap;               // the list size is only known once the test ran everywhere
+    if (okRuns && okRows && okNbr) {
       c->nEdges = (size_t)c->countersHost[1];
+      // every internal-internal pair appears as two directed edges, every internal-ghost pair as one
+      c->npairs = (size_t)((c->countersHost[1] + c->countersHost[0])/2);
       c->nSlots = needNbr;
+      c->listRows = (int)((needRows + needRows/8 + 15)/8*8);       // staging for the next build: longest list + 12 %
       c->pairsValid = true;
       c->stats.directed_edges = c->nEdges;
       return 0;
     }
     if (!okRuns && sphb200_ensure(c, c->runs, c->runsCap, needRuns + needRuns/8)) return 1;
-    if (!okMask && sphb200_ensure(c, c->mask, c->maskCap, needMask + needMask/8)) return 1;
-    if (okRuns && okMask && !okNbr && sphb200_ensure(c, c->nbr, c->nbrCap, needNbr + needNbr/8)) return 1;
+    if (okRuns && !okRows) {
+      c->listRows = (int)(needRows + needRows/8 + 16);
+    }
+    if (okRuns && needNbr > c->nbrCap && sphb200_ensure(c, c->nbr, c->nbrCap, needNbr + needNbr/8)) return 1;
   }
   return sphb200_fail(c, "build_pairs: neighbour buffers failed to converge");
 }

@@ -108,10 +108,11 @@ struct sphb200_ctx {
   uint4* runs = nullptr; size_t runsCap = 0;   // candidate runs of all tiles: {first sorted slot, length, sx|sy<<16, sz}
   uint32_t* tileRunStart = nullptr; // per tile: first run
   uint32_t* tileRunCount = nullptr; // per tile: number of runs
-  uint32_t* tileWords = nullptr;    // per tile: 32-candidate words of the hit mask
+  int listRows = 0;                 // rows of the shared-memory list staging of k_nbr_build (adapts to the longest list)
+  uint32_t* tileWords = nullptr;    // (unused)
   unsigned long long* maskOff = nullptr;
   uint32_t* mask = nullptr; size_t maskCap = 0;
-  unsigned long long* counters = nullptr; // [0]=npairs [1]=directed edges [2]=run cursor
+  unsigned long long* counters = nullptr; // see NbrArgs::counters (8 entries)
   unsigned long long* countersHost = nullptr; // pinned
   size_t npairs = 0, nEdges = 0, nSlots = 0;
   bool pairsValid = false;
