@@ -408,7 +408,6 @@ __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build(NbrArgs a, int listRo
   const float csf[3] = {(float)a.g.cs[0], (float)a.g.cs[1], (float)a.g.cs[2]};
   uint32_t cnt = 0, ghostHits = 0;
   unsigned short* lp = slist + lane;               // next free entry of this lane's column
-  unsigned short* const lend = slist + (size_t)listRows*32;
 
   // software pipeline: the rows of run r+1 travel to registers while run r is tested out of shared memory
   const float4 FAR0 = make_float4(-1.0e30f, 0.f, 0.f, -1.f), FAR1 = make_float4(-1.f, 0.f, 0.f, 0.f);   // padding candidate: at infinity
@@ -474,10 +473,11 @@ __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build(NbrArgs a, int listRo
     if (self < len) hitWord &= ~(1u << self);
     cnt += __popc(hitWord);
     ghostHits += __popc(hitWord & ghostWord);
-    // append the hits to this lane's column of the list
-    for (uint32_t m = hitWord; m; m &= m - 1u) {
-      if (lp < lend) *lp = (unsigned short)((r << 5) | (uint32_t)(__ffs(m) - 1));
-      lp += 32;
+    // append the hits to this lane's column of the list; the bound is checked once per run (a list that does not fit
+    // is reported through counters[4] and the host redoes the build with a larger staging area)
+    if (cnt <= (uint32_t)listRows) {
+      const uint32_t rbase = r << 5;
+      for (uint32_t m = hitWord; m; m &= m - 1u) { *lp = (unsigned short)(rbase | (uint32_t)(__ffs(m) - 1)); lp += 32; }
     }
   }
 
@@ -696,7 +696,7 @@ int sphb200_neighbors(sphb200_ctx* c) {
       // every internal-internal pair appears as two directed edges, every internal-ghost pair as one
       c->npairs = (size_t)((c->countersHost[1] + c->countersHost[0])/2);
       c->nSlots = needNbr;
-      c->listRows = (int)((needRows + needRows/8 + 15)/8*8);       // staging for the next build: longest list + 12 %
+      c->listRows = (int)((needRows + 8 + 7)/8*8);                  // staging for the next build: longest list + a little
       c->pairsValid = true;
       c->stats.directed_edges = c->nEdges;
       return 0;
