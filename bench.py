@@ -48,13 +48,15 @@ def workload_spec(name):
     raise SystemExit("unknown workload " + name)
 
 
-def make_inputs(spec, seed=14892042, n_override=None):
+def make_inputs(spec, seed=14892042, n_override=None, slab=0):
+    """One unit cube of the workload; slab k of a domain-decomposed run is the cube shifted to x in [k, k+1)."""
     n = n_override or spec["n"]
     nPerh = spec["nPerh"]
     pos, mass, H, d = ng.lattice(3, n, nPerh=nPerh)
     N = pos.shape[0]
     jit = 0.2 if spec["kind"] == "glass" else 0.05
     pos = ng.jitter(pos, jit, d, seed=seed)
+    pos[:, 0] += float(slab)
     rho = np.ones(N)
     r = np.linalg.norm(pos, axis=1)
     if spec["kind"] == "noh":
@@ -199,7 +201,7 @@ def main():
     threads = os.cpu_count() or 1
     metric = "particle-updates/sec (3D SPH derivs+neighbour)"
     config = {"workload": spec["label"], "particles_per_gpu": spec["n"]**3, "dim": 3,
-              "decomposition": "one independent domain of the named size per GPU (weak)",
+              "decomposition": "1-D slabs along x, one unit cube of the named size per GPU, ghost halo exchanged over NCCL every step (weak)",
               "l2": "per-step working set (node rows + neighbour lists + pair accelerations) exceeds the 126 MB L2"}
 
     # ------------------------------------------------------------------ reference arm (CPU) ----------------------------
@@ -223,37 +225,74 @@ def main():
     from spheral_b200 import _lib as L, engine, kernel as K
     import ctypes as C
 
-    st, N = make_inputs(spec, seed=14892042 + rank)
+    st, N = make_inputs(spec, seed=14892042 + rank, slab=rank)
     WT = K.TableKernel(K.BSplineKernel(3), 1000)
     e = engine.Engine(3, device=local, **options_kwargs(spec))
     e.set_kernel_table(WT)
     e.set_nodes(N, 0)
+    ext = torch.cuda.ExternalStream(e.stream, device=torch.device("cuda", local))
 
-    # pinned host buffers for the e2e leg
+    # pinned host buffers for the e2e leg (internal nodes only: ghosts arrive over NVLink, not from the host)
     up_names = ("position", "velocity", "H", "mass", "massDensity", "specificThermalEnergy", "pressure", "soundSpeed", "omegaGradh")
     down_names = ("DxDt", "DrhoDt", "DvDt", "DepsDt", "DvDx", "DHDt", "Hideal")
-    hs, hd = L.HostState(), L.HostDerivs()
-    pinned, up_mask, down_mask, h2d, d2h = [], 0, 0, 0, 0
+    hs = L.HostState()
+    pinned, up_mask, h2d = [], 0, 0
     dp = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
     for k in up_names:
         t = torch.from_numpy(st[k]).clone().pin_memory()
         pinned.append(t); setattr(hs, k, dp(t)); up_mask |= L.STATE_BITS[k]; h2d += t.numel()*8
+    down_mask = 0
     for k in down_names:
-        t = torch.empty(N*L.deriv_width(3, k), dtype=torch.float64).pin_memory()
-        pinned.append(t); setattr(hd, k, dp(t)); down_mask |= L.DERIV_BITS[k]; d2h += t.numel()*8
+        down_mask |= L.DERIV_BITS[k]
+    d2h = sum(N*L.deriv_width(3, k)*8 for k in down_names)
+    down_bufs = {}
+
+    def download():
+        # destination sized for internal + current ghosts (the C ABI writes every node; ghost entries are zeros)
+        n = e.nInternal + e.nGhost
+        if down_bufs.get("n", 0) < n:
+            hd = L.HostDerivs()
+            keep = []
+            for k in down_names:
+                t = torch.empty((n + n//16)*L.deriv_width(3, k), dtype=torch.float64).pin_memory()
+                keep.append(t); setattr(hd, k, dp(t))
+            down_bufs.update(n=n + n//16, hd=hd, keep=keep)
+        e._check(e._lib.sphb200_download_derivs(e._h, down_mask, C.byref(down_bufs["hd"])))
 
     e.upload_state_pinned(up_mask, hs)
     e.sync()
 
+    dsph = None
+    if world > 1:
+        from spheral_b200 import distributed as D
+        dsph = D.DistributedSPH(e, 0, float(rank), float(rank + 1))
+
     def step():
-        e.build_pairs()
-        e.evaluate_derivatives(0.0, 1.0)
+        if dsph is not None:
+            dsph.step_connectivity_and_derivatives(0.0, 1.0)     # ghost selection + NVLink halo exchange + K1..K5
+        else:
+            e.build_pairs()
+            e.evaluate_derivatives(0.0, 1.0)
 
     def step_e2e():
+        if dsph is not None:
+            e.set_nodes(N, 0)
         e.upload_state_pinned(up_mask, hs)
-        e.build_pairs()
-        e.evaluate_derivatives(0.0, 1.0)
-        e._check(e._lib.sphb200_download_derivs(e._h, down_mask, C.byref(hd)))
+        step()
+        download()
+
+    def timed(fn, k):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(dist, local)
+        t0 = time.perf_counter()
+        ev0.record(ext)
+        for _ in range(k):
+            fn()
+        ev1.record(ext)
+        e.sync()
+        wall = time.perf_counter() - t0
+        barrier(dist, local)
+        return ev0.elapsed_time(ev1)*1e-3, wall
 
     for _ in range(warmup):
         step()
@@ -262,37 +301,30 @@ def main():
     launches0 = e.stats()["launches"]
 
     sampler = ClockSampler(local)
-    barrier(dist, local)
     if rank == 0:
         sampler.start()
-    dev_ms, pair_ms, nbr_ms, build_ms, eval_ms = 0.0, [], [], [], []
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-        s_ = e.stats()          # synchronises the engine stream; times are CUDA events on that stream
-        dev_ms += s_["ms_build_pairs"] + s_["ms_evaluate"]
-        pair_ms.append(s_["ms_pair_kernel"]); nbr_ms.append(s_["ms_neighbor_kernels"])
-        build_ms.append(s_["ms_build_pairs"]); eval_ms.append(s_["ms_evaluate"])
-    e.sync()
-    wall = time.perf_counter() - t0
-    barrier(dist, local)
+    dev_s, wall = timed(step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = e.stats()["launches"] - launches0
-    edges = e.stats()["directed_edges"]
-    dev_s = max_over_ranks(dist, dev_ms*1e-3, local)
+    dev_s = max_over_ranks(dist, dev_s, local)
     wall_s = max_over_ranks(dist, wall, local)
 
-    # e2e leg
+    # per-kernel breakdown (CUDA events inside the library, on the same stream), outside the timed region
+    pair_ms, nbr_ms, build_ms, eval_ms = [], [], [], []
+    for _ in range(3):
+        step()
+        s_ = e.stats()
+        pair_ms.append(s_["ms_pair_kernel"]); nbr_ms.append(s_["ms_neighbor_kernels"])
+        build_ms.append(s_["ms_build_pairs"]); eval_ms.append(s_["ms_evaluate"])
+    edges = e.stats()["directed_edges"]
+    halo_info = dict(dsph.last) if dsph is not None else None
+
+    # e2e leg: host buffers in, host buffers out, every step
     for _ in range(2):
         step_e2e()
     e.sync()
-    barrier(dist, local)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    e.sync()
-    e2e_s = max_over_ranks(dist, time.perf_counter() - t0, local)
-    barrier(dist, local)
+    _, e2e_wall = timed(step_e2e, args.steps)
+    e2e_s = max_over_ranks(dist, e2e_wall, local)
 
     if rank == 0:
         nbrs = edges/float(N)
@@ -320,7 +352,8 @@ def main():
         line = {"metric": metric, "value": value, "unit": "particle-updates/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warmup, "ms_per_step": dev_s/args.steps*1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": dict(config, neighbours_per_particle=nbrs, timing="CUDA events on the engine stream, max over ranks"),
+                "config": dict(config, neighbours_per_particle=nbrs, halo=halo_info,
+                               timing="CUDA events on the engine stream around the K steps, max over ranks"),
                 "clocks": clocks,
                 "e2e": {"value": total_updates/e2e_s, "unit": "particle-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "timing": "host wall clock around synchronised C-ABI calls (pinned host buffers)"},

@@ -160,6 +160,15 @@ int  sphb200_halo_pack(sphb200_ctx* ctx, unsigned fieldMask, const uint32_t* sen
                        void* stagingDevice);
 int  sphb200_halo_unpack(sphb200_ctx* ctx, unsigned fieldMask, size_t firstGhost, size_t count,
                          const void* stagingDevice);
+/* Domain bounds for the ghost-set decision (the role of the bounding boxes all-gathered by
+   NestedGridDistributedBoundary.cc:116-170 / TreeDistributedBoundary.cc:150-295): coordinate range and the largest
+   per-axis kernel extent kext*sqrt((H^-2)_aa) (Neighbor::HExtent, NeighborInline.hh:52-64) over nodes [0,count). */
+int  sphb200_node_bounds(sphb200_ctx* ctx, size_t count, double lo[3], double hi[3], double maxExtent[3]);
+/* Send-node selection for a slab decomposition along `axis` (DistributedBoundary::buildSendNodes role): among nodes
+   [0,count), those with x < lo + width go to the lower neighbour, those with x >= hi - width to the upper one.  Index
+   lists are written in ascending node order (deterministic) into caller-provided device buffers of `cap` entries. */
+int  sphb200_halo_select(sphb200_ctx* ctx, int axis, size_t count, double lo, double hi, double width,
+                         uint32_t* sendLowDevice, size_t* nLow, uint32_t* sendHighDevice, size_t* nHigh, size_t cap);
 /* raw stream handle (cudaStream_t) so the plumbing can order NCCL calls after pack / before unpack */
 void* sphb200_stream(sphb200_ctx* ctx);
 

@@ -76,7 +76,7 @@ EXPORTS = ("sphb200_abi_version", "sphb200_create", "sphb200_destroy", "sphb200_
            "sphb200_download_pairs", "sphb200_download_neighbor_counts", "sphb200_evaluate_derivatives",
            "sphb200_download_derivs", "sphb200_download_pair_accelerations", "sphb200_copy_DvDx_to_Q",
            "sphb200_update_energy_compatible", "sphb200_halo_bytes_per_node", "sphb200_halo_pack",
-           "sphb200_halo_unpack", "sphb200_stream", "sphb200_get_stats", "sphb200_measure_fp64_peak")
+           "sphb200_halo_unpack", "sphb200_node_bounds", "sphb200_halo_select", "sphb200_stream", "sphb200_get_stats", "sphb200_measure_fp64_peak")
 
 _lib = None
 
@@ -121,6 +121,9 @@ def lib():
     L.sphb200_halo_bytes_per_node.restype = C.c_size_t
     L.sphb200_halo_pack.argtypes = [vp, C.c_uint, vp, C.c_size_t, vp]
     L.sphb200_halo_unpack.argtypes = [vp, C.c_uint, C.c_size_t, C.c_size_t, vp]
+    L.sphb200_node_bounds.argtypes = [vp, C.c_size_t, _dp, _dp, _dp]
+    L.sphb200_halo_select.argtypes = [vp, C.c_int, C.c_size_t, C.c_double, C.c_double, C.c_double,
+                                      vp, C.POINTER(C.c_size_t), vp, C.POINTER(C.c_size_t), C.c_size_t]
     L.sphb200_stream.argtypes = [vp]
     L.sphb200_stream.restype = vp
     L.sphb200_get_stats.argtypes = [vp, C.POINTER(Stats)]

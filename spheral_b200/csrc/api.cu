@@ -52,6 +52,22 @@ __global__ void __launch_bounds__(RB) k_halo_pack(const double* __restrict__ fie
   const size_t k = t/width; const int q = (int)(t % width);
   out[t] = field[(size_t)nodes[k]*width + q];
 }
+// slab halo selection: flags, then (after exclusive scans) ordered scatter of the node indices
+__global__ void __launch_bounds__(RB) k_halo_flags(const double* __restrict__ pos, int ndim, int axis, size_t count, double lowCut, double highCut,
+                                                   uint32_t* __restrict__ fLow, uint32_t* __restrict__ fHigh) {
+  const size_t i = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (i >= count) return;
+  const double x = pos[i*ndim + axis];
+  fLow[i] = (x < lowCut) ? 1u : 0u;
+  fHigh[i] = (x >= highCut) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(RB) k_halo_scatter(const uint32_t* __restrict__ offLow, const uint32_t* __restrict__ offHigh, size_t count,
+                                                     size_t cap, uint32_t* __restrict__ outLow, uint32_t* __restrict__ outHigh) {
+  const size_t i = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (i >= count) return;
+  if (offLow[i + 1] != offLow[i] && offLow[i] < cap) outLow[offLow[i]] = (uint32_t)i;
+  if (offHigh[i + 1] != offHigh[i] && offHigh[i] < cap) outHigh[offHigh[i]] = (uint32_t)i;
+}
 // dependent-chain FP64 FMA throughput probe: 8 independent chains per thread
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x*1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -63,19 +79,28 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
   if (s == 12345.678) out[blockIdx.x*blockDim.x + threadIdx.x] = s;
 }
 
+// (Re)size the per-node arrays.  The host-ordered state fields keep their contents when the capacity grows (the ghost
+// count changes from step to step while the internal state lives on the device); everything else is scratch.
 int alloc_nodes(sphb200_ctx* c, size_t n) {
   if (n <= c->cap) return 0;
   const size_t cap = n + n/32 + 32;
+  const size_t keep = c->n;                     // nodes whose state must survive
+  for (int s = 0; s < S_COUNT; ++s) {
+    const size_t w = (size_t)sphb200_state_width(c->ndim, s);
+    double* p = nullptr;
+    CU_CHECK(c, cudaMalloc((void**)&p, cap*w*sizeof(double)));
+    if (c->api[s] && c->have[s] && keep)
+      CU_CHECK(c, cudaMemcpyAsync(p, c->api[s], keep*w*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    else c->have[s] = false;
+    if (c->api[s]) { CU_CHECK(c, cudaStreamSynchronize(c->stream)); cudaFree(c->api[s]); }
+    c->api[s] = p;
+  }
   auto reall = [&](double*& p, size_t cnt) -> int {
     if (p) cudaFree(p);
     p = nullptr;
     CU_CHECK(c, cudaMalloc((void**)&p, cnt*sizeof(double)));
     return 0;
   };
-  for (int s = 0; s < S_COUNT; ++s) {
-    if (reall(c->api[s], cap*(size_t)sphb200_state_width(c->ndim, s))) return 1;
-    c->have[s] = false;
-  }
   if (reall(c->rows, cap*(size_t)(c->ndim == 3 ? 16 : 12))) return 1;
   for (int s = 0; s < DV_COUNT; ++s) if (reall(c->deriv[s], cap*(size_t)sphb200_deriv_width(c->ndim, s))) return 1;
   auto reall32 = [&](uint32_t*& p, size_t cnt) -> int {
@@ -86,10 +111,7 @@ int alloc_nodes(sphb200_ctx* c, size_t n) {
   };
   if (reall32(c->cellKeyApi, cap) || reall32(c->perm, cap) || reall32(c->skey, cap) || reall32(c->nbrCount, cap)) return 1;
   const size_t nt = (cap + SPHB200_TILE - 1)/SPHB200_TILE + 1;
-  if (reall32(c->tileRows, nt) || reall32(c->tileWords, nt) || reall32(c->tileRunStart, nt) || reall32(c->tileRunCount, nt)) return 1;
-  if (c->maskOff) cudaFree(c->maskOff);
-  c->maskOff = nullptr;
-  CU_CHECK(c, cudaMalloc((void**)&c->maskOff, (nt + 1)*sizeof(unsigned long long)));
+  if (reall32(c->tileRows, nt) || reall32(c->tileRunStart, nt) || reall32(c->tileRunCount, nt)) return 1;
   if (c->tileOff) cudaFree(c->tileOff);
   c->tileOff = nullptr;
   CU_CHECK(c, cudaMalloc((void**)&c->tileOff, (nt + 1)*sizeof(unsigned long long)));
@@ -97,6 +119,7 @@ int alloc_nodes(sphb200_ctx* c, size_t n) {
   for (double** p : {&c->auxPneg, &c->auxSomr2, &c->auxDvDxQ, &c->auxfCl, &c->auxfCq}) { if (*p) cudaFree(*p); *p = nullptr; }
   if (c->frows) { cudaFree(c->frows); c->frows = nullptr; c->frowsCap = 0; }
   c->cap = cap;
+  c->sortValid = c->rowsValid = c->pairsValid = c->derivsValid = false;
   return 0;
 }
 
@@ -167,7 +190,7 @@ void sphb200_destroy(sphb200_ctx* c) {
   for (void* p : {(void*)c->W.coef, (void*)c->W.nperhVals, (void*)c->WQ.coef, (void*)c->WQ.nperhVals, (void*)c->cellKeyApi, (void*)c->cellStart,
                   (void*)c->cellCursor, (void*)c->perm, (void*)c->skey, (void*)c->reduceBuf, (void*)c->rows, (void*)c->auxPneg, (void*)c->auxSomr2,
                   (void*)c->auxDvDxQ, (void*)c->auxfCl, (void*)c->auxfCq, (void*)c->nbrCount, (void*)c->tileRows, (void*)c->tileOff, (void*)c->nbr,
-                  (void*)c->counters, (void*)c->frows, (void*)c->tileWords, (void*)c->maskOff, (void*)c->mask, (void*)c->scanTmp, (void*)c->pacc, (void*)c->stage,
+                  (void*)c->counters, (void*)c->frows, (void*)c->scanTmp, (void*)c->pacc, (void*)c->stage,
                   (void*)c->runs, (void*)c->tileRunStart, (void*)c->tileRunCount, (void*)c->dilTab}) cudaFree(p);
   cudaFreeHost(c->reduceHost); cudaFreeHost(c->countersHost);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -446,6 +469,46 @@ int sphb200_halo_unpack(sphb200_ctx* c, unsigned mask, size_t firstGhost, size_t
     if (s == S_POS || s == S_H) { c->sortValid = false; c->pairsValid = false; }
     if (s != S_EPS) c->rowsValid = false;
   }
+  return 0;
+}
+
+int sphb200_node_bounds(sphb200_ctx* c, size_t count, double lo[3], double hi[3], double maxExtent[3]) {
+  if (!c || !lo || !hi || !maxExtent) return sphb200_fail(c, "node_bounds: null argument");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (count > c->n) return sphb200_fail(c, "node_bounds: count exceeds node count");
+  if (!c->have[S_POS] || !c->have[S_H] || !c->W.set) return sphb200_fail(c, "node_bounds: position, H and the kernel table must be set first");
+  for (int a = 0; a < 3; ++a) { lo[a] = 0.0; hi[a] = 0.0; maxExtent[a] = 0.0; }
+  if (count == 0) return 0;
+  if (sphb200_bounds_reduce(c, count)) return 1;
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  for (int a = 0; a < c->ndim; ++a) { lo[a] = c->reduceHost[a]; hi[a] = c->reduceHost[3 + a]; maxExtent[a] = c->reduceHost[6 + a]; }
+  return 0;
+}
+
+int sphb200_halo_select(sphb200_ctx* c, int axis, size_t count, double lo, double hi, double width,
+                        uint32_t* sendLow, size_t* nLow, uint32_t* sendHigh, size_t* nHigh, size_t cap) {
+  if (!c || !nLow || !nHigh) return sphb200_fail(c, "halo_select: null argument");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (axis < 0 || axis >= c->ndim) return sphb200_fail(c, "halo_select: bad axis");
+  if (count > c->n) return sphb200_fail(c, "halo_select: count exceeds node count");
+  if (!c->have[S_POS]) return sphb200_fail(c, "halo_select: positions are not on the device");
+  *nLow = *nHigh = 0;
+  if (count == 0) return 0;
+  if (ensure_stage(c, 2*(count + 1)*sizeof(uint32_t))) return 1;
+  uint32_t* fLow = (uint32_t*)c->stage; uint32_t* fHigh = fLow + (count + 1);
+  const unsigned nb = (unsigned)((count + RB - 1)/RB);
+  k_halo_flags<<<nb, RB, 0, c->stream>>>(c->api[S_POS], c->ndim, axis, count, lo + width, hi - width, fLow, fHigh);
+  KERNEL_CHECK(c, "k_halo_flags");
+  if (sphb200_scan_u32(c, fLow, fLow, count)) return 1;
+  if (sphb200_scan_u32(c, fHigh, fHigh, count)) return 1;
+  k_halo_scatter<<<nb, RB, 0, c->stream>>>(fLow, fHigh, count, cap, sendLow, sendHigh);
+  KERNEL_CHECK(c, "k_halo_scatter");
+  uint32_t tot[2];
+  CU_CHECK(c, cudaMemcpyAsync(&tot[0], fLow + count, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(c, cudaMemcpyAsync(&tot[1], fHigh + count, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  *nLow = tot[0]; *nHigh = tot[1];
+  if (tot[0] > cap || tot[1] > cap) return sphb200_fail(c, "halo_select: send list capacity too small");
   return 0;
 }
 

@@ -103,12 +103,12 @@ __global__ void __launch_bounds__(RB) k_bbox(const double* __restrict__ pos, con
     partial[blockIdx.x*9 + threadIdx.x] = v;
   }
 }
-__global__ void k_bbox_final(const double* __restrict__ partial, int nb, double* __restrict__ out) {
-  if (threadIdx.x < 9) {
-    double v = partial[threadIdx.x];
-    for (int k = 1; k < nb; ++k) v = (threadIdx.x < 3) ? fmin(v, partial[k*9 + threadIdx.x]) : fmax(v, partial[k*9 + threadIdx.x]);
-    out[threadIdx.x] = v;
-  }
+__global__ void k_bbox_final(const double* __restrict__ partial, int nb, double* __restrict__ out) {   // 9 warps, one per output
+  const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double v = (q < 3) ? 1e300 : -1e300;
+  for (int k = lane; k < nb; k += 32) v = (q < 3) ? fmin(v, partial[k*9 + q]) : fmax(v, partial[k*9 + q]);
+  v = (q < 3) ? warp_min(v) : warp_max(v);
+  if (lane == 0) out[q] = v;
 }
 
 // ---- K1b: cell key + histogram --------------------------------------------------------------------------------------
@@ -609,19 +609,25 @@ int sphb200_pack_rows(sphb200_ctx* c) {
   return 0;
 }
 
+int sphb200_bounds_reduce(sphb200_ctx* c, size_t count) {
+  const double kext = std::max(c->W.kext, c->WQ.set ? c->WQ.kext : 0.0);
+  const int nbb = (int)std::min<size_t>(296, (count + RB - 1)/RB);
+  if (c->ndim == 3) k_bbox<3><<<nbb, RB, 0, c->stream>>>(c->api[S_POS], c->api[S_H], count, kext, c->reduceBuf);
+  else              k_bbox<2><<<nbb, RB, 0, c->stream>>>(c->api[S_POS], c->api[S_H], count, kext, c->reduceBuf);
+  KERNEL_CHECK(c, "k_bbox");
+  k_bbox_final<<<1, 32*9, 0, c->stream>>>(c->reduceBuf, nbb, c->reduceBuf + 296*9);
+  KERNEL_CHECK(c, "k_bbox_final");
+  CU_CHECK(c, cudaMemcpyAsync(c->reduceHost, c->reduceBuf + 296*9, 9*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+
 int sphb200_sort_and_pack(sphb200_ctx* c) {
   const size_t n = c->n;
   if (!c->have[S_POS] || !c->have[S_H]) return sphb200_fail(c, "build_pairs: position and H must be uploaded first");
   if (!c->W.set) return sphb200_fail(c, "build_pairs: kernel table not set (need the kernel extent)");
   const double kext = std::max(c->W.kext, c->WQ.set ? c->WQ.kext : 0.0);
   // bbox + extents
-  const int nbb = (int)std::min<size_t>(296, (n + RB - 1)/RB);
-  if (c->ndim == 3) k_bbox<3><<<nbb, RB, 0, c->stream>>>(c->api[S_POS], c->api[S_H], n, kext, c->reduceBuf);
-  else              k_bbox<2><<<nbb, RB, 0, c->stream>>>(c->api[S_POS], c->api[S_H], n, kext, c->reduceBuf);
-  KERNEL_CHECK(c, "k_bbox");
-  k_bbox_final<<<1, 32, 0, c->stream>>>(c->reduceBuf, nbb, c->reduceBuf + 296*9);
-  KERNEL_CHECK(c, "k_bbox_final");
-  CU_CHECK(c, cudaMemcpyAsync(c->reduceHost, c->reduceBuf + 296*9, 9*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (sphb200_bounds_reduce(c, n)) return 1;
   CU_CHECK(c, cudaStreamSynchronize(c->stream));
   for (int a = 0; a < c->ndim; ++a)
     if (!std::isfinite(c->reduceHost[a]) || !std::isfinite(c->reduceHost[3 + a]) || !std::isfinite(c->reduceHost[6 + a]))

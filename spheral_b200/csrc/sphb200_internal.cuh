@@ -109,9 +109,6 @@ struct sphb200_ctx {
   uint32_t* tileRunStart = nullptr; // per tile: first run
   uint32_t* tileRunCount = nullptr; // per tile: number of runs
   int listRows = 0;                 // rows of the shared-memory list staging of k_nbr_build (adapts to the longest list)
-  uint32_t* tileWords = nullptr;    // (unused)
-  unsigned long long* maskOff = nullptr;
-  uint32_t* mask = nullptr; size_t maskCap = 0;
   unsigned long long* counters = nullptr; // see NbrArgs::counters (8 entries)
   unsigned long long* countersHost = nullptr; // pinned
   size_t npairs = 0, nEdges = 0, nSlots = 0;
@@ -143,6 +140,7 @@ int sphb200_scan_tiles(sphb200_ctx* c, const uint32_t* rows, unsigned long long*
 
 // implemented in neighbors.cu / derivs.cu / energy.cu
 int sphb200_sort_and_pack(sphb200_ctx* c);
+int sphb200_bounds_reduce(sphb200_ctx* c, size_t count);   // bbox + max extents of nodes [0,count) -> reduceHost[0..8] (async copy)
 int sphb200_pack_rows(sphb200_ctx* c);
 int sphb200_neighbors(sphb200_ctx* c);
 int sphb200_launch_derivs(sphb200_ctx* c);

@@ -1,0 +1,221 @@
+"""Spatial domain decomposition and ghost-node (halo) exchange for the SPH hot path on 1-8 GPUs of one box.
+
+Replaces, for this path, the MPI ghost exchange of src/Distributed:
+    DistributedBoundary::setAllGhostNodes / buildReceiveAndGhostNodes   (Distributed/DistributedBoundary.cc:565-753, 1256-1353)
+    TreeDistributedBoundary::setAllGhostNodes                            (Distributed/TreeDistributedBoundary.cc:62-91, 150-295)
+with one process per GPU, `torch.distributed` point-to-point operations (NCCL send/recv over NVLink on GPUs; gloo in the
+CPU tests) and device-side pack / unpack kernels reached through the C ABI (sphb200_halo_select / _pack / _unpack).
+
+Decomposition: 1-D slabs along one axis -- two peers per rank.  A node is sent to a neighbouring slab when it
+lies within `width` of the shared face, where `width` is the largest per-axis kernel extent kext*sqrt((H^-2)_aa) over ALL
+ranks (an all-reduce MAX), so that both the gather (H_i) and the scatter (H_j) side of the reference's pair predicate
+(ConnectivityMap.cc:916-931) are covered; the ghost set is a superset of what the reference would send, never a subset.
+
+The derivative evaluation itself needs no communication: ghosts are filled beforehand and derivatives are only defined on
+internal nodes.  The exchange is split in two so that only positions and H sit on the critical path:
+    phase A  position, H            -> needed by the neighbour build (K1 + K2)
+    phase B  every other state field -> needed by the pair loop (K3); in flight while K1 + K2 run.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+
+PHASE_A = ("position", "H")
+PHASE_B = ("velocity", "mass", "massDensity", "specificThermalEnergy", "pressure", "soundSpeed", "omegaGradh")
+
+
+def slab_edges(xmin, xmax, world):
+    """Equal-width slab faces along the decomposition axis: world+1 values."""
+    return np.linspace(float(xmin), float(xmax), world + 1)
+
+
+def kernel_extent_axis(H, ndim, kext, axis):
+    """kext*sqrt((H^-2)_aa) per node (Neighbor::HExtent, NeighborInline.hh:52-64) -- numpy reference of what
+    sphb200_node_bounds reduces on the device."""
+    H = np.asarray(H, dtype=np.float64)
+    n = H.shape[0]
+    F = np.zeros((n, ndim, ndim))
+    if ndim == 3:
+        idx = ((0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2))
+    else:
+        idx = ((0, 0), (0, 1), (1, 1))
+    for k, (r, c) in enumerate(idx):
+        F[:, r, c] = H[:, k]
+        F[:, c, r] = H[:, k]
+    Fi = np.linalg.inv(F)
+    return kext*np.sqrt((Fi[:, axis, :]**2).sum(axis=1))
+
+
+def select_halo_numpy(pos, count, axis, lo, hi, width):
+    """Host reference of sphb200_halo_select: ascending indices of nodes [0,count) to send to the lower / upper slab."""
+    x = np.asarray(pos)[:count, axis]
+    return (np.nonzero(x < lo + width)[0].astype(np.uint32), np.nonzero(x >= hi - width)[0].astype(np.uint32))
+
+
+class SlabHalo:
+    """Point-to-point plumbing between a slab and its two neighbours.  Works on torch tensors, so the same code runs over
+    NCCL (CUDA tensors) and gloo (CPU tensors, used by tests/test_distributed_gloo.py)."""
+
+    def __init__(self, rank=None, world=None, group=None):
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.group = group
+        self.lower = self.rank - 1 if self.rank > 0 else None
+        self.upper = self.rank + 1 if self.rank < self.world - 1 else None
+
+    def allreduce_max(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def exchange_counts(self, nLow, nHigh, device):
+        """Tell each neighbour how many nodes it will receive; returns (nFromLower, nFromUpper)."""
+        if self.world == 1:
+            return 0, 0
+        mine = torch.tensor([nLow, nHigh], dtype=torch.int64, device=device)
+        parts = [torch.empty(2, dtype=torch.int64, device=device) for _ in range(self.world)]
+        dist.all_gather(parts, mine, group=self.group)
+        allc = torch.stack(parts).cpu().numpy()
+        nFromLower = int(allc[self.lower, 1]) if self.lower is not None else 0     # the lower slab's "high" list is ours
+        nFromUpper = int(allc[self.upper, 0]) if self.upper is not None else 0
+        return nFromLower, nFromUpper
+
+    def start(self, sendLow, sendHigh, recvLow, recvHigh):
+        """Post the sends and receives of one phase; returns the work handles (wait() orders the current stream after them)."""
+        ops = []
+        if self.lower is not None:
+            if sendLow is not None and sendLow.numel():
+                ops.append(dist.P2POp(dist.isend, sendLow, self.lower, self.group))
+            if recvLow is not None and recvLow.numel():
+                ops.append(dist.P2POp(dist.irecv, recvLow, self.lower, self.group))
+        if self.upper is not None:
+            if sendHigh is not None and sendHigh.numel():
+                ops.append(dist.P2POp(dist.isend, sendHigh, self.upper, self.group))
+            if recvHigh is not None and recvHigh.numel():
+                ops.append(dist.P2POp(dist.irecv, recvHigh, self.upper, self.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    @staticmethod
+    def finish(works):
+        for w in works:
+            w.wait()
+
+
+def ordered_fields(names):
+    """Fields in the order sphb200_halo_pack lays them out: ascending mask bit."""
+    return [k for k in L.STATE_FIELDS if k in names]
+
+
+def pack_fields_numpy(state, names, idx, ndim):
+    """Host reference of sphb200_halo_pack: field-major staging, each field len(idx)*width doubles."""
+    return np.concatenate([np.asarray(state[k], dtype=np.float64).reshape(-1, L.state_width(ndim, k))[idx].ravel()
+                           for k in ordered_fields(names)]) if len(idx) else np.zeros(0)
+
+
+def unpack_fields_numpy(buf, names, count, ndim):
+    """Host reference of sphb200_halo_unpack: staging -> {field: (count, width) array}."""
+    out, off = {}, 0
+    for k in ordered_fields(names):
+        w = L.state_width(ndim, k)
+        out[k] = np.asarray(buf[off:off + count*w]).reshape(count, w) if w > 1 else np.asarray(buf[off:off + count])
+        off += count*w
+    return out
+
+
+def field_mask(names):
+    m = 0
+    for k in names:
+        m |= L.STATE_BITS[k]
+    return m
+
+
+class DistributedSPH:
+    """One slab of a domain-decomposed problem on one GPU: an Engine plus the ghost exchange with the two neighbouring
+    slabs.  `step_connectivity_and_derivatives()` is what Integrator::setGhostNodes + evaluateDerivatives do per stage
+    (Integrator.cc:372-445, 217-229): ghost selection, exchange, neighbour build, derivative evaluation."""
+
+    def __init__(self, engine, axis, lo, hi, halo=None, extra_fields=()):
+        self.e = engine
+        self.axis, self.lo, self.hi = axis, float(lo), float(hi)
+        self.halo = halo if halo is not None else SlabHalo()
+        self.dev = torch.device("cuda", engine_device(engine))
+        self.stream = torch.cuda.ExternalStream(engine.stream, device=self.dev)
+        self.maskA = field_mask(PHASE_A)
+        self.maskB = field_mask(PHASE_B + tuple(extra_fields))
+        self.bytesA = engine.halo_bytes_per_node(self.maskA)
+        self.bytesB = engine.halo_bytes_per_node(self.maskB)
+        self._cap = 0
+        self.nInternal = engine.nInternal
+        self.nFromLower = self.nFromUpper = 0
+        self.width = 0.0
+        self.last = {}
+
+    def _ensure(self, cap):
+        if cap <= self._cap:
+            return
+        cap = int(cap*1.25) + 1024
+        dev = self.dev
+        self.idxLow = torch.empty(cap, dtype=torch.int32, device=dev)
+        self.idxHigh = torch.empty(cap, dtype=torch.int32, device=dev)
+        mk = lambda nbytes: torch.empty(cap*nbytes//8, dtype=torch.float64, device=dev)
+        self.sLowA, self.sHighA, self.rLowA, self.rHighA = mk(self.bytesA), mk(self.bytesA), mk(self.bytesA), mk(self.bytesA)
+        self.sLowB, self.sHighB, self.rLowB, self.rHighB = mk(self.bytesB), mk(self.bytesB), mk(self.bytesB), mk(self.bytesB)
+        self._cap = cap
+
+    def refresh_ghosts_and_build(self):
+        """Ghost selection + two-phase exchange + neighbour build.  Returns the number of node pairs of this slab."""
+        e, h = self.e, self.halo
+        nInt = self.nInternal
+        with torch.cuda.stream(self.stream):
+            # halo width: largest kernel extent along the axis over all ranks (gather AND scatter neighbours are covered)
+            _, _, ext = e.node_bounds(nInt)
+            w = torch.tensor([float(ext[self.axis])], dtype=torch.float64, device=self.dev)
+            self.width = float(h.allreduce_max(w).item())*(1.0 + 1.0e-9)
+            # device-side send lists (deterministic ascending order); capacity grows on demand
+            if self._cap == 0:
+                self._ensure(max(1024, nInt//8))
+            while True:
+                try:
+                    nLow, nHigh = e.halo_select(self.axis, self.lo, self.hi, self.width, self.idxLow.data_ptr(), self.idxHigh.data_ptr(), self._cap, nInt)
+                    break
+                except RuntimeError as err:
+                    if "capacity" not in str(err):
+                        raise
+                    self._ensure(self._cap*2)
+            if h.lower is None:
+                nLow = 0
+            if h.upper is None:
+                nHigh = 0
+            nFL, nFU = h.exchange_counts(nLow, nHigh, self.dev)
+            self._ensure(max(nLow, nHigh, nFL, nFU))
+            self.nFromLower, self.nFromUpper = nFL, nFU
+            e.set_nodes(nInt, nFL + nFU)
+            # pack both phases, then post A and B; K1+K2 only wait for A
+            wA, wB = self.bytesA//8, self.bytesB//8
+            e.halo_pack(self.maskA, self.idxLow.data_ptr(), nLow, self.sLowA.data_ptr())
+            e.halo_pack(self.maskA, self.idxHigh.data_ptr(), nHigh, self.sHighA.data_ptr())
+            e.halo_pack(self.maskB, self.idxLow.data_ptr(), nLow, self.sLowB.data_ptr())
+            e.halo_pack(self.maskB, self.idxHigh.data_ptr(), nHigh, self.sHighB.data_ptr())
+            worksA = h.start(self.sLowA[:nLow*wA], self.sHighA[:nHigh*wA], self.rLowA[:nFL*wA], self.rHighA[:nFU*wA])
+            worksB = h.start(self.sLowB[:nLow*wB], self.sHighB[:nHigh*wB], self.rLowB[:nFL*wB], self.rHighB[:nFU*wB])
+            h.finish(worksA)
+            e.halo_unpack(self.maskA, nInt, nFL, self.rLowA.data_ptr())
+            e.halo_unpack(self.maskA, nInt + nFL, nFU, self.rHighA.data_ptr())
+            npairs = e.build_pairs()                      # phase B is in flight on the NCCL stream meanwhile
+            h.finish(worksB)
+            e.halo_unpack(self.maskB, nInt, nFL, self.rLowB.data_ptr())
+            e.halo_unpack(self.maskB, nInt + nFL, nFU, self.rHighB.data_ptr())
+        self.last = dict(nSendLow=nLow, nSendHigh=nHigh, nFromLower=nFL, nFromUpper=nFU, width=self.width,
+                         h2h_bytes=(nLow + nHigh)*(self.bytesA + self.bytesB))
+        return npairs
+
+    def step_connectivity_and_derivatives(self, time=0.0, dt=1.0):
+        npairs = self.refresh_ghosts_and_build()
+        self.e.evaluate_derivatives(time, dt)
+        return npairs
+
+
+def engine_device(engine):
+    return int(getattr(engine, "device", 0))

@@ -38,6 +38,7 @@ class Engine:
     def __init__(self, ndim, device=0, options=None, **kw):
         self._lib = L.lib()
         self.ndim = ndim
+        self.device = device
         self.options = options if options is not None else make_options(ndim, **kw)
         self._h = C.c_void_p()
         if self._lib.sphb200_create(C.byref(self._h), device, C.byref(self.options)) != 0:
@@ -192,6 +193,19 @@ class Engine:
 
     def halo_unpack(self, mask, first_ghost, count, staging_ptr):
         self._check(self._lib.sphb200_halo_unpack(self._h, mask, first_ghost, count, staging_ptr))
+
+    def node_bounds(self, count=None):
+        """(lo[ndim], hi[ndim], maxExtent[ndim]) of nodes [0,count) -- default: the internal nodes."""
+        lo, hi, ext = np.zeros(3), np.zeros(3), np.zeros(3)
+        self._check(self._lib.sphb200_node_bounds(self._h, self.nInternal if count is None else count, _dp(lo), _dp(hi), _dp(ext)))
+        return lo[:self.ndim], hi[:self.ndim], ext[:self.ndim]
+
+    def halo_select(self, axis, lo, hi, width, send_low_ptr, send_high_ptr, cap, count=None):
+        """Device-side send-node selection of a slab decomposition; returns (nLow, nHigh)."""
+        nl, nh = C.c_size_t(), C.c_size_t()
+        self._check(self._lib.sphb200_halo_select(self._h, axis, self.nInternal if count is None else count, lo, hi, width,
+                                                  send_low_ptr, C.byref(nl), send_high_ptr, C.byref(nh), cap))
+        return nl.value, nh.value
 
     # -- instrumentation -----------------------------------------------------------------------------------------------
     def stats(self):

@@ -228,3 +228,18 @@ def test_neighbour_pairs_bit_exact_on_ragged_inputs(oracle, eng_mod):
         pi, pj, cnt = oracle.pairs(ndim, nInt, nGhost, pos, H, 2.0, "brute")
         assert npairs == len(pi)
         assert np.array_equal(gi, pi) and np.array_equal(gj, pj) and np.array_equal(gc, cnt)
+
+
+def test_two_gpu_slab_halo_parity(sphlib, oracle):
+    """Domain-decomposed run on 2 GPUs (NCCL halo) against the oracle on the whole problem; needs >= 2 devices."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run tests/mgpu_parity.py under torchrun on a multi-GPU box)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tests", "mgpu_parity.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
