@@ -14,7 +14,7 @@ echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_list.log 2>&1; echo "ncu list rc=$?"
 echo "== ncu full"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_sph_derivs|k_nbr_test|k_nbr_fill|k_energy$' -s 8 -c 4 -f -o $OUT/prof \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_sph_derivs|k_nbr_build|k_tile_runs|k_pack' -s 8 -c 4 -f -o $OUT/prof \
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
 fi
 ls -la $OUT

@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Generate the golden input/output vectors of tests/golden/*.npz with the CPU oracle.
+
+    python tests/golden/make_golden.py
+
+The reference holds no per-node derivative vectors for this path and cannot be built here, so these
+vectors are ORACLE outputs: they freeze the oracle (any later change of oracle/ that moves a value is caught by
+tests/test_golden.py) and give the GPU tests a fixture that does not depend on the oracle being rebuilt on the GPU box.
+Inputs are regenerated from the seeds stored in each file; the state arrays are stored as well so the fixture is
+self-contained."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CASES = {
+    # name: (ndim, n, nPerh, kind, kernel, options)
+    "sph3d_lattice": dict(ndim=3, n=7, nPerh=1.51, kind="lattice", kernel="BSpline", seed=41, ghosts=False,
+                          opts=dict(Cl=2.0, Cq=2.0)),
+    "asph3d_aniso": dict(ndim=3, n=6, nPerh=1.51, kind="aniso", kernel="BSpline", seed=42, ghosts=False,
+                         opts=dict(Cl=1.0, Cq=1.0, hEvolution=1, XSPH=0)),
+    "sph2d_ghosts_wendland": dict(ndim=2, n=14, nPerh=4.01, kind="lattice", kernel="WendlandC4", seed=43, ghosts=True,
+                                  opts=dict(Cl=1.0, Cq=1.0)),
+    "sph3d_limitedq_tensile": dict(ndim=3, n=6, nPerh=1.51, kind="lattice", kernel="BSpline", seed=44, ghosts=False, negP=True, q=True,
+                                   opts=dict(Cl=2.0, Cq=2.0, Qkind=1, balsara=1, epsTensile=0.3, compatibleEnergy=0, evolveTotalEnergy=1)),
+}
+
+
+def build_case(name):
+    import common
+    from spheral_b200 import kernel as K
+    c = CASES[name]
+    ndim = c["ndim"]
+    kern = {"BSpline": K.BSplineKernel, "WendlandC4": K.WendlandC4Kernel}[c["kernel"]](ndim)
+    WT = K.TableKernel(kern, 1000)
+    st, nInt, nGhost = common.make_problem(ndim, c["n"], nPerh=c["nPerh"], kind=c["kind"], seed=c["seed"], ghosts=c["ghosts"],
+                                           negP=c.get("negP", False), kext=WT.kernelExtent)
+    if c.get("q"):
+        st = common.add_q_fields(st, ndim, seed=c["seed"])
+    opts = dict(c["opts"], nPerh=c["nPerh"])
+    return c, WT, st, nInt, nGhost, opts
+
+
+def oracle_outputs(name):
+    import common
+    from oracle import oracle as orc
+    c, WT, st, nInt, nGhost, opts = build_case(name)
+    ndim = c["ndim"]
+    oo = orc.default_options(ndim, **opts)
+    s = common.to_oracle_state(st)
+    pi, pj, cnt = orc.pairs(ndim, nInt, nGhost, s["pos"], s["H"], WT.kernelExtent)
+    ref = orc.evaluate_derivatives(oo, common.oracle_table(orc, WT), s, nInt, nGhost, pi, pj, cnt)
+    out = {"pairs_i": pi, "pairs_j": pj, "counts": cnt, "nInt": np.int64(nInt), "nGhost": np.int64(nGhost)}
+    out.update({"state_" + k: v for k, v in st.items()})
+    out.update({"deriv_" + k: v for k, v in ref.items()})
+    return out
+
+
+if __name__ == "__main__":
+    for name in CASES:
+        out = oracle_outputs(name)
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("%-28s nodes %5d+%4d pairs %7d  %6.1f kB" % (name, out["nInt"], out["nGhost"], len(out["pairs_i"]), os.path.getsize(path)/1e3))

@@ -1,0 +1,89 @@
+"""The host-side mirror of the reference's Physics package interface (spheral_b200/physics.py): field keys, factory
+defaults and error behaviour (CPU), and one evaluateDerivatives(time, dt, dataBase, state, derivs) call against the
+oracle (GPU) written the way the reference's own unit test drives the package
+(tests/unit/SPH/testLinearVelocityGradient.py:268-292)."""
+import numpy as np
+import pytest
+
+import common
+from spheral_b200 import kernel as K
+
+
+def _setup(ndim=3, n=9, nPerh=1.51, **hydro_kw):
+    from spheral_b200 import physics as P
+    st, nInt, nGhost = common.make_problem(ndim, n, nPerh=nPerh, seed=77)
+    nodes = P.FluidNodeList("nodes", ndim, nInt, nGhost, nPerh=nPerh)
+    for abi in ("position", "velocity", "H", "mass", "massDensity", "specificThermalEnergy"):
+        nodes.setField(P.STATE_KEYS[abi], st[abi])
+    db = P.DataBase()
+    db.appendNodeList(nodes)
+    WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    hydro = P.SPH(dataBase=db, W=WT, **hydro_kw)
+    return P, st, nodes, db, WT, hydro
+
+
+def test_factory_defaults_and_registration_contract(sphlib):
+    P, st, nodes, db, WT, hydro = _setup()
+    # SPHHydros.py:88-94 -- default Q is LimitedMonaghanGingold with Cl = 2(kext/2), Cq = 2(kext/2)^2
+    assert isinstance(hydro.Q, P.LimitedMonaghanGingoldViscosity) and hydro.Q.Cl == 2.0 and hydro.Q.Cq == 2.0
+    assert hydro.preSubPackages() == [hydro.Q]
+    assert isinstance(hydro.postSubPackages()[0], P.SPHSmoothingScale)
+    assert hydro.requireConnectivity() and not hydro.requireGhostConnectivity()
+    assert hydro.compatibleEnergyEvolution and hydro.XSPH and hydro.correctVelocityGradient and not hydro.evolveTotalEnergy
+    assert isinstance(P.ASPH(WT, dataBase=db).postSubPackages()[0], P.ASPHSmoothingScale)
+    state, derivs = P.State(db, [hydro]), P.StateDerivatives(db, [hydro])
+    for key in ("mass", "position", "velocity", "mass density", "specific thermal energy", "H", "pressure", "sound speed",
+                "grad h corrections", "time step mask", "velocity gradient for artificial viscosity"):
+        assert state.registered(key, "nodes"), key
+    for key in ("delta position", "delta mass density", "delta velocity hydro", "delta specific thermal energy",
+                "velocity gradient", "internal velocity gradient", "mass density gradient", "M SPH gradient correction",
+                "new mass density", "normalization", "XSPH weight sum", "XSPH delta vi", "max viscous pressure",
+                "effective viscous pressure", "delta H", "new H", "mass zeroth moment", "mass first moment"):
+        assert derivs.registered(key, "nodes"), key
+    assert "pair-wise accelerations" in derivs
+    assert state.field("position", "nodes") is nodes.positions()            # enrolled by reference, not copied
+    assert state.policies["specific thermal energy"] == "SpecificThermalEnergyPolicy"
+
+
+def test_compatible_and_total_energy_are_exclusive(sphlib):
+    from spheral_b200 import physics as P
+    with pytest.raises(P.SPHB200Error, match="cannot simultaneously"):
+        _setup(compatibleEnergyEvolution=True, evolveTotalEnergy=True)
+
+
+@pytest.mark.gpu
+def test_evaluate_derivatives_through_physics_interface(sphlib, oracle):
+    P, st, nodes, db, WT, hydro = _setup(Q=None)
+    hydro.Q = P.MonaghanGingoldViscosity(2.0, 2.0)
+    hydro.initializeProblemStartup(db)
+    state, derivs = P.State(db, [hydro]), P.StateDerivatives(db, [hydro])
+    state.field("pressure", "nodes")[...] = st["pressure"]
+    state.field("sound speed", "nodes")[...] = st["soundSpeed"]
+    state.field("grad h corrections", "nodes")[...] = st["omegaGradh"]
+    with pytest.raises(P.SPHB200Error, match="connectivity is stale"):
+        hydro.evaluateDerivatives(0.0, 1.0, db, state, derivs)
+    npairs = hydro.updateConnectivity(db, state)
+    derivs.Zero()
+    hydro.evaluateDerivatives(0.0, 1.0, db, state, derivs)
+
+    nInt = nodes.numInternalNodes
+    oo = oracle.default_options(3, nPerh=1.51, Cl=2.0, Cq=2.0)
+    s = common.to_oracle_state(st)
+    pi, pj, cnt = oracle.pairs(3, nInt, 0, s["pos"], s["H"], WT.kernelExtent)
+    ref = oracle.evaluate_derivatives(oo, common.oracle_table(oracle, WT), s, nInt, 0, pi, pj, cnt)
+    assert npairs == len(pi)
+    floors = common.physical_floors(st, nInt, 3)
+    for abi, key in P.DERIV_KEYS.items():
+        got = derivs.field(key, "nodes")
+        assert common.field_err(got, np.asarray(ref[abi]).reshape(got.shape), nInt, floors[abi]) <= 1e-10, key
+    pa = np.asarray(hydro.pairAccelerations)
+    assert pa.shape == (npairs, 3) and np.abs(pa - ref["pairAccelerations"]).max() <= 1e-10*np.abs(ref["pairAccelerations"]).max()
+    # compatible energy through the policy hook: total energy is conserved by construction
+    eps0 = state.field("specific thermal energy", "nodes").copy()
+    dtc = 1.0e-3
+    hydro.updateSpecificThermalEnergy(dtc, db, state, derivs)
+    eps1 = state.field("specific thermal energy", "nodes")
+    m, v, a = st["mass"], st["velocity"], derivs.field("delta velocity hydro", "nodes")
+    dKE = (m*((v + dtc*a)**2).sum(axis=1)).sum()*0.5 - (m*(v**2).sum(axis=1)).sum()*0.5
+    dTE = (m*(eps1 - eps0)).sum()
+    assert abs(dKE + dTE) <= 1e-12*max(abs(dKE), abs(dTE), 1e-300)
