@@ -17,7 +17,7 @@ HEADERS = [os.path.join(CSRC, "sphb200_internal.cuh"), os.path.join(ROOT, "inclu
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-ccbin", "/usr/bin/g++",
-         "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+         "-I", os.path.join(ROOT, "include"), "-I", CSRC] + os.environ.get("SPHB200_NVCC_FLAGS", "").split()
 
 
 def _stale(target, deps):

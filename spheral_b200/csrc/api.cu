@@ -102,6 +102,7 @@ int alloc_nodes(sphb200_ctx* c, size_t n) {
     return 0;
   };
   if (reall(c->rows, cap*(size_t)(c->ndim == 3 ? 16 : 12))) return 1;
+  if (reall(c->aux2, cap*2)) return 1;
   for (int s = 0; s < DV_COUNT; ++s) if (reall(c->deriv[s], cap*(size_t)sphb200_deriv_width(c->ndim, s))) return 1;
   auto reall32 = [&](uint32_t*& p, size_t cnt) -> int {
     if (p) cudaFree(p);
@@ -188,7 +189,7 @@ void sphb200_destroy(sphb200_ctx* c) {
   for (int s = 0; s < S_COUNT; ++s) cudaFree(c->api[s]);
   for (int s = 0; s < DV_COUNT; ++s) cudaFree(c->deriv[s]);
   for (void* p : {(void*)c->W.coef, (void*)c->W.nperhVals, (void*)c->WQ.coef, (void*)c->WQ.nperhVals, (void*)c->cellKeyApi, (void*)c->cellStart,
-                  (void*)c->cellCursor, (void*)c->perm, (void*)c->skey, (void*)c->reduceBuf, (void*)c->rows, (void*)c->auxPneg, (void*)c->auxSomr2,
+                  (void*)c->cellCursor, (void*)c->perm, (void*)c->skey, (void*)c->reduceBuf, (void*)c->rows, (void*)c->aux2, (void*)c->auxPneg, (void*)c->auxSomr2,
                   (void*)c->auxDvDxQ, (void*)c->auxfCl, (void*)c->auxfCq, (void*)c->nbrCount, (void*)c->tileRows, (void*)c->tileOff, (void*)c->nbr,
                   (void*)c->counters, (void*)c->frows, (void*)c->scanTmp, (void*)c->pacc, (void*)c->stage,
                   (void*)c->runs, (void*)c->tileRunStart, (void*)c->tileRunCount, (void*)c->dilTab}) cudaFree(p);

@@ -16,7 +16,7 @@
 namespace {
 
 struct DerivArgs {
-  const double* rows; const uint32_t* perm;
+  const double* rows; const double* aux2; const uint32_t* perm;
   const uint32_t* nbrCount; const uint32_t* tileRows; const unsigned long long* tileOff; const uint32_t* nbr;
   const double *auxPneg, *auxSomr2, *auxDvDxQ, *auxfCl, *auxfCq;
   const double* tabW; const double* tabQ;       // interleaved coefficient tables (6 per interval)
@@ -36,24 +36,19 @@ struct DerivArgs {
 // the pair loop are finite, positive and far from the denormal range.  The 1e-10 parity bar leaves 6 digits of head room.
 __device__ __forceinline__ double fast_rcp(double x) {
   double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));       // relative error e0 <= 2^-23
   double e = fma(-x, r, 1.0);
-  e = fma(e, e, e);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
+  e = fma(e, e, e);                                            // r*(1 + e + e^2): error e0^3 ~ 2^-69
   return fma(r, e, r);
 }
 __device__ __forceinline__ double fast_rsqrt(double x) {
   double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));     // relative error e0 <= 2^-22
   const double t = y*y;
   const double e = fma(-t, x, 1.0);
   const double p = fma(e, 0.375, 0.5);
   const double q = e*y;
-  y = fma(p, q, y);
-  // one more Newton step: cheap insurance that the result is good to the last few ulps
-  const double e2 = fma(-(y*y), x, 1.0);
-  return fma(0.5*y, e2, y);
+  return fma(p, q, y);                                         // y*(1 + e/2 + 3e^2/8): error O(e0^3) ~ 2^-64
 }
 
 __device__ __forceinline__ double2 lds128(unsigned addr) {      // 32-bit shared-window address: no generic->shared conversion per use
@@ -69,18 +64,27 @@ __device__ __forceinline__ double2 lds128(unsigned addr) {      // 32-bit shared
 // of an integer, where the true division decides (an off-by-one interval would change W at the 1e-6 level).
 __device__ __forceinline__ void table_eval_raw(unsigned tab, double kext, double xmin, double xstep, double rxstep,
                                                uint32_t n1, double eta, double& W, double& gW) {
-  double x = eta - xmin;
-  x = x > 0.0 ? x : 0.0;
+  const double x = eta - xmin;                  // max(0, .) of the reference is applied to the integer index below
   const double q = x*rxstep;
   int k = __double2int_rz(q);
   const double fr = q - (double)k;
-  if (fr < 1.0e-9 || fr > 1.0 - 1.0e-9) k = (int)(x/xstep);
-  k = min(k, (int)n1);
+#if SPHB200_TABLE_ZERO
+  k = max(min(k, (int)n1 + 1), 0);              // record n1+1 is all zeros: eta >= kext gives W = gradW = 0 without a select
+  if (fr < 1.0e-9 || fr > 1.0 - 1.0e-9)         // within 1e-9 of an interval edge (or of kext): the reference's own expressions decide
+    k = (eta < kext) ? min((int)(fmax(x, 0.0)/xstep), (int)n1) : (int)n1 + 1;
+  const unsigned c = tab + 48u*(unsigned)k;
+  const double2 c01 = lds128(c), c23 = lds128(c + 16u), c45 = lds128(c + 32u);
+  W  = fma(fma(c23.x, eta, c01.y), eta, c01.x);
+  gW = fma(fma(c45.y, eta, c45.x), eta, c23.y);
+#else
+  if (fr < 1.0e-9 || fr > 1.0 - 1.0e-9) k = (int)(fmax(x, 0.0)/xstep);
+  k = max(min(k, (int)n1), 0);
   const unsigned c = tab + 48u*(unsigned)k;
   const double2 c01 = lds128(c), c23 = lds128(c + 16u), c45 = lds128(c + 32u);
   const bool in = eta < kext;
   W  = in ? fma(fma(c23.x, eta, c01.y), eta, c01.x) : 0.0;
   gW = in ? fma(fma(c45.y, eta, c45.x), eta, c23.y) : 0.0;
+#endif
 }
 
 template <int DIM> __device__ __forceinline__ double rootnu(double x) {
@@ -204,9 +208,34 @@ __device__ __forceinline__ void cp_async16_s(unsigned smemDst, const void* gmemS
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smemDst), "l"(gmemSrc) : "memory");
 }
 
-constexpr int PAIR_STAGES = 4;          // depth of the neighbour-row ring
-constexpr int PAIR_WARPS = 4;           // warps (= tiles in flight) per CTA
-template <int DIM> struct RingGeom { static constexpr int ROWB = Dm<DIM>::ROW*8 + 16; };   // +16 B pad: conflict-free 128-bit LDS
+#ifndef SPHB200_COPY_LANES
+#define SPHB200_COPY_LANES 8
+#endif
+#ifndef SPHB200_TABLE_ZERO
+#define SPHB200_TABLE_ZERO 1
+#endif
+#ifndef SPHB200_PAIR_STAGES
+#define SPHB200_PAIR_STAGES 4
+#endif
+#ifndef SPHB200_PAIR_WARPS
+#define SPHB200_PAIR_WARPS 4
+#endif
+#ifndef SPHB200_PAIR_CTAS
+#define SPHB200_PAIR_CTAS 2
+#endif
+__device__ __forceinline__ const unsigned char* mad_wide(uint32_t a, uint32_t b, const unsigned char* c) {   // c + a*b in one IMAD.WIDE
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"((unsigned long long)c));
+  return reinterpret_cast<const unsigned char*>(r);
+}
+
+constexpr int PAIR_STAGES = SPHB200_PAIR_STAGES;   // depth of the neighbour-row ring
+constexpr int PAIR_WARPS = SPHB200_PAIR_WARPS;     // warps (= tiles in flight) per CTA
+constexpr int PAIR_CTAS = SPHB200_PAIR_CTAS;       // resident CTAs per SM the register budget is sized for
+template <int DIM> struct RingGeom {
+  static constexpr int ROWB = Dm<DIM>::ROW*8 + 16;          // +16 B pad: conflict-free 128-bit LDS
+  static constexpr int STAGEB = 32*ROWB + 32*16;             // 32 rows + 32 aux records {det H, 1/rho}
+};
 
 // The pair-loop kernel: one warp per tile of 32 Morton-consecutive nodes, lane <-> node i; persistent CTAs stride over tiles.
 //   GEN    : general path -- every option of the reference is honoured at run time (LimitedMG, Balsara, Cl/Cq multipliers,
@@ -214,15 +243,16 @@ template <int DIM> struct RingGeom { static constexpr int ROWB = Dm<DIM>::ROW*8 
 //   !GEN   : the plain MonaghanGingold path named by BASELINE.json, with XSPH / SPH-moments / pair-acceleration storage
 //            fixed at compile time so that unused accumulators cost no registers.
 template <int DIM, bool GEN, bool XSPH_, bool HSPH_, bool COMPAT_>
-__global__ void __launch_bounds__(32*PAIR_WARPS, 2) k_sph_derivs(DerivArgs a) {
+__global__ void __launch_bounds__(32*PAIR_WARPS, PAIR_CTAS) k_sph_derivs(DerivArgs a) {
   using D = Dm<DIM>;
   constexpr int NS = D::NS, NT = D::NT, ROW = D::ROW;
   constexpr int ROWB = RingGeom<DIM>::ROWB;
   extern __shared__ __align__(16) double smem[];
   // stage the interleaved W/gradW table(s) in shared memory
-  const uint32_t nW = 6u*(a.n1W + 1u), nQ = (GEN && !a.oneKernel) ? 6u*(a.n1Q + 1u) : 0u;
-  for (uint32_t k = threadIdx.x; k < nW; k += blockDim.x) smem[k] = a.tabW[k];
-  for (uint32_t k = threadIdx.x; k < nQ; k += blockDim.x) smem[nW + k] = a.tabQ[k];
+  // n1+1 interval records of 6 coefficients plus one all-zero record (eta >= kext)
+  const uint32_t nW = 6u*(a.n1W + 2u), nQ = (GEN && !a.oneKernel) ? 6u*(a.n1Q + 2u) : 0u;
+  for (uint32_t k = threadIdx.x; k < nW; k += blockDim.x) smem[k] = (k < nW - 6u) ? a.tabW[k] : 0.0;
+  for (uint32_t k = threadIdx.x; k < nQ; k += blockDim.x) smem[nW + k] = (k < nQ - 6u) ? a.tabQ[k] : 0.0;
   __syncthreads();
   const unsigned tW = (unsigned)__cvta_generic_to_shared(smem);
   const unsigned tQ = tW + 8u*nW;
@@ -231,7 +261,8 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, 2) k_sph_derivs(DerivArgs a) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   // ring of this warp: PAIR_STAGES stages x 32 lane slots of ROWB bytes
-  const unsigned warpRing = tW + 8u*(nW + nQ) + (unsigned)warp*(PAIR_STAGES*32*ROWB);
+  constexpr int STAGEB = RingGeom<DIM>::STAGEB;
+  const unsigned warpRing = tW + 8u*(nW + nQ) + (unsigned)warp*(PAIR_STAGES*STAGEB);
   const sphb200_options& o = a.o;
   const size_t nTiles = (a.n + SPHB200_TILE - 1)/SPHB200_TILE;
   for (size_t tile = (size_t)blockIdx.x*PAIR_WARPS + warp; tile < nTiles; tile += (size_t)gridDim.x*PAIR_WARPS) {
@@ -297,16 +328,31 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, 2) k_sph_derivs(DerivArgs a) {
   constexpr int CH = ROW*8/16;                       // 16-byte chunks per row: 8 (3-D) / 6 (2-D)
   // positions past the end of a lane's list fetch row 0 (never read back): no predication in the copy
   const unsigned char* const rowsB = reinterpret_cast<const unsigned char*>(a.rows);
+  const unsigned char* const srcLane = rowsB + 16*(lane & (SPHB200_COPY_LANES - 1));
   auto issue_rows = [&](uint32_t p, uint32_t jraw) {  // jraw: this lane's list entry at position p (0 if none)
     const uint32_t jrow = jraw;
-    const unsigned stage = warpRing + (p % PAIR_STAGES)*(32u*ROWB);
+    const unsigned stage = warpRing + (p % PAIR_STAGES)*(unsigned)STAGEB;
+    cp_async16_s(stage + 32u*ROWB + 16u*lane, a.aux2 + 2*(size_t)jrow);        // this lane's own neighbour: {det H, 1/rho}
+#if SPHB200_COPY_LANES == 8
     if (CH == 8) {
+      // 8 lanes per row (one 16-byte chunk each): an LDGSTS touches 4 full lines
       const unsigned dst = stage + (unsigned)(lane >> 3)*ROWB + 16u*(lane & 7);
-      const unsigned char* const src = rowsB + 16*(lane & 7);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const uint32_t jr = __shfl_sync(0xffffffffu, jrow, 4*q + (lane >> 3));
-        cp_async16_s(dst + (unsigned)q*(4u*ROWB), src + (size_t)jr*(ROW*8));
+        cp_async16_s(dst + (unsigned)q*(4u*ROWB), mad_wide(jr, (uint32_t)(ROW*8), srcLane));
+      }
+    } else
+#endif
+    if (CH == 8) {
+      // 4 lanes per row (two 16-byte chunks each): 4 shuffles + 4 address computations feed 8 LDGSTS
+      const unsigned dst = stage + (unsigned)(lane >> 2)*ROWB + 16u*(lane & 3);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t jr = __shfl_sync(0xffffffffu, jrow, 8*g + (lane >> 2));
+        const unsigned char* src = mad_wide(jr, (uint32_t)(ROW*8), srcLane);
+        cp_async16_s(dst + (unsigned)g*(8u*ROWB), src);
+        cp_async16_s(dst + (unsigned)g*(8u*ROWB) + 64u, src + 64);
       }
     } else {
 #pragma unroll
@@ -334,10 +380,13 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, 2) k_sph_derivs(DerivArgs a) {
     __syncwarp();                                     // ... and so have every other lane's
     // ---- node j state: one 128-byte (3-D) / 96-byte (2-D) row, from this lane's ring slot
     double rw[ROW];
+    double2 aux;
     {
-      const unsigned rp = warpRing + (k % PAIR_STAGES)*(32u*ROWB) + (unsigned)lane*ROWB;
+      const unsigned st = warpRing + (k % PAIR_STAGES)*(unsigned)STAGEB;
+      const unsigned rp = st + (unsigned)lane*ROWB;
 #pragma unroll
       for (int q = 0; q < ROW/2; ++q) { const double2 v = lds128(rp + 16u*q); rw[2*q] = v.x; rw[2*q + 1] = v.y; }
+      aux = lds128(st + 32u*ROWB + 16u*lane);
     }
     {
       // refill the stage consumed in the previous iteration (every lane is past its reads: they precede the __syncwarp above)
@@ -351,8 +400,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, 2) k_sph_derivs(DerivArgs a) {
     const uint32_t j = GEN ? a.nbr[slot] : 0u;
     const double* rj = rw + D::R_POS; const double* vj = rw + D::R_VEL; const double* Hj = rw + D::R_H;
     const double mj = rw[D::R_M], rhoj = rw[D::R_RHO], cj = rw[D::R_CS];
-    const double Hdetj = sym_det<DIM>(Hj);
-    const double rhojInv = fast_rcp(rhoj);
+    const double Hdetj = aux.x, rhojInv = aux.y;          // per-node values, computed once in k_pack
 
     // SPH.cc:363-369 : rij, eta = H.rij, |eta|, unit vectors (safeInvVar: 0 for coincident nodes)
     double rij[DIM], etai[DIM], etaj[DIM];
@@ -620,7 +668,7 @@ static double host_table_eval(const TableDev& t, double eta, bool grad) {
 
 int sphb200_launch_derivs(sphb200_ctx* c) {
   DerivArgs a{};
-  a.rows = c->rows; a.perm = c->perm; a.nbrCount = c->nbrCount; a.tileRows = c->tileRows; a.tileOff = c->tileOff; a.nbr = c->nbr;
+  a.rows = c->rows; a.aux2 = c->aux2; a.perm = c->perm; a.nbrCount = c->nbrCount; a.tileRows = c->tileRows; a.tileOff = c->tileOff; a.nbr = c->nbr;
   const bool tens = c->opt.epsTensile != 0.0;
   const bool needQ = (c->opt.Qkind == SPHB200_Q_LIMITED_MG) || c->opt.balsara;
   const bool mult = c->have[S_FCL] && c->have[S_FCQ];
@@ -642,13 +690,13 @@ int sphb200_launch_derivs(sphb200_ctx* c) {
   }
   a.pacc = c->pacc; a.nSlots = c->nSlots;
   const int wpb = PAIR_WARPS;
-  const size_t ringBytes = (size_t)PAIR_WARPS*PAIR_STAGES*32*(c->ndim == 3 ? RingGeom<3>::ROWB : RingGeom<2>::ROWB);
-  const size_t shm = (size_t)6*(c->W.n1 + 1)*sizeof(double) + (c->oneKernel ? 0 : (size_t)6*(c->WQ.n1 + 1)*sizeof(double)) + ringBytes;
+  const size_t ringBytes = (size_t)PAIR_WARPS*PAIR_STAGES*(c->ndim == 3 ? RingGeom<3>::STAGEB : RingGeom<2>::STAGEB);
+  const size_t shm = (size_t)6*(c->W.n1 + 2)*sizeof(double) + (c->oneKernel ? 0 : (size_t)6*(c->WQ.n1 + 2)*sizeof(double)) + ringBytes;
   if (shm > 226*1024) return sphb200_fail(c, "kernel table too large for shared memory");
   // persistent CTAs: 2 per SM (register-limited), each striding over the tiles
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
-  const unsigned nb = (unsigned)std::min<size_t>((c->nTiles + wpb - 1)/wpb, (size_t)nsm*2);
+  const unsigned nb = (unsigned)std::min<size_t>((c->nTiles + wpb - 1)/wpb, (size_t)nsm*PAIR_CTAS);
   const bool gen = (c->opt.Qkind != SPHB200_Q_MG) || c->opt.balsara || mult || tens || !c->oneKernel ||
                    c->opt.linearInExpansion || c->opt.quadraticInExpansion;
   if (c->ndim == 3) { if (launch_dim<3>(c, a, nb, wpb*32, shm, gen)) return 1; }

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(RB) k_cell_order(const uint32_t* __restrict__ 
 // ---- K1d: gather the host-ordered fields into Morton-sorted 128-byte node rows --------------------------------------------
 struct PackArgs {
   const double *pos, *vel, *H, *mass, *rho, *P, *omega, *cs, *DvDxQ, *fCl, *fCq;
-  double *rows, *auxPneg, *auxSomr2, *auxDvDxQ, *auxfCl, *auxfCq;
+  double *rows, *aux2, *auxPneg, *auxSomr2, *auxDvDxQ, *auxfCl, *auxfCq;
   const uint32_t *perm, *keyApi;
   uint32_t* skey;
   size_t n;
@@ -170,6 +170,10 @@ __global__ void __launch_bounds__(RB) k_pack(PackArgs a) {
   r[D::R_M] = m; r[D::R_RHO] = rho; r[D::R_CS] = cs;
   r[D::R_PRHO] = safeOmega*P/(rho*rho);                          // SPH.cc:425 with Peff == P
   if (DIM == 2) r[11] = 0.0;
+  { double hh[D::NS];
+#pragma unroll
+    for (int k = 0; k < D::NS; ++k) hh[k] = r[D::R_H + k];
+    a.aux2[2*s] = sym_det<DIM>(hh); a.aux2[2*s + 1] = 1.0/rho; }
   if (a.auxPneg) { a.auxPneg[s] = (P < 0.0 ? -P : 0.0); a.auxSomr2[s] = safeOmega/(rho*rho); }
   if (a.auxDvDxQ) {
 #pragma unroll
@@ -593,7 +597,7 @@ int sphb200_pack_rows(sphb200_ctx* c) {
   a.P = c->have[S_P] ? c->api[S_P] : nullptr; a.omega = c->have[S_OMEGA] ? c->api[S_OMEGA] : nullptr;
   a.cs = c->have[S_CS] ? c->api[S_CS] : nullptr;
   a.DvDxQ = needQ ? c->api[S_DVDXQ] : nullptr; a.fCl = mult ? c->api[S_FCL] : nullptr; a.fCq = mult ? c->api[S_FCQ] : nullptr;
-  a.rows = c->rows; a.auxPneg = tens ? c->auxPneg : nullptr; a.auxSomr2 = tens ? c->auxSomr2 : nullptr;
+  a.rows = c->rows; a.aux2 = c->aux2; a.auxPneg = tens ? c->auxPneg : nullptr; a.auxSomr2 = tens ? c->auxSomr2 : nullptr;
   a.auxDvDxQ = needQ ? c->auxDvDxQ : nullptr; a.auxfCl = mult ? c->auxfCl : nullptr; a.auxfCq = mult ? c->auxfCq : nullptr;
   a.perm = c->perm; a.keyApi = c->cellKeyApi; a.skey = c->skey; a.n = c->n;
   { size_t fcap = c->frows ? c->frowsCap : 0;

@@ -92,6 +92,7 @@ struct sphb200_ctx {
   // sorted rows + aux
   double* rows = nullptr;
   float* frows = nullptr; size_t frowsCap = 0;   // FP32 pre-filter rows of K2 (relpos, H, band thresholds)
+  double* aux2 = nullptr;           // {det H, 1/rho} per node (sorted): the per-node part of the pair arithmetic
   double* auxPneg = nullptr;        // max(-P,0)                      (tensile, SPH.cc:417)
   double* auxSomr2 = nullptr;       // safeInv(omega)/(rho*rho)        (tensile)
   double* auxDvDxQ = nullptr;       // ndim*ndim per node (sorted)     (LimitedMG / Balsara)
