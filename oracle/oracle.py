@@ -89,6 +89,15 @@ def lib():
                                                u32p, C.POINTER(Derivs), C.c_int]
         L.orc_update_energy_compatible.argtypes = [C.c_int, C.c_size_t, C.c_size_t, _dp, _dp, _dp, _dp, C.c_size_t,
                                                    u32p, u32p, _dp, C.c_double, _dp]
+        L.orc_crk_sum_volume.argtypes = [C.c_int, C.POINTER(Table), C.c_size_t, C.c_size_t, _dp, _dp, C.c_size_t, u32p, u32p, _dp]
+        L.orc_crk_corrections.argtypes = [C.c_int, C.POINTER(Table), C.c_size_t, C.c_size_t, _dp, _dp, _dp, C.c_size_t,
+                                          u32p, u32p, _dp]
+        L.orc_crk_sum_density.argtypes = [C.c_int, C.POINTER(Table), C.c_size_t, C.c_size_t, _dp, _dp, _dp, _dp, C.c_size_t,
+                                          u32p, u32p, C.c_double, C.c_double, _dp]
+        L.orc_crk_evaluate_derivatives.argtypes = [C.POINTER(Options), C.POINTER(Table), C.c_size_t, C.c_size_t,
+                                                   C.POINTER(State), _dp, _dp, C.c_size_t, u32p, u32p, C.POINTER(Derivs)]
+        L.orc_rk_kernel_grad.argtypes = [C.c_int, C.POINTER(Table), _dp, _dp, _dp, _dp, _dp]
+        L.orc_rk_kernel_grad.restype = None
         _lib = L
     return _lib
 
@@ -260,3 +269,73 @@ def update_energy_compatible(ndim, nInt, nGhost, mass, vel, DvDt, DepsDt0, pi, p
     lib().orc_update_energy_compatible(ndim, nInt, nGhost, _p(mass), _p(vel), _p(DvDt), _p(DepsDt0), len(pi),
                                        _u(pi), _u(pj), _p(pacc), multiplier, _p(eps))
     return eps
+
+
+# ---- CRKSPH (LinearOrder reproducing kernels, RKSumVolume) -------------------------------------------------
+def crk_ncorr(ndim):
+    return (1 + ndim)*(1 + ndim)
+
+
+def crk_sum_volume(ndim, W, nInt, nGhost, pos, H, pi, pj, vol=None):
+    """computeRKSumVolume: internal entries are written, ghost entries keep the caller's values."""
+    pos, H = _c(pos), _c(H)
+    vol = np.zeros(nInt + nGhost) if vol is None else np.array(vol, dtype=np.float64, copy=True)
+    pi, pj = _c(pi, np.uint32), _c(pj, np.uint32)
+    t = W.ctable()
+    lib().orc_crk_sum_volume(ndim, C.byref(t), nInt, nGhost, _p(pos), _p(H), len(pi), _u(pi), _u(pj), _p(vol))
+    return vol
+
+
+def crk_corrections(ndim, W, nInt, nGhost, pos, H, vol, pi, pj, corr=None):
+    """RKUtilities::computeCorrections (LinearOrder): (n, (1+ndim)^2); internal rows written."""
+    pos, H, vol = _c(pos), _c(H), _c(vol)
+    nc = crk_ncorr(ndim)
+    corr = np.zeros((nInt + nGhost, nc)) if corr is None else np.array(corr, dtype=np.float64, copy=True).reshape(-1, nc)
+    pi, pj = _c(pi, np.uint32), _c(pj, np.uint32)
+    t = W.ctable()
+    lib().orc_crk_corrections(ndim, C.byref(t), nInt, nGhost, _p(pos), _p(H), _p(vol), len(pi), _u(pi), _u(pj), _p(corr))
+    return corr
+
+
+def crk_sum_density(ndim, W, nInt, nGhost, pos, mass, vol, H, pi, pj, rhoMin=0.0, rhoMax=1.0e300, rho=None):
+    pos, mass, vol, H = _c(pos), _c(mass), _c(vol), _c(H)
+    rho = np.zeros(nInt + nGhost) if rho is None else np.array(rho, dtype=np.float64, copy=True)
+    pi, pj = _c(pi, np.uint32), _c(pj, np.uint32)
+    t = W.ctable()
+    lib().orc_crk_sum_density(ndim, C.byref(t), nInt, nGhost, _p(pos), _p(mass), _p(vol), _p(H), len(pi), _u(pi), _u(pj),
+                              rhoMin, rhoMax, _p(rho))
+    return rho
+
+
+def rk_kernel_grad(ndim, W, x, H, corr):
+    x, H, corr = _c(x), _c(H), _c(corr)
+    WR = C.c_double()
+    g = np.zeros(ndim)
+    t = W.ctable()
+    lib().orc_rk_kernel_grad(ndim, C.byref(t), _p(x), _p(H), _p(corr), C.byref(WR), _p(g))
+    return WR.value, g
+
+
+def crk_evaluate_derivatives(opts, W, state, vol, corr, nInt, nGhost, pi, pj):
+    """CRKSPH::evaluateDerivatives + smoothing-scale sub-package.  Same output dict as evaluate_derivatives."""
+    L = lib()
+    nd = opts.ndim
+    n = nInt + nGhost
+    ns, nt = nsym(nd), nd*nd
+    keep = {k: _c(state.get(k)) for k in ("pos", "vel", "H", "mass", "rho", "P", "cs", "omega", "DvDxQ", "fCl", "fCq")}
+    s = State(**{k: _p(v) for k, v in keep.items()})
+    npairs = len(pi)
+    shapes = dict(DxDt=nd, DrhoDt=1, DvDt=nd, DepsDt=1, DvDx=nt, localDvDx=nt, gradRho=nd, M=nt, localM=nt,
+                  rhoSum=1, normalization=1, maxViscousPressure=1, effViscousPressure=1, XSPHWeightSum=1,
+                  XSPHDeltaV=nd, DHDt=ns, Hideal=ns, massZerothMoment=1, massFirstMoment=nd)
+    out = {k: np.zeros((n, w) if w > 1 else n) for k, w in shapes.items()}
+    out["pairAccelerations"] = np.zeros((npairs, nd))
+    d = Derivs(**{k: _p(v) for k, v in out.items()})
+    pi, pj = _c(pi, np.uint32), _c(pj, np.uint32)
+    vol, corr = _c(vol), _c(corr)
+    tW = W.ctable()
+    rc = L.orc_crk_evaluate_derivatives(C.byref(opts), C.byref(tW), nInt, nGhost, C.byref(s), _p(vol), _p(corr),
+                                        npairs, _u(pi), _u(pj), C.byref(d))
+    if rc != 0:
+        raise RuntimeError("oracle error %d" % rc)
+    return out

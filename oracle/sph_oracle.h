@@ -125,6 +125,23 @@ int orc_update_energy_compatible(int ndim, size_t nInt, size_t nGhost, const dou
                                  const uint32_t* pi, const uint32_t* pj, const double* pairAccelerations,
                                  double multiplier, double* eps);
 
+/* ---- CRKSPH (BASELINE config 4): LinearOrder reproducing kernels, RKSumVolume ---------------------
+   corrections: (1+ndim)*(1+ndim) doubles per node = C[1+ndim] then dC_d[1+ndim] per direction
+   (RKCoefficients layout, RK/RKUtilitiesInline.hh:58-105).  vol / corr / rho are written for internal
+   nodes only; ghost entries must be supplied by the caller (the reference's boundary conditions). */
+int orc_crk_sum_volume(int ndim, const orc_table* W, size_t nInt, size_t nGhost, const double* pos, const double* H,
+                       size_t npairs, const uint32_t* pi, const uint32_t* pj, double* vol);      /* RK/computeRKSumVolume.cc:33-116 */
+int orc_crk_corrections(int ndim, const orc_table* W, size_t nInt, size_t nGhost, const double* pos, const double* H,
+                        const double* vol, size_t npairs, const uint32_t* pi, const uint32_t* pj, double* corr);  /* RK/RKUtilities.cc:252-491 */
+int orc_crk_sum_density(int ndim, const orc_table* W, size_t nInt, size_t nGhost, const double* pos, const double* mass,
+                        const double* vol, const double* H, size_t npairs, const uint32_t* pi, const uint32_t* pj,
+                        double rhoMin, double rhoMax, double* rho);                              /* CRKSPH/computeCRKSPHSumMassDensity.cc:21-131 */
+int orc_crk_evaluate_derivatives(const orc_options* o, const orc_table* W, size_t nInt, size_t nGhost,
+                                 const orc_state* s, const double* vol, const double* corr,
+                                 size_t npairs, const uint32_t* pi, const uint32_t* pj, orc_derivs* d);  /* CRKSPH/CRKSPH.cc:176-440 */
+void orc_rk_kernel_grad(int ndim, const orc_table* W, const double* x, const double* H, const double* corr,
+                        double* WR, double* gradWR);                                             /* RK/RKUtilities.cc:180-209 */
+
 #ifdef __cplusplus
 }
 #endif
