@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPHB200_ABI_VERSION 1
+#define SPHB200_ABI_VERSION 2
 
 typedef struct sphb200_ctx sphb200_ctx;
 
@@ -38,6 +38,9 @@ enum { SPHB200_Q_MG = 0, SPHB200_Q_LIMITED_MG = 1 };
 enum { SPHB200_H_SPH = 0, SPHB200_H_ASPH = 1, SPHB200_H_NONE = 2 };
 /* analytic kernels for sphb200_table_kernel_build (Kernel/*KernelInline.hh) */
 enum { SPHB200_KERNEL_BSPLINE = 0, SPHB200_KERNEL_WENDLANDC4 = 1, SPHB200_KERNEL_WENDLANDC2 = 2 };
+/* hydro flavour served by the context: SPH<Dim> (SPH/SPH.cc) | CRKSPH<Dim> (CRKSPH/CRKSPH.cc; RKOrder::LinearOrder,
+   RKVolumeType::RKSumVolume -- the settings of tests/functional/Hydro/Sedov/Sedov-spherical-3d.py:60-61) */
+enum { SPHB200_HYDRO_SPH = 0, SPHB200_HYDRO_CRKSPH = 1 };
 /* which TableKernel a table upload refers to (SPHBase.hh:182-183: kernel() / PiKernel()) */
 enum { SPHB200_TABLE_W = 0, SPHB200_TABLE_WPI = 1 };
 
@@ -59,6 +62,7 @@ typedef struct {
   double etaCritFrac, etaFoldFrac;
   int    hEvolution;                /* SPHB200_H_* */
   double hmin, hmax;
+  int    hydro;                     /* SPHB200_HYDRO_* (0 = SPH) */
 } sphb200_options;
 
 /* State fields read by the path (SPH.cc:206-216; Appendix B of SURVEY.md). Bits for fieldMask. */
@@ -67,11 +71,14 @@ enum {
   SPHB200_F_MASS = 1u << 3,      SPHB200_F_RHO = 1u << 4,       SPHB200_F_EPS = 1u << 5,
   SPHB200_F_PRESSURE = 1u << 6,  SPHB200_F_SOUNDSPEED = 1u << 7, SPHB200_F_OMEGA = 1u << 8,
   SPHB200_F_DVDXQ = 1u << 9,     SPHB200_F_FCL = 1u << 10,      SPHB200_F_FCQ = 1u << 11,
+  /* CRKSPH only: HydroFieldNames::volume (Scalar) and RKFieldNames::rkCorrections(LinearOrder)
+     ((1+ndim)^2 doubles per node: C[1+ndim], then dC_d[1+ndim] per direction; RK/RKUtilitiesInline.hh:58-105) */
+  SPHB200_F_VOLUME = 1u << 12,   SPHB200_F_RKCORR = 1u << 13,
   SPHB200_F_ALL_BASIC = 0x1FFu
 };
 typedef struct {
   const double *position, *velocity, *H, *mass, *massDensity, *specificThermalEnergy,
-               *pressure, *soundSpeed, *omegaGradh, *DvDxQ, *fCl, *fCq;
+               *pressure, *soundSpeed, *omegaGradh, *DvDxQ, *fCl, *fCq, *volume, *rkCorrections;
 } sphb200_host_state;
 
 /* Derivative fields written by the path (SPH.cc:230-245, SPHSmoothingScale.cc:130-137). Bits for fieldMask. */
@@ -143,6 +150,21 @@ int  sphb200_download_derivs(sphb200_ctx* ctx, unsigned fieldMask, const sphb200
 int  sphb200_download_pair_accelerations(sphb200_ctx* ctx, double* pairAccelerations, size_t cap);
 /* ArtificialViscosityHandle::postStateUpdate copy DvDx -> Q velocity gradient (ArtificialViscosityHandle.cc:165-180) */
 int  sphb200_copy_DvDx_to_Q(sphb200_ctx* ctx);
+
+/* ---- CRKSPH (contexts created with hydro = SPHB200_HYDRO_CRKSPH) --------------------------------
+   The reference sequence per stage is RKCorrections::preStepInitialize (volumes, RK/RKCorrections.cc:298-340) ->
+   boundaries -> RKCorrections::initialize (corrections, :346-372) -> boundaries -> CRKSPH::evaluateDerivatives.
+   Each call below writes the INTERNAL entries of its field on the device; ghost entries are the caller's (boundary
+   conditions / halo exchange), exactly as in the reference, and travel with upload_state / halo_pack+unpack
+   under SPHB200_F_VOLUME / SPHB200_F_RKCORR.
+     sphb200_crk_compute_volume       computeRKSumVolume                   RK/computeRKSumVolume.cc:33-116
+     sphb200_crk_compute_corrections  RKUtilities::computeCorrections      RK/RKUtilities.cc:252-491 (LinearOrder)
+     sphb200_crk_sum_mass_density     computeCRKSPHSumMassDensity          CRKSPH/computeCRKSPHSumMassDensity.cc:21-131
+   sphb200_evaluate_derivatives then runs CRKSPH<Dim>::evaluateDerivativesImpl (CRKSPH/CRKSPH.cc:176-440) + the
+   smoothing-scale sub-package; pair accelerations and sphb200_update_energy_compatible work as for SPH. */
+int  sphb200_crk_compute_volume(sphb200_ctx* ctx);
+int  sphb200_crk_compute_corrections(sphb200_ctx* ctx);
+int  sphb200_crk_sum_mass_density(sphb200_ctx* ctx, double rhoMin, double rhoMax);
 
 /* ---- compatible energy -----------------------------------------------------------------------------------------
    replaces: SpecificThermalEnergyPolicy::update (Hydro/SpecificThermalEnergyPolicy.cc:47-174):

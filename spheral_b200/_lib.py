@@ -15,9 +15,10 @@ Q_MG, Q_LIMITED_MG = 0, 1
 H_SPH, H_ASPH, H_NONE = 0, 1, 2
 KERNEL_BSPLINE, KERNEL_WENDLANDC4, KERNEL_WENDLANDC2 = 0, 1, 2
 TABLE_W, TABLE_WPI = 0, 1
+HYDRO_SPH, HYDRO_CRKSPH = 0, 1
 
 STATE_FIELDS = ("position", "velocity", "H", "mass", "massDensity", "specificThermalEnergy",
-                "pressure", "soundSpeed", "omegaGradh", "DvDxQ", "fCl", "fCq")
+                "pressure", "soundSpeed", "omegaGradh", "DvDxQ", "fCl", "fCq", "volume", "rkCorrections")
 STATE_BITS = {k: 1 << i for i, k in enumerate(STATE_FIELDS)}
 DERIV_FIELDS = ("DxDt", "DrhoDt", "DvDt", "DepsDt", "DvDx", "localDvDx", "gradRho", "M", "localM",
                 "rhoSum", "normalization", "maxViscousPressure", "effViscousPressure", "XSPHWeightSum",
@@ -32,6 +33,8 @@ def state_width(ndim, name):
         return 6 if ndim == 3 else 3
     if name == "DvDxQ":
         return ndim*ndim
+    if name == "rkCorrections":
+        return (ndim + 1)*(ndim + 1)
     return 1
 
 
@@ -53,7 +56,7 @@ class Options(C.Structure):
                 ("negligibleSoundSpeed", C.c_double),
                 ("balsara", C.c_int), ("linearInExpansion", C.c_int), ("quadraticInExpansion", C.c_int),
                 ("etaCritFrac", C.c_double), ("etaFoldFrac", C.c_double),
-                ("hEvolution", C.c_int), ("hmin", C.c_double), ("hmax", C.c_double)]
+                ("hEvolution", C.c_int), ("hmin", C.c_double), ("hmax", C.c_double), ("hydro", C.c_int)]
 
 
 class HostState(C.Structure):
@@ -76,7 +79,8 @@ EXPORTS = ("sphb200_abi_version", "sphb200_create", "sphb200_destroy", "sphb200_
            "sphb200_download_pairs", "sphb200_download_neighbor_counts", "sphb200_evaluate_derivatives",
            "sphb200_download_derivs", "sphb200_download_pair_accelerations", "sphb200_copy_DvDx_to_Q",
            "sphb200_update_energy_compatible", "sphb200_halo_bytes_per_node", "sphb200_halo_pack",
-           "sphb200_halo_unpack", "sphb200_node_bounds", "sphb200_halo_select", "sphb200_stream", "sphb200_get_stats", "sphb200_measure_fp64_peak")
+           "sphb200_halo_unpack", "sphb200_node_bounds", "sphb200_halo_select", "sphb200_stream", "sphb200_get_stats", "sphb200_measure_fp64_peak",
+           "sphb200_crk_compute_volume", "sphb200_crk_compute_corrections", "sphb200_crk_sum_mass_density")
 
 _lib = None
 
@@ -128,5 +132,8 @@ def lib():
     L.sphb200_stream.restype = vp
     L.sphb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.sphb200_measure_fp64_peak.argtypes = [vp, _dp]
+    L.sphb200_crk_compute_volume.argtypes = [vp]
+    L.sphb200_crk_compute_corrections.argtypes = [vp]
+    L.sphb200_crk_sum_mass_density.argtypes = [vp, C.c_double, C.c_double]
     _lib = L
     return L

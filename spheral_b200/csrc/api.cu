@@ -85,7 +85,9 @@ int alloc_nodes(sphb200_ctx* c, size_t n) {
   if (n <= c->cap) return 0;
   const size_t cap = n + n/32 + 32;
   const size_t keep = c->n;                     // nodes whose state must survive
+  const bool crk = c->opt.hydro == SPHB200_HYDRO_CRKSPH;
   for (int s = 0; s < S_COUNT; ++s) {
+    if (!crk && (s == S_VOLUME || s == S_RKCORR)) continue;       // CRKSPH-only fields
     const size_t w = (size_t)sphb200_state_width(c->ndim, s);
     double* p = nullptr;
     CU_CHECK(c, cudaMalloc((void**)&p, cap*w*sizeof(double)));
@@ -103,6 +105,7 @@ int alloc_nodes(sphb200_ctx* c, size_t n) {
   };
   if (reall(c->rows, cap*(size_t)(c->ndim == 3 ? 16 : 12))) return 1;
   if (reall(c->aux2, cap*2)) return 1;
+  if (crk && (reall(c->crkVolS, cap) || reall(c->crkCorrS, cap*(size_t)(c->ndim == 3 ? 16 : 10)))) return 1;
   for (int s = 0; s < DV_COUNT; ++s) if (reall(c->deriv[s], cap*(size_t)sphb200_deriv_width(c->ndim, s))) return 1;
   auto reall32 = [&](uint32_t*& p, size_t cnt) -> int {
     if (p) cudaFree(p);
@@ -153,6 +156,7 @@ static int check_options(sphb200_ctx* c, const sphb200_options* o) {
   if (!(o->nPerh > 0.0)) return sphb200_fail(c, "nPerh must be positive");
   if (o->Qkind != SPHB200_Q_MG && o->Qkind != SPHB200_Q_LIMITED_MG) return sphb200_fail(c, "unknown Qkind");
   if (o->hEvolution < SPHB200_H_SPH || o->hEvolution > SPHB200_H_NONE) return sphb200_fail(c, "unknown hEvolution");
+  if (o->hydro != SPHB200_HYDRO_SPH && o->hydro != SPHB200_HYDRO_CRKSPH) return sphb200_fail(c, "unknown hydro");
   return 0;
 }
 
@@ -192,7 +196,7 @@ void sphb200_destroy(sphb200_ctx* c) {
                   (void*)c->cellCursor, (void*)c->perm, (void*)c->skey, (void*)c->reduceBuf, (void*)c->rows, (void*)c->aux2, (void*)c->auxPneg, (void*)c->auxSomr2,
                   (void*)c->auxDvDxQ, (void*)c->auxfCl, (void*)c->auxfCq, (void*)c->nbrCount, (void*)c->tileRows, (void*)c->tileOff, (void*)c->nbr,
                   (void*)c->counters, (void*)c->frows, (void*)c->scanTmp, (void*)c->pacc, (void*)c->stage,
-                  (void*)c->runs, (void*)c->tileRunStart, (void*)c->tileRunCount, (void*)c->dilTab}) cudaFree(p);
+                  (void*)c->runs, (void*)c->tileRunStart, (void*)c->tileRunCount, (void*)c->dilTab, (void*)c->crkVolS, (void*)c->crkCorrS}) cudaFree(p);
   cudaFreeHost(c->reduceHost); cudaFreeHost(c->countersHost);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -203,6 +207,7 @@ int sphb200_set_options(sphb200_ctx* c, const sphb200_options* o) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
   if (check_options(c, o)) return 1;
   if (o->ndim != c->ndim) return sphb200_fail(c, "ndim cannot change after creation");
+  if (o->hydro != c->opt.hydro) return sphb200_fail(c, "hydro (SPH | CRKSPH) cannot change after creation");
   const bool repack = (o->epsTensile != c->opt.epsTensile) || (o->Qkind != c->opt.Qkind) || (o->balsara != c->opt.balsara);
   c->opt = *o;
   if (repack) c->rowsValid = false;
@@ -271,6 +276,7 @@ static const double* state_ptr(const sphb200_host_state* s, int slot) {
     case S_RHO: return s->massDensity; case S_EPS: return s->specificThermalEnergy; case S_P: return s->pressure;
     case S_CS: return s->soundSpeed; case S_OMEGA: return s->omegaGradh; case S_DVDXQ: return s->DvDxQ;
     case S_FCL: return s->fCl; case S_FCQ: return s->fCq;
+    case S_VOLUME: return s->volume; case S_RKCORR: return s->rkCorrections;
   }
   return nullptr;
 }
@@ -283,11 +289,12 @@ int sphb200_upload_state(sphb200_ctx* c, unsigned mask, const sphb200_host_state
     if (!(mask & (1u << slot))) continue;
     const double* src = state_ptr(s, slot);
     if (!src) return sphb200_fail(c, "upload_state: field selected in mask but pointer is null");
+    if (!c->api[slot] && c->n) return sphb200_fail(c, "upload_state: volume / RK corrections exist only in CRKSPH contexts");
     const size_t bytes = c->n*(size_t)sphb200_state_width(c->ndim, slot)*sizeof(double);
     if (bytes) CU_CHECK(c, cudaMemcpyAsync(c->api[slot], src, bytes, cudaMemcpyHostToDevice, c->stream));
     c->have[slot] = true;
     if (slot == S_POS || slot == S_H) { c->sortValid = false; c->pairsValid = false; }
-    if (slot != S_EPS) c->rowsValid = false;
+    if (slot != S_EPS && slot != S_VOLUME && slot != S_RKCORR) c->rowsValid = false;
   }
   return 0;
 }
@@ -358,13 +365,17 @@ int sphb200_evaluate_derivatives(sphb200_ctx* c, double /*time*/, double /*dt*/)
   CU_CHECK(c, cudaSetDevice(c->device));
   if (!c->pairsValid) return sphb200_fail(c, "evaluateDerivatives: connectivity is stale or missing (requireConnectivity: call build_pairs first)");
   if (c->n == 0) { c->derivsValid = true; return 0; }
-  for (int s : {S_POS, S_VEL, S_H, S_MASS, S_RHO, S_P, S_CS, S_OMEGA})
-    if (!c->have[s]) return sphb200_fail(c, "evaluateDerivatives: required state field missing on device (position, velocity, H, mass, mass density, pressure, sound speed, grad h corrections)");
+  const bool crk = c->opt.hydro == SPHB200_HYDRO_CRKSPH;
+  for (int s : {S_POS, S_VEL, S_H, S_MASS, S_RHO, S_P, S_CS})
+    if (!c->have[s]) return sphb200_fail(c, "evaluateDerivatives: required state field missing on device (position, velocity, H, mass, mass density, pressure, sound speed)");
+  if (!crk && !c->have[S_OMEGA]) return sphb200_fail(c, "evaluateDerivatives: required state field missing on device (grad h corrections)");
+  if (crk && (!c->have[S_VOLUME] || !c->have[S_RKCORR]))
+    return sphb200_fail(c, "evaluateDerivatives: CRKSPH needs the volume and the RK corrections (call crk_compute_volume / crk_compute_corrections or upload them)");
   if (!c->W.set) return sphb200_fail(c, "evaluateDerivatives: kernel table not set");
   cudaEventRecord(c->ev[3], c->stream);
   if (!c->rowsValid && sphb200_pack_rows(c)) return 1;
   cudaEventRecord(c->ev[4], c->stream);
-  if (sphb200_launch_derivs(c)) return 1;
+  if (crk ? sphb200_launch_crk_derivs(c) : sphb200_launch_derivs(c)) return 1;
   cudaEventRecord(c->ev[5], c->stream);
   return 0;
 }
@@ -468,7 +479,7 @@ int sphb200_halo_unpack(sphb200_ctx* c, unsigned mask, size_t firstGhost, size_t
     in += count*(size_t)w;
     c->have[s] = true;
     if (s == S_POS || s == S_H) { c->sortValid = false; c->pairsValid = false; }
-    if (s != S_EPS) c->rowsValid = false;
+    if (s != S_EPS && s != S_VOLUME && s != S_RKCORR) c->rowsValid = false;
   }
   return 0;
 }

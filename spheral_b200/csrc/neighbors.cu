@@ -152,6 +152,7 @@ struct PackArgs {
   uint32_t* skey;
   size_t n;
   float* frows; GridDev g; double kext; double csmax;
+  int rawP;                       // CRKSPH: the row carries P itself (CRKSPH.cc:376 uses Pi + Pj), not safeInv(omega)*P/rho^2
 };
 template <int DIM>
 __global__ void __launch_bounds__(RB) k_pack(PackArgs a) {
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(RB) k_pack(PackArgs a) {
   const double om = a.omega ? a.omega[o] : 1.0, cs = a.cs ? a.cs[o] : 0.0;
   const double safeOmega = om/(om*om + 1.0e-30);                 // safeInv, Utilities/safeInv.hh:13-19 (SPH.cc:310)
   r[D::R_M] = m; r[D::R_RHO] = rho; r[D::R_CS] = cs;
-  r[D::R_PRHO] = safeOmega*P/(rho*rho);                          // SPH.cc:425 with Peff == P
+  r[D::R_PRHO] = a.rawP ? P : safeOmega*P/(rho*rho);             // SPH.cc:425 with Peff == P
   if (DIM == 2) r[11] = 0.0;
   { double hh[D::NS];
 #pragma unroll
@@ -600,6 +601,7 @@ int sphb200_pack_rows(sphb200_ctx* c) {
   a.rows = c->rows; a.aux2 = c->aux2; a.auxPneg = tens ? c->auxPneg : nullptr; a.auxSomr2 = tens ? c->auxSomr2 : nullptr;
   a.auxDvDxQ = needQ ? c->auxDvDxQ : nullptr; a.auxfCl = mult ? c->auxfCl : nullptr; a.auxfCq = mult ? c->auxfCq : nullptr;
   a.perm = c->perm; a.keyApi = c->cellKeyApi; a.skey = c->skey; a.n = c->n;
+  a.rawP = (c->opt.hydro == SPHB200_HYDRO_CRKSPH) ? 1 : 0;
   { size_t fcap = c->frows ? c->frowsCap : 0;
     if (sphb200_ensure(c, c->frows, fcap, c->cap*(size_t)Fr::ROW)) return 1;
     c->frowsCap = fcap; }

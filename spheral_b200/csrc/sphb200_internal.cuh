@@ -22,7 +22,7 @@
 #define SPHB200_TILE 32
 #define SPHB200_DIL 32768          /* entries per axis of the dilated-coordinate table (max cells per axis) */
 
-enum StateSlot { S_POS = 0, S_VEL, S_H, S_MASS, S_RHO, S_EPS, S_P, S_CS, S_OMEGA, S_DVDXQ, S_FCL, S_FCQ, S_COUNT };
+enum StateSlot { S_POS = 0, S_VEL, S_H, S_MASS, S_RHO, S_EPS, S_P, S_CS, S_OMEGA, S_DVDXQ, S_FCL, S_FCQ, S_VOLUME, S_RKCORR, S_COUNT };
 enum DerivSlot { DV_DXDT = 0, DV_DRHODT, DV_DVDT, DV_DEPSDT, DV_DVDX, DV_LOCALDVDX, DV_GRADRHO, DV_M, DV_LOCALM,
                  DV_RHOSUM, DV_NORM, DV_MAXQ, DV_EFFQ, DV_XSPHW, DV_XSPHDV, DV_DHDT, DV_HIDEAL, DV_M0, DV_M1, DV_COUNT };
 
@@ -32,6 +32,7 @@ __host__ __device__ inline int sphb200_state_width(int ndim, int slot) {
     case S_POS: case S_VEL: return ndim;
     case S_H: return ndim == 3 ? 6 : 3;
     case S_DVDXQ: return ndim*ndim;
+    case S_RKCORR: return (ndim + 1)*(ndim + 1);
     default: return 1;
   }
 }
@@ -97,6 +98,8 @@ struct sphb200_ctx {
   double* auxSomr2 = nullptr;       // safeInv(omega)/(rho*rho)        (tensile)
   double* auxDvDxQ = nullptr;       // ndim*ndim per node (sorted)     (LimitedMG / Balsara)
   double* auxfCl = nullptr; double* auxfCq = nullptr;
+  double* crkVolS = nullptr;        // CRKSPH: volume per node (sorted)
+  double* crkCorrS = nullptr;       // CRKSPH: (1+ndim)^2 RK coefficients per node (sorted, AoS)
   bool rowsValid = false;           // rows reflect current api state for the current sort
   bool sortValid = false;
 
@@ -146,6 +149,7 @@ int sphb200_pack_rows(sphb200_ctx* c);
 int sphb200_neighbors(sphb200_ctx* c);
 int sphb200_launch_derivs(sphb200_ctx* c);
 int sphb200_launch_energy(sphb200_ctx* c, double multiplier);
+int sphb200_launch_crk_derivs(sphb200_ctx* c);
 int sphb200_pairs_to_host(sphb200_ctx* c, uint32_t* pi, uint32_t* pj, size_t cap, double* pacc, size_t paccCap);
 
 // ---- device helpers ---------------------------------------------------------------------------------------

@@ -23,6 +23,7 @@ def make_options(ndim, **kw):
     o.balsara = o.linearInExpansion = o.quadraticInExpansion = 0
     o.etaCritFrac, o.etaFoldFrac = 1.0, 0.2
     o.hEvolution, o.hmin, o.hmax = L.H_SPH, 1.0e-20, 1.0e20
+    o.hydro = L.HYDRO_SPH
     for k, v in kw.items():
         if not hasattr(o, k):
             raise KeyError(k)
@@ -183,6 +184,19 @@ class Engine:
 
     def update_energy_compatible(self, multiplier):
         self._check(self._lib.sphb200_update_energy_compatible(self._h, multiplier))
+
+    # -- CRKSPH (contexts created with hydro=HYDRO_CRKSPH) -----------------------------------------------------------
+    def crk_compute_volume(self):
+        """computeRKSumVolume -> internal entries of 'volume' on the device."""
+        self._check(self._lib.sphb200_crk_compute_volume(self._h))
+
+    def crk_compute_corrections(self):
+        """RKUtilities::computeCorrections (LinearOrder) -> internal entries of 'rkCorrections' on the device."""
+        self._check(self._lib.sphb200_crk_compute_corrections(self._h))
+
+    def crk_sum_mass_density(self, rhoMin=0.0, rhoMax=1.0e300):
+        """computeCRKSPHSumMassDensity -> internal entries of 'massDensity' on the device."""
+        self._check(self._lib.sphb200_crk_sum_mass_density(self._h, rhoMin, rhoMax))
 
     # -- halo ----------------------------------------------------------------------------------------------------------
     def halo_bytes_per_node(self, mask):

@@ -59,6 +59,24 @@ class HydroFieldNames:
     ArtificialViscousClMultiplier = "Cl multiplier for artificial viscosity"
     ArtificialViscousCqMultiplier = "Cq multiplier for artificial viscosity"
     ArtificialViscosityVelocityGradient = "velocity gradient for artificial viscosity"
+    volume = "volume"
+    surfacePoint = "surface point"
+
+
+class RKOrder:
+    """RK/RKCorrectionParams.hh: the orders this path implements."""
+    ZerothOrder, LinearOrder = 0, 1
+
+
+class RKFieldNames:
+    """RK/RKFieldNames.hh: rkCorrections(order) / reproducingKernel(order)."""
+    @staticmethod
+    def rkCorrections(order): return "rkCorrections_%d" % order
+    @staticmethod
+    def reproducingKernel(order): return "reproducingKernel_%d" % order
+
+
+RKSumVolume, RKMassOverDensity, RKVoronoiVolume = "RKSumVolume", "RKMassOverDensity", "RKVoronoiVolume"
 
 
 DELTA, NEW = "delta ", "new "          # IncrementState::prefix(), ReplaceState::prefix()
@@ -71,6 +89,7 @@ STATE_KEYS = {
     "soundSpeed": HydroFieldNames.soundSpeed, "omegaGradh": HydroFieldNames.omegaGradh,
     "DvDxQ": HydroFieldNames.ArtificialViscosityVelocityGradient,
     "fCl": HydroFieldNames.ArtificialViscousClMultiplier, "fCq": HydroFieldNames.ArtificialViscousCqMultiplier,
+    "volume": HydroFieldNames.volume, "rkCorrections": RKFieldNames.rkCorrections(RKOrder.LinearOrder),
 }
 # C-ABI name -> StateDerivatives key (outputs) ; SPH.cc:230-245, SPHBase.cc:127-140, SmoothingScaleBase.cc:45-46
 DERIV_KEYS = {
@@ -318,6 +337,8 @@ class SPHB200(Physics):
         self._ndim = nl.ndim
 
     # -- properties (SPHBase.hh:131-197) ----------------------------------------------------------------------------------
+    _hydro = L.HYDRO_SPH
+
     def label(self): return "SPH"
     kernel = property(lambda s: s._W)
     PiKernel = property(lambda s: s._WPi)
@@ -346,7 +367,7 @@ class SPHB200(Physics):
                             balsara=int(Q.balsaraShearCorrection), linearInExpansion=int(Q.linearInExpansion),
                             quadraticInExpansion=int(Q.quadraticInExpansion), etaCritFrac=Q.etaCritFrac,
                             etaFoldFrac=Q.etaFoldFrac, hEvolution=(sm.hEvolution if sm is not None else L.H_NONE),
-                            hmin=nl.hmin, hmax=nl.hmax)
+                            hmin=nl.hmin, hmax=nl.hmax, hydro=self._hydro)
 
     def _push_options(self):
         if self._engine is not None:
@@ -491,6 +512,86 @@ class SPHB200(Physics):
         self._uploaded["specificThermalEnergy"] = (id(state[k]), self._dirty.get("specificThermalEnergy", 0))
 
 
+class CRKSPHB200(SPHB200):
+    """Drop-in for CRKSPH<Dim> (CRKSPH/CRKSPH.hh, CRKSPHBase.hh) together with the RKCorrections package the controller
+    inserts in front of it (SpheralController.py:690-745; RK/RKCorrections.cc), for RKOrder.LinearOrder and RKSumVolume --
+    the settings of tests/functional/Hydro/Sedov/Sedov-spherical-3d.py:60-61.  Hooks, in the integrator's call order:
+      preStepInitialize  RKCorrections::preStepInitialize (volumes, RKCorrections.cc:298-340) then
+                         CRKSPHBase::preStepInitialize (RigorousSumDensity, CRKSPHBase.cc:229-256)
+      initialize         RKCorrections::initialize (corrections, RKCorrections.cc:346-372); returns True so that the
+                         integrator re-applies ghost boundaries (to the corrections)
+      evaluateDerivatives CRKSPH::evaluateDerivatives (CRKSPH.cc:148-440) + smoothing-scale sub-package."""
+    _hydro = L.HYDRO_CRKSPH
+
+    def __init__(self, dataBase, Q, W, order=RKOrder.LinearOrder, cfl=0.25, useVelocityMagnitudeForDt=False,
+                 compatibleEnergyEvolution=True, evolveTotalEnergy=False, XSPH=True, densityUpdate=RigorousSumDensity,
+                 epsTensile=0.0, nTensile=4.0, volumeType=RKSumVolume, device=0):
+        if order != RKOrder.LinearOrder:
+            raise SPHB200Error("CRKSPH: only RKOrder.LinearOrder is implemented on the device path")
+        if volumeType != RKSumVolume:
+            raise SPHB200Error("CRKSPH: only RKVolumeType.RKSumVolume is implemented on the device path "
+                               "(RKVoronoiVolume needs the polytope tessellation, out of scope)")
+        super().__init__(dataBase=dataBase, Q=Q, W=W, WPi=W, cfl=cfl, useVelocityMagnitudeForDt=useVelocityMagnitudeForDt,
+                         compatibleEnergyEvolution=compatibleEnergyEvolution, evolveTotalEnergy=evolveTotalEnergy,
+                         gradhCorrection=False, XSPH=XSPH, correctVelocityGradient=False, densityUpdate=densityUpdate,
+                         epsTensile=epsTensile, nTensile=nTensile, device=device)
+        self._order, self.volumeType = order, volumeType
+
+    def label(self): return "CRKSPH"
+    correctionOrder = property(lambda s: s._order)
+    def requireReproducingKernels(self): return {RKOrder.ZerothOrder, self._order}
+
+    def _resize_owned(self, nl):
+        super()._resize_owned(nl)
+        n, nd = nl.numNodes, self._ndim
+        own = self._own
+        if HydroFieldNames.volume not in own or own[HydroFieldNames.volume].shape[0] != n:
+            own[HydroFieldNames.volume] = np.zeros(n)
+        k = RKFieldNames.rkCorrections(self._order)
+        if k not in own or own[k].shape[0] != n:
+            own[k] = np.zeros((n, (nd + 1)*(nd + 1)))
+            own[k][:, 0] = 1.0
+
+    def registerState(self, dataBase, state):
+        """RKCorrections::registerState (volume, corrections; RKCorrections.cc:150-176) + CRKSPHBase::registerState
+        (CRKSPHBase.cc:131-187)."""
+        super().registerState(dataBase, state)
+        nl = dataBase.nodeLists[0]
+        state.enroll(nl.name, HydroFieldNames.volume, self._own[HydroFieldNames.volume])
+        k = RKFieldNames.rkCorrections(self._order)
+        state.enroll(nl.name, k, self._own[k])
+
+    def _pull(self, nl, state, abi):
+        """device -> the State's host array for one field (internal values were produced on the device)."""
+        got = self._engine.download_state(abi)[abi]
+        k = _key(STATE_KEYS[abi], nl.name)
+        state[k][...] = got.reshape(state[k].shape)
+        self._uploaded[abi] = (id(state[k]), self._dirty.get(abi, 0))
+
+    def preStepInitialize(self, dataBase, state, derivs):
+        nl = dataBase.nodeLists[0]
+        if (self._uploaded.get("position"), self._uploaded.get("H")) != self._pairsKey or not dataBase.connectivityValid:
+            raise SPHB200Error("CRKSPH::preStepInitialize: connectivity is stale (call updateConnectivity first)")
+        self._sync_state(nl, state, ("mass", "volume"))
+        self._engine.crk_compute_volume()
+        self._pull(nl, state, "volume")
+        if self.densityUpdate == RigorousSumDensity:
+            self._engine.crk_sum_mass_density(nl.rhoMin, nl.rhoMax)
+            self._pull(nl, state, "massDensity")
+
+    def initialize(self, time, dt, dataBase, state, derivs):
+        nl = dataBase.nodeLists[0]
+        self._sync_state(nl, state, ("volume", "rkCorrections"))      # ghost values set by the host's boundary conditions
+        self._engine.crk_compute_corrections()
+        self._pull(nl, state, "rkCorrections")
+        return True
+
+    def evaluateDerivatives(self, time, dt, dataBase, state, derivs):
+        nl = dataBase.nodeLists[0]
+        self._sync_state(nl, state, ("volume", "rkCorrections"))
+        super().evaluateDerivatives(time, dt, dataBase, state, derivs)
+
+
 # ---- factories (SPH/SPHHydros.py:9-140, :145-208) ----------------------------------------------------------------------------
 def SPH(W, WPi=None, WGrad=None, dataBase=None, Q=None, filter=None, cfl=0.25, useVelocityMagnitudeForDt=False,
         compatibleEnergyEvolution=True, evolveTotalEnergy=False, gradhCorrection=True, XSPH=True,
@@ -525,3 +626,35 @@ def ASPH(W, **kw):
     """SPHHydros.py:145-208"""
     kw["ASPH"] = True
     return SPH(W, **kw)
+
+
+def CRKSPH(dataBase, W, Q=None, order=RKOrder.LinearOrder, filter=0.0, cfl=0.25, useVelocityMagnitudeForDt=False,
+           compatibleEnergyEvolution=True, evolveTotalEnergy=False, XSPH=True, densityUpdate=RigorousSumDensity,
+           HUpdate=IdealH, epsTensile=0.0, nTensile=4.0, damageRelieveRubble=False, ASPH=False, etaMinAxis=0.1,
+           crktype="default", smoothingScaleMethod=None, volumeType=RKSumVolume, device=0):
+    """CRKSPH/CRKSPHHydros.py:9-112 -- same keywords and defaults (volumeType is the controller's keyword,
+    SpheralController.py:53; here the device path implements RKSumVolume)."""
+    if dataBase.numSolidNodeLists > 0:
+        raise RuntimeError("Cannot mix solid and fluid NodeLists.")
+    if crktype.lower() != "default":
+        raise SPHB200Error("CRKSPH: only crktype='default' is implemented on the device path")
+    if not Q:                                                     # CRKSPHHydros.py:64-68
+        Cl = 2.0*(W.kernelExtent/4.0)
+        Cq = 1.0*(W.kernelExtent/4.0)**2
+        Q = LimitedMonaghanGingoldViscosity(Clinear=Cl, Cquadratic=Cq, kernel=W)
+    result = CRKSPHB200(dataBase=dataBase, Q=Q, W=W, order=order, cfl=cfl, useVelocityMagnitudeForDt=useVelocityMagnitudeForDt,
+                        compatibleEnergyEvolution=compatibleEnergyEvolution, evolveTotalEnergy=evolveTotalEnergy, XSPH=XSPH,
+                        densityUpdate=densityUpdate, epsTensile=epsTensile, nTensile=nTensile, volumeType=volumeType,
+                        device=device)
+    result.prependSubPackage(Q)                                   # CRKSPHHydros.py:91
+    if smoothingScaleMethod is None:                              # CRKSPHHydros.py:94-103
+        smoothingScaleMethod = ASPHSmoothingScale(HUpdate, W) if ASPH else SPHSmoothingScale(HUpdate, W)
+    result._smoothingScaleMethod = smoothingScaleMethod
+    result.appendSubPackage(smoothingScaleMethod)
+    return result
+
+
+def ACRKSPH(*args, **kw):
+    """CRKSPHHydros.py:115-117"""
+    kw["ASPH"] = True
+    return CRKSPH(*args, **kw)
