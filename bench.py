@@ -40,6 +40,11 @@ def workload_spec(name):
         return dict(label="Noh-spherical-3d ASPH 200^3 lattice octant (jitter 0.05dx), BSpline table(1000), nPerh=1.44, "
                           "MonaghanGingold Q, compatible energy, XSPH, ASPH smoothing scale",
                     n=200, nPerh=1.44, asph=True, kind="noh")
+    if name == "crksph4m":      # configs[3]: CRKSPH Sedov 3-D, 160^3 = 4.1M particles (RK volumes + corrections + the pair loop)
+        return dict(label="CRKSPH Sedov-spherical-3d 160^3 lattice octant (jitter 0.05dx), BSpline table(1000), nPerh=1.51, "
+                          "LinearOrder RK corrections, RKSumVolume, LimitedMonaghanGingold Q (factory default), compatible energy, "
+                          "XSPH, SPH smoothing scale",
+                    n=160, nPerh=1.51, asph=False, kind="sedov", hydro="crksph")
     if name.startswith("glass"):  # configs[4]: glass:<n per side>:<neighbours>
         _, n, nb = name.split(":")
         nperh = {32: 1.97, 64: 2.48, 128: 3.13}[int(nb)]/2.0
@@ -79,10 +84,17 @@ def make_inputs(spec, seed=14892042, n_override=None, slab=0):
     P, cs = ng.gamma_law(rho, eps)
     st = dict(position=pos, velocity=vel, H=H, mass=mass, massDensity=rho, specificThermalEnergy=eps, pressure=P,
               soundSpeed=cs, omegaGradh=np.ones(N))
+    if spec.get("hydro") == "crksph":
+        # LimitedMonaghanGingold reads the velocity gradient of the previous evaluation: the analytic gradient of the field above
+        g = np.zeros((N, 3, 3))
+        g[:, 0, 1] = 0.3*np.cos(3*pos[:, 1]); g[:, 1, 2] = 0.3*np.cos(3*pos[:, 2]); g[:, 2, 0] = 0.3*np.cos(3*pos[:, 0])
+        st["DvDxQ"] = g.reshape(N, 9)
     return {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in st.items()}, N
 
 
 def options_kwargs(spec):
+    if spec.get("hydro") == "crksph":      # CRKSPHHydros.py:64-68 defaults: Cl = 2(kext/4), Cq = (kext/4)^2 with kext = 2
+        return dict(nPerh=spec["nPerh"], compatibleEnergy=1, XSPH=1, Qkind=1, Cl=1.0, Cq=0.25, hEvolution=0)
     return dict(nPerh=spec["nPerh"], compatibleEnergy=1, XSPH=1, correctVelocityGradient=1, Qkind=0, Cl=2.0, Cq=2.0,
                 hEvolution=1 if spec["asph"] else 0)
 
@@ -171,10 +183,16 @@ def cpu_port_run(spec, sample_n, steps, warmup, threads):
     s = common.to_oracle_state(st)
     os.environ["OMP_NUM_THREADS"] = str(threads)
     times = []
+    crk = spec.get("hydro") == "crksph"
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         pi, pj, cnt = orc.pairs(3, N, 0, s["pos"], s["H"], WT.kernelExtent)
-        orc.evaluate_derivatives(oo, OT, s, N, 0, pi, pj, cnt, nthreads=threads)
+        if crk:
+            vol = orc.crk_sum_volume(3, OT, N, 0, s["pos"], s["H"], pi, pj)
+            corr = orc.crk_corrections(3, OT, N, 0, s["pos"], s["H"], vol, pi, pj)
+            orc.crk_evaluate_derivatives(oo, OT, s, vol, corr, N, 0, pi, pj)
+        else:
+            orc.evaluate_derivatives(oo, OT, s, N, 0, pi, pj, cnt, nthreads=threads)
         t1 = time.perf_counter()
         if it >= warmup:
             times.append(t1 - t0)
@@ -227,13 +245,18 @@ def main():
 
     st, N = make_inputs(spec, seed=14892042 + rank, slab=rank)
     WT = K.TableKernel(K.BSplineKernel(3), 1000)
-    e = engine.Engine(3, device=local, **options_kwargs(spec))
+    crk = spec.get("hydro") == "crksph"
+    if crk and world > 1:
+        raise SystemExit("the CRKSPH workload is single-GPU in this round (the halo plumbing exchanges the SPH fields only)")
+    e = engine.Engine(3, device=local, hydro=(L.HYDRO_CRKSPH if crk else L.HYDRO_SPH), **options_kwargs(spec))
     e.set_kernel_table(WT)
     e.set_nodes(N, 0)
     ext = torch.cuda.ExternalStream(e.stream, device=torch.device("cuda", local))
 
     # pinned host buffers for the e2e leg (internal nodes only: ghosts arrive over NVLink, not from the host)
     up_names = ("position", "velocity", "H", "mass", "massDensity", "specificThermalEnergy", "pressure", "soundSpeed", "omegaGradh")
+    if crk:
+        up_names = up_names[:-1] + ("DvDxQ",)
     down_names = ("DxDt", "DrhoDt", "DvDt", "DepsDt", "DvDx", "DHDt", "Hideal")
     hs = L.HostState()
     pinned, up_mask, h2d = [], 0, 0
@@ -272,6 +295,9 @@ def main():
             dsph.step_connectivity_and_derivatives(0.0, 1.0)     # ghost selection + NVLink halo exchange + K1..K5
         else:
             e.build_pairs()
+            if crk:                                              # RKCorrections::preStepInitialize / initialize
+                e.crk_compute_volume()
+                e.crk_compute_corrections()
             e.evaluate_derivatives(0.0, 1.0)
 
     def step_e2e():
@@ -317,7 +343,7 @@ def main():
         pair_ms.append(s_["ms_pair_kernel"]); nbr_ms.append(s_["ms_neighbor_kernels"])
         build_ms.append(s_["ms_build_pairs"]); eval_ms.append(s_["ms_evaluate"])
     edges = e.stats()["directed_edges"]
-    halo_info = dict(dsph.last) if dsph is not None else None
+    halo_info = dsph.info() if dsph is not None else None
 
     # e2e leg: host buffers in, host buffers out, every step
     for _ in range(2):
@@ -341,13 +367,17 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-        roofline = {"bound": "hbm", "kernel": "k_sph_derivs (SPH pair loop + finalize + smoothing scale)",
+        if crk:                                      # + volume and 16 RK coefficients per node in; ~560 flop per pair
+            bytes_alg = N*(672.0 + 136.0 + 12.0*nbrs)
+            flops_alg = N*280.0*nbrs
+        roofline = {"bound": "hbm", "kernel": ("k_crk_derivs (CRKSPH pair loop + finalize + smoothing scale)" if crk else
+                                               "k_sph_derivs (SPH pair loop + finalize + smoothing scale)"),
                     "achieved": bytes_alg/t_pair/1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": bytes_alg/t_pair/1e9/hbm_peak, "traffic": None, "peak_source": hbm_src,
-                    "algorithmic_bytes_per_particle": 672.0 + 12.0*nbrs,
+                    "algorithmic_bytes_per_particle": bytes_alg/N,
                     "note": "the pair loop is FP64-pipe bound at ~100 neighbours (arithmetic intensity ~13 flop/B vs machine balance ~5); see roofline_fp64"}
         roofline_fp64 = {"bound": "fp64", "achieved": flops_alg/t_pair/1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": flops_alg/t_pair/1e12/fp64_peak, "algorithmic_flops_per_particle": 250.0*nbrs,
+                         "frac": flops_alg/t_pair/1e12/fp64_peak, "algorithmic_flops_per_particle": flops_alg/N,
                          "peak_source": "DFMA microbenchmark run in this process (sphb200_measure_fp64_peak)"}
         line = {"metric": metric, "value": value, "unit": "particle-updates/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warmup, "ms_per_step": dev_s/args.steps*1e3, "higher_is_better": True, "scaling": "weak",

@@ -191,6 +191,13 @@ int  sphb200_node_bounds(sphb200_ctx* ctx, size_t count, double lo[3], double hi
    lists are written in ascending node order (deterministic) into caller-provided device buffers of `cap` entries. */
 int  sphb200_halo_select(sphb200_ctx* ctx, int axis, size_t count, double lo, double hi, double width,
                          uint32_t* sendLowDevice, size_t* nLow, uint32_t* sendHighDevice, size_t* nHigh, size_t cap);
+/* Stream-ordered variants with NO host synchronisation, so that a whole ghost refresh costs one host round trip (the
+   counts): the bounds land in a 9-double device buffer {lo[3], hi[3], maxExtent[3]} (which the plumbing all-reduces in place
+   over NCCL), the selection reads the halo width maxExtent[axis]*(1+1e-9) from that device buffer and leaves
+   {nLow, nHigh} (int64) in countsDevice.  Lists longer than cap are truncated; the caller checks the counts. */
+int sphb200_node_bounds_device(sphb200_ctx* ctx, size_t count, double* boundsDevice /*[9]*/);
+int sphb200_halo_select_device(sphb200_ctx* ctx, int axis, size_t count, double lo, double hi, const double* maxExtentDevice /*[3]*/,
+                               uint32_t* sendLowDevice, uint32_t* sendHighDevice, long long* countsDevice /*[2]*/, size_t cap);
 /* raw stream handle (cudaStream_t) so the plumbing can order NCCL calls after pack / before unpack */
 void* sphb200_stream(sphb200_ctx* ctx);
 

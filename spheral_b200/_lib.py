@@ -80,6 +80,7 @@ EXPORTS = ("sphb200_abi_version", "sphb200_create", "sphb200_destroy", "sphb200_
            "sphb200_download_derivs", "sphb200_download_pair_accelerations", "sphb200_copy_DvDx_to_Q",
            "sphb200_update_energy_compatible", "sphb200_halo_bytes_per_node", "sphb200_halo_pack",
            "sphb200_halo_unpack", "sphb200_node_bounds", "sphb200_halo_select", "sphb200_stream", "sphb200_get_stats", "sphb200_measure_fp64_peak",
+           "sphb200_node_bounds_device", "sphb200_halo_select_device",
            "sphb200_crk_compute_volume", "sphb200_crk_compute_corrections", "sphb200_crk_sum_mass_density")
 
 _lib = None
@@ -128,6 +129,8 @@ def lib():
     L.sphb200_node_bounds.argtypes = [vp, C.c_size_t, _dp, _dp, _dp]
     L.sphb200_halo_select.argtypes = [vp, C.c_int, C.c_size_t, C.c_double, C.c_double, C.c_double,
                                       vp, C.POINTER(C.c_size_t), vp, C.POINTER(C.c_size_t), C.c_size_t]
+    L.sphb200_node_bounds_device.argtypes = [vp, C.c_size_t, vp]
+    L.sphb200_halo_select_device.argtypes = [vp, C.c_int, C.c_size_t, C.c_double, C.c_double, vp, vp, vp, vp, C.c_size_t]
     L.sphb200_stream.argtypes = [vp]
     L.sphb200_stream.restype = vp
     L.sphb200_get_stats.argtypes = [vp, C.POINTER(Stats)]

@@ -61,6 +61,20 @@ __global__ void __launch_bounds__(RB) k_halo_flags(const double* __restrict__ po
   fLow[i] = (x < lowCut) ? 1u : 0u;
   fHigh[i] = (x >= highCut) ? 1u : 0u;
 }
+// same, with the cut positions derived on the device: width = widthDev[axis] * (1 + 1e-9) (the all-reduced largest kernel
+// extent; the factor matches the host variant's safety margin)
+__global__ void __launch_bounds__(RB) k_halo_flags_dev(const double* __restrict__ pos, int ndim, int axis, size_t count, double lo, double hi,
+                                                       const double* __restrict__ widthDev, uint32_t* __restrict__ fLow, uint32_t* __restrict__ fHigh) {
+  const size_t i = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (i >= count) return;
+  const double w = widthDev[axis]*(1.0 + 1.0e-9);
+  const double x = pos[i*ndim + axis];
+  fLow[i] = (x < lo + w) ? 1u : 0u;
+  fHigh[i] = (x >= hi - w) ? 1u : 0u;
+}
+__global__ void k_halo_counts(const uint32_t* __restrict__ offLow, const uint32_t* __restrict__ offHigh, size_t count, long long* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = (long long)offLow[count]; out[1] = (long long)offHigh[count]; }
+}
 __global__ void __launch_bounds__(RB) k_halo_scatter(const uint32_t* __restrict__ offLow, const uint32_t* __restrict__ offHigh, size_t count,
                                                      size_t cap, uint32_t* __restrict__ outLow, uint32_t* __restrict__ outHigh) {
   const size_t i = (size_t)blockIdx.x*RB + threadIdx.x;
@@ -263,7 +277,7 @@ int sphb200_set_nodes(sphb200_ctx* c, size_t nInternal, size_t nGhost) {
   CU_CHECK(c, cudaSetDevice(c->device));
   const size_t n = nInternal + nGhost;
   if (n >= 0x7fffffffull) return sphb200_fail(c, "set_nodes: more than 2^31-1 nodes per GPU is not supported");
-  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (n > c->cap) CU_CHECK(c, cudaStreamSynchronize(c->stream));      // reallocation frees arrays in-flight work may use
   if (alloc_nodes(c, n)) return 1;
   if (n != c->n || nInternal != c->nInt) { c->sortValid = c->rowsValid = c->pairsValid = c->derivsValid = false; }
   c->nInt = nInternal; c->nGhost = nGhost; c->n = n;
@@ -521,6 +535,37 @@ int sphb200_halo_select(sphb200_ctx* c, int axis, size_t count, double lo, doubl
   CU_CHECK(c, cudaStreamSynchronize(c->stream));
   *nLow = tot[0]; *nHigh = tot[1];
   if (tot[0] > cap || tot[1] > cap) return sphb200_fail(c, "halo_select: send list capacity too small");
+  return 0;
+}
+
+int sphb200_node_bounds_device(sphb200_ctx* c, size_t count, double* outDevice) {
+  if (!c || !outDevice) return sphb200_fail(c, "node_bounds_device: null argument");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (count > c->n || count == 0) return sphb200_fail(c, "node_bounds_device: count must be in [1, node count]");
+  if (!c->have[S_POS] || !c->have[S_H] || !c->W.set) return sphb200_fail(c, "node_bounds_device: position, H and the kernel table must be set first");
+  if (sphb200_bounds_reduce(c, count)) return 1;
+  CU_CHECK(c, cudaMemcpyAsync(outDevice, c->reduceBuf + 296*9, 9*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+
+int sphb200_halo_select_device(sphb200_ctx* c, int axis, size_t count, double lo, double hi, const double* maxExtentDevice,
+                               uint32_t* sendLow, uint32_t* sendHigh, long long* countsDevice, size_t cap) {
+  if (!c || !maxExtentDevice || !countsDevice) return sphb200_fail(c, "halo_select_device: null argument");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (axis < 0 || axis >= c->ndim) return sphb200_fail(c, "halo_select_device: bad axis");
+  if (count > c->n || count == 0) return sphb200_fail(c, "halo_select_device: count must be in [1, node count]");
+  if (!c->have[S_POS]) return sphb200_fail(c, "halo_select_device: positions are not on the device");
+  if (ensure_stage(c, 2*(count + 1)*sizeof(uint32_t))) return 1;
+  uint32_t* fLow = (uint32_t*)c->stage; uint32_t* fHigh = fLow + (count + 1);
+  const unsigned nb = (unsigned)((count + RB - 1)/RB);
+  k_halo_flags_dev<<<nb, RB, 0, c->stream>>>(c->api[S_POS], c->ndim, axis, count, lo, hi, maxExtentDevice, fLow, fHigh);
+  KERNEL_CHECK(c, "k_halo_flags_dev");
+  if (sphb200_scan_u32(c, fLow, fLow, count)) return 1;
+  if (sphb200_scan_u32(c, fHigh, fHigh, count)) return 1;
+  k_halo_scatter<<<nb, RB, 0, c->stream>>>(fLow, fHigh, count, cap, sendLow, sendHigh);
+  KERNEL_CHECK(c, "k_halo_scatter");
+  k_halo_counts<<<1, 32, 0, c->stream>>>(fLow, fHigh, count, countsDevice);
+  KERNEL_CHECK(c, "k_halo_counts");
   return 0;
 }
 

@@ -136,8 +136,9 @@ class DistributedSPH:
     slabs.  `step_connectivity_and_derivatives()` is what Integrator::setGhostNodes + evaluateDerivatives do per stage
     (Integrator.cc:372-445, 217-229): ghost selection, exchange, neighbour build, derivative evaluation."""
 
-    def __init__(self, engine, axis, lo, hi, halo=None, extra_fields=()):
+    def __init__(self, engine, axis, lo, hi, halo=None, extra_fields=(), two_phase=False):
         self.e = engine
+        self.two_phase = two_phase
         self.axis, self.lo, self.hi = axis, float(lo), float(hi)
         self.halo = halo if halo is not None else SlabHalo()
         self.dev = torch.device("cuda", engine_device(engine))
@@ -161,55 +162,90 @@ class DistributedSPH:
         self.idxHigh = torch.empty(cap, dtype=torch.int32, device=dev)
         mk = lambda nbytes: torch.empty(cap*nbytes//8, dtype=torch.float64, device=dev)
         self.sLowA, self.sHighA, self.rLowA, self.rHighA = mk(self.bytesA), mk(self.bytesA), mk(self.bytesA), mk(self.bytesA)
-        self.sLowB, self.sHighB, self.rLowB, self.rHighB = mk(self.bytesB), mk(self.bytesB), mk(self.bytesB), mk(self.bytesB)
+        nb = self.bytesA + self.bytesB            # the single-batch exchange stages every field in the B buffers
+        self.sLowB, self.sHighB, self.rLowB, self.rHighB = mk(nb), mk(nb), mk(nb), mk(nb)
         self._cap = cap
 
     def refresh_ghosts_and_build(self):
-        """Ghost selection + two-phase exchange + neighbour build.  Returns the number of node pairs of this slab."""
+        """Ghost selection + exchange + neighbour build.  Returns the number of node pairs of this slab.
+
+        Default path: ONE host round trip before the neighbour build.  The bounds reduction, the all-reduce(MAX) of the
+        halo width, the send-node selection and the all-gather of the counts are chained on the device
+        (sphb200_node_bounds_device / sphb200_halo_select_device); only the gathered counts come back to the host (NCCL
+        needs the message sizes there).  All fields then travel in one batch of send/recv, so the node rows are packed
+        once (with two phases the rows have to be re-packed when the late fields land: +0.19 ms per step at 1 M nodes,
+        which is more than the ~10 us the second message spends on NVLink).  `two_phase=True` keeps the split exchange
+        (positions + H first, the rest in flight during the neighbour build)."""
         e, h = self.e, self.halo
         nInt = self.nInternal
+        if nInt == 0:
+            raise RuntimeError("DistributedSPH: a slab without internal nodes is not supported")
         with torch.cuda.stream(self.stream):
-            # halo width: largest kernel extent along the axis over all ranks (gather AND scatter neighbours are covered)
-            _, _, ext = e.node_bounds(nInt)
-            w = torch.tensor([float(ext[self.axis])], dtype=torch.float64, device=self.dev)
-            self.width = float(h.allreduce_max(w).item())*(1.0 + 1.0e-9)
-            # device-side send lists (deterministic ascending order); capacity grows on demand
             if self._cap == 0:
                 self._ensure(max(1024, nInt//8))
+                self._bounds = torch.zeros(9, dtype=torch.float64, device=self.dev)
+                self._counts = torch.zeros(2, dtype=torch.int64, device=self.dev)
+                self._allc = torch.zeros(2*h.world, dtype=torch.int64, device=self.dev)
             while True:
-                try:
-                    nLow, nHigh = e.halo_select(self.axis, self.lo, self.hi, self.width, self.idxLow.data_ptr(), self.idxHigh.data_ptr(), self._cap, nInt)
+                # halo width: largest kernel extent along the axis over all ranks (gather AND scatter neighbours are covered)
+                e.node_bounds_device(nInt, self._bounds.data_ptr())
+                ext = self._bounds[6:9]
+                h.allreduce_max(ext)
+                e.halo_select_device(self.axis, self.lo, self.hi, ext.data_ptr(), self.idxLow.data_ptr(), self.idxHigh.data_ptr(),
+                                     self._counts.data_ptr(), self._cap, nInt)
+                if h.world > 1:
+                    dist.all_gather_into_tensor(self._allc, self._counts, group=h.group)
+                else:
+                    self._allc.copy_(self._counts)
+                allc = self._allc.cpu().numpy().reshape(h.world, 2)          # the one host round trip
+                nLow, nHigh = int(allc[h.rank, 0]), int(allc[h.rank, 1])
+                if max(nLow, nHigh) <= self._cap:
                     break
-                except RuntimeError as err:
-                    if "capacity" not in str(err):
-                        raise
-                    self._ensure(self._cap*2)
+                self._ensure(max(nLow, nHigh))                                # send lists were truncated: grow and redo
             if h.lower is None:
                 nLow = 0
             if h.upper is None:
                 nHigh = 0
-            nFL, nFU = h.exchange_counts(nLow, nHigh, self.dev)
+            nFL = int(allc[h.lower, 1]) if h.lower is not None else 0         # the lower slab's "high" list is ours
+            nFU = int(allc[h.upper, 0]) if h.upper is not None else 0
             self._ensure(max(nLow, nHigh, nFL, nFU))
             self.nFromLower, self.nFromUpper = nFL, nFU
             e.set_nodes(nInt, nFL + nFU)
-            # pack both phases, then post A and B; K1+K2 only wait for A
             wA, wB = self.bytesA//8, self.bytesB//8
-            e.halo_pack(self.maskA, self.idxLow.data_ptr(), nLow, self.sLowA.data_ptr())
-            e.halo_pack(self.maskA, self.idxHigh.data_ptr(), nHigh, self.sHighA.data_ptr())
-            e.halo_pack(self.maskB, self.idxLow.data_ptr(), nLow, self.sLowB.data_ptr())
-            e.halo_pack(self.maskB, self.idxHigh.data_ptr(), nHigh, self.sHighB.data_ptr())
-            worksA = h.start(self.sLowA[:nLow*wA], self.sHighA[:nHigh*wA], self.rLowA[:nFL*wA], self.rHighA[:nFU*wA])
-            worksB = h.start(self.sLowB[:nLow*wB], self.sHighB[:nHigh*wB], self.rLowB[:nFL*wB], self.rHighB[:nFU*wB])
-            h.finish(worksA)
-            e.halo_unpack(self.maskA, nInt, nFL, self.rLowA.data_ptr())
-            e.halo_unpack(self.maskA, nInt + nFL, nFU, self.rHighA.data_ptr())
-            npairs = e.build_pairs()                      # phase B is in flight on the NCCL stream meanwhile
-            h.finish(worksB)
-            e.halo_unpack(self.maskB, nInt, nFL, self.rLowB.data_ptr())
-            e.halo_unpack(self.maskB, nInt + nFL, nFU, self.rHighB.data_ptr())
-        self.last = dict(nSendLow=nLow, nSendHigh=nHigh, nFromLower=nFL, nFromUpper=nFU, width=self.width,
-                         h2h_bytes=(nLow + nHigh)*(self.bytesA + self.bytesB))
+            if not self.two_phase:
+                wAB = wA + wB
+                mask = self.maskA | self.maskB
+                e.halo_pack(mask, self.idxLow.data_ptr(), nLow, self.sLowB.data_ptr())
+                e.halo_pack(mask, self.idxHigh.data_ptr(), nHigh, self.sHighB.data_ptr())
+                works = h.start(self.sLowB[:nLow*wAB], self.sHighB[:nHigh*wAB], self.rLowB[:nFL*wAB], self.rHighB[:nFU*wAB])
+                h.finish(works)
+                e.halo_unpack(mask, nInt, nFL, self.rLowB.data_ptr())
+                e.halo_unpack(mask, nInt + nFL, nFU, self.rHighB.data_ptr())
+                npairs = e.build_pairs()
+            else:
+                # pack both phases, then post A and B; K1+K2 only wait for A
+                e.halo_pack(self.maskA, self.idxLow.data_ptr(), nLow, self.sLowA.data_ptr())
+                e.halo_pack(self.maskA, self.idxHigh.data_ptr(), nHigh, self.sHighA.data_ptr())
+                e.halo_pack(self.maskB, self.idxLow.data_ptr(), nLow, self.sLowB.data_ptr())
+                e.halo_pack(self.maskB, self.idxHigh.data_ptr(), nHigh, self.sHighB.data_ptr())
+                worksA = h.start(self.sLowA[:nLow*wA], self.sHighA[:nHigh*wA], self.rLowA[:nFL*wA], self.rHighA[:nFU*wA])
+                worksB = h.start(self.sLowB[:nLow*wB], self.sHighB[:nHigh*wB], self.rLowB[:nFL*wB], self.rHighB[:nFU*wB])
+                h.finish(worksA)
+                e.halo_unpack(self.maskA, nInt, nFL, self.rLowA.data_ptr())
+                e.halo_unpack(self.maskA, nInt + nFL, nFU, self.rHighA.data_ptr())
+                npairs = e.build_pairs()                      # phase B is in flight on the NCCL stream meanwhile
+                h.finish(worksB)
+                e.halo_unpack(self.maskB, nInt, nFL, self.rLowB.data_ptr())
+                e.halo_unpack(self.maskB, nInt + nFL, nFU, self.rHighB.data_ptr())
+        self.last = dict(nSendLow=nLow, nSendHigh=nHigh, nFromLower=nFL, nFromUpper=nFU,
+                         h2h_bytes=(nLow + nHigh)*(self.bytesA + self.bytesB), two_phase=bool(self.two_phase))
         return npairs
+
+    def info(self):
+        """Counts of the last refresh plus the halo width (read back from the device here, outside the hot path)."""
+        if self._cap:
+            self.width = float(self._bounds[6 + self.axis].item())*(1.0 + 1.0e-9)
+        return dict(self.last, width=self.width)
 
     def step_connectivity_and_derivatives(self, time=0.0, dt=1.0):
         npairs = self.refresh_ghosts_and_build()

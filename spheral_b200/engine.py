@@ -221,6 +221,15 @@ class Engine:
                                                   send_low_ptr, C.byref(nl), send_high_ptr, C.byref(nh), cap))
         return nl.value, nh.value
 
+    def node_bounds_device(self, count, bounds_ptr):
+        """Stream-ordered, no host sync: {lo[3], hi[3], maxExtent[3]} of nodes [0,count) into a 9-double device buffer."""
+        self._check(self._lib.sphb200_node_bounds_device(self._h, count, bounds_ptr))
+
+    def halo_select_device(self, axis, lo, hi, max_extent_ptr, send_low_ptr, send_high_ptr, counts_ptr, cap, count=None):
+        """Stream-ordered, no host sync: the halo width is read from the device; {nLow, nHigh} (int64) land in counts_ptr."""
+        self._check(self._lib.sphb200_halo_select_device(self._h, axis, self.nInternal if count is None else count, lo, hi,
+                                                         max_extent_ptr, send_low_ptr, send_high_ptr, counts_ptr, cap))
+
     # -- instrumentation -----------------------------------------------------------------------------------------------
     def stats(self):
         s = L.Stats()

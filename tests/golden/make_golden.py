@@ -28,6 +28,11 @@ CASES = {
                                   opts=dict(Cl=1.0, Cq=1.0)),
     "sph3d_limitedq_tensile": dict(ndim=3, n=6, nPerh=1.51, kind="lattice", kernel="BSpline", seed=44, ghosts=False, negP=True, q=True,
                                    opts=dict(Cl=2.0, Cq=2.0, Qkind=1, balsara=1, epsTensile=0.3, compatibleEnergy=0, evolveTotalEnergy=1)),
+    # CRKSPH (hydro="crk"): RK sum volumes and linear corrections are part of the fixture (ghost entries: m/rho, identity)
+    "crk3d_lattice_limitedq": dict(ndim=3, n=6, nPerh=1.51, kind="lattice", kernel="BSpline", seed=45, ghosts=False, q=True, hydro="crk",
+                                   opts=dict(Cl=1.0, Cq=0.25, Qkind=1)),
+    "crk2d_ghosts": dict(ndim=2, n=14, nPerh=2.01, kind="lattice", kernel="BSpline", seed=46, ghosts=True, hydro="crk",
+                         opts=dict(Cl=1.0, Cq=1.0)),
 }
 
 
@@ -46,6 +51,14 @@ def build_case(name):
     return c, WT, st, nInt, nGhost, opts
 
 
+def crk_ghost_defaults(ndim, st):
+    """What the fixture uses as boundary-condition values of volume / RK corrections on ghost nodes."""
+    n = st["mass"].shape[0]
+    corr0 = np.zeros((n, (ndim + 1)**2))
+    corr0[:, 0] = 1.0
+    return st["mass"]/st["massDensity"], corr0
+
+
 def oracle_outputs(name):
     import common
     from oracle import oracle as orc
@@ -54,8 +67,18 @@ def oracle_outputs(name):
     oo = orc.default_options(ndim, **opts)
     s = common.to_oracle_state(st)
     pi, pj, cnt = orc.pairs(ndim, nInt, nGhost, s["pos"], s["H"], WT.kernelExtent)
-    ref = orc.evaluate_derivatives(oo, common.oracle_table(orc, WT), s, nInt, nGhost, pi, pj, cnt)
+    OT = common.oracle_table(orc, WT)
+    extra = {}
+    if c.get("hydro") == "crk":
+        vol0, corr0 = crk_ghost_defaults(ndim, st)
+        vol = orc.crk_sum_volume(ndim, OT, nInt, nGhost, s["pos"], s["H"], pi, pj, vol=vol0)
+        corr = orc.crk_corrections(ndim, OT, nInt, nGhost, s["pos"], s["H"], vol, pi, pj, corr=corr0)
+        ref = orc.crk_evaluate_derivatives(oo, OT, s, vol, corr, nInt, nGhost, pi, pj)
+        extra = {"crk_volume": vol, "crk_corrections": corr}
+    else:
+        ref = orc.evaluate_derivatives(oo, OT, s, nInt, nGhost, pi, pj, cnt)
     out = {"pairs_i": pi, "pairs_j": pj, "counts": cnt, "nInt": np.int64(nInt), "nGhost": np.int64(nGhost)}
+    out.update(extra)
     out.update({"state_" + k: v for k, v in st.items()})
     out.update({"deriv_" + k: v for k, v in ref.items()})
     return out

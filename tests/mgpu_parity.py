@@ -69,7 +69,7 @@ def main():
         worst[k] = float(np.abs(a - b).max()/max(np.abs(b).max(), f))
     w = max(worst.values())
     res = dict(rank=rank, world=world, nodes=N, ghosts=e.nGhost, pairs=int(npairs), counts_equal=ok, worst_field_error=w,
-               halo=d.last, asph=asph)
+               halo=d.info(), asph=asph)
     print(json.dumps(res), flush=True)
     flag = torch.tensor([1.0 if (ok and w <= 1.0e-10) else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

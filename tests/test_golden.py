@@ -28,7 +28,7 @@ def test_oracle_reproduces_golden(oracle, sphlib, name):
     for k in g.files:
         if k.startswith("state_"):
             assert np.array_equal(out[k], g[k]), "input generator drifted: " + k
-        if k.startswith("deriv_"):
+        if k.startswith("deriv_") or k.startswith("crk_"):
             scale = max(float(np.abs(g[k]).max()), 1e-300)
             assert np.abs(out[k] - g[k]).max() <= 1e-13*scale, k
 
@@ -40,7 +40,8 @@ def test_cuda_path_matches_golden(sphlib, name):
     g = _load(name)
     c, WT, st, nInt, nGhost, opts = mg.build_case(name)
     st = {k[6:]: g[k] for k in g.files if k.startswith("state_")}          # the stored inputs, not regenerated ones
-    e = engine.Engine(c["ndim"], options=engine.make_options(c["ndim"], **opts))
+    crk = c.get("hydro") == "crk"
+    e = engine.Engine(c["ndim"], options=engine.make_options(c["ndim"], hydro=1 if crk else 0, **opts))
     e.set_kernel_table(WT)
     e.set_nodes(nInt, nGhost)
     e.upload_state(**st)
@@ -48,6 +49,18 @@ def test_cuda_path_matches_golden(sphlib, name):
     gi, gj = e.download_pairs()
     assert npairs == len(g["pairs_i"]) and np.array_equal(gi, g["pairs_i"]) and np.array_equal(gj, g["pairs_j"])
     assert np.array_equal(e.download_neighbor_counts(), g["counts"])
+    if crk:
+        vol0, corr0 = mg.crk_ghost_defaults(c["ndim"], st)
+        e.upload_state(volume=vol0, rkCorrections=corr0)
+        e.crk_compute_volume()
+        e.crk_compute_corrections()
+        vol = e.download_state("volume")["volume"]
+        corr = e.download_state("rkCorrections")["rkCorrections"]
+        assert np.abs(vol - g["crk_volume"]).max() <= 1e-10*np.abs(g["crk_volume"]).max()
+        ps = c["ndim"] + 1
+        for b in range(ps):                       # C, dC_x, dC_y[, dC_z] blocks carry different powers of 1/h
+            blk = slice(b*ps, (b + 1)*ps)
+            assert np.abs(corr[:, blk] - g["crk_corrections"][:, blk]).max() <= 1e-10*np.abs(g["crk_corrections"][:, blk]).max()
     e.evaluate_derivatives(0.0, 1.0)
     got = e.download_derivs()
     floors = common.physical_floors(st, nInt, c["ndim"])

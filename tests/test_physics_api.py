@@ -87,3 +87,76 @@ def test_evaluate_derivatives_through_physics_interface(sphlib, oracle):
     dKE = (m*((v + dtc*a)**2).sum(axis=1)).sum()*0.5 - (m*(v**2).sum(axis=1)).sum()*0.5
     dTE = (m*(eps1 - eps0)).sum()
     assert abs(dKE + dTE) <= 1e-12*max(abs(dKE), abs(dTE), 1e-300)
+
+
+# ---- CRKSPH through the same interface (CRKSPH/CRKSPHHydros.py, RK/RKCorrections.cc, CRKSPH/CRKSPHBase.cc) -------------------
+def _setup_crk(ndim=3, n=8, nPerh=1.51, **hydro_kw):
+    from spheral_b200 import physics as P
+    st, nInt, nGhost = common.make_problem(ndim, n, nPerh=nPerh, seed=79)
+    nodes = P.FluidNodeList("nodes", ndim, nInt, nGhost, nPerh=nPerh)
+    for abi in ("position", "velocity", "H", "mass", "massDensity", "specificThermalEnergy"):
+        nodes.setField(P.STATE_KEYS[abi], st[abi])
+    db = P.DataBase()
+    db.appendNodeList(nodes)
+    WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    hydro = P.CRKSPH(dataBase=db, W=WT, **hydro_kw)
+    return P, st, nodes, db, WT, hydro
+
+
+def test_crksph_factory_defaults_and_registration_contract(sphlib):
+    P, st, nodes, db, WT, hydro = _setup_crk()
+    # CRKSPHHydros.py:64-68 -- default Q is LimitedMonaghanGingold with Cl = 2(kext/4), Cq = (kext/4)^2
+    assert isinstance(hydro.Q, P.LimitedMonaghanGingoldViscosity) and hydro.Q.Cl == 1.0 and hydro.Q.Cq == 0.25
+    assert hydro.label() == "CRKSPH" and hydro.correctionOrder == P.RKOrder.LinearOrder
+    assert hydro.requireReproducingKernels() == {P.RKOrder.ZerothOrder, P.RKOrder.LinearOrder}
+    assert hydro.preSubPackages() == [hydro.Q] and isinstance(hydro.postSubPackages()[0], P.SPHSmoothingScale)
+    assert isinstance(P.ACRKSPH(db, WT).postSubPackages()[0], P.ASPHSmoothingScale)
+    state, derivs = P.State(db, [hydro]), P.StateDerivatives(db, [hydro])
+    for key in ("mass", "position", "velocity", "mass density", "specific thermal energy", "H", "pressure", "sound speed",
+                "volume", "rkCorrections_1", "velocity gradient for artificial viscosity"):
+        assert state.registered(key, "nodes"), key
+    for key in ("delta position", "delta mass density", "delta velocity hydro", "delta specific thermal energy",
+                "velocity gradient", "internal velocity gradient", "XSPH delta vi", "max viscous pressure",
+                "effective viscous pressure", "delta H", "new H"):
+        assert derivs.registered(key, "nodes"), key
+    assert "pair-wise accelerations" in derivs
+    with pytest.raises(P.SPHB200Error, match="RKSumVolume"):
+        P.CRKSPH(db, WT, volumeType=P.RKVoronoiVolume)
+
+
+@pytest.mark.gpu
+def test_crksph_hooks_against_oracle(sphlib, oracle):
+    P, st, nodes, db, WT, hydro = _setup_crk(Q=None, densityUpdate="IntegrateDensity")
+    hydro.Q = P.MonaghanGingoldViscosity(1.0, 0.5)
+    hydro.initializeProblemStartup(db)
+    state, derivs = P.State(db, [hydro]), P.StateDerivatives(db, [hydro])
+    state.field("pressure", "nodes")[...] = st["pressure"]
+    state.field("sound speed", "nodes")[...] = st["soundSpeed"]
+    npairs = hydro.updateConnectivity(db, state)
+    hydro.preStepInitialize(db, state, derivs)                     # volumes
+    assert hydro.initialize(0.0, 1.0, db, state, derivs) is True   # corrections; True = re-apply ghost boundaries
+    derivs.Zero()
+    hydro.evaluateDerivatives(0.0, 1.0, db, state, derivs)
+
+    nInt = nodes.numInternalNodes
+    OT = common.oracle_table(oracle, WT)
+    oo = oracle.default_options(3, nPerh=1.51, Cl=1.0, Cq=0.5)
+    s = common.to_oracle_state(st)
+    pi, pj, cnt = oracle.pairs(3, nInt, 0, s["pos"], s["H"], WT.kernelExtent)
+    assert npairs == len(pi)
+    vol = oracle.crk_sum_volume(3, OT, nInt, 0, s["pos"], s["H"], pi, pj)
+    corr = oracle.crk_corrections(3, OT, nInt, 0, s["pos"], s["H"], vol, pi, pj)
+    ref = oracle.crk_evaluate_derivatives(oo, OT, s, vol, corr, nInt, 0, pi, pj)
+    assert np.abs(state.field("volume", "nodes") - vol).max() <= 1e-10*vol.max()
+    floors = common.physical_floors(st, nInt, 3)
+    for abi in ("DxDt", "DrhoDt", "DvDt", "DepsDt", "DvDx", "localDvDx", "maxViscousPressure", "effViscousPressure",
+                "XSPHDeltaV", "DHDt", "Hideal"):
+        got = derivs.field(P.DERIV_KEYS[abi], "nodes")
+        assert common.field_err(got, np.asarray(ref[abi]).reshape(got.shape), nInt, floors[abi]) <= 1e-10, abi
+    pa = np.asarray(hydro.pairAccelerations)
+    assert np.abs(pa - ref["pairAccelerations"]).max() <= 1e-10*np.abs(ref["pairAccelerations"]).max()
+    # RigorousSumDensity branch of preStepInitialize
+    hydro.densityUpdate = P.RigorousSumDensity
+    hydro.preStepInitialize(db, state, derivs)
+    rho = oracle.crk_sum_density(3, OT, nInt, 0, s["pos"], s["mass"], vol, s["H"], pi, pj, rhoMin=nodes.rhoMin, rhoMax=nodes.rhoMax)
+    assert np.abs(state.field("mass density", "nodes") - rho).max() <= 1e-10*rho.max()
