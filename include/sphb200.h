@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPHB200_ABI_VERSION 2
+#define SPHB200_ABI_VERSION 3
 
 typedef struct sphb200_ctx sphb200_ctx;
 
@@ -165,6 +165,46 @@ int  sphb200_copy_DvDx_to_Q(sphb200_ctx* ctx);
 int  sphb200_crk_compute_volume(sphb200_ctx* ctx);
 int  sphb200_crk_compute_corrections(sphb200_ctx* ctx);
 int  sphb200_crk_sum_mass_density(sphb200_ctx* ctx, double rhoMin, double rhoMax);
+
+/* ---- per-step callers of the derivative path, device-resident ----------------------------------
+   With these the state never leaves the GPU between the stages of CheapSynchronousRK2 (Integrator/CheapSynchronousRK2.cc:40-132);
+   the host integrator (spheral_b200/integrator.py, or a C++ Integrator subclass) reads back one number per step: dt.
+     sphb200_sum_mass_density      computeSPHSumMassDensity (SPHBase::preStepInitialize, RigorousSumDensity)
+                                   SPH/computeSPHSumMassDensity.cc:15-89, SPH/SPHBase.cc:336-352.  Internal rho entries are written.
+     sphb200_compute_omega_gradh   computeSPHOmegaGradhCorrection (SPHBase::postStateUpdate)
+                                   SPH/computeSPHOmegaGradhCorrection.cc:20-113, SPH/SPHBase.cc:539-547
+     sphb200_update_eos_gamma_law  PressurePolicy / SoundSpeedPolicy with GammaLawGas: P and cs of every node
+                                   Hydro/PressurePolicy.cc, Material/GammaLawGas.cc:185-189, 233-238, EquationOfStateInline.hh:98-106
+     sphb200_state_copy / _assign  State::copyState / State::assign (CheapSynchronousRK2.cc:70-71, 104, 113)
+     sphb200_state_update          State::update(derivs, multiplier, t, dt) (DataBase/State.cc:221-300) for the policies the hydro and
+                                   smoothing-scale packages register (SPHBase.cc:203-261, SPH.cc:96-113, SmoothingScaleBase.cc:56-83,
+                                   ASPHSmoothingScale.cc:72-90): rho IncrementBoundedState, position / velocity IncrementState,
+                                   eps SpecificThermalEnergyPolicy (compatible) or IncrementState, H IncrementBoundedState /
+                                   ReplaceBoundedState / IncrementASPHHtensor, then pressure and sound speed.  timeAdvanceOnly != 0
+                                   degrades every policy to its increment (updateAsIncrement).  Uses the derivatives of the last
+                                   sphb200_evaluate_derivatives call, which stay usable after a later sphb200_build_pairs.
+     sphb200_compute_dt            GenericHydro::dt (Physics/GenericHydro.cc:112-381); reason: 0 sound speed, 1 artificial
+                                   viscosity, 2 velocity divergence, 3 acceleration, 4 velocity magnitude, 5 pairwise velocity
+                                   difference; node = the limiting node.  Synchronises (one 16-byte read-back). */
+typedef struct {
+  double gamma;                               /* GammaLawGas */
+  double minimumPressure, maximumPressure, externalPressure;
+  int    minPressureType;                     /* 0 PressureFloor | 1 ZeroPressure */
+} sphb200_gamma_law;
+enum { SPHB200_HEVOLUTION_IDEALH = 0, SPHB200_HEVOLUTION_INTEGRATEH = 1, SPHB200_HEVOLUTION_FIXEDH = 2 };
+typedef struct {
+  sphb200_gamma_law eos;
+  double rhoMin, rhoMax;                      /* FluidNodeList::rhoMin / rhoMax */
+  double hminratio;                           /* NodeList::hminratio (ASPH) */
+  int    HEvolution;                          /* SPHB200_HEVOLUTION_* (SmoothingScaleBase.hh) */
+} sphb200_step_options;
+int  sphb200_sum_mass_density(sphb200_ctx* ctx);
+int  sphb200_compute_omega_gradh(sphb200_ctx* ctx);
+int  sphb200_update_eos_gamma_law(sphb200_ctx* ctx, const sphb200_gamma_law* eos);
+int  sphb200_state_copy(sphb200_ctx* ctx);
+int  sphb200_state_assign(sphb200_ctx* ctx);
+int  sphb200_state_update(sphb200_ctx* ctx, const sphb200_step_options* so, double multiplier, int timeAdvanceOnly);
+int  sphb200_compute_dt(sphb200_ctx* ctx, double cfl, int useVelocityMagnitudeForDt, double* dt, int* reason, uint32_t* node);
 
 /* ---- compatible energy -----------------------------------------------------------------------------------------
    replaces: SpecificThermalEnergyPolicy::update (Hydro/SpecificThermalEnergyPolicy.cc:47-174):

@@ -61,6 +61,16 @@ class Derivs(C.Structure):
     _fields_ = [(k, _dp) for k in DERIV_FIELDS]
 
 
+class StepOptions(C.Structure):
+    _fields_ = [("gamma", C.c_double), ("minimumPressure", C.c_double), ("maximumPressure", C.c_double),
+                ("externalPressure", C.c_double), ("minPressureType", C.c_int), ("rhoMin", C.c_double), ("rhoMax", C.c_double),
+                ("hminratio", C.c_double), ("HEvolution", C.c_int), ("cfl", C.c_double), ("useVelocityMagnitudeForDt", C.c_int)]
+
+
+HEVOLUTION_IDEALH, HEVOLUTION_INTEGRATEH, HEVOLUTION_FIXEDH = 0, 1, 2
+DT_REASONS = ("sound speed", "artificial viscosity", "velocity divergence", "acceleration", "velocity magnitude",
+              "pairwise velocity difference")
+
 _lib = None
 
 
@@ -98,6 +108,17 @@ def lib():
                                                    C.POINTER(State), _dp, _dp, C.c_size_t, u32p, u32p, C.POINTER(Derivs)]
         L.orc_rk_kernel_grad.argtypes = [C.c_int, C.POINTER(Table), _dp, _dp, _dp, _dp, _dp]
         L.orc_rk_kernel_grad.restype = None
+        L.orc_sum_mass_density.argtypes = [C.c_int, C.POINTER(Table), C.c_size_t, C.c_size_t, _dp, _dp, _dp, C.c_size_t, u32p, u32p, _dp]
+        L.orc_omega_gradh.argtypes = [C.c_int, C.POINTER(Table), C.c_size_t, C.c_size_t, _dp, _dp, C.c_size_t, u32p, u32p, u32p, _dp]
+        L.orc_eos_gamma_law.argtypes = [C.POINTER(StepOptions), C.c_size_t, _dp, _dp, _dp, _dp]
+        L.orc_eos_gamma_law.restype = None
+        L.orc_state_update.argtypes = [C.POINTER(Options), C.POINTER(StepOptions), C.c_size_t, C.c_size_t, C.c_double, C.c_int, C.c_int,
+                                       C.POINTER(Derivs), _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.orc_hydro_dt.restype = C.c_double
+        L.orc_hydro_dt.argtypes = [C.POINTER(Options), C.POINTER(StepOptions), C.c_size_t, _dp, _dp, _dp, _dp, C.POINTER(Derivs),
+                                   C.c_size_t, u32p, u32p, C.POINTER(C.c_int), u32p]
+        L.orc_sym_bound.argtypes = [C.c_int, _dp, C.c_double, C.c_double]
+        L.orc_sym_bound.restype = None
         _lib = L
     return _lib
 
@@ -339,3 +360,80 @@ def crk_evaluate_derivatives(opts, W, state, vol, corr, nInt, nGhost, pi, pj):
     if rc != 0:
         raise RuntimeError("oracle error %d" % rc)
     return out
+
+
+# ---- per-step callers of the derivative path ------------------------------------------------
+def default_step_options(**kw):
+    """GammaLawGas(gamma=5/3) with no pressure limits, rho in [1e-10, 1e10] (the FluidNodeList defaults),
+    hminratio 0.1 (NodeList default), IdealH, cfl 0.25 (GenericHydro default)."""
+    so = StepOptions()
+    so.gamma = 5.0/3.0
+    so.minimumPressure, so.maximumPressure, so.externalPressure, so.minPressureType = -1.0e200, 1.0e200, 0.0, 0
+    so.rhoMin, so.rhoMax, so.hminratio = 1.0e-10, 1.0e10, 0.1
+    so.HEvolution, so.cfl, so.useVelocityMagnitudeForDt = HEVOLUTION_IDEALH, 0.25, 0
+    for k, v in kw.items():
+        if not hasattr(so, k):
+            raise KeyError(k)
+        setattr(so, k, v)
+    return so
+
+
+def sum_mass_density(ndim, W, nInt, nGhost, pos, mass, H, pi, pj, rho=None):
+    """computeSPHSumMassDensity: internal entries written, ghost entries keep the caller's values."""
+    pos, mass, H = _c(pos), _c(mass), _c(H)
+    rho = np.zeros(nInt + nGhost) if rho is None else np.array(rho, dtype=np.float64, copy=True)
+    pi, pj = _c(pi, np.uint32), _c(pj, np.uint32)
+    t = W.ctable()
+    rc = lib().orc_sum_mass_density(ndim, C.byref(t), nInt, nGhost, _p(pos), _p(mass), _p(H), len(pi), _u(pi), _u(pj), _p(rho))
+    assert rc == 0
+    return rho
+
+
+def omega_gradh(ndim, W, nInt, nGhost, pos, H, pi, pj, counts, omega=None):
+    """computeSPHOmegaGradhCorrection: internal entries written."""
+    pos, H = _c(pos), _c(H)
+    omega = np.ones(nInt + nGhost) if omega is None else np.array(omega, dtype=np.float64, copy=True)
+    pi, pj, counts = _c(pi, np.uint32), _c(pj, np.uint32), _c(counts, np.uint32)
+    t = W.ctable()
+    rc = lib().orc_omega_gradh(ndim, C.byref(t), nInt, nGhost, _p(pos), _p(H), len(pi), _u(pi), _u(pj), _u(counts), _p(omega))
+    assert rc == 0
+    return omega
+
+
+def eos_gamma_law(so, rho, eps):
+    rho, eps = _c(rho), _c(eps)
+    P, cs = np.zeros_like(rho), np.zeros_like(rho)
+    lib().orc_eos_gamma_law(C.byref(so), len(rho), _p(rho), _p(eps), _p(P), _p(cs))
+    return P, cs
+
+
+def _derivs_struct(derivs):
+    keep = {k: _c(derivs[k]) for k in DERIV_FIELDS if k in derivs and derivs[k] is not None}
+    return Derivs(**{k: _p(v) for k, v in keep.items()}), keep
+
+
+def state_update(opts, so, nInt, nGhost, multiplier, timeAdvanceOnly, derivs, state, epsDone=False):
+    """State::update over the internal nodes.  state: dict pos, vel, H, rho, eps, P, cs (copied, returned updated)."""
+    out = {k: np.array(state[k], dtype=np.float64, copy=True) for k in ("pos", "vel", "H", "rho", "eps", "P", "cs")}
+    d, keep = _derivs_struct(derivs)
+    rc = lib().orc_state_update(C.byref(opts), C.byref(so), nInt, nGhost, multiplier, int(timeAdvanceOnly), int(epsDone), C.byref(d),
+                                _p(out["pos"]), _p(out["vel"]), _p(out["H"]), _p(out["rho"]), _p(out["eps"]), _p(out["P"]), _p(out["cs"]))
+    assert rc == 0
+    return out
+
+
+def hydro_dt(opts, so, nInt, vel, H, rho, cs, derivs, pi, pj):
+    """GenericHydro::dt -> (dt, reason string, node)."""
+    vel, H, rho, cs = _c(vel), _c(H), _c(rho), _c(cs)
+    pi, pj = _c(pi, np.uint32), _c(pj, np.uint32)
+    d, keep = _derivs_struct(derivs)
+    reason, node = C.c_int(), C.c_uint32()
+    dt = lib().orc_hydro_dt(C.byref(opts), C.byref(so), nInt, _p(vel), _p(H), _p(rho), _p(cs), C.byref(d), len(pi), _u(pi), _u(pj),
+                            C.byref(reason), C.byref(node))
+    return dt, DT_REASONS[reason.value], node.value
+
+
+def sym_bound(ndim, H, minv, maxv):
+    H = np.array(H, dtype=np.float64, copy=True)
+    lib().orc_sym_bound(ndim, _p(H), minv, maxv)
+    return H

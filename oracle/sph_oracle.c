@@ -337,3 +337,41 @@ void orc_rk_kernel_grad(int ndim, const orc_table* W, const double* x, const dou
                         double* WR, double* gradWR) {
   if (ndim == 3) rk_kernel_grad_3d(W, x, H, corr, WR, gradWR); else rk_kernel_grad_2d(W, x, H, corr, WR, gradWR);
 }
+
+/* ---- per-step callers (step_oracle_dim.inc) ------------------------------------------------------------------*/
+/* helpers of sph_oracle_dim.inc that the step file needs again (those macros are undefined at this point) */
+#define D 3
+#include "step_oracle_dim.inc"
+#undef D
+#define D 2
+#include "step_oracle_dim.inc"
+#undef D
+
+int orc_sum_mass_density(int ndim, const orc_table* W, size_t nInt, size_t nGhost, const double* pos, const double* mass,
+                         const double* H, size_t npairs, const uint32_t* pi, const uint32_t* pj, double* rho) {
+  return ndim == 3 ? sum_mass_density_3d(W, nInt, nGhost, pos, mass, H, npairs, pi, pj, rho)
+                   : sum_mass_density_2d(W, nInt, nGhost, pos, mass, H, npairs, pi, pj, rho);
+}
+int orc_omega_gradh(int ndim, const orc_table* W, size_t nInt, size_t nGhost, const double* pos, const double* H,
+                    size_t npairs, const uint32_t* pi, const uint32_t* pj, const uint32_t* numNeighbors, double* omega) {
+  return ndim == 3 ? omega_gradh_3d(W, nInt, nGhost, pos, H, npairs, pi, pj, numNeighbors, omega)
+                   : omega_gradh_2d(W, nInt, nGhost, pos, H, npairs, pi, pj, numNeighbors, omega);
+}
+void orc_eos_gamma_law(const orc_step_options* so, size_t n, const double* rho, const double* eps, double* P, double* cs) {
+  eos_gamma_law_3d(so, n, rho, eps, P, cs);
+}
+int orc_state_update(const orc_options* o, const orc_step_options* so, size_t nInt, size_t nGhost, double multiplier,
+                     int timeAdvanceOnly, int epsDone, const orc_derivs* d,
+                     double* pos, double* vel, double* H, double* rho, double* eps, double* P, double* cs) {
+  return o->ndim == 3 ? state_update_3d(o, so, nInt, nGhost, multiplier, timeAdvanceOnly, epsDone, d, pos, vel, H, rho, eps, P, cs)
+                      : state_update_2d(o, so, nInt, nGhost, multiplier, timeAdvanceOnly, epsDone, d, pos, vel, H, rho, eps, P, cs);
+}
+double orc_hydro_dt(const orc_options* o, const orc_step_options* so, size_t nInt, const double* vel, const double* H,
+                    const double* rho, const double* cs, const orc_derivs* d, size_t npairs, const uint32_t* pi,
+                    const uint32_t* pj, int* reason, uint32_t* node) {
+  return o->ndim == 3 ? hydro_dt_3d(o, so, nInt, vel, H, rho, cs, d, npairs, pi, pj, reason, node)
+                      : hydro_dt_2d(o, so, nInt, vel, H, rho, cs, d, npairs, pi, pj, reason, node);
+}
+void orc_sym_bound(int ndim, double* H, double minv, double maxv) {
+  if (ndim == 3) sym_bound_3d(H, minv, maxv); else sym_bound_2d(H, minv, maxv);
+}

@@ -142,6 +142,31 @@ int orc_crk_evaluate_derivatives(const orc_options* o, const orc_table* W, size_
 void orc_rk_kernel_grad(int ndim, const orc_table* W, const double* x, const double* H, const double* corr,
                         double* WR, double* gradWR);                                             /* RK/RKUtilities.cc:180-209 */
 
+/* ---- per-step callers of the derivative path (step_oracle_dim.inc) -----------------------
+   orc_step_options: what the reference keeps on the FluidNodeList / EquationOfState / Integrator / SmoothingScaleBase. */
+typedef struct {
+  double gamma;                              /* GammaLawGas (Material/GammaLawGas.cc) */
+  double minimumPressure, maximumPressure, externalPressure;
+  int    minPressureType;                    /* 0 PressureFloor | 1 ZeroPressure (EquationOfStateInline.hh:98-106) */
+  double rhoMin, rhoMax;                     /* FluidNodeList::rhoMin/rhoMax */
+  double hminratio;                          /* NodeList::hminratio (IncrementASPHHtensor.cc:58) */
+  int    HEvolution;                         /* 0 IdealH | 1 IntegrateH | 2 FixedH (SmoothingScaleBase.hh) */
+  double cfl;                                /* GenericHydro::cfl */
+  int    useVelocityMagnitudeForDt;
+} orc_step_options;
+int orc_sum_mass_density(int ndim, const orc_table* W, size_t nInt, size_t nGhost, const double* pos, const double* mass,
+                         const double* H, size_t npairs, const uint32_t* pi, const uint32_t* pj, double* rho);
+int orc_omega_gradh(int ndim, const orc_table* W, size_t nInt, size_t nGhost, const double* pos, const double* H,
+                    size_t npairs, const uint32_t* pi, const uint32_t* pj, const uint32_t* numNeighbors, double* omega);
+void orc_eos_gamma_law(const orc_step_options* so, size_t n, const double* rho, const double* eps, double* P, double* cs);
+int orc_state_update(const orc_options* o, const orc_step_options* so, size_t nInt, size_t nGhost, double multiplier,
+                     int timeAdvanceOnly, int epsDone, const orc_derivs* d,
+                     double* pos, double* vel, double* H, double* rho, double* eps, double* P, double* cs);
+double orc_hydro_dt(const orc_options* o, const orc_step_options* so, size_t nInt, const double* vel, const double* H,
+                    const double* rho, const double* cs, const orc_derivs* d, size_t npairs, const uint32_t* pi,
+                    const uint32_t* pj, int* reason, uint32_t* node);
+void orc_sym_bound(int ndim, double* H, double minv, double maxv);   /* test hook: eigenvalue clamp of one SymTensor */
+
 #ifdef __cplusplus
 }
 #endif

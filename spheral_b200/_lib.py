@@ -67,6 +67,21 @@ class HostDerivs(C.Structure):
     _fields_ = [(k, _dp) for k in DERIV_FIELDS]
 
 
+class GammaLaw(C.Structure):
+    _fields_ = [("gamma", C.c_double), ("minimumPressure", C.c_double), ("maximumPressure", C.c_double),
+                ("externalPressure", C.c_double), ("minPressureType", C.c_int)]
+
+
+HEVOLUTION_IDEALH, HEVOLUTION_INTEGRATEH, HEVOLUTION_FIXEDH = 0, 1, 2
+DT_REASONS = ("sound speed", "artificial viscosity", "velocity divergence", "acceleration", "velocity magnitude",
+              "pairwise velocity difference")
+
+
+class StepOptions(C.Structure):
+    _fields_ = [("eos", GammaLaw), ("rhoMin", C.c_double), ("rhoMax", C.c_double), ("hminratio", C.c_double),
+                ("HEvolution", C.c_int)]
+
+
 class Stats(C.Structure):
     _fields_ = [("launches", C.c_uint64), ("ms_build_pairs", C.c_float), ("ms_evaluate", C.c_float),
                 ("ms_energy", C.c_float), ("ms_pair_kernel", C.c_float), ("ms_neighbor_kernels", C.c_float),
@@ -81,7 +96,9 @@ EXPORTS = ("sphb200_abi_version", "sphb200_create", "sphb200_destroy", "sphb200_
            "sphb200_update_energy_compatible", "sphb200_halo_bytes_per_node", "sphb200_halo_pack",
            "sphb200_halo_unpack", "sphb200_node_bounds", "sphb200_halo_select", "sphb200_stream", "sphb200_get_stats", "sphb200_measure_fp64_peak",
            "sphb200_node_bounds_device", "sphb200_halo_select_device",
-           "sphb200_crk_compute_volume", "sphb200_crk_compute_corrections", "sphb200_crk_sum_mass_density")
+           "sphb200_crk_compute_volume", "sphb200_crk_compute_corrections", "sphb200_crk_sum_mass_density",
+           "sphb200_sum_mass_density", "sphb200_compute_omega_gradh", "sphb200_update_eos_gamma_law", "sphb200_state_copy",
+           "sphb200_state_assign", "sphb200_state_update", "sphb200_compute_dt")
 
 _lib = None
 
@@ -138,5 +155,12 @@ def lib():
     L.sphb200_crk_compute_volume.argtypes = [vp]
     L.sphb200_crk_compute_corrections.argtypes = [vp]
     L.sphb200_crk_sum_mass_density.argtypes = [vp, C.c_double, C.c_double]
+    L.sphb200_sum_mass_density.argtypes = [vp]
+    L.sphb200_compute_omega_gradh.argtypes = [vp]
+    L.sphb200_update_eos_gamma_law.argtypes = [vp, C.POINTER(GammaLaw)]
+    L.sphb200_state_copy.argtypes = [vp]
+    L.sphb200_state_assign.argtypes = [vp]
+    L.sphb200_state_update.argtypes = [vp, C.POINTER(StepOptions), C.c_double, C.c_int]
+    L.sphb200_compute_dt.argtypes = [vp, C.c_double, C.c_int, _dp, C.POINTER(C.c_int), _u32p]
     _lib = L
     return L

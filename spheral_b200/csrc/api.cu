@@ -119,7 +119,8 @@ int alloc_nodes(sphb200_ctx* c, size_t n) {
   };
   if (reall(c->rows, cap*(size_t)(c->ndim == 3 ? 16 : 12))) return 1;
   if (reall(c->aux2, cap*2)) return 1;
-  if (crk && (reall(c->crkVolS, cap) || reall(c->crkCorrS, cap*(size_t)(c->ndim == 3 ? 16 : 10)))) return 1;
+  if (crk && (reall(c->crkVolS, cap) || reall(c->crkCorrS, cap*(size_t)(c->ndim == 3 ? 16 : 10)) ||
+              reall(c->crkQS, cap*(size_t)(c->ndim == 3 ? 10 : 6)) || reall(c->crkAux, cap*2))) return 1;
   for (int s = 0; s < DV_COUNT; ++s) if (reall(c->deriv[s], cap*(size_t)sphb200_deriv_width(c->ndim, s))) return 1;
   auto reall32 = [&](uint32_t*& p, size_t cnt) -> int {
     if (p) cudaFree(p);
@@ -138,6 +139,7 @@ int alloc_nodes(sphb200_ctx* c, size_t n) {
   if (c->frows) { cudaFree(c->frows); c->frows = nullptr; c->frowsCap = 0; }
   c->cap = cap;
   c->sortValid = c->rowsValid = c->pairsValid = c->derivsValid = false;
+  c->derivNodeValid = false;
   return 0;
 }
 
@@ -210,7 +212,8 @@ void sphb200_destroy(sphb200_ctx* c) {
                   (void*)c->cellCursor, (void*)c->perm, (void*)c->skey, (void*)c->reduceBuf, (void*)c->rows, (void*)c->aux2, (void*)c->auxPneg, (void*)c->auxSomr2,
                   (void*)c->auxDvDxQ, (void*)c->auxfCl, (void*)c->auxfCq, (void*)c->nbrCount, (void*)c->tileRows, (void*)c->tileOff, (void*)c->nbr,
                   (void*)c->counters, (void*)c->frows, (void*)c->scanTmp, (void*)c->pacc, (void*)c->stage,
-                  (void*)c->runs, (void*)c->tileRunStart, (void*)c->tileRunCount, (void*)c->dilTab, (void*)c->crkVolS, (void*)c->crkCorrS}) cudaFree(p);
+                  (void*)c->runs, (void*)c->tileRunStart, (void*)c->tileRunCount, (void*)c->dilTab, (void*)c->crkVolS, (void*)c->crkCorrS, (void*)c->crkQS, (void*)c->crkAux, (void*)c->permEval, (void*)c->dtCand, (void*)c->dtAux}) cudaFree(p);
+  for (int s = 0; s < S_COUNT; ++s) if (c->api0[s]) cudaFree(c->api0[s]);
   cudaFreeHost(c->reduceHost); cudaFreeHost(c->countersHost);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -391,6 +394,10 @@ int sphb200_evaluate_derivatives(sphb200_ctx* c, double /*time*/, double /*dt*/)
   cudaEventRecord(c->ev[4], c->stream);
   if (crk ? sphb200_launch_crk_derivs(c) : sphb200_launch_derivs(c)) return 1;
   cudaEventRecord(c->ev[5], c->stream);
+  // keep the sorted order these node-wise derivatives are stored in (see permEval)
+  if (sphb200_ensure(c, c->permEval, c->permEvalCap, c->cap)) return 1;
+  CU_CHECK(c, cudaMemcpyAsync(c->permEval, c->perm, c->n*sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+  c->nEval = c->n; c->capEval = c->cap; c->nIntEval = c->nInt; c->derivNodeValid = true;
   return 0;
 }
 
@@ -433,10 +440,12 @@ int sphb200_download_derivs(sphb200_ctx* c, unsigned mask, const sphb200_host_de
 
 int sphb200_copy_DvDx_to_Q(sphb200_ctx* c) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  if (!c->derivsValid) return sphb200_fail(c, "copy_DvDx_to_Q: derivatives have not been evaluated");
+  // node-wise derivatives stay usable after a later build_pairs (permEval keeps the order they are stored in)
+  if (!c->derivNodeValid) return sphb200_fail(c, "copy_DvDx_to_Q: derivatives have not been evaluated");
+  if (c->nEval != c->n) return sphb200_fail(c, "copy_DvDx_to_Q: the node count changed since the derivatives were evaluated");
   CU_CHECK(c, cudaSetDevice(c->device));
   if (c->n == 0) return 0;
-  k_copy_dvdx<<<(unsigned)((c->n + RB - 1)/RB), RB, 0, c->stream>>>(c->deriv[DV_DVDX], c->cap, c->perm, c->n, c->ndim*c->ndim, c->api[S_DVDXQ]);
+  k_copy_dvdx<<<(unsigned)((c->nEval + RB - 1)/RB), RB, 0, c->stream>>>(c->deriv[DV_DVDX], c->capEval, c->permEval, c->nEval, c->ndim*c->ndim, c->api[S_DVDXQ]);
   KERNEL_CHECK(c, "k_copy_dvdx");
   c->have[S_DVDXQ] = true;
   c->rowsValid = false;

@@ -13,19 +13,42 @@
 // its field; ghost entries come from the caller (boundary conditions / halo), as in the reference.
 #include "sphb200_internal.cuh"
 #include "pair_common.cuh"
+#include "nbr_ring.cuh"
 #include <algorithm>
 #include <cmath>
+
+#ifndef SPHB200_CRK_LIGHT_WARPS
+#define SPHB200_CRK_LIGHT_WARPS 8
+#endif
+#ifndef SPHB200_CRK_LIGHT_STAGES
+#define SPHB200_CRK_LIGHT_STAGES 4
+#endif
+#ifndef SPHB200_CRK_WARPS
+#define SPHB200_CRK_WARPS 8
+#endif
+#ifndef SPHB200_CRK_STAGES
+#define SPHB200_CRK_STAGES 2
+#endif
 
 namespace {
 
 constexpr int RB = 256;
-constexpr int CRK_WARPS = 4;
+// Persistent CTAs, one per SM.  Light loops (volume, corrections, sum density): LW warps with a ring LS deep of node rows;
+// the derivative loop: CW warps with a ring CS deep of {node row, RK corrections, {volume, Q velocity gradient}} (352 B per
+// neighbour in 3-D, so the ring depth is what shared memory allows).
+constexpr int LW = SPHB200_CRK_LIGHT_WARPS, LS = SPHB200_CRK_LIGHT_STAGES;
+constexpr int CW = SPHB200_CRK_WARPS, CS = SPHB200_CRK_STAGES;
 
 template <int DIM> struct Ck {
   static constexpr int PS = DIM + 1;            // polynomialSize of LinearOrder (RKUtilitiesInline.hh:44-55)
   static constexpr int NC = PS*(1 + DIM);       // correctionsSize(false): C, then dC_d per direction
   static constexpr int CST = (DIM == 3) ? 16 : 10;   // stride of the sorted copy (16-byte aligned records)
+  static constexpr int QST = (DIM == 3) ? 10 : 6;    // sorted record {volume, Q velocity gradient (ndim^2), pad}
 };
+template <int DIM> struct LightPrefix { static constexpr int BYTES = ((Dm<DIM>::R_M + 1)*8 + 15)/16*16; };   // position .. mass: 112 B (3-D) / 64 B (2-D)
+template <int DIM> using LightRing = NbrRing<DIM, 0, 0, LS, LightPrefix<DIM>::BYTES>;
+template <int DIM> using PosRing = NbrRing<DIM, 0, 0, LS, (DIM == 3 ? 32 : 16)>;            // the position only
+template <int DIM> using DerivRing = NbrRing<DIM, Ck<DIM>::CST*8, Ck<DIM>::QST*8, CS>;
 
 // api (host order, AoS, width doubles per node) -> sorted copy with stride `stride`
 __global__ void __launch_bounds__(RB) k_gather_sorted(const double* __restrict__ api, int width, int stride,
@@ -36,10 +59,29 @@ __global__ void __launch_bounds__(RB) k_gather_sorted(const double* __restrict__
   out[t] = (q < width) ? api[(size_t)perm[s]*width + q] : 0.0;
 }
 
+// {volume (host order), Q velocity gradient (already sorted, or absent)} -> sorted records of stride qst
+__global__ void __launch_bounds__(RB) k_crk_qrec(const double* __restrict__ volApi, const double* __restrict__ dvdxqS, int nt, int qst,
+                                                 const uint32_t* __restrict__ perm, size_t n, double* __restrict__ out) {
+  const size_t t = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (t >= n*(size_t)qst) return;
+  const size_t s = t/qst; const int q = (int)(t - s*qst);
+  out[t] = (q == 0) ? volApi[perm[s]] : ((q <= nt && dvdxqS) ? dvdxqS[s*nt + (q - 1)] : 0.0);
+}
+
+// sorted volume + the CRK aux record {det H, volume} the light loops stream through the ring in place of {det H, 1/rho}
+__global__ void __launch_bounds__(RB) k_crk_volaux(const double* __restrict__ volApi, const double* __restrict__ aux2,
+                                                   const uint32_t* __restrict__ perm, size_t n, double* __restrict__ volS, double* __restrict__ vaux) {
+  const size_t s = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (s >= n) return;
+  const double v = volApi[perm[s]];
+  volS[s] = v;
+  vaux[2*s] = aux2[2*s]; vaux[2*s + 1] = v;
+}
+
 struct CrkArgs {
   const double* rows; const double* aux2; const uint32_t* perm;
   const uint32_t* nbrCount; const uint32_t* tileRows; const unsigned long long* tileOff; const uint32_t* nbr;
-  const double* volS; const double* corrS;
+  const double* volS; const double* corrS; const double* qrecS;
   const double *auxDvDxQ, *auxfCl, *auxfCq;
   const double* tabW; double kext, xmin, xstep; uint32_t n1;
   const double* nperhVals; uint32_t nperhN; double nperhXmin, nperhXmax, nperhXstep;
@@ -67,46 +109,67 @@ template <int DIM> __device__ __forceinline__ void load_row(const double* __rest
   for (int q = 0; q < ROW/2; ++q) { const double2 v = __ldg(p + q); rw[2*q] = v.x; rw[2*q + 1] = v.y; }
 }
 
+// per-lane view of one tile of 32 Morton-consecutive nodes
+struct TileLane { size_t i; bool inRange, active; uint32_t o, cnt, rowsT; unsigned long long base; };
+__device__ __forceinline__ TileLane tile_lane(const CrkArgs& a, size_t tile, int lane) {
+  TileLane t;
+  t.i = tile*SPHB200_TILE + lane;
+  t.inRange = t.i < a.n;
+  t.o = t.inRange ? a.perm[t.i] : 0xffffffffu;
+  t.active = t.inRange && t.o < a.nInt;
+  t.cnt = t.active ? a.nbrCount[t.i] : 0u;
+  t.rowsT = a.tileRows[tile];
+  t.base = a.tileOff[tile] + lane;
+  return t;
+}
+template <typename Ring> __device__ __forceinline__ Ring make_ring(const CrkArgs& a, unsigned tW, int warp) {
+  Ring r;
+  r.base = tW + 48u*(a.n1 + 2u) + (unsigned)warp*(unsigned)Ring::WARPB;
+  r.rows = reinterpret_cast<const unsigned char*>(a.rows);
+  r.x1 = reinterpret_cast<const unsigned char*>(a.corrS);
+  r.x2 = reinterpret_cast<const unsigned char*>(a.qrecS);
+  r.aux2 = reinterpret_cast<const unsigned char*>(a.aux2);
+  return r;
+}
+
 // ---- computeRKSumVolume ------------------------------------------------------------------------------------------------
 template <int DIM>
-__global__ void __launch_bounds__(32*CRK_WARPS) k_crk_volume(CrkArgs a) {
+__global__ void __launch_bounds__(32*LW, 1) k_crk_volume(CrkArgs a) {
   using D = Dm<DIM>;
   extern __shared__ __align__(16) double smem[];
   const unsigned tW = stage_table(smem, a.tabW, a.n1);
   const double rx = 1.0/a.xstep;
-  const int lane = threadIdx.x & 31;
-  const size_t tile = (size_t)blockIdx.x*CRK_WARPS + (threadIdx.x >> 5);
-  const size_t i = tile*SPHB200_TILE + lane;
-  if (tile*SPHB200_TILE >= a.n) return;
-  const bool inRange = i < a.n;
-  const uint32_t o = inRange ? a.perm[i] : 0xffffffffu;
-  const bool active = inRange && o < a.nInt;
-  double ri[DIM], Hi[D::NS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const PosRing<DIM> ring = make_ring<PosRing<DIM>>(a, tW, warp);
+  const size_t nTiles = (a.n + SPHB200_TILE - 1)/SPHB200_TILE;
+  for (size_t tile = (size_t)blockIdx.x*LW + warp; tile < nTiles; tile += (size_t)gridDim.x*LW) {
+    const TileLane t = tile_lane(a, tile, lane);
+    double ri[DIM], Hi[D::NS];
 #pragma unroll
-  for (int k = 0; k < DIM; ++k) ri[k] = inRange ? a.rows[i*D::ROW + D::R_POS + k] : 0.0;
+    for (int k = 0; k < DIM; ++k) ri[k] = t.inRange ? a.rows[t.i*D::ROW + D::R_POS + k] : 0.0;
 #pragma unroll
-  for (int k = 0; k < D::NS; ++k) Hi[k] = inRange ? a.rows[i*D::ROW + D::R_H + k] : 0.0;
-  const uint32_t cnt = active ? a.nbrCount[i] : 0u;
-  const uint32_t rowsT = a.tileRows[tile];
-  const unsigned long long base = a.tileOff[tile] + lane;
-  double sum = 0.0;
-  for (uint32_t k = 0; k < rowsT; ++k) {
-    if (k >= cnt) continue;
-    const size_t j = a.nbr[base + (unsigned long long)k*SPHB200_TILE];
-    double rij[DIM], eta[DIM];
+    for (int k = 0; k < D::NS; ++k) Hi[k] = t.inRange ? a.rows[t.i*D::ROW + D::R_H + k] : 0.0;
+    double sum = 0.0;
+    ring_walk<PosRing<DIM>, LS>(ring, lane, t.rowsT, t.cnt,
+      [&](uint32_t p) -> uint32_t { return (p < t.cnt) ? a.nbr[t.base + (unsigned long long)p*SPHB200_TILE] : 0u; },
+      [&](uint32_t k, uint32_t) {
+        double rj[DIM == 3 ? 4 : 2];
+        ring.read_row(k, lane, rj);                            // the position leads the row
+        double rij[DIM], eta[DIM];
 #pragma unroll
-    for (int q = 0; q < DIM; ++q) rij[q] = ri[q] - __ldg(a.rows + j*D::ROW + D::R_POS + q);
-    sym_dot<DIM>(Hi, rij, eta);
-    const double e2 = vdot<DIM>(eta, eta);
-    const double etaMag = e2*fast_rsqrt(e2 + 1.0e-300);
-    double W, gW;
-    table_eval_raw(tW, a.kext, a.xmin, a.xstep, rx, a.n1, etaMag, W, gW);
-    sum += W;                                              // Wi = Hdeti * W(eta_i), Hdeti applied once below
-  }
-  if (active) {
-    const double Hdeti = sym_det<DIM>(Hi);
-    const double s = sum*Hdeti + Hdeti*a.W0;               // :104-113 self contribution and the eta-space cap
-    a.volApi[o] = fmin(a.etaVolMax/Hdeti, 1.0/s);
+        for (int q = 0; q < DIM; ++q) rij[q] = ri[q] - rj[q];
+        sym_dot<DIM>(Hi, rij, eta);
+        const double e2 = vdot<DIM>(eta, eta);
+        const double etaMag = e2*fast_rsqrt(e2 + 1.0e-300);
+        double W, gW;
+        table_eval_raw(tW, a.kext, a.xmin, a.xstep, rx, a.n1, etaMag, W, gW);
+        sum += W;                                            // Wi = Hdeti * W(eta_i), Hdeti applied once below
+      });
+    if (t.active) {
+      const double Hdeti = sym_det<DIM>(Hi);
+      const double s = sum*Hdeti + Hdeti*a.W0;               // :104-113 self contribution and the eta-space cap
+      a.volApi[t.o] = fmin(a.etaVolMax/Hdeti, 1.0/s);
+    }
   }
 }
 
@@ -207,25 +270,21 @@ template <int N> __device__ __forceinline__ void qr_solve(const QrDev<N>& q, con
 
 // ---- RKUtilities<Dim, LinearOrder>::computeCorrections ----------------------------------------------------------------------
 template <int DIM>
-__global__ void __launch_bounds__(32*CRK_WARPS) k_crk_corrections(CrkArgs a) {
+__global__ void __launch_bounds__(32*LW, 1) k_crk_corrections(CrkArgs a) {
   using D = Dm<DIM>;
   constexpr int PS = Ck<DIM>::PS, NC = Ck<DIM>::NC;
   extern __shared__ __align__(16) double smem[];
   const unsigned tW = stage_table(smem, a.tabW, a.n1);
   const double rx = 1.0/a.xstep;
-  const int lane = threadIdx.x & 31;
-  const size_t tile = (size_t)blockIdx.x*CRK_WARPS + (threadIdx.x >> 5);
-  const size_t i = tile*SPHB200_TILE + lane;
-  if (tile*SPHB200_TILE >= a.n) return;
-  const bool inRange = i < a.n;
-  const uint32_t o = inRange ? a.perm[i] : 0xffffffffu;
-  const bool active = inRange && o < a.nInt;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const LightRing<DIM> ring = make_ring<LightRing<DIM>>(a, tW, warp);
+  const size_t nTiles = (a.n + SPHB200_TILE - 1)/SPHB200_TILE;
+  for (size_t tile = (size_t)blockIdx.x*LW + warp; tile < nTiles; tile += (size_t)gridDim.x*LW) {
+  const TileLane t = tile_lane(a, tile, lane);
+  const size_t i = t.i; const uint32_t o = t.o;
   double ri[DIM];
 #pragma unroll
-  for (int k = 0; k < DIM; ++k) ri[k] = inRange ? a.rows[i*D::ROW + D::R_POS + k] : 0.0;
-  const uint32_t cnt = active ? a.nbrCount[i] : 0u;
-  const uint32_t rowsT = a.tileRows[tile];
-  const unsigned long long base = a.tileOff[tile] + lane;
+  for (int k = 0; k < DIM; ++k) ri[k] = t.inRange ? a.rows[i*D::ROW + D::R_POS + k] : 0.0;
 
   double M[PS][PS], dM[DIM][PS][PS];
 #pragma unroll
@@ -259,12 +318,13 @@ __global__ void __launch_bounds__(32*CRK_WARPS) k_crk_corrections(CrkArgs a) {
       }
   };
 
-  for (uint32_t k = 0; k < rowsT; ++k) {
-    if (k >= cnt) continue;
-    const size_t j = a.nbr[base + (unsigned long long)k*SPHB200_TILE];
-    double rw[D::ROW];
-    load_row<DIM>(a.rows, j, rw);
-    const double vj = __ldg(a.volS + j), Hdetj = __ldg(a.aux2 + 2*j);
+  ring_walk<LightRing<DIM>, LS>(ring, lane, t.rowsT, t.cnt,
+    [&](uint32_t p) -> uint32_t { return (p < t.cnt) ? a.nbr[t.base + (unsigned long long)p*SPHB200_TILE] : 0u; },
+    [&](uint32_t k, uint32_t) {
+    double rw[LightPrefix<DIM>::BYTES/8];
+    ring.read_row(k, lane, rw);
+    const double2 ax = ring.read_aux(k, lane);              // {det Hj, Vj}
+    const double Hdetj = ax.x, vj = ax.y;
     double xij[DIM], eta[DIM], Heta[DIM], dw[DIM];
 #pragma unroll
     for (int q = 0; q < DIM; ++q) xij[q] = ri[q] - rw[D::R_POS + q];
@@ -278,8 +338,8 @@ __global__ void __launch_bounds__(32*CRK_WARPS) k_crk_corrections(CrkArgs a) {
 #pragma unroll
     for (int q = 0; q < DIM; ++q) dw[q] = sc*Heta[q];
     add(xij, vj, W*Hdetj, dw);
-  }
-  if (!active) return;
+  });
+  if (!t.active) continue;
   {
     // self contribution (RKUtilities.cc:383): x = 0, unitVector() of the zero vector is (1,0,0) (GeomVectorInline.hh:998-1001)
     double Hi[D::NS], xij[DIM], dw[DIM];
@@ -318,73 +378,73 @@ __global__ void __launch_bounds__(32*CRK_WARPS) k_crk_corrections(CrkArgs a) {
 #pragma unroll
     for (int k = 0; k < PS; ++k) out[PS*(1 + d) + k] = dC[k];
   }
+  }   // tile loop
 }
 
 // ---- computeCRKSPHSumMassDensity ----------------------------------------------------------------------------------------------
 template <int DIM>
-__global__ void __launch_bounds__(32*CRK_WARPS) k_crk_sum_density(CrkArgs a) {
+__global__ void __launch_bounds__(32*LW, 1) k_crk_sum_density(CrkArgs a) {
   using D = Dm<DIM>;
   extern __shared__ __align__(16) double smem[];
   const unsigned tW = stage_table(smem, a.tabW, a.n1);
   const double rx = 1.0/a.xstep;
-  const int lane = threadIdx.x & 31;
-  const size_t tile = (size_t)blockIdx.x*CRK_WARPS + (threadIdx.x >> 5);
-  const size_t i = tile*SPHB200_TILE + lane;
-  if (tile*SPHB200_TILE >= a.n) return;
-  const bool inRange = i < a.n;
-  const uint32_t o = inRange ? a.perm[i] : 0xffffffffu;
-  const bool active = inRange && o < a.nInt;
-  double ri[DIM];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const LightRing<DIM> ring = make_ring<LightRing<DIM>>(a, tW, warp);
+  const size_t nTiles = (a.n + SPHB200_TILE - 1)/SPHB200_TILE;
+  for (size_t tile = (size_t)blockIdx.x*LW + warp; tile < nTiles; tile += (size_t)gridDim.x*LW) {
+    const TileLane t = tile_lane(a, tile, lane);
+    const size_t i = t.i;
+    double ri[DIM];
 #pragma unroll
-  for (int k = 0; k < DIM; ++k) ri[k] = inRange ? a.rows[i*D::ROW + D::R_POS + k] : 0.0;
-  const uint32_t cnt = active ? a.nbrCount[i] : 0u;
-  const uint32_t rowsT = a.tileRows[tile];
-  const unsigned long long base = a.tileOff[tile] + lane;
-  double wsum = 0.0, md = 0.0, vol1 = 0.0;
-  for (uint32_t k = 0; k < rowsT; ++k) {
-    if (k >= cnt) continue;
-    const size_t j = a.nbr[base + (unsigned long long)k*SPHB200_TILE];
-    double rw[D::ROW];
-    load_row<DIM>(a.rows, j, rw);
-    const double Vj = __ldg(a.volS + j), Hdetj = __ldg(a.aux2 + 2*j);
-    double rij[DIM], eta[DIM];
+    for (int k = 0; k < DIM; ++k) ri[k] = t.inRange ? a.rows[i*D::ROW + D::R_POS + k] : 0.0;
+    double wsum = 0.0, md = 0.0, vol1 = 0.0;
+    ring_walk<LightRing<DIM>, LS>(ring, lane, t.rowsT, t.cnt,
+      [&](uint32_t p) -> uint32_t { return (p < t.cnt) ? a.nbr[t.base + (unsigned long long)p*SPHB200_TILE] : 0u; },
+      [&](uint32_t k, uint32_t) {
+        double rw[LightPrefix<DIM>::BYTES/8];
+        ring.read_row(k, lane, rw);
+        const double2 ax = ring.read_aux(k, lane);            // {det Hj, Vj}
+        const double Hdetj = ax.x, Vj = ax.y;
+        double rij[DIM], eta[DIM];
 #pragma unroll
-    for (int q = 0; q < DIM; ++q) rij[q] = ri[q] - rw[D::R_POS + q];
-    sym_dot<DIM>(rw + D::R_H, rij, eta);
-    const double e2 = vdot<DIM>(eta, eta);
-    double W, gW;
-    table_eval_raw(tW, a.kext, a.xmin, a.xstep, rx, a.n1, e2*fast_rsqrt(e2 + 1.0e-300), W, gW);
-    const double VW = Vj*(W*Hdetj);                          // :87-92, i side
-    wsum += VW; md = fma(rw[D::R_M], VW, md); vol1 = fma(Vj, VW, vol1);
-  }
-  if (active) {
-    const double mi = a.rows[i*D::ROW + D::R_M], Vi = a.volS[i], Hdeti = a.aux2[2*i];
-    const double ws = wsum + Vi*Hdeti*a.W0;                  // :115-122
-    const double v1 = (vol1 + Vi*Vi*Hdeti*a.W0)/ws;
-    a.rhoApi[o] = fmax(fmax(a.rhoMin, 0.1*mi*Hdeti), fmin(a.rhoMax, (md + mi*Vi*Hdeti*a.W0)/(ws*v1)));
+        for (int q = 0; q < DIM; ++q) rij[q] = ri[q] - rw[D::R_POS + q];
+        sym_dot<DIM>(rw + D::R_H, rij, eta);
+        const double e2 = vdot<DIM>(eta, eta);
+        double W, gW;
+        table_eval_raw(tW, a.kext, a.xmin, a.xstep, rx, a.n1, e2*fast_rsqrt(e2 + 1.0e-300), W, gW);
+        const double VW = Vj*(W*Hdetj);                        // :87-92, i side
+        wsum += VW; md = fma(rw[D::R_M], VW, md); vol1 = fma(Vj, VW, vol1);
+      });
+    if (t.active) {
+      const double mi = a.rows[i*D::ROW + D::R_M], Vi = a.volS[i], Hdeti = a.aux2[2*i];
+      const double ws = wsum + Vi*Hdeti*a.W0;                  // :115-122
+      const double v1 = (vol1 + Vi*Vi*Hdeti*a.W0)/ws;
+      a.rhoApi[t.o] = fmax(fmax(a.rhoMin, 0.1*mi*Hdeti), fmin(a.rhoMax, (md + mi*Vi*Hdeti*a.W0)/(ws*v1)));
+    }
   }
 }
 
 // ---- CRKSPH<Dim>::evaluateDerivativesImpl + smoothing-scale sub-package ---------------------------------------------------------
 template <int DIM>
-__global__ void __launch_bounds__(32*CRK_WARPS) k_crk_derivs(CrkArgs a) {
+__global__ void __launch_bounds__(32*CW, 1) k_crk_derivs(CrkArgs a) {
   using D = Dm<DIM>;
-  constexpr int NS = D::NS, NT = D::NT, ROW = D::ROW, PS = Ck<DIM>::PS, CST = Ck<DIM>::CST;
+  constexpr int NS = D::NS, NT = D::NT, ROW = D::ROW, PS = Ck<DIM>::PS, CST = Ck<DIM>::CST, QST = Ck<DIM>::QST;
   extern __shared__ __align__(16) double smem[];
   const unsigned tW = stage_table(smem, a.tabW, a.n1);
   const double rx = 1.0/a.xstep;
-  const int lane = threadIdx.x & 31;
-  const size_t tile = (size_t)blockIdx.x*CRK_WARPS + (threadIdx.x >> 5);
-  const size_t i = tile*SPHB200_TILE + lane;
-  if (tile*SPHB200_TILE >= a.n) return;
-  const bool inRange = i < a.n;
-  const uint32_t o = inRange ? a.perm[i] : 0xffffffffu;
-  const bool active = inRange && o < a.nInt;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const DerivRing<DIM> ring = make_ring<DerivRing<DIM>>(a, tW, warp);
+  const size_t nTiles = (a.n + SPHB200_TILE - 1)/SPHB200_TILE;
+  for (size_t tile = (size_t)blockIdx.x*CW + warp; tile < nTiles; tile += (size_t)gridDim.x*CW) {
+  const TileLane t = tile_lane(a, tile, lane);
+  const size_t i = t.i;
+  const bool inRange = t.inRange, active = t.active;
   const sphb200_options& op = a.o;
   const bool xsph = op.XSPH != 0, hsph = op.hEvolution == SPHB200_H_SPH, compat = op.compatibleEnergy != 0;
   const bool limited = op.Qkind == SPHB200_Q_LIMITED_MG;
   const bool needQ = limited || op.balsara;
   const bool mult = a.auxfCl != nullptr;
+  const double etaCrit = op.etaCritFrac/op.nPerh, rEtaFold = op.nPerh/op.etaFoldFrac;
 
   double rwi[ROW], ci_[CST];
   if (inRange) {
@@ -416,23 +476,16 @@ __global__ void __launch_bounds__(32*CRK_WARPS) k_crk_derivs(CrkArgs a) {
 #pragma unroll
   for (int q = 0; q < NT; ++q) DvDx[q] = 0;
 
-  const uint32_t cnt = active ? a.nbrCount[i] : 0u;
-  const uint32_t rowsT = a.tileRows[tile];
-  const unsigned long long base = a.tileOff[tile] + lane;
   double* const paccTile = compat ? a.pacc + (size_t)DIM*a.tileOff[tile] + lane : nullptr;
 
-  uint32_t jn = (0u < cnt) ? a.nbr[base] : 0u;
-  for (uint32_t k = 0; k < rowsT; ++k) {
-    const uint32_t j = jn;
-    jn = (k + 1u < cnt) ? a.nbr[base + (unsigned long long)(k + 1u)*SPHB200_TILE] : 0u;     // next index, one iteration ahead
-    if (k >= cnt) continue;
-    double rw[ROW], cj_[CST];
-    load_row<DIM>(a.rows, j, rw);
-    { const double2* p = reinterpret_cast<const double2*>(a.corrS + (size_t)j*CST);
-#pragma unroll
-      for (int q = 0; q < CST/2; ++q) { const double2 v = __ldg(p + q); cj_[2*q] = v.x; cj_[2*q + 1] = v.y; } }
-    const double2 auxj = __ldg(reinterpret_cast<const double2*>(a.aux2) + j);
-    const double Hdetj = auxj.x, volj = __ldg(a.volS + j);
+  ring_walk<DerivRing<DIM>, CS>(ring, lane, t.rowsT, t.cnt,
+    [&](uint32_t p) -> uint32_t { return (p < t.cnt) ? a.nbr[t.base + (unsigned long long)p*SPHB200_TILE] : 0u; },
+    [&](uint32_t k, uint32_t j) {
+    // records are read from the ring where they are first needed (42 doubles of neighbour state would otherwise be live at once)
+    double rw[ROW], cj_[CST], qj_[QST];
+    ring.read_row(k, lane, rw);
+    const double2 auxj = ring.read_aux(k, lane);            // {det Hj, Vj}
+    const double Hdetj = auxj.x, volj = auxj.y;
     const double* rj = rw + D::R_POS; const double* vj = rw + D::R_VEL; const double* Hj = rw + D::R_H;
     const double mj = rw[D::R_M], rhoj = rw[D::R_RHO], Pj = rw[D::R_PRHO], csj = rw[D::R_CS];
 
@@ -457,6 +510,7 @@ __global__ void __launch_bounds__(32*CRK_WARPS) k_crk_derivs(CrkArgs a) {
     sym_dot<DIM>(Hj, etaj, Hej);
     const double sj = gWbj*invj, si = -(gWbi*invi);          // x = -rij flips the unit vector of the i-side base gradient
 
+    ring.template read_x1<CST>(k, lane, cj_);
     // :339-341 evaluateKernelAndGradient (RKUtilities.cc:180-209), P = {1, x}, dP_d = e_{1+d}
     //   (Wj, gradWj) = WR( rij, Hj, corrections_i)     (Wi, gradWi) = WR(-rij, Hi, corrections_j)
     double CPj = ci_[0], CPi = cj_[0];
@@ -483,23 +537,24 @@ __global__ void __launch_bounds__(32*CRK_WARPS) k_crk_derivs(CrkArgs a) {
       double fshear = 1.0, fClj = 1.0, fCqj = 1.0;
       if (mult) { fClj = a.auxfCl[j]; fCqj = a.auxfCq[j]; }
       if (needQ) {
-        double DvDxQj[NT];
-#pragma unroll
-        for (int q = 0; q < NT; ++q) DvDxQj[q] = __ldg(a.auxDvDxQ + (size_t)j*NT + q);
+        ring.template read_x2<QST>(k, lane, qj_);            // {Vj, Q velocity gradient of j}
+        const double* DvDxQj = qj_ + 1;
         if (op.balsara) fshear = 0.5*(balsi + balsara<DIM>(op, DvDxQj, Hdetj, csj));
         if (limited) {
-          const double etaCrit = op.etaCritFrac/op.nPerh, etaFold = op.etaFoldFrac/op.nPerh;
           double xij[DIM], t1[DIM], t2[DIM];
 #pragma unroll
           for (int q = 0; q < DIM; ++q) xij[q] = 0.5*rij[q];
           ten_dot<DIM>(DvDxQi, xij, t1); const double gradi = vdot<DIM>(t1, xij);
           ten_dot<DIM>(DvDxQj, xij, t2); const double gradj = vdot<DIM>(t2, xij);
-          const double rri = gradi/(d_sgn(gradj)*fmax(1.0e-30, fabs(gradj)));
-          const double rrj = gradj/(d_sgn(gradi)*fmax(1.0e-30, fabs(gradi)));
-          const double x = fmin(rri, rrj);
-          double phi = (x > 0.0 ? 2.0/(1.0 + x)*2.0*x/(1.0 + x) : 0.0);
-          const double etaij = fmin(etaMagi, etaMagj);
-          if (etaij < etaCrit) { const double z = (etaij - etaCrit)/etaFold; phi *= exp(-z*z); }
+          // safeInvVar / van Leer with refined hardware reciprocals (|argument| >= 1e-30, so never denormal)
+          const double agj = fabs(gradj), agi = fabs(gradi);
+          const double rri = gradi*(d_sgn(gradj)*fast_rcp(agj > 1.0e-30 ? agj : 1.0e-30));
+          const double rrj = gradj*(d_sgn(gradi)*fast_rcp(agi > 1.0e-30 ? agi : 1.0e-30));
+          const double x = rri < rrj ? rri : rrj;
+          double phi = 0.0;
+          if (x > 0.0) { const double r1 = fast_rcp(1.0 + x); phi = 2.0*r1*2.0*x*r1; }
+          const double etaij = etaMagi < etaMagj ? etaMagi : etaMagj;
+          if (etaij < etaCrit) { const double z = (etaij - etaCrit)*rEtaFold; phi *= exp(-z*z); }
 #pragma unroll
           for (int q = 0; q < DIM; ++q) vijQ[q] = (vi[q] - phi*t1[q]) - (vj[q] + phi*t2[q]);
         }
@@ -514,7 +569,7 @@ __global__ void __launch_bounds__(32*CRK_WARPS) k_crk_derivs(CrkArgs a) {
     const double ej = -Clij*csj*(op.linearInExpansion ? muj : muj0) + Cqij*(op.quadraticInExpansion ? -d_sgn(muj)*muj*muj : muj0*muj0);
     const double Qi = rhoi*ei, Qj = rhoj*ej;                 // rho_i^2 QPiij = rho_i e_i = Qi (QPiij = e_i/rho_i)
     const double vdg = vdot<DIM>(vij, dg);
-    maxQ = fmax(maxQ, 4.0*Qi);                               // :354
+    { const double q4 = 4.0*Qi; maxQ = q4 > maxQ ? q4 : maxQ; }   // :354
     effQ = fma(volj*Qi, Wj, effQ);                           // :356
 
     // :362-368 velocity gradient
@@ -536,7 +591,7 @@ __global__ void __launch_bounds__(32*CRK_WARPS) k_crk_derivs(CrkArgs a) {
     if (compat) {
       // stored per directed edge as force/(mi mj): -mj*stored = -force/mi is the pair acceleration of the pair's i-node (:384),
       // mi*stored the (antisymmetric) one seen from its j-node -- the convention k_energy / k_emit_pacc use for SPH
-      const double ps = accsc/mj;
+      const double ps = accsc*fast_rcp(mj);
       double* const paccRow = paccTile + (size_t)k*(DIM*32);
 #pragma unroll
       for (int q = 0; q < DIM; ++q) paccRow[32*q] = ps*dg[q];
@@ -556,14 +611,14 @@ __global__ void __launch_bounds__(32*CRK_WARPS) k_crk_derivs(CrkArgs a) {
 #pragma unroll
       for (int q = 0; q < DIM; ++q) m1[q] = fma(-WSPHi, etai[q], m1[q]);
     }
-  }
+  });
 
-  if (!inRange) return;
+  if (!inRange) continue;
   const size_t cap = a.cap;
   auto put = [&](int slot, int comp, double v) { a.deriv[slot][(size_t)comp*cap + i] = v; };
   if (!active) {
     for (int s = 0; s < DV_COUNT; ++s) { const int w = sphb200_deriv_width(DIM, s); for (int q = 0; q < w; ++q) put(s, q, 0.0); }
-    return;
+    continue;
   }
   // :409-437
 #pragma unroll
@@ -606,6 +661,7 @@ __global__ void __launch_bounds__(32*CRK_WARPS) k_crk_derivs(CrkArgs a) {
 #pragma unroll
     for (int q = 0; q < NS; ++q) { put(DV_DHDT, q, dh[q]); put(DV_HIDEAL, q, 0.0); }
   }
+  }   // tile loop
 }
 
 double host_table_value(const TableDev& t, double eta, bool grad) {
@@ -622,7 +678,7 @@ int crk_common(sphb200_ctx* c, CrkArgs& a, const char* who) {
   if (!c->W.set) return sphb200_fail(c, std::string(who) + ": kernel table not set");
   a = CrkArgs{};
   a.rows = c->rows; a.aux2 = c->aux2; a.perm = c->perm; a.nbrCount = c->nbrCount; a.tileRows = c->tileRows; a.tileOff = c->tileOff; a.nbr = c->nbr;
-  a.volS = c->crkVolS; a.corrS = c->crkCorrS;
+  a.volS = c->crkVolS; a.corrS = c->crkCorrS; a.qrecS = c->crkQS;
   a.tabW = c->W.coef; a.kext = c->W.kext; a.xmin = c->W.xmin; a.xstep = c->W.xstep; a.n1 = c->W.n1;
   a.nperhVals = c->W.nperhVals; a.nperhN = c->W.nperhN; a.nperhXmin = c->W.nperhXmin; a.nperhXmax = c->W.nperhXmax; a.nperhXstep = c->W.nperhXstep;
   a.W0 = host_table_value(c->W, 0.0, false); a.gW0 = host_table_value(c->W, 0.0, true);
@@ -634,8 +690,6 @@ int crk_common(sphb200_ctx* c, CrkArgs& a, const char* who) {
   return 0;
 }
 
-size_t crk_shm(const sphb200_ctx* c) { return (size_t)6*(c->W.n1 + 2)*sizeof(double); }
-
 int gather(sphb200_ctx* c, int slot, int stride, double* out) {
   const int w = sphb200_state_width(c->ndim, slot);
   const size_t total = c->n*(size_t)stride;
@@ -643,14 +697,29 @@ int gather(sphb200_ctx* c, int slot, int stride, double* out) {
   KERNEL_CHECK(c, "k_gather_sorted");
   return 0;
 }
+// volume -> sorted copy + {det H, volume} records
+int gather_volume(sphb200_ctx* c) {
+  k_crk_volaux<<<(unsigned)((c->n + RB - 1)/RB), RB, 0, c->stream>>>(c->api[S_VOLUME], c->aux2, c->perm, c->n, c->crkVolS, c->crkAux);
+  KERNEL_CHECK(c, "k_crk_volaux");
+  return 0;
+}
 
-template <typename K> int launch_tiles(sphb200_ctx* c, K kern, const CrkArgs& a, const char* name) {
-  const size_t shm = crk_shm(c);
-  if (shm > 200*1024) return sphb200_fail(c, "kernel table too large for shared memory");
+// persistent launch: one CTA per SM, `warps` tiles in flight per CTA, ring of `ringWarpBytes` per warp behind the table
+template <typename K> int launch_tiles(sphb200_ctx* c, K kern, const CrkArgs& a, const char* name, int warps, size_t ringWarpBytes) {
+  const size_t shm = (size_t)6*(c->W.n1 + 2)*sizeof(double) + (size_t)warps*ringWarpBytes;
+  if (shm > 227*1024) return sphb200_fail(c, "kernel table too large for shared memory");
   CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-  kern<<<(unsigned)((c->nTiles + CRK_WARPS - 1)/CRK_WARPS), 32*CRK_WARPS, shm, c->stream>>>(a);
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+  int perSM = 1;                                     // resident CTAs per SM (registers + shared memory): the persistent grid fills them
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, 32*warps, shm) != cudaSuccess || perSM < 1) perSM = 1;
+  const unsigned nb = (unsigned)std::min<size_t>((c->nTiles + warps - 1)/warps, (size_t)nsm*perSM);
+  kern<<<nb, 32*warps, shm, c->stream>>>(a);
   KERNEL_CHECK(c, name);
   return 0;
+}
+template <int DIM, typename K> int launch_light(sphb200_ctx* c, K kern, const CrkArgs& a, const char* name) {
+  return launch_tiles(c, kern, a, name, LW, (size_t)LightRing<DIM>::WARPB);
 }
 
 }  // namespace
@@ -661,14 +730,21 @@ int sphb200_launch_crk_derivs(sphb200_ctx* c) {
   const bool needQ = (c->opt.Qkind == SPHB200_Q_LIMITED_MG) || c->opt.balsara;
   const bool mult = c->have[S_FCL] && c->have[S_FCQ];
   a.auxDvDxQ = needQ ? c->auxDvDxQ : nullptr; a.auxfCl = mult ? c->auxfCl : nullptr; a.auxfCq = mult ? c->auxfCq : nullptr;
-  if (gather(c, S_VOLUME, 1, c->crkVolS)) return 1;
+  if (gather_volume(c)) return 1;
   if (gather(c, S_RKCORR, c->ndim == 3 ? Ck<3>::CST : Ck<2>::CST, c->crkCorrS)) return 1;
+  {
+    const int nt = c->ndim*c->ndim, qst = c->ndim == 3 ? Ck<3>::QST : Ck<2>::QST;
+    const size_t total = c->n*(size_t)qst;
+    k_crk_qrec<<<(unsigned)((total + RB - 1)/RB), RB, 0, c->stream>>>(c->api[S_VOLUME], a.auxDvDxQ, nt, qst, c->perm, c->n, c->crkQS);
+    KERNEL_CHECK(c, "k_crk_qrec");
+  }
+  a.aux2 = c->crkAux;
   if (c->opt.compatibleEnergy && sphb200_ensure(c, c->pacc, c->paccCap, c->nSlots*(size_t)c->ndim)) return 1;
   a.pacc = c->pacc;
   if (c->opt.hEvolution == SPHB200_H_SPH && (!a.nperhVals || a.nperhN < 2))
     return sphb200_fail(c, "evaluateDerivatives: SPHSmoothingScale needs the TableKernel nperh lookup (nperhVals) but none was set");
-  if (c->ndim == 3) { if (launch_tiles(c, k_crk_derivs<3>, a, "k_crk_derivs")) return 1; }
-  else              { if (launch_tiles(c, k_crk_derivs<2>, a, "k_crk_derivs")) return 1; }
+  if (c->ndim == 3) { if (launch_tiles(c, k_crk_derivs<3>, a, "k_crk_derivs", CW, (size_t)DerivRing<3>::WARPB)) return 1; }
+  else              { if (launch_tiles(c, k_crk_derivs<2>, a, "k_crk_derivs", CW, (size_t)DerivRing<2>::WARPB)) return 1; }
   c->derivsValid = true;
   return 0;
 }
@@ -681,8 +757,8 @@ int sphb200_crk_compute_volume(sphb200_ctx* c) {
   CrkArgs a;
   if (crk_common(c, a, "crk_compute_volume")) return 1;
   if (c->n == 0) return 0;
-  if (c->ndim == 3) { if (launch_tiles(c, k_crk_volume<3>, a, "k_crk_volume")) return 1; }
-  else              { if (launch_tiles(c, k_crk_volume<2>, a, "k_crk_volume")) return 1; }
+  if (c->ndim == 3) { if (launch_tiles(c, k_crk_volume<3>, a, "k_crk_volume", LW, (size_t)PosRing<3>::WARPB)) return 1; }
+  else              { if (launch_tiles(c, k_crk_volume<2>, a, "k_crk_volume", LW, (size_t)PosRing<2>::WARPB)) return 1; }
   c->have[S_VOLUME] = true;
   return 0;
 }
@@ -694,9 +770,10 @@ int sphb200_crk_compute_corrections(sphb200_ctx* c) {
   if (crk_common(c, a, "crk_compute_corrections")) return 1;
   if (!c->have[S_VOLUME]) return sphb200_fail(c, "crk_compute_corrections: the volume is not on the device (call crk_compute_volume or upload it)");
   if (c->n == 0) return 0;
-  if (gather(c, S_VOLUME, 1, c->crkVolS)) return 1;
-  if (c->ndim == 3) { if (launch_tiles(c, k_crk_corrections<3>, a, "k_crk_corrections")) return 1; }
-  else              { if (launch_tiles(c, k_crk_corrections<2>, a, "k_crk_corrections")) return 1; }
+  if (gather_volume(c)) return 1;
+  a.aux2 = c->crkAux;
+  if (c->ndim == 3) { if (launch_light<3>(c, k_crk_corrections<3>, a, "k_crk_corrections")) return 1; }
+  else              { if (launch_light<2>(c, k_crk_corrections<2>, a, "k_crk_corrections")) return 1; }
   c->have[S_RKCORR] = true;
   return 0;
 }
@@ -709,10 +786,11 @@ int sphb200_crk_sum_mass_density(sphb200_ctx* c, double rhoMin, double rhoMax) {
   if (!c->have[S_VOLUME] || !c->have[S_MASS]) return sphb200_fail(c, "crk_sum_mass_density: volume and mass must be on the device");
   if (c->n == 0) return 0;
   if (!c->rowsValid && sphb200_pack_rows(c)) return 1;        // the rows carry the masses
-  if (gather(c, S_VOLUME, 1, c->crkVolS)) return 1;
+  if (gather_volume(c)) return 1;
+  a.aux2 = c->crkAux;
   a.rhoMin = rhoMin; a.rhoMax = rhoMax;
-  if (c->ndim == 3) { if (launch_tiles(c, k_crk_sum_density<3>, a, "k_crk_sum_density")) return 1; }
-  else              { if (launch_tiles(c, k_crk_sum_density<2>, a, "k_crk_sum_density")) return 1; }
+  if (c->ndim == 3) { if (launch_light<3>(c, k_crk_sum_density<3>, a, "k_crk_sum_density")) return 1; }
+  else              { if (launch_light<2>(c, k_crk_sum_density<2>, a, "k_crk_sum_density")) return 1; }
   c->have[S_RHO] = true;
   c->rowsValid = false;                                       // the rows carry rho as well
   return 0;

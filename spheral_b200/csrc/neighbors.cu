@@ -539,6 +539,7 @@ template int sphb200_ensure<uint32_t>(sphb200_ctx*, uint32_t*&, size_t&, size_t)
 template int sphb200_ensure<double>(sphb200_ctx*, double*&, size_t&, size_t);
 template int sphb200_ensure<float>(sphb200_ctx*, float*&, size_t&, size_t);
 template int sphb200_ensure<uint4>(sphb200_ctx*, uint4*&, size_t&, size_t);
+template int sphb200_ensure<unsigned long long>(sphb200_ctx*, unsigned long long*&, size_t&, size_t);
 
 static int build_grid(sphb200_ctx* c, const double* bb /*lo3 hi3 ext3*/) {
   GridDev& g = c->grid;

@@ -100,6 +100,8 @@ struct sphb200_ctx {
   double* auxfCl = nullptr; double* auxfCq = nullptr;
   double* crkVolS = nullptr;        // CRKSPH: volume per node (sorted)
   double* crkCorrS = nullptr;       // CRKSPH: (1+ndim)^2 RK coefficients per node (sorted, AoS)
+  double* crkQS = nullptr;          // CRKSPH: {volume, Q velocity gradient} per node (sorted, stride 10 / 6)
+  double* crkAux = nullptr;         // CRKSPH: {det H, volume} per node (sorted)
   bool rowsValid = false;           // rows reflect current api state for the current sort
   bool sortValid = false;
 
@@ -123,6 +125,16 @@ struct sphb200_ctx {
   double* deriv[DV_COUNT] = {nullptr};
   double* pacc = nullptr; size_t paccCap = 0;   // ndim * nSlots
   bool derivsValid = false;
+  // node-wise derivatives outlive the connectivity they were computed on (CheapSynchronousRK2 advances the next step's trial
+  // state with them after the neighbour update): the sorted order of the evaluation is kept beside them
+  uint32_t* permEval = nullptr; size_t permEvalCap = 0;
+  size_t nEval = 0, capEval = 0, nIntEval = 0;
+  bool derivNodeValid = false;
+  // state0 of the integrator (State::copyState, CheapSynchronousRK2.cc:70-71)
+  double* api0[S_COUNT] = {nullptr}; size_t cap0[S_COUNT] = {0}; bool have0[S_COUNT] = {false}; size_t n0 = 0;
+  // time-step reduction scratch
+  unsigned long long* dtCand = nullptr; size_t dtCandCap = 0;
+  double* dtAux = nullptr; size_t dtAuxCap = 0;
   double* stage = nullptr; size_t stageBytes = 0;   // download staging (device)
 
   // instrumentation

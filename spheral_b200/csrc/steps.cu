@@ -1,0 +1,622 @@
+// steps.cu -- the per-step callers either side of the derivative path, device-resident:
+//
+//   k_sph_sum_density   computeSPHSumMassDensity            SPH/computeSPHSumMassDensity.cc:15-89   (SPHBase::preStepInitialize)
+//   k_sph_omega         computeSPHOmegaGradhCorrection      SPH/computeSPHOmegaGradhCorrection.cc:20-113 (SPHBase::postStateUpdate)
+//   k_eos_gamma         PressurePolicy / SoundSpeedPolicy with GammaLawGas (Material/GammaLawGas.cc:185-189, 233-238)
+//   k_state_update      State::update with the policies the hydro and smoothing-scale packages register
+//                       (IncrementState, IncrementBoundedState, ReplaceBoundedState, IncrementASPHHtensor; DataBase/State.cc:221-300)
+//   k_dt_nodes/_pairs   GenericHydro::dt                    Physics/GenericHydro.cc:112-381
+//
+// so that no field leaves the GPU between the stages of CheapSynchronousRK2 (Integrator/CheapSynchronousRK2.cc:40-132): the
+// host integrator (spheral_b200/integrator.py) issues these calls and reads back one number per step, the time step.
+// The pair loops use the same i-centric gather and the same warp-cooperative record ring as the derivative kernels.
+#include "sphb200_internal.cuh"
+#include "pair_common.cuh"
+#include "nbr_ring.cuh"
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+constexpr int RB = 256;
+constexpr int SW = 8, SS = 4;                      // warps per CTA and ring depth of the light pair loops
+
+template <int DIM> struct StepPrefix { static constexpr int MASS = ((Dm<DIM>::R_M + 1)*8 + 15)/16*16;      // position .. mass
+                                       static constexpr int VEL = (2*DIM*8 + 15)/16*16; };                  // position, velocity
+template <int DIM> using MassRing = NbrRing<DIM, 0, 0, SS, StepPrefix<DIM>::MASS>;
+template <int DIM> using PosRing = NbrRing<DIM, 0, 0, SS, (DIM == 3 ? 32 : 16)>;
+template <int DIM> using VelRing = NbrRing<DIM, 0, 0, SS, StepPrefix<DIM>::VEL>;
+
+struct LoopArgs {
+  const double* rows; const double* aux2; const uint32_t* perm;
+  const uint32_t* nbrCount; const uint32_t* tileRows; const unsigned long long* tileOff; const uint32_t* nbr;
+  const double* tabW; double kext, xmin, xstep; uint32_t n1; double W0;
+  size_t n; uint32_t nInt;
+  double* out;                                       // api-order destination (rho / omega)
+  // dt
+  unsigned long long* best;                          // {dt bits, tag} pairs per CTA
+};
+
+struct TileLane { size_t i; bool inRange, active; uint32_t o, cnt, rowsT; unsigned long long base; };
+__device__ __forceinline__ TileLane tile_lane(const LoopArgs& a, size_t tile, int lane) {
+  TileLane t;
+  t.i = tile*SPHB200_TILE + lane;
+  t.inRange = t.i < a.n;
+  t.o = t.inRange ? a.perm[t.i] : 0xffffffffu;
+  t.active = t.inRange && t.o < a.nInt;
+  t.cnt = t.active ? a.nbrCount[t.i] : 0u;
+  t.rowsT = a.tileRows[tile];
+  t.base = a.tileOff[tile] + lane;
+  return t;
+}
+__device__ __forceinline__ unsigned stage_table(double* smem, const double* __restrict__ tab, uint32_t n1) {
+  const uint32_t nW = 6u*(n1 + 2u);
+  for (uint32_t k = threadIdx.x; k < nW; k += blockDim.x) smem[k] = (k < nW - 6u) ? tab[k] : 0.0;
+  __syncthreads();
+  return (unsigned)__cvta_generic_to_shared(smem);
+}
+template <typename Ring> __device__ __forceinline__ Ring make_ring(const LoopArgs& a, unsigned ringBase, int warp) {
+  Ring r;
+  r.base = ringBase + (unsigned)warp*(unsigned)Ring::WARPB;
+  r.rows = reinterpret_cast<const unsigned char*>(a.rows);
+  r.x1 = nullptr; r.x2 = nullptr;
+  r.aux2 = reinterpret_cast<const unsigned char*>(a.aux2);
+  return r;
+}
+
+// ---- computeSPHSumMassDensity: rho_i = m_i W(0) Hdet_i + sum_j m_j Hdet_j W(|Hj (ri - rj)|)  (scatter form: the neighbour's H) ----
+template <int DIM>
+__global__ void __launch_bounds__(32*SW, 1) k_sph_sum_density(LoopArgs a) {
+  using D = Dm<DIM>;
+  extern __shared__ __align__(16) double smem[];
+  const unsigned tW = stage_table(smem, a.tabW, a.n1);
+  const double rx = 1.0/a.xstep;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const MassRing<DIM> ring = make_ring<MassRing<DIM>>(a, tW + 48u*(a.n1 + 2u), warp);
+  const size_t nTiles = (a.n + SPHB200_TILE - 1)/SPHB200_TILE;
+  for (size_t tile = (size_t)blockIdx.x*SW + warp; tile < nTiles; tile += (size_t)gridDim.x*SW) {
+    const TileLane t = tile_lane(a, tile, lane);
+    double ri[DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) ri[k] = t.inRange ? a.rows[t.i*D::ROW + D::R_POS + k] : 0.0;
+    double sum = 0.0;
+    ring_walk<MassRing<DIM>, SS>(ring, lane, t.rowsT, t.cnt,
+      [&](uint32_t p) -> uint32_t { return (p < t.cnt) ? a.nbr[t.base + (unsigned long long)p*SPHB200_TILE] : 0u; },
+      [&](uint32_t k, uint32_t) {
+        double rw[StepPrefix<DIM>::MASS/8];
+        ring.read_row(k, lane, rw);
+        const double Hdetj = ring.read_aux(k, lane).x;
+        double rij[DIM], eta[DIM];
+#pragma unroll
+        for (int q = 0; q < DIM; ++q) rij[q] = ri[q] - rw[D::R_POS + q];
+        sym_dot<DIM>(rw + D::R_H, rij, eta);
+        const double e2 = vdot<DIM>(eta, eta);
+        double W, gW;
+        table_eval_raw(tW, a.kext, a.xmin, a.xstep, rx, a.n1, e2*fast_rsqrt(e2 + 1.0e-300), W, gW);
+        sum = fma(rw[D::R_M], W*Hdetj, sum);                 // :78  massDensity_i += mj*Wj
+      });
+    if (t.active) a.out[t.o] = sum + a.rows[t.i*D::ROW + D::R_M]*(a.W0*a.aux2[2*t.i]);      // :37-46 self contribution
+  }
+}
+
+// ---- computeSPHOmegaGradhCorrection: omega_i = max(1e-30, -sum_j eta_i gW_i / (nDim (sum_j W_i + Hdet_i W0))) -------------------
+template <int DIM>
+__global__ void __launch_bounds__(32*SW, 1) k_sph_omega(LoopArgs a) {
+  using D = Dm<DIM>;
+  extern __shared__ __align__(16) double smem[];
+  const unsigned tW = stage_table(smem, a.tabW, a.n1);
+  const double rx = 1.0/a.xstep;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const PosRing<DIM> ring = make_ring<PosRing<DIM>>(a, tW + 48u*(a.n1 + 2u), warp);
+  const size_t nTiles = (a.n + SPHB200_TILE - 1)/SPHB200_TILE;
+  for (size_t tile = (size_t)blockIdx.x*SW + warp; tile < nTiles; tile += (size_t)gridDim.x*SW) {
+    const TileLane t = tile_lane(a, tile, lane);
+    double ri[DIM], Hi[D::NS];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) ri[k] = t.inRange ? a.rows[t.i*D::ROW + D::R_POS + k] : 0.0;
+#pragma unroll
+    for (int k = 0; k < D::NS; ++k) Hi[k] = t.inRange ? a.rows[t.i*D::ROW + D::R_H + k] : 0.0;
+    double wsum = 0.0, gsum = 0.0;
+    ring_walk<PosRing<DIM>, SS>(ring, lane, t.rowsT, t.cnt,
+      [&](uint32_t p) -> uint32_t { return (p < t.cnt) ? a.nbr[t.base + (unsigned long long)p*SPHB200_TILE] : 0u; },
+      [&](uint32_t k, uint32_t) {
+        double rj[DIM == 3 ? 4 : 2];
+        ring.read_row(k, lane, rj);
+        double rij[DIM], eta[DIM];
+#pragma unroll
+        for (int q = 0; q < DIM; ++q) rij[q] = ri[q] - rj[q];
+        sym_dot<DIM>(Hi, rij, eta);
+        const double e2 = vdot<DIM>(eta, eta);
+        const double etaMag = e2*fast_rsqrt(e2 + 1.0e-300);
+        double W, gW;
+        table_eval_raw(tW, a.kext, a.xmin, a.xstep, rx, a.n1, etaMag, W, gW);
+        wsum += W; gsum = fma(etaMag, gW, gsum);             // :85-89, Hdet_i factored out of both sums
+      });
+    if (t.active) {
+      double om = 1.0;                                       // :99-100 isolated point
+      if (t.cnt != 0u) {
+        const double Hdeti = sym_det<DIM>(Hi);
+        const double o1 = wsum*Hdeti + Hdeti*a.W0;           // :103-106
+        om = fmax(1.0e-30, -(gsum*Hdeti)/((double)DIM*o1));
+      }
+      a.out[t.o] = om;
+    }
+  }
+}
+
+// ---- GammaLawGas behind PressurePolicy / SoundSpeedPolicy: every node of the Field (ghosts included) ------------------------------
+__global__ void __launch_bounds__(RB) k_eos_gamma(const double* __restrict__ rho, const double* __restrict__ eps, size_t n,
+                                                  sphb200_gamma_law e, double* __restrict__ P, double* __restrict__ cs) {
+  const size_t i = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (i >= n) return;
+  const double g1 = e.gamma - 1.0;
+  double p = g1*rho[i]*eps[i] - e.externalPressure;                                         // GammaLawGas.cc:188, EquationOfStateInline.hh:98-106
+  p = (p < e.minimumPressure ? (e.minPressureType == 0 ? e.minimumPressure : 0.0) : (p > e.maximumPressure ? e.maximumPressure : p));
+  P[i] = p;
+  cs[i] = sqrt(fmax(0.0, e.gamma*g1*eps[i]));                                               // GammaLawGas.cc:237
+}
+
+// ---- symmetric eigen-decomposition (the role of GeomSymmetricTensor::eigenVectors, GeomSymmetricTensorInline.hh:2279-2364) -------
+// 2-D: the reference's closed form.  3-D: the reference calls Eigen::SelfAdjointEigenSolver; every use here rebuilds
+// R diag(f(lambda)) R^T, which is independent of eigenvector sign / order / degenerate-subspace basis, so cyclic Jacobi is used.
+template <int DIM> __device__ void sym_eigen(const double* H, double* lam, double* V) {
+  if (DIM == 2) {
+    const double fscale = fmax(10.0*DBL_EPSILON, fmax(fabs(H[0]), fmax(fabs(H[1]), fabs(H[2]))));
+    const double fi = 1.0/fscale;
+    const double axx = H[0]*fi, axy = H[1]*fi, ayy = H[2]*fi;
+    if (fabs(axy) < 1.0e-50) { lam[0] = H[0]; lam[1] = H[2]; V[0] = 1; V[1] = 0; V[2] = 0; V[3] = 1; return; }
+    const double theta = 0.5*atan2(2.0*axy, ayy - axx);
+    const double xh = cos(theta), yh = sin(theta);
+    lam[0] = (xh*(axx*xh - axy*yh) - yh*(axy*xh - ayy*yh))*fscale;
+    lam[1] = (yh*(axx*yh + axy*xh) + xh*(axy*yh + ayy*xh))*fscale;
+    V[0] = xh; V[1] = yh; V[2] = -yh; V[3] = xh;
+  } else {
+    double A[3][3] = {{H[0], H[1], H[2]}, {H[1], H[3], H[4]}, {H[2], H[4], H[5]}};
+    double R[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 30; ++sweep) {
+      const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+      const double diag = fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]);
+      if (off <= 1.0e-300 || off <= 1.0e-18*diag) break;
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int q = p + 1; q < 3; ++q) {
+          if (A[p][q] == 0.0) continue;
+          const double th = (A[q][q] - A[p][p])/(2.0*A[p][q]);
+          const double tt = d_sgn(th)/(fabs(th) + sqrt(th*th + 1.0));
+          const double cc = 1.0/sqrt(tt*tt + 1.0), ss = tt*cc;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = cc*akp - ss*akq; A[k][q] = ss*akp + cc*akq; }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = cc*apk - ss*aqk; A[q][k] = ss*apk + cc*aqk; }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { const double rkp = R[k][p], rkq = R[k][q]; R[k][p] = cc*rkp - ss*rkq; R[k][q] = ss*rkp + cc*rkq; }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { lam[k] = A[k][k];
+#pragma unroll
+      for (int l = 0; l < 3; ++l) V[3*k + l] = R[k][l]; }
+  }
+}
+template <int DIM> __device__ void sym_rebuild(const double* lam, const double* V, double* H) {
+  double F[DIM][DIM];
+#pragma unroll
+  for (int r = 0; r < DIM; ++r)
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) s += V[DIM*r + k]*lam[k]*V[DIM*c + k];
+      F[r][c] = s;
+    }
+  if (DIM == 3) { H[0] = F[0][0]; H[1] = 0.5*(F[0][1] + F[1][0]); H[2] = 0.5*(F[0][2] + F[2][0]); H[3] = F[1][1]; H[4] = 0.5*(F[1][2] + F[2][1]); H[5] = F[2][2]; }
+  else { H[0] = F[0][0]; H[1] = 0.5*(F[0][1] + F[1][0]); H[2] = F[1][1]; }
+}
+// min(maxv, max(minv, H)): enforceMinEigenValue then enforceMaxEigenValue (GeomSymmetricTensorInline.hh:2554-2640): H is returned
+// untouched unless an eigenvalue is out of bounds
+template <int DIM> __device__ void sym_bound(double* H, double minv, double maxv) {
+  double lam[DIM], V[DIM*DIM];
+  sym_eigen<DIM>(H, lam, V);
+  double lo = lam[0], hi = lam[0];
+#pragma unroll
+  for (int k = 1; k < DIM; ++k) { lo = fmin(lo, lam[k]); hi = fmax(hi, lam[k]); }
+  if (lo < minv) {
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) lam[k] = fmax(lam[k], minv);
+    sym_rebuild<DIM>(lam, V, H);
+    sym_eigen<DIM>(H, lam, V);
+    hi = lam[0];
+#pragma unroll
+    for (int k = 1; k < DIM; ++k) hi = fmax(hi, lam[k]);
+  }
+  if (hi > maxv) {
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) lam[k] = fmin(lam[k], maxv);
+    sym_rebuild<DIM>(lam, V, H);
+  }
+}
+// GeomSymmetricTensor::eigenValues().maxElement() (GeomSymmetricTensorInline.hh:2210-2256): the closed form GenericHydro::dt uses
+template <int DIM> __device__ double sym_max_eigenvalue(const double* H) {
+  if (DIM == 2) {
+    if (fabs(H[1]) < 1.0e-50) return fmax(H[0], H[2]);
+    const double b = H[0] + H[2], c = H[0]*H[2] - H[1]*H[1];
+    const double q = 0.5*(b + d_sgn(b)*sqrt(fmax(0.0, b*b - 4.0*c)));
+    return fmax(q, c/q);
+  }
+  const double fscale = fmax(10.0*DBL_EPSILON, fmax(fmax(fabs(H[0]), fabs(H[1])), fmax(fmax(fabs(H[2]), fabs(H[3])), fmax(fabs(H[4]), fabs(H[5])))));
+  const double fi = 1.0/fscale;
+  const double a00 = H[0]*fi, a01 = H[1]*fi, a02 = H[2]*fi, a11 = H[3]*fi, a12 = H[4]*fi, a22 = H[5]*fi;
+  const double c0 = a00*a11*a22 + 2.0*a01*a02*a12 - a00*a12*a12 - a11*a02*a02 - a22*a01*a01;
+  const double c1 = a00*a11 - a01*a01 + a00*a22 - a02*a02 + a11*a22 - a12*a12;
+  const double c2 = a00 + a11 + a22;
+  const double third = 1.0/3.0;
+  const double c2Div3 = c2*third;
+  const double aDiv3 = fmin(0.0, third*(c1 - c2*c2Div3));
+  const double mbDiv2 = 0.5*(c0 + c2Div3*(2.0*c2Div3*c2Div3 - c1));
+  const double q = fmin(0.0, mbDiv2*mbDiv2 + aDiv3*aDiv3*aDiv3);
+  const double mag = sqrt(-aDiv3);
+  const double angle = atan2(sqrt(-q), mbDiv2)*third;
+  const double cs = cos(angle), sn = sin(angle), s3 = sqrt(3.0);
+  return fmax(fscale*(c2Div3 + 2.0*mag*cs), fmax(fscale*(c2Div3 - mag*(cs + s3*sn)), fscale*(c2Div3 - mag*(cs - s3*sn))));
+}
+
+// ---- State::update over the internal nodes ------------------------------------------------------------------------------------------
+struct UpdateArgs {
+  const uint32_t* permEval; size_t nEval, capEval; uint32_t nInt;
+  const double* deriv[DV_COUNT];
+  double *pos, *vel, *H, *rho, *eps;
+  double multiplier; int timeAdvanceOnly, epsDone;
+  int hEvolution /*SPHB200_H_**/, HEvolution /*0 ideal 1 integrate 2 fixed*/;
+  double rhoMin, rhoMax, hminInv, hmaxInv, hminratio;
+};
+template <int DIM>
+__global__ void __launch_bounds__(RB) k_state_update(UpdateArgs a) {
+  constexpr int NS = Dm<DIM>::NS;
+  const size_t s = (size_t)blockIdx.x*RB + threadIdx.x;        // sorted slot of the evaluation the derivatives came from
+  if (s >= a.nEval) return;
+  const size_t o = a.permEval[s];
+  if (o >= a.nInt) return;
+  const size_t cap = a.capEval;
+  const double mult = a.multiplier;
+  a.rho[o] = fmin(a.rhoMax, fmax(a.rhoMin, a.rho[o] + mult*a.deriv[DV_DRHODT][s]));        // IncrementBoundedStateInline.hh:69
+  if (!a.epsDone) a.eps[o] += mult*a.deriv[DV_DEPSDT][s];                                  // IncrementStateInline.hh:69
+#pragma unroll
+  for (int q = 0; q < DIM; ++q) {
+    a.pos[o*DIM + q] += mult*a.deriv[DV_DXDT][(size_t)q*cap + s];
+    a.vel[o*DIM + q] += mult*a.deriv[DV_DVDT][(size_t)q*cap + s];
+  }
+  if (a.HEvolution == 2 || a.hEvolution == SPHB200_H_NONE) return;                         // FixedH
+  double Hi[NS];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) Hi[q] = a.H[o*NS + q];
+  if (a.hEvolution == SPHB200_H_ASPH) {                                                    // IncrementASPHHtensor.cc:82-88
+#pragma unroll
+    for (int q = 0; q < NS; ++q) Hi[q] += mult*a.deriv[DV_DHDT][(size_t)q*cap + s];
+    double lam[DIM], V[DIM*DIM];
+    sym_eigen<DIM>(Hi, lam, V);
+    double lo = lam[0];
+#pragma unroll
+    for (int k = 1; k < DIM; ++k) lo = fmin(lo, lam[k]);
+    const double hminEffInv = fmin(a.hminInv, fmax(a.hmaxInv, lo)/a.hminratio);
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) lam[k] = fmax(a.hmaxInv, fmin(hminEffInv, lam[k]));
+    sym_rebuild<DIM>(lam, V, Hi);
+  } else if (a.HEvolution == 1 || a.timeAdvanceOnly) {                                      // IntegrateH, or IdealH degraded to an increment
+#pragma unroll
+    for (int q = 0; q < NS; ++q) Hi[q] += mult*a.deriv[DV_DHDT][(size_t)q*cap + s];
+    sym_bound<DIM>(Hi, a.hmaxInv, a.hminInv);
+  } else {                                                                                  // IdealH: ReplaceBoundedState("new H")
+#pragma unroll
+    for (int q = 0; q < NS; ++q) Hi[q] = a.deriv[DV_HIDEAL][(size_t)q*cap + s];
+    sym_bound<DIM>(Hi, a.hmaxInv, a.hminInv);
+  }
+#pragma unroll
+  for (int q = 0; q < NS; ++q) a.H[o*NS + q] = Hi[q];
+}
+
+// ---- GenericHydro::dt ------------------------------------------------------------------------------------------------------------------
+// A candidate is {dt, tag}; tag = phase<<40 | node<<3 | reason orders equal dt values the way the reference meets them (nodes in
+// index order with the checks in source order, then the pair loop), so the reported reason / node match the reference's.
+__device__ __forceinline__ void dt_take(double& best, unsigned long long& tag, double v, unsigned long long t) {
+  if (v < best || (v == best && t < tag)) { best = v; tag = t; }
+}
+__device__ __forceinline__ void dt_block_reduce(double best, unsigned long long tag, unsigned long long* out) {
+  __shared__ double sb[32]; __shared__ unsigned long long st[32];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double ob = __shfl_down_sync(0xffffffffu, best, off);
+    const unsigned long long ot = __shfl_down_sync(0xffffffffu, tag, off);
+    dt_take(best, tag, ob, ot);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sb[warp] = best; st[warp] = tag; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    best = lane < nw ? sb[lane] : DBL_MAX; tag = lane < nw ? st[lane] : ~0ull;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ob = __shfl_down_sync(0xffffffffu, best, off);
+      const unsigned long long ot = __shfl_down_sync(0xffffffffu, tag, off);
+      dt_take(best, tag, ob, ot);
+    }
+    if (lane == 0) { out[2*blockIdx.x] = (unsigned long long)__double_as_longlong(best); out[2*blockIdx.x + 1] = tag; }
+  }
+}
+struct DtNodeArgs {
+  const uint32_t* permEval; size_t nEval, capEval; uint32_t nInt;
+  const double *vel, *H, *rho, *cs;                  // api order
+  const double *maxQ, *DvDx, *DvDt;                  // sorted (evaluation order)
+  double nPerh; int useVelMag;
+  unsigned long long* best;
+};
+template <int DIM>
+__global__ void __launch_bounds__(RB) k_dt_nodes(DtNodeArgs a) {
+  constexpr int NS = Dm<DIM>::NS, NT = Dm<DIM>::NT;
+  const double tiny = DBL_EPSILON;
+  double best = DBL_MAX; unsigned long long tag = ~0ull;
+  for (size_t s = (size_t)blockIdx.x*RB + threadIdx.x; s < a.nEval; s += (size_t)gridDim.x*RB) {
+    const size_t o = a.permEval[s];
+    if (o >= a.nInt) continue;
+    double Hi[NS], v[DIM], acc[DIM];
+#pragma unroll
+    for (int q = 0; q < NS; ++q) Hi[q] = a.H[o*NS + q];
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) { v[q] = a.vel[o*DIM + q]; acc[q] = a.DvDt[(size_t)q*a.capEval + s]; }
+    const double nodeScale = 1.0/sym_max_eigenvalue<DIM>(Hi)/a.nPerh;                               // :190
+    const unsigned long long base = (unsigned long long)o << 3;
+    dt_take(best, tag, nodeScale/(a.cs[o] + tiny), base | 0ull);                                       // :197 sound speed
+    dt_take(best, tag, nodeScale/(sqrt(a.maxQ[s]/a.rho[o]) + tiny), base | 1ull);                      // :253 artificial viscosity
+    double div = 0.0;
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) div += a.DvDx[(size_t)(q*DIM + q)*a.capEval + s];
+    dt_take(best, tag, 1.0/(fabs(div) + tiny), base | 2ull);                                           // :272 velocity divergence
+    const double vmag = sqrt(vdot<DIM>(v, v)), amag = sqrt(vdot<DIM>(acc, acc));
+    dt_take(best, tag, 0.1*fmax(nodeScale/(vmag + tiny), vmag/(amag + tiny)), base | 3ull);            // :288 total acceleration
+    if (a.useVelMag) dt_take(best, tag, nodeScale/(vmag + 1.0e-10), base | 4ull);                      // :305 velocity magnitude
+    (void)NT;
+  }
+  dt_block_reduce(best, tag, a.best);
+}
+// per sorted node: {nodeScale, 0} for the pair loop (one closed-form eigenvalue per node instead of one per edge)
+template <int DIM>
+__global__ void __launch_bounds__(RB) k_node_scale(const double* __restrict__ rows, size_t n, double nPerh, double* __restrict__ out) {
+  const size_t s = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (s >= n) return;
+  double Hi[Dm<DIM>::NS];
+#pragma unroll
+  for (int q = 0; q < Dm<DIM>::NS; ++q) Hi[q] = rows[s*Dm<DIM>::ROW + Dm<DIM>::R_H + q];
+  out[2*s] = 1.0/sym_max_eigenvalue<DIM>(Hi)/nPerh;
+  out[2*s + 1] = 0.0;
+}
+// :320-346 pairwise velocity difference limit: min over pairs of min(scale_i, scale_j)/|v_i - v_j|
+template <int DIM>
+__global__ void __launch_bounds__(32*SW, 1) k_dt_pairs(LoopArgs a) {
+  using D = Dm<DIM>;
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const VelRing<DIM> ring = make_ring<VelRing<DIM>>(a, (unsigned)__cvta_generic_to_shared(smem), warp);   // aux2 = {nodeScale, 0}
+  const size_t nTiles = (a.n + SPHB200_TILE - 1)/SPHB200_TILE;
+  const double tiny = DBL_EPSILON;
+  double best = DBL_MAX; unsigned long long tag = ~0ull;
+  for (size_t tile = (size_t)blockIdx.x*SW + warp; tile < nTiles; tile += (size_t)gridDim.x*SW) {
+    const TileLane t = tile_lane(a, tile, lane);
+    double vi[DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) vi[k] = t.inRange ? a.rows[t.i*D::ROW + D::R_VEL + k] : 0.0;
+    const double si = t.inRange ? a.aux2[2*t.i] : 0.0;
+    ring_walk<VelRing<DIM>, SS>(ring, lane, t.rowsT, t.cnt,
+      [&](uint32_t p) -> uint32_t { return (p < t.cnt) ? a.nbr[t.base + (unsigned long long)p*SPHB200_TILE] : 0u; },
+      [&](uint32_t k, uint32_t j) {
+        double rw[StepPrefix<DIM>::VEL/8];
+        ring.read_row(k, lane, rw);
+        const double sj = ring.read_aux(k, lane).x;
+        double vij[DIM];
+#pragma unroll
+        for (int q = 0; q < DIM; ++q) vij[q] = vi[q] - rw[D::R_VEL + q];
+        const double vm = sqrt(vdot<DIM>(vij, vij));
+        const double dtv = fmin(si, sj)*(1.0/fmax(tiny, vm));                                   // safeInvVar(|vij|, tiny)
+        const uint32_t oj = a.perm[j];
+        const unsigned long long node = t.o < oj ? t.o : oj;                                   // the pair's i_node
+        dt_take(best, tag, dtv, (1ull << 40) | (node << 3) | 5ull);
+      });
+  }
+  dt_block_reduce(best, tag, a.best);
+}
+__global__ void __launch_bounds__(RB) k_dt_final(const unsigned long long* __restrict__ cand, int n, unsigned long long* __restrict__ out) {
+  double best = DBL_MAX; unsigned long long tag = ~0ull;
+  for (int k = threadIdx.x; k < n; k += RB) dt_take(best, tag, __longlong_as_double((long long)cand[2*k]), cand[2*k + 1]);
+  dt_block_reduce(best, tag, out);
+}
+
+void fill_loop_args(sphb200_ctx* c, LoopArgs& a) {
+  a = LoopArgs{};
+  a.rows = c->rows; a.aux2 = c->aux2; a.perm = c->perm; a.nbrCount = c->nbrCount; a.tileRows = c->tileRows; a.tileOff = c->tileOff; a.nbr = c->nbr;
+  a.tabW = c->W.coef; a.kext = c->W.kext; a.xmin = c->W.xmin; a.xstep = c->W.xstep; a.n1 = c->W.n1;
+  a.n = c->n; a.nInt = (uint32_t)c->nInt;
+}
+double table_W0(const TableDev& t) { return t.hostW.empty() ? 0.0 : t.hostW[0]; }     // W(0) = a0 of the first interval
+
+template <typename K> int launch_loop(sphb200_ctx* c, K kern, const LoopArgs& a, const char* name, size_t ringWarpBytes, bool withTable,
+                                      unsigned* grid = nullptr) {
+  const size_t shm = (withTable ? (size_t)6*(c->W.n1 + 2)*sizeof(double) : 0) + (size_t)SW*ringWarpBytes;
+  if (shm > 227*1024) return sphb200_fail(c, "kernel table too large for shared memory");
+  CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+  int nsm = 148, perSM = 1;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, 32*SW, shm) != cudaSuccess || perSM < 1) perSM = 1;
+  const unsigned nb = (unsigned)std::min<size_t>((c->nTiles + SW - 1)/SW, (size_t)nsm*perSM);
+  kern<<<nb, 32*SW, shm, c->stream>>>(a);
+  KERNEL_CHECK(c, name);
+  if (grid) *grid = nb;
+  return 0;
+}
+int loop_ready(sphb200_ctx* c, const char* who) {
+  if (!c->pairsValid) return sphb200_fail(c, std::string(who) + ": connectivity is stale or missing (call build_pairs first)");
+  if (!c->W.set) return sphb200_fail(c, std::string(who) + ": kernel table not set");
+  if (!c->rowsValid && sphb200_pack_rows(c)) return 1;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sphb200_sum_mass_density(sphb200_ctx* c) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (!c->have[S_MASS]) return sphb200_fail(c, "sum_mass_density: the mass is not on the device");
+  if (c->n == 0) return 0;
+  if (loop_ready(c, "sum_mass_density")) return 1;
+  LoopArgs a; fill_loop_args(c, a);
+  a.W0 = table_W0(c->W); a.out = c->api[S_RHO];
+  if (c->ndim == 3) { if (launch_loop(c, k_sph_sum_density<3>, a, "k_sph_sum_density", MassRing<3>::WARPB, true)) return 1; }
+  else              { if (launch_loop(c, k_sph_sum_density<2>, a, "k_sph_sum_density", MassRing<2>::WARPB, true)) return 1; }
+  c->have[S_RHO] = true;
+  c->rowsValid = false;                              // the rows carry rho and P/rho^2
+  return 0;
+}
+
+int sphb200_compute_omega_gradh(sphb200_ctx* c) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (c->n == 0) return 0;
+  if (loop_ready(c, "compute_omega_gradh")) return 1;
+  LoopArgs a; fill_loop_args(c, a);
+  a.W0 = table_W0(c->W); a.out = c->api[S_OMEGA];
+  if (!c->have[S_OMEGA]) {                           // ghost entries default to 1 (SPHBase.cc:210 resizes the field with 1.0)
+    std::vector<double> ones(c->n, 1.0);
+    CU_CHECK(c, cudaMemcpyAsync(c->api[S_OMEGA], ones.data(), c->n*sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  }
+  if (c->ndim == 3) { if (launch_loop(c, k_sph_omega<3>, a, "k_sph_omega", PosRing<3>::WARPB, true)) return 1; }
+  else              { if (launch_loop(c, k_sph_omega<2>, a, "k_sph_omega", PosRing<2>::WARPB, true)) return 1; }
+  c->have[S_OMEGA] = true;
+  c->rowsValid = false;                              // P/rho^2 in the rows carries 1/omega
+  return 0;
+}
+
+int sphb200_update_eos_gamma_law(sphb200_ctx* c, const sphb200_gamma_law* e) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  if (!e) return sphb200_fail(c, "update_eos_gamma_law: null equation of state");
+  if (!(e->gamma > 1.0)) return sphb200_fail(c, "update_eos_gamma_law: gamma must exceed 1");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (!c->have[S_RHO] || !c->have[S_EPS]) return sphb200_fail(c, "update_eos_gamma_law: mass density and specific thermal energy must be on the device");
+  if (c->n == 0) return 0;
+  k_eos_gamma<<<(unsigned)((c->n + RB - 1)/RB), RB, 0, c->stream>>>(c->api[S_RHO], c->api[S_EPS], c->n, *e, c->api[S_P], c->api[S_CS]);
+  KERNEL_CHECK(c, "k_eos_gamma");
+  c->have[S_P] = c->have[S_CS] = true;
+  c->rowsValid = false;
+  return 0;
+}
+
+int sphb200_state_update(sphb200_ctx* c, const sphb200_step_options* so, double multiplier, int timeAdvanceOnly) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  if (!so) return sphb200_fail(c, "state_update: null options");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (!c->derivNodeValid) return sphb200_fail(c, "state_update: no derivatives on the device (call evaluate_derivatives first)");
+  if (c->nIntEval != c->nInt) return sphb200_fail(c, "state_update: the internal node count changed since the derivatives were evaluated");
+  for (int s : {S_POS, S_VEL, S_H, S_RHO, S_EPS})
+    if (!c->have[s]) return sphb200_fail(c, "state_update: position, velocity, H, mass density and specific thermal energy must be on the device");
+  if (c->nInt == 0) return 0;
+  int epsDone = 0;
+  if (c->opt.compatibleEnergy && !timeAdvanceOnly) {
+    // SpecificThermalEnergyPolicy fires before velocity and position (they declare it as a dependency, SPHBase.cc:237-245)
+    if (sphb200_update_energy_compatible(c, multiplier)) return 1;
+    epsDone = 1;
+  }
+  UpdateArgs a{};
+  a.permEval = c->permEval; a.nEval = c->nEval; a.capEval = c->capEval; a.nInt = (uint32_t)c->nInt;
+  for (int s = 0; s < DV_COUNT; ++s) a.deriv[s] = c->deriv[s];
+  a.pos = c->api[S_POS]; a.vel = c->api[S_VEL]; a.H = c->api[S_H]; a.rho = c->api[S_RHO]; a.eps = c->api[S_EPS];
+  a.multiplier = multiplier; a.timeAdvanceOnly = timeAdvanceOnly; a.epsDone = epsDone;
+  a.hEvolution = c->opt.hEvolution; a.HEvolution = so->HEvolution;
+  a.rhoMin = so->rhoMin; a.rhoMax = so->rhoMax; a.hminInv = 1.0/c->opt.hmin; a.hmaxInv = 1.0/c->opt.hmax; a.hminratio = so->hminratio;
+  const unsigned nb = (unsigned)((c->nEval + RB - 1)/RB);
+  if (c->ndim == 3) k_state_update<3><<<nb, RB, 0, c->stream>>>(a); else k_state_update<2><<<nb, RB, 0, c->stream>>>(a);
+  KERNEL_CHECK(c, "k_state_update");
+  // positions and H moved: the rows are stale.  The connectivity is deliberately kept -- the reference evaluates the mid-step
+  // derivatives on the connectivity of the step start (CheapSynchronousRK2.cc:76-90) -- and the next build_pairs re-sorts anyway.
+  c->rowsValid = false;
+  return sphb200_update_eos_gamma_law(c, &so->eos);
+}
+
+int sphb200_state_copy(sphb200_ctx* c) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  for (int s = 0; s < S_COUNT; ++s) {
+    if (!c->have[s] || !c->api[s]) { c->have0[s] = false; continue; }
+    const size_t bytes = c->cap*(size_t)sphb200_state_width(c->ndim, s)*sizeof(double);
+    if (c->cap0[s] < c->cap) {
+      if (c->api0[s]) cudaFree(c->api0[s]);
+      c->api0[s] = nullptr; c->cap0[s] = 0;
+      CU_CHECK(c, cudaMalloc((void**)&c->api0[s], bytes));
+      c->cap0[s] = c->cap;
+    }
+    CU_CHECK(c, cudaMemcpyAsync(c->api0[s], c->api[s], c->n*(size_t)sphb200_state_width(c->ndim, s)*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    c->have0[s] = true;
+  }
+  c->n0 = c->n;
+  return 0;
+}
+
+int sphb200_state_assign(sphb200_ctx* c) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (c->n0 != c->n) return sphb200_fail(c, "state_assign: the node count changed since state_copy");
+  for (int s = 0; s < S_COUNT; ++s) {
+    if (!c->have0[s]) continue;
+    CU_CHECK(c, cudaMemcpyAsync(c->api[s], c->api0[s], c->n*(size_t)sphb200_state_width(c->ndim, s)*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  c->rowsValid = false;
+  return 0;
+}
+
+int sphb200_compute_dt(sphb200_ctx* c, double cfl, int useVelocityMagnitudeForDt, double* dt, int* reason, uint32_t* node) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (!c->derivNodeValid) return sphb200_fail(c, "compute_dt: no derivatives on the device (call evaluate_derivatives first)");
+  if (c->nIntEval != c->nInt) return sphb200_fail(c, "compute_dt: the internal node count changed since the derivatives were evaluated");
+  for (int s : {S_VEL, S_H, S_RHO, S_CS})
+    if (!c->have[s]) return sphb200_fail(c, "compute_dt: velocity, H, mass density and sound speed must be on the device");
+  if (c->nInt == 0) { if (dt) *dt = DBL_MAX; if (reason) *reason = -1; if (node) *node = 0; return 0; }
+  if (loop_ready(c, "compute_dt")) return 1;
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+  const int nbNodes = (int)std::min<size_t>((c->nEval + RB - 1)/RB, (size_t)nsm*4);
+  const size_t maxCand = (size_t)nbNodes + (size_t)nsm*8;
+  if (sphb200_ensure(c, c->dtCand, c->dtCandCap, 2*maxCand + 2)) return 1;
+  if (sphb200_ensure(c, c->dtAux, c->dtAuxCap, 2*c->cap)) return 1;
+  DtNodeArgs na{};
+  na.permEval = c->permEval; na.nEval = c->nEval; na.capEval = c->capEval; na.nInt = (uint32_t)c->nInt;
+  na.vel = c->api[S_VEL]; na.H = c->api[S_H]; na.rho = c->api[S_RHO]; na.cs = c->api[S_CS];
+  na.maxQ = c->deriv[DV_MAXQ]; na.DvDx = c->deriv[DV_DVDX]; na.DvDt = c->deriv[DV_DVDT];
+  na.nPerh = c->opt.nPerh; na.useVelMag = useVelocityMagnitudeForDt; na.best = c->dtCand;
+  if (c->ndim == 3) k_dt_nodes<3><<<nbNodes, RB, 0, c->stream>>>(na); else k_dt_nodes<2><<<nbNodes, RB, 0, c->stream>>>(na);
+  KERNEL_CHECK(c, "k_dt_nodes");
+  { const unsigned nb = (unsigned)((c->n + RB - 1)/RB);
+    if (c->ndim == 3) k_node_scale<3><<<nb, RB, 0, c->stream>>>(c->rows, c->n, c->opt.nPerh, c->dtAux);
+    else              k_node_scale<2><<<nb, RB, 0, c->stream>>>(c->rows, c->n, c->opt.nPerh, c->dtAux);
+    KERNEL_CHECK(c, "k_node_scale"); }
+  LoopArgs a; fill_loop_args(c, a);
+  a.aux2 = c->dtAux; a.best = c->dtCand + 2*(size_t)nbNodes;
+  unsigned nbPairs = 0;
+  if (c->ndim == 3) { if (launch_loop(c, k_dt_pairs<3>, a, "k_dt_pairs", VelRing<3>::WARPB, false, &nbPairs)) return 1; }
+  else              { if (launch_loop(c, k_dt_pairs<2>, a, "k_dt_pairs", VelRing<2>::WARPB, false, &nbPairs)) return 1; }
+  if ((size_t)nbNodes + nbPairs > maxCand) return sphb200_fail(c, "compute_dt: internal candidate buffer too small");
+  k_dt_final<<<1, RB, 0, c->stream>>>(c->dtCand, nbNodes + (int)nbPairs, c->dtCand + 2*maxCand);
+  KERNEL_CHECK(c, "k_dt_final");
+  unsigned long long res[2];
+  CU_CHECK(c, cudaMemcpyAsync(res, c->dtCand + 2*maxCand, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  double best; memcpy(&best, &res[0], 8);
+  if (dt) *dt = best*cfl;                                                                   // :378 scale by the cfl safety factor
+  if (reason) *reason = (res[1] == ~0ull) ? -1 : (int)(res[1] & 7ull);
+  if (node) *node = (res[1] == ~0ull) ? 0u : (uint32_t)((res[1] >> 3) & 0xffffffffull);
+  return 0;
+}
+
+}  // extern "C"

@@ -31,6 +31,23 @@ def make_options(ndim, **kw):
     return o
 
 
+def make_step_options(**kw):
+    """GammaLawGas(5/3) without pressure limits, the FluidNodeList defaults rhoMin/rhoMax = 1e-10/1e10 and hminratio = 0.1,
+    IdealH (NodeList/FluidNodeList.hh, NodeList/NodeList.hh, SmoothingScale/SmoothingScaleBase.hh)."""
+    so = L.StepOptions()
+    so.eos.gamma = 5.0/3.0
+    so.eos.minimumPressure, so.eos.maximumPressure, so.eos.externalPressure, so.eos.minPressureType = -1.0e200, 1.0e200, 0.0, 0
+    so.rhoMin, so.rhoMax, so.hminratio, so.HEvolution = 1.0e-10, 1.0e10, 0.1, L.HEVOLUTION_IDEALH
+    for k, v in kw.items():
+        if hasattr(so.eos, k):
+            setattr(so.eos, k, v)
+        elif hasattr(so, k):
+            setattr(so, k, v)
+        else:
+            raise KeyError(k)
+    return so
+
+
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
@@ -197,6 +214,36 @@ class Engine:
     def crk_sum_mass_density(self, rhoMin=0.0, rhoMax=1.0e300):
         """computeCRKSPHSumMassDensity -> internal entries of 'massDensity' on the device."""
         self._check(self._lib.sphb200_crk_sum_mass_density(self._h, rhoMin, rhoMax))
+
+    # -- per-step callers, device-resident (SURVEY 8f rows 1-3) ------------------------------------------------------------
+    def sum_mass_density(self):
+        """computeSPHSumMassDensity -> internal entries of 'massDensity' on the device."""
+        self._check(self._lib.sphb200_sum_mass_density(self._h))
+
+    def compute_omega_gradh(self):
+        """computeSPHOmegaGradhCorrection -> internal entries of 'omegaGradh' on the device."""
+        self._check(self._lib.sphb200_compute_omega_gradh(self._h))
+
+    def update_eos_gamma_law(self, eos):
+        """PressurePolicy / SoundSpeedPolicy with GammaLawGas over every node; eos: _lib.GammaLaw."""
+        self._check(self._lib.sphb200_update_eos_gamma_law(self._h, C.byref(eos)))
+
+    def state_copy(self):
+        self._check(self._lib.sphb200_state_copy(self._h))
+
+    def state_assign(self):
+        self._check(self._lib.sphb200_state_assign(self._h))
+
+    def state_update(self, step_options, multiplier, timeAdvanceOnly=False):
+        """State::update(derivs, multiplier, t, dt) for the hydro + smoothing-scale policies, then P and cs."""
+        self._check(self._lib.sphb200_state_update(self._h, C.byref(step_options), multiplier, int(bool(timeAdvanceOnly))))
+
+    def compute_dt(self, cfl=0.25, useVelocityMagnitudeForDt=False):
+        """GenericHydro::dt -> (dt, reason string, limiting node)."""
+        dt, reason, node = C.c_double(), C.c_int(), C.c_uint32()
+        self._check(self._lib.sphb200_compute_dt(self._h, cfl, int(bool(useVelocityMagnitudeForDt)), C.byref(dt), C.byref(reason),
+                                                 C.byref(node)))
+        return dt.value, (L.DT_REASONS[reason.value] if reason.value >= 0 else ""), node.value
 
     # -- halo ----------------------------------------------------------------------------------------------------------
     def halo_bytes_per_node(self, mask):

@@ -1,0 +1,130 @@
+"""CheapSynchronousRK2 -- host-side mirror of Spheral's integrator over the device-resident state.
+
+Reference: Integrator/CheapSynchronousRK2.cc:40-132 (the stage sequence), Integrator/Integrator.cc:66-111 (step: connectivity
+update, retry with a halved dt multiplier), :114-166 (selectDt: package votes, dtGrowth*lastDt, [dtMin, dtMax]), and the hooks
+of the SPH package that run inside a stage: SPHBase::preStepInitialize (sum density, SPHBase.cc:322-352),
+SPHBase::postStateUpdate (grad-h correction, :527-547), ArtificialViscosityHandle::postStateUpdate (DvDx -> Q gradient).
+
+Every field stays on the GPU: one step issues the C-ABI calls below and reads back a single number, the hydro time-step vote
+(sphb200_compute_dt).  Method and attribute names follow the reference (`step`, `advance`, `currentTime`, `currentCycle`,
+`lastDt`, `dtMin`, `dtMax`, `dtGrowth`, `allowDtCheck`).
+"""
+from . import _lib as L
+from . import engine as E
+
+INTEGRATE_DENSITY, RIGOROUS_SUM_DENSITY = 0, 1      # MassDensityType (Hydro/GenericHydro.hh)
+
+
+class CheapSynchronousRK2:
+    def __init__(self, engine, step_options=None, densityUpdate=RIGOROUS_SUM_DENSITY, gradhCorrection=True, cfl=0.25,
+                 useVelocityMagnitudeForDt=False, dtMin=0.0, dtMax=1.0e100, dtGrowth=2.0, allowDtCheck=False,
+                 ghostRefresh=None):
+        self.engine = engine
+        self.so = step_options if step_options is not None else E.make_step_options()
+        self.densityUpdate, self.gradhCorrection = densityUpdate, gradhCorrection
+        self.cfl, self.useVelocityMagnitudeForDt = cfl, useVelocityMagnitudeForDt
+        self.dtMin, self.dtMax, self.dtGrowth = dtMin, dtMax, dtGrowth
+        self.allowDtCheck = allowDtCheck
+        # applyGhostBoundaries + finalizeGhostBoundaries: a callable refreshing the ghost entries on the device (halo exchange);
+        # None for a problem without ghost nodes
+        self.ghostRefresh = ghostRefresh
+        self.currentTime, self.currentCycle, self.lastDt = 0.0, 0, 1.0e100
+        self.dtMultiplier = 1.0
+        self.lastDtReason, self.lastDtNode = "", 0
+        self._needQ = (engine.options.Qkind == L.Q_LIMITED_MG) or bool(engine.options.balsara)
+
+    # -- pieces of a stage -----------------------------------------------------------------------------------------------
+    def _ghosts(self):
+        if self.ghostRefresh is not None:
+            self.ghostRefresh()
+
+    def _post_state_update(self):
+        """Integrator::postStateUpdate (Integrator.cc:252-271)."""
+        e = self.engine
+        if self._needQ:
+            e.copy_DvDx_to_Q()                       # ArtificialViscosityHandle.cc:165-180
+        if self.gradhCorrection:
+            e.compute_omega_gradh()                  # SPHBase.cc:539-547
+            self._ghosts()
+
+    def selectDt(self, dtMin, dtMax):
+        """Integrator::selectDt (Integrator.cc:114-166) with the one package vote of GenericHydro::dt."""
+        vote, why, node = self.engine.compute_dt(self.cfl, self.useVelocityMagnitudeForDt)
+        dt = dtMax
+        if 0.0 < vote < dt:
+            dt = vote
+            self.lastDtReason, self.lastDtNode = why, node
+        dt *= self.dtMultiplier
+        dt = min(dt, self.dtGrowth*self.lastDt)
+        return min(dtMax, max(dtMin, dt))
+
+    def initializeDerivatives(self):
+        """The first evaluation of a run: CheapSynchronousRK2 advances the trial state with the previous step's derivatives,
+        so a fresh problem needs one (the reference does this in SpheralController.reinitializeProblem -> evaluateDerivatives)."""
+        e = self.engine
+        e.build_pairs()
+        if self.densityUpdate == RIGOROUS_SUM_DENSITY:
+            e.sum_mass_density()
+        e.update_eos_gamma_law(self.so.eos)
+        if self.gradhCorrection:
+            e.compute_omega_gradh()
+        self._ghosts()
+        e.evaluate_derivatives(self.currentTime, 0.0)
+
+    # -- one step ----------------------------------------------------------------------------------------------------------
+    def _try_step(self, maxTime):
+        """CheapSynchronousRK2::step(maxTime, state, derivs) (CheapSynchronousRK2.cc:40-132)."""
+        e, so = self.engine, self.so
+        t = self.currentTime
+        # preStepInitialize (SPHBase.cc:322-352)
+        if self.densityUpdate == RIGOROUS_SUM_DENSITY:
+            e.sum_mass_density()
+            e.update_eos_gamma_law(so.eos)           # pressure / sound speed follow the density they depend on
+            self._ghosts()
+        dt = self.selectDt(min(self.dtMin, maxTime - t), min(self.dtMax, maxTime - t))
+        hdt = 0.5*dt
+        e.state_copy()                                # state0
+        # trial advance to the mid point with the previous derivatives (timeAdvanceOnly)
+        e.state_update(so, hdt, True)
+        self._ghosts()
+        self._post_state_update()
+        # derivatives at the mid point, on the connectivity of the step start
+        e.evaluate_derivatives(t + hdt, hdt)
+        if self.allowDtCheck:
+            dtnew = self.selectDt(min(self.dtMin, maxTime - t), min(self.dtMax, maxTime - t))
+            if dtnew < 0.5*dt:
+                e.state_assign()
+                return False
+        # full step from state0 with the mid-point derivatives
+        e.state_assign()
+        e.state_update(so, dt, False)
+        self.currentTime = t + dt
+        self._ghosts()
+        self._post_state_update()
+        self.currentCycle += 1
+        self.lastDt = dt
+        return True
+
+    def step(self, maxTime=1.0e100):
+        """Integrator::step(maxTime) (Integrator.cc:66-111): neighbour update, then up to 10 attempts with a halved dt."""
+        self._ghosts()                                # setGhostNodes
+        self.engine.build_pairs()                     # Neighbor::updateNodes + ConnectivityMap::computeConnectivity
+        ok, count = False, 0
+        allow = self.allowDtCheck
+        while not ok and count < 10:
+            count += 1
+            if count == 10:
+                self.allowDtCheck = False
+            ok = self._try_step(maxTime)
+            if not ok:
+                self.dtMultiplier *= 0.5
+        self.allowDtCheck = allow
+        self.dtMultiplier = 1.0
+        return ok
+
+    def advance(self, goalTime, maxSteps=None):
+        n = 0
+        while self.currentTime < goalTime and (maxSteps is None or n < maxSteps):
+            self.step(goalTime)
+            n += 1
+        return n

@@ -98,3 +98,98 @@ def physical_floors(st, nInt, ndim):
     return dict(DxDt=v, DrhoDt=rho*v/h, DvDt=cs*cs/h, DepsDt=cs*cs*v/h, DvDx=v/h, localDvDx=v/h, gradRho=rho/h, M=1.0,
                 localM=1.0, rhoSum=rho, normalization=1.0, maxViscousPressure=P, effViscousPressure=P, XSPHWeightSum=1.0,
                 XSPHDeltaV=v, DHDt=v/(h*h), Hideal=1.0/h, massZerothMoment=1.0, massFirstMoment=1.0)
+
+
+# ---- CheapSynchronousRK2 driven through the oracle (the checker of spheral_b200/integrator.py) -----------------------------
+class OracleRK2:
+    """Same stage sequence as CheapSynchronousRK2.cc:40-132, every piece an oracle call.  No ghost nodes."""
+
+    def __init__(self, orc, oo, so, OT, st, densityUpdate=1, gradhCorrection=True, dtMin=0.0, dtMax=1.0e100, dtGrowth=2.0):
+        self.orc, self.oo, self.so, self.OT = orc, oo, so, OT
+        self.ndim = oo.ndim
+        self.s = {k: np.array(v, dtype=np.float64, copy=True) for k, v in to_oracle_state(st).items()}
+        self.s["eps"] = np.array(st["specificThermalEnergy"], dtype=np.float64, copy=True)
+        self.N = self.s["pos"].shape[0]
+        self.densityUpdate, self.gradhCorrection = densityUpdate, gradhCorrection
+        self.dtMin, self.dtMax, self.dtGrowth = dtMin, dtMax, dtGrowth
+        self.t, self.cycle, self.lastDt = 0.0, 0, 1.0e100
+        self.needQ = (oo.Qkind == orc.Q_LIMITED_MG) or bool(oo.balsara)
+        self.derivs = None
+        self.reason, self.node = "", 0
+
+    def _pairs(self):
+        self.pi, self.pj, self.cnt = self.orc.pairs(self.ndim, self.N, 0, self.s["pos"], self.s["H"], self.OT.kext)
+
+    def _sum_density(self):
+        self.s["rho"] = self.orc.sum_mass_density(self.ndim, self.OT, self.N, 0, self.s["pos"], self.s["mass"], self.s["H"],
+                                                  self.pi, self.pj, rho=self.s["rho"])
+
+    def _eos(self):
+        self.s["P"], self.s["cs"] = self.orc.eos_gamma_law(self.so, self.s["rho"], self.s["eps"])
+
+    def _omega(self):
+        self.s["omega"] = self.orc.omega_gradh(self.ndim, self.OT, self.N, 0, self.s["pos"], self.s["H"], self.pi, self.pj,
+                                               self.cnt, omega=self.s["omega"])
+
+    def _evaluate(self):
+        self.derivs = self.orc.evaluate_derivatives(self.oo, self.OT, self.s, self.N, 0, self.pi, self.pj, self.cnt)
+        self.pairs_eval = (self.pi, self.pj)
+
+    def _post_state_update(self):
+        if self.needQ:
+            self.s["DvDxQ"] = np.array(self.derivs["DvDx"], copy=True)
+        if self.gradhCorrection:
+            self._omega()
+
+    def _update(self, mult, timeAdvanceOnly):
+        d = self.derivs
+        epsDone = False
+        if self.oo.compatibleEnergy and not timeAdvanceOnly:
+            pi, pj = self.pairs_eval
+            self.s["eps"] = self.orc.update_energy_compatible(self.ndim, self.N, 0, self.s["mass"], self.s["vel"], d["DvDt"],
+                                                              d["DepsDt"], pi, pj, d["pairAccelerations"], mult, self.s["eps"])
+            epsDone = True
+        out = self.orc.state_update(self.oo, self.so, self.N, 0, mult, timeAdvanceOnly, d, self.s, epsDone=epsDone)
+        self.s.update(out)
+
+    def _select_dt(self, maxTime):
+        vote, why, node = self.orc.hydro_dt(self.oo, self.so, self.N, self.s["vel"], self.s["H"], self.s["rho"], self.s["cs"],
+                                            self.derivs, self.pi, self.pj)
+        dtMin, dtMax = min(self.dtMin, maxTime - self.t), min(self.dtMax, maxTime - self.t)
+        dt = dtMax
+        if 0.0 < vote < dt:
+            dt, self.reason, self.node = vote, why, node
+        dt = min(dt, self.dtGrowth*self.lastDt)
+        return min(dtMax, max(dtMin, dt))
+
+    def initializeDerivatives(self):
+        self._pairs()
+        if self.densityUpdate == 1:
+            self._sum_density()
+        self._eos()
+        if self.gradhCorrection:
+            self._omega()
+        self._evaluate()
+
+    def step(self, maxTime=1.0e100):
+        self._pairs()
+        if self.densityUpdate == 1:
+            self._sum_density()
+            self._eos()
+        dt = self._select_dt(maxTime)
+        hdt = 0.5*dt
+        s0 = {k: np.array(v, copy=True) for k, v in self.s.items()}
+        self._update(hdt, True)
+        self._post_state_update()
+        self._evaluate()
+        self.s = s0                 # state.assign(state0) restores every registered field, the Q gradient and omega included
+        self._update(dt, False)
+        self.t += dt
+        self._post_state_update()
+        self.cycle += 1
+        self.lastDt = dt
+        return dt
+
+    def total_energy(self):
+        m, v, e = self.s["mass"], self.s["vel"], self.s["eps"]
+        return float(np.sum(m*(0.5*np.sum(v*v, axis=1) + e)))

@@ -1,0 +1,186 @@
+"""GPU parity of the per-step callers, through the C ABI, against the oracle:
+sum density, grad-h correction, gamma-law EOS, State::update policies, GenericHydro::dt and whole CheapSynchronousRK2 steps
+with the state resident on the device.  Bar: 1e-10 relative per field (FP64, re-associated sums); dt to 1e-12."""
+import numpy as np
+import pytest
+
+import common
+from spheral_b200 import kernel as K
+
+pytestmark = pytest.mark.gpu
+TOL = 1.0e-10
+
+
+@pytest.fixture(scope="module")
+def mods(sphlib):
+    from spheral_b200 import engine, integrator
+    return engine, integrator
+
+
+def setup(oracle, engine, ndim, n, nPerh, kind="lattice", ghosts=False, **kw):
+    st, nInt, nGhost = common.make_problem(ndim, n, nPerh=nPerh, kind=kind, ghosts=ghosts)
+    WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    OT = common.oracle_table(oracle, WT)
+    oo, po = common.opts_pair(oracle, engine, ndim, nPerh=nPerh, **kw)
+    e = engine.Engine(ndim, options=po)
+    e.set_kernel_table(WT)
+    e.set_nodes(nInt, nGhost)
+    e.upload_state(**st)
+    e.build_pairs()
+    s = common.to_oracle_state(st)
+    s["eps"] = st["specificThermalEnergy"]
+    pi, pj, cnt = oracle.pairs(ndim, nInt, nGhost, s["pos"], s["H"], OT.kext)
+    return st, nInt, nGhost, OT, oo, e, s, (pi, pj, cnt)
+
+
+def rel(a, b, n):
+    a, b = np.asarray(a)[:n], np.asarray(b)[:n]
+    return float(np.abs(a - b).max()/max(np.abs(b).max(), 1e-300))
+
+
+@pytest.mark.parametrize("ndim,n,nPerh,kind,ghosts", [(3, 12, 1.51, "lattice", False), (2, 30, 2.01, "lattice", True),
+                                                      (3, 9, 1.51, "aniso", False)])
+def test_sum_density_and_omega(oracle, mods, ndim, n, nPerh, kind, ghosts):
+    engine, _ = mods
+    st, nInt, nGhost, OT, oo, e, s, (pi, pj, cnt) = setup(oracle, engine, ndim, n, nPerh, kind, ghosts)
+    ref_rho = oracle.sum_mass_density(ndim, OT, nInt, nGhost, s["pos"], s["mass"], s["H"], pi, pj, rho=s["rho"])
+    ref_om = oracle.omega_gradh(ndim, OT, nInt, nGhost, s["pos"], s["H"], pi, pj, cnt, omega=s["omega"])
+    e.sum_mass_density()
+    e.compute_omega_gradh()
+    got = e.download_state("massDensity", "omegaGradh")
+    assert rel(got["massDensity"], ref_rho, nInt) <= TOL
+    assert rel(got["omegaGradh"], ref_om, nInt) <= TOL
+    # ghost entries are the caller's: untouched
+    assert np.array_equal(got["massDensity"][nInt:], st["massDensity"][nInt:])
+    assert np.array_equal(got["omegaGradh"][nInt:], st["omegaGradh"][nInt:])
+
+
+def test_eos_gamma_law(oracle, mods):
+    engine, _ = mods
+    st, nInt, nGhost, OT, oo, e, s, _ = setup(oracle, engine, 3, 8, 1.51)
+    so = oracle.default_step_options(gamma=1.4, minimumPressure=0.3, maximumPressure=0.55, externalPressure=0.05, minPressureType=1)
+    pso = engine.make_step_options(gamma=1.4, minimumPressure=0.3, maximumPressure=0.55, externalPressure=0.05, minPressureType=1)
+    P, cs = oracle.eos_gamma_law(so, s["rho"], s["eps"])
+    e.update_eos_gamma_law(pso.eos)
+    got = e.download_state("pressure", "soundSpeed")
+    assert np.abs(got["pressure"] - P).max() <= 1e-15*np.abs(P).max()
+    assert np.abs(got["soundSpeed"] - cs).max() <= 1e-15*np.abs(cs).max()
+    assert (P == 0.0).any() and (P == 0.55).any()          # both limits exercised
+
+
+CASES = [  # ndim, n, nPerh, kind, options, step options, timeAdvanceOnly
+    (3, 10, 1.51, "lattice", dict(), dict(), False),
+    (3, 10, 1.51, "lattice", dict(), dict(), True),
+    (2, 28, 2.01, "lattice", dict(compatibleEnergy=0), dict(HEvolution=1, rhoMin=0.95, rhoMax=1.15), False),
+    (3, 8, 1.51, "aniso", dict(hEvolution=1, hmin=1e-3, hmax=1e3), dict(), False),
+    (2, 24, 2.01, "aniso", dict(hEvolution=1, hmin=1e-3, hmax=0.08), dict(hminratio=0.5), True),
+    (3, 9, 1.51, "lattice", dict(hmin=1e-3, hmax=0.11), dict(HEvolution=1), False),     # eigenvalue clamp active (hmax)
+]
+
+
+@pytest.mark.parametrize("ndim,n,nPerh,kind,okw,skw,tao", CASES)
+def test_state_update(oracle, mods, ndim, n, nPerh, kind, okw, skw, tao):
+    engine, _ = mods
+    st, nInt, nGhost, OT, oo, e, s, (pi, pj, cnt) = setup(oracle, engine, ndim, n, nPerh, kind, **okw)
+    so = oracle.default_step_options(**skw)
+    pso = engine.make_step_options(**skw)
+    d = oracle.evaluate_derivatives(oo, OT, s, nInt, nGhost, pi, pj, cnt)
+    mult = 2.0e-3
+    epsDone = False
+    s_in = dict(s)
+    if oo.compatibleEnergy and not tao:
+        s_in["eps"] = oracle.update_energy_compatible(ndim, nInt, nGhost, s["mass"], s["vel"], d["DvDt"], d["DepsDt"], pi, pj,
+                                                      d["pairAccelerations"], mult, s["eps"])
+        epsDone = True
+    ref = oracle.state_update(oo, so, nInt, nGhost, mult, tao, d, s_in, epsDone=epsDone)
+    e.evaluate_derivatives(0.0, 1.0)
+    e.state_copy()
+    e.state_update(pso, mult, tao)
+    got = e.download_state("position", "velocity", "H", "massDensity", "specificThermalEnergy", "pressure", "soundSpeed")
+    names = dict(position="pos", velocity="vel", H="H", massDensity="rho", specificThermalEnergy="eps", pressure="P", soundSpeed="cs")
+    worst = {k: rel(got[k], ref[o], nInt) for k, o in names.items()}
+    assert all(v <= TOL for v in worst.values()), worst
+    # the update is not a no-op, and state_assign restores state0 bit for bit
+    assert rel(got["position"], st["position"], nInt) > 0
+    e.state_assign()
+    back = e.download_state("position", "velocity", "H", "massDensity", "specificThermalEnergy")
+    for k in back:
+        assert np.array_equal(back[k], st[k]), k
+
+
+@pytest.mark.parametrize("ndim,n,nPerh,kind,okw", [(3, 11, 1.51, "lattice", dict()), (2, 30, 2.01, "lattice", dict()),
+                                                   (3, 9, 1.51, "aniso", dict(hEvolution=1))])
+def test_compute_dt(oracle, mods, ndim, n, nPerh, kind, okw):
+    engine, _ = mods
+    st, nInt, nGhost, OT, oo, e, s, (pi, pj, cnt) = setup(oracle, engine, ndim, n, nPerh, kind, **okw)
+    d = oracle.evaluate_derivatives(oo, OT, s, nInt, nGhost, pi, pj, cnt)
+    e.evaluate_derivatives(0.0, 1.0)
+    for velmag in (False, True):
+        so = oracle.default_step_options(cfl=0.3, useVelocityMagnitudeForDt=int(velmag))
+        ref, why, node = oracle.hydro_dt(oo, so, nInt, s["vel"], s["H"], s["rho"], s["cs"], d, pi, pj)
+        dt, gwhy, gnode = e.compute_dt(0.3, velmag)
+        assert abs(dt - ref) <= 1e-12*ref, (dt, ref)
+        assert gwhy == why and gnode == node, (gwhy, why, gnode, node)
+    # a limit set by the pair loop: blow up one node's velocity
+    st2 = dict(st); v = st["velocity"].copy(); v[nInt//2] += 50.0; st2["velocity"] = v
+    e.upload_state(velocity=v)
+    s2 = dict(s); s2["vel"] = v
+    so = oracle.default_step_options()
+    ref, why, node = oracle.hydro_dt(oo, so, nInt, v, s["H"], s["rho"], s["cs"], d, pi, pj)
+    dt, gwhy, gnode = e.compute_dt(0.25, False)
+    assert abs(dt - ref) <= 1e-12*ref and gwhy == why and gnode == node, (dt, ref, gwhy, why, gnode, node)
+
+
+@pytest.mark.parametrize("ndim,n,nPerh,okw,rho_update", [(3, 12, 1.51, dict(Cl=1.0, Cq=1.0), 1), (2, 32, 2.01, dict(Cl=1.0, Cq=1.0), 0),
+                                                          (3, 10, 1.51, dict(Qkind=1, Cl=1.0, Cq=1.0), 1)])
+def test_rk2_steps_device_resident(oracle, mods, ndim, n, nPerh, okw, rho_update):
+    """Whole CheapSynchronousRK2 steps: device-resident integrator vs the oracle-driven one."""
+    engine, integrator = mods
+    st, nInt, _ = common.make_problem(ndim, n, nPerh=nPerh)
+    st["velocity"] = 0.3*st["velocity"]
+    if okw.get("Qkind"):
+        st["DvDxQ"] = np.zeros((nInt, ndim*ndim))
+    WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    OT = common.oracle_table(oracle, WT)
+    oo, po = common.opts_pair(oracle, engine, ndim, nPerh=nPerh, **okw)
+    so = oracle.default_step_options()
+    ref = common.OracleRK2(oracle, oo, so, OT, st, densityUpdate=rho_update)
+    e = engine.Engine(ndim, options=po)
+    e.set_kernel_table(WT)
+    e.set_nodes(nInt, 0)
+    e.upload_state(**st)
+    rk = integrator.CheapSynchronousRK2(e, engine.make_step_options(), densityUpdate=rho_update)
+    ref.initializeDerivatives()
+    rk.initializeDerivatives()
+    nsteps = 3
+    for _ in range(nsteps):
+        dt_ref = ref.step()
+        assert rk.step()
+        assert abs(rk.lastDt - dt_ref) <= 1e-11*dt_ref, (rk.lastDt, dt_ref)
+        assert rk.lastDtReason == ref.reason
+    assert rk.currentCycle == nsteps and abs(rk.currentTime - ref.t) <= 1e-11*ref.t
+    got = e.download_state("position", "velocity", "H", "massDensity", "specificThermalEnergy", "pressure", "soundSpeed", "omegaGradh")
+    names = dict(position="pos", velocity="vel", H="H", massDensity="rho", specificThermalEnergy="eps", pressure="P", soundSpeed="cs",
+                 omegaGradh="omega")
+    worst = {k: rel(got[k], ref.s[o], nInt) for k, o in names.items()}
+    assert all(v <= 1.0e-9 for v in worst.values()), worst      # three steps of accumulated 1e-10-level differences
+    # conservation on the device result itself (compatible energy): |dE/E| at round-off
+    m, v, eps = st["mass"], got["velocity"], got["specificThermalEnergy"]
+    E1 = float(np.sum(m*(0.5*np.sum(v*v, axis=1) + eps)))
+    v0, eps0 = st["velocity"], st["specificThermalEnergy"]
+    E0 = float(np.sum(m*(0.5*np.sum(v0*v0, axis=1) + eps0)))
+    assert abs(E1 - E0) <= 1e-12*abs(E0)
+
+
+def test_step_errors(oracle, mods):
+    engine, _ = mods
+    st, nInt, nGhost, OT, oo, e, s, _ = setup(oracle, engine, 3, 6, 1.51)
+    with pytest.raises(engine.SPHB200Error, match="no derivatives"):
+        e.state_update(engine.make_step_options(), 1e-3, True)
+    with pytest.raises(engine.SPHB200Error, match="no derivatives"):
+        e.compute_dt()
+    with pytest.raises(engine.SPHB200Error, match="gamma"):
+        e.update_eos_gamma_law(engine.make_step_options(gamma=1.0).eos)
+    e.upload_state(position=st["position"])           # stale connectivity
+    with pytest.raises(engine.SPHB200Error, match="connectivity"):
+        e.sum_mass_density()
