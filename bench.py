@@ -345,6 +345,27 @@ def main():
     edges = e.stats()["directed_edges"]
     halo_info = dsph.info() if dsph is not None else None
 
+    # device-resident CheapSynchronousRK2 steps: neighbour update + sum density + dt vote + trial advance +
+    # grad-h correction + derivatives + compatible-energy update + full advance, no field leaving the GPU
+    rk2 = None
+    if dsph is None and not crk:
+        from spheral_b200 import integrator as I
+        rk = I.CheapSynchronousRK2(e, engine.make_step_options())
+        rk.initializeDerivatives()
+        for _ in range(2):
+            rk.step()
+        e.sync()
+        nrk = max(3, args.steps//2)
+        rk_s, _ = timed(rk.step, nrk)
+        rk2 = {"ms_per_step": rk_s/nrk*1e3, "value": N*nrk/rk_s, "unit": "particle-updates/s", "steps": nrk,
+               "what": "CheapSynchronousRK2 step with the state resident in HBM: build_pairs + computeSPHSumMassDensity + GenericHydro::dt + "
+                       "State::update (x2) + computeSPHOmegaGradhCorrection (x2) + evaluateDerivatives + compatible energy; "
+                       "one 16-byte read-back (dt) per step",
+               "last_dt": rk.lastDt, "dt_reason": rk.lastDtReason}
+        # put the bench state back (the e2e leg uploads it anyway)
+        e.upload_state_pinned(up_mask, hs)
+        e.sync()
+
     # e2e leg: host buffers in, host buffers out, every step
     for _ in range(2):
         step_e2e()
@@ -392,6 +413,8 @@ def main():
                                  "evaluate": float(np.mean(eval_ms)), "pair_kernel": float(np.mean(pair_ms)),
                                  "wall_per_step": wall_s/args.steps*1e3},
                 "roofline": roofline, "roofline_fp64": roofline_fp64}
+        if rk2 is not None:
+            line["rk2_step_resident"] = rk2
         if not args.no_cpu_baseline and world == 1:
             val, tmed, Ns, npairs, sample = cpu_port_run(spec, args.cpu_sample, 3, 1, threads)
             line["cpu_baseline"] = {"value": val, "unit": "particle-updates/s", "cores": threads, "kind": "port", "sample": sample,

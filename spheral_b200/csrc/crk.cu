@@ -47,8 +47,8 @@ template <int DIM> struct Ck {
 };
 template <int DIM> struct LightPrefix { static constexpr int BYTES = ((Dm<DIM>::R_M + 1)*8 + 15)/16*16; };   // position .. mass: 112 B (3-D) / 64 B (2-D)
 template <int DIM> using LightRing = NbrRing<DIM, 0, 0, LS, LightPrefix<DIM>::BYTES>;
-template <int DIM> using PosRing = NbrRing<DIM, 0, 0, LS, (DIM == 3 ? 32 : 16)>;            // the position only
-template <int DIM> using DerivRing = NbrRing<DIM, Ck<DIM>::CST*8, Ck<DIM>::QST*8, CS>;
+template <int DIM> using PosRing = NbrRing<DIM, 0, 0, LS, (DIM == 3 ? 32 : 16), false>;     // the position only, no aux record
+template <int DIM> using DerivRing = NbrRing<DIM, Ck<DIM>::CST*8, Ck<DIM>::QST*8, CS, Dm<DIM>::ROW*8, false>;   // det Hj recomputed, Vj in the Q record
 
 // api (host order, AoS, width doubles per node) -> sorted copy with stride `stride`
 __global__ void __launch_bounds__(RB) k_gather_sorted(const double* __restrict__ api, int width, int stride,
@@ -484,8 +484,8 @@ __global__ void __launch_bounds__(32*CW, 1) k_crk_derivs(CrkArgs a) {
     // records are read from the ring where they are first needed (42 doubles of neighbour state would otherwise be live at once)
     double rw[ROW], cj_[CST], qj_[QST];
     ring.read_row(k, lane, rw);
-    const double2 auxj = ring.read_aux(k, lane);            // {det Hj, Vj}
-    const double Hdetj = auxj.x, volj = auxj.y;
+    const double Hdetj = sym_det<DIM>(rw + D::R_H);         // recomputed: a per-lane 16-byte aux copy costs as much as the 32 rows (nbr_ring.cuh)
+    const double volj = ring_lds128(ring.stage(k) + DerivRing<DIM>::X2OFF + (unsigned)lane*DerivRing<DIM>::X2B).x;   // {Vj, Q velocity gradient}
     const double* rj = rw + D::R_POS; const double* vj = rw + D::R_VEL; const double* Hj = rw + D::R_H;
     const double mj = rw[D::R_M], rhoj = rw[D::R_RHO], Pj = rw[D::R_PRHO], csj = rw[D::R_CS];
 

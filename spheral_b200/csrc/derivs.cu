@@ -63,6 +63,12 @@ __device__ __forceinline__ void cp_async16_s(unsigned smemDst, const void* gmemS
 #ifndef SPHB200_PAIR_CTAS
 #define SPHB200_PAIR_CTAS 2
 #endif
+// 1: stream the per-node {det H, 1/rho} record of every neighbour through the ring as well; 0: recompute both from the row.
+// The per-lane 16-byte copy costs 32 shared-memory wavefronts per iteration, as many as the 32 rows together, and the LSU data
+// pipe is the unit this kernel saturates first (profiles/r01_notes.md); 23 extra FP64 instructions per edge are cheaper.
+#ifndef SPHB200_PAIR_AUX
+#define SPHB200_PAIR_AUX 0
+#endif
 __device__ __forceinline__ const unsigned char* mad_wide(uint32_t a, uint32_t b, const unsigned char* c) {   // c + a*b in one IMAD.WIDE
   unsigned long long r;
   asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"((unsigned long long)c));
@@ -74,7 +80,7 @@ constexpr int PAIR_WARPS = SPHB200_PAIR_WARPS;     // warps (= tiles in flight) 
 constexpr int PAIR_CTAS = SPHB200_PAIR_CTAS;       // resident CTAs per SM the register budget is sized for
 template <int DIM> struct RingGeom {
   static constexpr int ROWB = Dm<DIM>::ROW*8 + 16;          // +16 B pad: conflict-free 128-bit LDS
-  static constexpr int STAGEB = 32*ROWB + 32*16;             // 32 rows + 32 aux records {det H, 1/rho}
+  static constexpr int STAGEB = 32*ROWB + (SPHB200_PAIR_AUX ? 32*16 : 0);   // 32 rows (+ 32 aux records {det H, 1/rho})
 };
 
 // The pair-loop kernel: one warp per tile of 32 Morton-consecutive nodes, lane <-> node i; persistent CTAs stride over tiles.
@@ -172,7 +178,9 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, PAIR_CTAS) k_sph_derivs(DerivAr
   auto issue_rows = [&](uint32_t p, uint32_t jraw) {  // jraw: this lane's list entry at position p (0 if none)
     const uint32_t jrow = jraw;
     const unsigned stage = warpRing + (p % PAIR_STAGES)*(unsigned)STAGEB;
+#if SPHB200_PAIR_AUX
     cp_async16_s(stage + 32u*ROWB + 16u*lane, a.aux2 + 2*(size_t)jrow);        // this lane's own neighbour: {det H, 1/rho}
+#endif
 #if SPHB200_COPY_LANES == 8
     if (CH == 8) {
       // 8 lanes per row (one 16-byte chunk each): an LDGSTS touches 4 full lines
@@ -226,7 +234,11 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, PAIR_CTAS) k_sph_derivs(DerivAr
       const unsigned rp = st + (unsigned)lane*ROWB;
 #pragma unroll
       for (int q = 0; q < ROW/2; ++q) { const double2 v = lds128(rp + 16u*q); rw[2*q] = v.x; rw[2*q + 1] = v.y; }
+#if SPHB200_PAIR_AUX
       aux = lds128(st + 32u*ROWB + 16u*lane);
+#else
+      aux.x = sym_det<DIM>(rw + D::R_H); aux.y = fast_rcp(rw[D::R_RHO]);
+#endif
     }
     {
       // refill the stage consumed in the previous iteration (every lane is past its reads: they precede the __syncwarp above)

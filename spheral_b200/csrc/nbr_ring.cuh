@@ -7,7 +7,7 @@
 // fetch the 8 16-byte chunks of one 128-byte record, so an LDGSTS touches 4 full lines -- into a ring of STAGES stages,
 // STAGES-1 iterations ahead of the arithmetic, which also takes the L2 latency of the gather off the critical path.
 //
-// Stage layout (per warp):  32 x RB node rows | 32 x X1B first extra record | 32 x X2B second extra record | 32 x 16 B aux2
+// Stage layout (per warp):  32 x RB node rows | 32 x X1B first extra record | 32 x X2B second extra record | 32 x 16 B aux2 (optional)
 // Record strides are padded to an odd number of 16-byte units so that the per-lane 128-bit reads are bank-conflict free.
 #pragma once
 #include "sphb200_internal.cuh"
@@ -67,13 +67,16 @@ __device__ __forceinline__ void ring_copy_records(unsigned dst0, const unsigned 
 }
 
 // ROWCOPY: leading bytes of the node row a kernel needs (the position leads the row, then velocity, H, m, rho, P/rho^2, cs)
-template <int DIM, int X1BYTES, int X2BYTES, int STAGES, int ROWCOPY = Dm<DIM>::ROW*8>
+// AUX: also copy this lane's own 16-byte per-node record (aux2).  A per-lane 16-byte copy costs 32 shared-memory wavefronts per
+// iteration -- as many as the 32 node rows together -- and the pair loops are bound by exactly that (LSU data-pipe wavefronts
+// 93 % busy, profiles/r01_notes.md), so kernels that can recompute those two numbers from the row leave it out.
+template <int DIM, int X1BYTES, int X2BYTES, int STAGES, int ROWCOPY = Dm<DIM>::ROW*8, bool AUX = true>
 struct NbrRing {
   static constexpr int ROWBYTES = Dm<DIM>::ROW*8;
   static constexpr int RB = ring_pad(ROWCOPY);
   static constexpr int X1B = ring_pad(X1BYTES), X2B = ring_pad(X2BYTES);
   static constexpr int X1OFF = 32*RB, X2OFF = X1OFF + 32*X1B, AUXOFF = X2OFF + 32*X2B;
-  static constexpr int STAGEB = AUXOFF + 32*16;
+  static constexpr int STAGEB = AUXOFF + (AUX ? 32*16 : 0);
   static constexpr int WARPB = STAGES*STAGEB;
 
   unsigned base;                                  // 32-bit shared address of this warp's ring
@@ -83,7 +86,7 @@ struct NbrRing {
   // jrow: this lane's list entry at position p (0 past the end of the lane's list: row 0 is fetched and never read back)
   __device__ __forceinline__ void issue(uint32_t p, uint32_t jrow, int lane) const {
     const unsigned st = stage(p);
-    ring_cp16(st + AUXOFF + 16u*lane, aux2 + 16*(size_t)jrow);
+    if (AUX) ring_cp16(st + AUXOFF + 16u*lane, aux2 + 16*(size_t)jrow);
     ring_copy_records<ROWCOPY, RB, ROWBYTES>(st, rows, jrow, lane);
     if (X1BYTES) ring_copy_records<X1BYTES == 0 ? 16 : X1BYTES, X1B == 0 ? 16 : X1B>(st + X1OFF, x1, jrow, lane);
     if (X2BYTES) ring_copy_records<X2BYTES == 0 ? 16 : X2BYTES, X2B == 0 ? 16 : X2B>(st + X2OFF, x2, jrow, lane);
@@ -102,17 +105,28 @@ struct NbrRing {
 // The pipelined walk over one tile's neighbour list.  `body(k, j)` runs for every list position k < cnt of this lane with the
 // records of neighbour j readable from ring stage k; it must read them before returning.
 //   load_idx(p): this lane's list entry at position p (0 past the end)
+// Two queues run ahead of the arithmetic: list entries are loaded IDX iterations before they are needed as copy addresses (the
+// index load is an L2 round trip of its own; one iteration ahead left it on the critical path of the short loops), and record
+// copies are issued STAGES-1 iterations before the body reads them.
+#ifndef SPHB200_RING_IDX_AHEAD
+#define SPHB200_RING_IDX_AHEAD 4
+#endif
 template <typename Ring, int STAGES, typename LoadIdx, typename Body>
 __device__ __forceinline__ void ring_walk(const Ring& ring, int lane, uint32_t rowsT, uint32_t cnt, LoadIdx load_idx, Body body) {
-  uint32_t jn = load_idx(0u);
-  uint32_t jq[STAGES];                            // list entries in flight (entry of position k is needed again by the body)
+  constexpr int IDX = SPHB200_RING_IDX_AHEAD;
+  uint32_t ji[IDX];                               // entries of positions q .. q+IDX-1, q = next position to issue
+#pragma unroll
+  for (int s = 0; s < IDX; ++s) ji[s] = load_idx((uint32_t)s);
+  uint32_t jq[STAGES];                            // entries whose copies are in flight (the body gets its own entry back)
 #pragma unroll
   for (int s = 0; s < STAGES; ++s) jq[s] = 0u;
 #pragma unroll
   for (uint32_t p = 0; p < (uint32_t)STAGES - 1u; ++p) {
-    ring.issue(p, jn, lane);
-    jq[p] = jn;
-    jn = load_idx(p + 1u);
+    ring.issue(p, ji[0], lane);
+    jq[p] = ji[0];
+#pragma unroll
+    for (int s = 0; s < IDX - 1; ++s) ji[s] = ji[s + 1];
+    ji[IDX - 1] = load_idx(p + (uint32_t)IDX);
   }
   for (uint32_t k = 0; k < rowsT; ++k) {
     ring_wait<STAGES - 2>();                      // this lane's copies for position k have landed ...
@@ -121,9 +135,11 @@ __device__ __forceinline__ void ring_walk(const Ring& ring, int lane, uint32_t r
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) jq[s] = jq[s + 1];
     // refill the stage consumed in the previous iteration (it aliases position k+STAGES-1; every lane is past those reads)
-    ring.issue(k + (uint32_t)STAGES - 1u, jn, lane);
-    jq[STAGES - 2] = jn;
-    jn = load_idx(k + (uint32_t)STAGES);
+    ring.issue(k + (uint32_t)STAGES - 1u, ji[0], lane);
+    jq[STAGES - 2] = ji[0];
+#pragma unroll
+    for (int s = 0; s < IDX - 1; ++s) ji[s] = ji[s + 1];
+    ji[IDX - 1] = load_idx(k + (uint32_t)(STAGES - 1 + IDX));
     if (k < cnt) body(k, j);
   }
   ring_wait<0>();

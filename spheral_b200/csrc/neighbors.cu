@@ -709,7 +709,9 @@ int sphb200_neighbors(sphb200_ctx* c) {
       // every internal-internal pair appears as two directed edges, every internal-ghost pair as one
       c->npairs = (size_t)((c->countersHost[1] + c->countersHost[0])/2);
       c->nSlots = needNbr;
-      c->listRows = (int)((needRows + 8 + 7)/8*8);                  // staging for the next build: longest list + a little
+      // staging for the next build: longest list + 1/8 (in an evolving problem the longest list grows from step to step, and a
+      // build that overflows its staging is redone at full cost)
+      c->listRows = (int)((needRows + needRows/8 + 8 + 7)/8*8);
       c->pairsValid = true;
       c->stats.directed_edges = c->nEdges;
       return 0;

@@ -23,11 +23,23 @@ namespace {
 constexpr int RB = 256;
 constexpr int SW = 8, SS = 4;                      // warps per CTA and ring depth of the light pair loops
 
-template <int DIM> struct StepPrefix { static constexpr int MASS = ((Dm<DIM>::R_M + 1)*8 + 15)/16*16;      // position .. mass
-                                       static constexpr int VEL = (2*DIM*8 + 15)/16*16; };                  // position, velocity
-template <int DIM> using MassRing = NbrRing<DIM, 0, 0, SS, StepPrefix<DIM>::MASS>;
-template <int DIM> using PosRing = NbrRing<DIM, 0, 0, SS, (DIM == 3 ? 32 : 16)>;
-template <int DIM> using VelRing = NbrRing<DIM, 0, 0, SS, StepPrefix<DIM>::VEL>;
+template <int DIM> struct StepPrefix { static constexpr int MASS = ((Dm<DIM>::R_M + 1)*8 + 15)/16*16; };    // position .. mass
+template <int DIM> using MassRing = NbrRing<DIM, 0, 0, SS, StepPrefix<DIM>::MASS, false>;
+template <int DIM> using PosRing = NbrRing<DIM, 0, 0, SS, (DIM == 3 ? 32 : 16), false>;
+// dt pair loop: its own compact 32-byte record {v (DIM), nodeScale} per node, built by k_node_scale; no node rows at all
+struct DtRing {
+  static constexpr int REC = 32, RB = ring_pad(REC), STAGEB = 32*RB, WARPB = SS*STAGEB;
+  unsigned base; const unsigned char* recs;
+  __device__ __forceinline__ unsigned stage(uint32_t p) const { return base + (p % SS)*(unsigned)STAGEB; }
+  __device__ __forceinline__ void issue(uint32_t p, uint32_t jrow, int lane) const {
+    ring_copy_records<REC, RB, REC>(stage(p), recs, jrow, lane);
+    ring_commit();
+  }
+  __device__ __forceinline__ void read(uint32_t k, int lane, double* o) const {
+    const double2 a = ring_lds128(stage(k) + (unsigned)lane*RB), b = ring_lds128(stage(k) + (unsigned)lane*RB + 16u);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+  }
+};
 
 struct LoopArgs {
   const double* rows; const double* aux2; const uint32_t* perm;
@@ -87,7 +99,7 @@ __global__ void __launch_bounds__(32*SW, 1) k_sph_sum_density(LoopArgs a) {
       [&](uint32_t k, uint32_t) {
         double rw[StepPrefix<DIM>::MASS/8];
         ring.read_row(k, lane, rw);
-        const double Hdetj = ring.read_aux(k, lane).x;
+        const double Hdetj = sym_det<DIM>(rw + D::R_H);        // recomputed: cheaper than a per-lane 16-byte copy (nbr_ring.cuh)
         double rij[DIM], eta[DIM];
 #pragma unroll
         for (int q = 0; q < DIM; ++q) rij[q] = ri[q] - rw[D::R_POS + q];
@@ -381,7 +393,7 @@ __global__ void __launch_bounds__(RB) k_dt_nodes(DtNodeArgs a) {
   }
   dt_block_reduce(best, tag, a.best);
 }
-// per sorted node: {nodeScale, 0} for the pair loop (one closed-form eigenvalue per node instead of one per edge)
+// per sorted node: the dt record {v (DIM), [0,] nodeScale} (one closed-form eigenvalue per node instead of one per edge)
 template <int DIM>
 __global__ void __launch_bounds__(RB) k_node_scale(const double* __restrict__ rows, size_t n, double nPerh, double* __restrict__ out) {
   const size_t s = (size_t)blockIdx.x*RB + threadIdx.x;
@@ -389,39 +401,43 @@ __global__ void __launch_bounds__(RB) k_node_scale(const double* __restrict__ ro
   double Hi[Dm<DIM>::NS];
 #pragma unroll
   for (int q = 0; q < Dm<DIM>::NS; ++q) Hi[q] = rows[s*Dm<DIM>::ROW + Dm<DIM>::R_H + q];
-  out[2*s] = 1.0/sym_max_eigenvalue<DIM>(Hi)/nPerh;
-  out[2*s + 1] = 0.0;
+  out[4*s] = rows[s*Dm<DIM>::ROW + Dm<DIM>::R_VEL]; out[4*s + 1] = rows[s*Dm<DIM>::ROW + Dm<DIM>::R_VEL + 1];
+  out[4*s + 2] = (DIM == 3) ? rows[s*Dm<DIM>::ROW + Dm<DIM>::R_VEL + 2] : 0.0;
+  out[4*s + 3] = 1.0/sym_max_eigenvalue<DIM>(Hi)/nPerh;
 }
 // :320-346 pairwise velocity difference limit: min over pairs of min(scale_i, scale_j)/|v_i - v_j|
 template <int DIM>
 __global__ void __launch_bounds__(32*SW, 1) k_dt_pairs(LoopArgs a) {
-  using D = Dm<DIM>;
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const VelRing<DIM> ring = make_ring<VelRing<DIM>>(a, (unsigned)__cvta_generic_to_shared(smem), warp);   // aux2 = {nodeScale, 0}
+  DtRing ring;
+  ring.base = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)warp*(unsigned)DtRing::WARPB;
+  ring.recs = reinterpret_cast<const unsigned char*>(a.aux2);                                  // {v, nodeScale} records
   const size_t nTiles = (a.n + SPHB200_TILE - 1)/SPHB200_TILE;
   const double tiny = DBL_EPSILON;
   double best = DBL_MAX; unsigned long long tag = ~0ull;
   for (size_t tile = (size_t)blockIdx.x*SW + warp; tile < nTiles; tile += (size_t)gridDim.x*SW) {
     const TileLane t = tile_lane(a, tile, lane);
-    double vi[DIM];
+    double ri[4] = {0.0, 0.0, 0.0, 0.0};
+    if (t.inRange) {
 #pragma unroll
-    for (int k = 0; k < DIM; ++k) vi[k] = t.inRange ? a.rows[t.i*D::ROW + D::R_VEL + k] : 0.0;
-    const double si = t.inRange ? a.aux2[2*t.i] : 0.0;
-    ring_walk<VelRing<DIM>, SS>(ring, lane, t.rowsT, t.cnt,
+      for (int q = 0; q < 4; ++q) ri[q] = a.aux2[4*t.i + q];
+    }
+    ring_walk<DtRing, SS>(ring, lane, t.rowsT, t.cnt,
       [&](uint32_t p) -> uint32_t { return (p < t.cnt) ? a.nbr[t.base + (unsigned long long)p*SPHB200_TILE] : 0u; },
       [&](uint32_t k, uint32_t j) {
-        double rw[StepPrefix<DIM>::VEL/8];
-        ring.read_row(k, lane, rw);
-        const double sj = ring.read_aux(k, lane).x;
-        double vij[DIM];
+        double rj[4];
+        ring.read(k, lane, rj);
+        double vij[3];
 #pragma unroll
-        for (int q = 0; q < DIM; ++q) vij[q] = vi[q] - rw[D::R_VEL + q];
-        const double vm = sqrt(vdot<DIM>(vij, vij));
-        const double dtv = fmin(si, sj)*(1.0/fmax(tiny, vm));                                   // safeInvVar(|vij|, tiny)
-        const uint32_t oj = a.perm[j];
-        const unsigned long long node = t.o < oj ? t.o : oj;                                   // the pair's i_node
-        dt_take(best, tag, dtv, (1ull << 40) | (node << 3) | 5ull);
+        for (int q = 0; q < 3; ++q) vij[q] = ri[q] - rj[q];
+        const double vm = sqrt(vij[0]*vij[0] + vij[1]*vij[1] + vij[2]*vij[2]);
+        const double dtv = fmin(ri[3], rj[3])*(1.0/fmax(tiny, vm));                           // safeInvVar(|vij|, tiny)
+        if (dtv <= best) {                                                                   // rare: resolve the pair's i_node only then
+          const uint32_t oj = a.perm[j];
+          const unsigned long long node = t.o < oj ? t.o : oj;
+          dt_take(best, tag, dtv, (1ull << 40) | (node << 3) | 5ull);
+        }
       });
   }
   dt_block_reduce(best, tag, a.best);
@@ -589,7 +605,7 @@ int sphb200_compute_dt(sphb200_ctx* c, double cfl, int useVelocityMagnitudeForDt
   const int nbNodes = (int)std::min<size_t>((c->nEval + RB - 1)/RB, (size_t)nsm*4);
   const size_t maxCand = (size_t)nbNodes + (size_t)nsm*8;
   if (sphb200_ensure(c, c->dtCand, c->dtCandCap, 2*maxCand + 2)) return 1;
-  if (sphb200_ensure(c, c->dtAux, c->dtAuxCap, 2*c->cap)) return 1;
+  if (sphb200_ensure(c, c->dtAux, c->dtAuxCap, 4*c->cap)) return 1;
   DtNodeArgs na{};
   na.permEval = c->permEval; na.nEval = c->nEval; na.capEval = c->capEval; na.nInt = (uint32_t)c->nInt;
   na.vel = c->api[S_VEL]; na.H = c->api[S_H]; na.rho = c->api[S_RHO]; na.cs = c->api[S_CS];
@@ -604,8 +620,8 @@ int sphb200_compute_dt(sphb200_ctx* c, double cfl, int useVelocityMagnitudeForDt
   LoopArgs a; fill_loop_args(c, a);
   a.aux2 = c->dtAux; a.best = c->dtCand + 2*(size_t)nbNodes;
   unsigned nbPairs = 0;
-  if (c->ndim == 3) { if (launch_loop(c, k_dt_pairs<3>, a, "k_dt_pairs", VelRing<3>::WARPB, false, &nbPairs)) return 1; }
-  else              { if (launch_loop(c, k_dt_pairs<2>, a, "k_dt_pairs", VelRing<2>::WARPB, false, &nbPairs)) return 1; }
+  if (c->ndim == 3) { if (launch_loop(c, k_dt_pairs<3>, a, "k_dt_pairs", DtRing::WARPB, false, &nbPairs)) return 1; }
+  else              { if (launch_loop(c, k_dt_pairs<2>, a, "k_dt_pairs", DtRing::WARPB, false, &nbPairs)) return 1; }
   if ((size_t)nbNodes + nbPairs > maxCand) return sphb200_fail(c, "compute_dt: internal candidate buffer too small");
   k_dt_final<<<1, RB, 0, c->stream>>>(c->dtCand, nbNodes + (int)nbPairs, c->dtCand + 2*maxCand);
   KERNEL_CHECK(c, "k_dt_final");
