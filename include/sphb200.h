@@ -206,6 +206,28 @@ int  sphb200_state_assign(sphb200_ctx* ctx);
 int  sphb200_state_update(sphb200_ctx* ctx, const sphb200_step_options* so, double multiplier, int timeAdvanceOnly);
 int  sphb200_compute_dt(sphb200_ctx* ctx, double cfl, int useVelocityMagnitudeForDt, double* dt, int* reason, uint32_t* node);
 
+/* ---- reflecting-plane boundaries on the device -------------------------------------------
+   planes: nPlanes points and inward normals, ndim doubles each (the stock Noh / Sedov octant: the coordinate planes).
+     sphb200_reflect_set_ghost_nodes   PlanarBoundary::setGhostNodes per plane in order (Integrator/Integrator.cc:415-424,
+                                       Boundary/findNodesTouchingThroughPlanes.cc, Boundary/mapPositionThroughPlanes.hh:17-27):
+                                       discards the current ghosts, selects the control nodes of each plane on the device
+                                       (ascending node order; later planes mirror the ghosts of earlier ones), resizes the node
+                                       set and fills every field present.  Internal state is kept.  One host round trip per plane.
+     sphb200_reflect_apply_ghosts      ReflectingBoundary::applyGhostBoundary (Boundary/ReflectingBoundary.cc:182-250) for the
+                                       masked state fields: scalars copied, vectors R v, tensors R (T R), H (R (H R)).Symmetric().
+                                       The connectivity is kept (the reference refreshes ghost values mid-step on a fixed one).
+     sphb200_reflect_finalize_derivatives  SPHBase::finalizeDerivatives (SPH/SPHBase.cc:502-519): with compatible energy the ghost
+                                       entries of the acceleration (R a) and of DepsDt (copy) are set from their control nodes --
+                                       SpecificThermalEnergyPolicy reads them for the ghost end of an internal-ghost pair
+     sphb200_reflect_enforce           PlanarBoundary::enforceBoundary (Boundary/PlanarBoundary.cc:153-190,
+                                       ReflectingBoundary.cc:255-330): internal nodes behind a plane are mirrored back, their
+                                       velocity reflected.  nViolations may be NULL (then no host synchronisation). */
+int  sphb200_reflect_configure(sphb200_ctx* ctx, int nPlanes, const double* points, const double* normals);
+int  sphb200_reflect_set_ghost_nodes(sphb200_ctx* ctx, size_t* nGhost);
+int  sphb200_reflect_apply_ghosts(sphb200_ctx* ctx, unsigned fieldMask);
+int  sphb200_reflect_finalize_derivatives(sphb200_ctx* ctx);
+int  sphb200_reflect_enforce(sphb200_ctx* ctx, size_t* nViolations);
+
 /* ---- compatible energy -----------------------------------------------------------------------------------------
    replaces: SpecificThermalEnergyPolicy::update (Hydro/SpecificThermalEnergyPolicy.cc:47-174):
    eps += multiplier * (pair-wise discrete work), using the velocity/mass/eps currently on the device and the

@@ -98,7 +98,9 @@ EXPORTS = ("sphb200_abi_version", "sphb200_create", "sphb200_destroy", "sphb200_
            "sphb200_node_bounds_device", "sphb200_halo_select_device",
            "sphb200_crk_compute_volume", "sphb200_crk_compute_corrections", "sphb200_crk_sum_mass_density",
            "sphb200_sum_mass_density", "sphb200_compute_omega_gradh", "sphb200_update_eos_gamma_law", "sphb200_state_copy",
-           "sphb200_state_assign", "sphb200_state_update", "sphb200_compute_dt")
+           "sphb200_state_assign", "sphb200_state_update", "sphb200_compute_dt",
+           "sphb200_reflect_configure", "sphb200_reflect_set_ghost_nodes", "sphb200_reflect_apply_ghosts", "sphb200_reflect_enforce",
+           "sphb200_reflect_finalize_derivatives")
 
 _lib = None
 
@@ -162,5 +164,10 @@ def lib():
     L.sphb200_state_assign.argtypes = [vp]
     L.sphb200_state_update.argtypes = [vp, C.POINTER(StepOptions), C.c_double, C.c_int]
     L.sphb200_compute_dt.argtypes = [vp, C.c_double, C.c_int, _dp, C.POINTER(C.c_int), _u32p]
+    L.sphb200_reflect_configure.argtypes = [vp, C.c_int, _dp, _dp]
+    L.sphb200_reflect_set_ghost_nodes.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.sphb200_reflect_apply_ghosts.argtypes = [vp, C.c_uint]
+    L.sphb200_reflect_enforce.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.sphb200_reflect_finalize_derivatives.argtypes = [vp]
     _lib = L
     return L

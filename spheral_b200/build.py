@@ -12,8 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsphb200.so")
-SOURCES = ["api.cu", "scan.cu", "neighbors.cu", "derivs.cu", "crk.cu", "steps.cu", "energy.cu", "tablekernel_host.cpp"]
-HEADERS = [os.path.join(CSRC, "sphb200_internal.cuh"), os.path.join(CSRC, "pair_common.cuh"), os.path.join(CSRC, "nbr_ring.cuh"), os.path.join(ROOT, "include", "sphb200.h")]
+SOURCES = ["api.cu", "scan.cu", "neighbors.cu", "derivs.cu", "crk.cu", "steps.cu", "boundary.cu", "energy.cu", "tablekernel_host.cpp"]
+HEADERS = [os.path.join(CSRC, "sphb200_internal.cuh"), os.path.join(CSRC, "pair_common.cuh"), os.path.join(CSRC, "nbr_ring.cuh"), os.path.join(CSRC, "sym_eigen.cuh"), os.path.join(ROOT, "include", "sphb200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-ccbin", "/usr/bin/g++",

@@ -31,10 +31,11 @@ __global__ void __launch_bounds__(RB) k_unpermute(const double* __restrict__ src
 }
 // DvDx (sorted SoA) -> api DvDxQ (AoS, original order)
 __global__ void __launch_bounds__(RB) k_copy_dvdx(const double* __restrict__ src, size_t cap, const uint32_t* __restrict__ perm,
-                                                  size_t n, int width, double* __restrict__ dst) {
+                                                  size_t n, size_t nLimit, int width, double* __restrict__ dst) {
   const size_t s = (size_t)blockIdx.x*RB + threadIdx.x;
   if (s >= n) return;
   const size_t o = perm[s];
+  if (o >= nLimit) return;
   for (int q = 0; q < width; ++q) dst[o*width + q] = src[(size_t)q*cap + s];
 }
 __global__ void __launch_bounds__(RB) k_counts_by_orig(const uint32_t* __restrict__ nbrCount, const uint32_t* __restrict__ perm,
@@ -214,6 +215,8 @@ void sphb200_destroy(sphb200_ctx* c) {
                   (void*)c->counters, (void*)c->frows, (void*)c->scanTmp, (void*)c->pacc, (void*)c->stage,
                   (void*)c->runs, (void*)c->tileRunStart, (void*)c->tileRunCount, (void*)c->dilTab, (void*)c->crkVolS, (void*)c->crkCorrS, (void*)c->crkQS, (void*)c->crkAux, (void*)c->permEval, (void*)c->dtCand, (void*)c->dtAux}) cudaFree(p);
   for (int s = 0; s < S_COUNT; ++s) if (c->api0[s]) cudaFree(c->api0[s]);
+  for (int p = 0; p < SPHB200_MAX_PLANES; ++p) if (c->planeCtl[p]) cudaFree(c->planeCtl[p]);
+  if (c->invPerm) cudaFree(c->invPerm);
   cudaFreeHost(c->reduceHost); cudaFreeHost(c->countersHost);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -442,10 +445,14 @@ int sphb200_copy_DvDx_to_Q(sphb200_ctx* c) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
   // node-wise derivatives stay usable after a later build_pairs (permEval keeps the order they are stored in)
   if (!c->derivNodeValid) return sphb200_fail(c, "copy_DvDx_to_Q: derivatives have not been evaluated");
-  if (c->nEval != c->n) return sphb200_fail(c, "copy_DvDx_to_Q: the node count changed since the derivatives were evaluated");
+  if (c->nIntEval != c->nInt) return sphb200_fail(c, "copy_DvDx_to_Q: the internal node count changed since the derivatives were evaluated");
   CU_CHECK(c, cudaSetDevice(c->device));
   if (c->n == 0) return 0;
-  k_copy_dvdx<<<(unsigned)((c->nEval + RB - 1)/RB), RB, 0, c->stream>>>(c->deriv[DV_DVDX], c->capEval, c->permEval, c->nEval, c->ndim*c->ndim, c->api[S_DVDXQ]);
+  // same ghost set as at the evaluation: every node is written (ghost derivatives are zeros); otherwise the internal nodes only,
+  // the ghost entries being the boundary conditions' / halo exchange's to fill (ArtificialViscosityHandle.cc:165-180 + boundaries)
+  const size_t limit = (c->nEval == c->n) ? c->n : c->nInt;
+  if (!c->have[S_DVDXQ]) CU_CHECK(c, cudaMemsetAsync(c->api[S_DVDXQ], 0, c->n*(size_t)(c->ndim*c->ndim)*sizeof(double), c->stream));
+  k_copy_dvdx<<<(unsigned)((c->nEval + RB - 1)/RB), RB, 0, c->stream>>>(c->deriv[DV_DVDX], c->capEval, c->permEval, c->nEval, limit, c->ndim*c->ndim, c->api[S_DVDXQ]);
   KERNEL_CHECK(c, "k_copy_dvdx");
   c->have[S_DVDXQ] = true;
   c->rowsValid = false;

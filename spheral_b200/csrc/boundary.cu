@@ -1,0 +1,343 @@
+// boundary.cu -- reflecting-plane boundary conditions on the device: ghost-node generation,
+// ghost-value refresh and enforcement, so that the stock Noh / Sedov set-ups (reflecting planes through the origin) run with the
+// state resident on the GPU.
+//
+//   sphb200_reflect_set_ghost_nodes   ReflectingBoundary / PlanarBoundary::setGhostNodes, one plane after the other so that later
+//                                     planes mirror the ghosts of earlier ones (Integrator/Integrator.cc:415-424);
+//                                     control nodes by findNodesTouchingThroughPlanes (Boundary/findNodesTouchingThroughPlanes.cc),
+//                                     ghost positions by mapPositionThroughPlanes (Boundary/mapPositionThroughPlanes.hh:17-27)
+//   sphb200_reflect_apply_ghosts      ReflectingBoundary::applyGhostBoundary (Boundary/ReflectingBoundary.cc:182-250): scalars
+//                                     copied, vectors R v, tensors R (T R), symmetric tensors (R (H R)).Symmetric(),
+//                                     R = I - 2 n (x) n (Utilities/planarReflectingOperator.hh:14-19)
+//   sphb200_reflect_enforce           PlanarBoundary::setViolationNodes / enforceBoundary (Boundary/PlanarBoundary.cc:153-190,
+//                                     ReflectingBoundary.cc:255-330): an internal node that crossed a plane is mapped back and its
+//                                     velocity reflected
+//
+// Control lists are built in ascending node order (flags + scan + scatter), so ghost indices are a fixed function of the input.
+#include "sphb200_internal.cuh"
+#include "sym_eigen.cuh"
+#include <algorithm>
+#include <cmath>
+
+namespace {
+
+constexpr int RB = 256;
+
+struct Plane { double p[3]; double n[3]; };
+
+template <int DIM> __device__ __forceinline__ double signed_distance(const Plane& pl, const double* r) {
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < DIM; ++q) s += (r[q] - pl.p[q])*pl.n[q];
+  return s;
+}
+
+// pass 1: hmax = largest 1/min-eigenvalue(H_i) among nodes within kext*hmax_i of the plane (0 <= signed distance)
+template <int DIM>
+__global__ void __launch_bounds__(RB) k_reflect_hmax(const double* __restrict__ pos, const double* __restrict__ H, size_t n, Plane pl,
+                                                     double kext, unsigned long long* __restrict__ hmaxBits) {
+  constexpr int NS = Dm<DIM>::NS;
+  const size_t i = (size_t)blockIdx.x*RB + threadIdx.x;
+  double v = 0.0;
+  if (i < n) {
+    double Hi[NS], r[DIM];
+#pragma unroll
+    for (int q = 0; q < NS; ++q) Hi[q] = H[i*NS + q];
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) r[q] = pos[i*DIM + q];
+    const double hi = 1.0/sym_min_eigenvalue<DIM>(Hi);
+    const double sd = signed_distance<DIM>(pl, r);
+    if (sd >= 0.0 && sd <= kext*hi) v = hi;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, off));
+  if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(hmaxBits, (unsigned long long)__double_as_longlong(v));   // positive doubles order as integers
+}
+// pass 2: control flags 0 <= sd/hmax <= kext
+template <int DIM>
+__global__ void __launch_bounds__(RB) k_reflect_flags(const double* __restrict__ pos, size_t n, Plane pl, double kext,
+                                                      const unsigned long long* __restrict__ hmaxBits, uint32_t* __restrict__ flags) {
+  const size_t i = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (i >= n) return;
+  const double hmax = __longlong_as_double((long long)*hmaxBits);
+  double r[DIM];
+#pragma unroll
+  for (int q = 0; q < DIM; ++q) r[q] = pos[i*DIM + q];
+  const double x = signed_distance<DIM>(pl, r)/hmax;
+  flags[i] = (hmax > 0.0 && x >= 0.0 && x <= kext) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(RB) k_reflect_scatter(const uint32_t* __restrict__ scan, size_t n, uint32_t* __restrict__ ctl, size_t cap) {
+  const size_t i = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (i >= n) return;
+  if (scan[i + 1] != scan[i] && scan[i] < cap) ctl[scan[i]] = (uint32_t)i;
+}
+
+// one field of the ghosts [first, first+count) of a plane from their control nodes
+//   kind 0 scalar copy | 1 position (mirror) | 2 vector R v | 3 tensor R (T R) | 4 symmetric tensor (R (H R)).Symmetric() | 5 any width, copy
+template <int DIM>
+__global__ void __launch_bounds__(RB) k_reflect_fill(double* __restrict__ f, int kind, int width, const uint32_t* __restrict__ ctl,
+                                                     size_t first, size_t count, Plane pl) {
+  const size_t k = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (k >= count) return;
+  const size_t c = ctl[k], g = first + k;
+  const double* s = f + c*(size_t)width;
+  double* d = f + g*(size_t)width;
+  if (kind == 0 || kind == 5) { for (int q = 0; q < width; ++q) d[q] = s[q]; return; }
+  double R[DIM][DIM];
+#pragma unroll
+  for (int a = 0; a < DIM; ++a)
+#pragma unroll
+    for (int b = 0; b < DIM; ++b) R[a][b] = (a == b ? 1.0 : 0.0) - 2.0*pl.n[a]*pl.n[b];
+  if (kind == 1) {                                   // closestPointOnPlane(r) - signedDistance(r) n = r - 2 sd n
+    double r[DIM];
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) r[q] = s[q];
+    const double sd = signed_distance<DIM>(pl, r);
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) d[q] = r[q] - 2.0*sd*pl.n[q];
+  } else if (kind == 2) {
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) { double t = 0.0;
+#pragma unroll
+      for (int b = 0; b < DIM; ++b) t += R[a][b]*s[b];
+      d[a] = t; }
+  } else {
+    double T[DIM][DIM], TR[DIM][DIM], O[DIM][DIM];
+    if (kind == 3) {
+#pragma unroll
+      for (int a = 0; a < DIM; ++a)
+#pragma unroll
+        for (int b = 0; b < DIM; ++b) T[a][b] = s[a*DIM + b];
+    } else if (DIM == 3) {
+      T[0][0] = s[0]; T[0][1] = T[1][0] = s[1]; T[0][2] = T[2][0] = s[2]; T[1][1] = s[3]; T[1][2] = T[2][1] = s[4]; T[2][2] = s[5];
+    } else {
+      T[0][0] = s[0]; T[0][1] = T[1][0] = s[1]; T[1][1] = s[2];
+    }
+#pragma unroll
+    for (int a = 0; a < DIM; ++a)
+#pragma unroll
+      for (int b = 0; b < DIM; ++b) { double t = 0.0;
+#pragma unroll
+        for (int e = 0; e < DIM; ++e) t += T[a][e]*R[e][b];
+        TR[a][b] = t; }
+#pragma unroll
+    for (int a = 0; a < DIM; ++a)
+#pragma unroll
+      for (int b = 0; b < DIM; ++b) { double t = 0.0;
+#pragma unroll
+        for (int e = 0; e < DIM; ++e) t += R[a][e]*TR[e][b];
+        O[a][b] = t; }
+    if (kind == 3) {
+#pragma unroll
+      for (int a = 0; a < DIM; ++a)
+#pragma unroll
+        for (int b = 0; b < DIM; ++b) d[a*DIM + b] = O[a][b];
+    } else if (DIM == 3) {
+      d[0] = O[0][0]; d[1] = 0.5*(O[0][1] + O[1][0]); d[2] = 0.5*(O[0][2] + O[2][0]); d[3] = O[1][1]; d[4] = 0.5*(O[1][2] + O[2][1]); d[5] = O[2][2];
+    } else {
+      d[0] = O[0][0]; d[1] = 0.5*(O[0][1] + O[1][0]); d[2] = O[1][1];
+    }
+  }
+}
+
+// enforceBoundary: internal nodes behind a plane (signed distance < 0) are mirrored back, their velocity reflected
+template <int DIM>
+__global__ void __launch_bounds__(RB) k_reflect_enforce(double* __restrict__ pos, double* __restrict__ vel, size_t nInt, Plane pl,
+                                                        unsigned long long* __restrict__ nViolations) {
+  const size_t i = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (i >= nInt) return;
+  double r[DIM];
+#pragma unroll
+  for (int q = 0; q < DIM; ++q) r[q] = pos[i*DIM + q];
+  const double sd = signed_distance<DIM>(pl, r);
+  if (sd >= 0.0) return;
+  double vn = 0.0;
+#pragma unroll
+  for (int q = 0; q < DIM; ++q) { pos[i*DIM + q] = r[q] - 2.0*sd*pl.n[q]; vn += vel[i*DIM + q]*pl.n[q]; }
+#pragma unroll
+  for (int q = 0; q < DIM; ++q) vel[i*DIM + q] -= 2.0*vn*pl.n[q];
+  atomicAdd(nViolations, 1ull);
+}
+
+// finalizeDerivatives: ghost values of the acceleration (R a) and of DepsDt (copy) in the sorted, component-major derivative arrays
+__global__ void __launch_bounds__(RB) k_inverse_perm(const uint32_t* __restrict__ perm, size_t n, uint32_t* __restrict__ inv) {
+  const size_t s = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (s < n) inv[perm[s]] = (uint32_t)s;
+}
+template <int DIM>
+__global__ void __launch_bounds__(RB) k_reflect_derivs(double* __restrict__ DvDt, double* __restrict__ DepsDt, size_t cap,
+                                                       const uint32_t* __restrict__ inv, const uint32_t* __restrict__ ctl,
+                                                       size_t first, size_t count, Plane pl) {
+  const size_t k = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (k >= count) return;
+  const size_t sc = inv[ctl[k]], sg = inv[first + k];
+  double a[DIM], an = 0.0;
+#pragma unroll
+  for (int q = 0; q < DIM; ++q) { a[q] = DvDt[(size_t)q*cap + sc]; an += a[q]*pl.n[q]; }
+#pragma unroll
+  for (int q = 0; q < DIM; ++q) DvDt[(size_t)q*cap + sg] = a[q] - 2.0*an*pl.n[q];
+  DepsDt[sg] = DepsDt[sc];
+}
+
+int field_kind(int ndim, int slot) {
+  switch (slot) {
+    case S_POS: return 1; case S_VEL: return 2; case S_H: return 4; case S_DVDXQ: return 3; case S_RKCORR: return 5;
+    default: return 0;
+  }
+}
+Plane plane_of(const sphb200_ctx* c, int p) {
+  Plane pl{};
+  for (int q = 0; q < 3; ++q) { pl.p[q] = c->planes[6*p + q]; pl.n[q] = c->planes[6*p + 3 + q]; }
+  return pl;
+}
+int fill_plane(sphb200_ctx* c, int p, unsigned mask) {
+  const size_t first = c->planeFirst[p], count = c->planeCount[p];
+  if (count == 0) return 0;
+  const Plane pl = plane_of(c, p);
+  const unsigned nb = (unsigned)((count + RB - 1)/RB);
+  for (int s = 0; s < S_COUNT; ++s) {
+    if (!(mask & (1u << s)) || !c->have[s] || !c->api[s]) continue;
+    const int kind = field_kind(c->ndim, s), w = sphb200_state_width(c->ndim, s);
+    if (c->ndim == 3) k_reflect_fill<3><<<nb, RB, 0, c->stream>>>(c->api[s], kind, w, c->planeCtl[p], first, count, pl);
+    else              k_reflect_fill<2><<<nb, RB, 0, c->stream>>>(c->api[s], kind, w, c->planeCtl[p], first, count, pl);
+    KERNEL_CHECK(c, "k_reflect_fill");
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sphb200_reflect_configure(sphb200_ctx* c, int nPlanes, const double* points, const double* normals) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  if (nPlanes < 0 || nPlanes > SPHB200_MAX_PLANES) return sphb200_fail(c, "reflect_configure: between 0 and 6 planes are supported");
+  if (nPlanes && (!points || !normals)) return sphb200_fail(c, "reflect_configure: null plane data");
+  for (int p = 0; p < nPlanes; ++p) {
+    double nn = 0.0;
+    for (int q = 0; q < c->ndim; ++q) nn += normals[p*c->ndim + q]*normals[p*c->ndim + q];
+    if (!(nn > 0.0)) return sphb200_fail(c, "reflect_configure: zero plane normal");
+    nn = std::sqrt(nn);
+    for (int q = 0; q < 3; ++q) {
+      c->planes[6*p + q] = q < c->ndim ? points[p*c->ndim + q] : 0.0;
+      c->planes[6*p + 3 + q] = q < c->ndim ? normals[p*c->ndim + q]/nn : 0.0;       // unit normal, pointing into the domain
+    }
+    c->planeFirst[p] = c->planeCount[p] = 0;
+  }
+  c->nPlanes = nPlanes;
+  return 0;
+}
+
+int sphb200_reflect_set_ghost_nodes(sphb200_ctx* c, size_t* nGhostOut) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (!c->have[S_POS] || !c->have[S_H]) return sphb200_fail(c, "reflect_set_ghost_nodes: position and H must be on the device");
+  if (!c->W.set) return sphb200_fail(c, "reflect_set_ghost_nodes: kernel table not set (need the kernel extent)");
+  const double kext = std::max(c->W.kext, c->WQ.set ? c->WQ.kext : 0.0);
+  // start from the internal nodes alone: previous ghosts are discarded (Integrator::setGhostNodes, Integrator.cc:389-397)
+  if (sphb200_set_nodes(c, c->nInt, 0)) return 1;
+  unsigned mask = 0;
+  for (int s = 0; s < S_COUNT; ++s) if (c->have[s] && c->api[s]) mask |= 1u << s;
+  for (int p = 0; p < c->nPlanes; ++p) {
+    const size_t n = c->n;
+    const Plane pl = plane_of(c, p);
+    c->planeFirst[p] = n; c->planeCount[p] = 0;
+    if (n == 0) continue;
+    if (sphb200_ensure(c, c->planeCtl[p], c->planeCtlCap[p], n + n/8 + 32)) return 1;
+    // flags live in the download staging area: n+1 counters + one 64-bit cell for hmax
+    const size_t need = (n + 4)*sizeof(uint32_t) + 16;
+    if (need > c->stageBytes) {
+      CU_CHECK(c, cudaStreamSynchronize(c->stream));
+      if (c->stage) cudaFree(c->stage);
+      c->stage = nullptr; c->stageBytes = 0;
+      CU_CHECK(c, cudaMalloc((void**)&c->stage, need + need/8));
+      c->stageBytes = need + need/8;
+    }
+    unsigned long long* hmaxBits = (unsigned long long*)c->stage;
+    uint32_t* flags = (uint32_t*)(hmaxBits + 2);
+    CU_CHECK(c, cudaMemsetAsync(hmaxBits, 0, 16, c->stream));
+    const unsigned nb = (unsigned)((n + RB - 1)/RB);
+    if (c->ndim == 3) k_reflect_hmax<3><<<nb, RB, 0, c->stream>>>(c->api[S_POS], c->api[S_H], n, pl, kext, hmaxBits);
+    else              k_reflect_hmax<2><<<nb, RB, 0, c->stream>>>(c->api[S_POS], c->api[S_H], n, pl, kext, hmaxBits);
+    KERNEL_CHECK(c, "k_reflect_hmax");
+    if (c->ndim == 3) k_reflect_flags<3><<<nb, RB, 0, c->stream>>>(c->api[S_POS], n, pl, kext, hmaxBits, flags);
+    else              k_reflect_flags<2><<<nb, RB, 0, c->stream>>>(c->api[S_POS], n, pl, kext, hmaxBits, flags);
+    KERNEL_CHECK(c, "k_reflect_flags");
+    if (sphb200_scan_u32(c, flags, flags, n)) return 1;
+    k_reflect_scatter<<<nb, RB, 0, c->stream>>>(flags, n, c->planeCtl[p], c->planeCtlCap[p]);
+    KERNEL_CHECK(c, "k_reflect_scatter");
+    uint32_t count = 0;
+    CU_CHECK(c, cudaMemcpyAsync(&count, flags + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (count > c->planeCtlCap[p]) return sphb200_fail(c, "reflect_set_ghost_nodes: internal control list too small");
+    c->planeCount[p] = count;
+    if (count == 0) continue;
+    if (sphb200_set_nodes(c, c->nInt, c->nGhost + count)) return 1;       // state of the existing nodes is kept
+    if (fill_plane(c, p, mask)) return 1;
+  }
+  c->sortValid = c->rowsValid = c->pairsValid = false;
+  if (nGhostOut) *nGhostOut = c->nGhost;
+  return 0;
+}
+
+int sphb200_reflect_apply_ghosts(sphb200_ctx* c, unsigned fieldMask) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  size_t total = 0;
+  for (int p = 0; p < c->nPlanes; ++p) total += c->planeCount[p];
+  if (total != c->nGhost) return sphb200_fail(c, "reflect_apply_ghosts: the ghost nodes were not generated by reflect_set_ghost_nodes (or the node count changed since)");
+  for (int p = 0; p < c->nPlanes; ++p) if (fill_plane(c, p, fieldMask)) return 1;      // in order: later planes mirror earlier ghosts
+  // ghost values changed under a fixed connectivity (the reference refreshes ghosts mid-step without a neighbour update)
+  c->rowsValid = false;
+  return 0;
+}
+
+int sphb200_reflect_finalize_derivatives(sphb200_ctx* c) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (!c->derivsValid || !c->pairsValid) return sphb200_fail(c, "reflect_finalize_derivatives: derivatives have not been evaluated on the current connectivity");
+  size_t total = 0;
+  for (int p = 0; p < c->nPlanes; ++p) total += c->planeCount[p];
+  if (total != c->nGhost) return sphb200_fail(c, "reflect_finalize_derivatives: the ghost nodes were not generated by reflect_set_ghost_nodes");
+  if (total == 0) return 0;
+  if (sphb200_ensure(c, c->invPerm, c->invPermCap, c->cap)) return 1;
+  k_inverse_perm<<<(unsigned)((c->n + RB - 1)/RB), RB, 0, c->stream>>>(c->perm, c->n, c->invPerm);
+  KERNEL_CHECK(c, "k_inverse_perm");
+  for (int p = 0; p < c->nPlanes; ++p) {
+    const size_t count = c->planeCount[p];
+    if (count == 0) continue;
+    const Plane pl = plane_of(c, p);
+    const unsigned nb = (unsigned)((count + RB - 1)/RB);
+    if (c->ndim == 3) k_reflect_derivs<3><<<nb, RB, 0, c->stream>>>(c->deriv[DV_DVDT], c->deriv[DV_DEPSDT], c->cap, c->invPerm, c->planeCtl[p], c->planeFirst[p], count, pl);
+    else              k_reflect_derivs<2><<<nb, RB, 0, c->stream>>>(c->deriv[DV_DVDT], c->deriv[DV_DEPSDT], c->cap, c->invPerm, c->planeCtl[p], c->planeFirst[p], count, pl);
+    KERNEL_CHECK(c, "k_reflect_derivs");
+  }
+  return 0;
+}
+
+int sphb200_reflect_enforce(sphb200_ctx* c, size_t* nViolations) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (!c->have[S_POS] || !c->have[S_VEL]) return sphb200_fail(c, "reflect_enforce: position and velocity must be on the device");
+  if (nViolations) *nViolations = 0;
+  if (c->nInt == 0 || c->nPlanes == 0) return 0;
+  CU_CHECK(c, cudaMemsetAsync(c->counters + 7, 0, sizeof(unsigned long long), c->stream));
+  const unsigned nb = (unsigned)((c->nInt + RB - 1)/RB);
+  for (int p = 0; p < c->nPlanes; ++p) {
+    const Plane pl = plane_of(c, p);
+    if (c->ndim == 3) k_reflect_enforce<3><<<nb, RB, 0, c->stream>>>(c->api[S_POS], c->api[S_VEL], c->nInt, pl, c->counters + 7);
+    else              k_reflect_enforce<2><<<nb, RB, 0, c->stream>>>(c->api[S_POS], c->api[S_VEL], c->nInt, pl, c->counters + 7);
+    KERNEL_CHECK(c, "k_reflect_enforce");
+  }
+  c->rowsValid = false;
+  if (nViolations) {
+    unsigned long long v = 0;
+    CU_CHECK(c, cudaMemcpyAsync(&v, c->counters + 7, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    *nViolations = (size_t)v;
+    if (v) { c->sortValid = false; c->pairsValid = false; }
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -20,6 +20,7 @@
 #include "sphb200.h"
 
 #define SPHB200_TILE 32
+#define SPHB200_MAX_PLANES 6
 #define SPHB200_DIL 32768          /* entries per axis of the dilated-coordinate table (max cells per axis) */
 
 enum StateSlot { S_POS = 0, S_VEL, S_H, S_MASS, S_RHO, S_EPS, S_P, S_CS, S_OMEGA, S_DVDXQ, S_FCL, S_FCQ, S_VOLUME, S_RKCORR, S_COUNT };
@@ -132,6 +133,11 @@ struct sphb200_ctx {
   bool derivNodeValid = false;
   // state0 of the integrator (State::copyState, CheapSynchronousRK2.cc:70-71)
   double* api0[S_COUNT] = {nullptr}; size_t cap0[S_COUNT] = {0}; bool have0[S_COUNT] = {false}; size_t n0 = 0;
+  // reflecting planes (boundary.cu): {point[3], unit normal[3]} per plane, the ghost range and the control list of each
+  int nPlanes = 0; double planes[6*SPHB200_MAX_PLANES] = {0};
+  size_t planeFirst[SPHB200_MAX_PLANES] = {0}, planeCount[SPHB200_MAX_PLANES] = {0};
+  uint32_t* planeCtl[SPHB200_MAX_PLANES] = {nullptr}; size_t planeCtlCap[SPHB200_MAX_PLANES] = {0};
+  uint32_t* invPerm = nullptr; size_t invPermCap = 0;      // original index -> sorted slot (built on demand)
   // time-step reduction scratch
   unsigned long long* dtCand = nullptr; size_t dtCandCap = 0;
   double* dtAux = nullptr; size_t dtAuxCap = 0;

@@ -245,6 +245,34 @@ class Engine:
                                                  C.byref(node)))
         return dt.value, (L.DT_REASONS[reason.value] if reason.value >= 0 else ""), node.value
 
+    # -- reflecting planes on the device -----------------------------------------------------------------
+    def reflect_configure(self, planes):
+        """planes: list of (point, inward normal)."""
+        pts = np.ascontiguousarray([p for p, _ in planes], dtype=np.float64).reshape(-1)
+        nrm = np.ascontiguousarray([n for _, n in planes], dtype=np.float64).reshape(-1)
+        self._check(self._lib.sphb200_reflect_configure(self._h, len(planes), _dp(pts) if len(planes) else None,
+                                                        _dp(nrm) if len(planes) else None))
+
+    def reflect_set_ghost_nodes(self):
+        """PlanarBoundary::setGhostNodes for every plane; returns (and records) the new ghost count."""
+        ng = C.c_size_t()
+        self._check(self._lib.sphb200_reflect_set_ghost_nodes(self._h, C.byref(ng)))
+        self.nGhost = ng.value
+        return self.nGhost
+
+    def reflect_apply_ghosts(self, mask=None):
+        """ReflectingBoundary::applyGhostBoundary for the masked state fields (default: every field on the device)."""
+        self._check(self._lib.sphb200_reflect_apply_ghosts(self._h, 0xFFFFFFFF if mask is None else mask))
+
+    def reflect_finalize_derivatives(self):
+        """SPHBase::finalizeDerivatives: ghost values of DvDt and DepsDt (needed by the compatible energy update)."""
+        self._check(self._lib.sphb200_reflect_finalize_derivatives(self._h))
+
+    def reflect_enforce(self, count=False):
+        nv = C.c_size_t()
+        self._check(self._lib.sphb200_reflect_enforce(self._h, C.byref(nv) if count else None))
+        return nv.value
+
     # -- halo ----------------------------------------------------------------------------------------------------------
     def halo_bytes_per_node(self, mask):
         return self._lib.sphb200_halo_bytes_per_node(self._h, mask)

@@ -18,7 +18,7 @@ INTEGRATE_DENSITY, RIGOROUS_SUM_DENSITY = 0, 1      # MassDensityType (Hydro/Gen
 class CheapSynchronousRK2:
     def __init__(self, engine, step_options=None, densityUpdate=RIGOROUS_SUM_DENSITY, gradhCorrection=True, cfl=0.25,
                  useVelocityMagnitudeForDt=False, dtMin=0.0, dtMax=1.0e100, dtGrowth=2.0, allowDtCheck=False,
-                 ghostRefresh=None):
+                 ghostRefresh=None, reflectingPlanes=None):
         self.engine = engine
         self.so = step_options if step_options is not None else E.make_step_options()
         self.densityUpdate, self.gradhCorrection = densityUpdate, gradhCorrection
@@ -28,6 +28,10 @@ class CheapSynchronousRK2:
         # applyGhostBoundaries + finalizeGhostBoundaries: a callable refreshing the ghost entries on the device (halo exchange);
         # None for a problem without ghost nodes
         self.ghostRefresh = ghostRefresh
+        # reflecting planes handled on the device (ReflectingBoundary): list of (point, inward normal)
+        self.reflectingPlanes = reflectingPlanes
+        if reflectingPlanes:
+            engine.reflect_configure(reflectingPlanes)
         self.currentTime, self.currentCycle, self.lastDt = 0.0, 0, 1.0e100
         self.dtMultiplier = 1.0
         self.lastDtReason, self.lastDtNode = "", 0
@@ -35,6 +39,21 @@ class CheapSynchronousRK2:
 
     # -- pieces of a stage -----------------------------------------------------------------------------------------------
     def _ghosts(self):
+        """applyGhostBoundaries + finalizeGhostBoundaries (Integrator.cc:530-600)."""
+        if self.reflectingPlanes:
+            self.engine.reflect_apply_ghosts()
+        if self.ghostRefresh is not None:
+            self.ghostRefresh()
+
+    def _finalize_derivatives(self):
+        """SPHBase::finalizeDerivatives (SPHBase.cc:502-519): boundary conditions on DvDt and DepsDt for the compatible energy."""
+        if self.reflectingPlanes and self.engine.options.compatibleEnergy:
+            self.engine.reflect_finalize_derivatives()
+
+    def _set_ghost_nodes(self):
+        """Integrator::setGhostNodes (Integrator.cc:372-445): regenerate the ghost nodes, then refresh their values."""
+        if self.reflectingPlanes:
+            self.engine.reflect_set_ghost_nodes()
         if self.ghostRefresh is not None:
             self.ghostRefresh()
 
@@ -62,6 +81,7 @@ class CheapSynchronousRK2:
         """The first evaluation of a run: CheapSynchronousRK2 advances the trial state with the previous step's derivatives,
         so a fresh problem needs one (the reference does this in SpheralController.reinitializeProblem -> evaluateDerivatives)."""
         e = self.engine
+        self._set_ghost_nodes()
         e.build_pairs()
         if self.densityUpdate == RIGOROUS_SUM_DENSITY:
             e.sum_mass_density()
@@ -70,6 +90,7 @@ class CheapSynchronousRK2:
             e.compute_omega_gradh()
         self._ghosts()
         e.evaluate_derivatives(self.currentTime, 0.0)
+        self._finalize_derivatives()
 
     # -- one step ----------------------------------------------------------------------------------------------------------
     def _try_step(self, maxTime):
@@ -90,6 +111,7 @@ class CheapSynchronousRK2:
         self._post_state_update()
         # derivatives at the mid point, on the connectivity of the step start
         e.evaluate_derivatives(t + hdt, hdt)
+        self._finalize_derivatives()
         if self.allowDtCheck:
             dtnew = self.selectDt(min(self.dtMin, maxTime - t), min(self.dtMax, maxTime - t))
             if dtnew < 0.5*dt:
@@ -101,13 +123,15 @@ class CheapSynchronousRK2:
         self.currentTime = t + dt
         self._ghosts()
         self._post_state_update()
+        if self.reflectingPlanes:
+            e.reflect_enforce()                       # enforceBoundaries (CheapSynchronousRK2.cc:121-123)
         self.currentCycle += 1
         self.lastDt = dt
         return True
 
     def step(self, maxTime=1.0e100):
         """Integrator::step(maxTime) (Integrator.cc:66-111): neighbour update, then up to 10 attempts with a halved dt."""
-        self._ghosts()                                # setGhostNodes
+        self._set_ghost_nodes()                       # setGhostNodes
         self.engine.build_pairs()                     # Neighbor::updateNodes + ConnectivityMap::computeConnectivity
         ok, count = False, 0
         allow = self.allowDtCheck

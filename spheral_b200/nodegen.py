@@ -135,7 +135,37 @@ def gamma_law(rho, eps, gamma=5.0/3.0):
     return P, cs
 
 
-def reflect_ghosts(ndim, fields, planes, kext):
+def reflect_map(ndim, name, c, sd, nhat):
+    """Ghost values of one field from its control values c (ReflectingBoundary::applyGhostBoundary,
+    Boundary/ReflectingBoundary.cc:182-250; positions by mapPositionThroughPlanes)."""
+    R = np.eye(ndim) - 2.0*np.outer(nhat, nhat)
+    if name == "pos":
+        return c - 2.0*np.outer(sd, nhat)                       # closest point on plane minus signed distance
+    if name == "H":
+        Fr = np.einsum("ab,nbc,cd->nad", R, sym_to_full(ndim, c), R)
+        return full_to_sym(ndim, 0.5*(Fr + np.transpose(Fr, (0, 2, 1))))
+    if c.ndim == 2 and c.shape[1] == ndim:                      # vectors
+        return c @ R.T
+    if c.ndim == 2 and c.shape[1] == ndim*ndim:                 # tensors R.(T.R)
+        return np.einsum("ab,nbc,cd->nad", R, c.reshape(-1, ndim, ndim), R).reshape(-1, ndim*ndim)
+    return c.copy()                                             # scalars (and any other width): copy
+
+
+def reflect_apply(ndim, fields, planes, ctl_per_plane, n0):
+    """Refresh the ghost entries of `fields` (arrays of n0 internal + ghosts, ghosts laid out plane after plane) from their
+    control nodes, plane by plane so that later planes see the refreshed ghosts of earlier ones."""
+    first = n0
+    for (point, normal), ctl in zip(planes, ctl_per_plane):
+        nhat = np.asarray(normal, dtype=float)
+        nhat = nhat/np.linalg.norm(nhat)
+        sd = (fields["pos"][ctl] - np.asarray(point, dtype=float)) @ nhat
+        for k, v in fields.items():
+            v[first:first + len(ctl)] = reflect_map(ndim, k, v[ctl], sd, nhat)
+        first += len(ctl)
+    return fields
+
+
+def reflect_ghosts(ndim, fields, planes, kext, per_plane=False):
     """Append reflecting-boundary ghosts for axis-aligned or general planes, applied sequentially so that later
     planes also mirror earlier ghosts (Integrator.cc:415-424).
 
@@ -144,7 +174,7 @@ def reflect_ghosts(ndim, fields, planes, kext):
     Returns (fields_with_ghosts, control_index array for the ghosts)."""
     out = {k: np.array(v, dtype=float, copy=True) for k, v in fields.items()}
     n0 = out["pos"].shape[0]
-    control = []
+    control, lists = [], []
     for point, normal in planes:
         point = np.asarray(point, dtype=float)
         nhat = np.asarray(normal, dtype=float)
@@ -155,6 +185,7 @@ def reflect_ghosts(ndim, fields, planes, kext):
         sd = (pos - point) @ nhat                               # signed distance
         near = (sd >= 0.0) & (sd <= kext*hmax_i)
         if not near.any():
+            lists.append(np.zeros(0, dtype=np.int64))
             continue
         hmax = hmax_i[near].max()
         ctl = np.nonzero((sd/hmax >= 0.0) & (sd/hmax <= kext))[0]
@@ -178,4 +209,7 @@ def reflect_ghosts(ndim, fields, planes, kext):
         for k in out:
             out[k] = np.concatenate([out[k], new[k]], axis=0)
         control.extend(ctl.tolist())
+        lists.append(ctl)
+    if per_plane:
+        return out, lists, n0
     return out, np.array(control, dtype=np.int64), n0

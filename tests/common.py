@@ -102,14 +102,17 @@ def physical_floors(st, nInt, ndim):
 
 # ---- CheapSynchronousRK2 driven through the oracle (the checker of spheral_b200/integrator.py) -----------------------------
 class OracleRK2:
-    """Same stage sequence as CheapSynchronousRK2.cc:40-132, every piece an oracle call.  No ghost nodes."""
+    """Same stage sequence as CheapSynchronousRK2.cc:40-132, every piece an oracle call.  Optional reflecting planes
+    (ghosts regenerated every step by nodegen.reflect_ghosts, refreshed by nodegen.reflect_apply)."""
 
-    def __init__(self, orc, oo, so, OT, st, densityUpdate=1, gradhCorrection=True, dtMin=0.0, dtMax=1.0e100, dtGrowth=2.0):
+    def __init__(self, orc, oo, so, OT, st, densityUpdate=1, gradhCorrection=True, dtMin=0.0, dtMax=1.0e100, dtGrowth=2.0,
+                 planes=None, nInt=None):
         self.orc, self.oo, self.so, self.OT = orc, oo, so, OT
         self.ndim = oo.ndim
-        self.s = {k: np.array(v, dtype=np.float64, copy=True) for k, v in to_oracle_state(st).items()}
-        self.s["eps"] = np.array(st["specificThermalEnergy"], dtype=np.float64, copy=True)
-        self.N = self.s["pos"].shape[0]
+        self.N = st["position"].shape[0] if nInt is None else nInt
+        self.s = {k: np.array(v[:self.N], dtype=np.float64, copy=True) for k, v in to_oracle_state(st).items()}
+        self.s["eps"] = np.array(st["specificThermalEnergy"][:self.N], dtype=np.float64, copy=True)
+        self.nGhost, self.planes, self.ctl = 0, planes, None
         self.densityUpdate, self.gradhCorrection = densityUpdate, gradhCorrection
         self.dtMin, self.dtMax, self.dtGrowth = dtMin, dtMax, dtGrowth
         self.t, self.cycle, self.lastDt = 0.0, 0, 1.0e100
@@ -117,39 +120,72 @@ class OracleRK2:
         self.derivs = None
         self.reason, self.node = "", 0
 
+    # -- boundaries ------------------------------------------------------------------------------------------------------
+    def _set_ghosts(self):
+        if not self.planes:
+            return
+        inner = {k: v[:self.N] for k, v in self.s.items()}
+        out, self.ctl, n0 = ng.reflect_ghosts(self.ndim, inner, self.planes, self.OT.kext, per_plane=True)
+        self.s = out
+        self.nGhost = out["pos"].shape[0] - self.N
+
+    def _apply_ghosts(self):
+        if self.planes:
+            ng.reflect_apply(self.ndim, self.s, self.planes, self.ctl, self.N)
+
+    def _enforce(self):
+        if not self.planes:
+            return
+        for point, normal in self.planes:
+            nhat = np.asarray(normal, dtype=float)/np.linalg.norm(normal)
+            sd = (self.s["pos"][:self.N] - np.asarray(point, dtype=float)) @ nhat
+            bad = np.nonzero(sd < 0.0)[0]
+            self.s["pos"][bad] -= 2.0*np.outer(sd[bad], nhat)
+            self.s["vel"][bad] -= 2.0*np.outer(self.s["vel"][bad] @ nhat, nhat)
+
+    # -- pieces ------------------------------------------------------------------------------------------------------------
     def _pairs(self):
-        self.pi, self.pj, self.cnt = self.orc.pairs(self.ndim, self.N, 0, self.s["pos"], self.s["H"], self.OT.kext)
+        self.pi, self.pj, self.cnt = self.orc.pairs(self.ndim, self.N, self.nGhost, self.s["pos"], self.s["H"], self.OT.kext)
 
     def _sum_density(self):
-        self.s["rho"] = self.orc.sum_mass_density(self.ndim, self.OT, self.N, 0, self.s["pos"], self.s["mass"], self.s["H"],
+        self.s["rho"] = self.orc.sum_mass_density(self.ndim, self.OT, self.N, self.nGhost, self.s["pos"], self.s["mass"], self.s["H"],
                                                   self.pi, self.pj, rho=self.s["rho"])
 
     def _eos(self):
         self.s["P"], self.s["cs"] = self.orc.eos_gamma_law(self.so, self.s["rho"], self.s["eps"])
 
     def _omega(self):
-        self.s["omega"] = self.orc.omega_gradh(self.ndim, self.OT, self.N, 0, self.s["pos"], self.s["H"], self.pi, self.pj,
+        self.s["omega"] = self.orc.omega_gradh(self.ndim, self.OT, self.N, self.nGhost, self.s["pos"], self.s["H"], self.pi, self.pj,
                                                self.cnt, omega=self.s["omega"])
 
     def _evaluate(self):
-        self.derivs = self.orc.evaluate_derivatives(self.oo, self.OT, self.s, self.N, 0, self.pi, self.pj, self.cnt)
+        self.derivs = self.orc.evaluate_derivatives(self.oo, self.OT, self.s, self.N, self.nGhost, self.pi, self.pj, self.cnt)
         self.pairs_eval = (self.pi, self.pj)
+        if self.planes and self.oo.compatibleEnergy:
+            # SPHBase::finalizeDerivatives (SPHBase.cc:502-519): ghost values of the acceleration and the energy derivative,
+            # which SpecificThermalEnergyPolicy reads for the ghost end of an internal-ghost pair
+            f = dict(pos=self.s["pos"], DvDt=self.derivs["DvDt"], DepsDt=self.derivs["DepsDt"])
+            ng.reflect_apply(self.ndim, f, self.planes, self.ctl, self.N)
 
     def _post_state_update(self):
         if self.needQ:
-            self.s["DvDxQ"] = np.array(self.derivs["DvDx"], copy=True)
+            q = np.zeros((self.N + self.nGhost, self.ndim*self.ndim))
+            q[:self.N] = self.derivs["DvDx"][:self.N]
+            self.s["DvDxQ"] = q
+            self._apply_ghosts()
         if self.gradhCorrection:
             self._omega()
+            self._apply_ghosts()
 
     def _update(self, mult, timeAdvanceOnly):
         d = self.derivs
         epsDone = False
         if self.oo.compatibleEnergy and not timeAdvanceOnly:
             pi, pj = self.pairs_eval
-            self.s["eps"] = self.orc.update_energy_compatible(self.ndim, self.N, 0, self.s["mass"], self.s["vel"], d["DvDt"],
+            self.s["eps"] = self.orc.update_energy_compatible(self.ndim, self.N, self.nGhost, self.s["mass"], self.s["vel"], d["DvDt"],
                                                               d["DepsDt"], pi, pj, d["pairAccelerations"], mult, self.s["eps"])
             epsDone = True
-        out = self.orc.state_update(self.oo, self.so, self.N, 0, mult, timeAdvanceOnly, d, self.s, epsDone=epsDone)
+        out = self.orc.state_update(self.oo, self.so, self.N, self.nGhost, mult, timeAdvanceOnly, d, self.s, epsDone=epsDone)
         self.s.update(out)
 
     def _select_dt(self, maxTime):
@@ -162,34 +198,52 @@ class OracleRK2:
         dt = min(dt, self.dtGrowth*self.lastDt)
         return min(dtMax, max(dtMin, dt))
 
+    def _pad_derivs(self):
+        """Derivatives of the previous step live on the internal nodes; the ghost set may have changed since."""
+        n = self.N + self.nGhost
+        for k, v in list(self.derivs.items()):
+            if k == "pairAccelerations" or v.shape[0] == n:
+                continue
+            w = np.zeros((n,) + v.shape[1:])
+            w[:self.N] = v[:self.N]
+            self.derivs[k] = w
+
     def initializeDerivatives(self):
+        self._set_ghosts()
         self._pairs()
         if self.densityUpdate == 1:
             self._sum_density()
         self._eos()
         if self.gradhCorrection:
             self._omega()
+        self._apply_ghosts()
         self._evaluate()
 
     def step(self, maxTime=1.0e100):
+        self._set_ghosts()
+        self._pad_derivs()
         self._pairs()
         if self.densityUpdate == 1:
             self._sum_density()
             self._eos()
+            self._apply_ghosts()
         dt = self._select_dt(maxTime)
         hdt = 0.5*dt
         s0 = {k: np.array(v, copy=True) for k, v in self.s.items()}
         self._update(hdt, True)
+        self._apply_ghosts()
         self._post_state_update()
         self._evaluate()
         self.s = s0                 # state.assign(state0) restores every registered field, the Q gradient and omega included
         self._update(dt, False)
         self.t += dt
+        self._apply_ghosts()
         self._post_state_update()
+        self._enforce()
         self.cycle += 1
         self.lastDt = dt
         return dt
 
     def total_energy(self):
-        m, v, e = self.s["mass"], self.s["vel"], self.s["eps"]
+        m, v, e = self.s["mass"][:self.N], self.s["vel"][:self.N], self.s["eps"][:self.N]
         return float(np.sum(m*(0.5*np.sum(v*v, axis=1) + e)))
