@@ -122,7 +122,20 @@ int alloc_nodes(sphb200_ctx* c, size_t n) {
   if (reall(c->aux2, cap*2)) return 1;
   if (crk && (reall(c->crkVolS, cap) || reall(c->crkCorrS, cap*(size_t)(c->ndim == 3 ? 16 : 10)) ||
               reall(c->crkQS, cap*(size_t)(c->ndim == 3 ? 10 : 6)) || reall(c->crkAux, cap*2))) return 1;
-  for (int s = 0; s < DV_COUNT; ++s) if (reall(c->deriv[s], cap*(size_t)sphb200_deriv_width(c->ndim, s))) return 1;
+  // node-wise derivatives survive a growth of the node set (the ghost count changes from step to step while the integrator
+  // still needs the previous evaluation): component c of a field moves from stride capEval to stride cap
+  const bool keepDerivs = c->derivNodeValid && c->nEval > 0;
+  for (int s = 0; s < DV_COUNT; ++s) {
+    const int w = sphb200_deriv_width(c->ndim, s);
+    double* p = nullptr;
+    CU_CHECK(c, cudaMalloc((void**)&p, cap*(size_t)w*sizeof(double)));
+    if (keepDerivs && c->deriv[s])
+      for (int q = 0; q < w; ++q)
+        CU_CHECK(c, cudaMemcpyAsync(p + (size_t)q*cap, c->deriv[s] + (size_t)q*c->capEval, c->nEval*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    if (c->deriv[s]) { CU_CHECK(c, cudaStreamSynchronize(c->stream)); cudaFree(c->deriv[s]); }
+    c->deriv[s] = p;
+  }
+  if (keepDerivs) c->capEval = cap;
   auto reall32 = [&](uint32_t*& p, size_t cnt) -> int {
     if (p) cudaFree(p);
     p = nullptr;
@@ -140,7 +153,7 @@ int alloc_nodes(sphb200_ctx* c, size_t n) {
   if (c->frows) { cudaFree(c->frows); c->frows = nullptr; c->frowsCap = 0; }
   c->cap = cap;
   c->sortValid = c->rowsValid = c->pairsValid = c->derivsValid = false;
-  c->derivNodeValid = false;
+  if (!keepDerivs) c->derivNodeValid = false;
   return 0;
 }
 

@@ -490,7 +490,9 @@ int sphb200_state_assign(sphb200_ctx* c) {
 int sphb200_compute_dt(sphb200_ctx* c, double cfl, int useVelocityMagnitudeForDt, double* dt, int* reason, uint32_t* node) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
   CU_CHECK(c, cudaSetDevice(c->device));
-  if (!c->derivNodeValid) return sphb200_fail(c, "compute_dt: no derivatives on the device (call evaluate_derivatives first)");
+  if (!c->derivNodeValid)
+    return sphb200_fail(c, "compute_dt: no derivatives on the device (call evaluate_derivatives first; a growth of the node arrays discards them: n = " +
+                        std::to_string(c->n) + ", capacity " + std::to_string(c->cap) + ", at the evaluation " + std::to_string(c->nEval) + " / " + std::to_string(c->capEval) + ")");
   if (c->nIntEval != c->nInt) return sphb200_fail(c, "compute_dt: the internal node count changed since the derivatives were evaluated");
   for (int s : {S_VEL, S_H, S_RHO, S_CS})
     if (!c->have[s]) return sphb200_fail(c, "compute_dt: velocity, H, mass density and sound speed must be on the device");
