@@ -208,9 +208,10 @@ int sphb200_create(sphb200_ctx** out, int device, const sphb200_options* opts) {
   for (auto& ev : c->ev) cudaEventCreate(&ev);
   cudaMalloc((void**)&c->reduceBuf, (296*9 + 16)*sizeof(double));
   cudaMallocHost((void**)&c->reduceHost, 16*sizeof(double));
-  cudaMalloc((void**)&c->counters, 8*sizeof(unsigned long long));
+  cudaMalloc((void**)&c->counters, 16*sizeof(unsigned long long));      // [0,8) neighbour build, [8] anisotropy flag of k_pack
+  cudaMemset(c->counters, 0, 16*sizeof(unsigned long long));
   cudaMalloc((void**)&c->dilTab, 3*SPHB200_DIL*sizeof(uint32_t));
-  cudaMallocHost((void**)&c->countersHost, 8*sizeof(unsigned long long));
+  cudaMallocHost((void**)&c->countersHost, 16*sizeof(unsigned long long));
   if (cudaGetLastError() != cudaSuccess) { sphb200_destroy(c); return sphb200_fail(nullptr, "context allocation failed"); }
   *out = c;
   return 0;

@@ -425,7 +425,11 @@ __global__ void __launch_bounds__(32*LW, 1) k_crk_sum_density(CrkArgs a) {
 }
 
 // ---- CRKSPH<Dim>::evaluateDerivativesImpl + smoothing-scale sub-package ---------------------------------------------------------
-template <int DIM>
+//   GEN  : every option of the reference at run time (Balsara, Cl/Cq multipliers, linear / quadraticInExpansion, any
+//          XSPH / smoothing-scale / compatible-energy choice)
+//   !GEN : the factory configuration of CRKSPHHydros.py (XSPH, SPH smoothing scale, compatible energy; LIMITED picks
+//          LimitedMonaghanGingold or plain MonaghanGingold) fixed at compile time, so the unused paths cost no registers
+template <int DIM, bool GEN, bool LIMITED>
 __global__ void __launch_bounds__(32*CW, 1) k_crk_derivs(CrkArgs a) {
   using D = Dm<DIM>;
   constexpr int NS = D::NS, NT = D::NT, ROW = D::ROW, PS = Ck<DIM>::PS, CST = Ck<DIM>::CST, QST = Ck<DIM>::QST;
@@ -440,10 +444,13 @@ __global__ void __launch_bounds__(32*CW, 1) k_crk_derivs(CrkArgs a) {
   const size_t i = t.i;
   const bool inRange = t.inRange, active = t.active;
   const sphb200_options& op = a.o;
-  const bool xsph = op.XSPH != 0, hsph = op.hEvolution == SPHB200_H_SPH, compat = op.compatibleEnergy != 0;
-  const bool limited = op.Qkind == SPHB200_Q_LIMITED_MG;
-  const bool needQ = limited || op.balsara;
-  const bool mult = a.auxfCl != nullptr;
+  const bool xsph = GEN ? op.XSPH != 0 : true, hsph = GEN ? op.hEvolution == SPHB200_H_SPH : true;
+  const bool compat = GEN ? op.compatibleEnergy != 0 : true;
+  const bool limited = GEN ? op.Qkind == SPHB200_Q_LIMITED_MG : LIMITED;
+  const bool bals = GEN && op.balsara;
+  const bool needQ = limited || bals;
+  const bool mult = GEN && a.auxfCl != nullptr;
+  const bool linExp = GEN && op.linearInExpansion, quadExp = GEN && op.quadraticInExpansion;
   const double etaCrit = op.etaCritFrac/op.nPerh, rEtaFold = op.nPerh/op.etaFoldFrac;
 
   double rwi[ROW], ci_[CST];
@@ -467,7 +474,7 @@ __global__ void __launch_bounds__(32*CW, 1) k_crk_derivs(CrkArgs a) {
 #pragma unroll
   for (int q = 0; q < NT; ++q) DvDxQi[q] = (needQ && inRange) ? a.auxDvDxQ[i*NT + q] : 0.0;
   const double fCli = (mult && inRange) ? a.auxfCl[i] : 1.0, fCqi = (mult && inRange) ? a.auxfCq[i] : 1.0;
-  const double balsi = (op.balsara && inRange) ? balsara<DIM>(op, DvDxQi, Hdeti, csi) : 1.0;
+  const double balsi = (bals && inRange) ? balsara<DIM>(op, DvDxQi, Hdeti, csi) : 1.0;
 
   double DepsDt = 0, maxQ = 0, effQ = 0, m0 = 0;
   double DvDt[DIM], XdV[DIM], m1[DIM], DvDx[NT];
@@ -539,7 +546,7 @@ __global__ void __launch_bounds__(32*CW, 1) k_crk_derivs(CrkArgs a) {
       if (needQ) {
         ring.template read_x2<QST>(k, lane, qj_);            // {Vj, Q velocity gradient of j}
         const double* DvDxQj = qj_ + 1;
-        if (op.balsara) fshear = 0.5*(balsi + balsara<DIM>(op, DvDxQj, Hdetj, csj));
+        if (bals) fshear = 0.5*(balsi + balsara<DIM>(op, DvDxQj, Hdetj, csj));
         if (limited) {
           double xij[DIM], t1[DIM], t2[DIM];
 #pragma unroll
@@ -559,14 +566,16 @@ __global__ void __launch_bounds__(32*CW, 1) k_crk_derivs(CrkArgs a) {
           for (int q = 0; q < DIM; ++q) vijQ[q] = (vi[q] - phi*t1[q]) - (vj[q] + phi*t2[q]);
         }
       }
-      Clij = 0.5*(fCli + fClj)*fshear*op.Cl;
-      Cqij = 0.5*(fCqi + fCqj)*fshear*op.Cq;
+      if (GEN) {
+        Clij = 0.5*(fCli + fClj)*fshear*op.Cl;
+        Cqij = 0.5*(fCqi + fCqj)*fshear*op.Cq;
+      }
     }
     const double mui = vdot<DIM>(vijQ, etai)*fast_rcp(e2i + op.eps2);
     const double muj = vdot<DIM>(vijQ, etaj)*fast_rcp(e2j + op.eps2);
     const double mui0 = mui < 0.0 ? mui : 0.0, muj0 = muj < 0.0 ? muj : 0.0;
-    const double ei = -Clij*csi*(op.linearInExpansion ? mui : mui0) + Cqij*(op.quadraticInExpansion ? -d_sgn(mui)*mui*mui : mui0*mui0);
-    const double ej = -Clij*csj*(op.linearInExpansion ? muj : muj0) + Cqij*(op.quadraticInExpansion ? -d_sgn(muj)*muj*muj : muj0*muj0);
+    const double ei = -Clij*csi*(linExp ? mui : mui0) + Cqij*(quadExp ? -d_sgn(mui)*mui*mui : mui0*mui0);
+    const double ej = -Clij*csj*(linExp ? muj : muj0) + Cqij*(quadExp ? -d_sgn(muj)*muj*muj : muj0*muj0);
     const double Qi = rhoi*ei, Qj = rhoj*ej;                 // rho_i^2 QPiij = rho_i e_i = Qi (QPiij = e_i/rho_i)
     const double vdg = vdot<DIM>(vij, dg);
     { const double q4 = 4.0*Qi; maxQ = q4 > maxQ ? q4 : maxQ; }   // :354
@@ -624,7 +633,7 @@ __global__ void __launch_bounds__(32*CW, 1) k_crk_derivs(CrkArgs a) {
 #pragma unroll
   for (int q = 0; q < DIM; ++q) { put(DV_DXDT, q, xsph ? vi[q] + XdV[q] : vi[q]); put(DV_DVDT, q, DvDt[q]); put(DV_XSPHDV, q, XdV[q]); put(DV_GRADRHO, q, 0.0); }
   put(DV_DRHODT, 0, -rhoi*ten_trace<DIM>(DvDx));
-  if (op.evolveTotalEnergy) DepsDt = mi*(vdot<DIM>(vi, DvDt) + DepsDt);
+  if (GEN && op.evolveTotalEnergy) DepsDt = mi*(vdot<DIM>(vi, DvDt) + DepsDt);
   put(DV_DEPSDT, 0, DepsDt);
   put(DV_RHOSUM, 0, 0.0); put(DV_NORM, 0, 0.0); put(DV_MAXQ, 0, maxQ); put(DV_EFFQ, 0, effQ); put(DV_XSPHW, 0, 0.0);
 #pragma unroll
@@ -653,7 +662,7 @@ __global__ void __launch_bounds__(32*CW, 1) k_crk_derivs(CrkArgs a) {
 #pragma unroll
     for (int q = 0; q < DIM; ++q) put(DV_M1, q, 0.0);
     double dh[NS];
-    if (op.hEvolution == SPHB200_H_ASPH) asph_DHDt<DIM>(Hi, DvDx, dh);
+    if (GEN && op.hEvolution == SPHB200_H_ASPH) asph_DHDt<DIM>(Hi, DvDx, dh);
     else {
 #pragma unroll
       for (int q = 0; q < NS; ++q) dh[q] = 0.0;
@@ -743,8 +752,18 @@ int sphb200_launch_crk_derivs(sphb200_ctx* c) {
   a.pacc = c->pacc;
   if (c->opt.hEvolution == SPHB200_H_SPH && (!a.nperhVals || a.nperhN < 2))
     return sphb200_fail(c, "evaluateDerivatives: SPHSmoothingScale needs the TableKernel nperh lookup (nperhVals) but none was set");
-  if (c->ndim == 3) { if (launch_tiles(c, k_crk_derivs<3>, a, "k_crk_derivs", CW, (size_t)DerivRing<3>::WARPB)) return 1; }
-  else              { if (launch_tiles(c, k_crk_derivs<2>, a, "k_crk_derivs", CW, (size_t)DerivRing<2>::WARPB)) return 1; }
+  const sphb200_options& o = c->opt;
+  const bool fast = o.XSPH && o.hEvolution == SPHB200_H_SPH && o.compatibleEnergy && !o.evolveTotalEnergy && !o.balsara && !mult &&
+                    !o.linearInExpansion && !o.quadraticInExpansion;
+  const bool lim = o.Qkind == SPHB200_Q_LIMITED_MG;
+  int rc;
+  if (c->ndim == 3) rc = !fast ? launch_tiles(c, k_crk_derivs<3, true, true>, a, "k_crk_derivs", CW, (size_t)DerivRing<3>::WARPB)
+                        : lim ? launch_tiles(c, k_crk_derivs<3, false, true>, a, "k_crk_derivs", CW, (size_t)DerivRing<3>::WARPB)
+                              : launch_tiles(c, k_crk_derivs<3, false, false>, a, "k_crk_derivs", CW, (size_t)DerivRing<3>::WARPB);
+  else              rc = !fast ? launch_tiles(c, k_crk_derivs<2, true, true>, a, "k_crk_derivs", CW, (size_t)DerivRing<2>::WARPB)
+                        : lim ? launch_tiles(c, k_crk_derivs<2, false, true>, a, "k_crk_derivs", CW, (size_t)DerivRing<2>::WARPB)
+                              : launch_tiles(c, k_crk_derivs<2, false, false>, a, "k_crk_derivs", CW, (size_t)DerivRing<2>::WARPB);
+  if (rc) return 1;
   c->derivsValid = true;
   return 0;
 }

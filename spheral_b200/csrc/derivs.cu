@@ -66,6 +66,9 @@ __device__ __forceinline__ void cp_async16_s(unsigned smemDst, const void* gmemS
 // 1: stream the per-node {det H, 1/rho} record of every neighbour through the ring as well; 0: recompute both from the row.
 // The per-lane 16-byte copy costs 32 shared-memory wavefronts per iteration, as many as the 32 rows together, and the LSU data
 // pipe is the unit this kernel saturates first (profiles/r01_notes.md); 23 extra FP64 instructions per edge are cheaper.
+#ifndef SPHB200_PAIR_CTAS_ISO
+#define SPHB200_PAIR_CTAS_ISO 2
+#endif
 #ifndef SPHB200_PAIR_AUX
 #define SPHB200_PAIR_AUX 0
 #endif
@@ -88,8 +91,13 @@ template <int DIM> struct RingGeom {
 //            tensile correction, separate Pi kernel, linear/quadraticInExpansion, any XSPH/compatible/smoothing-scale choice).
 //   !GEN   : the plain MonaghanGingold path named by BASELINE.json, with XSPH / SPH-moments / pair-acceleration storage
 //            fixed at compile time so that unused accumulators cost no registers.
-template <int DIM, bool GEN, bool XSPH_, bool HSPH_, bool COMPAT_>
-__global__ void __launch_bounds__(32*PAIR_WARPS, PAIR_CTAS) k_sph_derivs(DerivArgs a) {
+//   ISO    : every H on the device is a multiple of the identity (checked in k_pack; the normal state of an SPH -- as opposed to
+//            ASPH -- run).  Then eta = r/h, both kernel gradients are parallel to r_ij and the tensor products collapse to
+//            scalar factors: ~40 % fewer FP64 instructions per edge, 3 accumulators less (M is symmetric).  Same terms as the
+//            general path, re-associated (parity 1e-10).
+template <int DIM, bool GEN, bool XSPH_, bool HSPH_, bool COMPAT_, bool ISO>
+__global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : PAIR_CTAS) k_sph_derivs(DerivArgs a) {
+  static_assert(!(GEN && ISO), "the isotropic fast path exists for the plain MonaghanGingold configuration only");
   using D = Dm<DIM>;
   constexpr int NS = D::NS, NT = D::NT, ROW = D::ROW;
   constexpr int ROWB = RingGeom<DIM>::ROWB;
@@ -141,6 +149,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, PAIR_CTAS) k_sph_derivs(DerivAr
     for (int k = 0; k < NS; ++k) Hi[k] = 0;
   }
   const double Hdeti = sym_det<DIM>(Hi);
+  const double hiInv = Hi[0], hi2 = hiInv*hiInv;           // ISO: H_i = hiInv * I
   const double rhoiInv = 1.0/rhoi;
   const double mi_over_rhoi = mi/rhoi;
   const double Pnegi = (tens && inRange) ? a.auxPneg[i] : 0.0;
@@ -237,7 +246,9 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, PAIR_CTAS) k_sph_derivs(DerivAr
 #if SPHB200_PAIR_AUX
       aux = lds128(st + 32u*ROWB + 16u*lane);
 #else
-      aux.x = sym_det<DIM>(rw + D::R_H); aux.y = fast_rcp(rw[D::R_RHO]);
+      if constexpr (ISO) { const double hj = rw[D::R_H]; aux.x = (DIM == 3) ? hj*hj*hj : hj*hj; }
+      else aux.x = sym_det<DIM>(rw + D::R_H);
+      aux.y = fast_rcp(rw[D::R_RHO]);
 #endif
     }
     {
@@ -258,9 +269,28 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, PAIR_CTAS) k_sph_derivs(DerivAr
     double rij[DIM], etai[DIM], etaj[DIM];
 #pragma unroll
     for (int q = 0; q < DIM; ++q) rij[q] = ri[q] - rj[q];
+    double e2i, e2j, Wi, gWi, Wj, gWj, gWiRaw;
+    double gradWi[DIM], gradWj[DIM];
+    double gi = 0.0, gj = 0.0, hjInv = 0.0;               // ISO: gradW_i = gi * rij, gradW_j = gj * rij
+    if constexpr (ISO) {
+      hjInv = Hj[0];
+      const double r2 = vdot<DIM>(rij, rij);
+      // coincident nodes: r = 0 multiplies the finite reciprocal below, as safeInvVar's 0 * 1e30 does in the reference
+      const double rinv = fast_rsqrt(r2 + 1.0e-300);
+      const double r = r2*rinv;
+      e2i = hi2*r2; e2j = (hjInv*hjInv)*r2;
+      table_eval_raw(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, hiInv*r, Wi, gWi);
+      table_eval_raw(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, hjInv*r, Wj, gWj);
+      gWiRaw = gWi;
+      Wi *= Hdeti; Wj *= Hdetj;
+      gi = (gWi*Hdeti)*(hiInv*rinv);                       // gWi * Hi * etaiUnit = gWi * hiInv * rij/r
+      gj = (gWj*Hdetj)*(hjInv*rinv);
+#pragma unroll
+      for (int q = 0; q < DIM; ++q) { etai[q] = hiInv*rij[q]; etaj[q] = hjInv*rij[q]; gradWi[q] = gi*rij[q]; gradWj[q] = gj*rij[q]; }
+    } else {
     sym_dot<DIM>(Hi, rij, etai);
     sym_dot<DIM>(Hj, rij, etaj);
-    const double e2i = vdot<DIM>(etai, etai), e2j = vdot<DIM>(etaj, etaj);
+    e2i = vdot<DIM>(etai, etai); e2j = vdot<DIM>(etaj, etaj);
     // coincident nodes (eta == 0): 1e-300 keeps the reciprocal finite; it multiplies exact zeros (H.eta, eta^2) below, which
     // reproduces safeInvVar's 0 * 1e30 = 0 (SPH.cc:368-369); for every other pair the addend is below half an ulp
     const double invi = fast_rsqrt(e2i + 1.0e-300);
@@ -268,28 +298,34 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, PAIR_CTAS) k_sph_derivs(DerivAr
     const double etaMagi = e2i*invi, etaMagj = e2j*invj;
 
     // SPH.cc:374-377 : W, gradW (table values carry no Hdet yet)
-    double Wi, gWi, Wj, gWj;
     table_eval_raw(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, etaMagi, Wi, gWi);
     table_eval_raw(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, etaMagj, Wj, gWj);
-    const double gWiRaw = gWi;
+    gWiRaw = gWi;
     Wi *= Hdeti; gWi *= Hdeti; Wj *= Hdetj; gWj *= Hdetj;
-    double Hei[DIM], Hej[DIM], gradWi[DIM], gradWj[DIM];
+    double Hei[DIM], Hej[DIM];
     sym_dot<DIM>(Hi, etai, Hei);                 // gWi*Hi*etaiUnit == (gWi/|etai|) * (Hi.etai)
     sym_dot<DIM>(Hj, etaj, Hej);
     { const double si = gWi*invi, sj = gWj*invj;
 #pragma unroll
       for (int q = 0; q < DIM; ++q) { gradWi[q] = si*Hei[q]; gradWj[q] = sj*Hej[q]; } }
+    }
     double WQi = Wi, WQj = Wj, gradWQi[DIM], gradWQj[DIM];
 #pragma unroll
     for (int q = 0; q < DIM; ++q) { gradWQi[q] = gradWi[q]; gradWQj[q] = gradWj[q]; }
+    if constexpr (GEN) {
     if (twoK) {                                   // SPH.cc:383-388
       double gWQi, gWQj;
-      table_eval_raw(tQ, a.kextQ, a.xminQ, a.xstepQ, rxQ, a.n1Q, etaMagi, WQi, gWQi);
-      table_eval_raw(tQ, a.kextQ, a.xminQ, a.xstepQ, rxQ, a.n1Q, etaMagj, WQj, gWQj);
+      const double invi = fast_rsqrt(e2i + 1.0e-300), invj = fast_rsqrt(e2j + 1.0e-300);
+      double Hei[DIM], Hej[DIM];
+      sym_dot<DIM>(Hi, etai, Hei);
+      sym_dot<DIM>(Hj, etaj, Hej);
+      table_eval_raw(tQ, a.kextQ, a.xminQ, a.xstepQ, rxQ, a.n1Q, e2i*invi, WQi, gWQi);
+      table_eval_raw(tQ, a.kextQ, a.xminQ, a.xstepQ, rxQ, a.n1Q, e2j*invj, WQj, gWQj);
       WQi *= Hdeti; WQj *= Hdetj;
       const double si = gWQi*Hdeti*invi, sj = gWQj*Hdetj*invj;
 #pragma unroll
       for (int q = 0; q < DIM; ++q) { gradWQi[q] = si*Hei[q]; gradWQj[q] = sj*Hej[q]; }
+    }
     }
 
     // SPH.cc:391-396 (i side)
@@ -320,7 +356,8 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, PAIR_CTAS) k_sph_derivs(DerivAr
           const double rrj = gradj/(d_sgn(gradi)*fmax(1.0e-30, fabs(gradi)));
           const double x = fmin(rri, rrj);
           double phi = (x > 0.0 ? 2.0/(1.0 + x)*2.0*x/(1.0 + x) : 0.0);       // van Leer
-          const double etaij = fmin(etaMagi, etaMagj);
+          const double e2m = e2i < e2j ? e2i : e2j;
+          const double etaij = e2m*fast_rsqrt(e2m + 1.0e-300);
           if (etaij < etaCrit) { const double z = (etaij - etaCrit)/etaFold; phi *= exp(-z*z); }
 #pragma unroll
           for (int q = 0; q < DIM; ++q) vijQ[q] = (vi[q] - phi*t1[q]) - (vj[q] + phi*t2[q]);
@@ -382,10 +419,20 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, PAIR_CTAS) k_sph_derivs(DerivAr
 #pragma unroll
       for (int r = 0; r < DIM; ++r)
 #pragma unroll
-        for (int c2 = 0; c2 < DIM; ++c2) {
-          DvDx[r*DIM + c2] = fma(-vij[r], g[c2], DvDx[r*DIM + c2]);
-          M[r*DIM + c2] = fma(-rij[r], g[c2], M[r*DIM + c2]);
-        }
+        for (int c2 = 0; c2 < DIM; ++c2) DvDx[r*DIM + c2] = fma(-vij[r], g[c2], DvDx[r*DIM + c2]);
+      if constexpr (ISO) {
+        // rij (x) gradWi = gi rij (x) rij is symmetric: upper triangle only (mirrored in the finalize)
+        int t = 0;
+#pragma unroll
+        for (int r = 0; r < DIM; ++r)
+#pragma unroll
+          for (int c2 = r; c2 < DIM; ++c2) { M[t] = fma(-rij[r], g[c2], M[t]); ++t; }
+      } else {
+#pragma unroll
+        for (int r = 0; r < DIM; ++r)
+#pragma unroll
+          for (int c2 = 0; c2 < DIM; ++c2) M[r*DIM + c2] = fma(-rij[r], g[c2], M[r*DIM + c2]);
+      }
       // SPH.cc:457-460
       const double f = rhoj - rhoi;
 #pragma unroll
@@ -421,6 +468,13 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, PAIR_CTAS) k_sph_derivs(DerivAr
   }
   rhoSum += mi*a.W0*Hdeti;
   norm += mi_over_rhoi*a.W0*Hdeti;
+  if constexpr (ISO) {                                   // unpack the upper triangle accumulated above
+    double S[NS];
+#pragma unroll
+    for (int q = 0; q < NS; ++q) S[q] = M[q];
+    if (DIM == 3) { M[0] = S[0]; M[1] = S[1]; M[2] = S[2]; M[3] = S[1]; M[4] = S[3]; M[5] = S[4]; M[6] = S[2]; M[7] = S[4]; M[8] = S[5]; }
+    else { M[0] = S[0]; M[1] = S[1]; M[2] = S[1]; M[3] = S[2]; }
+  }
   double Minv[NT], DvDxF[NT];
   const uint32_t pownu2 = (DIM == 3) ? 8u : 4u;
   if (o.correctVelocityGradient && fabs(ten_det<DIM>(M)) > 1.0e-10 && cnt > pownu2) {
@@ -485,10 +539,10 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, PAIR_CTAS) k_sph_derivs(DerivAr
   }   // tile loop
 }
 
-template <int DIM, bool GEN, bool X, bool H, bool C>
+template <int DIM, bool GEN, bool X, bool H, bool C, bool ISO = false>
 int launch_one(sphb200_ctx* c, const DerivArgs& a, unsigned nb, int threads, size_t shm) {
-  CU_CHECK(c, cudaFuncSetAttribute(k_sph_derivs<DIM, GEN, X, H, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-  k_sph_derivs<DIM, GEN, X, H, C><<<nb, threads, shm, c->stream>>>(a);
+  CU_CHECK(c, cudaFuncSetAttribute(k_sph_derivs<DIM, GEN, X, H, C, ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+  k_sph_derivs<DIM, GEN, X, H, C, ISO><<<nb, threads, shm, c->stream>>>(a);
   return 0;
 }
 template <int DIM>
@@ -496,6 +550,18 @@ int launch_dim(sphb200_ctx* c, const DerivArgs& a, unsigned nb, int threads, siz
   const bool x = a.o.XSPH != 0, h = a.o.hEvolution == SPHB200_H_SPH, p = a.o.compatibleEnergy != 0;
   if (gen) return launch_one<DIM, true, true, true, true>(c, a, nb, threads, shm);
   const int code = (x ? 4 : 0) | (h ? 2 : 0) | (p ? 1 : 0);
+  if (c->allIsotropic && a.o.hEvolution != SPHB200_H_ASPH) {      // every H = h^-1 I (k_pack checked the rows this launch reads)
+    switch (code) {
+      case 0: return launch_one<DIM, false, false, false, false, true>(c, a, nb, threads, shm);
+      case 1: return launch_one<DIM, false, false, false, true, true>(c, a, nb, threads, shm);
+      case 2: return launch_one<DIM, false, false, true, false, true>(c, a, nb, threads, shm);
+      case 3: return launch_one<DIM, false, false, true, true, true>(c, a, nb, threads, shm);
+      case 4: return launch_one<DIM, false, true, false, false, true>(c, a, nb, threads, shm);
+      case 5: return launch_one<DIM, false, true, false, true, true>(c, a, nb, threads, shm);
+      case 6: return launch_one<DIM, false, true, true, false, true>(c, a, nb, threads, shm);
+      default: return launch_one<DIM, false, true, true, true, true>(c, a, nb, threads, shm);
+    }
+  }
   switch (code) {
     case 0: return launch_one<DIM, false, false, false, false>(c, a, nb, threads, shm);
     case 1: return launch_one<DIM, false, false, false, true>(c, a, nb, threads, shm);
@@ -548,7 +614,8 @@ int sphb200_launch_derivs(sphb200_ctx* c) {
   // persistent CTAs: 2 per SM (register-limited), each striding over the tiles
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
-  const unsigned nb = (unsigned)std::min<size_t>((c->nTiles + wpb - 1)/wpb, (size_t)nsm*PAIR_CTAS);
+  const bool isoPath = c->allIsotropic && c->opt.hEvolution != SPHB200_H_ASPH;
+  const unsigned nb = (unsigned)std::min<size_t>((c->nTiles + wpb - 1)/wpb, (size_t)nsm*(isoPath ? SPHB200_PAIR_CTAS_ISO : PAIR_CTAS));
   const bool gen = (c->opt.Qkind != SPHB200_Q_MG) || c->opt.balsara || mult || tens || !c->oneKernel ||
                    c->opt.linearInExpansion || c->opt.quadraticInExpansion;
   if (c->ndim == 3) { if (launch_dim<3>(c, a, nb, wpb*32, shm, gen)) return 1; }

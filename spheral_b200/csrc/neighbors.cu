@@ -153,6 +153,7 @@ struct PackArgs {
   size_t n;
   float* frows; GridDev g; double kext; double csmax;
   int rawP;                       // CRKSPH: the row carries P itself (CRKSPH.cc:376 uses Pi + Pj), not safeInv(omega)*P/rho^2
+  unsigned long long* aniso;      // set to 1 if any H is not a multiple of the identity (selects the isotropic pair loop)
 };
 template <int DIM>
 __global__ void __launch_bounds__(RB) k_pack(PackArgs a) {
@@ -163,18 +164,19 @@ __global__ void __launch_bounds__(RB) k_pack(PackArgs a) {
   double* r = a.rows + s*D::ROW;
 #pragma unroll
   for (int k = 0; k < DIM; ++k) { r[D::R_POS + k] = a.pos[o*DIM + k]; r[D::R_VEL + k] = a.vel ? a.vel[o*DIM + k] : 0.0; }
+  double Hn[D::NS];                                              // this node's H, read once
 #pragma unroll
-  for (int k = 0; k < D::NS; ++k) r[D::R_H + k] = a.H[o*D::NS + k];
+  for (int k = 0; k < D::NS; ++k) { Hn[k] = a.H[o*D::NS + k]; r[D::R_H + k] = Hn[k]; }
+  { const bool iso = (DIM == 3) ? (Hn[1] == 0.0 && Hn[2] == 0.0 && Hn[4] == 0.0 && Hn[3] == Hn[0] && Hn[5] == Hn[0])
+                                : (Hn[1] == 0.0 && Hn[2] == Hn[0]);
+    if (!iso) *a.aniso = 1ull; }
   const double m = a.mass ? a.mass[o] : 0.0, rho = a.rho ? a.rho[o] : 1.0, P = a.P ? a.P[o] : 0.0;
   const double om = a.omega ? a.omega[o] : 1.0, cs = a.cs ? a.cs[o] : 0.0;
   const double safeOmega = om/(om*om + 1.0e-30);                 // safeInv, Utilities/safeInv.hh:13-19 (SPH.cc:310)
   r[D::R_M] = m; r[D::R_RHO] = rho; r[D::R_CS] = cs;
   r[D::R_PRHO] = a.rawP ? P : safeOmega*P/(rho*rho);             // SPH.cc:425 with Peff == P
   if (DIM == 2) r[11] = 0.0;
-  { double hh[D::NS];
-#pragma unroll
-    for (int k = 0; k < D::NS; ++k) hh[k] = r[D::R_H + k];
-    a.aux2[2*s] = sym_det<DIM>(hh); a.aux2[2*s + 1] = 1.0/rho; }
+  a.aux2[2*s] = sym_det<DIM>(Hn); a.aux2[2*s + 1] = 1.0/rho;
   if (a.auxPneg) { a.auxPneg[s] = (P < 0.0 ? -P : 0.0); a.auxSomr2[s] = safeOmega/(rho*rho); }
   if (a.auxDvDxQ) {
 #pragma unroll
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(RB) k_pack(PackArgs a) {
     float* f = a.frows + s*Fr::ROW;
     double h[D::NS], hf = 0.0;
 #pragma unroll
-    for (int k = 0; k < D::NS; ++k) { h[k] = a.H[o*D::NS + k]; hf += h[k]*h[k]; }
+    for (int k = 0; k < D::NS; ++k) { h[k] = Hn[k]; hf += h[k]*h[k]; }
     if (DIM == 3) hf += h[1]*h[1] + h[2]*h[2] + h[4]*h[4]; else hf += h[1]*h[1];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -603,6 +605,8 @@ int sphb200_pack_rows(sphb200_ctx* c) {
   a.auxDvDxQ = needQ ? c->auxDvDxQ : nullptr; a.auxfCl = mult ? c->auxfCl : nullptr; a.auxfCq = mult ? c->auxfCq : nullptr;
   a.perm = c->perm; a.keyApi = c->cellKeyApi; a.skey = c->skey; a.n = c->n;
   a.rawP = (c->opt.hydro == SPHB200_HYDRO_CRKSPH) ? 1 : 0;
+  a.aniso = c->counters + 8;
+  CU_CHECK(c, cudaMemsetAsync(c->counters + 8, 0, sizeof(unsigned long long), c->stream));
   { size_t fcap = c->frows ? c->frowsCap : 0;
     if (sphb200_ensure(c, c->frows, fcap, c->cap*(size_t)Fr::ROW)) return 1;
     c->frowsCap = fcap; }
@@ -698,7 +702,7 @@ int sphb200_neighbors(sphb200_ctx* c) {
       KERNEL_CHECK(c, "k_nbr_build");
     }
     // one host round trip: totals and capacity check
-    CU_CHECK(c, cudaMemcpyAsync(c->countersHost, c->counters, 8*sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(c, cudaMemcpyAsync(c->countersHost, c->counters, 9*sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
     const size_t needRuns = (size_t)c->countersHost[2], needNbr = (size_t)c->countersHost[3], needRows = (size_t)c->countersHost[4];
     const bool okRuns = needRuns <= c->runsCap;
@@ -713,6 +717,7 @@ int sphb200_neighbors(sphb200_ctx* c) {
       // build that overflows its staging is redone at full cost)
       c->listRows = (int)((needRows + needRows/8 + 8 + 7)/8*8);
       c->pairsValid = true;
+      c->allIsotropic = (c->countersHost[8] == 0ull);       // k_pack of this build saw only H = h^-1 I
       c->stats.directed_edges = c->nEdges;
       return 0;
     }

@@ -103,6 +103,7 @@ struct sphb200_ctx {
   double* crkCorrS = nullptr;       // CRKSPH: (1+ndim)^2 RK coefficients per node (sorted, AoS)
   double* crkQS = nullptr;          // CRKSPH: {volume, Q velocity gradient} per node (sorted, stride 10 / 6)
   double* crkAux = nullptr;         // CRKSPH: {det H, volume} per node (sorted)
+  bool allIsotropic = false;        // every H packed at the last build_pairs was a multiple of the identity (k_pack; read back with the counters)
   bool rowsValid = false;           // rows reflect current api state for the current sort
   bool sortValid = false;
 
