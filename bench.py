@@ -211,6 +211,8 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="override lattice points per side (debug)")
     ap.add_argument("--cpu-sample", type=int, default=48, help="lattice points per side of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hjitter", type=float, default=0.0,
+                    help="scale every node's H by a random factor in [1-x, 1+x] (diagnostic: the lattice workloads have a constant h)")
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     spec = workload_spec(args.workload)
@@ -244,6 +246,9 @@ def main():
     import ctypes as C
 
     st, N = make_inputs(spec, seed=14892042 + rank, slab=rank)
+    if args.hjitter:
+        st["H"] = st["H"]*(1.0 + args.hjitter*np.random.default_rng(5 + rank).uniform(-1.0, 1.0, size=(N, 1)))
+        config["workload"] += " [h jittered by +-%g]" % args.hjitter
     WT = K.TableKernel(K.BSplineKernel(3), 1000)
     crk = spec.get("hydro") == "crksph"
     if crk and world > 1:
