@@ -244,6 +244,14 @@ int  sphb200_halo_pack(sphb200_ctx* ctx, unsigned fieldMask, const uint32_t* sen
                        void* stagingDevice);
 int  sphb200_halo_unpack(sphb200_ctx* ctx, unsigned fieldMask, size_t firstGhost, size_t count,
                          const void* stagingDevice);
+/* Ghost-value refresh on a FIXED connectivity (Integrator::applyGhostBoundaries between the stages of a step): like
+   sphb200_halo_unpack, but positions / H landing in the ghost slots do not invalidate the pair lists. */
+int  sphb200_halo_unpack_values(sphb200_ctx* ctx, unsigned fieldMask, size_t firstGhost, size_t count, const void* stagingDevice);
+/* SPHBase::finalizeDerivatives across a domain boundary (SPH/SPHBase.cc:502-519; SURVEY 8e: "with compatible energy, one
+   [exchange] after: DvDt, DepsDt on ghosts"): pack {DvDt (ndim), DepsDt} of the listed send nodes / land a received block in
+   the ghost entries of the derivative arrays.  Staging: count*ndim doubles of DvDt, then count doubles of DepsDt. */
+int  sphb200_halo_pack_derivs(sphb200_ctx* ctx, const uint32_t* sendNodesDevice, size_t count, void* stagingDevice);
+int  sphb200_halo_unpack_derivs(sphb200_ctx* ctx, size_t firstGhost, size_t count, const void* stagingDevice);
 /* Domain bounds for the ghost-set decision (the role of the bounding boxes all-gathered by
    NestedGridDistributedBoundary.cc:116-170 / TreeDistributedBoundary.cc:150-295): coordinate range and the largest
    per-axis kernel extent kext*sqrt((H^-2)_aa) (Neighbor::HExtent, NeighborInline.hh:52-64) over nodes [0,count). */

@@ -100,7 +100,8 @@ EXPORTS = ("sphb200_abi_version", "sphb200_create", "sphb200_destroy", "sphb200_
            "sphb200_sum_mass_density", "sphb200_compute_omega_gradh", "sphb200_update_eos_gamma_law", "sphb200_state_copy",
            "sphb200_state_assign", "sphb200_state_update", "sphb200_compute_dt",
            "sphb200_reflect_configure", "sphb200_reflect_set_ghost_nodes", "sphb200_reflect_apply_ghosts", "sphb200_reflect_enforce",
-           "sphb200_reflect_finalize_derivatives")
+           "sphb200_reflect_finalize_derivatives", "sphb200_halo_unpack_values", "sphb200_halo_pack_derivs",
+           "sphb200_halo_unpack_derivs")
 
 _lib = None
 
@@ -169,5 +170,8 @@ def lib():
     L.sphb200_reflect_apply_ghosts.argtypes = [vp, C.c_uint]
     L.sphb200_reflect_enforce.argtypes = [vp, C.POINTER(C.c_size_t)]
     L.sphb200_reflect_finalize_derivatives.argtypes = [vp]
+    L.sphb200_halo_unpack_values.argtypes = [vp, C.c_uint, C.c_size_t, C.c_size_t, vp]
+    L.sphb200_halo_pack_derivs.argtypes = [vp, vp, C.c_size_t, vp]
+    L.sphb200_halo_unpack_derivs.argtypes = [vp, C.c_size_t, C.c_size_t, vp]
     _lib = L
     return L

@@ -54,6 +54,31 @@ __global__ void __launch_bounds__(RB) k_halo_pack(const double* __restrict__ fie
   out[t] = field[(size_t)nodes[k]*width + q];
 }
 // slab halo selection: flags, then (after exclusive scans) ordered scatter of the node indices
+// original index -> sorted slot
+__global__ void __launch_bounds__(RB) k_inverse_perm(const uint32_t* __restrict__ perm, size_t n, uint32_t* __restrict__ inv) {
+  const size_t s = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (s < n) inv[perm[s]] = (uint32_t)s;
+}
+// finalizeDerivatives over a domain boundary: {DvDt (ndim), DepsDt} of listed nodes, sorted component-major arrays <-> staging
+// (DvDt block of count*ndim doubles, then DepsDt block of count doubles)
+__global__ void __launch_bounds__(RB) k_halo_pack_derivs(const double* __restrict__ DvDt, const double* __restrict__ DepsDt, size_t cap, int ndim,
+                                                         const uint32_t* __restrict__ inv, const uint32_t* __restrict__ nodes, size_t count,
+                                                         double* __restrict__ out) {
+  const size_t k = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (k >= count) return;
+  const size_t s = inv[nodes[k]];
+  for (int q = 0; q < ndim; ++q) out[k*ndim + q] = DvDt[(size_t)q*cap + s];
+  out[count*ndim + k] = DepsDt[s];
+}
+__global__ void __launch_bounds__(RB) k_halo_unpack_derivs(double* __restrict__ DvDt, double* __restrict__ DepsDt, size_t cap, int ndim,
+                                                           const uint32_t* __restrict__ inv, size_t first, size_t count,
+                                                           const double* __restrict__ in) {
+  const size_t k = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (k >= count) return;
+  const size_t s = inv[first + k];
+  for (int q = 0; q < ndim; ++q) DvDt[(size_t)q*cap + s] = in[k*ndim + q];
+  DepsDt[s] = in[count*ndim + k];
+}
 __global__ void __launch_bounds__(RB) k_halo_flags(const double* __restrict__ pos, int ndim, int axis, size_t count, double lowCut, double highCut,
                                                    uint32_t* __restrict__ fLow, uint32_t* __restrict__ fHigh) {
   const size_t i = (size_t)blockIdx.x*RB + threadIdx.x;
@@ -510,7 +535,7 @@ int sphb200_halo_pack(sphb200_ctx* c, unsigned mask, const uint32_t* nodes, size
   return 0;
 }
 
-int sphb200_halo_unpack(sphb200_ctx* c, unsigned mask, size_t firstGhost, size_t count, const void* staging) {
+static int halo_unpack_impl(sphb200_ctx* c, unsigned mask, size_t firstGhost, size_t count, const void* staging, bool keepConnectivity) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
   CU_CHECK(c, cudaSetDevice(c->device));
   if (firstGhost + count > c->n) return sphb200_fail(c, "halo_unpack: ghost range exceeds node count");
@@ -522,9 +547,50 @@ int sphb200_halo_unpack(sphb200_ctx* c, unsigned mask, size_t firstGhost, size_t
     if (count) CU_CHECK(c, cudaMemcpyAsync(c->api[s] + firstGhost*(size_t)w, in, count*(size_t)w*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     in += count*(size_t)w;
     c->have[s] = true;
-    if (s == S_POS || s == S_H) { c->sortValid = false; c->pairsValid = false; }
+    if (!keepConnectivity && (s == S_POS || s == S_H)) { c->sortValid = false; c->pairsValid = false; }
     if (s != S_EPS && s != S_VOLUME && s != S_RKCORR) c->rowsValid = false;
   }
+  return 0;
+}
+int sphb200_halo_unpack(sphb200_ctx* c, unsigned mask, size_t firstGhost, size_t count, const void* staging) {
+  return halo_unpack_impl(c, mask, firstGhost, count, staging, false);
+}
+int sphb200_halo_unpack_values(sphb200_ctx* c, unsigned mask, size_t firstGhost, size_t count, const void* staging) {
+  return halo_unpack_impl(c, mask, firstGhost, count, staging, true);
+}
+
+int sphb200_inverse_perm(sphb200_ctx* c) {
+  if (sphb200_ensure(c, c->invPerm, c->invPermCap, c->cap)) return 1;
+  if (c->n == 0) return 0;
+  k_inverse_perm<<<(unsigned)((c->n + RB - 1)/RB), RB, 0, c->stream>>>(c->perm, c->n, c->invPerm);
+  KERNEL_CHECK(c, "k_inverse_perm");
+  return 0;
+}
+
+int sphb200_halo_pack_derivs(sphb200_ctx* c, const uint32_t* nodes, size_t count, void* staging) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (!c->derivsValid || !c->pairsValid) return sphb200_fail(c, "halo_pack_derivs: derivatives have not been evaluated on the current connectivity");
+  if (count == 0) return 0;
+  if (!nodes || !staging) return sphb200_fail(c, "halo_pack_derivs: null argument");
+  if (sphb200_inverse_perm(c)) return 1;
+  k_halo_pack_derivs<<<(unsigned)((count + RB - 1)/RB), RB, 0, c->stream>>>(c->deriv[DV_DVDT], c->deriv[DV_DEPSDT], c->cap, c->ndim, c->invPerm,
+                                                                           nodes, count, (double*)staging);
+  KERNEL_CHECK(c, "k_halo_pack_derivs");
+  return 0;
+}
+
+int sphb200_halo_unpack_derivs(sphb200_ctx* c, size_t firstGhost, size_t count, const void* staging) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (!c->derivsValid || !c->pairsValid) return sphb200_fail(c, "halo_unpack_derivs: derivatives have not been evaluated on the current connectivity");
+  if (firstGhost + count > c->n) return sphb200_fail(c, "halo_unpack_derivs: ghost range exceeds node count");
+  if (count == 0) return 0;
+  if (!staging) return sphb200_fail(c, "halo_unpack_derivs: null argument");
+  if (sphb200_inverse_perm(c)) return 1;
+  k_halo_unpack_derivs<<<(unsigned)((count + RB - 1)/RB), RB, 0, c->stream>>>(c->deriv[DV_DVDT], c->deriv[DV_DEPSDT], c->cap, c->ndim, c->invPerm,
+                                                                             firstGhost, count, (const double*)staging);
+  KERNEL_CHECK(c, "k_halo_unpack_derivs");
   return 0;
 }
 

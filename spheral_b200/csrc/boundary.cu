@@ -160,10 +160,6 @@ __global__ void __launch_bounds__(RB) k_reflect_enforce(double* __restrict__ pos
 }
 
 // finalizeDerivatives: ghost values of the acceleration (R a) and of DepsDt (copy) in the sorted, component-major derivative arrays
-__global__ void __launch_bounds__(RB) k_inverse_perm(const uint32_t* __restrict__ perm, size_t n, uint32_t* __restrict__ inv) {
-  const size_t s = (size_t)blockIdx.x*RB + threadIdx.x;
-  if (s < n) inv[perm[s]] = (uint32_t)s;
-}
 template <int DIM>
 __global__ void __launch_bounds__(RB) k_reflect_derivs(double* __restrict__ DvDt, double* __restrict__ DepsDt, size_t cap,
                                                        const uint32_t* __restrict__ inv, const uint32_t* __restrict__ ctl,
@@ -300,9 +296,7 @@ int sphb200_reflect_finalize_derivatives(sphb200_ctx* c) {
   for (int p = 0; p < c->nPlanes; ++p) total += c->planeCount[p];
   if (total != c->nGhost) return sphb200_fail(c, "reflect_finalize_derivatives: the ghost nodes were not generated by reflect_set_ghost_nodes");
   if (total == 0) return 0;
-  if (sphb200_ensure(c, c->invPerm, c->invPermCap, c->cap)) return 1;
-  k_inverse_perm<<<(unsigned)((c->n + RB - 1)/RB), RB, 0, c->stream>>>(c->perm, c->n, c->invPerm);
-  KERNEL_CHECK(c, "k_inverse_perm");
+  if (sphb200_inverse_perm(c)) return 1;
   for (int p = 0; p < c->nPlanes; ++p) {
     const size_t count = c->planeCount[p];
     if (count == 0) continue;

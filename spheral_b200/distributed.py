@@ -167,7 +167,10 @@ class DistributedSPH:
         self._cap = cap
 
     def refresh_ghosts_and_build(self):
-        """Ghost selection + exchange + neighbour build.  Returns the number of node pairs of this slab.
+        return self.refresh_ghosts(build=True)
+
+    def refresh_ghosts(self, build=True):
+        """Ghost selection + exchange (+ neighbour build).  Returns the number of node pairs of this slab (None without the build).
 
         Default path: ONE host round trip before the neighbour build.  The bounds reduction, the all-reduce(MAX) of the
         halo width, the send-node selection and the all-gather of the counts are chained on the device
@@ -212,7 +215,7 @@ class DistributedSPH:
             self.nFromLower, self.nFromUpper = nFL, nFU
             e.set_nodes(nInt, nFL + nFU)
             wA, wB = self.bytesA//8, self.bytesB//8
-            if not self.two_phase:
+            if not self.two_phase or not build:
                 wAB = wA + wB
                 mask = self.maskA | self.maskB
                 e.halo_pack(mask, self.idxLow.data_ptr(), nLow, self.sLowB.data_ptr())
@@ -221,7 +224,7 @@ class DistributedSPH:
                 h.finish(works)
                 e.halo_unpack(mask, nInt, nFL, self.rLowB.data_ptr())
                 e.halo_unpack(mask, nInt + nFL, nFU, self.rHighB.data_ptr())
-                npairs = e.build_pairs()
+                npairs = e.build_pairs() if build else None
             else:
                 # pack both phases, then post A and B; K1+K2 only wait for A
                 e.halo_pack(self.maskA, self.idxLow.data_ptr(), nLow, self.sLowA.data_ptr())
@@ -240,6 +243,44 @@ class DistributedSPH:
         self.last = dict(nSendLow=nLow, nSendHigh=nHigh, nFromLower=nFL, nFromUpper=nFU,
                          h2h_bytes=(nLow + nHigh)*(self.bytesA + self.bytesB), two_phase=bool(self.two_phase))
         return npairs
+
+    def apply_ghosts(self, names=None):
+        """Integrator::applyGhostBoundaries on the ghost set of the last refresh: the current values of the send nodes travel
+        again and land in the same ghost slots; the connectivity is kept (DistributedBoundary::applyGhostBoundary,
+        Distributed/DistributedBoundary.cc:210-330)."""
+        e, h = self.e, self.halo
+        nInt, L_ = self.nInternal, self.last
+        nLow, nHigh, nFL, nFU = L_["nSendLow"], L_["nSendHigh"], L_["nFromLower"], L_["nFromUpper"]
+        mask = (self.maskA | self.maskB) if names is None else field_mask(names)
+        w = e.halo_bytes_per_node(mask)//8
+        with torch.cuda.stream(self.stream):
+            e.halo_pack(mask, self.idxLow.data_ptr(), nLow, self.sLowB.data_ptr())
+            e.halo_pack(mask, self.idxHigh.data_ptr(), nHigh, self.sHighB.data_ptr())
+            h.finish(h.start(self.sLowB[:nLow*w], self.sHighB[:nHigh*w], self.rLowB[:nFL*w], self.rHighB[:nFU*w]))
+            e.halo_unpack_values(mask, nInt, nFL, self.rLowB.data_ptr())
+            e.halo_unpack_values(mask, nInt + nFL, nFU, self.rHighB.data_ptr())
+
+    def finalize_derivatives(self):
+        """SPHBase::finalizeDerivatives (SPHBase.cc:502-519) across the slab faces: the ghost entries of DvDt and DepsDt become
+        their owners' values; SpecificThermalEnergyPolicy reads them for the ghost end of an internal-ghost pair."""
+        e, h = self.e, self.halo
+        nInt, L_ = self.nInternal, self.last
+        nLow, nHigh, nFL, nFU = L_["nSendLow"], L_["nSendHigh"], L_["nFromLower"], L_["nFromUpper"]
+        w = e.ndim + 1
+        with torch.cuda.stream(self.stream):
+            e.halo_pack_derivs(self.idxLow.data_ptr(), nLow, self.sLowB.data_ptr())
+            e.halo_pack_derivs(self.idxHigh.data_ptr(), nHigh, self.sHighB.data_ptr())
+            h.finish(h.start(self.sLowB[:nLow*w], self.sHighB[:nHigh*w], self.rLowB[:nFL*w], self.rHighB[:nFU*w]))
+            e.halo_unpack_derivs(nInt, nFL, self.rLowB.data_ptr())
+            e.halo_unpack_derivs(nInt + nFL, nFU, self.rHighB.data_ptr())
+
+    def allreduce_min(self, x):
+        """Integrator::selectDt's allReduce(dt, MIN) (Integrator.cc:150-154)."""
+        if self.halo.world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.halo.group)
+        return float(t.item())
 
     def info(self):
         """Counts of the last refresh plus the halo width (read back from the device here, outside the hot path)."""

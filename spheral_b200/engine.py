@@ -283,6 +283,16 @@ class Engine:
     def halo_unpack(self, mask, first_ghost, count, staging_ptr):
         self._check(self._lib.sphb200_halo_unpack(self._h, mask, first_ghost, count, staging_ptr))
 
+    def halo_unpack_values(self, mask, first_ghost, count, staging_ptr):
+        """Ghost-value refresh that keeps the connectivity (applyGhostBoundaries between the stages of a step)."""
+        self._check(self._lib.sphb200_halo_unpack_values(self._h, mask, first_ghost, count, staging_ptr))
+
+    def halo_pack_derivs(self, send_nodes_ptr, count, staging_ptr):
+        self._check(self._lib.sphb200_halo_pack_derivs(self._h, send_nodes_ptr, count, staging_ptr))
+
+    def halo_unpack_derivs(self, first_ghost, count, staging_ptr):
+        self._check(self._lib.sphb200_halo_unpack_derivs(self._h, first_ghost, count, staging_ptr))
+
     def node_bounds(self, count=None):
         """(lo[ndim], hi[ndim], maxExtent[ndim]) of nodes [0,count) -- default: the internal nodes."""
         lo, hi, ext = np.zeros(3), np.zeros(3), np.zeros(3)

@@ -18,7 +18,7 @@ INTEGRATE_DENSITY, RIGOROUS_SUM_DENSITY = 0, 1      # MassDensityType (Hydro/Gen
 class CheapSynchronousRK2:
     def __init__(self, engine, step_options=None, densityUpdate=RIGOROUS_SUM_DENSITY, gradhCorrection=True, cfl=0.25,
                  useVelocityMagnitudeForDt=False, dtMin=0.0, dtMax=1.0e100, dtGrowth=2.0, allowDtCheck=False,
-                 ghostRefresh=None, reflectingPlanes=None):
+                 ghostRefresh=None, reflectingPlanes=None, distributed=None):
         self.engine = engine
         self.so = step_options if step_options is not None else E.make_step_options()
         self.densityUpdate, self.gradhCorrection = densityUpdate, gradhCorrection
@@ -32,6 +32,10 @@ class CheapSynchronousRK2:
         self.reflectingPlanes = reflectingPlanes
         if reflectingPlanes:
             engine.reflect_configure(reflectingPlanes)
+        # domain decomposition (spheral_b200.distributed.DistributedSPH): ghost exchange with the neighbouring slabs over NCCL
+        self.distributed = distributed
+        if distributed is not None and reflectingPlanes:
+            raise ValueError("reflecting planes and the slab halo both own the ghost tail; combining them is not supported yet")
         self.currentTime, self.currentCycle, self.lastDt = 0.0, 0, 1.0e100
         self.dtMultiplier = 1.0
         self.lastDtReason, self.lastDtNode = "", 0
@@ -42,18 +46,26 @@ class CheapSynchronousRK2:
         """applyGhostBoundaries + finalizeGhostBoundaries (Integrator.cc:530-600)."""
         if self.reflectingPlanes:
             self.engine.reflect_apply_ghosts()
+        if self.distributed is not None:
+            self.distributed.apply_ghosts()
         if self.ghostRefresh is not None:
             self.ghostRefresh()
 
     def _finalize_derivatives(self):
         """SPHBase::finalizeDerivatives (SPHBase.cc:502-519): boundary conditions on DvDt and DepsDt for the compatible energy."""
-        if self.reflectingPlanes and self.engine.options.compatibleEnergy:
+        if not self.engine.options.compatibleEnergy:
+            return
+        if self.reflectingPlanes:
             self.engine.reflect_finalize_derivatives()
+        if self.distributed is not None:
+            self.distributed.finalize_derivatives()
 
     def _set_ghost_nodes(self):
         """Integrator::setGhostNodes (Integrator.cc:372-445): regenerate the ghost nodes, then refresh their values."""
         if self.reflectingPlanes:
             self.engine.reflect_set_ghost_nodes()
+        if self.distributed is not None:
+            self.distributed.refresh_ghosts(build=False)
         if self.ghostRefresh is not None:
             self.ghostRefresh()
 
@@ -69,6 +81,8 @@ class CheapSynchronousRK2:
     def selectDt(self, dtMin, dtMax):
         """Integrator::selectDt (Integrator.cc:114-166) with the one package vote of GenericHydro::dt."""
         vote, why, node = self.engine.compute_dt(self.cfl, self.useVelocityMagnitudeForDt)
+        if self.distributed is not None:
+            vote = self.distributed.allreduce_min(vote)          # allReduce(dt, MIN), Integrator.cc:150-154
         dt = dtMax
         if 0.0 < vote < dt:
             dt = vote
