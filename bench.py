@@ -396,10 +396,22 @@ def main():
         if crk:                                      # + volume and 16 RK coefficients per node in; ~560 flop per pair
             bytes_alg = N*(672.0 + 136.0 + 12.0*nbrs)
             flops_alg = N*280.0*nbrs
+        # DRAM bytes the dominant kernel really moved per launch: from the committed `ncu --set full` capture of this workload
+        # (profiles/traffic.json, written by scripts/ncu_traffic.py); null for workloads / sizes without a capture
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            ent = tj.get(args.workload if not args.n and not args.hjitter else "", {})
+            key = "k_crk_derivs" if crk else "k_sph_derivs"
+            if key in ent:
+                traffic = float(ent[key]["dram_bytes_read"]) + float(ent[key]["dram_bytes_write"])
+                traffic_src = ent[key].get("source")
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": ("k_crk_derivs (CRKSPH pair loop + finalize + smoothing scale)" if crk else
                                                "k_sph_derivs (SPH pair loop + finalize + smoothing scale)"),
                     "achieved": bytes_alg/t_pair/1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": bytes_alg/t_pair/1e9/hbm_peak, "traffic": None, "peak_source": hbm_src,
+                    "frac": bytes_alg/t_pair/1e9/hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": hbm_src,
                     "algorithmic_bytes_per_particle": bytes_alg/N,
                     "note": "the pair loop is FP64-pipe bound at ~100 neighbours (arithmetic intensity ~13 flop/B vs machine balance ~5); see roofline_fp64"}
         roofline_fp64 = {"bound": "fp64", "achieved": flops_alg/t_pair/1e12, "peak": fp64_peak, "unit": "TFLOP/s",
