@@ -182,6 +182,16 @@ int alloc_nodes(sphb200_ctx* c, size_t n) {
   return 0;
 }
 
+}  // namespace
+
+int sphb200_join_uploads(sphb200_ctx* c, bool all) {
+  if (c->pendGeomUp) { CU_CHECK(c, cudaStreamWaitEvent(c->stream, c->evGeomUp, 0)); c->pendGeomUp = false; }
+  if (all && c->pendRestUp) { CU_CHECK(c, cudaStreamWaitEvent(c->stream, c->evRestUp, 0)); c->pendRestUp = false; }
+  return 0;
+}
+
+namespace {
+
 int ensure_stage(sphb200_ctx* c, size_t bytes) {
   if (bytes <= c->stageBytes) return 0;
   if (c->stage) cudaFree(c->stage);
@@ -231,6 +241,9 @@ int sphb200_create(sphb200_ctx** out, int device, const sphb200_options* opts) {
     return sphb200_fail(nullptr, "cudaSetDevice/cudaStreamCreate failed");
   }
   for (auto& ev : c->ev) cudaEventCreate(&ev);
+  cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->evGeomUp, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->evRestUp, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->evMainMark, cudaEventDisableTiming);
   cudaMalloc((void**)&c->reduceBuf, (296*9 + 16)*sizeof(double));
   cudaMallocHost((void**)&c->reduceHost, 16*sizeof(double));
   cudaMalloc((void**)&c->counters, 16*sizeof(unsigned long long));      // [0,8) neighbour build, [8] anisotropy flag of k_pack
@@ -245,7 +258,9 @@ int sphb200_create(sphb200_ctx** out, int device, const sphb200_options* opts) {
 void sphb200_destroy(sphb200_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->copyStream) { cudaStreamSynchronize(c->copyStream); cudaStreamDestroy(c->copyStream); }
   if (c->stream) cudaStreamSynchronize(c->stream);
+  for (cudaEvent_t ev : {c->evGeomUp, c->evRestUp, c->evMainMark}) if (ev) cudaEventDestroy(ev);
   for (int s = 0; s < S_COUNT; ++s) cudaFree(c->api[s]);
   for (int s = 0; s < DV_COUNT; ++s) cudaFree(c->deriv[s]);
   for (void* p : {(void*)c->W.coef, (void*)c->W.nperhVals, (void*)c->WQ.coef, (void*)c->WQ.nperhVals, (void*)c->cellKeyApi, (void*)c->cellStart,
@@ -274,8 +289,9 @@ int sphb200_set_options(sphb200_ctx* c, const sphb200_options* o) {
 }
 
 int sphb200_sync(sphb200_ctx* c) {
+  if (c && c->copyStream) cudaStreamSynchronize(c->copyStream);
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   CU_CHECK(c, cudaStreamSynchronize(c->stream));
   CU_CHECK(c, cudaGetLastError());
   return 0;
@@ -290,7 +306,7 @@ int sphb200_set_kernel_table(sphb200_ctx* c, int which, double kext, double xmin
   if (!c) return sphb200_fail(nullptr, "null ctx");
   if (which != SPHB200_TABLE_W && which != SPHB200_TABLE_WPI) return sphb200_fail(c, "set_kernel_table: bad table id");
   if (!Wc || !gWc || !(kext > 0.0) || !(xstep > 0.0)) return sphb200_fail(c, "set_kernel_table: bad arguments");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   TableDev& t = (which == SPHB200_TABLE_W) ? c->W : c->WQ;
   const size_t nint = n1 + 1;
   std::vector<double> inter(6*nint);
@@ -319,7 +335,7 @@ int sphb200_set_kernel_table(sphb200_ctx* c, int which, double kext, double xmin
 
 int sphb200_set_nodes(sphb200_ctx* c, size_t nInternal, size_t nGhost) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   const size_t n = nInternal + nGhost;
   if (n >= 0x7fffffffull) return sphb200_fail(c, "set_nodes: more than 2^31-1 nodes per GPU is not supported");
   if (n > c->cap) CU_CHECK(c, cudaStreamSynchronize(c->stream));      // reallocation frees arrays in-flight work may use
@@ -344,23 +360,36 @@ int sphb200_upload_state(sphb200_ctx* c, unsigned mask, const sphb200_host_state
   if (!c) return sphb200_fail(nullptr, "null ctx");
   if (!s) return sphb200_fail(c, "upload_state: null state");
   CU_CHECK(c, cudaSetDevice(c->device));
-  for (int slot = 0; slot < S_COUNT; ++slot) {
-    if (!(mask & (1u << slot))) continue;
-    const double* src = state_ptr(s, slot);
-    if (!src) return sphb200_fail(c, "upload_state: field selected in mask but pointer is null");
-    if (!c->api[slot] && c->n) return sphb200_fail(c, "upload_state: volume / RK corrections exist only in CRKSPH contexts");
-    const size_t bytes = c->n*(size_t)sphb200_state_width(c->ndim, slot)*sizeof(double);
-    if (bytes) CU_CHECK(c, cudaMemcpyAsync(c->api[slot], src, bytes, cudaMemcpyHostToDevice, c->stream));
-    c->have[slot] = true;
-    if (slot == S_POS || slot == S_H) { c->sortValid = false; c->pairsValid = false; }
-    if (slot != S_EPS && slot != S_VOLUME && slot != S_RKCORR) c->rowsValid = false;
+  for (int slot = 0; slot < S_COUNT; ++slot)
+    if ((mask & (1u << slot)) && !state_ptr(s, slot)) return sphb200_fail(c, "upload_state: field selected in mask but pointer is null");
+  // the copy stream starts after everything already queued on the main stream (kernels there may still read the arrays)
+  // and after its own earlier copies; positions and H go first so that build_pairs can start while the rest is in flight
+  CU_CHECK(c, cudaEventRecord(c->evMainMark, c->stream));
+  CU_CHECK(c, cudaStreamWaitEvent(c->copyStream, c->evMainMark, 0));
+  for (int pass = 0; pass < 2; ++pass) {
+    bool any = false;
+    for (int slot = 0; slot < S_COUNT; ++slot) {
+      if (!(mask & (1u << slot))) continue;
+      const bool geom = (slot == S_POS || slot == S_H);
+      if (geom != (pass == 0)) continue;
+      const double* src = state_ptr(s, slot);
+      if (!c->api[slot] && c->n) return sphb200_fail(c, "upload_state: volume / RK corrections exist only in CRKSPH contexts");
+      const size_t bytes = c->n*(size_t)sphb200_state_width(c->ndim, slot)*sizeof(double);
+      if (bytes) CU_CHECK(c, cudaMemcpyAsync(c->api[slot], src, bytes, cudaMemcpyHostToDevice, c->copyStream));
+      any = true;
+      c->have[slot] = true;
+      if (geom) { c->sortValid = false; c->pairsValid = false; }
+      if (slot != S_EPS && slot != S_VOLUME && slot != S_RKCORR) c->rowsValid = false;
+    }
+    if (any && pass == 0) { CU_CHECK(c, cudaEventRecord(c->evGeomUp, c->copyStream)); c->pendGeomUp = true; }
+    if (any && pass == 1) { CU_CHECK(c, cudaEventRecord(c->evRestUp, c->copyStream)); c->pendRestUp = true; }
   }
   return 0;
 }
 
 int sphb200_download_state(sphb200_ctx* c, unsigned mask, double* const* fields) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   for (int slot = 0; slot < S_COUNT; ++slot) {
     if (!(mask & (1u << slot))) continue;
     if (!fields[slot]) return sphb200_fail(c, "download_state: null destination");
@@ -375,6 +404,10 @@ int sphb200_download_state(sphb200_ctx* c, unsigned mask, double* const* fields)
 int sphb200_build_pairs(sphb200_ctx* c, size_t* npairs) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
   CU_CHECK(c, cudaSetDevice(c->device));
+  // only positions and H are needed here: the other state fields may still be in flight on the copy stream (k_pack then reads
+  // stale values of those, which is harmless: the rows are marked stale and re-packed once the fields have landed)
+  if (sphb200_join_uploads(c, false)) return 1;
+  const bool restInFlight = c->pendRestUp;
   if (c->n == 0) { c->npairs = c->nEdges = c->nSlots = 0; c->nTiles = 0; c->pairsValid = true; c->sortValid = true; c->rowsValid = true; if (npairs) *npairs = 0; return 0; }
   cudaEventRecord(c->ev[0], c->stream);
   if (sphb200_sort_and_pack(c)) return 1;
@@ -385,6 +418,7 @@ int sphb200_build_pairs(sphb200_ctx* c, size_t* npairs) {
   cudaEventElapsedTime(&c->stats.ms_build_pairs, c->ev[0], c->ev[2]);
   cudaEventElapsedTime(&c->stats.ms_neighbor_kernels, c->ev[1], c->ev[2]);
   c->derivsValid = false;
+  if (restInFlight) c->rowsValid = false;
   if (npairs) *npairs = c->npairs;
   return 0;
 }
@@ -392,7 +426,7 @@ int sphb200_build_pairs(sphb200_ctx* c, size_t* npairs) {
 int sphb200_download_pairs(sphb200_ctx* c, uint32_t* i, uint32_t* j, size_t cap) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
   if (!c->pairsValid) return sphb200_fail(c, "download_pairs: no valid pair list (call build_pairs after changing position/H)");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (c->npairs == 0) return 0;
   return sphb200_pairs_to_host(c, i, j, cap, nullptr, 0);
 }
@@ -401,7 +435,7 @@ int sphb200_download_pair_accelerations(sphb200_ctx* c, double* pacc, size_t cap
   if (!c) return sphb200_fail(nullptr, "null ctx");
   if (!c->pairsValid || !c->derivsValid) return sphb200_fail(c, "download_pair_accelerations: derivatives have not been evaluated for the current pair list");
   if (!c->opt.compatibleEnergy) return sphb200_fail(c, "download_pair_accelerations: pair-wise accelerations exist only with compatibleEnergyEvolution (SPH.cc:129-133)");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (c->npairs == 0) return 0;
   return sphb200_pairs_to_host(c, nullptr, nullptr, 0, pacc, cap);
 }
@@ -409,7 +443,7 @@ int sphb200_download_pair_accelerations(sphb200_ctx* c, double* pacc, size_t cap
 int sphb200_download_neighbor_counts(sphb200_ctx* c, uint32_t* counts) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
   if (!c->pairsValid) return sphb200_fail(c, "download_neighbor_counts: no valid pair list");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (c->nInt == 0) return 0;
   if (ensure_stage(c, c->nInt*sizeof(uint32_t))) return 1;
   k_counts_by_orig<<<(unsigned)((c->n + RB - 1)/RB), RB, 0, c->stream>>>(c->nbrCount, c->perm, c->n, (uint32_t)c->nInt, (uint32_t*)c->stage);
@@ -421,7 +455,7 @@ int sphb200_download_neighbor_counts(sphb200_ctx* c, uint32_t* counts) {
 
 int sphb200_evaluate_derivatives(sphb200_ctx* c, double /*time*/, double /*dt*/) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (!c->pairsValid) return sphb200_fail(c, "evaluateDerivatives: connectivity is stale or missing (requireConnectivity: call build_pairs first)");
   if (c->n == 0) { c->derivsValid = true; return 0; }
   const bool crk = c->opt.hydro == SPHB200_HYDRO_CRKSPH;
@@ -459,7 +493,7 @@ int sphb200_download_derivs(sphb200_ctx* c, unsigned mask, const sphb200_host_de
   if (!c) return sphb200_fail(nullptr, "null ctx");
   if (!d) return sphb200_fail(c, "download_derivs: null destination struct");
   if (!c->derivsValid) return sphb200_fail(c, "download_derivs: derivatives have not been evaluated");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (c->n == 0) return 0;
   size_t total = 0;
   for (int s = 0; s < DV_COUNT; ++s) if (mask & (1u << s)) total += c->n*(size_t)sphb200_deriv_width(c->ndim, s);
@@ -485,7 +519,7 @@ int sphb200_copy_DvDx_to_Q(sphb200_ctx* c) {
   // node-wise derivatives stay usable after a later build_pairs (permEval keeps the order they are stored in)
   if (!c->derivNodeValid) return sphb200_fail(c, "copy_DvDx_to_Q: derivatives have not been evaluated");
   if (c->nIntEval != c->nInt) return sphb200_fail(c, "copy_DvDx_to_Q: the internal node count changed since the derivatives were evaluated");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (c->n == 0) return 0;
   // same ghost set as at the evaluation: every node is written (ghost derivatives are zeros); otherwise the internal nodes only,
   // the ghost entries being the boundary conditions' / halo exchange's to fill (ArtificialViscosityHandle.cc:165-180 + boundaries)
@@ -500,7 +534,7 @@ int sphb200_copy_DvDx_to_Q(sphb200_ctx* c) {
 
 int sphb200_update_energy_compatible(sphb200_ctx* c, double multiplier) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (!c->opt.compatibleEnergy) return sphb200_fail(c, "update_energy_compatible: compatibleEnergyEvolution is off");
   if (!c->derivsValid || !c->pairsValid) return sphb200_fail(c, "update_energy_compatible: needs the derivatives and pair accelerations of the current pair list");
   for (int s : {S_VEL, S_MASS, S_EPS}) if (!c->have[s]) return sphb200_fail(c, "update_energy_compatible: velocity, mass and specific thermal energy must be on the device");
@@ -520,7 +554,7 @@ size_t sphb200_halo_bytes_per_node(const sphb200_ctx* c, unsigned mask) {
 
 int sphb200_halo_pack(sphb200_ctx* c, unsigned mask, const uint32_t* nodes, size_t count, void* staging) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   double* out = (double*)staging;
   for (int s = 0; s < S_COUNT; ++s) {
     if (!(mask & (1u << s))) continue;
@@ -537,7 +571,7 @@ int sphb200_halo_pack(sphb200_ctx* c, unsigned mask, const uint32_t* nodes, size
 
 static int halo_unpack_impl(sphb200_ctx* c, unsigned mask, size_t firstGhost, size_t count, const void* staging, bool keepConnectivity) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (firstGhost + count > c->n) return sphb200_fail(c, "halo_unpack: ghost range exceeds node count");
   const double* in = (const double*)staging;
   for (int s = 0; s < S_COUNT; ++s) {
@@ -569,7 +603,7 @@ int sphb200_inverse_perm(sphb200_ctx* c) {
 
 int sphb200_halo_pack_derivs(sphb200_ctx* c, const uint32_t* nodes, size_t count, void* staging) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (!c->derivsValid || !c->pairsValid) return sphb200_fail(c, "halo_pack_derivs: derivatives have not been evaluated on the current connectivity");
   if (count == 0) return 0;
   if (!nodes || !staging) return sphb200_fail(c, "halo_pack_derivs: null argument");
@@ -582,7 +616,7 @@ int sphb200_halo_pack_derivs(sphb200_ctx* c, const uint32_t* nodes, size_t count
 
 int sphb200_halo_unpack_derivs(sphb200_ctx* c, size_t firstGhost, size_t count, const void* staging) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (!c->derivsValid || !c->pairsValid) return sphb200_fail(c, "halo_unpack_derivs: derivatives have not been evaluated on the current connectivity");
   if (firstGhost + count > c->n) return sphb200_fail(c, "halo_unpack_derivs: ghost range exceeds node count");
   if (count == 0) return 0;
@@ -596,7 +630,7 @@ int sphb200_halo_unpack_derivs(sphb200_ctx* c, size_t firstGhost, size_t count, 
 
 int sphb200_node_bounds(sphb200_ctx* c, size_t count, double lo[3], double hi[3], double maxExtent[3]) {
   if (!c || !lo || !hi || !maxExtent) return sphb200_fail(c, "node_bounds: null argument");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (count > c->n) return sphb200_fail(c, "node_bounds: count exceeds node count");
   if (!c->have[S_POS] || !c->have[S_H] || !c->W.set) return sphb200_fail(c, "node_bounds: position, H and the kernel table must be set first");
   for (int a = 0; a < 3; ++a) { lo[a] = 0.0; hi[a] = 0.0; maxExtent[a] = 0.0; }
@@ -610,7 +644,7 @@ int sphb200_node_bounds(sphb200_ctx* c, size_t count, double lo[3], double hi[3]
 int sphb200_halo_select(sphb200_ctx* c, int axis, size_t count, double lo, double hi, double width,
                         uint32_t* sendLow, size_t* nLow, uint32_t* sendHigh, size_t* nHigh, size_t cap) {
   if (!c || !nLow || !nHigh) return sphb200_fail(c, "halo_select: null argument");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (axis < 0 || axis >= c->ndim) return sphb200_fail(c, "halo_select: bad axis");
   if (count > c->n) return sphb200_fail(c, "halo_select: count exceeds node count");
   if (!c->have[S_POS]) return sphb200_fail(c, "halo_select: positions are not on the device");
@@ -636,7 +670,7 @@ int sphb200_halo_select(sphb200_ctx* c, int axis, size_t count, double lo, doubl
 
 int sphb200_node_bounds_device(sphb200_ctx* c, size_t count, double* outDevice) {
   if (!c || !outDevice) return sphb200_fail(c, "node_bounds_device: null argument");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (count > c->n || count == 0) return sphb200_fail(c, "node_bounds_device: count must be in [1, node count]");
   if (!c->have[S_POS] || !c->have[S_H] || !c->W.set) return sphb200_fail(c, "node_bounds_device: position, H and the kernel table must be set first");
   if (sphb200_bounds_reduce(c, count)) return 1;
@@ -647,7 +681,7 @@ int sphb200_node_bounds_device(sphb200_ctx* c, size_t count, double* outDevice) 
 int sphb200_halo_select_device(sphb200_ctx* c, int axis, size_t count, double lo, double hi, const double* maxExtentDevice,
                                uint32_t* sendLow, uint32_t* sendHigh, long long* countsDevice, size_t cap) {
   if (!c || !maxExtentDevice || !countsDevice) return sphb200_fail(c, "halo_select_device: null argument");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (axis < 0 || axis >= c->ndim) return sphb200_fail(c, "halo_select_device: bad axis");
   if (count > c->n || count == 0) return sphb200_fail(c, "halo_select_device: count must be in [1, node count]");
   if (!c->have[S_POS]) return sphb200_fail(c, "halo_select_device: positions are not on the device");
@@ -667,7 +701,7 @@ int sphb200_halo_select_device(sphb200_ctx* c, int axis, size_t count, double lo
 
 int sphb200_get_stats(sphb200_ctx* c, sphb200_stats* out) {
   if (!c || !out) return sphb200_fail(c, "get_stats: null argument");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   CU_CHECK(c, cudaStreamSynchronize(c->stream));
   if (c->derivsValid && c->n) {
     if (cudaEventElapsedTime(&c->stats.ms_evaluate, c->ev[3], c->ev[5]) != cudaSuccess) c->stats.ms_evaluate = 0;
@@ -681,7 +715,7 @@ int sphb200_get_stats(sphb200_ctx* c, sphb200_stats* out) {
 
 int sphb200_measure_fp64_peak(sphb200_ctx* c, double* tflops) {
   if (!c || !tflops) return sphb200_fail(c, "measure_fp64_peak: null argument");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   cudaDeviceProp prop;
   CU_CHECK(c, cudaGetDeviceProperties(&prop, c->device));
   const int blocks = prop.multiProcessorCount*8, threads = 256, iters = 20000;

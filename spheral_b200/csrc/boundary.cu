@@ -226,7 +226,7 @@ int sphb200_reflect_configure(sphb200_ctx* c, int nPlanes, const double* points,
 
 int sphb200_reflect_set_ghost_nodes(sphb200_ctx* c, size_t* nGhostOut) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (!c->have[S_POS] || !c->have[S_H]) return sphb200_fail(c, "reflect_set_ghost_nodes: position and H must be on the device");
   if (!c->W.set) return sphb200_fail(c, "reflect_set_ghost_nodes: kernel table not set (need the kernel extent)");
   const double kext = std::max(c->W.kext, c->WQ.set ? c->WQ.kext : 0.0);
@@ -278,7 +278,7 @@ int sphb200_reflect_set_ghost_nodes(sphb200_ctx* c, size_t* nGhostOut) {
 
 int sphb200_reflect_apply_ghosts(sphb200_ctx* c, unsigned fieldMask) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   size_t total = 0;
   for (int p = 0; p < c->nPlanes; ++p) total += c->planeCount[p];
   if (total != c->nGhost) return sphb200_fail(c, "reflect_apply_ghosts: the ghost nodes were not generated by reflect_set_ghost_nodes (or the node count changed since)");
@@ -290,7 +290,7 @@ int sphb200_reflect_apply_ghosts(sphb200_ctx* c, unsigned fieldMask) {
 
 int sphb200_reflect_finalize_derivatives(sphb200_ctx* c) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (!c->derivsValid || !c->pairsValid) return sphb200_fail(c, "reflect_finalize_derivatives: derivatives have not been evaluated on the current connectivity");
   size_t total = 0;
   for (int p = 0; p < c->nPlanes; ++p) total += c->planeCount[p];
@@ -311,7 +311,7 @@ int sphb200_reflect_finalize_derivatives(sphb200_ctx* c) {
 
 int sphb200_reflect_enforce(sphb200_ctx* c, size_t* nViolations) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (!c->have[S_POS] || !c->have[S_VEL]) return sphb200_fail(c, "reflect_enforce: position and velocity must be on the device");
   if (nViolations) *nViolations = 0;
   if (c->nInt == 0 || c->nPlanes == 0) return 0;

@@ -772,7 +772,7 @@ extern "C" {
 
 int sphb200_crk_compute_volume(sphb200_ctx* c) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   CrkArgs a;
   if (crk_common(c, a, "crk_compute_volume")) return 1;
   if (c->n == 0) return 0;
@@ -784,7 +784,7 @@ int sphb200_crk_compute_volume(sphb200_ctx* c) {
 
 int sphb200_crk_compute_corrections(sphb200_ctx* c) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   CrkArgs a;
   if (crk_common(c, a, "crk_compute_corrections")) return 1;
   if (!c->have[S_VOLUME]) return sphb200_fail(c, "crk_compute_corrections: the volume is not on the device (call crk_compute_volume or upload it)");
@@ -799,7 +799,7 @@ int sphb200_crk_compute_corrections(sphb200_ctx* c) {
 
 int sphb200_crk_sum_mass_density(sphb200_ctx* c, double rhoMin, double rhoMax) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   CrkArgs a;
   if (crk_common(c, a, "crk_sum_mass_density")) return 1;
   if (!c->have[S_VOLUME] || !c->have[S_MASS]) return sphb200_fail(c, "crk_sum_mass_density: volume and mass must be on the device");

@@ -70,6 +70,11 @@ struct sphb200_ctx {
   int ndim = 3;
   sphb200_options opt{};
   cudaStream_t stream = nullptr;
+  // host->device uploads run on their own stream so that the neighbour build (which needs positions and H only) overlaps the
+  // transfer of the other state fields; every entry point joins the pending uploads it depends on (sphb200_join_uploads)
+  cudaStream_t copyStream = nullptr;
+  cudaEvent_t evGeomUp = nullptr, evRestUp = nullptr, evMainMark = nullptr;
+  bool pendGeomUp = false, pendRestUp = false;
   std::string err;
 
   size_t nInt = 0, nGhost = 0, n = 0, cap = 0;
@@ -162,6 +167,7 @@ int sphb200_scan_u32(sphb200_ctx* c, const uint32_t* in, uint32_t* out, size_t n
 int sphb200_scan_tiles(sphb200_ctx* c, const uint32_t* rows, unsigned long long* out, size_t n);   // out = 32*rows prefix
 
 // implemented in neighbors.cu / derivs.cu / energy.cu
+int sphb200_join_uploads(sphb200_ctx* c, bool all);   // main stream waits for pending uploads: positions + H only, or everything
 int sphb200_sort_and_pack(sphb200_ctx* c);
 extern "C" int sphb200_inverse_perm(sphb200_ctx* c);        // (re)builds c->invPerm from the current sort (api.cu)
 int sphb200_bounds_reduce(sphb200_ctx* c, size_t count);   // bbox + max extents of nodes [0,count) -> reduceHost[0..8] (async copy)

@@ -379,7 +379,7 @@ extern "C" {
 
 int sphb200_sum_mass_density(sphb200_ctx* c) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (!c->have[S_MASS]) return sphb200_fail(c, "sum_mass_density: the mass is not on the device");
   if (c->n == 0) return 0;
   if (loop_ready(c, "sum_mass_density")) return 1;
@@ -394,7 +394,7 @@ int sphb200_sum_mass_density(sphb200_ctx* c) {
 
 int sphb200_compute_omega_gradh(sphb200_ctx* c) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (c->n == 0) return 0;
   if (loop_ready(c, "compute_omega_gradh")) return 1;
   LoopArgs a; fill_loop_args(c, a);
@@ -415,7 +415,7 @@ int sphb200_update_eos_gamma_law(sphb200_ctx* c, const sphb200_gamma_law* e) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
   if (!e) return sphb200_fail(c, "update_eos_gamma_law: null equation of state");
   if (!(e->gamma > 1.0)) return sphb200_fail(c, "update_eos_gamma_law: gamma must exceed 1");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (!c->have[S_RHO] || !c->have[S_EPS]) return sphb200_fail(c, "update_eos_gamma_law: mass density and specific thermal energy must be on the device");
   if (c->n == 0) return 0;
   k_eos_gamma<<<(unsigned)((c->n + RB - 1)/RB), RB, 0, c->stream>>>(c->api[S_RHO], c->api[S_EPS], c->n, *e, c->api[S_P], c->api[S_CS]);
@@ -428,7 +428,7 @@ int sphb200_update_eos_gamma_law(sphb200_ctx* c, const sphb200_gamma_law* e) {
 int sphb200_state_update(sphb200_ctx* c, const sphb200_step_options* so, double multiplier, int timeAdvanceOnly) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
   if (!so) return sphb200_fail(c, "state_update: null options");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (!c->derivNodeValid) return sphb200_fail(c, "state_update: no derivatives on the device (call evaluate_derivatives first)");
   if (c->nIntEval != c->nInt) return sphb200_fail(c, "state_update: the internal node count changed since the derivatives were evaluated");
   for (int s : {S_POS, S_VEL, S_H, S_RHO, S_EPS})
@@ -458,7 +458,7 @@ int sphb200_state_update(sphb200_ctx* c, const sphb200_step_options* so, double 
 
 int sphb200_state_copy(sphb200_ctx* c) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   for (int s = 0; s < S_COUNT; ++s) {
     if (!c->have[s] || !c->api[s]) { c->have0[s] = false; continue; }
     const size_t bytes = c->cap*(size_t)sphb200_state_width(c->ndim, s)*sizeof(double);
@@ -477,7 +477,7 @@ int sphb200_state_copy(sphb200_ctx* c) {
 
 int sphb200_state_assign(sphb200_ctx* c) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (c->n0 != c->n) return sphb200_fail(c, "state_assign: the node count changed since state_copy");
   for (int s = 0; s < S_COUNT; ++s) {
     if (!c->have0[s]) continue;
@@ -489,7 +489,7 @@ int sphb200_state_assign(sphb200_ctx* c) {
 
 int sphb200_compute_dt(sphb200_ctx* c, double cfl, int useVelocityMagnitudeForDt, double* dt, int* reason, uint32_t* node) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device));
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (!c->derivNodeValid)
     return sphb200_fail(c, "compute_dt: no derivatives on the device (call evaluate_derivatives first; a growth of the node arrays discards them: n = " +
                         std::to_string(c->n) + ", capacity " + std::to_string(c->cap) + ", at the evaluation " + std::to_string(c->nEval) + " / " + std::to_string(c->capEval) + ")");
