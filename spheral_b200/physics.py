@@ -490,15 +490,60 @@ class SPHB200(Physics):
             if k in derivs:
                 derivs[k][...] = got[abi].reshape(derivs[k].shape)
 
+    def preStepInitialize(self, dataBase, state, derivs):
+        """SPHBase::preStepInitialize (SPH/SPHBase.cc:322-352): with RigorousSumDensity the mass density is replaced by the SPH
+        sum (computeSPHSumMassDensity) before the step; done on the device, the State's field is refreshed."""
+        if self.densityUpdate != RigorousSumDensity or self._engine is None:
+            return
+        nl = dataBase.nodeLists[0]
+        self._sync_state(nl, state, ("position", "H", "mass", "massDensity"))
+        if (self._uploaded.get("position"), self._uploaded.get("H")) != self._pairsKey or not dataBase.connectivityValid:
+            raise SPHB200Error("SPH::preStepInitialize: connectivity is stale (positions/H changed since updateConnectivity)")
+        self._engine.sum_mass_density()
+        k = _key(HydroFieldNames.massDensity, nl.name)
+        state[k][...] = self._engine.download_state("massDensity")["massDensity"]
+        self._uploaded["massDensity"] = (id(state[k]), self._dirty.get("massDensity", 0))
+
     def postStateUpdate(self, time, dt, dataBase, state, derivs):
         """ArtificialViscosityHandle::postStateUpdate copies DvDx into the Q's velocity gradient
-        (ArtificialViscosityHandle.cc:165-180); done device-side."""
-        if HydroFieldNames.ArtificialViscosityVelocityGradient in self._own and self._engine is not None:
+        (ArtificialViscosityHandle.cc:165-180) and SPHBase::postStateUpdate recomputes the grad-h corrections
+        (SPHBase.cc:527-547, computeSPHOmegaGradhCorrection); both device-side.  Returns True when boundaries must be
+        re-applied (the grad-h field changed), as the reference does."""
+        if self._engine is None:
+            return False
+        nl = dataBase.nodeLists[0]
+        if HydroFieldNames.ArtificialViscosityVelocityGradient in self._own:
             self._engine.copy_DvDx_to_Q()
-            nl = dataBase.nodeLists[0]
             k = _key(HydroFieldNames.ArtificialViscosityVelocityGradient, nl.name)
             self._uploaded["DvDxQ"] = (id(state[k]), self._dirty.get("DvDxQ", 0)) if k in state else None
-        return False
+        if not self.gradhCorrection:
+            return False
+        self._sync_state(nl, state, ("position", "H"))
+        # the reference evaluates the corrections on the connectivity of the step start although positions moved
+        # (CheapSynchronousRK2.cc:76-84): the device keeps its pair lists unless build_pairs is called again
+        if not self._engine_pairs_usable():
+            self._engine.build_pairs()
+        self._engine.compute_omega_gradh()
+        k = _key(HydroFieldNames.omegaGradh, nl.name)
+        if k in state:
+            state[k][...] = self._engine.download_state("omegaGradh")["omegaGradh"]
+            self._uploaded["omegaGradh"] = (id(state[k]), self._dirty.get("omegaGradh", 0))
+        return True
+
+    def _engine_pairs_usable(self):
+        try:
+            self._engine.download_neighbor_counts()
+            return True
+        except SPHB200Error:
+            return False
+
+    def dt(self, dataBase, state, derivs, currentTime=0.0):
+        """GenericHydro::dt (Physics/GenericHydro.cc:112-381) -> (dt, reason), from the state on the host and the derivatives
+        of the last evaluateDerivatives call on the device."""
+        nl = dataBase.nodeLists[0]
+        self._sync_state(nl, state, ("velocity", "H", "massDensity", "soundSpeed"))
+        vote, why, node = self._engine.compute_dt(self.cfl, self.useVelocityMagnitudeForDt)
+        return vote, "%s limit: dt = %g (node %d)" % (why.capitalize(), vote, node)
 
     def updateSpecificThermalEnergy(self, multiplier, dataBase, state, derivs):
         """SpecificThermalEnergyPolicy::update (Hydro/SpecificThermalEnergyPolicy.cc:47-174) on the device; the new eps is

@@ -59,6 +59,28 @@ def crk_ghost_defaults(ndim, st):
     return st["mass"]/st["massDensity"], corr0
 
 
+STEP_MULT = 1.0e-3
+
+
+def step_outputs(orc, oo, OT, ndim, st, s, nInt, nGhost, pi, pj, cnt, ref):
+    """The per-step callers on the same inputs: sum density, grad-h correction, the dt vote and one
+    State::update (full policies, default step options) with the derivatives of this fixture."""
+    so = orc.default_step_options()
+    out = {"step_sum_density": orc.sum_mass_density(ndim, OT, nInt, nGhost, s["pos"], s["mass"], s["H"], pi, pj, rho=s["rho"]),
+           "step_omega": orc.omega_gradh(ndim, OT, nInt, nGhost, s["pos"], s["H"], pi, pj, cnt, omega=s["omega"])}
+    dt, why, node = orc.hydro_dt(oo, so, nInt, s["vel"], s["H"], s["rho"], s["cs"], ref, pi, pj)
+    out["step_dt"] = np.array([dt, float(orc.DT_REASONS.index(why)), float(node)])
+    s_in = dict(s, eps=st["specificThermalEnergy"])
+    epsDone = False
+    if oo.compatibleEnergy:
+        s_in["eps"] = orc.update_energy_compatible(ndim, nInt, nGhost, s["mass"], s["vel"], ref["DvDt"], ref["DepsDt"], pi, pj,
+                                                   ref["pairAccelerations"], STEP_MULT, s_in["eps"])
+        epsDone = True
+    upd = orc.state_update(oo, so, nInt, nGhost, STEP_MULT, False, ref, s_in, epsDone=epsDone)
+    out.update({"step_state_" + k: v for k, v in upd.items()})
+    return out
+
+
 def oracle_outputs(name):
     import common
     from oracle import oracle as orc
@@ -77,6 +99,7 @@ def oracle_outputs(name):
         extra = {"crk_volume": vol, "crk_corrections": corr}
     else:
         ref = orc.evaluate_derivatives(oo, OT, s, nInt, nGhost, pi, pj, cnt)
+        extra = step_outputs(orc, oo, OT, ndim, st, s, nInt, nGhost, pi, pj, cnt, ref)
     out = {"pairs_i": pi, "pairs_j": pj, "counts": cnt, "nInt": np.int64(nInt), "nGhost": np.int64(nGhost)}
     out.update(extra)
     out.update({"state_" + k: v for k, v in st.items()})

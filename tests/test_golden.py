@@ -28,7 +28,7 @@ def test_oracle_reproduces_golden(oracle, sphlib, name):
     for k in g.files:
         if k.startswith("state_"):
             assert np.array_equal(out[k], g[k]), "input generator drifted: " + k
-        if k.startswith("deriv_") or k.startswith("crk_"):
+        if k.startswith("deriv_") or k.startswith("crk_") or k.startswith("step_"):
             scale = max(float(np.abs(g[k]).max()), 1e-300)
             assert np.abs(out[k] - g[k]).max() <= 1e-13*scale, k
 
@@ -70,3 +70,23 @@ def test_cuda_path_matches_golden(sphlib, name):
     if opts.get("compatibleEnergy", 1):
         pa = e.download_pair_accelerations()
         assert np.abs(pa - g["deriv_pairAccelerations"]).max() <= 1e-10*max(np.abs(g["deriv_pairAccelerations"]).max(), 1e-300)
+    if crk:
+        return
+    # the per-step callers against the same fixture
+    def rel(a, b):
+        return float(np.abs(np.asarray(a)[:nInt] - np.asarray(b)[:nInt]).max()/max(np.abs(np.asarray(b)[:nInt]).max(), 1e-300))
+    dt, why, node = e.compute_dt(0.25, False)
+    assert abs(dt - g["step_dt"][0]) <= 1e-12*g["step_dt"][0]
+    assert engine.L.DT_REASONS.index(why) == int(g["step_dt"][1]) and node == int(g["step_dt"][2])
+    e.state_copy()
+    e.state_update(engine.make_step_options(), mg.STEP_MULT, False)
+    got = e.download_state("position", "velocity", "H", "massDensity", "specificThermalEnergy", "pressure", "soundSpeed")
+    names = dict(position="pos", velocity="vel", H="H", massDensity="rho", specificThermalEnergy="eps", pressure="P", soundSpeed="cs")
+    for k, o in names.items():
+        assert rel(got[k], g["step_state_" + o]) <= 1e-10, k
+    e.state_assign()
+    e.sum_mass_density()
+    e.compute_omega_gradh()
+    got = e.download_state("massDensity", "omegaGradh")
+    assert rel(got["massDensity"], g["step_sum_density"]) <= 1e-10
+    assert rel(got["omegaGradh"], g["step_omega"]) <= 1e-10

@@ -160,3 +160,40 @@ def test_crksph_hooks_against_oracle(sphlib, oracle):
     hydro.preStepInitialize(db, state, derivs)
     rho = oracle.crk_sum_density(3, OT, nInt, 0, s["pos"], s["mass"], vol, s["H"], pi, pj, rhoMin=nodes.rhoMin, rhoMax=nodes.rhoMax)
     assert np.abs(state.field("mass density", "nodes") - rho).max() <= 1e-10*rho.max()
+
+
+@pytest.mark.gpu
+def test_step_hooks_through_physics_interface(sphlib, oracle):
+    """preStepInitialize (sum density), postStateUpdate (grad-h correction) and dt() driven the way Integrator does
+    (Integrator.cc:177-183, 252-271, 114-166), against the oracle."""
+    P, st, nodes, db, WT, hydro = _setup(Q=None)
+    hydro.Q = P.MonaghanGingoldViscosity(2.0, 2.0)
+    hydro.initializeProblemStartup(db)
+    state, derivs = P.State(db, [hydro]), P.StateDerivatives(db, [hydro])
+    state.field("pressure", "nodes")[...] = st["pressure"]
+    state.field("sound speed", "nodes")[...] = st["soundSpeed"]
+    state.field("grad h corrections", "nodes")[...] = st["omegaGradh"]
+    hydro.updateConnectivity(db, state)
+    nInt = nodes.numInternalNodes
+    OT = common.oracle_table(oracle, WT)
+    s = common.to_oracle_state(st)
+    pi, pj, cnt = oracle.pairs(3, nInt, 0, s["pos"], s["H"], WT.kernelExtent)
+    # preStepInitialize: RigorousSumDensity is the factory default
+    hydro.preStepInitialize(db, state, derivs)
+    rho_ref = oracle.sum_mass_density(3, OT, nInt, 0, s["pos"], s["mass"], s["H"], pi, pj)
+    rho = state.field("mass density", "nodes")
+    assert np.abs(rho - rho_ref).max() <= 1e-10*np.abs(rho_ref).max()
+    # postStateUpdate: grad-h corrections, returns True (boundaries must be re-applied)
+    assert hydro.postStateUpdate(0.0, 1.0, db, state, derivs) is True
+    om_ref = oracle.omega_gradh(3, OT, nInt, 0, s["pos"], s["H"], pi, pj, cnt)
+    om = state.field("grad h corrections", "nodes")
+    assert np.abs(om - om_ref).max() <= 1e-10*np.abs(om_ref).max()
+    # dt after one evaluation
+    derivs.Zero()
+    hydro.evaluateDerivatives(0.0, 1.0, db, state, derivs)
+    s2 = dict(s, rho=rho_ref, omega=om_ref)
+    oo = oracle.default_options(3, nPerh=1.51, Cl=2.0, Cq=2.0)
+    d = oracle.evaluate_derivatives(oo, OT, s2, nInt, 0, pi, pj, cnt)
+    ref_dt, why, node = oracle.hydro_dt(oo, oracle.default_step_options(cfl=hydro.cfl), nInt, s2["vel"], s2["H"], s2["rho"], s2["cs"], d, pi, pj)
+    vote, reason = hydro.dt(db, state, derivs, 0.0)
+    assert abs(vote - ref_dt) <= 1e-11*ref_dt and reason.lower().startswith(why)
