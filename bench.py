@@ -353,7 +353,7 @@ def main():
     # device-resident CheapSynchronousRK2 steps: neighbour update + sum density + dt vote + trial advance +
     # grad-h correction + derivatives + compatible-energy update + full advance, no field leaving the GPU
     rk2 = None
-    if dsph is None and not crk:
+    if dsph is None:
         from spheral_b200 import integrator as I
         rk = I.CheapSynchronousRK2(e, engine.make_step_options())
         rk.initializeDerivatives()
@@ -363,9 +363,12 @@ def main():
         nrk = max(3, args.steps//2)
         rk_s, _ = timed(rk.step, nrk)
         rk2 = {"ms_per_step": rk_s/nrk*1e3, "value": N*nrk/rk_s, "unit": "particle-updates/s", "steps": nrk,
-               "what": "CheapSynchronousRK2 step with the state resident in HBM: build_pairs + computeSPHSumMassDensity + GenericHydro::dt + "
-                       "State::update (x2) + computeSPHOmegaGradhCorrection (x2) + evaluateDerivatives + compatible energy; "
-                       "one 16-byte read-back (dt) per step",
+               "what": ("CheapSynchronousRK2 step with the state resident in HBM: build_pairs + computeRKSumVolume + computeCRKSPHSumMassDensity + "
+                        "RK corrections (x2) + GenericHydro::dt + State::update (x2) + evaluateDerivatives + compatible energy; "
+                        "one 16-byte read-back (dt) per step" if crk else
+                        "CheapSynchronousRK2 step with the state resident in HBM: build_pairs + computeSPHSumMassDensity + GenericHydro::dt + "
+                        "State::update (x2) + computeSPHOmegaGradhCorrection (x2) + evaluateDerivatives + compatible energy; "
+                        "one 16-byte read-back (dt) per step"),
                "last_dt": rk.lastDt, "dt_reason": rk.lastDtReason}
         # put the bench state back (the e2e leg uploads it anyway)
         e.upload_state_pinned(up_mask, hs)

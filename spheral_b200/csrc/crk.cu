@@ -685,6 +685,8 @@ int crk_common(sphb200_ctx* c, CrkArgs& a, const char* who) {
   if (c->opt.hydro != SPHB200_HYDRO_CRKSPH) return sphb200_fail(c, std::string(who) + ": the context was not created for CRKSPH (options.hydro)");
   if (!c->pairsValid) return sphb200_fail(c, std::string(who) + ": connectivity is stale or missing (call build_pairs first)");
   if (!c->W.set) return sphb200_fail(c, std::string(who) + ": kernel table not set");
+  // positions / H may have moved on a kept connectivity (the mid-step evaluation of CheapSynchronousRK2): the sorted rows follow
+  if (c->n && !c->rowsValid && sphb200_pack_rows(c)) return 1;
   a = CrkArgs{};
   a.rows = c->rows; a.aux2 = c->aux2; a.perm = c->perm; a.nbrCount = c->nbrCount; a.tileRows = c->tileRows; a.tileOff = c->tileOff; a.nbr = c->nbr;
   a.volS = c->crkVolS; a.corrS = c->crkCorrS; a.qrecS = c->crkQS;

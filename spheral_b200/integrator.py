@@ -40,6 +40,11 @@ class CheapSynchronousRK2:
         self.dtMultiplier = 1.0
         self.lastDtReason, self.lastDtNode = "", 0
         self._needQ = (engine.options.Qkind == L.Q_LIMITED_MG) or bool(engine.options.balsara)
+        # CRKSPH (engine created with hydro = HYDRO_CRKSPH): the RKCorrections package runs in front of the hydro
+        # (SpheralController.py:690-745): volumes in preStepInitialize, corrections in initialize (before EVERY evaluation)
+        self._crk = engine.options.hydro == L.HYDRO_CRKSPH
+        if self._crk:
+            self.gradhCorrection = False                     # CRKSPHBase has no grad-h term
 
     # -- pieces of a stage -----------------------------------------------------------------------------------------------
     def _ghosts(self):
@@ -78,6 +83,29 @@ class CheapSynchronousRK2:
             e.compute_omega_gradh()                  # SPHBase.cc:539-547
             self._ghosts()
 
+    def _pre_step_initialize(self):
+        """Integrator::preStepInitialize (Integrator.cc:177-183): RKCorrections::preStepInitialize (RK/RKCorrections.cc:298-340)
+        then the hydro's (SPHBase.cc:322-352 / CRKSPHBase.cc:229-256); returns True if the density was replaced."""
+        e, so = self.engine, self.so
+        if self._crk:
+            e.crk_compute_volume()
+            self._ghosts()
+        if self.densityUpdate == RIGOROUS_SUM_DENSITY:
+            if self._crk:
+                e.crk_sum_mass_density(so.rhoMin, so.rhoMax)
+            else:
+                e.sum_mass_density()
+            e.update_eos_gamma_law(so.eos)               # pressure / sound speed follow the density they depend on
+            self._ghosts()
+            return True
+        return False
+
+    def _initialize(self):
+        """Integrator::initializeDerivatives (Integrator.cc:186-210): RKCorrections::initialize (RKCorrections.cc:346-372)."""
+        if self._crk:
+            self.engine.crk_compute_corrections()
+            self._ghosts()
+
     def selectDt(self, dtMin, dtMax):
         """Integrator::selectDt (Integrator.cc:114-166) with the one package vote of GenericHydro::dt."""
         vote, why, node = self.engine.compute_dt(self.cfl, self.useVelocityMagnitudeForDt)
@@ -97,12 +125,12 @@ class CheapSynchronousRK2:
         e = self.engine
         self._set_ghost_nodes()
         e.build_pairs()
-        if self.densityUpdate == RIGOROUS_SUM_DENSITY:
-            e.sum_mass_density()
-        e.update_eos_gamma_law(self.so.eos)
+        if not self._pre_step_initialize():
+            e.update_eos_gamma_law(self.so.eos)
         if self.gradhCorrection:
             e.compute_omega_gradh()
         self._ghosts()
+        self._initialize()
         e.evaluate_derivatives(self.currentTime, 0.0)
         self._finalize_derivatives()
 
@@ -111,11 +139,8 @@ class CheapSynchronousRK2:
         """CheapSynchronousRK2::step(maxTime, state, derivs) (CheapSynchronousRK2.cc:40-132)."""
         e, so = self.engine, self.so
         t = self.currentTime
-        # preStepInitialize (SPHBase.cc:322-352)
-        if self.densityUpdate == RIGOROUS_SUM_DENSITY:
-            e.sum_mass_density()
-            e.update_eos_gamma_law(so.eos)           # pressure / sound speed follow the density they depend on
-            self._ghosts()
+        self._pre_step_initialize()
+        self._initialize()                            # initializeDerivatives(t, 0) (CheapSynchronousRK2.cc:56)
         dt = self.selectDt(min(self.dtMin, maxTime - t), min(self.dtMax, maxTime - t))
         hdt = 0.5*dt
         e.state_copy()                                # state0
@@ -124,6 +149,7 @@ class CheapSynchronousRK2:
         self._ghosts()
         self._post_state_update()
         # derivatives at the mid point, on the connectivity of the step start
+        self._initialize()                            # initializeDerivatives(t + hdt, hdt) (CheapSynchronousRK2.cc:86)
         e.evaluate_derivatives(t + hdt, hdt)
         self._finalize_derivatives()
         if self.allowDtCheck:

@@ -106,7 +106,10 @@ class OracleRK2:
     (ghosts regenerated every step by nodegen.reflect_ghosts, refreshed by nodegen.reflect_apply)."""
 
     def __init__(self, orc, oo, so, OT, st, densityUpdate=1, gradhCorrection=True, dtMin=0.0, dtMax=1.0e100, dtGrowth=2.0,
-                 planes=None, nInt=None):
+                 planes=None, nInt=None, crk=False):
+        self.crk = crk
+        if crk:
+            gradhCorrection = False
         self.orc, self.oo, self.so, self.OT = orc, oo, so, OT
         self.ndim = oo.ndim
         self.N = st["position"].shape[0] if nInt is None else nInt
@@ -147,7 +150,27 @@ class OracleRK2:
     def _pairs(self):
         self.pi, self.pj, self.cnt = self.orc.pairs(self.ndim, self.N, self.nGhost, self.s["pos"], self.s["H"], self.OT.kext)
 
+    def _crk_volume(self):
+        v0 = self.s.get("vol")
+        if v0 is None or v0.shape[0] != self.N + self.nGhost:
+            v0 = self.s["mass"]/self.s["rho"]
+        self.s["vol"] = self.orc.crk_sum_volume(self.ndim, self.OT, self.N, self.nGhost, self.s["pos"], self.s["H"], self.pi, self.pj, vol=v0)
+
+    def _crk_corrections(self):
+        if not self.crk:
+            return
+        c0 = self.s.get("corr")
+        if c0 is None or c0.shape[0] != self.N + self.nGhost:
+            c0 = np.zeros((self.N + self.nGhost, (self.ndim + 1)**2)); c0[:, 0] = 1.0
+        self.s["corr"] = self.orc.crk_corrections(self.ndim, self.OT, self.N, self.nGhost, self.s["pos"], self.s["H"], self.s["vol"],
+                                                  self.pi, self.pj, corr=c0)
+
     def _sum_density(self):
+        if self.crk:
+            self.s["rho"] = self.orc.crk_sum_density(self.ndim, self.OT, self.N, self.nGhost, self.s["pos"], self.s["mass"], self.s["vol"],
+                                                     self.s["H"], self.pi, self.pj, rhoMin=self.so.rhoMin, rhoMax=self.so.rhoMax,
+                                                     rho=self.s["rho"])
+            return
         self.s["rho"] = self.orc.sum_mass_density(self.ndim, self.OT, self.N, self.nGhost, self.s["pos"], self.s["mass"], self.s["H"],
                                                   self.pi, self.pj, rho=self.s["rho"])
 
@@ -159,7 +182,11 @@ class OracleRK2:
                                                self.cnt, omega=self.s["omega"])
 
     def _evaluate(self):
-        self.derivs = self.orc.evaluate_derivatives(self.oo, self.OT, self.s, self.N, self.nGhost, self.pi, self.pj, self.cnt)
+        if self.crk:
+            self.derivs = self.orc.crk_evaluate_derivatives(self.oo, self.OT, self.s, self.s["vol"], self.s["corr"], self.N, self.nGhost,
+                                                            self.pi, self.pj)
+        else:
+            self.derivs = self.orc.evaluate_derivatives(self.oo, self.OT, self.s, self.N, self.nGhost, self.pi, self.pj, self.cnt)
         self.pairs_eval = (self.pi, self.pj)
         if self.planes and self.oo.compatibleEnergy:
             # SPHBase::finalizeDerivatives (SPHBase.cc:502-519): ghost values of the acceleration and the energy derivative,
@@ -211,28 +238,35 @@ class OracleRK2:
     def initializeDerivatives(self):
         self._set_ghosts()
         self._pairs()
+        if self.crk:
+            self._crk_volume()
         if self.densityUpdate == 1:
             self._sum_density()
         self._eos()
         if self.gradhCorrection:
             self._omega()
         self._apply_ghosts()
+        self._crk_corrections()
         self._evaluate()
 
     def step(self, maxTime=1.0e100):
         self._set_ghosts()
         self._pad_derivs()
         self._pairs()
+        if self.crk:
+            self._crk_volume()
         if self.densityUpdate == 1:
             self._sum_density()
             self._eos()
             self._apply_ghosts()
+        self._crk_corrections()
         dt = self._select_dt(maxTime)
         hdt = 0.5*dt
         s0 = {k: np.array(v, copy=True) for k, v in self.s.items()}
         self._update(hdt, True)
         self._apply_ghosts()
         self._post_state_update()
+        self._crk_corrections()
         self._evaluate()
         self.s = s0                 # state.assign(state0) restores every registered field, the Q gradient and omega included
         self._update(dt, False)

@@ -184,3 +184,42 @@ def test_step_errors(oracle, mods):
     e.upload_state(position=st["position"])           # stale connectivity
     with pytest.raises(engine.SPHB200Error, match="connectivity"):
         e.sum_mass_density()
+
+
+@pytest.mark.parametrize("ndim,n,nPerh,Qkind", [(3, 10, 1.51, 1), (2, 28, 2.01, 0)])
+def test_rk2_steps_crksph_device_resident(oracle, mods, ndim, n, nPerh, Qkind):
+    """CRKSPH through the device-resident integrator: volumes in preStepInitialize, corrections before every evaluation
+    (RKCorrections.cc:298-372), CRK sum density, CRKSPH derivatives; against the oracle-driven integrator."""
+    engine, integrator = mods
+    from spheral_b200 import _lib as L
+    st, nInt, _ = common.make_problem(ndim, n, nPerh=nPerh)
+    st["velocity"] = 0.3*st["velocity"]
+    if Qkind:
+        st["DvDxQ"] = np.zeros((nInt, ndim*ndim))
+    WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    OT = common.oracle_table(oracle, WT)
+    okw = dict(nPerh=nPerh, Cl=1.0, Cq=0.25, Qkind=Qkind, correctVelocityGradient=0)
+    oo, po = common.opts_pair(oracle, engine, ndim, **okw)
+    po.hydro = L.HYDRO_CRKSPH
+    so = oracle.default_step_options()
+    ref = common.OracleRK2(oracle, oo, so, OT, st, densityUpdate=1, crk=True)
+    e = engine.Engine(ndim, options=po)
+    e.set_kernel_table(WT)
+    e.set_nodes(nInt, 0)
+    e.upload_state(**st)
+    rk = integrator.CheapSynchronousRK2(e, engine.make_step_options(), densityUpdate=1)
+    ref.initializeDerivatives()
+    rk.initializeDerivatives()
+    for _ in range(3):
+        dt_ref = ref.step()
+        assert rk.step()
+        assert abs(rk.lastDt - dt_ref) <= 1e-10*dt_ref, (rk.lastDt, dt_ref)
+    got = e.download_state("position", "velocity", "H", "massDensity", "specificThermalEnergy", "pressure", "soundSpeed", "volume")
+    names = dict(position="pos", velocity="vel", H="H", massDensity="rho", specificThermalEnergy="eps", pressure="P", soundSpeed="cs",
+                 volume="vol")
+    worst = {k: rel(got[k], ref.s[o], nInt) for k, o in names.items()}
+    assert all(v <= 1.0e-9 for v in worst.values()), worst
+    m, v, eps = st["mass"], got["velocity"], got["specificThermalEnergy"]
+    E1 = float(np.sum(m*(0.5*np.sum(v*v, axis=1) + eps)))
+    E0 = float(np.sum(m*(0.5*np.sum(st["velocity"]**2, axis=1) + st["specificThermalEnergy"])))
+    assert abs(E1 - E0) <= 1e-12*abs(E0)
