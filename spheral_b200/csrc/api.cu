@@ -53,6 +53,26 @@ __global__ void __launch_bounds__(RB) k_halo_pack(const double* __restrict__ fie
   const size_t k = t/width; const int q = (int)(t % width);
   out[t] = field[(size_t)nodes[k]*width + q];
 }
+// all masked fields of one side in ONE launch (a launch per field left the GPU idle between ~36 tiny operations per refresh)
+struct HaloFields { const double* src[S_COUNT]; double* dst[S_COUNT]; int width[S_COUNT]; unsigned long long off[S_COUNT]; int nf; unsigned long long total; };
+__global__ void __launch_bounds__(RB) k_halo_pack_all(HaloFields f, const uint32_t* __restrict__ nodes, size_t count, double* __restrict__ out) {
+  const size_t t = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (t >= f.total) return;
+  int a = 0;
+  while (a + 1 < f.nf && t >= f.off[a + 1]) ++a;
+  const size_t u = t - f.off[a];
+  const int w = f.width[a];
+  const size_t k = u/w; const int q = (int)(u - k*w);
+  out[t] = f.src[a][(size_t)nodes[k]*w + q];
+}
+__global__ void __launch_bounds__(RB) k_halo_unpack_all(HaloFields f, size_t firstGhost, const double* __restrict__ in) {
+  const size_t t = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (t >= f.total) return;
+  int a = 0;
+  while (a + 1 < f.nf && t >= f.off[a + 1]) ++a;
+  const size_t u = t - f.off[a];
+  f.dst[a][firstGhost*(size_t)f.width[a] + u] = in[t];
+}
 // slab halo selection: flags, then (after exclusive scans) ordered scatter of the node indices
 // original index -> sorted slot
 __global__ void __launch_bounds__(RB) k_inverse_perm(const uint32_t* __restrict__ perm, size_t n, uint32_t* __restrict__ inv) {
@@ -555,16 +575,17 @@ size_t sphb200_halo_bytes_per_node(const sphb200_ctx* c, unsigned mask) {
 int sphb200_halo_pack(sphb200_ctx* c, unsigned mask, const uint32_t* nodes, size_t count, void* staging) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
   CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
-  double* out = (double*)staging;
+  HaloFields f{};
   for (int s = 0; s < S_COUNT; ++s) {
     if (!(mask & (1u << s))) continue;
     if (!c->have[s]) return sphb200_fail(c, "halo_pack: field not on device");
-    const int w = sphb200_state_width(c->ndim, s);
-    if (count) {
-      k_halo_pack<<<(unsigned)((count*w + RB - 1)/RB), RB, 0, c->stream>>>(c->api[s], w, nodes, count, out);
-      KERNEL_CHECK(c, "k_halo_pack");
-    }
-    out += count*(size_t)w;
+    f.src[f.nf] = c->api[s]; f.width[f.nf] = sphb200_state_width(c->ndim, s); f.off[f.nf] = f.total;
+    f.total += count*(unsigned long long)f.width[f.nf];
+    ++f.nf;
+  }
+  if (f.total) {
+    k_halo_pack_all<<<(unsigned)((f.total + RB - 1)/RB), RB, 0, c->stream>>>(f, nodes, count, (double*)staging);
+    KERNEL_CHECK(c, "k_halo_pack_all");
   }
   return 0;
 }
@@ -573,16 +594,21 @@ static int halo_unpack_impl(sphb200_ctx* c, unsigned mask, size_t firstGhost, si
   if (!c) return sphb200_fail(nullptr, "null ctx");
   CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (firstGhost + count > c->n) return sphb200_fail(c, "halo_unpack: ghost range exceeds node count");
-  const double* in = (const double*)staging;
+  HaloFields f{};
   for (int s = 0; s < S_COUNT; ++s) {
     if (!(mask & (1u << s))) continue;
-    const int w = sphb200_state_width(c->ndim, s);
-    // ghosts are a contiguous tail of the host-ordered arrays, so landing a field block is one D2D copy
-    if (count) CU_CHECK(c, cudaMemcpyAsync(c->api[s] + firstGhost*(size_t)w, in, count*(size_t)w*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    in += count*(size_t)w;
+    if (!c->api[s] && c->n) return sphb200_fail(c, "halo_unpack: volume / RK corrections exist only in CRKSPH contexts");
+    // ghosts are a contiguous tail of the host-ordered arrays: field block a lands at api[s] + firstGhost*width
+    f.dst[f.nf] = c->api[s]; f.width[f.nf] = sphb200_state_width(c->ndim, s); f.off[f.nf] = f.total;
+    f.total += count*(unsigned long long)f.width[f.nf];
+    ++f.nf;
     c->have[s] = true;
     if (!keepConnectivity && (s == S_POS || s == S_H)) { c->sortValid = false; c->pairsValid = false; }
     if (s != S_EPS && s != S_VOLUME && s != S_RKCORR) c->rowsValid = false;
+  }
+  if (f.total) {
+    k_halo_unpack_all<<<(unsigned)((f.total + RB - 1)/RB), RB, 0, c->stream>>>(f, firstGhost, (const double*)staging);
+    KERNEL_CHECK(c, "k_halo_unpack_all");
   }
   return 0;
 }

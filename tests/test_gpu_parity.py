@@ -243,3 +243,20 @@ def test_two_gpu_slab_halo_parity(sphlib, oracle):
            "--master-port", "29517", os.path.join(root, "tests", "mgpu_parity.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("ndim,n,nPerh,kind,kw", [(3, 9, 1.51, "lattice", dict()), (3, 7, 1.51, "aniso", dict(hEvolution=1)),
+                                                  (2, 24, 2.01, "lattice", dict(Qkind=1))])
+def test_coincident_nodes_derivatives(oracle, eng_mod, ndim, n, nPerh, kind, kw):
+    """Two nodes at the same position (eta = 0: the reference's safeInvVar gives a zero unit vector, SPH.cc:368-369): the
+    isotropic fast path, the general tensor path and the general-options path must all reproduce the oracle."""
+    st, nInt, nGhost = common.make_problem(ndim, n, nPerh=nPerh, kind=kind, seed=57)
+    st["position"][nInt//2] = st["position"][nInt//2 + 1]
+    st["position"][3] = st["position"][nInt - 2]
+    if kw.get("Qkind"):
+        st = common.add_q_fields(st, ndim)
+    WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    r = run_both(oracle, eng_mod, ndim, st, nInt, nGhost, WT, nPerh=nPerh, Cl=1.5, Cq=1.5, **kw)
+    assert_parity(r, st, nInt, ndim)
+    for k in ("DvDt", "DepsDt", "DvDx"):
+        assert np.all(np.isfinite(r["got"][k]))
