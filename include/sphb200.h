@@ -146,6 +146,12 @@ int  sphb200_download_neighbor_counts(sphb200_ctx* ctx, uint32_t* counts);
    evaluateDerivatives; derivatives are zeroed first (CheapSynchronousRK2.cc:87 derivs.Zero()). Asynchronous. */
 int  sphb200_evaluate_derivatives(sphb200_ctx* ctx, double time, double dt);
 int  sphb200_download_derivs(sphb200_ctx* ctx, unsigned fieldMask, const sphb200_host_derivs* d);
+/* Restart: SPHBase::restoreState (SPH/SPHBase.cc:741-765) reads the package-owned derivative fields back, because
+   CheapSynchronousRK2 advances the first trial state after a restart with them.  Uploads node-wise derivative fields (host AoS,
+   original order); sphb200_state_update / sphb200_compute_dt / sphb200_copy_DvDx_to_Q then work as after an evaluation.  Pair-wise
+   data are not restored: the compatible energy update needs a new sphb200_evaluate_derivatives, as in the reference, where the
+   PairwiseField is rebuilt with the connectivity (SPH.cc:129-133). */
+int  sphb200_upload_derivs(sphb200_ctx* ctx, unsigned fieldMask, const sphb200_host_derivs* d);
 /* PairwiseField "pair-wise accelerations" (SPH.cc:129-133, :430) in NodePairList order, npairs*ndim doubles. */
 int  sphb200_download_pair_accelerations(sphb200_ctx* ctx, double* pairAccelerations, size_t cap);
 /* ArtificialViscosityHandle::postStateUpdate copy DvDx -> Q velocity gradient (ArtificialViscosityHandle.cc:165-180) */

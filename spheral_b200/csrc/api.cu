@@ -29,6 +29,16 @@ __global__ void __launch_bounds__(RB) k_unpermute(const double* __restrict__ src
   const size_t o = perm[s];
   for (int q = 0; q < width; ++q) dst[o*width + q] = src[(size_t)q*cap + s];
 }
+// host AoS (original order) -> component-major derivative array stored in ORIGINAL order (restart: permEval = identity)
+__global__ void __launch_bounds__(RB) k_derivs_in(const double* __restrict__ src, size_t cap, size_t n, int width, double* __restrict__ dst) {
+  const size_t o = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (o >= n) return;
+  for (int q = 0; q < width; ++q) dst[(size_t)q*cap + o] = src[o*width + q];
+}
+__global__ void __launch_bounds__(RB) k_iota(uint32_t* __restrict__ p, size_t n) {
+  const size_t o = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (o < n) p[o] = (uint32_t)o;
+}
 // DvDx (sorted SoA) -> api DvDxQ (AoS, original order)
 __global__ void __launch_bounds__(RB) k_copy_dvdx(const double* __restrict__ src, size_t cap, const uint32_t* __restrict__ perm,
                                                   size_t n, size_t nLimit, int width, double* __restrict__ dst) {
@@ -531,6 +541,40 @@ int sphb200_download_derivs(sphb200_ctx* c, unsigned mask, const sphb200_host_de
     off += c->n*(size_t)w;
   }
   CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int sphb200_upload_derivs(sphb200_ctx* c, unsigned mask, const sphb200_host_derivs* d) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  if (!d) return sphb200_fail(c, "upload_derivs: null source struct");
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
+  if (c->n == 0) return 0;
+  size_t total = 0;
+  for (int s = 0; s < DV_COUNT; ++s) if (mask & (1u << s)) {
+    if (!deriv_ptr(d, s)) return sphb200_fail(c, "upload_derivs: field selected in mask but pointer is null");
+    total += c->n*(size_t)sphb200_deriv_width(c->ndim, s);
+  }
+  if (ensure_stage(c, total*sizeof(double))) return 1;
+  // the derivative arrays are (re)interpreted in original node order: every field not uploaded is zeroed so that no value of a
+  // previous, differently ordered evaluation survives
+  for (int s = 0; s < DV_COUNT; ++s)
+    CU_CHECK(c, cudaMemsetAsync(c->deriv[s], 0, c->cap*(size_t)sphb200_deriv_width(c->ndim, s)*sizeof(double), c->stream));
+  size_t off = 0;
+  const unsigned nb = (unsigned)((c->n + RB - 1)/RB);
+  for (int s = 0; s < DV_COUNT; ++s) {
+    if (!(mask & (1u << s))) continue;
+    const int w = sphb200_deriv_width(c->ndim, s);
+    CU_CHECK(c, cudaMemcpyAsync(c->stage + off, deriv_ptr(d, s), c->n*(size_t)w*sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_derivs_in<<<nb, RB, 0, c->stream>>>(c->stage + off, c->cap, c->n, w, c->deriv[s]);
+    KERNEL_CHECK(c, "k_derivs_in");
+    off += c->n*(size_t)w;
+  }
+  if (sphb200_ensure(c, c->permEval, c->permEvalCap, c->cap)) return 1;
+  k_iota<<<nb, RB, 0, c->stream>>>(c->permEval, c->n);
+  KERNEL_CHECK(c, "k_iota");
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));                 // the host buffers may be pageable
+  c->nEval = c->n; c->capEval = c->cap; c->nIntEval = c->nInt; c->derivNodeValid = true;
+  c->derivsValid = false;                                        // the pair-wise data (pair accelerations) are not restored
   return 0;
 }
 

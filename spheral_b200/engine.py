@@ -191,6 +191,21 @@ class Engine:
         self._check(self._lib.sphb200_download_derivs(self._h, mask, C.byref(hd)))
         return out
 
+    def upload_derivs(self, **fields):
+        """Restart (SPHBase::restoreState): node-wise derivative fields back onto the device; names from _lib.DERIV_FIELDS."""
+        hd = L.HostDerivs()
+        mask, keep = 0, []
+        for k, v in fields.items():
+            if k not in L.DERIV_BITS:
+                raise KeyError(k)
+            a = np.ascontiguousarray(v, dtype=np.float64)
+            if a.size != self.n*L.deriv_width(self.ndim, k):
+                raise ValueError("field %s has %d values, expected %d" % (k, a.size, self.n*L.deriv_width(self.ndim, k)))
+            keep.append(a)
+            setattr(hd, k, _dp(a))
+            mask |= L.DERIV_BITS[k]
+        self._check(self._lib.sphb200_upload_derivs(self._h, mask, C.byref(hd)))
+
     def download_pair_accelerations(self):
         out = np.zeros((max(self.npairs, 1), self.ndim))
         self._check(self._lib.sphb200_download_pair_accelerations(self._h, _dp(out), out.size))

@@ -186,6 +186,40 @@ class CheapSynchronousRK2:
         self.dtMultiplier = 1.0
         return ok
 
+    # -- restart (RestartableObject: Integrator::dumpState / restoreState, SPHBase::dumpState / restoreState) -------------------------
+    RESTART_DERIVS = ("DxDt", "DrhoDt", "DvDt", "DepsDt", "DvDx", "maxViscousPressure", "DHDt", "Hideal")
+
+    def dumpState(self):
+        """Everything a restart needs, as host arrays: the state fields on the device, the derivative fields the next trial
+        advance and dt vote read (SPHBase.cc:714-735 dumps them for the same reason), and the integrator's counters
+        (Integrator.cc dumpState: time, cycle, lastDt)."""
+        e = self.engine
+        names = [k for k in L.STATE_FIELDS if k not in ("fCl", "fCq", "volume", "rkCorrections") or (self._crk and k in ("volume", "rkCorrections"))]
+        have = []
+        for k in names:
+            try:
+                e.download_state(k)
+                have.append(k)
+            except E.SPHB200Error:
+                pass
+        return dict(state=e.download_state(*have), derivs=e.download_derivs(*self.RESTART_DERIVS) if self._derivs_downloadable() else None,
+                    nInternal=e.nInternal, nGhost=e.nGhost, time=self.currentTime, cycle=self.currentCycle, lastDt=self.lastDt)
+
+    def _derivs_downloadable(self):
+        try:
+            self.engine.download_derivs("DrhoDt")
+            return True
+        except E.SPHB200Error:
+            return False
+
+    def restoreState(self, dump):
+        e = self.engine
+        e.set_nodes(dump["nInternal"], dump["nGhost"])
+        e.upload_state(**dump["state"])
+        if dump["derivs"] is not None:
+            e.upload_derivs(**dump["derivs"])
+        self.currentTime, self.currentCycle, self.lastDt = dump["time"], dump["cycle"], dump["lastDt"]
+
     def advance(self, goalTime, maxSteps=None):
         n = 0
         while self.currentTime < goalTime and (maxSteps is None or n < maxSteps):

@@ -223,3 +223,45 @@ def test_rk2_steps_crksph_device_resident(oracle, mods, ndim, n, nPerh, Qkind):
     E1 = float(np.sum(m*(0.5*np.sum(v*v, axis=1) + eps)))
     E0 = float(np.sum(m*(0.5*np.sum(st["velocity"]**2, axis=1) + st["specificThermalEnergy"])))
     assert abs(E1 - E0) <= 1e-12*abs(E0)
+
+
+@pytest.mark.parametrize("ndim,n,nPerh,Qkind,planes", [(3, 10, 1.51, 1, False), (2, 26, 2.01, 0, True)])
+def test_restart_is_bit_exact(oracle, mods, ndim, n, nPerh, Qkind, planes):
+    """The restart contract of the reference's ATS tests (Noh-cylindrical-2d.py --restoreCycle / --checkRestart: a run restarted
+    from a dump continues exactly like the uninterrupted one): dumpState after 2 steps, restoreState into a fresh context,
+    2 more steps on both -- every state field bit-identical."""
+    engine, integrator = mods
+    st, nInt, _ = common.make_problem(ndim, n, nPerh=nPerh, seed=91)
+    st["velocity"] = 0.3*st["velocity"]
+    if planes:
+        st["position"] = np.abs(st["position"])
+    if Qkind:
+        st["DvDxQ"] = np.zeros((nInt, ndim*ndim))
+    WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    pl = [(np.zeros(ndim), np.eye(ndim)[a]) for a in range(ndim)] if planes else None
+
+    def fresh():
+        e = engine.Engine(ndim, options=engine.make_options(ndim, nPerh=nPerh, Cl=1.0, Cq=1.0, Qkind=Qkind))
+        e.set_kernel_table(WT)
+        return e, integrator.CheapSynchronousRK2(e, engine.make_step_options(), densityUpdate=1, reflectingPlanes=pl)
+
+    e1, rk1 = fresh()
+    e1.set_nodes(nInt, 0)
+    e1.upload_state(**st)
+    rk1.initializeDerivatives()
+    for _ in range(2):
+        assert rk1.step()
+    dump = rk1.dumpState()
+    assert dump["cycle"] == 2 and dump["derivs"] is not None
+    for _ in range(2):
+        assert rk1.step()
+    a = e1.download_state("position", "velocity", "H", "massDensity", "specificThermalEnergy", "omegaGradh")
+
+    e2, rk2 = fresh()
+    rk2.restoreState(dump)
+    for _ in range(2):
+        assert rk2.step()
+    b = e2.download_state("position", "velocity", "H", "massDensity", "specificThermalEnergy", "omegaGradh")
+    assert rk2.currentCycle == rk1.currentCycle == 4 and rk2.currentTime == rk1.currentTime and rk2.lastDt == rk1.lastDt
+    for k in a:
+        assert np.array_equal(a[k][:nInt], b[k][:nInt]), k
