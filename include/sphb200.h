@@ -229,6 +229,14 @@ int  sphb200_compute_dt(sphb200_ctx* ctx, double cfl, int useVelocityMagnitudeFo
                                        ReflectingBoundary.cc:255-330): internal nodes behind a plane are mirrored back, their
                                        velocity reflected.  nViolations may be NULL (then no host synchronisation). */
 int  sphb200_reflect_configure(sphb200_ctx* ctx, int nPlanes, const double* points, const double* normals);
+/* General form: planar boundaries with an enter and an exit plane (Boundary/PlanarBoundary.hh).  Reflecting: exit == enter
+   (exit arrays ignored).  Periodic (Boundary/PeriodicBoundary.cc:60-62): a PeriodicBoundary(plane1, plane2) is TWO entries,
+   (enter = plane1, exit = plane2) and (enter = plane2, exit = plane1); ghosts are unreflected copies displaced through the
+   planes (mapPositionThroughPlanes.hh:17-27), escaped nodes re-enter through the other plane.  The sphb200_reflect_* calls
+   below serve both kinds. */
+enum { SPHB200_BOUNDARY_REFLECTING = 0, SPHB200_BOUNDARY_PERIODIC = 1 };
+int  sphb200_boundary_configure(sphb200_ctx* ctx, int nBoundaries, const int* kinds, const double* enterPoints, const double* enterNormals,
+                                const double* exitPoints, const double* exitNormals);
 int  sphb200_reflect_set_ghost_nodes(sphb200_ctx* ctx, size_t* nGhost);
 int  sphb200_reflect_apply_ghosts(sphb200_ctx* ctx, unsigned fieldMask);
 int  sphb200_reflect_finalize_derivatives(sphb200_ctx* ctx);

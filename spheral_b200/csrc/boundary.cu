@@ -23,16 +23,28 @@ namespace {
 
 constexpr int RB = 256;
 
-struct Plane { double p[3]; double n[3]; };
+// One planar boundary (PlanarBoundary.hh): enter plane {p, n} and exit plane {px, nx}, unit normals pointing into the domain.
+// Reflecting: exit == enter.  Periodic: a PeriodicBoundary is two of these, (plane1 -> plane2) and (plane2 -> plane1)
+// (PeriodicBoundary.cc:60-62).  Control nodes sit within a kernel extent of the EXIT plane; their ghosts appear behind the ENTER
+// plane at mapPosition(r, exit, enter) = closestPointOnPlane_enter(r) - signedDistance_exit(r) n_enter (PlanarBoundary.cc:318-320,
+// mapPositionThroughPlanes.hh:17-27).
+struct Plane { double p[3]; double n[3]; double px[3]; double nx[3]; int periodic; };
 
-template <int DIM> __device__ __forceinline__ double signed_distance(const Plane& pl, const double* r) {
+template <int DIM> __device__ __forceinline__ double signed_distance(const Plane& pl, const double* r) {      // to the enter plane
   double s = 0.0;
 #pragma unroll
   for (int q = 0; q < DIM; ++q) s += (r[q] - pl.p[q])*pl.n[q];
   return s;
 }
+template <int DIM> __device__ __forceinline__ double signed_distance_exit(const Plane& pl, const double* r) {
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < DIM; ++q) s += (r[q] - pl.px[q])*pl.nx[q];
+  return s;
+}
 
-// pass 1: hmax = largest 1/min-eigenvalue(H_i) among nodes within kext*hmax_i of the plane (0 <= signed distance)
+// pass 1: hmax = largest 1/min-eigenvalue(H_i) among nodes closer than kext*hmax_i to either plane
+// (findNodesTouchingThroughPlanes.cc, active branch)
 template <int DIM>
 __global__ void __launch_bounds__(RB) k_reflect_hmax(const double* __restrict__ pos, const double* __restrict__ H, size_t n, Plane pl,
                                                      double kext, unsigned long long* __restrict__ hmaxBits) {
@@ -46,14 +58,14 @@ __global__ void __launch_bounds__(RB) k_reflect_hmax(const double* __restrict__ 
 #pragma unroll
     for (int q = 0; q < DIM; ++q) r[q] = pos[i*DIM + q];
     const double hi = 1.0/sym_min_eigenvalue<DIM>(Hi);
-    const double sd = signed_distance<DIM>(pl, r);
-    if (sd >= 0.0 && sd <= kext*hi) v = hi;
+    const double dmin = fmin(fabs(signed_distance<DIM>(pl, r)), fabs(signed_distance_exit<DIM>(pl, r)));
+    if (dmin < kext*hi) v = hi;
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, off));
   if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(hmaxBits, (unsigned long long)__double_as_longlong(v));   // positive doubles order as integers
 }
-// pass 2: control flags 0 <= sd/hmax <= kext
+// pass 2: control flags 0 <= signedDistance_exit/hmax <= kext
 template <int DIM>
 __global__ void __launch_bounds__(RB) k_reflect_flags(const double* __restrict__ pos, size_t n, Plane pl, double kext,
                                                       const unsigned long long* __restrict__ hmaxBits, uint32_t* __restrict__ flags) {
@@ -63,7 +75,7 @@ __global__ void __launch_bounds__(RB) k_reflect_flags(const double* __restrict__
   double r[DIM];
 #pragma unroll
   for (int q = 0; q < DIM; ++q) r[q] = pos[i*DIM + q];
-  const double x = signed_distance<DIM>(pl, r)/hmax;
+  const double x = signed_distance_exit<DIM>(pl, r)/hmax;
   flags[i] = (hmax > 0.0 && x >= 0.0 && x <= kext) ? 1u : 0u;
 }
 __global__ void __launch_bounds__(RB) k_reflect_scatter(const uint32_t* __restrict__ scan, size_t n, uint32_t* __restrict__ ctl, size_t cap) {
@@ -82,19 +94,19 @@ __global__ void __launch_bounds__(RB) k_reflect_fill(double* __restrict__ f, int
   const size_t c = ctl[k], g = first + k;
   const double* s = f + c*(size_t)width;
   double* d = f + g*(size_t)width;
-  if (kind == 0 || kind == 5) { for (int q = 0; q < width; ++q) d[q] = s[q]; return; }
+  if (kind == 0 || kind == 5 || (pl.periodic && kind != 1)) { for (int q = 0; q < width; ++q) d[q] = s[q]; return; }
   double R[DIM][DIM];
 #pragma unroll
   for (int a = 0; a < DIM; ++a)
 #pragma unroll
     for (int b = 0; b < DIM; ++b) R[a][b] = (a == b ? 1.0 : 0.0) - 2.0*pl.n[a]*pl.n[b];
-  if (kind == 1) {                                   // closestPointOnPlane(r) - signedDistance(r) n = r - 2 sd n
+  if (kind == 1) {                                   // closestPointOnPlane_enter(r) - signedDistance_exit(r) n_enter
     double r[DIM];
 #pragma unroll
     for (int q = 0; q < DIM; ++q) r[q] = s[q];
-    const double sd = signed_distance<DIM>(pl, r);
+    const double sde = signed_distance<DIM>(pl, r), sdx = signed_distance_exit<DIM>(pl, r);
 #pragma unroll
-    for (int q = 0; q < DIM; ++q) d[q] = r[q] - 2.0*sd*pl.n[q];
+    for (int q = 0; q < DIM; ++q) d[q] = (r[q] - sde*pl.n[q]) - sdx*pl.n[q];
   } else if (kind == 2) {
 #pragma unroll
     for (int a = 0; a < DIM; ++a) { double t = 0.0;
@@ -150,12 +162,16 @@ __global__ void __launch_bounds__(RB) k_reflect_enforce(double* __restrict__ pos
 #pragma unroll
   for (int q = 0; q < DIM; ++q) r[q] = pos[i*DIM + q];
   const double sd = signed_distance<DIM>(pl, r);
-  if (sd >= 0.0) return;
+  if (sd >= 0.0) return;                             // not below the enter plane (PlanarBoundary.cc:165-167)
+  // mapPosition(r, enter, exit) = closestPointOnPlane_exit(r) - signedDistance_enter(r) n_exit (PlanarBoundary.cc:186)
+  const double sdx = signed_distance_exit<DIM>(pl, r);
   double vn = 0.0;
 #pragma unroll
-  for (int q = 0; q < DIM; ++q) { pos[i*DIM + q] = r[q] - 2.0*sd*pl.n[q]; vn += vel[i*DIM + q]*pl.n[q]; }
+  for (int q = 0; q < DIM; ++q) { pos[i*DIM + q] = (r[q] - sdx*pl.nx[q]) - sd*pl.nx[q]; vn += vel[i*DIM + q]*pl.n[q]; }
+  if (!pl.periodic) {                                // ReflectingBoundary::enforceBoundary(velocity): v -> R v
 #pragma unroll
-  for (int q = 0; q < DIM; ++q) vel[i*DIM + q] -= 2.0*vn*pl.n[q];
+    for (int q = 0; q < DIM; ++q) vel[i*DIM + q] -= 2.0*vn*pl.n[q];
+  }
   atomicAdd(nViolations, 1ull);
 }
 
@@ -170,6 +186,7 @@ __global__ void __launch_bounds__(RB) k_reflect_derivs(double* __restrict__ DvDt
   double a[DIM], an = 0.0;
 #pragma unroll
   for (int q = 0; q < DIM; ++q) { a[q] = DvDt[(size_t)q*cap + sc]; an += a[q]*pl.n[q]; }
+  if (pl.periodic) an = 0.0;                         // periodic images carry the control node's acceleration unchanged
 #pragma unroll
   for (int q = 0; q < DIM; ++q) DvDt[(size_t)q*cap + sg] = a[q] - 2.0*an*pl.n[q];
   DepsDt[sg] = DepsDt[sc];
@@ -183,7 +200,8 @@ int field_kind(int ndim, int slot) {
 }
 Plane plane_of(const sphb200_ctx* c, int p) {
   Plane pl{};
-  for (int q = 0; q < 3; ++q) { pl.p[q] = c->planes[6*p + q]; pl.n[q] = c->planes[6*p + 3 + q]; }
+  for (int q = 0; q < 3; ++q) { pl.p[q] = c->planes[12*p + q]; pl.n[q] = c->planes[12*p + 3 + q]; pl.px[q] = c->planes[12*p + 6 + q]; pl.nx[q] = c->planes[12*p + 9 + q]; }
+  pl.periodic = c->planeKind[p];
   return pl;
 }
 int fill_plane(sphb200_ctx* c, int p, unsigned mask) {
@@ -205,23 +223,39 @@ int fill_plane(sphb200_ctx* c, int p, unsigned mask) {
 
 extern "C" {
 
+int sphb200_boundary_configure(sphb200_ctx* c, int nBoundaries, const int* kinds, const double* enterPoints, const double* enterNormals,
+                               const double* exitPoints, const double* exitNormals) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  if (nBoundaries < 0 || nBoundaries > SPHB200_MAX_PLANES) return sphb200_fail(c, "boundary_configure: between 0 and 6 planar boundaries are supported");
+  if (nBoundaries && (!kinds || !enterPoints || !enterNormals)) return sphb200_fail(c, "boundary_configure: null boundary data");
+  for (int p = 0; p < nBoundaries; ++p) {
+    const bool periodic = kinds[p] == SPHB200_BOUNDARY_PERIODIC;
+    if (kinds[p] != SPHB200_BOUNDARY_REFLECTING && !periodic) return sphb200_fail(c, "boundary_configure: unknown boundary kind");
+    if (periodic && (!exitPoints || !exitNormals)) return sphb200_fail(c, "boundary_configure: a periodic boundary needs its exit plane");
+    const double* pts[2] = {enterPoints, periodic ? exitPoints : enterPoints};
+    const double* nrm[2] = {enterNormals, periodic ? exitNormals : enterNormals};
+    for (int side = 0; side < 2; ++side) {
+      double nn = 0.0;
+      for (int q = 0; q < c->ndim; ++q) nn += nrm[side][p*c->ndim + q]*nrm[side][p*c->ndim + q];
+      if (!(nn > 0.0)) return sphb200_fail(c, "boundary_configure: zero plane normal");
+      nn = std::sqrt(nn);
+      for (int q = 0; q < 3; ++q) {
+        c->planes[12*p + 6*side + q] = q < c->ndim ? pts[side][p*c->ndim + q] : 0.0;
+        c->planes[12*p + 6*side + 3 + q] = q < c->ndim ? nrm[side][p*c->ndim + q]/nn : 0.0;      // unit normal, pointing into the domain
+      }
+    }
+    c->planeKind[p] = periodic ? 1 : 0;
+    c->planeFirst[p] = c->planeCount[p] = 0;
+  }
+  c->nPlanes = nBoundaries;
+  return 0;
+}
+
 int sphb200_reflect_configure(sphb200_ctx* c, int nPlanes, const double* points, const double* normals) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
   if (nPlanes < 0 || nPlanes > SPHB200_MAX_PLANES) return sphb200_fail(c, "reflect_configure: between 0 and 6 planes are supported");
-  if (nPlanes && (!points || !normals)) return sphb200_fail(c, "reflect_configure: null plane data");
-  for (int p = 0; p < nPlanes; ++p) {
-    double nn = 0.0;
-    for (int q = 0; q < c->ndim; ++q) nn += normals[p*c->ndim + q]*normals[p*c->ndim + q];
-    if (!(nn > 0.0)) return sphb200_fail(c, "reflect_configure: zero plane normal");
-    nn = std::sqrt(nn);
-    for (int q = 0; q < 3; ++q) {
-      c->planes[6*p + q] = q < c->ndim ? points[p*c->ndim + q] : 0.0;
-      c->planes[6*p + 3 + q] = q < c->ndim ? normals[p*c->ndim + q]/nn : 0.0;       // unit normal, pointing into the domain
-    }
-    c->planeFirst[p] = c->planeCount[p] = 0;
-  }
-  c->nPlanes = nPlanes;
-  return 0;
+  int kinds[SPHB200_MAX_PLANES] = {0};
+  return sphb200_boundary_configure(c, nPlanes, kinds, points, normals, nullptr, nullptr);
 }
 
 int sphb200_reflect_set_ghost_nodes(sphb200_ctx* c, size_t* nGhostOut) {

@@ -510,10 +510,14 @@ __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build(NbrArgs a, int listRo
   __syncwarp();
   uint32_t* out = a.nbr + off + lane;
   for (uint32_t k = 0; k < mx; ++k) {
-    const uint32_t code = slist[k*32u + lane];
-    const uint32_t rr = code >> 5;
-    const uint32_t jb = (rr < (uint32_t)JB_CAP) ? sjb[rr] : __ldg(&a.runs[rs + rr].x);
-    out[(size_t)k*SPHB200_TILE] = (k < cnt) ? jb + (code & 31u) : 0u;        // padding entries point at slot 0 (never used)
+    uint32_t slot = 0u;                                                       // padding entries point at slot 0 (never used)
+    if (k < cnt) {                                                            // beyond a lane's own list the staging holds stale codes
+      const uint32_t code = slist[k*32u + lane];
+      const uint32_t rr = code >> 5;
+      const uint32_t jb = (rr < (uint32_t)JB_CAP) ? sjb[rr] : __ldg(&a.runs[rs + rr].x);
+      slot = jb + (code & 31u);
+    }
+    out[(size_t)k*SPHB200_TILE] = slot;
   }
 }
 

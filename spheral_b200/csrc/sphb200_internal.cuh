@@ -140,7 +140,7 @@ struct sphb200_ctx {
   // state0 of the integrator (State::copyState, CheapSynchronousRK2.cc:70-71)
   double* api0[S_COUNT] = {nullptr}; size_t cap0[S_COUNT] = {0}; bool have0[S_COUNT] = {false}; size_t n0 = 0;
   // reflecting planes (boundary.cu): {point[3], unit normal[3]} per plane, the ghost range and the control list of each
-  int nPlanes = 0; double planes[6*SPHB200_MAX_PLANES] = {0};
+  int nPlanes = 0; double planes[12*SPHB200_MAX_PLANES] = {0}; int planeKind[SPHB200_MAX_PLANES] = {0};   // enter {p, n}, exit {p, n}; 1 = periodic
   size_t planeFirst[SPHB200_MAX_PLANES] = {0}, planeCount[SPHB200_MAX_PLANES] = {0};
   uint32_t* planeCtl[SPHB200_MAX_PLANES] = {nullptr}; size_t planeCtlCap[SPHB200_MAX_PLANES] = {0};
   uint32_t* invPerm = nullptr; size_t invPermCap = 0;      // original index -> sorted slot (built on demand)

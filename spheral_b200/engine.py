@@ -268,6 +268,24 @@ class Engine:
         self._check(self._lib.sphb200_reflect_configure(self._h, len(planes), _dp(pts) if len(planes) else None,
                                                         _dp(nrm) if len(planes) else None))
 
+    def boundary_configure(self, boundaries):
+        """boundaries: list of ("reflecting", (point, normal)) or ("periodic", (point1, normal1), (point2, normal2)); a periodic
+        boundary expands to its two planar boundaries (plane1 -> plane2, plane2 -> plane1; PeriodicBoundary.cc:60-62)."""
+        kinds, ep, en, xp, xn = [], [], [], [], []
+        for b in boundaries:
+            if b[0] == "reflecting":
+                kinds.append(0); ep.append(b[1][0]); en.append(b[1][1]); xp.append(b[1][0]); xn.append(b[1][1])
+            elif b[0] == "periodic":
+                (p1, n1), (p2, n2) = b[1], b[2]
+                kinds += [1, 1]; ep += [p1, p2]; en += [n1, n2]; xp += [p2, p1]; xn += [n2, n1]
+            else:
+                raise ValueError("unknown boundary kind %r" % (b[0],))
+        arr = lambda v: np.ascontiguousarray(v, dtype=np.float64).reshape(-1)
+        k = (C.c_int*max(len(kinds), 1))(*kinds)
+        a = [arr(v) for v in (ep, en, xp, xn)]
+        self._keep_bnd = a
+        self._check(self._lib.sphb200_boundary_configure(self._h, len(kinds), k, *[_dp(v) if len(kinds) else None for v in a]))
+
     def reflect_set_ghost_nodes(self):
         """PlanarBoundary::setGhostNodes for every plane; returns (and records) the new ghost count."""
         ng = C.c_size_t()

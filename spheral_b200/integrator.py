@@ -18,7 +18,7 @@ INTEGRATE_DENSITY, RIGOROUS_SUM_DENSITY = 0, 1      # MassDensityType (Hydro/Gen
 class CheapSynchronousRK2:
     def __init__(self, engine, step_options=None, densityUpdate=RIGOROUS_SUM_DENSITY, gradhCorrection=True, cfl=0.25,
                  useVelocityMagnitudeForDt=False, dtMin=0.0, dtMax=1.0e100, dtGrowth=2.0, allowDtCheck=False,
-                 ghostRefresh=None, reflectingPlanes=None, distributed=None):
+                 ghostRefresh=None, reflectingPlanes=None, distributed=None, boundaries=None):
         self.engine = engine
         self.so = step_options if step_options is not None else E.make_step_options()
         self.densityUpdate, self.gradhCorrection = densityUpdate, gradhCorrection
@@ -29,8 +29,13 @@ class CheapSynchronousRK2:
         # None for a problem without ghost nodes
         self.ghostRefresh = ghostRefresh
         # reflecting planes handled on the device (ReflectingBoundary): list of (point, inward normal)
-        self.reflectingPlanes = reflectingPlanes
-        if reflectingPlanes:
+        # `boundaries` is the general form (engine.boundary_configure: reflecting and periodic planar boundaries)
+        self.reflectingPlanes = reflectingPlanes or boundaries
+        if boundaries:
+            if reflectingPlanes:
+                raise ValueError("give the planes either as reflectingPlanes or inside boundaries, not both")
+            engine.boundary_configure(boundaries)
+        elif reflectingPlanes:
             engine.reflect_configure(reflectingPlanes)
         # domain decomposition (spheral_b200.distributed.DistributedSPH): ghost exchange with the neighbouring slabs over NCCL
         self.distributed = distributed

@@ -135,12 +135,38 @@ def gamma_law(rho, eps, gamma=5.0/3.0):
     return P, cs
 
 
-def reflect_map(ndim, name, c, sd, nhat):
+def _unit(v):
+    v = np.asarray(v, dtype=float)
+    return v/np.linalg.norm(v)
+
+
+def expand_boundaries(boundaries):
+    """("reflecting", (p, n)) / ("periodic", (p1, n1), (p2, n2)) -> planar boundaries (periodic, enter (p, n), exit (p, n));
+    a PeriodicBoundary is two of them (Boundary/PeriodicBoundary.cc:60-62)."""
+    out = []
+    for b in boundaries:
+        if b[0] == "reflecting":
+            e = (np.asarray(b[1][0], dtype=float), _unit(b[1][1]))
+            out.append((False, e, e))
+        elif b[0] == "periodic":
+            e1 = (np.asarray(b[1][0], dtype=float), _unit(b[1][1]))
+            e2 = (np.asarray(b[2][0], dtype=float), _unit(b[2][1]))
+            out += [(True, e1, e2), (True, e2, e1)]
+        else:
+            raise ValueError(b[0])
+    return out
+
+
+def reflect_map(ndim, name, c, sd, nhat, periodic=False, sd_exit=None):
     """Ghost values of one field from its control values c (ReflectingBoundary::applyGhostBoundary,
-    Boundary/ReflectingBoundary.cc:182-250; positions by mapPositionThroughPlanes)."""
-    R = np.eye(ndim) - 2.0*np.outer(nhat, nhat)
+    Boundary/ReflectingBoundary.cc:182-250; periodic boundaries copy).  Positions: mapPosition(r, exit, enter) =
+    closestPointOnPlane_enter(r) - signedDistance_exit(r) n_enter (PlanarBoundary.cc:318-320); sd = distance to the enter plane."""
     if name == "pos":
-        return c - 2.0*np.outer(sd, nhat)                       # closest point on plane minus signed distance
+        sx = sd if sd_exit is None else sd_exit
+        return (c - np.outer(sd, nhat)) - np.outer(sx, nhat)
+    if periodic:
+        return c.copy()
+    R = np.eye(ndim) - 2.0*np.outer(nhat, nhat)
     if name == "H":
         Fr = np.einsum("ab,nbc,cd->nad", R, sym_to_full(ndim, c), R)
         return full_to_sym(ndim, 0.5*(Fr + np.transpose(Fr, (0, 2, 1))))
@@ -151,65 +177,52 @@ def reflect_map(ndim, name, c, sd, nhat):
     return c.copy()                                             # scalars (and any other width): copy
 
 
-def reflect_apply(ndim, fields, planes, ctl_per_plane, n0):
-    """Refresh the ghost entries of `fields` (arrays of n0 internal + ghosts, ghosts laid out plane after plane) from their
-    control nodes, plane by plane so that later planes see the refreshed ghosts of earlier ones."""
+def boundary_apply(ndim, fields, boundaries, ctl_per_plane, n0):
+    """Refresh the ghost entries of `fields` (arrays of n0 internal + ghosts, ghosts laid out boundary after boundary) from
+    their control nodes, in order, so that later boundaries see the refreshed ghosts of earlier ones."""
     first = n0
-    for (point, normal), ctl in zip(planes, ctl_per_plane):
-        nhat = np.asarray(normal, dtype=float)
-        nhat = nhat/np.linalg.norm(nhat)
-        sd = (fields["pos"][ctl] - np.asarray(point, dtype=float)) @ nhat
+    for (periodic, (pe, ne), (px, nx)), ctl in zip(expand_boundaries(boundaries), ctl_per_plane):
+        sd = (fields["pos"][ctl] - pe) @ ne
+        sx = (fields["pos"][ctl] - px) @ nx
         for k, v in fields.items():
-            v[first:first + len(ctl)] = reflect_map(ndim, k, v[ctl], sd, nhat)
+            v[first:first + len(ctl)] = reflect_map(ndim, k, v[ctl], sd, ne, periodic, sx)
         first += len(ctl)
     return fields
 
 
-def reflect_ghosts(ndim, fields, planes, kext, per_plane=False):
-    """Append reflecting-boundary ghosts for axis-aligned or general planes, applied sequentially so that later
-    planes also mirror earlier ghosts (Integrator.cc:415-424).
-
-    fields: dict with 'pos' (n,ndim), 'H' (n,nsym), optional vectors ('vel'), scalars, tensors ('DvDxQ').
-    planes: list of (point, normal) with the normal pointing INTO the domain.
-    Returns (fields_with_ghosts, control_index array for the ghosts)."""
+def boundary_ghosts(ndim, fields, boundaries, kext):
+    """Ghost nodes of planar boundaries applied one after the other (Integrator.cc:415-424): control nodes by
+    findNodesTouchingThroughPlanes (active branch): hmax = largest 1/lambda_min(H_i) among nodes closer than kext*hmax_i to either
+    plane; controls are the nodes with 0 <= signedDistance_exit/hmax <= kext.  Returns (fields with ghosts, control lists, n0)."""
     out = {k: np.array(v, dtype=float, copy=True) for k, v in fields.items()}
     n0 = out["pos"].shape[0]
-    control, lists = [], []
-    for point, normal in planes:
-        point = np.asarray(point, dtype=float)
-        nhat = np.asarray(normal, dtype=float)
-        nhat = nhat/np.linalg.norm(nhat)
-        pos, H = out["pos"], out["H"]
-        F = sym_to_full(ndim, H)
-        hmax_i = 1.0/np.linalg.eigvalsh(F)[:, 0]               # 1/min eigenvalue
-        sd = (pos - point) @ nhat                               # signed distance
-        near = (sd >= 0.0) & (sd <= kext*hmax_i)
+    lists = []
+    for periodic, (pe, ne), (px, nx) in expand_boundaries(boundaries):
+        pos = out["pos"]
+        hmax_i = 1.0/np.linalg.eigvalsh(sym_to_full(ndim, out["H"]))[:, 0]
+        sde, sdx = (pos - pe) @ ne, (pos - px) @ nx
+        near = np.minimum(np.abs(sde), np.abs(sdx)) < kext*hmax_i
         if not near.any():
             lists.append(np.zeros(0, dtype=np.int64))
             continue
         hmax = hmax_i[near].max()
-        ctl = np.nonzero((sd/hmax >= 0.0) & (sd/hmax <= kext))[0]
-        R = np.eye(ndim) - 2.0*np.outer(nhat, nhat)
-        new = {}
-        for k, v in out.items():
-            c = v[ctl]
-            if k == "pos":
-                new[k] = c - 2.0*np.outer(sd[ctl], nhat)        # closest point on plane minus signed distance
-            elif k == "H":
-                Fc = sym_to_full(ndim, c)
-                Fr = np.einsum("ab,nbc,cd->nad", R, Fc, R)
-                new[k] = full_to_sym(ndim, 0.5*(Fr + np.transpose(Fr, (0, 2, 1))))
-            elif v.ndim == 2 and v.shape[1] == ndim:            # vectors
-                new[k] = c @ R.T
-            elif v.ndim == 2 and v.shape[1] == ndim*ndim:       # tensors R.(T.R)
-                Tc = c.reshape(-1, ndim, ndim)
-                new[k] = np.einsum("ab,nbc,cd->nad", R, Tc, R).reshape(-1, ndim*ndim)
-            else:                                               # scalars copy
-                new[k] = c.copy()
+        ctl = np.nonzero((sdx/hmax >= 0.0) & (sdx/hmax <= kext))[0]
+        new = {k: reflect_map(ndim, k, v[ctl], sde[ctl], ne, periodic, sdx[ctl]) for k, v in out.items()}
         for k in out:
             out[k] = np.concatenate([out[k], new[k]], axis=0)
-        control.extend(ctl.tolist())
         lists.append(ctl)
+    return out, lists, n0
+
+
+def reflect_apply(ndim, fields, planes, ctl_per_plane, n0):
+    """boundary_apply for reflecting planes given as (point, inward normal)."""
+    return boundary_apply(ndim, fields, [("reflecting", pl) for pl in planes], ctl_per_plane, n0)
+
+
+def reflect_ghosts(ndim, fields, planes, kext, per_plane=False):
+    """Reflecting-boundary ghosts for planes given as (point, inward normal); see boundary_ghosts.
+    Returns (fields_with_ghosts, control index array -- or the per-plane lists --, n0)."""
+    out, lists, n0 = boundary_ghosts(ndim, fields, [("reflecting", pl) for pl in planes], kext)
     if per_plane:
         return out, lists, n0
-    return out, np.array(control, dtype=np.int64), n0
+    return out, np.concatenate(lists).astype(np.int64) if lists else np.zeros(0, dtype=np.int64), n0

@@ -154,3 +154,55 @@ def test_noh_cylindrical_2d_device_resident(oracle, mods):
     assert 12.0 < prof[3] < 16.5                                   # the compressed plateau behind the shock at r = 0.2
     assert abs(prof[6]/(1.0 + tend/0.325) - 1.0) < 0.06            # pre-shock: rho = 1 + t/r
     assert np.all(pos >= 0.0)
+
+
+@pytest.mark.parametrize("ndim,n,nPerh", [(2, 20, 2.01), (3, 8, 1.51)])
+def test_periodic_and_reflecting_boundaries(oracle, mods, ndim, n, nPerh):
+    """PeriodicBoundary in x (two planar boundaries, plane1 -> plane2 and back; PeriodicBoundary.cc:60-62) combined with
+    reflecting planes on the other axes: device ghost generation / refresh / enforcement against the numpy restatement
+    (nodegen.boundary_ghosts), and the derivatives on that ghost set against the oracle."""
+    engine, _ = mods
+    st, nInt, _ = common.make_problem(ndim, n, nPerh=nPerh, seed=13)
+    WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    ex = np.eye(ndim)[0]
+    bnds = [("periodic", (np.zeros(ndim), ex), (ex.copy(), -ex))] + [("reflecting", (np.zeros(ndim), np.eye(ndim)[a])) for a in range(1, ndim)]
+    f = {o: st[k] for k, o in PN.items()}
+    ref, lists, n0 = ng.boundary_ghosts(ndim, f, bnds, WT.kernelExtent)
+    e = engine.Engine(ndim, nPerh=nPerh)
+    e.set_kernel_table(WT)
+    e.set_nodes(nInt, 0)
+    e.upload_state(**st)
+    e.boundary_configure(bnds)
+    ngh = e.reflect_set_ghost_nodes()
+    assert ngh == ref["pos"].shape[0] - nInt and len(lists) == ndim + 1 and all(len(l) > 0 for l in lists)
+    got = e.download_state(*PN.keys())
+    for k, o in PN.items():
+        assert np.abs(got[k] - ref[o]).max() <= 1e-14*max(np.abs(ref[o]).max(), 1e-300), k
+    # periodic images are displaced by exactly one period and carry unreflected values
+    g0 = slice(nInt, nInt + len(lists[0]))
+    assert np.allclose(got["position"][g0] - got["position"][lists[0]], -ex, atol=1e-15)      # controls near x = 1 -> ghosts below x = 0
+    assert np.array_equal(got["velocity"][g0], got["velocity"][lists[0]])
+    # derivatives on that ghost set
+    OT = common.oracle_table(oracle, WT)
+    oo, po = common.opts_pair(oracle, engine, ndim, nPerh=nPerh)
+    pi, pj, cnt = oracle.pairs(ndim, nInt, ngh, ref["pos"], ref["H"], OT.kext)
+    d = oracle.evaluate_derivatives(oo, OT, dict(ref), nInt, ngh, pi, pj, cnt)
+    assert e.build_pairs() == len(pi)
+    e.evaluate_derivatives()
+    g = e.download_derivs("DvDt", "DrhoDt", "DepsDt", "DvDx")
+    floors = common.physical_floors({k: got[k] for k in PN}, nInt, ndim)
+    for k in g:
+        assert common.field_err(g[k], d[k], nInt, floors[k]) <= 1e-10, k
+    # enforcement: a node pushed through the periodic plane re-enters on the other side with its velocity unchanged, one pushed
+    # through a reflecting plane is mirrored
+    pos, vel = got["position"].copy(), got["velocity"].copy()
+    pos[5, 0] = -0.02
+    pos[6, 0] = 1.03
+    pos[7, 1] = -0.01
+    e.upload_state(position=pos)
+    assert e.reflect_enforce(count=True) == 3
+    back = e.download_state("position", "velocity")
+    assert abs(back["position"][5, 0] - 0.98) < 1e-15 and abs(back["position"][6, 0] - 0.03) < 1e-15
+    assert abs(back["position"][7, 1] - 0.01) < 1e-16
+    assert np.array_equal(back["velocity"][5], vel[5]) and np.array_equal(back["velocity"][6], vel[6])
+    assert back["velocity"][7, 1] == -vel[7, 1] and back["velocity"][7, 0] == vel[7, 0]
