@@ -301,6 +301,7 @@ void sphb200_destroy(sphb200_ctx* c) {
   for (int s = 0; s < S_COUNT; ++s) if (c->api0[s]) cudaFree(c->api0[s]);
   for (int p = 0; p < SPHB200_MAX_PLANES; ++p) if (c->planeCtl[p]) cudaFree(c->planeCtl[p]);
   if (c->invPerm) cudaFree(c->invPerm);
+  if (c->hDone) cudaFree(c->hDone);
   cudaFreeHost(c->reduceHost); cudaFreeHost(c->countersHost);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);

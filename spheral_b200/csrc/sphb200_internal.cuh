@@ -144,6 +144,7 @@ struct sphb200_ctx {
   size_t planeFirst[SPHB200_MAX_PLANES] = {0}, planeCount[SPHB200_MAX_PLANES] = {0};
   uint32_t* planeCtl[SPHB200_MAX_PLANES] = {nullptr}; size_t planeCtlCap[SPHB200_MAX_PLANES] = {0};
   uint32_t* invPerm = nullptr; size_t invPermCap = 0;      // original index -> sorted slot (built on demand)
+  uint32_t* hDone = nullptr; size_t hDoneCap = 0;           // iterateIdealH: nodes whose H has converged
   // time-step reduction scratch
   unsigned long long* dtCand = nullptr; size_t dtCandCap = 0;
   double* dtAux = nullptr; size_t dtAuxCap = 0;

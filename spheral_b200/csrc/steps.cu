@@ -225,6 +225,36 @@ __global__ void __launch_bounds__(RB) k_state_update(UpdateArgs a) {
   for (int q = 0; q < NS; ++q) a.H[o*NS + q] = Hi[q];
 }
 
+// ---- iterateIdealH (Utilities/iterateIdealH.cc:120-190): one sweep H <- "new H" over the nodes not yet converged -----------------------
+// deltaH_i = max |phi - 1| over the eigenvalues phi of H1^(1/2) H^-1 H1^(1/2).  The SPH smoothing scale's ideal H is a multiple of the
+// identity (SPHSmoothingScale.cc:262-268), H1 = h1 I, for which phi = h1/lambda(H): only the eigenvalue range of the current H is needed.
+template <int DIM>
+__global__ void __launch_bounds__(RB) k_iterate_h(const uint32_t* __restrict__ perm, size_t n, size_t cap, uint32_t nInt,
+                                                  const double* __restrict__ Hideal, double* __restrict__ H, uint32_t* __restrict__ done,
+                                                  double tolerance, unsigned long long* __restrict__ maxDeltaBits) {
+  constexpr int NS = Dm<DIM>::NS;
+  const size_t s = (size_t)blockIdx.x*RB + threadIdx.x;
+  double delta = 0.0;
+  if (s < n) {
+    const size_t o = perm[s];
+    if (o < nInt && done[o] == 0u) {
+      double Hi[NS], H1[NS];
+#pragma unroll
+      for (int q = 0; q < NS; ++q) { Hi[q] = H[o*NS + q]; H1[q] = Hideal[(size_t)q*cap + s]; }
+      double lo, hi;
+      sym_eigenvalue_range<DIM>(Hi, lo, hi);
+      const double h1 = H1[0];
+      delta = fmax(fabs(h1/hi - 1.0), fabs(h1/lo - 1.0));
+      if (delta <= tolerance) done[o] = 1u;
+#pragma unroll
+      for (int q = 0; q < NS; ++q) H[o*NS + q] = H1[q];
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) delta = fmax(delta, __shfl_down_sync(0xffffffffu, delta, off));
+  if ((threadIdx.x & 31) == 0 && delta > 0.0) atomicMax(maxDeltaBits, (unsigned long long)__double_as_longlong(delta));
+}
+
 // ---- GenericHydro::dt ------------------------------------------------------------------------------------------------------------------
 // A candidate is {dt, tag}; tag = phase<<40 | node<<3 | reason orders equal dt values the way the reference meets them (nodes in
 // index order with the checks in source order, then the pair loop), so the reported reason / node match the reference's.
@@ -484,6 +514,30 @@ int sphb200_state_assign(sphb200_ctx* c) {
     CU_CHECK(c, cudaMemcpyAsync(c->api[s], c->api0[s], c->n*(size_t)sphb200_state_width(c->ndim, s)*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   }
   c->rowsValid = false;
+  return 0;
+}
+
+int sphb200_iterate_ideal_h(sphb200_ctx* c, int firstSweep, double tolerance, double* maxDeltaH) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
+  if (c->opt.hEvolution != SPHB200_H_SPH) return sphb200_fail(c, "iterate_ideal_h: only the SPH smoothing scale computes an ideal H on the device (the ASPH ideal H needs the Voronoi second moment, out of scope)");
+  if (!c->derivsValid || !c->pairsValid) return sphb200_fail(c, "iterate_ideal_h: needs the derivatives ('new H') of the current connectivity");
+  if (maxDeltaH) *maxDeltaH = 0.0;
+  if (c->nInt == 0) return 0;
+  if (sphb200_ensure(c, c->hDone, c->hDoneCap, c->cap)) return 1;
+  if (firstSweep) CU_CHECK(c, cudaMemsetAsync(c->hDone, 0, c->cap*sizeof(uint32_t), c->stream));
+  CU_CHECK(c, cudaMemsetAsync(c->counters + 9, 0, sizeof(unsigned long long), c->stream));
+  const unsigned nb = (unsigned)((c->n + RB - 1)/RB);
+  if (c->ndim == 3) k_iterate_h<3><<<nb, RB, 0, c->stream>>>(c->perm, c->n, c->cap, (uint32_t)c->nInt, c->deriv[DV_HIDEAL], c->api[S_H], c->hDone, tolerance, c->counters + 9);
+  else              k_iterate_h<2><<<nb, RB, 0, c->stream>>>(c->perm, c->n, c->cap, (uint32_t)c->nInt, c->deriv[DV_HIDEAL], c->api[S_H], c->hDone, tolerance, c->counters + 9);
+  KERNEL_CHECK(c, "k_iterate_h");
+  unsigned long long bits = 0;
+  CU_CHECK(c, cudaMemcpyAsync(&bits, c->counters + 9, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(c, cudaStreamSynchronize(c->stream));
+  double d; memcpy(&d, &bits, 8);
+  if (maxDeltaH) *maxDeltaH = d;
+  // H changed: the connectivity and everything derived from it are stale
+  c->sortValid = c->rowsValid = c->pairsValid = c->derivsValid = false;
   return 0;
 }
 

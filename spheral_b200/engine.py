@@ -253,6 +253,12 @@ class Engine:
         """State::update(derivs, multiplier, t, dt) for the hydro + smoothing-scale policies, then P and cs."""
         self._check(self._lib.sphb200_state_update(self._h, C.byref(step_options), multiplier, int(bool(timeAdvanceOnly))))
 
+    def iterate_ideal_h(self, first_sweep, tolerance):
+        """One H <- 'new H' sweep of iterateIdealH over the nodes not yet converged; returns maxDeltaH."""
+        d = C.c_double()
+        self._check(self._lib.sphb200_iterate_ideal_h(self._h, int(bool(first_sweep)), tolerance, C.byref(d)))
+        return d.value
+
     def compute_dt(self, cfl=0.25, useVelocityMagnitudeForDt=False):
         """GenericHydro::dt -> (dt, reason string, limiting node)."""
         dt, reason, node = C.c_double(), C.c_int(), C.c_uint32()

@@ -231,3 +231,21 @@ class CheapSynchronousRK2:
             self.step(goalTime)
             n += 1
         return n
+
+
+def iterateIdealH(engine, maxIterations=100, tolerance=1.0e-10, setGhostNodes=None):
+    """Utilities/iterateIdealH.cc: the start-up relaxation of the smoothing scales, with the state on the device.  Every
+    iteration regenerates the ghost nodes (setGhostNodes: e.g. engine.reflect_set_ghost_nodes), rebuilds the connectivity,
+    evaluates the smoothing-scale derivatives and replaces H by the ideal H on the nodes that have not converged.
+    Returns (iterations, maxDeltaH).  SPH smoothing scale only."""
+    it, maxDeltaH = 0, 2.0*tolerance
+    while it < maxIterations and maxDeltaH > tolerance:
+        it += 1
+        if setGhostNodes is not None:
+            setGhostNodes()
+        engine.build_pairs()
+        engine.evaluate_derivatives(0.0, 1.0)
+        maxDeltaH = engine.iterate_ideal_h(it == 1, tolerance)
+    if setGhostNodes is not None:
+        setGhostNodes()
+    return it, maxDeltaH

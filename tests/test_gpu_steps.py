@@ -265,3 +265,47 @@ def test_restart_is_bit_exact(oracle, mods, ndim, n, nPerh, Qkind, planes):
     assert rk2.currentCycle == rk1.currentCycle == 4 and rk2.currentTime == rk1.currentTime and rk2.lastDt == rk1.lastDt
     for k in a:
         assert np.array_equal(a[k][:nInt], b[k][:nInt]), k
+
+
+@pytest.mark.parametrize("ndim,n,nPerh", [(3, 11, 1.51), (2, 30, 2.01)])
+def test_iterate_ideal_h(oracle, mods, ndim, n, nPerh):
+    """iterateIdealH (Utilities/iterateIdealH.cc) on the device against the same loop driven through the oracle: same number of
+    sweeps, same maxDeltaH history, H within 1e-10; and the fixed point property H == 'new H' at the end."""
+    engine, integrator = mods
+    st, nInt, _ = common.make_problem(ndim, n, nPerh=nPerh, seed=71)
+    rng = np.random.default_rng(3)
+    st["H"] = st["H"]*(1.0 + 0.3*rng.uniform(-1.0, 1.0, size=(nInt, 1)))
+    WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    OT = common.oracle_table(oracle, WT)
+    oo, po = common.opts_pair(oracle, engine, ndim, nPerh=nPerh)
+    tol, maxIt = 1.0e-4, 50
+    # oracle-driven loop (iterateIdealH.cc:120-190 for an isotropic ideal H: phi = h1/lambda(H))
+    s = common.to_oracle_state(st)
+    done = np.zeros(nInt, dtype=bool)
+    hist = []
+    for it in range(maxIt):
+        pi, pj, cnt = oracle.pairs(ndim, nInt, 0, s["pos"], s["H"], OT.kext)
+        d = oracle.evaluate_derivatives(oo, OT, s, nInt, 0, pi, pj, cnt)
+        lam = np.linalg.eigvalsh(common.ng.sym_to_full(ndim, s["H"]))
+        h1 = d["Hideal"][:, 0]
+        delta = np.maximum(np.abs(h1/lam[:, -1] - 1.0), np.abs(h1/lam[:, 0] - 1.0))
+        act = ~done
+        hist.append(float(delta[act].max()) if act.any() else 0.0)
+        done |= act & (delta <= tol)
+        H = s["H"].copy(); H[act] = d["Hideal"][act]
+        s = dict(s, H=H)
+        if hist[-1] <= tol:
+            break
+    e = engine.Engine(ndim, options=po)
+    e.set_kernel_table(WT)
+    e.set_nodes(nInt, 0)
+    e.upload_state(**st)
+    its, dmax = integrator.iterateIdealH(e, maxIterations=maxIt, tolerance=tol)
+    assert its == len(hist) and abs(dmax - hist[-1]) <= 1e-6*max(hist[-1], 1e-300) + 1e-12, (its, len(hist), dmax, hist[-1])
+    assert hist[-1] <= tol < hist[0]
+    got = e.download_state("H")["H"]
+    assert np.abs(got - s["H"]).max() <= 1e-10*np.abs(s["H"]).max()
+    # fixed point: one more evaluation reproduces H to the tolerance
+    e.build_pairs(); e.evaluate_derivatives()
+    hid = e.download_derivs("Hideal")["Hideal"]
+    assert np.abs(hid[:, 0]/got[:, 0] - 1.0).max() <= 10*tol
