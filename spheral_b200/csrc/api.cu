@@ -56,13 +56,6 @@ __global__ void __launch_bounds__(RB) k_counts_by_orig(const uint32_t* __restric
   if (o < nInt) out[o] = nbrCount[s];
 }
 // halo: gather listed nodes of one field into a staging block / scatter a block into a contiguous ghost range
-__global__ void __launch_bounds__(RB) k_halo_pack(const double* __restrict__ field, int width, const uint32_t* __restrict__ nodes,
-                                                  size_t count, double* __restrict__ out) {
-  const size_t t = (size_t)blockIdx.x*RB + threadIdx.x;
-  if (t >= count*(size_t)width) return;
-  const size_t k = t/width; const int q = (int)(t % width);
-  out[t] = field[(size_t)nodes[k]*width + q];
-}
 // all masked fields of one side in ONE launch (a launch per field left the GPU idle between ~36 tiny operations per refresh)
 struct HaloFields { const double* src[S_COUNT]; double* dst[S_COUNT]; int width[S_COUNT]; unsigned long long off[S_COUNT]; int nf; unsigned long long total; };
 __global__ void __launch_bounds__(RB) k_halo_pack_all(HaloFields f, const uint32_t* __restrict__ nodes, size_t count, double* __restrict__ out) {

@@ -32,18 +32,9 @@ struct DerivArgs {
   double* pacc; size_t nSlots;
 };
 
-// 256-bit read-only row loads (LDG.E.256, sm_100): a 128-byte node row is four of them.
-__device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d) {
-  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
-}
-
 // Asynchronous global->shared copies (LDGSTS): a warp streams the 128-byte rows of its lanes' upcoming neighbours into a
 // shared-memory ring, PAIR_STAGES iterations ahead of their use, so the L2 latency of the gather is off the critical path
 // although only 2 warps per scheduler are resident (the accumulators cost ~200 registers per thread).
-__device__ __forceinline__ void cp_async16(void* smemDst, const void* gmemSrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmemSrc) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
