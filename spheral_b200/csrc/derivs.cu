@@ -39,7 +39,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 __device__ __forceinline__ void cp_async16_s(unsigned smemDst, const void* gmemSrc) {
+#if defined(SPHB200_CP_CG) && SPHB200_CP_CG
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smemDst), "l"(gmemSrc) : "memory");     // L2 only
+#else
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smemDst), "l"(gmemSrc) : "memory");
+#endif
 }
 
 #ifndef SPHB200_COPY_LANES

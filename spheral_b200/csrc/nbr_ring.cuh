@@ -15,7 +15,11 @@
 namespace {
 
 __device__ __forceinline__ void ring_cp16(unsigned smemDst, const void* gmemSrc) {
+#if defined(SPHB200_CP_CG) && SPHB200_CP_CG
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smemDst), "l"(gmemSrc) : "memory");     // L2 only
+#else
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smemDst), "l"(gmemSrc) : "memory");
+#endif
 }
 __device__ __forceinline__ void ring_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void ring_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
