@@ -136,6 +136,9 @@ int  sphb200_download_state(sphb200_ctx* ctx, unsigned fieldMask, double* const*
              ConnectivityMap::computeConnectivity (ConnectivityMap.cc:747-1152).
    Uses the positions/H currently on the device.  npairs = size of the NodePairList (i<j once). */
 int  sphb200_build_pairs(sphb200_ctx* ctx, size_t* npairs);
+/* 1 if the pair lists on the device match the positions / H there (no upload or halo landing of either since the last build);
+   the role of DataBase::connectivityMap() being current.  No device work. */
+int  sphb200_connectivity_valid(const sphb200_ctx* ctx);
 /* NodePairList in the reference order (NodePairIdxType::operator<, NodePairIdxType.hh:34-58): sorted (i,j), i<j. */
 int  sphb200_download_pairs(sphb200_ctx* ctx, uint32_t* i, uint32_t* j, size_t cap);
 /* ConnectivityMap::numNeighborsForNode for internal nodes (ConnectivityMapInline.hh) */

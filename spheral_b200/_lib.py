@@ -101,7 +101,7 @@ EXPORTS = ("sphb200_abi_version", "sphb200_create", "sphb200_destroy", "sphb200_
            "sphb200_state_assign", "sphb200_state_update", "sphb200_compute_dt",
            "sphb200_reflect_configure", "sphb200_reflect_set_ghost_nodes", "sphb200_reflect_apply_ghosts", "sphb200_reflect_enforce",
            "sphb200_reflect_finalize_derivatives", "sphb200_halo_unpack_values", "sphb200_halo_pack_derivs",
-           "sphb200_halo_unpack_derivs", "sphb200_upload_derivs", "sphb200_boundary_configure", "sphb200_iterate_ideal_h")
+           "sphb200_halo_unpack_derivs", "sphb200_upload_derivs", "sphb200_boundary_configure", "sphb200_iterate_ideal_h", "sphb200_connectivity_valid")
 
 _lib = None
 
@@ -176,5 +176,6 @@ def lib():
     L.sphb200_upload_derivs.argtypes = [vp, C.c_uint, C.POINTER(HostDerivs)]
     L.sphb200_boundary_configure.argtypes = [vp, C.c_int, C.POINTER(C.c_int), _dp, _dp, _dp, _dp]
     L.sphb200_iterate_ideal_h.argtypes = [vp, C.c_int, C.c_double, _dp]
+    L.sphb200_connectivity_valid.argtypes = [vp]
     _lib = L
     return L

@@ -447,6 +447,8 @@ int sphb200_build_pairs(sphb200_ctx* c, size_t* npairs) {
   return 0;
 }
 
+int sphb200_connectivity_valid(const sphb200_ctx* c) { return (c && c->pairsValid) ? 1 : 0; }
+
 int sphb200_download_pairs(sphb200_ctx* c, uint32_t* i, uint32_t* j, size_t cap) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
   if (!c->pairsValid) return sphb200_fail(c, "download_pairs: no valid pair list (call build_pairs after changing position/H)");

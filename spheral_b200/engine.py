@@ -162,6 +162,9 @@ class Engine:
         self.npairs = np_.value
         return self.npairs
 
+    def connectivity_valid(self):
+        return bool(self._lib.sphb200_connectivity_valid(self._h))
+
     def download_pairs(self):
         pi = np.zeros(max(self.npairs, 1), dtype=np.uint32)
         pj = np.zeros(max(self.npairs, 1), dtype=np.uint32)

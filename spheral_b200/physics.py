@@ -531,11 +531,7 @@ class SPHB200(Physics):
         return True
 
     def _engine_pairs_usable(self):
-        try:
-            self._engine.download_neighbor_counts()
-            return True
-        except SPHB200Error:
-            return False
+        return self._engine.connectivity_valid()
 
     def dt(self, dataBase, state, derivs, currentTime=0.0):
         """GenericHydro::dt (Physics/GenericHydro.cc:112-381) -> (dt, reason), from the state on the host and the derivatives
