@@ -348,6 +348,7 @@ def main():
         pair_ms.append(s_["ms_pair_kernel"]); nbr_ms.append(s_["ms_neighbor_kernels"])
         build_ms.append(s_["ms_build_pairs"]); eval_ms.append(s_["ms_evaluate"])
     edges = e.stats()["directed_edges"]
+    stencil_radius = e.stats()["stencil_radius"]
     halo_info = dsph.info() if dsph is not None else None
 
     # device-resident CheapSynchronousRK2 steps: neighbour update + sum density + dt vote + trial advance +
@@ -423,7 +424,7 @@ def main():
         line = {"metric": metric, "value": value, "unit": "particle-updates/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warmup, "ms_per_step": dev_s/args.steps*1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": dict(config, neighbours_per_particle=nbrs, halo=halo_info,
+                "config": dict(config, neighbours_per_particle=nbrs, halo=halo_info, grid_stencil_radius=int(stencil_radius),
                                timing="CUDA events on the engine stream around the K steps, max over ranks"),
                 "clocks": clocks,
                 "e2e": {"value": total_updates/e2e_s, "unit": "particle-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

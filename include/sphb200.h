@@ -303,6 +303,8 @@ typedef struct {
   float ms_pair_kernel;        /* the K3 pair-loop kernel alone */
   float ms_neighbor_kernels;   /* K2 count+fill */
   uint64_t directed_edges;     /* sum of neighbour counts (2*internal-internal + internal-ghost pairs) */
+  uint32_t stencil_radius;     /* cells a tile walks in each direction at most: 1 when the grid cells are as wide as the largest
+                                  kernel extent, > 1 when a heavy tail of extents made the grid follow the typical extent */
 } sphb200_stats;
 int  sphb200_get_stats(sphb200_ctx* ctx, sphb200_stats* out);
 /* FP64 FMA throughput microbenchmark on the context's device (roofline denominator; returns TFLOP/s). */

@@ -267,7 +267,7 @@ int sphb200_create(sphb200_ctx** out, int device, const sphb200_options* opts) {
   cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&c->evGeomUp, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->evRestUp, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->evMainMark, cudaEventDisableTiming);
-  cudaMalloc((void**)&c->reduceBuf, (296*9 + 16)*sizeof(double));
+  cudaMalloc((void**)&c->reduceBuf, (296*12 + 16)*sizeof(double));
   cudaMallocHost((void**)&c->reduceHost, 16*sizeof(double));
   cudaMalloc((void**)&c->counters, 16*sizeof(unsigned long long));      // [0,8) neighbour build, [8] anisotropy flag of k_pack
   cudaMemset(c->counters, 0, 16*sizeof(unsigned long long));
@@ -295,6 +295,8 @@ void sphb200_destroy(sphb200_ctx* c) {
   for (int p = 0; p < SPHB200_MAX_PLANES; ++p) if (c->planeCtl[p]) cudaFree(c->planeCtl[p]);
   if (c->invPerm) cudaFree(c->invPerm);
   if (c->hDone) cudaFree(c->hDone);
+  if (c->cellReach) cudaFree(c->cellReach);
+  if (c->tileRadius) cudaFree(c->tileRadius);
   cudaFreeHost(c->reduceHost); cudaFreeHost(c->countersHost);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -436,7 +438,14 @@ int sphb200_build_pairs(sphb200_ctx* c, size_t* npairs) {
   cudaEventRecord(c->ev[0], c->stream);
   if (sphb200_sort_and_pack(c)) return 1;
   cudaEventRecord(c->ev[1], c->stream);
-  if (sphb200_neighbors(c)) return 1;
+  int nrc = sphb200_neighbors(c);
+  if (nrc == 2) {                                    // fine grid + wide stencil produced too many runs for a tile: wide cells instead
+    c->forceR1 = true;
+    if (sphb200_sort_and_pack(c)) return 1;
+    cudaEventRecord(c->ev[1], c->stream);
+    nrc = sphb200_neighbors(c);
+  }
+  if (nrc) return 1;
   cudaEventRecord(c->ev[2], c->stream);
   CU_CHECK(c, cudaStreamSynchronize(c->stream));
   cudaEventElapsedTime(&c->stats.ms_build_pairs, c->ev[0], c->ev[2]);
@@ -740,7 +749,7 @@ int sphb200_node_bounds_device(sphb200_ctx* c, size_t count, double* outDevice) 
   if (count > c->n || count == 0) return sphb200_fail(c, "node_bounds_device: count must be in [1, node count]");
   if (!c->have[S_POS] || !c->have[S_H] || !c->W.set) return sphb200_fail(c, "node_bounds_device: position, H and the kernel table must be set first");
   if (sphb200_bounds_reduce(c, count)) return 1;
-  CU_CHECK(c, cudaMemcpyAsync(outDevice, c->reduceBuf + 296*9, 9*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  CU_CHECK(c, cudaMemcpyAsync(outDevice, c->reduceBuf + 296*12, 9*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   return 0;
 }
 
@@ -775,6 +784,7 @@ int sphb200_get_stats(sphb200_ctx* c, sphb200_stats* out) {
   }
   if (cudaEventElapsedTime(&c->stats.ms_energy, c->ev[6], c->ev[7]) != cudaSuccess) c->stats.ms_energy = 0;
   cudaGetLastError();
+  c->stats.stencil_radius = (uint32_t)c->stencilR;
   *out = c->stats;
   return 0;
 }

@@ -73,12 +73,12 @@ template <int DIM> __device__ __forceinline__ void h_extent(const double* H, dou
 __device__ __forceinline__ double warp_min(double v) { for (int d = 16; d; d >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, d)); return v; }
 __device__ __forceinline__ double warp_max(double v) { for (int d = 16; d; d >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, d)); return v; }
 
-// partial[blk*9 + (0..2 lo, 3..5 hi, 6..8 ext)]
+// partial[blk*12 + (0..2 lo, 3..5 hi, 6..8 largest extent, 9..11 sum of extents)]
 template <int DIM>
 __global__ void __launch_bounds__(RB) k_bbox(const double* __restrict__ pos, const double* __restrict__ H, size_t n, double kext,
                                              double* __restrict__ partial) {
   constexpr int NS = Dm<DIM>::NS;
-  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, ex[3] = {0, 0, 0};
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, ex[3] = {0, 0, 0}, es[3] = {0, 0, 0};
   for (size_t i = (size_t)blockIdx.x*RB + threadIdx.x; i < n; i += (size_t)gridDim.x*RB) {
     double h[NS], e[DIM];
 #pragma unroll
@@ -87,27 +87,33 @@ __global__ void __launch_bounds__(RB) k_bbox(const double* __restrict__ pos, con
 #pragma unroll
     for (int a = 0; a < DIM; ++a) {
       const double x = pos[i*DIM + a];
-      lo[a] = fmin(lo[a], x); hi[a] = fmax(hi[a], x); ex[a] = fmax(ex[a], e[a]);
+      lo[a] = fmin(lo[a], x); hi[a] = fmax(hi[a], x); ex[a] = fmax(ex[a], e[a]); es[a] += e[a];
     }
   }
-  __shared__ double sm[RB/32][9];
+  __shared__ double sm[RB/32][12];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int a = 0; a < 3; ++a) {
     const double l = warp_min(lo[a]), h2 = warp_max(hi[a]), e2 = warp_max(ex[a]);
-    if (lane == 0) { sm[w][a] = l; sm[w][3 + a] = h2; sm[w][6 + a] = e2; }
+    double sum = es[a];
+    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if (lane == 0) { sm[w][a] = l; sm[w][3 + a] = h2; sm[w][6 + a] = e2; sm[w][9 + a] = sum; }
   }
   __syncthreads();
-  if (threadIdx.x < 9) {
+  if (threadIdx.x < 12) {
     double v = sm[0][threadIdx.x];
-    for (int k = 1; k < RB/32; ++k) v = (threadIdx.x < 3) ? fmin(v, sm[k][threadIdx.x]) : fmax(v, sm[k][threadIdx.x]);
-    partial[blockIdx.x*9 + threadIdx.x] = v;
+    for (int k = 1; k < RB/32; ++k) v = (threadIdx.x < 3) ? fmin(v, sm[k][threadIdx.x]) : (threadIdx.x < 9 ? fmax(v, sm[k][threadIdx.x]) : v + sm[k][threadIdx.x]);
+    partial[blockIdx.x*12 + threadIdx.x] = v;
   }
 }
-__global__ void k_bbox_final(const double* __restrict__ partial, int nb, double* __restrict__ out) {   // 9 warps, one per output
+__global__ void k_bbox_final(const double* __restrict__ partial, int nb, double* __restrict__ out) {   // 12 warps, one per output
   const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double v = (q < 3) ? 1e300 : -1e300;
-  for (int k = lane; k < nb; k += 32) v = (q < 3) ? fmin(v, partial[k*9 + q]) : fmax(v, partial[k*9 + q]);
-  v = (q < 3) ? warp_min(v) : warp_max(v);
+  double v = (q < 3) ? 1e300 : (q < 9 ? -1e300 : 0.0);
+  for (int k = lane; k < nb; k += 32) {
+    const double p = partial[k*12 + q];
+    v = (q < 3) ? fmin(v, p) : (q < 9 ? fmax(v, p) : v + p);
+  }
+  if (q < 3) v = warp_min(v); else if (q < 9) v = warp_max(v);
+  else { for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d); }
   if (lane == 0) out[q] = v;
 }
 
@@ -144,6 +150,51 @@ __global__ void __launch_bounds__(RB) k_cell_order(const uint32_t* __restrict__ 
   }
 }
 
+// ---- K1c': stencil radius per cell (only when the grid is finer than the largest extent) ---------------------------------------
+// A pair (i, j) is a neighbour pair if EITHER ellipsoid contains the other node, so a tile must walk as far as the extent of its
+// own nodes (gather) and as far as the extent of any node that may contain them (scatter).  Every node with an extent of more
+// than one cell writes its radius (in cells) over the block of cells it can reach; a tile then walks the largest radius
+// recorded on the cells of its nodes.
+template <int DIM>
+__global__ void __launch_bounds__(RB) k_cell_reach(const double* __restrict__ pos, const double* __restrict__ H, size_t n, double kext, GridDev g,
+                                                   const uint32_t* __restrict__ dilTab, int rmax, uint32_t* __restrict__ reach) {
+  constexpr int NS = Dm<DIM>::NS;
+  const size_t i = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (i >= n) return;
+  double h[NS], e[DIM];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) h[k] = H[i*NS + k];
+  h_extent<DIM>(h, kext, e);
+  int r = 1, ci[3] = {0, 0, 0};
+#pragma unroll
+  for (int a = 0; a < DIM; ++a) {
+    r = max(r, (int)ceil(e[a]/g.cs[a]));
+    ci[a] = cell_coord(pos[i*DIM + a], g.lo[a], g.cs[a], g.nc[a]);
+  }
+  if (r <= 1) return;
+  r = min(r, rmax);
+  const int zlo = (DIM == 3) ? max(ci[2] - r, 0) : 0, zhi = (DIM == 3) ? min(ci[2] + r, g.nc[2] - 1) : 0;
+  for (int z = zlo; z <= zhi; ++z)
+    for (int y = max(ci[1] - r, 0); y <= min(ci[1] + r, g.nc[1] - 1); ++y) {
+      const uint32_t kyz = dilTab[SPHB200_DIL + y] | ((DIM == 3) ? dilTab[2*SPHB200_DIL + z] : 0u);
+      for (int x = max(ci[0] - r, 0); x <= min(ci[0] + r, g.nc[0] - 1); ++x) {
+        uint32_t* p = reach + (dilTab[x] | kyz);
+        if (*p < (uint32_t)r) atomicMax(p, (uint32_t)r);
+      }
+    }
+}
+
+// candidate-volume proxy of the fine grid: sum over nodes of (2 r + 1)^DIM with r the radius recorded on the node's cell
+template <int DIM>
+__global__ void __launch_bounds__(RB) k_reach_cost(const uint32_t* __restrict__ keyApi, size_t n, const uint32_t* __restrict__ reach,
+                                                   unsigned long long* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x*RB + threadIdx.x;
+  unsigned long long v = 0;
+  if (i < n) { const unsigned long long w = 2ull*max(1u, reach[keyApi[i]]) + 1ull; v = (DIM == 3) ? w*w*w : w*w; }
+  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
+
 // ---- K1d: gather the host-ordered fields into Morton-sorted 128-byte node rows --------------------------------------------
 struct PackArgs {
   const double *pos, *vel, *H, *mass, *rho, *P, *omega, *cs, *DvDxQ, *fCl, *fCq;
@@ -151,7 +202,7 @@ struct PackArgs {
   const uint32_t *perm, *keyApi;
   uint32_t* skey;
   size_t n;
-  float* frows; GridDev g; double kext; double csmax;
+  float* frows; GridDev g; double kext; double csmax;   // csmax: largest cell width x (3 rad + 4)/7 (FP32 error of k*cs + rel, |k| <= rad)
   int rawP;                       // CRKSPH: the row carries P itself (CRKSPH.cc:376 uses Pi + Pj), not safeInv(omega)*P/rho^2
   unsigned long long* aniso;      // set to 1 if any H is not a multiple of the identity (selects the isotropic pair loop)
 };
@@ -250,26 +301,28 @@ struct NbrArgs {
   size_t n; uint32_t nInt; double kext2; GridDev g;
   uint32_t* nbrCount; uint32_t* tileRows; unsigned long long* tileOff; uint32_t* nbr; unsigned long long nbrCap;
   uint4* runs; unsigned long long runsCap; uint32_t* tileRunStart; uint32_t* tileRunCount;
-  unsigned long long* counters;      // [0] hits on ghost candidates  [1] directed edges  [2] run cursor  [3] list cursor  [4] longest list
+  const uint32_t* cellReach;         // per cell key: stencil radius its tiles must walk (null: radius 1 everywhere)
+  uint32_t* tileRadius;              // per tile: stencil radius used by k_tile_runs, read back by k_nbr_build
+  unsigned long long* counters;      // [0] hits on ghost candidates  [1] directed edges  [2] run cursor  [3] list cursor  [4] longest list  [5] tiles with too many runs for the 16-bit list codes
 };
 
 // Per-warp candidate walk: calls f(jb, je, sx, sy, sz) for every non-empty stencil cell, warp-uniformly.
 template <int DIM, typename F>
 __device__ __forceinline__ void walk_cells(const GridDev& g, const uint32_t* __restrict__ dilTab,
-                                           const uint32_t* __restrict__ cellStart, unsigned leaders, const int* ci, F&& f) {
+                                           const uint32_t* __restrict__ cellStart, unsigned leaders, const int* ci, int rad, F&& f) {
   for (unsigned lm = leaders; lm; lm &= lm - 1) {
     const int L = __ffs(lm) - 1;
     int lc[3];
     lc[0] = __shfl_sync(0xffffffffu, ci[0], L); lc[1] = __shfl_sync(0xffffffffu, ci[1], L); lc[2] = __shfl_sync(0xffffffffu, ci[2], L);
-    const int zlo = (DIM == 3) ? -1 : 0, zhi = (DIM == 3) ? 1 : 0;
+    const int zlo = (DIM == 3) ? -rad : 0, zhi = (DIM == 3) ? rad : 0;
     for (int dz = zlo; dz <= zhi; ++dz) {
       const int sz = lc[2] + dz;
       if (DIM == 3 && (sz < 0 || sz >= g.nc[2])) continue;
-      for (int dy = -1; dy <= 1; ++dy) {
+      for (int dy = -rad; dy <= rad; ++dy) {
         const int sy = lc[1] + dy;
         if (sy < 0 || sy >= g.nc[1]) continue;
         const uint32_t kyz = dilTab[SPHB200_DIL + sy] | ((DIM == 3) ? dilTab[2*SPHB200_DIL + sz] : 0u);
-        for (int dx = -1; dx <= 1; ++dx) {
+        for (int dx = -rad; dx <= rad; ++dx) {
           const int sx = lc[0] + dx;
           if (sx < 0 || sx >= g.nc[0]) continue;
           // skip cells already visited through an earlier leader's stencil
@@ -277,7 +330,7 @@ __device__ __forceinline__ void walk_cells(const GridDev& g, const uint32_t* __r
           for (unsigned pm = leaders & ((1u << L) - 1u); pm && !seen; pm &= pm - 1) {
             const int P = __ffs(pm) - 1;
             const int px = __shfl_sync(0xffffffffu, ci[0], P), py = __shfl_sync(0xffffffffu, ci[1], P), pz = __shfl_sync(0xffffffffu, ci[2], P);
-            seen = (abs(px - sx) <= 1) && (abs(py - sy) <= 1) && (DIM == 2 || abs(pz - sz) <= 1);
+            seen = (abs(px - sx) <= rad) && (abs(py - sy) <= rad) && (DIM == 2 || abs(pz - sz) <= rad);
           }
           if (seen) continue;
           const uint32_t key = dilTab[sx] | kyz;
@@ -324,6 +377,15 @@ __global__ void __launch_bounds__(128) k_tile_runs(NbrArgs a) {
   const unsigned same = __match_any_sync(0xffffffffu, active ? keyi : (0x80000000u | lane));
   const bool leader = active && ((__ffs(same & actMask) - 1) == lane);
   const unsigned leaders = __ballot_sync(0xffffffffu, leader);
+  // stencil radius of this tile: the largest reach recorded for the cells of its nodes (k_cell_reach: a node's own extent in
+  // cells AND the extents of the large nodes around it, so that gather and scatter neighbours are both inside the walk)
+  int rad = 1;
+  if (a.cellReach) {
+    uint32_t r = (active && keyi != 0xffffffffu) ? max(1u, a.cellReach[keyi]) : 1u;
+    r = __reduce_max_sync(0xffffffffu, r);
+    rad = (int)r;
+  }
+  if (lane == 0 && a.tileRadius) a.tileRadius[tile] = (uint32_t)rad;
   uint32_t R = 0;
   auto emit = [&](uint32_t jb, uint32_t je, int sx, int sy, int sz, uint32_t lo, bool toShared) {
     // a cell with more than 32 nodes becomes several runs
@@ -336,9 +398,10 @@ __global__ void __launch_bounds__(128) k_tile_runs(NbrArgs a) {
       ++R;
     }
   };
-  walk_cells<DIM>(a.g, a.dilTab, a.cellStart, leaders, ci, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) { emit(jb, je, sx, sy, sz, 0u, true); });
+  walk_cells<DIM>(a.g, a.dilTab, a.cellStart, leaders, ci, rad, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) { emit(jb, je, sx, sy, sz, 0u, true); });
   __syncwarp();
   const uint32_t Rtot = R;
+  if (Rtot >= 2048u && lane == 0) atomicAdd(&a.counters[5], 1ull);      // list codes are run << 5 | candidate in 16 bits
   unsigned long long start = 0;
   if (lane == 0) start = atomicAdd(&a.counters[2], (unsigned long long)Rtot);
   start = __shfl_sync(0xffffffffu, start, 0);
@@ -347,7 +410,7 @@ __global__ void __launch_bounds__(128) k_tile_runs(NbrArgs a) {
   for (uint32_t k = lane; k < min(Rtot, (uint32_t)RUN_CAP); k += 32) a.runs[start + k] = sruns[w][k];
   if (Rtot > RUN_CAP) {                              // rare: very ragged tile, walk again for the tail
     R = 0;
-    walk_cells<DIM>(a.g, a.dilTab, a.cellStart, leaders, ci, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) { emit(jb, je, sx, sy, sz, (uint32_t)start, false); });
+    walk_cells<DIM>(a.g, a.dilTab, a.cellStart, leaders, ci, rad, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) { emit(jb, je, sx, sy, sz, (uint32_t)start, false); });
   }
 }
 
@@ -398,7 +461,8 @@ __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build(NbrArgs a, int listRo
   if (!tile_prologue<DIM>(a, tile, lane, i, inRange, active, origi, ci)) return;
   const uint32_t R = a.tileRunCount[tile];
   const unsigned long long rs = a.tileRunStart[tile];
-  if (rs + R > a.runsCap) {                        // capacity miss: leave a consistent, empty tile; the host redoes the build
+  const int rad = a.tileRadius ? (int)a.tileRadius[tile] : 1;
+  if (rs + R > a.runsCap || R >= 2048u) {                        // capacity miss: leave a consistent, empty tile; the host redoes the build
     if (inRange) a.nbrCount[i] = 0;
     if (lane == 0) { a.tileRows[tile] = 0; a.tileOff[tile] = 0; }
     return;
@@ -435,9 +499,10 @@ __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build(NbrArgs a, int listRo
       rec = __ldg(a.runs + rs + r + 1u);
       if ((uint32_t)lane < rec.y) { const size_t c = (size_t)(rec.x + lane)*4; p0 = __ldg(frows4 + c); p1 = __ldg(frows4 + c + 1); p2 = __ldg(frows4 + c + 2); p3 = __ldg(frows4 + c + 3); }
     }
-    // A candidate outside the lane's own 3^DIM stencil is a certain miss (every cell is at least one kernel extent wide)
-    // and the error bands are derived for candidates inside it: such lanes (and ghost / padding lanes) see the run at infinity.
-    const bool near = active && abs(kx) <= 1 && abs(ky) <= 1 && abs(kz) <= 1;
+    // A candidate outside the lane's (2 rad + 1)^DIM stencil is a certain miss (rad cells cover the extent of this node and
+    // of every node that can reach it, k_cell_reach) and the error bands are derived for candidates inside it: such lanes
+    // (and ghost / padding lanes) see the run at infinity.
+    const bool near = active && abs(kx) <= rad && abs(ky) <= rad && abs(kz) <= rad;
     float bse[3];
     bse[0] = near ? fmaf((float)kx, csf[0], reli[0]) : 1.0e30f;
     bse[1] = fmaf((float)ky, csf[1], reli[1]);
@@ -547,7 +612,7 @@ template int sphb200_ensure<float>(sphb200_ctx*, float*&, size_t&, size_t);
 template int sphb200_ensure<uint4>(sphb200_ctx*, uint4*&, size_t&, size_t);
 template int sphb200_ensure<unsigned long long>(sphb200_ctx*, unsigned long long*&, size_t&, size_t);
 
-static int build_grid(sphb200_ctx* c, const double* bb /*lo3 hi3 ext3*/) {
+static int build_grid(sphb200_ctx* c, const double* bb /*lo3 hi3 ext3 sumext3*/) {
   GridDev& g = c->grid;
   const int nd = c->ndim;
   const int maxBitsTotal = 27;               // 128 Mi table entries
@@ -557,7 +622,13 @@ static int build_grid(sphb200_ctx* c, const double* bb /*lo3 hi3 ext3*/) {
   for (int a = 0; a < nd; ++a) {
     double e = bb[6 + a];
     if (!(e > 0.0) || !std::isfinite(e)) return sphb200_fail(c, "build_pairs: non-positive or non-finite kernel extent (bad H?)");
-    cs[a] = e*(1.0 + 1.0e-9);
+    // Cell width: the largest extent when the extents are similar (then the 3^DIM stencil of a node's cell holds every
+    // possible neighbour); with a heavy tail of large nodes, 1.25 x the mean extent, and the tiles near large nodes walk a
+    // wider stencil (k_cell_reach / tileRadius) -- otherwise a handful of large nodes would coarsen the grid for everyone.
+    const double emean = bb[9 + a]/(double)c->n;
+    double w = e;
+    if (!c->forceR1 && emean > 0.0 && 1.25*emean < e) w = std::max(1.25*emean, e/(double)SPHB200_MAX_STENCIL);
+    cs[a] = w*(1.0 + 1.0e-9);
   }
   // grow cells (never shrink) until the Morton table fits
   for (int iter = 0; iter < 64; ++iter) {
@@ -580,6 +651,10 @@ static int build_grid(sphb200_ctx* c, const double* bb /*lo3 hi3 ext3*/) {
     cs[amax] *= 2.0;
   }
   for (int a = 0; a < nd; ++a) { g.lo[a] = bb[a]; g.cs[a] = cs[a]; }
+  // stencil radius (in cells) that covers the largest extent
+  c->stencilR = 1;
+  for (int a = 0; a < nd; ++a) c->stencilR = std::max(c->stencilR, (int)std::ceil(bb[6 + a]/cs[a]));
+  if (c->stencilR > SPHB200_MAX_STENCIL) return sphb200_fail(c, "internal: stencil radius exceeds the supported maximum");
   // interleave: level by level, axes that still have bits
   int pos = 0;
   for (int l = 0; l < 16; ++l)
@@ -616,7 +691,7 @@ int sphb200_pack_rows(sphb200_ctx* c) {
     c->frowsCap = fcap; }
   a.frows = c->frows; a.g = c->grid;
   a.kext = std::max(c->W.kext, c->WQ.set ? c->WQ.kext : 0.0);
-  a.csmax = std::max(c->grid.cs[0], std::max(c->grid.cs[1], c->ndim == 3 ? c->grid.cs[2] : 0.0));
+  a.csmax = std::max(c->grid.cs[0], std::max(c->grid.cs[1], c->ndim == 3 ? c->grid.cs[2] : 0.0))*(3.0*c->stencilR + 4.0)/7.0;
   const unsigned nb = (unsigned)((c->n + RB - 1)/RB);
   if (c->ndim == 3) k_pack<3><<<nb, RB, 0, c->stream>>>(a); else k_pack<2><<<nb, RB, 0, c->stream>>>(a);
   KERNEL_CHECK(c, "k_pack");
@@ -630,14 +705,15 @@ int sphb200_bounds_reduce(sphb200_ctx* c, size_t count) {
   if (c->ndim == 3) k_bbox<3><<<nbb, RB, 0, c->stream>>>(c->api[S_POS], c->api[S_H], count, kext, c->reduceBuf);
   else              k_bbox<2><<<nbb, RB, 0, c->stream>>>(c->api[S_POS], c->api[S_H], count, kext, c->reduceBuf);
   KERNEL_CHECK(c, "k_bbox");
-  k_bbox_final<<<1, 32*9, 0, c->stream>>>(c->reduceBuf, nbb, c->reduceBuf + 296*9);
+  k_bbox_final<<<1, 32*12, 0, c->stream>>>(c->reduceBuf, nbb, c->reduceBuf + 296*12);
   KERNEL_CHECK(c, "k_bbox_final");
-  CU_CHECK(c, cudaMemcpyAsync(c->reduceHost, c->reduceBuf + 296*9, 9*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU_CHECK(c, cudaMemcpyAsync(c->reduceHost, c->reduceBuf + 296*12, 12*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   return 0;
 }
 
 int sphb200_sort_and_pack(sphb200_ctx* c) {
   const size_t n = c->n;
+  if (c->forceR1 && c->coarseHold > 0 && --c->coarseHold == 0) c->forceR1 = false;    // re-examine the fine grid now and then
   if (!c->have[S_POS] || !c->have[S_H]) return sphb200_fail(c, "build_pairs: position and H must be uploaded first");
   if (!c->W.set) return sphb200_fail(c, "build_pairs: kernel table not set (need the kernel extent)");
   const double kext = std::max(c->W.kext, c->WQ.set ? c->WQ.kext : 0.0);
@@ -669,6 +745,30 @@ int sphb200_sort_and_pack(sphb200_ctx* c) {
   k_cell_order<<<(c->grid.tableSize + RB - 1)/RB, RB, 0, c->stream>>>(c->cellStart, c->grid.tableSize, c->perm);
   KERNEL_CHECK(c, "k_cell_order");
   c->sortValid = true;
+  if (c->stencilR > 1) {
+    if (sphb200_ensure(c, c->cellReach, c->cellReachCap, tbl)) return 1;
+    CU_CHECK(c, cudaMemsetAsync(c->cellReach, 0, tbl*sizeof(uint32_t), c->stream));
+    if (c->ndim == 3) k_cell_reach<3><<<nb, RB, 0, c->stream>>>(c->api[S_POS], c->api[S_H], n, kext, c->grid, c->dilTab, c->stencilR, c->cellReach);
+    else              k_cell_reach<2><<<nb, RB, 0, c->stream>>>(c->api[S_POS], c->api[S_H], n, kext, c->grid, c->dilTab, c->stencilR, c->cellReach);
+    KERNEL_CHECK(c, "k_cell_reach");
+    // Is the fine grid worth it?  Candidate volume per node ~ (2 r + 1)^DIM cells of the fine width against 3^DIM cells of the
+    // largest extent.  Large nodes that are rare but spread evenly put every tile within reach of one of them, and the fine
+    // grid then costs more than the coarse one: measured on the reach map itself (one extra host round trip, only on builds
+    // with a heavy tail of extents), and remembered for the next builds.
+    CU_CHECK(c, cudaMemsetAsync(c->counters + 10, 0, sizeof(unsigned long long), c->stream));
+    if (c->ndim == 3) k_reach_cost<3><<<nb, RB, 0, c->stream>>>(c->cellKeyApi, n, c->cellReach, c->counters + 10);
+    else              k_reach_cost<2><<<nb, RB, 0, c->stream>>>(c->cellKeyApi, n, c->cellReach, c->counters + 10);
+    KERNEL_CHECK(c, "k_reach_cost");
+    unsigned long long sumCells = 0;
+    CU_CHECK(c, cudaMemcpyAsync(&sumCells, c->counters + 10, sizeof(sumCells), cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    double volFine = 1.0, volCoarse = 1.0;
+    for (int a = 0; a < c->ndim; ++a) { volFine *= c->grid.cs[a]; volCoarse *= 3.0*c->reduceHost[6 + a]; }
+    if ((double)sumCells*volFine > 0.8*(double)n*volCoarse) {
+      c->forceR1 = true; c->coarseHold = 32;             // wide cells for the next 32 builds, then look again
+      return sphb200_sort_and_pack(c);
+    }
+  }
   return sphb200_pack_rows(c);
 }
 
@@ -688,6 +788,8 @@ int sphb200_neighbors(sphb200_ctx* c) {
     a.nbrCount = c->nbrCount; a.tileRows = c->tileRows; a.tileOff = c->tileOff; a.nbr = c->nbr; a.nbrCap = c->nbrCap;
     a.runs = c->runs; a.runsCap = c->runsCap; a.tileRunStart = c->tileRunStart; a.tileRunCount = c->tileRunCount;
     a.counters = c->counters;
+    a.cellReach = (c->stencilR > 1) ? c->cellReach : nullptr;
+    if (c->stencilR > 1) { if (sphb200_ensure(c, c->tileRadius, c->tileRadiusCap, c->nTiles + 1)) return 1; a.tileRadius = c->tileRadius; }
     CU_CHECK(c, cudaMemsetAsync(c->counters, 0, 8*sizeof(unsigned long long), c->stream));
     // 1. candidate runs per tile
     if (c->ndim == 3) k_tile_runs<3><<<nb, 128, 0, c->stream>>>(a); else k_tile_runs<2><<<nb, 128, 0, c->stream>>>(a);
@@ -709,6 +811,7 @@ int sphb200_neighbors(sphb200_ctx* c) {
     CU_CHECK(c, cudaMemcpyAsync(c->countersHost, c->counters, 9*sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
     const size_t needRuns = (size_t)c->countersHost[2], needNbr = (size_t)c->countersHost[3], needRows = (size_t)c->countersHost[4];
+    if (c->countersHost[5] != 0ull) return 2;       // a tile has too many candidate runs for the list codes: the caller rebuilds with wide cells
     const bool okRuns = needRuns <= c->runsCap;
     const bool okRows = needRows <= (size_t)c->listRows;
     const bool okNbr = okRuns && needNbr <= c->nbrCap;               // the list size is only known once the test ran everywhere

@@ -21,6 +21,7 @@
 
 #define SPHB200_TILE 32
 #define SPHB200_MAX_PLANES 6
+#define SPHB200_MAX_STENCIL 4      /* largest stencil radius in cells (9^3 cells; run codes of k_nbr_build hold 2048 runs per tile) */
 #define SPHB200_DIL 32768          /* entries per axis of the dilated-coordinate table (max cells per axis) */
 
 enum StateSlot { S_POS = 0, S_VEL, S_H, S_MASS, S_RHO, S_EPS, S_P, S_CS, S_OMEGA, S_DVDXQ, S_FCL, S_FCQ, S_VOLUME, S_RKCORR, S_COUNT };
@@ -108,6 +109,11 @@ struct sphb200_ctx {
   double* crkCorrS = nullptr;       // CRKSPH: (1+ndim)^2 RK coefficients per node (sorted, AoS)
   double* crkQS = nullptr;          // CRKSPH: {volume, Q velocity gradient} per node (sorted, stride 10 / 6)
   double* crkAux = nullptr;         // CRKSPH: {det H, volume} per node (sorted)
+  int stencilR = 1;                 // stencil radius (cells) covering the largest kernel extent; 1 unless the extents have a heavy tail
+  int coarseHold = 0;               // builds left before the fine grid is tried again (0 with forceR1: never, run-code overflow)
+  bool forceR1 = false;             // fall back to cells as wide as the largest extent (set when a tile overflows its run codes)
+  uint32_t* cellReach = nullptr; size_t cellReachCap = 0;   // per cell: stencil radius tiles of that cell must walk
+  uint32_t* tileRadius = nullptr; size_t tileRadiusCap = 0;
   bool allIsotropic = false;        // every H packed at the last build_pairs was a multiple of the identity (k_pack; read back with the counters)
   bool rowsValid = false;           // rows reflect current api state for the current sort
   bool sortValid = false;

@@ -263,3 +263,44 @@ def test_coincident_nodes_derivatives(oracle, eng_mod, ndim, n, nPerh, kind, kw)
     assert_parity(r, st, nInt, ndim)
     for k in ("DvDt", "DepsDt", "DvDx"):
         assert np.all(np.isfinite(r["got"][k]))
+
+
+@pytest.mark.parametrize("ndim,N,frac,scale", [(3, 6000, 0.01, 1.8), (3, 4000, 0.2, 1.7), (2, 5000, 0.02, 3.7), (3, 3000, 0.5, 1.6), (3, 8000, 0.0, 1.9)])
+def test_heavy_tailed_smoothing_scales(oracle, eng_mod, ndim, N, frac, scale):
+    """A few nodes with much larger kernel extents than the rest: the grid follows the typical extent and the tiles near the
+    large nodes walk a wider stencil (k_cell_reach).  Pair set bit-exact against brute force -- gather AND scatter neighbours --
+    and derivatives within tolerance."""
+    rng = np.random.default_rng(101)
+    nPerh = 1.51 if ndim == 3 else 2.01
+    pos, H = ng.random_anisotropic(ndim, N, [[0, 1]]*ndim, nPerh=nPerh, seed=77)
+    big = rng.uniform(size=N) < frac
+    if frac == 0.0:
+        big = pos[:, 0] > 0.93                        # a clustered population (a free surface whose h has grown): the fine grid pays
+    H[big] /= scale                                   # extents 'scale' times larger
+    assert big.sum() > 3
+    e = eng_mod.Engine(ndim, nPerh=nPerh)
+    WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    e.set_kernel_table(WT)
+    e.set_nodes(N, 0)
+    st = dict(position=pos, velocity=common.smooth_velocity(pos), H=H, mass=np.full(N, 1.0/N), massDensity=np.ones(N),
+              specificThermalEnergy=np.ones(N), pressure=np.full(N, 2.0/3.0), soundSpeed=np.full(N, 1.05), omegaGradh=np.ones(N))
+    st = {k: np.ascontiguousarray(v) for k, v in st.items()}
+    e.upload_state(**st)
+    npairs = e.build_pairs()
+    radius = e.stats()["stencil_radius"]
+    print("heavy tail frac=%g scale=%g: stencil radius %d" % (frac, scale, radius))
+    if ndim == 2 and frac == 0.02:
+        assert radius > 1                             # rare, much larger nodes: the fine grid with wide stencils is chosen
+    if frac == 0.5:
+        assert radius == 1                            # half the nodes large: cells as wide as the largest extent
+    gi, gj = e.download_pairs()
+    pi, pj, cnt = oracle.pairs(ndim, N, 0, pos, H, 2.0, "brute")
+    assert npairs == len(pi) and np.array_equal(gi, pi) and np.array_equal(gj, pj)
+    assert np.array_equal(e.download_neighbor_counts(), cnt)
+    e.evaluate_derivatives()
+    got = e.download_derivs("DvDt", "DrhoDt", "DvDx", "DepsDt")
+    oo = oracle.default_options(ndim, nPerh=nPerh)
+    ref = oracle.evaluate_derivatives(oo, common.oracle_table(oracle, WT), common.to_oracle_state(st), N, 0, pi, pj, cnt)
+    floors = common.physical_floors(st, N, ndim)
+    for k in got:
+        assert common.field_err(got[k], ref[k], N, floors[k]) <= 1e-10, k
