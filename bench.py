@@ -211,6 +211,7 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="override lattice points per side (debug)")
     ap.add_argument("--cpu-sample", type=int, default=48, help="lattice points per side of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="A/B diagnostic: skip the device-resident RK2 leg (scripts/gpu_ab.sh)")
     ap.add_argument("--hjitter", type=float, default=0.0,
                     help="scale every node's H by a random factor in [1-x, 1+x] (diagnostic: the lattice workloads have a constant h)")
     args = ap.parse_args()
@@ -354,7 +355,7 @@ def main():
     # device-resident CheapSynchronousRK2 steps: neighbour update + sum density + dt vote + trial advance +
     # grad-h correction + derivatives + compatible-energy update + full advance, no field leaving the GPU
     rk2 = None
-    if dsph is None:
+    if dsph is None and not args.quick:
         from spheral_b200 import integrator as I
         rk = I.CheapSynchronousRK2(e, engine.make_step_options())
         rk.initializeDerivatives()

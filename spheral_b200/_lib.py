@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsphb200.so")
+# SPHB200_LIB: A/B measurements of tuning variants of the same library (scripts/build_variants.py); never a fallback
+LIB_PATH = os.environ.get("SPHB200_LIB") or os.path.join(HERE, "libsphb200.so")
 
 _dp = C.POINTER(C.c_double)
 _u32p = C.POINTER(C.c_uint32)

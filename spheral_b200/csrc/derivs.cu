@@ -100,8 +100,8 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
   // stage the interleaved W/gradW table(s) in shared memory
   // n1+1 interval records of 6 coefficients plus one all-zero record (eta >= kext)
   const uint32_t nW = 6u*(a.n1W + 2u), nQ = (GEN && !a.oneKernel) ? 6u*(a.n1Q + 2u) : 0u;
-  for (uint32_t k = threadIdx.x; k < nW; k += blockDim.x) smem[k] = (k < nW - 6u) ? a.tabW[k] : 0.0;
-  for (uint32_t k = threadIdx.x; k < nQ; k += blockDim.x) smem[nW + k] = (k < nQ - 6u) ? a.tabQ[k] : 0.0;
+  for (uint32_t k = threadIdx.x; k < nW; k += blockDim.x) smem[k] = (k + 6u < nW) ? a.tabW[k] : 0.0;
+  for (uint32_t k = threadIdx.x; k < nQ; k += blockDim.x) smem[nW + k] = (k + 6u < nQ) ? a.tabQ[k] : 0.0;
   __syncthreads();
   const unsigned tW = (unsigned)__cvta_generic_to_shared(smem);
   const unsigned tQ = tW + 8u*nW;
@@ -237,9 +237,9 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
       const unsigned st = warpRing + (k % PAIR_STAGES)*(unsigned)STAGEB;
       const unsigned rp = st + (unsigned)lane*ROWB;
 #pragma unroll
-      for (int q = 0; q < ROW/2; ++q) { const double2 v = lds128(rp + 16u*q); rw[2*q] = v.x; rw[2*q + 1] = v.y; }
+      for (int q = 0; q < ROW/2; ++q) { const double2 v = lds128v(rp + 16u*q); rw[2*q] = v.x; rw[2*q + 1] = v.y; }
 #if SPHB200_PAIR_AUX
-      aux = lds128(st + 32u*ROWB + 16u*lane);
+      aux = lds128v(st + 32u*ROWB + 16u*lane);
 #else
       if constexpr (ISO) { const double hj = rw[D::R_H]; aux.x = (DIM == 3) ? hj*hj*hj : hj*hj; }
       else aux.x = sym_det<DIM>(rw + D::R_H);

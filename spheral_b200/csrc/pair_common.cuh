@@ -38,6 +38,16 @@ __device__ __forceinline__ double2 lds128(unsigned addr) {      // 32-bit shared
   return v;
 }
 
+// Reads of shared memory that cp.async fills (the neighbour-row ring of k_sph_derivs): volatile, so that the compiler keeps them
+// behind the cp.async.wait_group / __syncwarp that publish the data.  The plain lds128 above is a pure function of its address to
+// the compiler and may be hoisted out of a loop -- fine for the read-only table, wrong for a ring slot (seen when a look-ahead
+// read of the next slot was tried: it was moved above the copies that fill it).
+__device__ __forceinline__ double2 lds128v(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+
 // TableKernelView::kernelAndGradValue (Kernel/TableKernelViewInline.hh:84-99) with
 // QuadraticInterpolatorView::lowerBound (Utilities/QuadraticInterpolatorViewInline.hh:71-77), WITHOUT the Hdet factor
 // (the caller multiplies; the raw gradient value is also kernelValueSPH of TableKernelViewInline.hh:118-127).
