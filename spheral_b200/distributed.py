@@ -149,17 +149,28 @@ class DistributedSPH:
         self.bytesB = engine.halo_bytes_per_node(self.maskB)
         self._cap = 0
         self.nInternal = engine.nInternal
+        # ghosts of the boundaries that come before the slab halo in the boundary list (reflecting / periodic planes generated on
+        # the device by sphb200_reflect_set_ghost_nodes): they sit right after the internal nodes, take part in the send-node
+        # selection like internal nodes (DistributedBoundary exchanges the ghosts of the other boundaries too, so that a node near
+        # a slab face AND a plane sees the mirror images owned by the neighbouring slab) and the halo lands after them
+        self.nBoundaryGhost = 0
         self.nFromLower = self.nFromUpper = 0
         self.width = 0.0
         self.last = {}
 
-    def _ensure(self, cap):
+    def _ensure(self, cap, keep_lists=False):
+        """Capacity (in nodes) of the send lists and of the four staging buffers.  keep_lists: the send lists have just been
+        selected and must survive the growth (the receive side of a slab may need more room than its own send side)."""
         if cap <= self._cap:
             return
         cap = int(cap*1.25) + 1024
         dev = self.dev
+        old = (self.idxLow, self.idxHigh) if (keep_lists and self._cap) else None
         self.idxLow = torch.empty(cap, dtype=torch.int32, device=dev)
         self.idxHigh = torch.empty(cap, dtype=torch.int32, device=dev)
+        if old is not None:
+            self.idxLow[:old[0].numel()].copy_(old[0])
+            self.idxHigh[:old[1].numel()].copy_(old[1])
         mk = lambda nbytes: torch.empty(cap*nbytes//8, dtype=torch.float64, device=dev)
         self.sLowA, self.sHighA, self.rLowA, self.rHighA = mk(self.bytesA), mk(self.bytesA), mk(self.bytesA), mk(self.bytesA)
         nb = self.bytesA + self.bytesB            # the single-batch exchange stages every field in the B buffers
@@ -169,8 +180,9 @@ class DistributedSPH:
     def refresh_ghosts_and_build(self):
         return self.refresh_ghosts(build=True)
 
-    def refresh_ghosts(self, build=True):
+    def refresh_ghosts(self, build=True, boundary_ghosts=0):
         """Ghost selection + exchange (+ neighbour build).  Returns the number of node pairs of this slab (None without the build).
+        `boundary_ghosts`: number of plane ghosts already generated behind the internal nodes (see nBoundaryGhost).
 
         Default path: ONE host round trip before the neighbour build.  The bounds reduction, the all-reduce(MAX) of the
         halo width, the send-node selection and the all-gather of the counts are chained on the device
@@ -183,37 +195,44 @@ class DistributedSPH:
         nInt = self.nInternal
         if nInt == 0:
             raise RuntimeError("DistributedSPH: a slab without internal nodes is not supported")
+        nBG = self.nBoundaryGhost = int(boundary_ghosts)
+        nOwn = nInt + nBG                                  # nodes this slab can send: internal + its own plane ghosts
         with torch.cuda.stream(self.stream):
             if self._cap == 0:
                 self._ensure(max(1024, nInt//8))
                 self._bounds = torch.zeros(9, dtype=torch.float64, device=self.dev)
-                self._counts = torch.zeros(2, dtype=torch.int64, device=self.dev)
-                self._allc = torch.zeros(2*h.world, dtype=torch.int64, device=self.dev)
+                self._counts = torch.zeros(3, dtype=torch.int64, device=self.dev)      # {nLow, nHigh, capacity of the send lists}
+                self._allc = torch.zeros(3*h.world, dtype=torch.int64, device=self.dev)
             while True:
                 # halo width: largest kernel extent along the axis over all ranks (gather AND scatter neighbours are covered)
-                e.node_bounds_device(nInt, self._bounds.data_ptr())
+                e.node_bounds_device(nOwn, self._bounds.data_ptr())
                 ext = self._bounds[6:9]
                 h.allreduce_max(ext)
                 e.halo_select_device(self.axis, self.lo, self.hi, ext.data_ptr(), self.idxLow.data_ptr(), self.idxHigh.data_ptr(),
-                                     self._counts.data_ptr(), self._cap, nInt)
+                                     self._counts.data_ptr(), self._cap, nOwn)
+                self._counts[2] = self._cap
                 if h.world > 1:
                     dist.all_gather_into_tensor(self._allc, self._counts, group=h.group)
                 else:
                     self._allc.copy_(self._counts)
-                allc = self._allc.cpu().numpy().reshape(h.world, 2)          # the one host round trip
+                allc = self._allc.cpu().numpy().reshape(h.world, 3)          # the one host round trip
                 nLow, nHigh = int(allc[h.rank, 0]), int(allc[h.rank, 1])
-                if max(nLow, nHigh) <= self._cap:
+                # Redo the selection if ANY rank truncated a send list it will use.  The decision is taken from the gathered table,
+                # identically on every rank: a rank-local test would let one slab repeat the all-gather while its neighbour moves
+                # on to the send/recv (a deadlock; seen when plane ghosts made the counts of the end slabs asymmetric).
+                need = [max(int(allc[r, 0]) if r > 0 else 0, int(allc[r, 1]) if r < h.world - 1 else 0) for r in range(h.world)]
+                if all(need[r] <= int(allc[r, 2]) for r in range(h.world)):
                     break
-                self._ensure(max(nLow, nHigh))                                # send lists were truncated: grow and redo
+                self._ensure(max(need))                                       # send lists were truncated: grow and redo
             if h.lower is None:
                 nLow = 0
             if h.upper is None:
                 nHigh = 0
             nFL = int(allc[h.lower, 1]) if h.lower is not None else 0         # the lower slab's "high" list is ours
             nFU = int(allc[h.upper, 0]) if h.upper is not None else 0
-            self._ensure(max(nLow, nHigh, nFL, nFU))
+            self._ensure(max(nLow, nHigh, nFL, nFU), keep_lists=True)
             self.nFromLower, self.nFromUpper = nFL, nFU
-            e.set_nodes(nInt, nFL + nFU)
+            e.set_nodes(nInt, nBG + nFL + nFU)
             wA, wB = self.bytesA//8, self.bytesB//8
             if not self.two_phase or not build:
                 wAB = wA + wB
@@ -222,8 +241,8 @@ class DistributedSPH:
                 e.halo_pack(mask, self.idxHigh.data_ptr(), nHigh, self.sHighB.data_ptr())
                 works = h.start(self.sLowB[:nLow*wAB], self.sHighB[:nHigh*wAB], self.rLowB[:nFL*wAB], self.rHighB[:nFU*wAB])
                 h.finish(works)
-                e.halo_unpack(mask, nInt, nFL, self.rLowB.data_ptr())
-                e.halo_unpack(mask, nInt + nFL, nFU, self.rHighB.data_ptr())
+                e.halo_unpack(mask, nOwn, nFL, self.rLowB.data_ptr())
+                e.halo_unpack(mask, nOwn + nFL, nFU, self.rHighB.data_ptr())
                 npairs = e.build_pairs() if build else None
             else:
                 # pack both phases, then post A and B; K1+K2 only wait for A
@@ -234,13 +253,13 @@ class DistributedSPH:
                 worksA = h.start(self.sLowA[:nLow*wA], self.sHighA[:nHigh*wA], self.rLowA[:nFL*wA], self.rHighA[:nFU*wA])
                 worksB = h.start(self.sLowB[:nLow*wB], self.sHighB[:nHigh*wB], self.rLowB[:nFL*wB], self.rHighB[:nFU*wB])
                 h.finish(worksA)
-                e.halo_unpack(self.maskA, nInt, nFL, self.rLowA.data_ptr())
-                e.halo_unpack(self.maskA, nInt + nFL, nFU, self.rHighA.data_ptr())
+                e.halo_unpack(self.maskA, nOwn, nFL, self.rLowA.data_ptr())
+                e.halo_unpack(self.maskA, nOwn + nFL, nFU, self.rHighA.data_ptr())
                 npairs = e.build_pairs()                      # phase B is in flight on the NCCL stream meanwhile
                 h.finish(worksB)
-                e.halo_unpack(self.maskB, nInt, nFL, self.rLowB.data_ptr())
-                e.halo_unpack(self.maskB, nInt + nFL, nFU, self.rHighB.data_ptr())
-        self.last = dict(nSendLow=nLow, nSendHigh=nHigh, nFromLower=nFL, nFromUpper=nFU,
+                e.halo_unpack(self.maskB, nOwn, nFL, self.rLowB.data_ptr())
+                e.halo_unpack(self.maskB, nOwn + nFL, nFU, self.rHighB.data_ptr())
+        self.last = dict(nSendLow=nLow, nSendHigh=nHigh, nFromLower=nFL, nFromUpper=nFU, nBoundaryGhost=nBG,
                          h2h_bytes=(nLow + nHigh)*(self.bytesA + self.bytesB), two_phase=bool(self.two_phase))
         return npairs
 
@@ -249,7 +268,7 @@ class DistributedSPH:
         again and land in the same ghost slots; the connectivity is kept (DistributedBoundary::applyGhostBoundary,
         Distributed/DistributedBoundary.cc:210-330)."""
         e, h = self.e, self.halo
-        nInt, L_ = self.nInternal, self.last
+        nInt, L_ = self.nInternal + self.nBoundaryGhost, self.last
         nLow, nHigh, nFL, nFU = L_["nSendLow"], L_["nSendHigh"], L_["nFromLower"], L_["nFromUpper"]
         mask = (self.maskA | self.maskB) if names is None else field_mask(names)
         w = e.halo_bytes_per_node(mask)//8
@@ -264,7 +283,7 @@ class DistributedSPH:
         """SPHBase::finalizeDerivatives (SPHBase.cc:502-519) across the slab faces: the ghost entries of DvDt and DepsDt become
         their owners' values; SpecificThermalEnergyPolicy reads them for the ghost end of an internal-ghost pair."""
         e, h = self.e, self.halo
-        nInt, L_ = self.nInternal, self.last
+        nInt, L_ = self.nInternal + self.nBoundaryGhost, self.last
         nLow, nHigh, nFL, nFU = L_["nSendLow"], L_["nSendHigh"], L_["nFromLower"], L_["nFromUpper"]
         w = e.ndim + 1
         with torch.cuda.stream(self.stream):

@@ -38,9 +38,10 @@ class CheapSynchronousRK2:
         elif reflectingPlanes:
             engine.reflect_configure(reflectingPlanes)
         # domain decomposition (spheral_b200.distributed.DistributedSPH): ghost exchange with the neighbouring slabs over NCCL
+        # With planes AND slabs the ghost tail is [plane ghosts | halo]: the planes come first in the boundary list, the distributed
+        # boundary last, and it exchanges the plane ghosts near a slab face as well (Integrator.cc:389-445, SpheralController.py:
+        # the DistributedBoundary is appended after the problem's own boundaries).
         self.distributed = distributed
-        if distributed is not None and reflectingPlanes:
-            raise ValueError("reflecting planes and the slab halo both own the ghost tail; combining them is not supported yet")
         self.currentTime, self.currentCycle, self.lastDt = 0.0, 0, 1.0e100
         self.dtMultiplier = 1.0
         self.lastDtReason, self.lastDtNode = "", 0
@@ -72,10 +73,9 @@ class CheapSynchronousRK2:
 
     def _set_ghost_nodes(self):
         """Integrator::setGhostNodes (Integrator.cc:372-445): regenerate the ghost nodes, then refresh their values."""
-        if self.reflectingPlanes:
-            self.engine.reflect_set_ghost_nodes()
+        nPlaneGhosts = self.engine.reflect_set_ghost_nodes() if self.reflectingPlanes else 0
         if self.distributed is not None:
-            self.distributed.refresh_ghosts(build=False)
+            self.distributed.refresh_ghosts(build=False, boundary_ghosts=nPlaneGhosts)
         if self.ghostRefresh is not None:
             self.ghostRefresh()
 

@@ -20,6 +20,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("MGPU_HANG_DUMP", "150")), exit=True)    # a deadlock prints its stack and ends
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -85,19 +87,23 @@ def rk2_mode(rank, world, e, d, G, mine, N, oo, WT, orc, common, engine):
     from spheral_b200 import integrator
     nsteps = int(os.environ.get("MGPU_STEPS", "3"))
     so = orc.default_step_options()
-    rk = integrator.CheapSynchronousRK2(e, engine.make_step_options(), densityUpdate=1, distributed=d)
+    # MGPU_PLANES=1: reflecting planes x = 0, y = 0, z = 0 on top of the slabs (the ghost tail of a rank is then
+    # [its plane ghosts | halo], and the halo carries the neighbours' plane ghosts near the shared face)
+    planes = [(np.zeros(3), np.eye(3)[a]) for a in range(3)] if os.environ.get("MGPU_PLANES", "0") == "1" else None
+    rk = integrator.CheapSynchronousRK2(e, engine.make_step_options(), densityUpdate=1, distributed=d, reflectingPlanes=planes)
     rk.initializeDerivatives()
     for _ in range(nsteps):
         assert rk.step()
     got = e.download_state("position", "velocity", "H", "massDensity", "specificThermalEnergy", "omegaGradh")
     e.sync()
     G2 = dict(G); G2["velocity"] = G["velocity"]
-    ref = common.OracleRK2(orc, oo, so, common.oracle_table(orc, WT), G2, densityUpdate=1)
+    ref = common.OracleRK2(orc, oo, so, common.oracle_table(orc, WT), G2, densityUpdate=1, planes=planes)
     ref.initializeDerivatives()
     for _ in range(nsteps):
         ref.step()
     names = dict(position="pos", velocity="vel", H="H", massDensity="rho", specificThermalEnergy="eps", omegaGradh="omega")
-    worst = {k: float(np.abs(got[k][:N] - ref.s[o][mine]).max()/max(np.abs(ref.s[o][mine]).max(), 1e-300)) for k, o in names.items()}
+    refInt = {o: ref.s[o][:world*N] for o in names.values()}           # the oracle state carries its plane ghosts behind the internal nodes
+    worst = {k: float(np.abs(got[k][:N] - refInt[o][mine]).max()/max(np.abs(refInt[o][mine]).max(), 1e-300)) for k, o in names.items()}
     w = max(worst.values())
     dt_err = abs(rk.lastDt - ref.lastDt)/ref.lastDt
     # global energy on the device results
@@ -107,7 +113,8 @@ def rk2_mode(rank, world, e, d, G, mine, N, oo, WT, orc, common, engine):
     t = torch.tensor([Eloc, E0loc], dtype=torch.float64, device="cuda")
     dist.all_reduce(t)
     dE = float((t[0] - t[1])/t[1])
-    print(json.dumps(dict(rank=rank, world=world, mode="rk2", steps=nsteps, ghosts=e.nGhost, worst_state_error=w, worst=worst,
+    print(json.dumps(dict(rank=rank, world=world, mode="rk2", planes=bool(planes), steps=nsteps, ghosts=e.nGhost, halo=d.last,
+                          oracle_plane_ghosts=ref.nGhost, worst_state_error=w, worst=worst,
                           dt_rel_err=dt_err, dE_over_E=dE, time=rk.currentTime)), flush=True)
     ok = (w <= 1.0e-9) and (dt_err <= 1.0e-10) and (abs(dE) <= 1.0e-12)
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")

@@ -39,7 +39,7 @@ def _global_problem(ndim, n, nPerh, aniso):
     return st, nInt
 
 
-def _worker(rank, world, port, ndim, n, nPerh, aniso):
+def _worker(rank, world, port, ndim, n, nPerh, aniso, planes=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -66,12 +66,31 @@ def _worker(rank, world, port, ndim, n, nPerh, aniso):
             mine = np.nonzero((x >= lo) & (x < hi))[0]
         local = {k: np.ascontiguousarray(v[mine]) for k, v in st.items()}
         nInt = len(mine)
+        nBG = 0
+        if planes:
+            # reflecting planes through the origin on every axis, generated per slab BEFORE the halo (boundary order of the
+            # reference: the problem's boundaries first, the DistributedBoundary last); the plane ghosts then take part in the
+            # send-node selection like internal nodes (DistributedSPH.refresh_ghosts(boundary_ghosts=...))
+            from spheral_b200 import nodegen as ng
+            PN = dict(position="pos", velocity="vel", H="H", mass="mass", massDensity="rho", specificThermalEnergy="eps", pressure="P",
+                      soundSpeed="cs", omegaGradh="omega")
+            plist = [(np.zeros(ndim), np.eye(ndim)[a]) for a in range(ndim)]
+            out, _, _ = ng.reflect_ghosts(ndim, {o: local[k] for k, o in PN.items()}, plist, kext, per_plane=True)
+            local = {k: np.ascontiguousarray(out[o]) for k, o in PN.items()}
+            nBG = local["position"].shape[0] - nInt
+            assert nBG > 0
+            gout, _, _ = ng.reflect_ghosts(ndim, {o: st[k] for k, o in PN.items()}, plist, kext, per_plane=True)
+            stg = {k: np.ascontiguousarray(gout[o]) for k, o in PN.items()}
+            NG = stg["position"].shape[0] - N
+        else:
+            stg, NG = st, 0
 
         halo = D.SlabHalo()
         assert (halo.lower, halo.upper) == ((None, 1) if rank == 0 else (0, None))
         ext = D.kernel_extent_axis(local["H"], ndim, kext, axis).max()
+        nOwn = nInt + nBG
         width = float(halo.allreduce_max(torch.tensor([ext], dtype=torch.float64)).item())*(1.0 + 1e-9)
-        idxLow, idxHigh = D.select_halo_numpy(local["position"], nInt, axis, lo, hi, width)
+        idxLow, idxHigh = D.select_halo_numpy(local["position"], nOwn, axis, lo, hi, width)
         if halo.lower is None:
             idxLow = idxLow[:0]
         if halo.upper is None:
@@ -88,16 +107,16 @@ def _worker(rank, world, port, ndim, n, nPerh, aniso):
             for k in names:
                 ghosts[k] = np.concatenate([gl[k], gh[k]])
         full = {k: np.ascontiguousarray(np.concatenate([local[k], ghosts[k]])) for k in local}
-        nGhost = nFL + nFU
-        assert nGhost > 0
+        nGhost = nBG + nFL + nFU
+        assert nFL + nFU > 0
 
         # oracle on the slab (internal + ghosts) versus oracle on the whole problem
         s = common.to_oracle_state(full)
         pi, pj, cnt = orc.pairs(ndim, nInt, nGhost, s["pos"], s["H"], kext)
         got = orc.evaluate_derivatives(oo, OT, s, nInt, nGhost, pi, pj, cnt)
-        sg = common.to_oracle_state(st)
-        gpi, gpj, gcnt = orc.pairs(ndim, N, 0, sg["pos"], sg["H"], kext)
-        ref = orc.evaluate_derivatives(oo, OT, sg, N, 0, gpi, gpj, gcnt)
+        sg = common.to_oracle_state(stg)
+        gpi, gpj, gcnt = orc.pairs(ndim, N, NG, sg["pos"], sg["H"], kext)
+        ref = orc.evaluate_derivatives(oo, OT, sg, N, NG, gpi, gpj, gcnt)
         assert np.array_equal(cnt, gcnt[mine]), "a slab node lost or gained neighbours: the halo is not a superset"
         floors = common.physical_floors(st, N, ndim)
         for k, f in floors.items():
@@ -108,10 +127,14 @@ def _worker(rank, world, port, ndim, n, nPerh, aniso):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("ndim,n,nPerh,aniso", [(3, 10, 1.51, False), (2, 24, 2.01, True)])
-def test_two_slab_halo_exchange_reproduces_global_derivatives(ndim, n, nPerh, aniso):
+@pytest.mark.parametrize("ndim,n,nPerh,aniso,planes", [(3, 10, 1.51, False, False), (2, 24, 2.01, True, False),
+                                                       (3, 10, 1.51, False, True), (2, 24, 2.01, True, True)])
+def test_two_slab_halo_exchange_reproduces_global_derivatives(ndim, n, nPerh, aniso, planes):
+    """planes=True: reflecting planes on top of the slabs -- the ghost tail of a slab is [its plane ghosts | halo] and the halo
+    carries the neighbour's plane ghosts near the shared face; the derivatives of the internal nodes must still equal those of the
+    undecomposed problem with the same planes."""
     from oracle import oracle as orc
     orc.build()
     from spheral_b200 import build as b
     b.build()
-    mp.spawn(_worker, args=(2, _free_port(), ndim, n, nPerh, aniso), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), ndim, n, nPerh, aniso, planes), nprocs=2, join=True)
