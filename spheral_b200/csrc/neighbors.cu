@@ -441,6 +441,19 @@ template <int DIM> __device__ __forceinline__ float eta2_f32(const float* H, con
 }
 
 constexpr int CROW = 20;             // floats per candidate row in shared memory (16 + 4 pad: conflict-free 128-bit stores)
+constexpr int S1F = 5*32;            // floats of the stage-1 SoA copy of a run: x[32] y[32] z[32] r2lo[32] r2hi[32]
+
+// Packed FP32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 work on two floats held in a 64-bit register).  Stage 1 of the neighbour
+// test is issue-bound (profiles/r01_notes.md); with the candidates of a run stored as SoA, one instruction advances two
+// candidates.  Same operations and rounding as the scalar expressions (rn, no ftz): results are bit-identical.
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) { unsigned long long r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) { unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+#ifndef SPHB200_NBR_PACKED
+#define SPHB200_NBR_PACKED 1
+#endif
 constexpr int NB_WARPS = 4;          // warps (tiles) per CTA of k_nbr_build
 constexpr int JB_CAP = 128;          // runs per tile whose first slot is cached in shared memory for the flush
 
@@ -452,9 +465,10 @@ template <int DIM>
 __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build(NbrArgs a, int listRows) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int w = threadIdx.x >> 5;
-  const size_t perWarp = (size_t)32*CROW*4 + (size_t)JB_CAP*4 + (size_t)listRows*64;
+  const size_t perWarp = (size_t)32*CROW*4 + (size_t)S1F*4 + (size_t)JB_CAP*4 + (size_t)listRows*64;
   float* const sc = reinterpret_cast<float*>(smemRaw + w*perWarp);
-  uint32_t* const sjb = reinterpret_cast<uint32_t*>(sc + 32*CROW);
+  float* const s1 = sc + 32*CROW;                   // stage-1 SoA copy of the current run
+  uint32_t* const sjb = reinterpret_cast<uint32_t*>(s1 + S1F);
   unsigned short* const slist = reinterpret_cast<unsigned short*>(sjb + JB_CAP);
 
   size_t tile, i; int lane, ci[3]; bool inRange, active; uint32_t origi;
@@ -490,6 +504,9 @@ __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build(NbrArgs a, int listRo
     const int kx = ci[0] - (int)(rec.z & 0xffffu), ky = ci[1] - (int)(rec.z >> 16), kz = (DIM == 3) ? ci[2] - (int)rec.w : 0;
     __syncwarp();                                                   // every lane is done with the previous run's rows
     { float4* d = reinterpret_cast<float4*>(sc + lane*CROW); d[0] = p0; d[1] = p1; d[2] = p2; d[3] = p3; }
+#if SPHB200_NBR_PACKED
+    s1[lane] = p0.x; s1[32 + lane] = p0.y; s1[64 + lane] = p0.z; s1[96 + lane] = p0.w; s1[128 + lane] = p1.x;
+#endif
     if (lane == 0 && r < (uint32_t)JB_CAP) sjb[r] = jb;
     // ghost candidates of the run (original index >= nInt): a hit on one of them is a pair counted once, not twice
     const unsigned ghostWord = __ballot_sync(0xffffffffu, (uint32_t)lane < len && __float_as_uint(p1.w) >= a.nInt);
@@ -511,6 +528,30 @@ __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build(NbrArgs a, int listRo
     // stage 1, branch-free: |r|^2 against the inner spheres (certain hit) and the outer spheres (possible hit).  Rows past
     // the end of the run are padding candidates at infinity, so the loop runs in groups of four.
     uint32_t hitWord = 0, inWord = 0;
+#if SPHB200_NBR_PACKED
+    const unsigned long long bx2 = f2_pack(bse[0], bse[0]), by2 = f2_pack(bse[1], bse[1]), bz2 = f2_pack(bse[2], bse[2]);
+    for (uint32_t c4 = 0; c4 < len; c4 += 4u) {
+      const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(s1 + c4), Y = *reinterpret_cast<const ulonglong2*>(s1 + 32 + c4);   // broadcast
+      const float4 LO = *reinterpret_cast<const float4*>(s1 + 96 + c4), HI = *reinterpret_cast<const float4*>(s1 + 128 + c4);
+      const unsigned long long rxa = f2_sub(bx2, X.x), rxb = f2_sub(bx2, X.y), rya = f2_sub(by2, Y.x), ryb = f2_sub(by2, Y.y);
+      unsigned long long qa = f2_fma(rya, rya, f2_mul(rxa, rxa)), qb = f2_fma(ryb, ryb, f2_mul(rxb, rxb));
+      if (DIM == 3) {
+        const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(s1 + 64 + c4);
+        const unsigned long long rza = f2_sub(bz2, Z.x), rzb = f2_sub(bz2, Z.y);
+        qa = f2_fma(rza, rza, qa); qb = f2_fma(rzb, rzb, qb);
+      }
+      float r2v[4];
+      f2_unpack(qa, r2v[0], r2v[1]); f2_unpack(qb, r2v[2], r2v[3]);
+      const float lo[4] = {LO.x, LO.y, LO.z, LO.w}, hi[4] = {HI.x, HI.y, HI.z, HI.w};
+      uint32_t hn = 0, in = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r2v[u] <= fmaxf(r2loi, lo[u])) hn |= 1u << u;
+        if (r2v[u] <= fmaxf(r2hii, hi[u])) in |= 1u << u;
+      }
+      hitWord |= hn << c4; inWord |= in << c4;
+    }
+#else
     for (uint32_t c4 = 0; c4 < len; c4 += 4u) {
       uint32_t hn = 0, in = 0;
 #pragma unroll
@@ -524,6 +565,7 @@ __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build(NbrArgs a, int listRo
       }
       hitWord |= hn << c4; inWord |= in << c4;
     }
+#endif
     // stage 2: candidates inside an outer sphere but no inner one ask the ellipsoids (FP32 with error band, else exact)
     uint32_t amb = inWord & ~hitWord;
     for (unsigned au = __reduce_or_sync(0xffffffffu, amb); au; au &= au - 1u) {
@@ -796,7 +838,7 @@ int sphb200_neighbors(sphb200_ctx* c) {
     KERNEL_CHECK(c, "k_tile_runs");
     // 2. the predicate, once per (node, candidate), and the sliced-ELL lists
     {
-      const size_t perWarp = (size_t)32*CROW*4 + (size_t)JB_CAP*4 + (size_t)c->listRows*64;
+      const size_t perWarp = (size_t)32*CROW*4 + (size_t)S1F*4 + (size_t)JB_CAP*4 + (size_t)c->listRows*64;
       int warps = NB_WARPS;
       while (warps > 1 && warps*perWarp > 220*1024) warps >>= 1;     // very long lists: fewer tiles per CTA
       if (perWarp > 220*1024)
