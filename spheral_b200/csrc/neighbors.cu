@@ -454,6 +454,9 @@ __device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsig
 #ifndef SPHB200_NBR_PACKED
 #define SPHB200_NBR_PACKED 1
 #endif
+#ifndef SPHB200_NBR_PAD
+#define SPHB200_NBR_PAD 0            // diagnostic: extra shared memory per warp (bytes), to measure how k_nbr_build reacts to occupancy
+#endif
 constexpr int NB_WARPS = 4;          // warps (tiles) per CTA of k_nbr_build
 constexpr int JB_CAP = 128;          // runs per tile whose first slot is cached in shared memory for the flush
 
@@ -465,7 +468,7 @@ template <int DIM>
 __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build(NbrArgs a, int listRows) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int w = threadIdx.x >> 5;
-  const size_t perWarp = (size_t)32*CROW*4 + (size_t)S1F*4 + (size_t)JB_CAP*4 + (size_t)listRows*64;
+  const size_t perWarp = (size_t)32*CROW*4 + (size_t)S1F*4 + (size_t)JB_CAP*4 + (size_t)listRows*64 + SPHB200_NBR_PAD;
   float* const sc = reinterpret_cast<float*>(smemRaw + w*perWarp);
   float* const s1 = sc + 32*CROW;                   // stage-1 SoA copy of the current run
   uint32_t* const sjb = reinterpret_cast<uint32_t*>(s1 + S1F);
@@ -838,7 +841,7 @@ int sphb200_neighbors(sphb200_ctx* c) {
     KERNEL_CHECK(c, "k_tile_runs");
     // 2. the predicate, once per (node, candidate), and the sliced-ELL lists
     {
-      const size_t perWarp = (size_t)32*CROW*4 + (size_t)S1F*4 + (size_t)JB_CAP*4 + (size_t)c->listRows*64;
+      const size_t perWarp = (size_t)32*CROW*4 + (size_t)S1F*4 + (size_t)JB_CAP*4 + (size_t)c->listRows*64 + SPHB200_NBR_PAD;
       int warps = NB_WARPS;
       while (warps > 1 && warps*perWarp > 220*1024) warps >>= 1;     // very long lists: fewer tiles per CTA
       if (perWarp > 220*1024)
