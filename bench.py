@@ -212,6 +212,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=48, help="lattice points per side of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="A/B diagnostic: skip the device-resident RK2 leg (scripts/gpu_ab.sh)")
+    ap.add_argument("--rk2-trace", action="store_true", help="diagnostic: per-step breakdown of the device-resident RK2 leg on stderr")
     ap.add_argument("--hjitter", type=float, default=0.0,
                     help="scale every node's H by a random factor in [1-x, 1+x] (diagnostic: the lattice workloads have a constant h)")
     args = ap.parse_args()
@@ -363,6 +364,15 @@ def main():
             rk.step()
         e.sync()
         nrk = max(3, args.steps//2)
+        if args.rk2_trace and rank == 0:
+            import time as _t
+            for q in range(nrk):
+                e.sync(); t0 = _t.perf_counter(); l0 = e.stats()["launches"]
+                rk.step()
+                e.sync(); t1 = _t.perf_counter(); s_ = e.stats()
+                sys.stderr.write("rk2 step %2d: wall %.2f ms  build %.2f  nbr %.2f  eval %.2f  pair %.2f  energy %.2f  launches %d  radius %d  edges/node %.1f\n"
+                                 % (q, (t1 - t0)*1e3, s_["ms_build_pairs"], s_["ms_neighbor_kernels"], s_["ms_evaluate"], s_["ms_pair_kernel"],
+                                    s_["ms_energy"], s_["launches"] - l0, s_["stencil_radius"], s_["directed_edges"]/float(N)))
         rk_s, _ = timed(rk.step, nrk)
         rk2 = {"ms_per_step": rk_s/nrk*1e3, "value": N*nrk/rk_s, "unit": "particle-updates/s", "steps": nrk,
                "what": ("CheapSynchronousRK2 step with the state resident in HBM: build_pairs + computeRKSumVolume + computeCRKSPHSumMassDensity + "
