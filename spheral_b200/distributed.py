@@ -144,9 +144,13 @@ class DistributedSPH:
         self.dev = torch.device("cuda", engine_device(engine))
         self.stream = torch.cuda.ExternalStream(engine.stream, device=self.dev)
         self.maskA = field_mask(PHASE_A)
-        self.maskB = field_mask(PHASE_B + tuple(extra_fields))
+        # extra_fields: state fields that only exist once a package has computed them (CRKSPH: "volume", "rkCorrections").  They join
+        # the exchange from the moment the integrator reports them ready (mark_ready); the staging is sized for all of them.
+        self.extra = tuple(extra_fields)
+        self.ready = set()
+        self.maskB = field_mask(PHASE_B)
         self.bytesA = engine.halo_bytes_per_node(self.maskA)
-        self.bytesB = engine.halo_bytes_per_node(self.maskB)
+        self.bytesB = engine.halo_bytes_per_node(field_mask(PHASE_B + self.extra))
         self._cap = 0
         self.nInternal = engine.nInternal
         # ghosts of the boundaries that come before the slab halo in the boundary list (reflecting / periodic planes generated on
@@ -157,6 +161,13 @@ class DistributedSPH:
         self.nFromLower = self.nFromUpper = 0
         self.width = 0.0
         self.last = {}
+
+    def mark_ready(self, *names):
+        """A package has computed these extra fields on the internal nodes: from now on they travel with the halo."""
+        for k in names:
+            if k in self.extra and k not in self.ready:
+                self.ready.add(k)
+                self.maskB = field_mask(PHASE_B + tuple(x for x in self.extra if x in self.ready))
 
     def _ensure(self, cap, keep_lists=False):
         """Capacity (in nodes) of the send lists and of the four staging buffers.  keep_lists: the send lists have just been
@@ -233,7 +244,7 @@ class DistributedSPH:
             self._ensure(max(nLow, nHigh, nFL, nFU), keep_lists=True)
             self.nFromLower, self.nFromUpper = nFL, nFU
             e.set_nodes(nInt, nBG + nFL + nFU)
-            wA, wB = self.bytesA//8, self.bytesB//8
+            wA, wB = self.bytesA//8, e.halo_bytes_per_node(self.maskB)//8
             if not self.two_phase or not build:
                 wAB = wA + wB
                 mask = self.maskA | self.maskB

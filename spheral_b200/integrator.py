@@ -94,6 +94,8 @@ class CheapSynchronousRK2:
         e, so = self.engine, self.so
         if self._crk:
             e.crk_compute_volume()
+            if self.distributed is not None:
+                self.distributed.mark_ready("volume")
             self._ghosts()
         if self.densityUpdate == RIGOROUS_SUM_DENSITY:
             if self._crk:
@@ -109,6 +111,8 @@ class CheapSynchronousRK2:
         """Integrator::initializeDerivatives (Integrator.cc:186-210): RKCorrections::initialize (RKCorrections.cc:346-372)."""
         if self._crk:
             self.engine.crk_compute_corrections()
+            if self.distributed is not None:
+                self.distributed.mark_ready("rkCorrections")
             self._ghosts()
 
     def selectDt(self, dtMin, dtMax):

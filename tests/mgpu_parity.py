@@ -47,15 +47,22 @@ def main():
     N = n**3
     mine = slice(rank*N, (rank + 1)*N)
     WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    crk = os.environ.get("MGPU_CRK", "0") == "1"          # CRKSPH: volumes and RK corrections travel with the halo
     kw = dict(nPerh=nPerh, Cl=2.0, Cq=2.0, hEvolution=1 if asph else 0)
+    if crk:
+        kw = dict(nPerh=nPerh, Cl=1.0, Cq=0.25, Qkind=0, correctVelocityGradient=0)
+        G["velocity"] = 0.3*G["velocity"]
     oo, po = common.opts_pair(orc, engine, ndim, **kw)
+    if crk:
+        from spheral_b200 import _lib as L
+        po.hydro = L.HYDRO_CRKSPH
     e = engine.Engine(ndim, device=local, options=po)
     e.set_kernel_table(WT)
     e.set_nodes(N, 0)
     e.upload_state(**{k: v[mine] for k, v in G.items()})
-    d = D.DistributedSPH(e, 0, float(rank), float(rank + 1))
-    if os.environ.get("MGPU_RK2", "0") == "1":
-        return rk2_mode(rank, world, e, d, G, mine, N, oo, WT, orc, common, engine)
+    d = D.DistributedSPH(e, 0, float(rank), float(rank + 1), extra_fields=("volume", "rkCorrections") if crk else ())
+    if os.environ.get("MGPU_RK2", "0") == "1" or crk:
+        return rk2_mode(rank, world, e, d, G, mine, N, oo, WT, orc, common, engine, crk)
     for _ in range(2):                       # twice: the second pass reuses every buffer
         npairs = d.step_connectivity_and_derivatives(0.0, 1.0)
     got = e.download_derivs()
@@ -81,7 +88,7 @@ def main():
     sys.exit(0 if flag.item() == 1.0 else 1)
 
 
-def rk2_mode(rank, world, e, d, G, mine, N, oo, WT, orc, common, engine):
+def rk2_mode(rank, world, e, d, G, mine, N, oo, WT, orc, common, engine, crk=False):
     """Device-resident CheapSynchronousRK2 steps on the decomposed problem (ghost refresh between the stages, DvDt / DepsDt of the
     ghosts after the derivatives, dt all-reduced) against the oracle-driven integrator on the WHOLE problem."""
     from spheral_b200 import integrator
@@ -94,14 +101,16 @@ def rk2_mode(rank, world, e, d, G, mine, N, oo, WT, orc, common, engine):
     rk.initializeDerivatives()
     for _ in range(nsteps):
         assert rk.step()
-    got = e.download_state("position", "velocity", "H", "massDensity", "specificThermalEnergy", "omegaGradh")
+    fields = ("position", "velocity", "H", "massDensity", "specificThermalEnergy") + (("volume",) if crk else ("omegaGradh",))
+    got = e.download_state(*fields)
     e.sync()
     G2 = dict(G); G2["velocity"] = G["velocity"]
-    ref = common.OracleRK2(orc, oo, so, common.oracle_table(orc, WT), G2, densityUpdate=1, planes=planes)
+    ref = common.OracleRK2(orc, oo, so, common.oracle_table(orc, WT), G2, densityUpdate=1, planes=planes, crk=crk)
     ref.initializeDerivatives()
     for _ in range(nsteps):
         ref.step()
-    names = dict(position="pos", velocity="vel", H="H", massDensity="rho", specificThermalEnergy="eps", omegaGradh="omega")
+    names = dict(position="pos", velocity="vel", H="H", massDensity="rho", specificThermalEnergy="eps")
+    names.update(dict(volume="vol") if crk else dict(omegaGradh="omega"))
     refInt = {o: ref.s[o][:world*N] for o in names.values()}           # the oracle state carries its plane ghosts behind the internal nodes
     worst = {k: float(np.abs(got[k][:N] - refInt[o][mine]).max()/max(np.abs(refInt[o][mine]).max(), 1e-300)) for k, o in names.items()}
     w = max(worst.values())
@@ -113,7 +122,7 @@ def rk2_mode(rank, world, e, d, G, mine, N, oo, WT, orc, common, engine):
     t = torch.tensor([Eloc, E0loc], dtype=torch.float64, device="cuda")
     dist.all_reduce(t)
     dE = float((t[0] - t[1])/t[1])
-    print(json.dumps(dict(rank=rank, world=world, mode="rk2", planes=bool(planes), steps=nsteps, ghosts=e.nGhost, halo=d.last,
+    print(json.dumps(dict(rank=rank, world=world, mode="rk2", crk=crk, planes=bool(planes), steps=nsteps, ghosts=e.nGhost, halo=d.last,
                           oracle_plane_ghosts=ref.nGhost, worst_state_error=w, worst=worst,
                           dt_rel_err=dt_err, dE_over_E=dE, time=rk.currentTime)), flush=True)
     ok = (w <= 1.0e-9) and (dt_err <= 1.0e-10) and (abs(dE) <= 1.0e-12)

@@ -249,6 +249,9 @@ def test_two_gpu_slab_halo_parity(sphlib, oracle):
     # the same with reflecting planes on top of the slabs (ghost tail = plane ghosts | halo; the halo carries plane ghosts)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MGPU_RK2="1", MGPU_PLANES="1"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    # CRKSPH decomposed: volumes and RK corrections are extra halo fields
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MGPU_CRK="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("ndim,n,nPerh,kind,kw", [(3, 9, 1.51, "lattice", dict()), (3, 7, 1.51, "aniso", dict(hEvolution=1)),
