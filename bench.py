@@ -428,7 +428,7 @@ def main():
                     "achieved": bytes_alg/t_pair/1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": bytes_alg/t_pair/1e9/hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": hbm_src,
                     "algorithmic_bytes_per_particle": bytes_alg/N,
-                    "note": "the pair loop is FP64-pipe bound at ~100 neighbours (arithmetic intensity ~13 flop/B vs machine balance ~5); see roofline_fp64"}
+                    "note": "HBM is not the binding roof at ~100 neighbours (arithmetic intensity ~13 flop/B vs machine balance ~5): the FP64 pipe is (roofline_fp64), and the unit the kernel actually saturates is the LSU data pipe of the L1 (neighbour-row gather + table look-ups: 81 % of peak wavefronts, FP64 pipe 38 %, profiles/r01_ncu_full_end_of_round_excerpt.csv)"}
         roofline_fp64 = {"bound": "fp64", "achieved": flops_alg/t_pair/1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": flops_alg/t_pair/1e12/fp64_peak, "algorithmic_flops_per_particle": flops_alg/N,
                          "peak_source": "DFMA microbenchmark run in this process (sphb200_measure_fp64_peak)"}
