@@ -54,6 +54,15 @@ def select_halo_numpy(pos, count, axis, lo, hi, width):
     return (np.nonzero(x < lo + width)[0].astype(np.uint32), np.nonzero(x >= hi - width)[0].astype(np.uint32))
 
 
+def send_list_needs(allc, world):
+    """From the all-gathered table {nLow, nHigh, capacity} of every rank: the send-list length each rank really needs (the low list
+    of the first slab and the high list of the last one are never sent) and whether every list fitted its rank's capacity.  Every
+    rank evaluates this on the same table, so all of them take the same decision to redo the selection or to go on -- a rank-local
+    test lets one slab repeat the all-gather while its neighbour is already in send/recv."""
+    need = [max(int(allc[r][0]) if r > 0 else 0, int(allc[r][1]) if r < world - 1 else 0) for r in range(world)]
+    return need, all(need[r] <= int(allc[r][2]) for r in range(world))
+
+
 class SlabHalo:
     """Point-to-point plumbing between a slab and its two neighbours.  Works on torch tensors, so the same code runs over
     NCCL (CUDA tensors) and gloo (CPU tensors, used by tests/test_distributed_gloo.py)."""
@@ -231,8 +240,8 @@ class DistributedSPH:
                 # Redo the selection if ANY rank truncated a send list it will use.  The decision is taken from the gathered table,
                 # identically on every rank: a rank-local test would let one slab repeat the all-gather while its neighbour moves
                 # on to the send/recv (a deadlock; seen when plane ghosts made the counts of the end slabs asymmetric).
-                need = [max(int(allc[r, 0]) if r > 0 else 0, int(allc[r, 1]) if r < h.world - 1 else 0) for r in range(h.world)]
-                if all(need[r] <= int(allc[r, 2]) for r in range(h.world)):
+                need, fits = send_list_needs(allc, h.world)
+                if fits:
                     break
                 self._ensure(max(need))                                       # send lists were truncated: grow and redo
             if h.lower is None:

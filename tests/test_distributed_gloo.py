@@ -138,3 +138,20 @@ def test_two_slab_halo_exchange_reproduces_global_derivatives(ndim, n, nPerh, an
     from spheral_b200 import build as b
     b.build()
     mp.spawn(_worker, args=(2, _free_port(), ndim, n, nPerh, aniso, planes), nprocs=2, join=True)
+
+
+def test_send_list_redo_decision_is_the_same_on_every_rank():
+    """The capacity check of the send-node selection (DistributedSPH.refresh_ghosts) is decided from the gathered table, so every
+    rank redoes the selection or none does.  Lists that are never sent (the first slab's low list -- e.g. full of the ghosts of an
+    x = 0 reflecting plane -- and the last slab's high list) must not trigger a redo."""
+    from spheral_b200 import distributed as D
+    # rank 0 overflows only its unused low list; everything that is sent fits
+    allc = np.array([[9000, 2500, 5000], [2600, 2700, 5000], [2500, 8000, 5000]])
+    need, fits = D.send_list_needs(allc, 3)
+    assert need == [2500, 2700, 2500] and fits
+    # one rank's used list does not fit: every rank sees the same verdict and the same size to grow to
+    allc[1, 1] = 5001
+    need, fits = D.send_list_needs(allc, 3)
+    assert not fits and max(need) == 5001
+    # single slab: nothing is sent at all
+    assert D.send_list_needs(np.array([[10**6, 10**6, 1024]]), 1) == ([0], True)
