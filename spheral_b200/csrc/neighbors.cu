@@ -10,6 +10,7 @@
 #include "sphb200_internal.cuh"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace {
 
@@ -301,6 +302,7 @@ struct NbrArgs {
   size_t n; uint32_t nInt; double kext2; GridDev g;
   uint32_t* nbrCount; uint32_t* tileRows; unsigned long long* tileOff; uint32_t* nbr; unsigned long long nbrCap;
   uint4* runs; unsigned long long runsCap; uint32_t* tileRunStart; uint32_t* tileRunCount;
+  int fine; GridDev gf;              // two-level walk: skey / cellStart / dilTab refer to the fine grid gf (cells of half the width)
   const uint32_t* cellReach;         // per cell key: stencil radius its tiles must walk (null: radius 1 everywhere)
   uint32_t* tileRadius;              // per tile: stencil radius used by k_tile_runs, read back by k_nbr_build
   unsigned long long* counters;      // [0] hits on ghost candidates  [1] directed edges  [2] run cursor  [3] list cursor  [4] longest list  [5] tiles with too many runs for the 16-bit list codes
@@ -342,6 +344,36 @@ __device__ __forceinline__ void walk_cells(const GridDev& g, const uint32_t* __r
   }
 }
 
+// The same walk handing out the stencil cells' coordinates only (two-level walk: the caller looks the children up itself).
+template <int DIM, typename F>
+__device__ __forceinline__ void walk_cells_coarse(const GridDev& g, unsigned leaders, const int* ci, int rad, F&& f) {
+  for (unsigned lm = leaders; lm; lm &= lm - 1) {
+    const int L = __ffs(lm) - 1;
+    int lc[3];
+    lc[0] = __shfl_sync(0xffffffffu, ci[0], L); lc[1] = __shfl_sync(0xffffffffu, ci[1], L); lc[2] = __shfl_sync(0xffffffffu, ci[2], L);
+    const int zlo = (DIM == 3) ? -rad : 0, zhi = (DIM == 3) ? rad : 0;
+    for (int dz = zlo; dz <= zhi; ++dz) {
+      const int sz = lc[2] + dz;
+      if (DIM == 3 && (sz < 0 || sz >= g.nc[2])) continue;
+      for (int dy = -rad; dy <= rad; ++dy) {
+        const int sy = lc[1] + dy;
+        if (sy < 0 || sy >= g.nc[1]) continue;
+        for (int dx = -rad; dx <= rad; ++dx) {
+          const int sx = lc[0] + dx;
+          if (sx < 0 || sx >= g.nc[0]) continue;
+          bool seen = false;
+          for (unsigned pm = leaders & ((1u << L) - 1u); pm && !seen; pm &= pm - 1) {
+            const int P = __ffs(pm) - 1;
+            const int px = __shfl_sync(0xffffffffu, ci[0], P), py = __shfl_sync(0xffffffffu, ci[1], P), pz = __shfl_sync(0xffffffffu, ci[2], P);
+            seen = (abs(px - sx) <= rad) && (abs(py - sy) <= rad) && (DIM == 2 || abs(pz - sz) <= rad);
+          }
+          if (!seen) f(sx, sy, sz);
+        }
+      }
+    }
+  }
+}
+
 // common per-lane prologue: identity, cell coordinates
 template <int DIM>
 __device__ __forceinline__ bool tile_prologue(const NbrArgs& a, size_t& tile, int& lane, size_t& i, bool& inRange, bool& active,
@@ -365,14 +397,16 @@ __device__ __forceinline__ bool tile_prologue(const NbrArgs& a, size_t& tile, in
 
 constexpr int RUN_CAP = 128;         // candidate runs per tile buffered in shared memory (typical: 40-70)
 
-template <int DIM>
+template <int DIM, bool FINE>
 __global__ void __launch_bounds__(128) k_tile_runs(NbrArgs a) {
   __shared__ uint4 sruns[4][RUN_CAP];
   size_t tile, i; int lane, ci[3]; bool inRange, active; uint32_t origi;
   if (!tile_prologue<DIM>(a, tile, lane, i, inRange, active, origi, ci)) return;
   const int w = threadIdx.x >> 5;
   // leaders: first internal lane of every distinct cell of the tile
-  const uint32_t keyi = inRange ? a.skey[i] : 0xffffffffu;
+  // two-level walk: the sort key is the fine one; the coarse cell (leaders, stencil, FP32 geometry) is its parent
+  const uint32_t keyf = inRange ? a.skey[i] : 0xffffffffu;
+  const uint32_t keyi = (FINE && inRange) ? (keyf >> DIM) : keyf;
   const unsigned actMask = __ballot_sync(0xffffffffu, active);
   const unsigned same = __match_any_sync(0xffffffffu, active ? keyi : (0x80000000u | lane));
   const bool leader = active && ((__ffs(same & actMask) - 1) == lane);
@@ -398,7 +432,42 @@ __global__ void __launch_bounds__(128) k_tile_runs(NbrArgs a) {
       ++R;
     }
   };
-  walk_cells<DIM>(a.g, a.dilTab, a.cellStart, leaders, ci, rad, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) { emit(jb, je, sx, sy, sz, 0u, true); });
+  // Two-level walk (experimental): the nodes are sorted by a key with one more level, so the 2^DIM children of a stencil cell are
+  // 2^DIM consecutive entries of cellStart and the cell is still one contiguous range.  Of every stencil cell only the children
+  // inside the hull of the tile's own fine cells, grown by two fine cells, can hold a neighbour (|dx| <= extent <= 2 fine widths on
+  // every axis, for the gather and the scatter side alike); consecutive needed children form one run.
+  int flo[3] = {0, 0, 0}, fhi[3] = {0, 0, 0};
+  if constexpr (FINE) {
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+      const int f = inRange ? cell_coord(a.rows[i*Dm<DIM>::ROW + Dm<DIM>::R_POS + k], a.gf.lo[k], a.gf.cs[k], a.gf.nc[k]) : 0;
+      flo[k] = __reduce_min_sync(0xffffffffu, active ? f : 0x7fffffff) - 2;
+      fhi[k] = __reduce_max_sync(0xffffffffu, active ? f : -0x7fffffff) + 2;
+    }
+  }
+  auto emit_fine = [&](int sx, int sy, int sz, uint32_t lo, bool toShared) {
+    const uint32_t k0 = a.dilTab[2*sx] | a.dilTab[SPHB200_DIL + 2*sy] | ((DIM == 3) ? a.dilTab[2*SPHB200_DIL + 2*sz] : 0u);   // child (0,0,0)
+    const int s3[3] = {sx, sy, sz};
+    int first = -1;
+    for (int ch = 0; ch <= (1 << DIM); ++ch) {
+      bool need = ch < (1 << DIM);
+      if (need) {
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) {
+          const int f = 2*s3[k] + ((ch >> a.gf.bitpos[k][0]) & 1);
+          need = need && f >= flo[k] && f <= fhi[k];
+        }
+      }
+      if (need && first < 0) first = ch;
+      if (!need && first >= 0) {
+        const uint32_t jb = a.cellStart[k0 + (uint32_t)first], je = a.cellStart[k0 + (uint32_t)ch];
+        if (je > jb) emit(jb, je, sx, sy, sz, lo, toShared);
+        first = -1;
+      }
+    }
+  };
+  if constexpr (FINE) walk_cells_coarse<DIM>(a.g, leaders, ci, rad, [&](int sx, int sy, int sz) { emit_fine(sx, sy, sz, 0u, true); });
+  else walk_cells<DIM>(a.g, a.dilTab, a.cellStart, leaders, ci, rad, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) { emit(jb, je, sx, sy, sz, 0u, true); });
   __syncwarp();
   const uint32_t Rtot = R;
   if (Rtot >= 2048u && lane == 0) atomicAdd(&a.counters[5], 1ull);      // list codes are run << 5 | candidate in 16 bits
@@ -410,7 +479,8 @@ __global__ void __launch_bounds__(128) k_tile_runs(NbrArgs a) {
   for (uint32_t k = lane; k < min(Rtot, (uint32_t)RUN_CAP); k += 32) a.runs[start + k] = sruns[w][k];
   if (Rtot > RUN_CAP) {                              // rare: very ragged tile, walk again for the tail
     R = 0;
-    walk_cells<DIM>(a.g, a.dilTab, a.cellStart, leaders, ci, rad, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) { emit(jb, je, sx, sy, sz, (uint32_t)start, false); });
+    if constexpr (FINE) walk_cells_coarse<DIM>(a.g, leaders, ci, rad, [&](int sx, int sy, int sz) { emit_fine(sx, sy, sz, (uint32_t)start, false); });
+    else walk_cells<DIM>(a.g, a.dilTab, a.cellStart, leaders, ci, rad, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) { emit(jb, je, sx, sy, sz, (uint32_t)start, false); });
   }
 }
 
@@ -706,6 +776,27 @@ static int build_grid(sphb200_ctx* c, const double* bb /*lo3 hi3 ext3 sumext3*/)
     for (int a = 0; a < nd; ++a)
       if (l < g.bits[a]) { g.bitpos[a][l] = (uint8_t)pos; g.mask[a] |= (1u << pos); ++pos; }
   g.tableSize = 1u << pos;
+  // Two-level walk (experimental, off unless SPHB200_FINE_WALK=1 is set in the environment): sort by cells of half the width.  With one
+  // more bit per axis, interleaved level by level like the coarse key, the lowest ndim bits of the fine key are the child index and
+  // fine key >> ndim is the coarse key, so a coarse cell stays one contiguous range of the sorted order.
+  c->fineWalk = false;
+  static const bool fineWanted = [] { const char* e = std::getenv("SPHB200_FINE_WALK"); return e && e[0] == '1'; }();
+  if (fineWanted && c->stencilR == 1 && pos + nd <= maxBitsTotal) {
+    bool fits = true;
+    for (int a = 0; a < nd; ++a) fits = fits && 2*g.nc[a] <= SPHB200_DIL && g.bits[a] + 1 <= 16;
+    if (fits) {
+      GridDev& f = c->gridFine;
+      f = g;
+      for (int a = 0; a < 3; ++a) { f.mask[a] = 0; f.bits[a] = 0; }
+      for (int a = 0; a < nd; ++a) { f.nc[a] = 2*g.nc[a]; f.cs[a] = 0.5*g.cs[a]; f.bits[a] = g.bits[a] + 1; }
+      int fp = 0;
+      for (int l = 0; l < 16; ++l)
+        for (int a = 0; a < nd; ++a)
+          if (l < f.bits[a]) { f.bitpos[a][l] = (uint8_t)fp; f.mask[a] |= (1u << fp); ++fp; }
+      f.tableSize = 1u << fp;
+      c->fineWalk = true;
+    }
+  }
   return 0;
 }
 
@@ -770,24 +861,25 @@ int sphb200_sort_and_pack(sphb200_ctx* c) {
       return sphb200_fail(c, "build_pairs: non-finite position or H");
   if (build_grid(c, c->reduceHost)) return 1;
 
-  const size_t tbl = (size_t)c->grid.tableSize + 1;
+  const GridDev& gs = c->fineWalk ? c->gridFine : c->grid;          // the grid the nodes are sorted by
+  const size_t tbl = (size_t)gs.tableSize + 1;
   if (sphb200_ensure(c, c->cellStart, c->cellCap, tbl)) return 1;
   if (sphb200_ensure(c, c->cellCursor, c->cellCursorCap, tbl)) return 1;
   CU_CHECK(c, cudaMemsetAsync(c->cellStart, 0, tbl*sizeof(uint32_t), c->stream));
   const unsigned nb = (unsigned)((n + RB - 1)/RB);
   {
-    int ncmax = std::max(c->grid.nc[0], std::max(c->grid.nc[1], c->grid.nc[2]));
-    k_dilate_table<<<dim3((unsigned)((ncmax + RB - 1)/RB), (unsigned)c->ndim), RB, 0, c->stream>>>(c->grid, c->dilTab);
+    int ncmax = std::max(gs.nc[0], std::max(gs.nc[1], gs.nc[2]));
+    k_dilate_table<<<dim3((unsigned)((ncmax + RB - 1)/RB), (unsigned)c->ndim), RB, 0, c->stream>>>(gs, c->dilTab);
     KERNEL_CHECK(c, "k_dilate_table");
   }
-  if (c->ndim == 3) k_cell_count<3><<<nb, RB, 0, c->stream>>>(c->api[S_POS], n, c->grid, c->dilTab, c->cellKeyApi, c->cellStart);
-  else              k_cell_count<2><<<nb, RB, 0, c->stream>>>(c->api[S_POS], n, c->grid, c->dilTab, c->cellKeyApi, c->cellStart);
+  if (c->ndim == 3) k_cell_count<3><<<nb, RB, 0, c->stream>>>(c->api[S_POS], n, gs, c->dilTab, c->cellKeyApi, c->cellStart);
+  else              k_cell_count<2><<<nb, RB, 0, c->stream>>>(c->api[S_POS], n, gs, c->dilTab, c->cellKeyApi, c->cellStart);
   KERNEL_CHECK(c, "k_cell_count");
-  if (sphb200_scan_u32(c, c->cellStart, c->cellStart, c->grid.tableSize)) return 1;
-  CU_CHECK(c, cudaMemcpyAsync(c->cellCursor, c->cellStart, (size_t)c->grid.tableSize*sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+  if (sphb200_scan_u32(c, c->cellStart, c->cellStart, gs.tableSize)) return 1;
+  CU_CHECK(c, cudaMemcpyAsync(c->cellCursor, c->cellStart, (size_t)gs.tableSize*sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
   k_cell_scatter<<<nb, RB, 0, c->stream>>>(c->cellKeyApi, n, c->cellCursor, c->perm);
   KERNEL_CHECK(c, "k_cell_scatter");
-  k_cell_order<<<(c->grid.tableSize + RB - 1)/RB, RB, 0, c->stream>>>(c->cellStart, c->grid.tableSize, c->perm);
+  k_cell_order<<<(gs.tableSize + RB - 1)/RB, RB, 0, c->stream>>>(c->cellStart, gs.tableSize, c->perm);
   KERNEL_CHECK(c, "k_cell_order");
   c->sortValid = true;
   if (c->stencilR > 1) {
@@ -833,11 +925,13 @@ int sphb200_neighbors(sphb200_ctx* c) {
     a.nbrCount = c->nbrCount; a.tileRows = c->tileRows; a.tileOff = c->tileOff; a.nbr = c->nbr; a.nbrCap = c->nbrCap;
     a.runs = c->runs; a.runsCap = c->runsCap; a.tileRunStart = c->tileRunStart; a.tileRunCount = c->tileRunCount;
     a.counters = c->counters;
+    a.fine = c->fineWalk ? 1 : 0; a.gf = c->gridFine;
     a.cellReach = (c->stencilR > 1) ? c->cellReach : nullptr;
     if (c->stencilR > 1) { if (sphb200_ensure(c, c->tileRadius, c->tileRadiusCap, c->nTiles + 1)) return 1; a.tileRadius = c->tileRadius; }
     CU_CHECK(c, cudaMemsetAsync(c->counters, 0, 8*sizeof(unsigned long long), c->stream));
     // 1. candidate runs per tile
-    if (c->ndim == 3) k_tile_runs<3><<<nb, 128, 0, c->stream>>>(a); else k_tile_runs<2><<<nb, 128, 0, c->stream>>>(a);
+    if (c->fineWalk) { if (c->ndim == 3) k_tile_runs<3, true><<<nb, 128, 0, c->stream>>>(a); else k_tile_runs<2, true><<<nb, 128, 0, c->stream>>>(a); }
+    else             { if (c->ndim == 3) k_tile_runs<3, false><<<nb, 128, 0, c->stream>>>(a); else k_tile_runs<2, false><<<nb, 128, 0, c->stream>>>(a); }
     KERNEL_CHECK(c, "k_tile_runs");
     // 2. the predicate, once per (node, candidate), and the sliced-ELL lists
     {

@@ -87,6 +87,8 @@ struct sphb200_ctx {
 
   // grid + sort
   GridDev grid{};
+  GridDev gridFine{};               // two-level walk (experimental, SPHB200_FINE_WALK=1): the sort grid, cells of half the width; grid stays the coarse one
+  bool fineWalk = false;            // the current sort used gridFine (keys, cellStart, dilTab refer to it; coarse key = fine key >> ndim)
   uint32_t* dilTab = nullptr;       // 3*SPHB200_DIL dilated cell coordinates
   uint32_t* cellKeyApi = nullptr;   // key per node, original order
   uint32_t* cellStart = nullptr;    // tableSize+1
