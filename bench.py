@@ -435,7 +435,7 @@ def main():
         line = {"metric": metric, "value": value, "unit": "particle-updates/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warmup, "ms_per_step": dev_s/args.steps*1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": dict(config, neighbours_per_particle=nbrs, halo=halo_info, grid_stencil_radius=int(stencil_radius),
+                "config": dict(config, neighbours_per_particle=nbrs, halo=halo_info, grid_stencil_radius=int(stencil_radius), grid_fine_walk=int(e.stats().get("fine_walk", 0)),
                                timing="CUDA events on the engine stream around the K steps, max over ranks"),
                 "clocks": clocks,
                 "e2e": {"value": total_updates/e2e_s, "unit": "particle-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

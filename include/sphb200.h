@@ -305,6 +305,7 @@ typedef struct {
   uint64_t directed_edges;     /* sum of neighbour counts (2*internal-internal + internal-ghost pairs) */
   uint32_t stencil_radius;     /* cells a tile walks in each direction at most: 1 when the grid cells are as wide as the largest
                                   kernel extent, > 1 when a heavy tail of extents made the grid follow the typical extent */
+  uint32_t fine_walk;          /* 1 if the last build sorted by cells of half the width and walked children (experimental, SPHB200_FINE_WALK=1) */
 } sphb200_stats;
 int  sphb200_get_stats(sphb200_ctx* ctx, sphb200_stats* out);
 /* FP64 FMA throughput microbenchmark on the context's device (roofline denominator; returns TFLOP/s). */

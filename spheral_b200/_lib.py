@@ -86,7 +86,7 @@ class StepOptions(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("launches", C.c_uint64), ("ms_build_pairs", C.c_float), ("ms_evaluate", C.c_float),
                 ("ms_energy", C.c_float), ("ms_pair_kernel", C.c_float), ("ms_neighbor_kernels", C.c_float),
-                ("directed_edges", C.c_uint64), ("stencil_radius", C.c_uint32)]
+                ("directed_edges", C.c_uint64), ("stencil_radius", C.c_uint32), ("fine_walk", C.c_uint32)]
 
 
 EXPORTS = ("sphb200_abi_version", "sphb200_create", "sphb200_destroy", "sphb200_set_options", "sphb200_last_error",

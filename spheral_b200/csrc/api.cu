@@ -785,6 +785,7 @@ int sphb200_get_stats(sphb200_ctx* c, sphb200_stats* out) {
   if (cudaEventElapsedTime(&c->stats.ms_energy, c->ev[6], c->ev[7]) != cudaSuccess) c->stats.ms_energy = 0;
   cudaGetLastError();
   c->stats.stencil_radius = (uint32_t)c->stencilR;
+  c->stats.fine_walk = c->fineWalk ? 1u : 0u;
   *out = c->stats;
   return 0;
 }
