@@ -136,7 +136,7 @@ def _c(a, dtype=np.float64):
 
 
 def nsym(ndim):
-    return 6 if ndim == 3 else 3
+    return {1: 1, 2: 3, 3: 6}[ndim]
 
 
 class TableKernel:

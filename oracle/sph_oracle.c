@@ -27,8 +27,47 @@ static inline int    orc_fuzzyEqual(double a, double b, double fuzz) {
  * BSpline:    Kernel/BSplineKernelInline.hh:8-90
  * WendlandC4: Kernel/WendlandC4KernelInline.hh:8-95
  * WendlandC2: Kernel/WendlandC2KernelInline.hh:8-90                                  */
+/* ---- NBSplineKernel(order): Kernel/NBSplineKernel.cc:17-122, NBSplineKernelInline.hh:55-97 ----------------------------------
+ * W(eta) = A/(k-1)! * sum_{i=0..k} (-1)^i C(k,i) (eta - i + k/2)_+^(k-1), k = order + 1; the derivatives lower the exponent and the
+ * factorial; kernel extent (order + 1)/2 in INTEGER arithmetic; A from simpsonsVolumeIntegral with 10000 bins
+ * (Kernel/VolumeIntegrationFunctions.cc:22-70, Utilities/simpsonsIntegration.hh:20-53). */
+static int nbs_factorial(int n) { if (n < 0) return 2147483647; int r = 1; for (int i = 1; i < n + 1; ++i) r *= i; return r; }
+static double nbs_sum(int order, double eta, int lower) {      /* lower = 1, 2, 3: value, gradient, second derivative (unnormalised) */
+  const int k = order + 1;
+  const int e = (k - lower > -lower + 1) ? k - lower : -lower + 1;           /* max(0,k-1), max(-1,k-2), max(-2,k-3) */
+  const double halfk = 0.5*k;
+  double result = 0.0;
+  for (int i = 0; i <= k; ++i) {
+    const double x = eta - i + halfk;
+    const int binom = nbs_factorial(k)/(nbs_factorial(k - i)*nbs_factorial(i));
+    result += pow(-1.0, i)*binom*(x >= 0.0 ? pow(x, e) : 0.0);
+  }
+  return result/nbs_factorial(e);
+}
+static double nbs_volume_normalization(int order, int ndim) {
+  static double cache[16][4];
+  if (order < 16 && cache[order][ndim] != 0.0) return cache[order][ndim];
+  const double kext = (double)((order + 1)/2);
+  const unsigned numBins = 10000u;
+  const double dx = (kext - 0.0)/numBins;
+  double result = 0.0;
+  for (unsigned i = 0; i < numBins + 1u; ++i) {
+    const double r = 0.0 + i*dx;
+    const double ve = (ndim == 1 ? 2.0 : ndim == 2 ? 2.0*M_PI*r : 4.0*M_PI*r*r);
+    const double integrand = ve*((r >= kext) ? 0.0 : nbs_sum(order, r, 1)*1.0*1.0);
+    if (i == 0 || i == numBins) result += integrand;
+    else if (i % 2 == 0) result += 2.0*integrand;
+    else result += 4.0*integrand;
+  }
+  result *= dx/3.0;
+  const double A = 1.0/result;
+  if (order < 16) cache[order][ndim] = A;
+  return A;
+}
+
 double orc_kernel_extent(int kind, int ndim) {
   (void)ndim;
+  if (kind >= ORC_KERNEL_NBSPLINE) return (double)((kind - ORC_KERNEL_NBSPLINE + 1)/2);
   switch (kind) {
     case ORC_KERNEL_BSPLINE: return 2.0;
     case ORC_KERNEL_WENDLANDC4: return 1.0;
@@ -77,6 +116,15 @@ void orc_kernel_analytic(int kind, int ndim, double eta, double* W, double* grad
       w  = A*1.0*(pow(1.0 - eta, 4)*(1.0 + 4.0*eta))*in;
       g  = A*1.0*(20.0*pow(eta - 1.0, 3)*eta)*in;
       g2 = A*1.0*(20.0*pow(eta - 1.0, 2)*(4.0*eta - 1.0))*in;
+    }
+  }
+  else if (kind >= ORC_KERNEL_NBSPLINE) {
+    const int order = kind - ORC_KERNEL_NBSPLINE;
+    if (eta < orc_kernel_extent(kind, ndim)) {
+      const double A = nbs_volume_normalization(order, ndim);
+      w = nbs_sum(order, eta, 1)*(A*1.0);
+      g = nbs_sum(order, eta, 2)*(A*1.0);
+      g2 = nbs_sum(order, eta, 3)*(A*1.0);
     }
   }
   if (W) *W = w;
@@ -281,16 +329,21 @@ int orc_table_build_nperh(const orc_table* t, int ndim, size_t numPoints, double
 #define D 2
 #include "sph_oracle_dim.inc"
 #undef D
+#define D 1
+#include "sph_oracle_dim.inc"
+#undef D
 
 size_t orc_pairs_bruteforce(int ndim, size_t nInt, size_t nGhost, const double* pos, const double* H,
                             double kext, uint32_t* pi, uint32_t* pj, size_t cap, uint32_t* counts) {
   return ndim == 3 ? pairs_bruteforce_3d(nInt, nGhost, pos, H, kext, pi, pj, cap, counts)
-                   : pairs_bruteforce_2d(nInt, nGhost, pos, H, kext, pi, pj, cap, counts);
+                   : (ndim == 2 ? pairs_bruteforce_2d(nInt, nGhost, pos, H, kext, pi, pj, cap, counts)
+                               : pairs_bruteforce_1d(nInt, nGhost, pos, H, kext, pi, pj, cap, counts));
 }
 size_t orc_pairs_cells(int ndim, size_t nInt, size_t nGhost, const double* pos, const double* H,
                        double kext, uint32_t* pi, uint32_t* pj, size_t cap, uint32_t* counts) {
   return ndim == 3 ? pairs_cells_3d(nInt, nGhost, pos, H, kext, pi, pj, cap, counts)
-                   : pairs_cells_2d(nInt, nGhost, pos, H, kext, pi, pj, cap, counts);
+                   : (ndim == 2 ? pairs_cells_2d(nInt, nGhost, pos, H, kext, pi, pj, cap, counts)
+                               : pairs_cells_1d(nInt, nGhost, pos, H, kext, pi, pj, cap, counts));
 }
 int orc_evaluate_derivatives(const orc_options* o, const orc_table* W, const orc_table* WQ,
                              size_t nInt, size_t nGhost, const orc_state* s,
@@ -298,14 +351,16 @@ int orc_evaluate_derivatives(const orc_options* o, const orc_table* W, const orc
                              const uint32_t* numNeighbors, orc_derivs* d, int nthreads) {
   if (o->compatibleEnergy && o->evolveTotalEnergy) return 2;      /* VERIFY2 at SPH.cc:97-98 */
   return o->ndim == 3 ? evaluate_derivatives_3d(o, W, WQ, nInt, nGhost, s, npairs, pi, pj, numNeighbors, d, nthreads)
-                      : evaluate_derivatives_2d(o, W, WQ, nInt, nGhost, s, npairs, pi, pj, numNeighbors, d, nthreads);
+                      : (o->ndim == 2 ? evaluate_derivatives_2d(o, W, WQ, nInt, nGhost, s, npairs, pi, pj, numNeighbors, d, nthreads)
+                               : evaluate_derivatives_1d(o, W, WQ, nInt, nGhost, s, npairs, pi, pj, numNeighbors, d, nthreads));
 }
 int orc_update_energy_compatible(int ndim, size_t nInt, size_t nGhost, const double* mass, const double* vel,
                                  const double* DvDt, const double* DepsDt0, size_t npairs,
                                  const uint32_t* pi, const uint32_t* pj, const double* pacc,
                                  double multiplier, double* eps) {
   return ndim == 3 ? update_energy_3d(nInt, nGhost, mass, vel, DvDt, DepsDt0, npairs, pi, pj, pacc, multiplier, eps)
-                   : update_energy_2d(nInt, nGhost, mass, vel, DvDt, DepsDt0, npairs, pi, pj, pacc, multiplier, eps);
+                   : (ndim == 2 ? update_energy_2d(nInt, nGhost, mass, vel, DvDt, DepsDt0, npairs, pi, pj, pacc, multiplier, eps)
+                               : update_energy_1d(nInt, nGhost, mass, vel, DvDt, DepsDt0, npairs, pi, pj, pacc, multiplier, eps));
 }
 
 /* ---- CRKSPH (crk_oracle_dim.inc) ----------------------------------------------------------------*/
@@ -346,16 +401,21 @@ void orc_rk_kernel_grad(int ndim, const orc_table* W, const double* x, const dou
 #define D 2
 #include "step_oracle_dim.inc"
 #undef D
+#define D 1
+#include "step_oracle_dim.inc"
+#undef D
 
 int orc_sum_mass_density(int ndim, const orc_table* W, size_t nInt, size_t nGhost, const double* pos, const double* mass,
                          const double* H, size_t npairs, const uint32_t* pi, const uint32_t* pj, double* rho) {
   return ndim == 3 ? sum_mass_density_3d(W, nInt, nGhost, pos, mass, H, npairs, pi, pj, rho)
-                   : sum_mass_density_2d(W, nInt, nGhost, pos, mass, H, npairs, pi, pj, rho);
+                   : (ndim == 2 ? sum_mass_density_2d(W, nInt, nGhost, pos, mass, H, npairs, pi, pj, rho)
+                               : sum_mass_density_1d(W, nInt, nGhost, pos, mass, H, npairs, pi, pj, rho));
 }
 int orc_omega_gradh(int ndim, const orc_table* W, size_t nInt, size_t nGhost, const double* pos, const double* H,
                     size_t npairs, const uint32_t* pi, const uint32_t* pj, const uint32_t* numNeighbors, double* omega) {
   return ndim == 3 ? omega_gradh_3d(W, nInt, nGhost, pos, H, npairs, pi, pj, numNeighbors, omega)
-                   : omega_gradh_2d(W, nInt, nGhost, pos, H, npairs, pi, pj, numNeighbors, omega);
+                   : (ndim == 2 ? omega_gradh_2d(W, nInt, nGhost, pos, H, npairs, pi, pj, numNeighbors, omega)
+                               : omega_gradh_1d(W, nInt, nGhost, pos, H, npairs, pi, pj, numNeighbors, omega));
 }
 void orc_eos_gamma_law(const orc_step_options* so, size_t n, const double* rho, const double* eps, double* P, double* cs) {
   eos_gamma_law_3d(so, n, rho, eps, P, cs);
@@ -364,14 +424,16 @@ int orc_state_update(const orc_options* o, const orc_step_options* so, size_t nI
                      int timeAdvanceOnly, int epsDone, const orc_derivs* d,
                      double* pos, double* vel, double* H, double* rho, double* eps, double* P, double* cs) {
   return o->ndim == 3 ? state_update_3d(o, so, nInt, nGhost, multiplier, timeAdvanceOnly, epsDone, d, pos, vel, H, rho, eps, P, cs)
-                      : state_update_2d(o, so, nInt, nGhost, multiplier, timeAdvanceOnly, epsDone, d, pos, vel, H, rho, eps, P, cs);
+                      : (o->ndim == 2 ? state_update_2d(o, so, nInt, nGhost, multiplier, timeAdvanceOnly, epsDone, d, pos, vel, H, rho, eps, P, cs)
+                               : state_update_1d(o, so, nInt, nGhost, multiplier, timeAdvanceOnly, epsDone, d, pos, vel, H, rho, eps, P, cs));
 }
 double orc_hydro_dt(const orc_options* o, const orc_step_options* so, size_t nInt, const double* vel, const double* H,
                     const double* rho, const double* cs, const orc_derivs* d, size_t npairs, const uint32_t* pi,
                     const uint32_t* pj, int* reason, uint32_t* node) {
   return o->ndim == 3 ? hydro_dt_3d(o, so, nInt, vel, H, rho, cs, d, npairs, pi, pj, reason, node)
-                      : hydro_dt_2d(o, so, nInt, vel, H, rho, cs, d, npairs, pi, pj, reason, node);
+                      : (o->ndim == 2 ? hydro_dt_2d(o, so, nInt, vel, H, rho, cs, d, npairs, pi, pj, reason, node)
+                               : hydro_dt_1d(o, so, nInt, vel, H, rho, cs, d, npairs, pi, pj, reason, node));
 }
 void orc_sym_bound(int ndim, double* H, double minv, double maxv) {
-  if (ndim == 3) sym_bound_3d(H, minv, maxv); else sym_bound_2d(H, minv, maxv);
+  if (ndim == 3) sym_bound_3d(H, minv, maxv); else if (ndim == 2) sym_bound_2d(H, minv, maxv); else sym_bound_1d(H, minv, maxv);
 }

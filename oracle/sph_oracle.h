@@ -33,7 +33,8 @@ extern "C" {
 #endif
 
 /* analytic kernel ids */
-enum { ORC_KERNEL_BSPLINE = 0, ORC_KERNEL_WENDLANDC4 = 1, ORC_KERNEL_WENDLANDC2 = 2, ORC_KERNEL_GAUSSIAN = 3 };
+enum { ORC_KERNEL_BSPLINE = 0, ORC_KERNEL_WENDLANDC4 = 1, ORC_KERNEL_WENDLANDC2 = 2, ORC_KERNEL_GAUSSIAN = 3,
+       ORC_KERNEL_NBSPLINE = 100 /* + order: NBSplineKernel(order), Kernel/NBSplineKernel.cc */ };
 /* artificial viscosity ids */
 enum { ORC_Q_MG = 0, ORC_Q_LIMITED_MG = 1 };
 /* smoothing scale package */

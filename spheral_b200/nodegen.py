@@ -17,7 +17,7 @@ import numpy as np
 
 
 def nsym(ndim):
-    return 6 if ndim == 3 else 3
+    return {1: 1, 2: 3, 3: 6}[ndim]
 
 
 def sym_from_diag(ndim, diag):
@@ -26,8 +26,10 @@ def sym_from_diag(ndim, diag):
     H = np.zeros((diag.shape[0], nsym(ndim)))
     if ndim == 3:
         H[:, 0], H[:, 3], H[:, 5] = diag[:, 0], diag[:, 1], diag[:, 2]
-    else:
+    elif ndim == 2:
         H[:, 0], H[:, 2] = diag[:, 0], diag[:, 1]
+    else:
+        H[:, 0] = diag[:, 0]
     return H
 
 
@@ -37,8 +39,10 @@ def sym_to_full(ndim, H):
     F = np.zeros((H.shape[0], ndim, ndim))
     if ndim == 3:
         idx = [(0, 0, 0), (0, 1, 1), (0, 2, 2), (1, 1, 3), (1, 2, 4), (2, 2, 5)]
-    else:
+    elif ndim == 2:
         idx = [(0, 0, 0), (0, 1, 1), (1, 1, 2)]
+    else:
+        idx = [(0, 0, 0)]
     for r, c, k in idx:
         F[:, r, c] = H[:, k]
         F[:, c, r] = H[:, k]
@@ -48,6 +52,8 @@ def sym_to_full(ndim, H):
 def full_to_sym(ndim, F):
     if ndim == 3:
         return np.stack([F[:, 0, 0], F[:, 0, 1], F[:, 0, 2], F[:, 1, 1], F[:, 1, 2], F[:, 2, 2]], axis=1)
+    if ndim == 1:
+        return F[:, 0, 0].reshape(-1, 1)
     return np.stack([F[:, 0, 0], F[:, 0, 1], F[:, 1, 1]], axis=1)
 
 
@@ -61,6 +67,8 @@ def lattice(ndim, n, xmin=None, xmax=None, rho0=1.0, nPerh=2.01):
     if ndim == 3:
         Z, Y, X = np.meshgrid(axes[2], axes[1], axes[0], indexing="ij")
         pos = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    elif ndim == 1:                                              # oracle-only (the reference's 1-D tests); the engine is 2-D / 3-D
+        pos = axes[0].reshape(-1, 1)
     else:
         Y, X = np.meshgrid(axes[1], axes[0], indexing="ij")
         pos = np.stack([X.ravel(), Y.ravel()], axis=1)
@@ -170,6 +178,8 @@ def reflect_map(ndim, name, c, sd, nhat, periodic=False, sd_exit=None):
     if name == "H":
         Fr = np.einsum("ab,nbc,cd->nad", R, sym_to_full(ndim, c), R)
         return full_to_sym(ndim, 0.5*(Fr + np.transpose(Fr, (0, 2, 1))))
+    if ndim == 1 and name.startswith("DvDx"):                   # a 1-D tensor has the width of a vector: R.(T.R) = T
+        return c.copy()
     if c.ndim == 2 and c.shape[1] == ndim:                      # vectors
         return c @ R.T
     if c.ndim == 2 and c.shape[1] == ndim*ndim:                 # tensors R.(T.R)
