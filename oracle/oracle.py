@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libsph_oracle.so")
 
 KERNEL_BSPLINE, KERNEL_WENDLANDC4, KERNEL_WENDLANDC2 = 0, 1, 2
+KERNEL_NBSPLINE = 100        # + order: NBSplineKernel(order)
 Q_MG, Q_LIMITED_MG = 0, 1
 H_SPH, H_ASPH, H_NONE = 0, 1, 2
 
@@ -268,7 +269,10 @@ def evaluate_derivatives(opts, W, state, nInt, nGhost, pi, pj, counts, WQ=None, 
     shapes = dict(DxDt=nd, DrhoDt=1, DvDt=nd, DepsDt=1, DvDx=nt, localDvDx=nt, gradRho=nd, M=nt, localM=nt,
                   rhoSum=1, normalization=1, maxViscousPressure=1, effViscousPressure=1, XSPHWeightSum=1,
                   XSPHDeltaV=nd, DHDt=ns, Hideal=ns, massZerothMoment=1, massFirstMoment=nd)
-    out = {k: np.zeros((n, w) if w > 1 else n) for k, w in shapes.items()}
+    scalars = ("DrhoDt", "DepsDt", "rhoSum", "normalization", "maxViscousPressure", "effViscousPressure", "XSPHWeightSum",
+               "massZerothMoment")
+    # vectors and tensors keep a component axis in 1-D too (their ghosts are reflected, scalars are copied)
+    out = {k: np.zeros(n if k in scalars else (n, w)) for k, w in shapes.items()}
     out["pairAccelerations"] = np.zeros((npairs, nd))
     d = Derivs(**{k: _p(v) for k, v in out.items()})
     pi, pj, counts = _c(pi, np.uint32), _c(pj, np.uint32), _c(counts, np.uint32)
@@ -349,7 +353,10 @@ def crk_evaluate_derivatives(opts, W, state, vol, corr, nInt, nGhost, pi, pj):
     shapes = dict(DxDt=nd, DrhoDt=1, DvDt=nd, DepsDt=1, DvDx=nt, localDvDx=nt, gradRho=nd, M=nt, localM=nt,
                   rhoSum=1, normalization=1, maxViscousPressure=1, effViscousPressure=1, XSPHWeightSum=1,
                   XSPHDeltaV=nd, DHDt=ns, Hideal=ns, massZerothMoment=1, massFirstMoment=nd)
-    out = {k: np.zeros((n, w) if w > 1 else n) for k, w in shapes.items()}
+    scalars = ("DrhoDt", "DepsDt", "rhoSum", "normalization", "maxViscousPressure", "effViscousPressure", "XSPHWeightSum",
+               "massZerothMoment")
+    # vectors and tensors keep a component axis in 1-D too (their ghosts are reflected, scalars are copied)
+    out = {k: np.zeros(n if k in scalars else (n, w)) for k, w in shapes.items()}
     out["pairAccelerations"] = np.zeros((npairs, nd))
     d = Derivs(**{k: _p(v) for k, v in out.items()})
     pi, pj = _c(pi, np.uint32), _c(pj, np.uint32)

@@ -14,8 +14,12 @@
  * tests/unit/SPH/testLinearVelocityGradient.py linear-field DvDx to 5e-5,
  * tests/unit/Kernel/testTableKernel.py:74-90 table vs analytic 1e-3/1e-2,
  * tests/functional/Hydro/Noh/Noh-cylindrical-2d.py:803-808 |dE/E|<1e-13).
- * No per-node golden derivative vectors exist in the reference tree, so
- * bit-level derivative values are "parity unpinned"; see DESIGN.md.
+ * and by the one numerical golden the reference stores for this path: the L1 / L2
+ * / Linf error norms of tests/functional/Hydro/Noh/Noh-planar-1d.py:226-240,
+ * which the oracle integrator reproduces to ~1e-6 relative over 1091 steps
+ * (tests/test_oracle_noh_planar_1d_golden.py; a 1-D run, hence the D = 1
+ * instantiation of the *_dim.inc files).  No per-node golden derivative vectors
+ * exist in the reference tree; see DESIGN.md section 7 for what that leaves open.
  *
  * Layout conventions (the reference's Field<DataType> AoS):
  *   Vector     : ndim doubles            (x,y[,z])

@@ -67,7 +67,7 @@ def lattice(ndim, n, xmin=None, xmax=None, rho0=1.0, nPerh=2.01):
     if ndim == 3:
         Z, Y, X = np.meshgrid(axes[2], axes[1], axes[0], indexing="ij")
         pos = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
-    elif ndim == 1:                                              # oracle-only (the reference's 1-D tests); the engine is 2-D / 3-D
+    elif ndim == 1:                                              # 1-D lattices serve the CPU test suite only; the engine is 2-D / 3-D
         pos = axes[0].reshape(-1, 1)
     else:
         Y, X = np.meshgrid(axes[1], axes[0], indexing="ij")

@@ -1,0 +1,34 @@
+"""Pins the oracle against the one stored numerical golden the reference holds for this path: the L1 / L2 / Linf error norms of
+tests/functional/Hydro/Noh/Noh-planar-1d.py (LnormRef["SPH"], lines 226-240, tolerance 1e-5), produced by the real Spheral.
+
+The oracle integrator (tests/common.OracleRK2: every piece an oracle/ call -- neighbour pairs, SPH pair loop with the
+LimitedMonaghanGingold viscosity, sum density, grad-h correction, GenericHydro::dt, State::update with IdealH, compatible energy,
+reflecting ghosts, iterateIdealH) runs the reference's set-up for 1091 steps and must land on the reference's 15 numbers.  The run
+is 1-D; the oracle's 1-D code differs from the 2-D / 3-D code the GPU engine is checked against only in the `#if D == ...` blocks
+of oracle/*_dim.inc (tensor algebra of one component), everything else is the same source.
+"""
+import numpy as np
+
+import noh_planar_1d as noh
+
+
+def test_noh_planar_1d_reproduces_the_reference_error_norms(oracle):
+    out, info = noh.run(oracle)
+    assert info["time"] == 0.6 and 1000 < info["cycles"] < 1200
+    worst = 0.0
+    for name, ref in noh.REF.items():
+        for got, want in zip(out[name], ref):
+            assert np.allclose(got, want, noh.TOL, noh.TOL), (name, got, want)      # the script's own criterion (:876-880)
+            worst = max(worst, abs(got/want - 1.0))
+    # the absolute part of that criterion is loose for the small norms: relative agreement is 3e-6 or better, except L1(h) at 1.6e-5
+    assert worst <= 2.0e-5, worst
+    assert abs(out["Mass density"][2]/noh.REF["Mass density"][2] - 1.0) <= 1.0e-6           # the shock front itself: 6e-8
+
+
+def test_the_golden_is_sharp_enough_to_catch_a_missequenced_first_step(oracle):
+    """Negative control: evaluating the derivatives once before the first step (which SpheralController only does on request) moves the
+    norms by ~1e-3 relative -- two orders of magnitude outside the acceptance band."""
+    out, _ = noh.run(oracle, first_step_sees_zero_derivatives=False)
+    rel = max(abs(out[k][0]/noh.REF[k][0] - 1.0) for k in noh.REF)
+    assert 2.0e-4 < rel < 1.0e-2
+    assert not np.allclose(out["Mass density"][0], noh.REF["Mass density"][0], noh.TOL, noh.TOL)
