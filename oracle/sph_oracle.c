@@ -367,30 +367,35 @@ int orc_update_energy_compatible(int ndim, size_t nInt, size_t nGhost, const dou
 int orc_crk_sum_volume(int ndim, const orc_table* W, size_t nInt, size_t nGhost, const double* pos, const double* H,
                        size_t npairs, const uint32_t* pi, const uint32_t* pj, double* vol) {
   return ndim == 3 ? crk_sum_volume_3d(W, nInt, nGhost, pos, H, npairs, pi, pj, vol)
-                   : crk_sum_volume_2d(W, nInt, nGhost, pos, H, npairs, pi, pj, vol);
+                   : (ndim == 2 ? crk_sum_volume_2d(W, nInt, nGhost, pos, H, npairs, pi, pj, vol)
+                               : crk_sum_volume_1d(W, nInt, nGhost, pos, H, npairs, pi, pj, vol));
 }
 int orc_crk_corrections(int ndim, const orc_table* W, size_t nInt, size_t nGhost, const double* pos, const double* H,
                         const double* vol, size_t npairs, const uint32_t* pi, const uint32_t* pj, double* corr) {
   return ndim == 3 ? crk_corrections_3d(W, nInt, nGhost, pos, H, vol, npairs, pi, pj, corr)
-                   : crk_corrections_2d(W, nInt, nGhost, pos, H, vol, npairs, pi, pj, corr);
+                   : (ndim == 2 ? crk_corrections_2d(W, nInt, nGhost, pos, H, vol, npairs, pi, pj, corr)
+                               : crk_corrections_1d(W, nInt, nGhost, pos, H, vol, npairs, pi, pj, corr));
 }
 int orc_crk_sum_density(int ndim, const orc_table* W, size_t nInt, size_t nGhost, const double* pos, const double* mass,
                         const double* vol, const double* H, size_t npairs, const uint32_t* pi, const uint32_t* pj,
                         double rhoMin, double rhoMax, double* rho) {
   return ndim == 3 ? crk_sum_density_3d(W, nInt, nGhost, pos, mass, vol, H, npairs, pi, pj, rhoMin, rhoMax, rho)
-                   : crk_sum_density_2d(W, nInt, nGhost, pos, mass, vol, H, npairs, pi, pj, rhoMin, rhoMax, rho);
+                   : (ndim == 2 ? crk_sum_density_2d(W, nInt, nGhost, pos, mass, vol, H, npairs, pi, pj, rhoMin, rhoMax, rho)
+                               : crk_sum_density_1d(W, nInt, nGhost, pos, mass, vol, H, npairs, pi, pj, rhoMin, rhoMax, rho));
 }
 int orc_crk_evaluate_derivatives(const orc_options* o, const orc_table* W, size_t nInt, size_t nGhost,
                                  const orc_state* s, const double* vol, const double* corr,
                                  size_t npairs, const uint32_t* pi, const uint32_t* pj, orc_derivs* d) {
   if (o->compatibleEnergy && o->evolveTotalEnergy) return 2;
   return o->ndim == 3 ? crk_evaluate_derivatives_3d(o, W, nInt, nGhost, s, vol, corr, npairs, pi, pj, d)
-                      : crk_evaluate_derivatives_2d(o, W, nInt, nGhost, s, vol, corr, npairs, pi, pj, d);
+                      : (o->ndim == 2 ? crk_evaluate_derivatives_2d(o, W, nInt, nGhost, s, vol, corr, npairs, pi, pj, d)
+                               : crk_evaluate_derivatives_1d(o, W, nInt, nGhost, s, vol, corr, npairs, pi, pj, d));
 }
 /* RKUtilities::evaluateKernelAndGradient for one point pair (test hook for the RK interpolation pinning test) */
 void orc_rk_kernel_grad(int ndim, const orc_table* W, const double* x, const double* H, const double* corr,
                         double* WR, double* gradWR) {
-  if (ndim == 3) rk_kernel_grad_3d(W, x, H, corr, WR, gradWR); else rk_kernel_grad_2d(W, x, H, corr, WR, gradWR);
+  if (ndim == 3) rk_kernel_grad_3d(W, x, H, corr, WR, gradWR); else if (ndim == 2) rk_kernel_grad_2d(W, x, H, corr, WR, gradWR);
+  else rk_kernel_grad_1d(W, x, H, corr, WR, gradWR);
 }
 
 /* ---- per-step callers (step_oracle_dim.inc) ------------------------------------------------------------------*/

@@ -85,7 +85,10 @@ __global__ void __launch_bounds__(RB) k_reflect_scatter(const uint32_t* __restri
 }
 
 // one field of the ghosts [first, first+count) of a plane from their control nodes
-//   kind 0 scalar copy | 1 position (mirror) | 2 vector R v | 3 tensor R (T R) | 4 symmetric tensor (R (H R)).Symmetric() | 5 any width, copy
+//   kind 0 scalar copy | 1 position (mirror) | 2 vector R v | 3 tensor R (T R) | 4 symmetric tensor (R (H R)).Symmetric()
+//   kind 5 RK coefficients of linear order {A, B_k | dA/dx_d, dB_k/dx_d}: ReflectingBoundary::applyGhostBoundary(Field<RKCoefficients>)
+//          (Boundary/ReflectingBoundary.cc:403-432) applies RKUtilities::getTransformationMatrix(R) (RK/RKUtilities.cc:637-715):
+//          A' = A, B' = R.B, (grad A)' = R.grad A, (grad B)' = R.(grad B).R; periodic boundaries copy
 template <int DIM>
 __global__ void __launch_bounds__(RB) k_reflect_fill(double* __restrict__ f, int kind, int width, const uint32_t* __restrict__ ctl,
                                                      size_t first, size_t count, Plane pl) {
@@ -94,12 +97,35 @@ __global__ void __launch_bounds__(RB) k_reflect_fill(double* __restrict__ f, int
   const size_t c = ctl[k], g = first + k;
   const double* s = f + c*(size_t)width;
   double* d = f + g*(size_t)width;
-  if (kind == 0 || kind == 5 || (pl.periodic && kind != 1)) { for (int q = 0; q < width; ++q) d[q] = s[q]; return; }
+  if (kind == 0 || (pl.periodic && kind != 1)) { for (int q = 0; q < width; ++q) d[q] = s[q]; return; }
   double R[DIM][DIM];
 #pragma unroll
   for (int a = 0; a < DIM; ++a)
 #pragma unroll
     for (int b = 0; b < DIM; ++b) R[a][b] = (a == b ? 1.0 : 0.0) - 2.0*pl.n[a]*pl.n[b];
+  if (kind == 5) {
+    constexpr int PS = DIM + 1;                      // polynomial size of linear order; block 0: coefficients, block 1+e: d/dx_e
+    double in[PS*PS];
+#pragma unroll
+    for (int q = 0; q < PS*PS; ++q) in[q] = s[q];    // the ghost may alias nothing of its control, but read first all the same
+    d[0] = in[0];
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) { double t = 0.0, u = 0.0;
+#pragma unroll
+      for (int b = 0; b < DIM; ++b) { t += R[a][b]*in[1 + b]; u += R[a][b]*in[PS*(1 + b)]; }
+      d[1 + a] = t;                                  // B' = R.B
+      d[PS*(1 + a)] = u; }                           // (grad A)' = R.grad A
+#pragma unroll
+    for (int a = 0; a < DIM; ++a)
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) { double t = 0.0;
+#pragma unroll
+        for (int e = 0; e < DIM; ++e)
+#pragma unroll
+          for (int m = 0; m < DIM; ++m) t += R[a][e]*in[PS*(1 + e) + 1 + m]*R[m][k];
+        d[PS*(1 + a) + 1 + k] = t; }                 // (grad B)' = R.(grad B).R
+    return;
+  }
   if (kind == 1) {                                   // closestPointOnPlane_enter(r) - signedDistance_exit(r) n_enter
     double r[DIM];
 #pragma unroll

@@ -180,6 +180,17 @@ def reflect_map(ndim, name, c, sd, nhat, periodic=False, sd_exit=None):
         return full_to_sym(ndim, 0.5*(Fr + np.transpose(Fr, (0, 2, 1))))
     if ndim == 1 and name.startswith("DvDx"):                   # a 1-D tensor has the width of a vector: R.(T.R) = T
         return c.copy()
+    if name in ("corr", "rkCorrections"):
+        # RK coefficients (LinearOrder): ReflectingBoundary::applyGhostBoundary(Field<RKCoefficients>) (Boundary/ReflectingBoundary.cc:403-432)
+        # applies RKUtilities::getTransformationMatrix(R) (RK/RKUtilities.cc:637-715): with the layout {A, B_k | dA/dx_d, dB_k/dx_d}
+        # A' = A, B' = R.B, (grad A)' = R.grad A, (grad B)' = R.(grad B).R
+        n = c.shape[0]
+        C = np.asarray(c, dtype=float).reshape(n, 1 + ndim, 1 + ndim)
+        out = C.copy()
+        out[:, 0, 1:] = C[:, 0, 1:] @ R.T
+        out[:, 1:, 0] = C[:, 1:, 0] @ R.T
+        out[:, 1:, 1:] = np.einsum("ab,nbc,cd->nad", R, C[:, 1:, 1:], R)
+        return out.reshape(c.shape)
     if c.ndim == 2 and c.shape[1] == ndim:                      # vectors
         return c @ R.T
     if c.ndim == 2 and c.shape[1] == ndim*ndim:                 # tensors R.(T.R)

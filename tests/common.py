@@ -155,6 +155,7 @@ class OracleRK2:
         if v0 is None or v0.shape[0] != self.N + self.nGhost:
             v0 = self.s["mass"]/self.s["rho"]
         self.s["vol"] = self.orc.crk_sum_volume(self.ndim, self.OT, self.N, self.nGhost, self.s["pos"], self.s["H"], self.pi, self.pj, vol=v0)
+        self._apply_ghosts()                      # RKCorrections::preStepInitialize applies the boundaries to the volume (RKCorrections.cc:298-340)
 
     def _crk_corrections(self):
         if not self.crk:
@@ -164,6 +165,7 @@ class OracleRK2:
             c0 = np.zeros((self.N + self.nGhost, (self.ndim + 1)**2)); c0[:, 0] = 1.0
         self.s["corr"] = self.orc.crk_corrections(self.ndim, self.OT, self.N, self.nGhost, self.s["pos"], self.s["H"], self.s["vol"],
                                                   self.pi, self.pj, corr=c0)
+        self._apply_ghosts()                      # RKCorrections::initialize applies the boundaries to the corrections (RKCorrections.cc:346-372)
 
     def _sum_density(self):
         if self.crk:

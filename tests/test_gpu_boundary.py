@@ -66,6 +66,43 @@ def test_ghost_generation_matches_host_restatement(oracle, mods, ndim, n, nPerh,
     assert np.abs(got2["H"] - ref2["H"]).max() <= 1e-14*np.abs(ref2["H"]).max()
 
 
+@pytest.mark.parametrize("ndim,n,nPerh", [(2, 20, 2.01), (3, 8, 1.51)])
+def test_rk_coefficients_are_transformed_not_copied_into_reflecting_ghosts(oracle, mods, ndim, n, nPerh):
+    """ReflectingBoundary::applyGhostBoundary(Field<RKCoefficients>) (Boundary/ReflectingBoundary.cc:403-432) applies
+    RKUtilities::getTransformationMatrix(R) (RK/RKUtilities.cc:637-715) to the copied coefficients: A' = A, B' = R.B,
+    (grad A)' = R.grad A, (grad B)' = R.(grad B).R.  Device ghosts of a CRKSPH context against the numpy restatement, and the
+    restatement against the truth: the transformed coefficients of a mirror image equal the coefficients computed for a real node at
+    the mirrored position (found with the reference's Noh-planar-1d CRKSPH golden: plain copies were off by O(1))."""
+    engine, _ = mods
+    from spheral_b200 import _lib as L
+    st, nInt, _ = common.make_problem(ndim, n, nPerh=nPerh, kind="lattice", seed=31)
+    WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    OT = common.oracle_table(oracle, WT)
+    s0 = common.to_oracle_state(st)
+    pi, pj, cnt = oracle.pairs(ndim, nInt, 0, s0["pos"], s0["H"], OT.kext)
+    vol = oracle.crk_sum_volume(ndim, OT, nInt, 0, s0["pos"], s0["H"], pi, pj)
+    corr = oracle.crk_corrections(ndim, OT, nInt, 0, s0["pos"], s0["H"], vol, pi, pj)       # one-sided at the faces: B and grad A non-zero
+    f = {o: st[k] for k, o in PN.items()}
+    f["vol"], f["corr"] = vol, corr
+    ref, lists, n0 = ng.reflect_ghosts(ndim, f, planes_of(ndim), WT.kernelExtent, per_plane=True)
+    po = engine.make_options(ndim, nPerh=nPerh, hydro=L.HYDRO_CRKSPH)
+    e = engine.Engine(ndim, options=po)
+    e.set_kernel_table(WT)
+    e.set_nodes(nInt, 0)
+    e.upload_state(volume=vol, rkCorrections=corr, **st)
+    e.reflect_configure(planes_of(ndim))
+    nG = e.reflect_set_ghost_nodes()
+    assert nG == ref["pos"].shape[0] - nInt and nG > 0
+    got = e.download_state("rkCorrections", "volume")
+    assert np.abs(got["volume"] - ref["vol"]).max() <= 1e-14*np.abs(ref["vol"]).max()
+    scale = np.abs(ref["corr"]).max()
+    assert np.abs(got["rkCorrections"] - ref["corr"]).max() <= 1e-13*scale
+    # a copy would be wrong: the first plane flips the sign of B_x and d A / dx of its ghosts
+    ctl0 = lists[0]
+    g0 = ref["corr"][nInt:nInt + len(ctl0)]
+    assert np.abs(g0[:, 1] + corr[ctl0, 1]).max() <= 1e-13*scale and np.abs(corr[ctl0, 1]).max() > 1e-3*scale
+
+
 def test_enforce_maps_violators_back(mods):
     engine, _ = mods
     ndim = 2

@@ -115,3 +115,28 @@ def test_crk_sum_density_recovers_uniform_density(oracle):
     rho = oracle.crk_sum_density(ndim, W, len(mass), 0, pos, mass, vol, H, pi, pj)
     inner = np.all(np.abs(pos - 0.5) < 0.1, axis=1)
     assert inner.sum() > 8 and np.allclose(rho[inner], mass[inner]/vol[inner], rtol=1e-12)
+
+
+@pytest.mark.parametrize("ndim,n", [(1, 40), (2, 12), (3, 6)])
+def test_reflected_rk_coefficients_equal_those_of_the_mirror_image(oracle, ndim, n):
+    """ReflectingBoundary::applyGhostBoundary(Field<RKCoefficients>) (Boundary/ReflectingBoundary.cc:403-432) transforms the copied
+    coefficients with RKUtilities::getTransformationMatrix(R) (RK/RKUtilities.cc:637-715).  The restatement (nodegen.reflect_map,
+    "corr") against the truth: in a mirror-symmetric node set the corrections computed for the image of a node equal the transformed
+    corrections of the node itself -- a plain copy does not (B and grad A change sign along the normal)."""
+    nPerh = {1: 1.35, 2: 2.01, 3: 1.51}[ndim]
+    pos, mass, H, d = ng.lattice(ndim, n, nPerh=nPerh)
+    pos = ng.jitter(pos, 0.15, d, seed=9)
+    N = pos.shape[0]
+    W = oracle.TableKernel(oracle.KERNEL_BSPLINE, ndim, 200)
+    nhat = np.eye(ndim)[0]
+    R = np.eye(ndim) - 2.0*np.outer(nhat, nhat)
+    P2 = np.concatenate([pos, pos @ R.T])                            # the node set and its mirror image through x = 0
+    H2 = np.concatenate([H, ng.reflect_map(ndim, "H", H, np.zeros(N), nhat)])
+    pi, pj, cnt = oracle.pairs(ndim, 2*N, 0, P2, H2, W.kext)
+    vol = oracle.crk_sum_volume(ndim, W, 2*N, 0, P2, H2, pi, pj)
+    corr = oracle.crk_corrections(ndim, W, 2*N, 0, P2, H2, vol, pi, pj)
+    mapped = ng.reflect_map(ndim, "corr", corr[:N], np.zeros(N), nhat)
+    scale = np.abs(corr).max()
+    assert np.abs(mapped - corr[N:]).max() <= 1e-9*scale
+    near = pos[:, 0] < 2.0*d[0]*nPerh                                # nodes whose support crosses the plane are not symmetric themselves
+    assert np.abs(corr[:N][near] - corr[N:][near]).max() > 1e-3*scale
