@@ -176,6 +176,7 @@ struct UpdateArgs {
   const uint32_t* permEval; size_t nEval, capEval; uint32_t nInt;
   const double* deriv[DV_COUNT];
   double *pos, *vel, *H, *rho, *eps;
+  double* vol; const double* mass;                     // CRKSPH: the volume evolves with ContinuityVolumePolicy (null otherwise)
   double multiplier; int timeAdvanceOnly, epsDone;
   int hEvolution /*SPHB200_H_**/, HEvolution /*0 ideal 1 integrate 2 fixed*/;
   double rhoMin, rhoMax, hminInv, hmaxInv, hminratio;
@@ -196,11 +197,12 @@ __global__ void __launch_bounds__(RB) k_state_update(UpdateArgs a) {
     a.pos[o*DIM + q] += mult*a.deriv[DV_DXDT][(size_t)q*cap + s];
     a.vel[o*DIM + q] += mult*a.deriv[DV_DVDT][(size_t)q*cap + s];
   }
-  if (a.HEvolution == 2 || a.hEvolution == SPHB200_H_NONE) return;                         // FixedH
   double Hi[NS];
 #pragma unroll
   for (int q = 0; q < NS; ++q) Hi[q] = a.H[o*NS + q];
-  if (a.hEvolution == SPHB200_H_ASPH) {                                                    // IncrementASPHHtensor.cc:82-88
+  const bool fixedH = (a.HEvolution == 2 || a.hEvolution == SPHB200_H_NONE);                // FixedH
+  if (fixedH) {
+  } else if (a.hEvolution == SPHB200_H_ASPH) {                                                    // IncrementASPHHtensor.cc:82-88
 #pragma unroll
     for (int q = 0; q < NS; ++q) Hi[q] += mult*a.deriv[DV_DHDT][(size_t)q*cap + s];
     double lam[DIM], V[DIM*DIM];
@@ -221,8 +223,21 @@ __global__ void __launch_bounds__(RB) k_state_update(UpdateArgs a) {
     for (int q = 0; q < NS; ++q) Hi[q] = a.deriv[DV_HIDEAL][(size_t)q*cap + s];
     sym_bound<DIM>(Hi, a.hmaxInv, a.hminInv);
   }
+  if (!fixedH) {
 #pragma unroll
-  for (int q = 0; q < NS; ++q) a.H[o*NS + q] = Hi[q];
+    for (int q = 0; q < NS; ++q) a.H[o*NS + q] = Hi[q];
+  }
+  if (a.vol) {
+    // ContinuityVolumePolicy::update (RK/ContinuityVolumePolicy.cc:33-66; CRKSPHBase.cc:155 enrolls the volume with it).  It depends
+    // on the mass and the mass density, so it fires after the density update above; in timeAdvanceOnly mode the same expression
+    // runs (UpdatePolicyBase.hh:54-61).  safeInvVar: sgn(x)/max(1e-30, |x|) (Utilities/safeInv.hh:24-27).
+    const double m = a.mass[o], rhoN = a.rho[o];
+    const double rho2 = rhoN*rhoN;
+    const double volMin = 0.5*m*(d_sgn(rhoN)/fmax(1.0e-30, fabs(rhoN)));
+    const double volMax = ((DIM == 3) ? 4.0*M_PI/(3.0*sym_det<DIM>(Hi)) : M_PI/sym_det<DIM>(Hi));
+    const double dVdt = -m*(d_sgn(rho2)/fmax(1.0e-30, fabs(rho2)))*a.deriv[DV_DRHODT][s];
+    a.vol[o] = fmax(volMin, fmin(volMax, a.vol[o] + mult*dVdt));
+  }
 }
 
 // ---- iterateIdealH (Utilities/iterateIdealH.cc:120-190): one sweep H <- "new H" over the nodes not yet converged -----------------------
@@ -475,6 +490,7 @@ int sphb200_state_update(sphb200_ctx* c, const sphb200_step_options* so, double 
   for (int s = 0; s < DV_COUNT; ++s) a.deriv[s] = c->deriv[s];
   a.pos = c->api[S_POS]; a.vel = c->api[S_VEL]; a.H = c->api[S_H]; a.rho = c->api[S_RHO]; a.eps = c->api[S_EPS];
   a.multiplier = multiplier; a.timeAdvanceOnly = timeAdvanceOnly; a.epsDone = epsDone;
+  if (c->opt.hydro == SPHB200_HYDRO_CRKSPH && c->have[S_VOLUME] && c->have[S_MASS]) { a.vol = c->api[S_VOLUME]; a.mass = c->api[S_MASS]; }
   a.hEvolution = c->opt.hEvolution; a.HEvolution = so->HEvolution;
   a.rhoMin = so->rhoMin; a.rhoMax = so->rhoMax; a.hminInv = 1.0/c->opt.hmin; a.hmaxInv = 1.0/c->opt.hmax; a.hminratio = so->hminratio;
   const unsigned nb = (unsigned)((c->nEval + RB - 1)/RB);

@@ -106,8 +106,9 @@ class OracleRK2:
     (ghosts regenerated every step by nodegen.reflect_ghosts, refreshed by nodegen.reflect_apply)."""
 
     def __init__(self, orc, oo, so, OT, st, densityUpdate=1, gradhCorrection=True, dtMin=0.0, dtMax=1.0e100, dtGrowth=2.0,
-                 planes=None, nInt=None, crk=False):
+                 planes=None, nInt=None, crk=False, volume_policy=True):
         self.crk = crk
+        self.volume_policy = volume_policy
         if crk:
             gradhCorrection = False
         self.orc, self.oo, self.so, self.OT = orc, oo, so, OT
@@ -216,6 +217,17 @@ class OracleRK2:
             epsDone = True
         out = self.orc.state_update(self.oo, self.so, self.N, self.nGhost, mult, timeAdvanceOnly, d, self.s, epsDone=epsDone)
         self.s.update(out)
+        if self.crk and self.volume_policy:
+            # ContinuityVolumePolicy (RK/ContinuityVolumePolicy.cc:33-66; CRKSPHBase.cc:155 enrolls the volume with it): depends on mass
+            # and mass density, so it fires after the density update; the same in timeAdvanceOnly mode (UpdatePolicyBase.hh:54-61)
+            N, m, rho = self.N, self.s["mass"][:self.N], self.s["rho"][:self.N]
+            Hdet = np.linalg.det(ng.sym_to_full(self.ndim, self.s["H"][:N]))
+            volMax = {1: 2.0, 2: np.pi, 3: 4.0*np.pi/3.0}[self.ndim]/Hdet
+            inv = lambda x: np.where(x < 0.0, -1.0, 1.0)/np.maximum(1.0e-30, np.abs(x))     # safeInvVar (Utilities/safeInv.hh:24-27)
+            dVdt = -m*inv(rho*rho)*np.asarray(d["DrhoDt"])[:N]
+            vol = np.array(self.s["vol"], copy=True)
+            vol[:N] = np.maximum(0.5*m*inv(rho), np.minimum(volMax, vol[:N] + mult*dVdt))
+            self.s["vol"] = vol
 
     def _select_dt(self, maxTime):
         vote, why, node = self.orc.hydro_dt(self.oo, self.so, self.N, self.s["vel"], self.s["H"], self.s["rho"], self.s["cs"],

@@ -24,6 +24,13 @@ REF = {"Mass density": (0.05376370586899846, 0.01472935554844709, 1.655862722339
        "Velocity":     (0.024463871274705278, 0.008419536302504558, 0.8561295316236415),
        "Spec Therm E": (0.010557215425476638, 0.0033659949510588386, 0.355220540682649),
        "h":            (0.00043625606815746957, 0.00012010712699702793, 0.008480811209733824)}
+# LnormRef["CRKSPH"] (:241-255), produced with the options of ATS test t200 (:36):
+#   --hydroType CRKSPH --cfl 0.25 --KernelConstructor NBSplineKernel --order 7 --nPerh 1.01 --Cl 2.0 --Cq 1.0
+REF_CRKSPH = {"Mass density": (0.05064113393844768, 0.015297215762507312, 1.6768360873659973),
+              "Pressure":     (0.01687133903296828, 0.006328924998534429, 0.7822574604543725),
+              "Velocity":     (0.007746512026971996, 0.0029862099280521903, 0.20321897008372736),
+              "Spec Therm E": (0.005051748111924938, 0.0015094950940911932, 0.14418618728403587),
+              "h":            (0.00019175169182527455, 6.850786936014129e-05, 0.004376337346566557)}
 TOL = 1.0e-5                                    # Noh-planar-1d.py:181
 
 
@@ -57,26 +64,31 @@ def analytic(t, x, gamma, h0):
     return np.where(inside, 0.0, -1.0), u, rho, (gamma - 1.0)*u*rho, np.where(inside, h0/4.0, h0)
 
 
-def run(orc, first_step_sees_zero_derivatives=True, iterate_initial_H=True):
-    nx, nPerh, gamma, goal = 100, 1.35, 5.0/3.0, 0.6
+def run(orc, first_step_sees_zero_derivatives=True, iterate_initial_H=True, hydro="SPH", volume_policy=True):
+    """hydro = "CRKSPH": the set-up of ATS test t200 (NBSpline order 7, nPerh 1.01, cfl 0.25, Cl 2, Cq 1; CRKSPH/CRKSPHHydros.py: LinearOrder
+    corrections, LimitedMonaghanGingold Q; controller: RKSumVolume).  volume_policy: CRKSPHBase.cc:155 enrolls the volume with
+    ContinuityVolumePolicy (switchable only to show that the golden notices its absence)."""
+    crk = hydro == "CRKSPH"
+    nx, nPerh, gamma, goal = 100, (1.01 if crk else 1.35), 5.0/3.0, 0.6
     pos, mass, H, d = ng.lattice(1, nx, [0.0], [1.0], 1.0, nPerh)        # distributeNodesInRange1d: x = (i + 1/2) dx, H = 1/(nPerh dx)
     N = nx
     st = dict(position=pos, velocity=-np.ones((N, 1)), H=H, mass=mass, massDensity=np.ones(N), specificThermalEnergy=np.zeros(N),
               pressure=np.zeros(N), soundSpeed=np.zeros(N), omegaGradh=np.ones(N))
-    WT = orc.TableKernel(orc.KERNEL_NBSPLINE + 5, 1, 1000)
+    WT = orc.TableKernel(orc.KERNEL_NBSPLINE + (7 if crk else 5), 1, 1000)
     kext = WT.kext
-    oo = orc.default_options(1, nPerh=nPerh, Qkind=orc.Q_LIMITED_MG, Cl=2.0*(kext/2.0), Cq=2.0*(kext/2.0)**2, XSPH=0,
+    Cl, Cq = (2.0, 1.0) if crk else (2.0*(kext/2.0), 2.0*(kext/2.0)**2)
+    oo = orc.default_options(1, nPerh=nPerh, Qkind=orc.Q_LIMITED_MG, Cl=Cl, Cq=Cq, XSPH=0,
                              compatibleEnergy=1, correctVelocityGradient=1, hmin=1.0e-4, hmax=0.1)
-    so = orc.default_step_options(cfl=0.5)
+    so = orc.default_step_options(cfl=0.25 if crk else 0.5)
     rk = common.OracleRK2(orc, oo, so, WT, st, densityUpdate=1, planes=[(np.zeros(1), np.ones(1))], dtMin=1.0e-5, dtMax=0.1,
-                          dtGrowth=2.0)
+                          dtGrowth=2.0, crk=crk, volume_policy=volume_policy)
     rk.s["DvDxQ"] = np.zeros((N, 1))
     if iterate_initial_H:                          # Utilities/iterateIdealH.cc:120-200 for an isotropic ideal H
         done = np.zeros(N, dtype=bool)
         for _ in range(50):
             rk._set_ghosts()
             rk._pairs()
-            dd = orc.evaluate_derivatives(oo, WT, rk.s, N, rk.nGhost, rk.pi, rk.pj, rk.cnt)
+            dd = orc.evaluate_derivatives(oo, WT, rk.s, N, rk.nGhost, rk.pi, rk.pj, rk.cnt)      # the smoothing-scale package alone
             h1 = np.asarray(dd["Hideal"]).reshape(-1)[:N]
             delta = np.abs(h1/rk.s["H"][:N, 0] - 1.0)
             act = ~done
