@@ -64,7 +64,8 @@ def analytic(t, x, gamma, h0):
     return np.where(inside, 0.0, -1.0), u, rho, (gamma - 1.0)*u*rho, np.where(inside, h0/4.0, h0)
 
 
-def run(orc, first_step_sees_zero_derivatives=True, iterate_initial_H=True, hydro="SPH", volume_policy=True):
+def run(orc, first_step_sees_zero_derivatives=True, iterate_initial_H=True, hydro="SPH", volume_policy=True, overrides=None,
+        gradhCorrection=True):
     """hydro = "CRKSPH": the set-up of ATS test t200 (NBSpline order 7, nPerh 1.01, cfl 0.25, Cl 2, Cq 1; CRKSPH/CRKSPHHydros.py: LinearOrder
     corrections, LimitedMonaghanGingold Q; controller: RKSumVolume).  volume_policy: CRKSPHBase.cc:155 enrolls the volume with
     ContinuityVolumePolicy (switchable only to show that the golden notices its absence)."""
@@ -79,9 +80,11 @@ def run(orc, first_step_sees_zero_derivatives=True, iterate_initial_H=True, hydr
     Cl, Cq = (2.0, 1.0) if crk else (2.0*(kext/2.0), 2.0*(kext/2.0)**2)
     oo = orc.default_options(1, nPerh=nPerh, Qkind=orc.Q_LIMITED_MG, Cl=Cl, Cq=Cq, XSPH=0,
                              compatibleEnergy=1, correctVelocityGradient=1, hmin=1.0e-4, hmax=0.1)
+    for k, v in (overrides or {}).items():         # negative controls only
+        setattr(oo, k, v)
     so = orc.default_step_options(cfl=0.25 if crk else 0.5)
     rk = common.OracleRK2(orc, oo, so, WT, st, densityUpdate=1, planes=[(np.zeros(1), np.ones(1))], dtMin=1.0e-5, dtMax=0.1,
-                          dtGrowth=2.0, crk=crk, volume_policy=volume_policy)
+                          dtGrowth=2.0, crk=crk, volume_policy=volume_policy, gradhCorrection=gradhCorrection)
     rk.s["DvDxQ"] = np.zeros((N, 1))
     if iterate_initial_H:                          # Utilities/iterateIdealH.cc:120-200 for an isotropic ideal H
         done = np.zeros(N, dtype=bool)

@@ -8,6 +8,7 @@ is 1-D; the oracle's 1-D code differs from the 2-D / 3-D code the GPU engine is 
 of oracle/*_dim.inc (tensor algebra of one component), everything else is the same source.
 """
 import numpy as np
+import pytest
 
 import noh_planar_1d as noh
 
@@ -53,3 +54,14 @@ def test_the_crksph_golden_notices_a_missing_volume_policy(oracle):
     out, _ = noh.run(oracle, hydro="CRKSPH", volume_policy=False)
     rel = max(abs(out[k][0]/noh.REF_CRKSPH[k][0] - 1.0) for k in noh.REF_CRKSPH)
     assert 5.0e-4 < rel < 1.0e-1
+
+
+@pytest.mark.parametrize("what,kw", [("XSPH on", dict(overrides=dict(XSPH=1))),
+                                     ("no velocity-gradient correction", dict(overrides=dict(correctVelocityGradient=0))),
+                                     ("no grad-h correction", dict(gradhCorrection=False))])
+def test_the_golden_tells_the_options_of_the_reference_run_apart(oracle, what, kw):
+    """Discriminating power of the stored norms: any of the script's physics options flipped moves them by 6e-3 .. 0.7 relative,
+    three to five orders of magnitude more than the agreement of the faithful run."""
+    out, _ = noh.run(oracle, **kw)
+    rel = max(abs(got/want - 1.0) for name, ref in noh.REF.items() for got, want in zip(out[name], ref))
+    assert rel > 5.0e-3, (what, rel)
