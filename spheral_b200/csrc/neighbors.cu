@@ -701,6 +701,248 @@ __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build(NbrArgs a, int listRo
   }
 }
 
+// ---- K2, second version: flattened candidate stream (round 2) ------------------------------------------------------------------
+// Same inputs (the tile's candidate runs of k_tile_runs), same three-stage predicate, same lists in the same order as k_nbr_build,
+// restructured after the round-2 profile of the 8 M configuration (profiles/r02_notes.md): k_nbr_build spent its instructions on
+// candidates that no node of the tile can reach (924 tested per node for 85 hits) and on per-run overhead (a warp-uniform stage-2
+// loop over the union of the lanes' ambiguous candidates, a divergent list append per run).  Here
+//   * positions live in ONE frame per tile (relative to the cell of the tile's first node), so a candidate is placed once, when its
+//     run is loaded, and stage 1 needs no per-run set-up;
+//   * the lane that loads a candidate tests it against the bounding box of the tile's nodes grown by the reach of either side
+//     (|r| <= max(outer radius) is necessary for a pair) and only survivors enter a shared-memory ring; they are tested in full
+//     chunks of 32, whatever run they came from;
+//   * stage 2 is a per-lane loop over the lane's own ambiguous candidates.
+// A tile whose nodes straddle a jump of the Morton curve (cells more than one apart) is handled in passes, one per cluster of
+// lanes, so that every coordinate of a pass stays within four cell widths of its origin (the FP32 error model of k_pack).
+// Only used with a stencil radius of 1 (cells at least as wide as every kernel extent).
+constexpr int Q2_RING = 64;            // surviving candidates buffered per warp: two chunks of 32
+constexpr int Q2_FIXED = 5*Q2_RING*4 + Q2_RING*32 + Q2_RING + JB_CAP*4;   // bytes per warp in front of the per-chunk records
+constexpr int Q2_CHUNKB = 32*4 + 32*2; // per chunk of 32 survivors: one hit mask per lane + the survivors' list codes
+
+// Hits are not appended one by one: a chunk leaves one 32-bit hit mask per lane (bit c <-> survivor c of the chunk) and the list
+// codes of its survivors (run << 5 | position in the run); the lists are expanded from the masks when the tile's block of the
+// sliced-ELL array is written, whole 128-byte rows at a time.  (The per-hit append of k_nbr_build is a divergent loop -- 17
+// iterations per chunk for 4.5 hits per lane -- with a shared-memory load in its dependency chain: 26 % of the samples of the
+// first version of this kernel.)
+template <int DIM>
+__global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build2(NbrArgs a, int maxChunks) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const int w = threadIdx.x >> 5;
+  const size_t perWarp = (size_t)Q2_FIXED + (size_t)maxChunks*Q2_CHUNKB;
+  unsigned char* const wb = smemRaw + w*perWarp;
+  float* const qx = reinterpret_cast<float*>(wb);                    // SoA of the ring: tile-frame position, inner / outer radius^2
+  float* const qy = qx + Q2_RING; float* const qz = qy + Q2_RING; float* const qlo = qz + Q2_RING; float* const qhi = qlo + Q2_RING;
+  float* const qrow = qhi + Q2_RING;                                  // stage-2 record per entry: H (6), e2lo, e2hi
+  unsigned char* const qself = reinterpret_cast<unsigned char*>(qrow + 8*Q2_RING);    // bits 0-4: lane of this tile the candidate IS (0x1f with bit 5: none); bit 7: ghost
+  uint32_t* const sjb = reinterpret_cast<uint32_t*>(qself + Q2_RING);
+  uint32_t* const smask = sjb + JB_CAP;                               // [chunk][lane]
+  unsigned short* const scode = reinterpret_cast<unsigned short*>(smask + 32*(size_t)maxChunks);   // [chunk][survivor]
+
+  size_t tile, i; int lane, ci[3]; bool inRange, active; uint32_t origi;
+  if (!tile_prologue<DIM>(a, tile, lane, i, inRange, active, origi, ci)) return;
+  const uint32_t R = a.tileRunCount[tile];
+  const unsigned long long rs = a.tileRunStart[tile];
+  if (rs + R > a.runsCap || R >= 2048u) {                        // capacity miss: leave a consistent, empty tile; the host redoes the build
+    if (inRange) a.nbrCount[i] = 0;
+    if (lane == 0) { a.tileRows[tile] = 0; a.tileOff[tile] = 0; }
+    return;
+  }
+  float reli[3] = {0.f, 0.f, 0.f}, Hi[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, r2loi = -1.f, r2hii = 0.f, e2loi = 0.f, e2hii = 0.f;
+  const float4* __restrict__ frows4 = reinterpret_cast<const float4*>(a.frows);
+  if (inRange) {
+    const float4 q0 = frows4[i*4], q1 = frows4[i*4 + 1], q2 = frows4[i*4 + 2], q3 = frows4[i*4 + 3];
+    reli[0] = q0.x; reli[1] = q0.y; reli[2] = q0.z; r2loi = q0.w;
+    r2hii = q1.x; e2loi = q1.y; e2hii = q1.z;
+    if (DIM == 3) { Hi[0] = q2.x; Hi[1] = q2.y; Hi[2] = q2.z; Hi[3] = q2.w; Hi[4] = q3.x; Hi[5] = q3.y; }
+    else { Hi[0] = q2.x; Hi[1] = q2.y; Hi[2] = q2.z; }
+  }
+  const float csf[3] = {(float)a.g.cs[0], (float)a.g.cs[1], (float)a.g.cs[2]};
+  uint32_t cnt = 0, ghostHits = 0;
+  for (uint32_t r = lane; r < min(R, (uint32_t)JB_CAP); r += 32u) sjb[r] = __ldg(&a.runs[rs + r].x);
+  const uint32_t tile0 = (uint32_t)(tile*SPHB200_TILE);
+  const unsigned ltMask = (1u << lane) - 1u;
+  uint32_t qtail = 0;                                  // survivors so far (chunk = index >> 5, ring entry = index & 63)
+
+  for (unsigned unhandled = __ballot_sync(0xffffffffu, active); unhandled; ) {
+    // ---- one pass: the lanes whose cell is within one cell of the first unhandled lane's
+    const int L0 = __ffs(unhandled) - 1;
+    const int c0x = __shfl_sync(0xffffffffu, ci[0], L0), c0y = __shfl_sync(0xffffffffu, ci[1], L0), c0z = __shfl_sync(0xffffffffu, ci[2], L0);
+    const int kix = ci[0] - c0x, kiy = ci[1] - c0y, kiz = (DIM == 3) ? ci[2] - c0z : 0;
+    const bool inPass = ((unhandled >> lane) & 1u) && abs(kix) <= 1 && abs(kiy) <= 1 && abs(kiz) <= 1;
+    unhandled &= ~__ballot_sync(0xffffffffu, inPass);
+    // my node in the pass frame; lanes outside the pass sit at infinity and hit nothing
+    float pi[3];
+    pi[0] = inPass ? fmaf((float)kix, csf[0], reli[0]) : 1.0e30f;
+    pi[1] = fmaf((float)kiy, csf[1], reli[1]);
+    pi[2] = (DIM == 3) ? fmaf((float)kiz, csf[2], reli[2]) : 0.f;
+    // bounding box of the pass nodes (coordinates shifted to be positive: integer min / max of the bit patterns), grown by 1e-5
+    // cell widths (two orders above the FP32 error of the coordinates), and their largest outer radius
+    float blo[3] = {0.f, 0.f, 0.f}, bhi[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) {
+      const float sh = 2.0f*csf[q];
+      const unsigned v = __float_as_uint(pi[q] + sh);
+      blo[q] = __uint_as_float(__reduce_min_sync(0xffffffffu, inPass ? v : 0x7f000000u)) - sh - 1.0e-5f*csf[q];
+      bhi[q] = __uint_as_float(__reduce_max_sync(0xffffffffu, inPass ? v : 0u)) - sh + 1.0e-5f*csf[q];
+    }
+    const float r2reach = __uint_as_float(__reduce_max_sync(0xffffffffu, inPass ? __float_as_uint(fmaxf(r2hii, 0.f)) : 0u));
+    const unsigned long long bx2 = f2_pack(pi[0], pi[0]), by2 = f2_pack(pi[1], pi[1]), bz2 = f2_pack(pi[2], pi[2]);
+
+    uint32_t qhead = qtail;                            // a multiple of 32 here
+    // ---- chunk of up to 32 buffered candidates: stage 1 for every lane, stage 2 for the ambiguous ones, one hit mask per lane
+    auto process = [&](uint32_t first, uint32_t n) {
+      const uint32_t base = first & (Q2_RING - 1), chunk = first >> 5;
+      uint32_t hitWord = 0, inWord = 0;
+      for (uint32_t c4 = 0; c4 < n; c4 += 4u) {
+        const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(qx + base + c4), Y = *reinterpret_cast<const ulonglong2*>(qy + base + c4);   // broadcast
+        const float4 LO = *reinterpret_cast<const float4*>(qlo + base + c4), HI = *reinterpret_cast<const float4*>(qhi + base + c4);
+        const unsigned long long rxa = f2_sub(bx2, X.x), rxb = f2_sub(bx2, X.y), rya = f2_sub(by2, Y.x), ryb = f2_sub(by2, Y.y);
+        unsigned long long qa = f2_fma(rya, rya, f2_mul(rxa, rxa)), qb = f2_fma(ryb, ryb, f2_mul(rxb, rxb));
+        if (DIM == 3) {
+          const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(qz + base + c4);
+          const unsigned long long rza = f2_sub(bz2, Z.x), rzb = f2_sub(bz2, Z.y);
+          qa = f2_fma(rza, rza, qa); qb = f2_fma(rzb, rzb, qb);
+        }
+        float r2v[4];
+        f2_unpack(qa, r2v[0], r2v[1]); f2_unpack(qb, r2v[2], r2v[3]);
+        const float lo[4] = {LO.x, LO.y, LO.z, LO.w}, hi[4] = {HI.x, HI.y, HI.z, HI.w};
+        uint32_t hn = 0, in = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (r2v[u] <= fmaxf(r2loi, lo[u])) hn |= 1u << u;
+          if (r2v[u] <= fmaxf(r2hii, hi[u])) in |= 1u << u;
+        }
+        hitWord |= hn << c4; inWord |= in << c4;
+      }
+      if (n < 32u) { const uint32_t m = (1u << n) - 1u; hitWord &= m; inWord &= m; }
+      const uint32_t t = ((uint32_t)lane < n) ? (uint32_t)qself[base + lane] : 0x3fu;
+      // a node is not its own neighbour: the (at most 32 per tile) buffered entries that ARE nodes of this tile clear their lane's bit
+      for (unsigned sm = __ballot_sync(0xffffffffu, (t & 0x20u) == 0u); sm; sm &= sm - 1u) {
+        const int c = __ffs(sm) - 1;
+        const uint32_t L = __shfl_sync(0xffffffffu, t, c) & 0x1fu;
+        if ((uint32_t)lane == L) { hitWord &= ~(1u << c); inWord &= ~(1u << c); }
+      }
+      // stage 2: inside an outer sphere but no inner one -> the ellipsoids (FP32 with error band, else exact), lane by lane
+      uint32_t amb = inWord & ~hitWord;
+      while (__any_sync(0xffffffffu, amb != 0u)) {
+        if (amb) {
+          const uint32_t c = (uint32_t)(__ffs(amb) - 1);
+          amb &= amb - 1u;
+          const uint32_t e = base + c;
+          const float4 h0 = *reinterpret_cast<const float4*>(qrow + 8*e), h1 = *reinterpret_cast<const float4*>(qrow + 8*e + 4);
+          float rv[3], Hj[6];
+          rv[0] = pi[0] - qx[e]; rv[1] = pi[1] - qy[e]; rv[2] = pi[2] - qz[e];
+          if (DIM == 3) { Hj[0] = h0.x; Hj[1] = h0.y; Hj[2] = h0.z; Hj[3] = h0.w; Hj[4] = h1.x; Hj[5] = h1.y; }
+          else { Hj[0] = h0.x; Hj[1] = h0.y; Hj[2] = h0.z; }
+          const float e2i = eta2_f32<DIM>(Hi, rv), e2j = eta2_f32<DIM>(Hj, rv);
+          bool hit = (e2i <= e2loi) || (e2j <= h1.z);
+          if (!hit && !(e2i > e2hii && e2j > h1.w)) {
+            const uint32_t code = (chunk < (uint32_t)maxChunks) ? scode[32u*chunk + c] : 0u;
+            const uint32_t rr = code >> 5;
+            const uint32_t jb = (rr < (uint32_t)JB_CAP) ? sjb[rr] : __ldg(&a.runs[rs + rr].x);
+            hit = (chunk < (uint32_t)maxChunks) && exact_pair<DIM>(a.rows, i, (size_t)jb + (code & 31u), a.kext2);
+          }
+          if (hit) hitWord |= 1u << c;
+        }
+      }
+      const unsigned ghostWord = __ballot_sync(0xffffffffu, (t & 0x80u) != 0u);
+      cnt += __popc(hitWord);
+      ghostHits += __popc(hitWord & ghostWord);
+      if (chunk < (uint32_t)maxChunks) smask[32u*chunk + lane] = hitWord;
+      __syncwarp();
+    };
+
+    // ---- the runs: one lane per candidate, records two runs and rows one run ahead of their use
+    uint4 rec = (R > 0u) ? __ldg(a.runs + rs) : make_uint4(0u, 0u, 0u, 0u);
+    uint4 recN = (R > 1u) ? __ldg(a.runs + rs + 1u) : make_uint4(0u, 0u, 0u, 0u);
+    float4 p0, p1, p2, p3;
+    { const size_t c = (size_t)(rec.x + ((uint32_t)lane < rec.y ? lane : 0))*4; p0 = __ldg(frows4 + c); p1 = __ldg(frows4 + c + 1); p2 = __ldg(frows4 + c + 2); p3 = __ldg(frows4 + c + 3); }
+    for (uint32_t r = 0; r < R; ++r) {
+      const uint32_t jb = rec.x, len = rec.y;
+      const int kx = (int)(rec.z & 0xffffu) - c0x, ky = (int)(rec.z >> 16) - c0y, kz = (DIM == 3) ? (int)rec.w - c0z : 0;
+      const float4 c0 = p0, c1 = p1, c2 = p2, c3 = p3;
+      rec = recN;
+      if (r + 1u < R) {                                             // rows of the next run (its record arrived an iteration ago)
+        const size_t c = (size_t)(rec.x + ((uint32_t)lane < rec.y ? lane : 0))*4;
+        p0 = __ldg(frows4 + c); p1 = __ldg(frows4 + c + 1); p2 = __ldg(frows4 + c + 2); p3 = __ldg(frows4 + c + 3);
+      }
+      if (r + 2u < R) recN = __ldg(a.runs + rs + r + 2u);
+      // a pass node sits within one cell of the origin cell and reaches one cell further: runs beyond two cells are out of reach
+      if (abs(kx) > 2 || abs(ky) > 2 || abs(kz) > 2) continue;
+      float pj[3];
+      pj[0] = fmaf((float)kx, csf[0], c0.x); pj[1] = fmaf((float)ky, csf[1], c0.y); pj[2] = (DIM == 3) ? fmaf((float)kz, csf[2], c0.z) : 0.f;
+      float d2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < DIM; ++q) { const float d = fmaxf(fmaxf(blo[q] - pj[q], pj[q] - bhi[q]), 0.f); d2 = fmaf(d, d, d2); }
+      const bool keep = (uint32_t)lane < len && d2 <= fmaxf(r2reach, c1.x)*1.00001f;
+      const unsigned keepMask = __ballot_sync(0xffffffffu, keep);
+      if (keepMask == 0u) continue;
+      if (keep) {
+        const uint32_t sidx = qtail + (uint32_t)__popc(keepMask & ltMask);
+        const uint32_t e = sidx & (Q2_RING - 1);
+        const uint32_t slot = jb + (uint32_t)lane;
+        qx[e] = pj[0]; qy[e] = pj[1]; qz[e] = pj[2]; qlo[e] = c0.w; qhi[e] = c1.x;
+        *reinterpret_cast<float4*>(qrow + 8*e) = c2;
+        *reinterpret_cast<float4*>(qrow + 8*e + 4) = make_float4(c3.x, c3.y, c1.y, c1.z);
+        qself[e] = (unsigned char)(((slot - tile0 < 32u) ? (slot - tile0) : 0x3fu) | ((__float_as_uint(c1.w) >= a.nInt) ? 0x80u : 0u));
+        if ((sidx >> 5) < (uint32_t)maxChunks) scode[sidx] = (unsigned short)((r << 5) | (uint32_t)lane);
+      }
+      qtail += (uint32_t)__popc(keepMask);
+      if (qtail - qhead >= 32u) {
+        __syncwarp();
+        process(qhead, 32u);
+        qhead += 32u;
+      }
+    }
+    const uint32_t nLeft = qtail - qhead;
+    if (nLeft) {
+      // pad the last group of four with candidates at infinity
+      if ((uint32_t)lane >= nLeft && (uint32_t)lane < ((nLeft + 3u) & ~3u)) { const uint32_t e = (qhead & (Q2_RING - 1)) + lane; qx[e] = -1.0e30f; qy[e] = 0.f; qz[e] = 0.f; qlo[e] = -1.f; qhi[e] = -1.f; }
+      __syncwarp();
+      process(qhead, nLeft);
+      qtail = qhead + 32u;                             // the next pass starts a new chunk
+    }
+  }
+
+  const uint32_t nChunks = (qtail + 31u) >> 5;
+  if (inRange) a.nbrCount[i] = cnt;
+  uint32_t mx = cnt;
+  unsigned long long sAll = cnt, sGhost = ghostHits;
+  for (int d = 16; d; d >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    sAll += __shfl_xor_sync(0xffffffffu, sAll, d);
+    sGhost += __shfl_xor_sync(0xffffffffu, sGhost, d);
+  }
+  unsigned long long off = 0;
+  if (lane == 0) {
+    off = atomicAdd(&a.counters[3], (unsigned long long)mx*SPHB200_TILE);
+    a.tileRows[tile] = mx; a.tileOff[tile] = off;
+    if (sAll) atomicAdd(&a.counters[1], sAll);
+    if (sGhost) atomicAdd(&a.counters[0], sGhost);
+    atomicMax(&a.counters[4], (unsigned long long)mx);
+    atomicMax(&a.counters[6], (unsigned long long)nChunks);      // sizes the per-chunk records of the next build (too few -> host redoes)
+  }
+  off = __shfl_sync(0xffffffffu, off, 0);
+  if (off + (unsigned long long)mx*SPHB200_TILE > a.nbrCap || nChunks > (uint32_t)maxChunks) return;
+  __syncwarp();
+  // ---- expand the masks into the tile's block of the sliced-ELL array, row by row (row k: the k-th neighbour of every lane)
+  uint32_t* out = a.nbr + off + lane;
+  uint32_t ch = 0, m = (nChunks > 0u) ? smask[lane] : 0u;
+  for (uint32_t k = 0; k < mx; ++k) {
+    uint32_t slot = 0u;                                                       // padding entries point at slot 0 (never used)
+    if (k < cnt) {
+      while (m == 0u) { ++ch; m = smask[32u*ch + lane]; }
+      const uint32_t c = (uint32_t)(__ffs(m) - 1);
+      m &= m - 1u;
+      const uint32_t code = scode[32u*ch + c];
+      const uint32_t rr = code >> 5;
+      const uint32_t jb = (rr < (uint32_t)JB_CAP) ? sjb[rr] : __ldg(&a.runs[rs + rr].x);
+      slot = jb + (code & 31u);
+    }
+    out[(size_t)k*SPHB200_TILE] = slot;
+  }
+}
+
 // dilated (Morton) coordinate tables: dilTab[axis*SPHB200_DIL + c] = bits of c spread to the axis' key positions
 __global__ void __launch_bounds__(RB) k_dilate_table(GridDev g, uint32_t* __restrict__ tab) {
   const int c = blockIdx.x*RB + threadIdx.x;
@@ -800,6 +1042,11 @@ static int build_grid(sphb200_ctx* c, const double* bb /*lo3 hi3 ext3 sumext3*/)
   return 0;
 }
 
+static bool sphb200_nbr_v2_wanted() {
+  static const bool v = [] { const char* e = std::getenv("SPHB200_NBR_V2"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
 int sphb200_pack_rows(sphb200_ctx* c) {
   if (!c->sortValid) return sphb200_fail(c, "internal: pack_rows before sort");
   const bool tens = c->opt.epsTensile != 0.0;
@@ -827,7 +1074,10 @@ int sphb200_pack_rows(sphb200_ctx* c) {
     c->frowsCap = fcap; }
   a.frows = c->frows; a.g = c->grid;
   a.kext = std::max(c->W.kext, c->WQ.set ? c->WQ.kext : 0.0);
-  a.csmax = std::max(c->grid.cs[0], std::max(c->grid.cs[1], c->ndim == 3 ? c->grid.cs[2] : 0.0))*(3.0*c->stencilR + 4.0)/7.0;
+  // FP32 error of a reconstructed relative position, in units of 7 * 2^-24 cell widths: k*cs + rel_i - rel_j with |k| <= rad in
+  // k_nbr_build; k_nbr_build2 places both nodes in the frame of the tile (|k_i| <= 1, |k_j| <= 2): 12 * 2^-24, budgeted as 14
+  c->nbrV2 = sphb200_nbr_v2_wanted() && c->stencilR == 1 && !c->fineWalk;
+  a.csmax = std::max(c->grid.cs[0], std::max(c->grid.cs[1], c->ndim == 3 ? c->grid.cs[2] : 0.0))*(c->nbrV2 ? 2.0 : (3.0*c->stencilR + 4.0)/7.0);
   const unsigned nb = (unsigned)((c->n + RB - 1)/RB);
   if (c->ndim == 3) k_pack<3><<<nb, RB, 0, c->stream>>>(a); else k_pack<2><<<nb, RB, 0, c->stream>>>(a);
   KERNEL_CHECK(c, "k_pack");
@@ -935,15 +1185,22 @@ int sphb200_neighbors(sphb200_ctx* c) {
     KERNEL_CHECK(c, "k_tile_runs");
     // 2. the predicate, once per (node, candidate), and the sliced-ELL lists
     {
-      const size_t perWarp = (size_t)32*CROW*4 + (size_t)S1F*4 + (size_t)JB_CAP*4 + (size_t)c->listRows*64 + SPHB200_NBR_PAD;
+      if (c->nbrChunks <= 0) c->nbrChunks = (c->ndim == 3) ? 48 : 24;
+      const size_t perWarp = c->nbrV2 ? (size_t)Q2_FIXED + (size_t)c->nbrChunks*Q2_CHUNKB
+                                      : (size_t)32*CROW*4 + (size_t)S1F*4 + (size_t)JB_CAP*4 + (size_t)c->listRows*64 + SPHB200_NBR_PAD;
       int warps = NB_WARPS;
       while (warps > 1 && warps*perWarp > 220*1024) warps >>= 1;     // very long lists: fewer tiles per CTA
       if (perWarp > 220*1024)
         return sphb200_fail(c, "build_pairs: a node has more neighbours than the list staging can hold (H far too large for the node spacing?)");
       const size_t shm = warps*perWarp;
       const unsigned nbb = (unsigned)((c->nTiles + warps - 1)/warps);
-      if (c->ndim == 3) { CU_CHECK(c, cudaFuncSetAttribute(k_nbr_build<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); k_nbr_build<3><<<nbb, 32*warps, shm, c->stream>>>(a, c->listRows); }
-      else              { CU_CHECK(c, cudaFuncSetAttribute(k_nbr_build<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); k_nbr_build<2><<<nbb, 32*warps, shm, c->stream>>>(a, c->listRows); }
+      if (c->nbrV2) {
+        if (c->ndim == 3) { CU_CHECK(c, cudaFuncSetAttribute(k_nbr_build2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); k_nbr_build2<3><<<nbb, 32*warps, shm, c->stream>>>(a, c->nbrChunks); }
+        else              { CU_CHECK(c, cudaFuncSetAttribute(k_nbr_build2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); k_nbr_build2<2><<<nbb, 32*warps, shm, c->stream>>>(a, c->nbrChunks); }
+      } else {
+        if (c->ndim == 3) { CU_CHECK(c, cudaFuncSetAttribute(k_nbr_build<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); k_nbr_build<3><<<nbb, 32*warps, shm, c->stream>>>(a, c->listRows); }
+        else              { CU_CHECK(c, cudaFuncSetAttribute(k_nbr_build<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); k_nbr_build<2><<<nbb, 32*warps, shm, c->stream>>>(a, c->listRows); }
+      }
       KERNEL_CHECK(c, "k_nbr_build");
     }
     // one host round trip: totals and capacity check
@@ -952,7 +1209,8 @@ int sphb200_neighbors(sphb200_ctx* c) {
     const size_t needRuns = (size_t)c->countersHost[2], needNbr = (size_t)c->countersHost[3], needRows = (size_t)c->countersHost[4];
     if (c->countersHost[5] != 0ull) return 2;       // a tile has too many candidate runs for the list codes: the caller rebuilds with wide cells
     const bool okRuns = needRuns <= c->runsCap;
-    const bool okRows = needRows <= (size_t)c->listRows;
+    const size_t needChunks = (size_t)c->countersHost[6];
+    const bool okRows = c->nbrV2 ? needChunks <= (size_t)c->nbrChunks : needRows <= (size_t)c->listRows;
     const bool okNbr = okRuns && needNbr <= c->nbrCap;               // the list size is only known once the test ran everywhere
     if (okRuns && okRows && okNbr) {
       c->nEdges = (size_t)c->countersHost[1];
@@ -962,6 +1220,7 @@ int sphb200_neighbors(sphb200_ctx* c) {
       // staging for the next build: longest list + 1/8 (in an evolving problem the longest list grows from step to step, and a
       // build that overflows its staging is redone at full cost)
       c->listRows = (int)((needRows + needRows/8 + 8 + 7)/8*8);
+      if (c->nbrV2) c->nbrChunks = (int)(needChunks + needChunks/4 + 2);
       c->pairsValid = true;
       c->allIsotropic = (c->countersHost[8] == 0ull);       // k_pack of this build saw only H = h^-1 I
       c->stats.directed_edges = c->nEdges;
@@ -969,7 +1228,8 @@ int sphb200_neighbors(sphb200_ctx* c) {
     }
     if (!okRuns && sphb200_ensure(c, c->runs, c->runsCap, needRuns + needRuns/8)) return 1;
     if (okRuns && !okRows) {
-      c->listRows = (int)(needRows + needRows/8 + 16);
+      if (c->nbrV2) c->nbrChunks = (int)(needChunks + needChunks/4 + 4);
+      else c->listRows = (int)(needRows + needRows/8 + 16);
     }
     if (okRuns && needNbr > c->nbrCap && sphb200_ensure(c, c->nbr, c->nbrCap, needNbr + needNbr/8)) return 1;
   }

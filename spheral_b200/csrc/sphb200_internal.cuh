@@ -88,6 +88,7 @@ struct sphb200_ctx {
   // grid + sort
   GridDev grid{};
   GridDev gridFine{};               // two-level walk (experimental, SPHB200_FINE_WALK=1): the sort grid, cells of half the width; grid stays the coarse one
+  bool nbrV2 = false;               // the current rows were packed for k_nbr_build2 (tile-frame coordinates: wider FP32 error bands)
   bool fineWalk = false;            // the current sort used gridFine (keys, cellStart, dilTab refer to it; coarse key = fine key >> ndim)
   uint32_t* dilTab = nullptr;       // 3*SPHB200_DIL dilated cell coordinates
   uint32_t* cellKeyApi = nullptr;   // key per node, original order
@@ -130,6 +131,7 @@ struct sphb200_ctx {
   uint32_t* tileRunStart = nullptr; // per tile: first run
   uint32_t* tileRunCount = nullptr; // per tile: number of runs
   int listRows = 0;                 // rows of the shared-memory list staging of k_nbr_build (adapts to the longest list)
+  int nbrChunks = 0;                // k_nbr_build2: chunks of 32 surviving candidates a tile may record (adapts to the busiest tile)
   unsigned long long* counters = nullptr; // see NbrArgs::counters (8 entries)
   unsigned long long* countersHost = nullptr; // pinned
   size_t npairs = 0, nEdges = 0, nSlots = 0;
