@@ -724,7 +724,9 @@ constexpr int Q2_CHUNKB = 32*4 + 32*2; // per chunk of 32 survivors: one hit mas
 // sliced-ELL array is written, whole 128-byte rows at a time.  (The per-hit append of k_nbr_build is a divergent loop -- 17
 // iterations per chunk for 4.5 hits per lane -- with a shared-memory load in its dependency chain: 26 % of the samples of the
 // first version of this kernel.)
-template <int DIM>
+// STAGEH: the H tensors of the survivors are staged in the ring for stage 2.  When the previous build saw only isotropic H, stage 2
+// is a rarity (a 1e-5-wide shell) and fetches its two rows from global memory instead: 16 of ~31 LSU wavefronts per run less.
+template <int DIM, bool STAGEH>
 __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build2(NbrArgs a, int maxChunks) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int w = threadIdx.x >> 5;
@@ -829,7 +831,16 @@ __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build2(NbrArgs a, int maxCh
           const uint32_t c = (uint32_t)(__ffs(amb) - 1);
           amb &= amb - 1u;
           const uint32_t e = base + c;
-          const float4 h0 = *reinterpret_cast<const float4*>(qrow + 8*e), h1 = *reinterpret_cast<const float4*>(qrow + 8*e + 4);
+          float4 h0, h1;
+          size_t slotj = 0;
+          if (STAGEH) { h0 = *reinterpret_cast<const float4*>(qrow + 8*e); h1 = *reinterpret_cast<const float4*>(qrow + 8*e + 4); }
+          else {
+            const uint32_t code = (chunk < (uint32_t)maxChunks) ? scode[32u*chunk + c] : 0u;
+            const uint32_t rr = code >> 5;
+            slotj = (size_t)((rr < (uint32_t)JB_CAP) ? sjb[rr] : __ldg(&a.runs[rs + rr].x)) + (code & 31u);
+            const float4 g1 = __ldg(frows4 + slotj*4 + 1), g3 = __ldg(frows4 + slotj*4 + 3);
+            h0 = __ldg(frows4 + slotj*4 + 2); h1 = make_float4(g3.x, g3.y, g1.y, g1.z);
+          }
           float rv[3], Hj[6];
           rv[0] = pi[0] - qx[e]; rv[1] = pi[1] - qy[e]; rv[2] = pi[2] - qz[e];
           if (DIM == 3) { Hj[0] = h0.x; Hj[1] = h0.y; Hj[2] = h0.z; Hj[3] = h0.w; Hj[4] = h1.x; Hj[5] = h1.y; }
@@ -837,10 +848,12 @@ __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build2(NbrArgs a, int maxCh
           const float e2i = eta2_f32<DIM>(Hi, rv), e2j = eta2_f32<DIM>(Hj, rv);
           bool hit = (e2i <= e2loi) || (e2j <= h1.z);
           if (!hit && !(e2i > e2hii && e2j > h1.w)) {
-            const uint32_t code = (chunk < (uint32_t)maxChunks) ? scode[32u*chunk + c] : 0u;
-            const uint32_t rr = code >> 5;
-            const uint32_t jb = (rr < (uint32_t)JB_CAP) ? sjb[rr] : __ldg(&a.runs[rs + rr].x);
-            hit = (chunk < (uint32_t)maxChunks) && exact_pair<DIM>(a.rows, i, (size_t)jb + (code & 31u), a.kext2);
+            if (STAGEH) {
+              const uint32_t code = (chunk < (uint32_t)maxChunks) ? scode[32u*chunk + c] : 0u;
+              const uint32_t rr = code >> 5;
+              slotj = (size_t)((rr < (uint32_t)JB_CAP) ? sjb[rr] : __ldg(&a.runs[rs + rr].x)) + (code & 31u);
+            }
+            hit = (chunk < (uint32_t)maxChunks) && exact_pair<DIM>(a.rows, i, slotj, a.kext2);
           }
           if (hit) hitWord |= 1u << c;
         }
@@ -852,23 +865,18 @@ __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build2(NbrArgs a, int maxCh
       __syncwarp();
     };
 
-    // ---- the runs: one lane per candidate, records two runs and rows one run ahead of their use
-    uint4 rec = (R > 0u) ? __ldg(a.runs + rs) : make_uint4(0u, 0u, 0u, 0u);
-    uint4 recN = (R > 1u) ? __ldg(a.runs + rs + 1u) : make_uint4(0u, 0u, 0u, 0u);
-    float4 p0, p1, p2, p3;
-    { const size_t c = (size_t)(rec.x + ((uint32_t)lane < rec.y ? lane : 0))*4; p0 = __ldg(frows4 + c); p1 = __ldg(frows4 + c + 1); p2 = __ldg(frows4 + c + 2); p3 = __ldg(frows4 + c + 3); }
-    for (uint32_t r = 0; r < R; ++r) {
-      const uint32_t jb = rec.x, len = rec.y;
-      const int kx = (int)(rec.z & 0xffffu) - c0x, ky = (int)(rec.z >> 16) - c0y, kz = (DIM == 3) ? (int)rec.w - c0z : 0;
-      const float4 c0 = p0, c1 = p1, c2 = p2, c3 = p3;
-      rec = recN;
-      if (r + 1u < R) {                                             // rows of the next run (its record arrived an iteration ago)
-        const size_t c = (size_t)(rec.x + ((uint32_t)lane < rec.y ? lane : 0))*4;
-        p0 = __ldg(frows4 + c); p1 = __ldg(frows4 + c + 1); p2 = __ldg(frows4 + c + 2); p3 = __ldg(frows4 + c + 3);
-      }
-      if (r + 2u < R) recN = __ldg(a.runs + rs + r + 2u);
+    // ---- the runs: one lane per candidate, records two runs and rows one run ahead of their use (two register sets, A and B,
+    //      alternate: the rows of run r + 1 travel while run r is culled and queued)
+    auto load_rows = [&](const uint4& rc, float4& p0, float4& p1, float4& p2, float4& p3) {
+      const size_t c = (size_t)(rc.x + ((uint32_t)lane < rc.y ? lane : 0))*4;
+      p0 = __ldg(frows4 + c); p1 = __ldg(frows4 + c + 1);
+      if (STAGEH) { p2 = __ldg(frows4 + c + 2); p3 = __ldg(frows4 + c + 3); }
+    };
+    auto do_run = [&](uint32_t r, const uint4& rc, const float4& c0, const float4& c1, const float4& c2, const float4& c3) {
+      const uint32_t jb = rc.x, len = rc.y;
+      const int kx = (int)(rc.z & 0xffffu) - c0x, ky = (int)(rc.z >> 16) - c0y, kz = (DIM == 3) ? (int)rc.w - c0z : 0;
       // a pass node sits within one cell of the origin cell and reaches one cell further: runs beyond two cells are out of reach
-      if (abs(kx) > 2 || abs(ky) > 2 || abs(kz) > 2) continue;
+      if (abs(kx) > 2 || abs(ky) > 2 || abs(kz) > 2) return;
       float pj[3];
       pj[0] = fmaf((float)kx, csf[0], c0.x); pj[1] = fmaf((float)ky, csf[1], c0.y); pj[2] = (DIM == 3) ? fmaf((float)kz, csf[2], c0.z) : 0.f;
       float d2 = 0.f;
@@ -876,14 +884,16 @@ __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build2(NbrArgs a, int maxCh
       for (int q = 0; q < DIM; ++q) { const float d = fmaxf(fmaxf(blo[q] - pj[q], pj[q] - bhi[q]), 0.f); d2 = fmaf(d, d, d2); }
       const bool keep = (uint32_t)lane < len && d2 <= fmaxf(r2reach, c1.x)*1.00001f;
       const unsigned keepMask = __ballot_sync(0xffffffffu, keep);
-      if (keepMask == 0u) continue;
+      if (keepMask == 0u) return;
       if (keep) {
         const uint32_t sidx = qtail + (uint32_t)__popc(keepMask & ltMask);
         const uint32_t e = sidx & (Q2_RING - 1);
         const uint32_t slot = jb + (uint32_t)lane;
         qx[e] = pj[0]; qy[e] = pj[1]; qz[e] = pj[2]; qlo[e] = c0.w; qhi[e] = c1.x;
-        *reinterpret_cast<float4*>(qrow + 8*e) = c2;
-        *reinterpret_cast<float4*>(qrow + 8*e + 4) = make_float4(c3.x, c3.y, c1.y, c1.z);
+        if (STAGEH) {
+          *reinterpret_cast<float4*>(qrow + 8*e) = c2;
+          *reinterpret_cast<float4*>(qrow + 8*e + 4) = make_float4(c3.x, c3.y, c1.y, c1.z);
+        }
         qself[e] = (unsigned char)(((slot - tile0 < 32u) ? (slot - tile0) : 0x3fu) | ((__float_as_uint(c1.w) >= a.nInt) ? 0x80u : 0u));
         if ((sidx >> 5) < (uint32_t)maxChunks) scode[sidx] = (unsigned short)((r << 5) | (uint32_t)lane);
       }
@@ -893,6 +903,22 @@ __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build2(NbrArgs a, int maxCh
         process(qhead, 32u);
         qhead += 32u;
       }
+    };
+    uint4 recA = (R > 0u) ? __ldg(a.runs + rs) : make_uint4(0u, 0u, 0u, 0u);
+    uint4 recB = (R > 1u) ? __ldg(a.runs + rs + 1u) : make_uint4(0u, 0u, 0u, 0u);
+    float4 a0, a1, a2, a3, b0, b1, b2, b3;
+    a0 = a1 = a2 = a3 = b0 = b1 = b2 = b3 = make_float4(0.f, 0.f, 0.f, 0.f);
+    load_rows(recA, a0, a1, a2, a3);
+    for (uint32_t r = 0; r < R; r += 2u) {
+      if (r + 1u < R) load_rows(recB, b0, b1, b2, b3);
+      const uint4 rcA = recA;
+      if (r + 2u < R) recA = __ldg(a.runs + rs + r + 2u);
+      do_run(r, rcA, a0, a1, a2, a3);
+      if (r + 1u >= R) break;
+      if (r + 2u < R) load_rows(recA, a0, a1, a2, a3);
+      const uint4 rcB = recB;
+      if (r + 3u < R) recB = __ldg(a.runs + rs + r + 3u);
+      do_run(r + 1u, rcB, b0, b1, b2, b3);
     }
     const uint32_t nLeft = qtail - qhead;
     if (nLeft) {
@@ -925,21 +951,33 @@ __global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build2(NbrArgs a, int maxCh
   off = __shfl_sync(0xffffffffu, off, 0);
   if (off + (unsigned long long)mx*SPHB200_TILE > a.nbrCap || nChunks > (uint32_t)maxChunks) return;
   __syncwarp();
-  // ---- expand the masks into the tile's block of the sliced-ELL array, row by row (row k: the k-th neighbour of every lane)
+  // ---- expand the masks into the tile's block of the sliced-ELL array, row by row (row k: the k-th neighbour of every lane),
+  //      four rows per trip so that the shared-memory look-ups of different rows overlap
   uint32_t* out = a.nbr + off + lane;
   uint32_t ch = 0, m = (nChunks > 0u) ? smask[lane] : 0u;
-  for (uint32_t k = 0; k < mx; ++k) {
-    uint32_t slot = 0u;                                                       // padding entries point at slot 0 (never used)
-    if (k < cnt) {
-      while (m == 0u) { ++ch; m = smask[32u*ch + lane]; }
-      const uint32_t c = (uint32_t)(__ffs(m) - 1);
-      m &= m - 1u;
-      const uint32_t code = scode[32u*ch + c];
-      const uint32_t rr = code >> 5;
-      const uint32_t jb = (rr < (uint32_t)JB_CAP) ? sjb[rr] : __ldg(&a.runs[rs + rr].x);
-      slot = jb + (code & 31u);
+  for (uint32_t k = 0; k < mx; k += 4u) {
+    uint32_t idx[4], slot[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      idx[u] = 0xffffffffu;
+      if (k + u < cnt) {
+        while (m == 0u) { ++ch; m = smask[32u*ch + lane]; }
+        idx[u] = 32u*ch + (uint32_t)(__ffs(m) - 1);
+        m &= m - 1u;
+      }
     }
-    out[(size_t)k*SPHB200_TILE] = slot;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) slot[u] = (idx[u] != 0xffffffffu) ? (uint32_t)scode[idx[u]] : 0xffffffffu;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t code = slot[u];
+      uint32_t sl = 0u;                                                         // padding entries point at slot 0 (never used)
+      if (code != 0xffffffffu) {
+        const uint32_t rr = code >> 5;
+        sl = ((rr < (uint32_t)JB_CAP) ? sjb[rr] : __ldg(&a.runs[rs + rr].x)) + (code & 31u);
+      }
+      if (k + u < mx) out[(size_t)(k + u)*SPHB200_TILE] = sl;
+    }
   }
 }
 
@@ -1195,8 +1233,14 @@ int sphb200_neighbors(sphb200_ctx* c) {
       const size_t shm = warps*perWarp;
       const unsigned nbb = (unsigned)((c->nTiles + warps - 1)/warps);
       if (c->nbrV2) {
-        if (c->ndim == 3) { CU_CHECK(c, cudaFuncSetAttribute(k_nbr_build2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); k_nbr_build2<3><<<nbb, 32*warps, shm, c->stream>>>(a, c->nbrChunks); }
-        else              { CU_CHECK(c, cudaFuncSetAttribute(k_nbr_build2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); k_nbr_build2<2><<<nbb, 32*warps, shm, c->stream>>>(a, c->nbrChunks); }
+        // the H tensors of the candidates are staged for stage 2 unless the previous build saw isotropic H only (a hint, not a promise:
+        // both variants decide every pair correctly, the unstaged one merely pays a global fetch per ambiguous candidate)
+        const bool stageH = !c->isoHint;
+#define SPHB200_LAUNCH_NB2(D, S) do { CU_CHECK(c, cudaFuncSetAttribute(k_nbr_build2<D, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); \
+                                       k_nbr_build2<D, S><<<nbb, 32*warps, shm, c->stream>>>(a, c->nbrChunks); } while (0)
+        if (c->ndim == 3) { if (stageH) SPHB200_LAUNCH_NB2(3, true); else SPHB200_LAUNCH_NB2(3, false); }
+        else              { if (stageH) SPHB200_LAUNCH_NB2(2, true); else SPHB200_LAUNCH_NB2(2, false); }
+#undef SPHB200_LAUNCH_NB2
       } else {
         if (c->ndim == 3) { CU_CHECK(c, cudaFuncSetAttribute(k_nbr_build<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); k_nbr_build<3><<<nbb, 32*warps, shm, c->stream>>>(a, c->listRows); }
         else              { CU_CHECK(c, cudaFuncSetAttribute(k_nbr_build<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); k_nbr_build<2><<<nbb, 32*warps, shm, c->stream>>>(a, c->listRows); }
@@ -1223,6 +1267,7 @@ int sphb200_neighbors(sphb200_ctx* c) {
       if (c->nbrV2) c->nbrChunks = (int)(needChunks + needChunks/4 + 2);
       c->pairsValid = true;
       c->allIsotropic = (c->countersHost[8] == 0ull);       // k_pack of this build saw only H = h^-1 I
+      c->isoHint = c->allIsotropic;
       c->stats.directed_edges = c->nEdges;
       return 0;
     }

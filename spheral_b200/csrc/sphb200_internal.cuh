@@ -118,6 +118,7 @@ struct sphb200_ctx {
   uint32_t* cellReach = nullptr; size_t cellReachCap = 0;   // per cell: stencil radius tiles of that cell must walk
   uint32_t* tileRadius = nullptr; size_t tileRadiusCap = 0;
   bool allIsotropic = false;        // every H packed at the last build_pairs was a multiple of the identity (k_pack; read back with the counters)
+  bool isoHint = false;             // allIsotropic of the last completed build: tuning hint for the next one (never a correctness input)
   bool rowsValid = false;           // rows reflect current api state for the current sort
   bool sortValid = false;
 
