@@ -178,9 +178,12 @@ __global__ void __launch_bounds__(RB) k_reflect_fill(double* __restrict__ f, int
   }
 }
 
-// enforceBoundary: internal nodes behind a plane (signed distance < 0) are mirrored back, their velocity reflected
+// enforceBoundary: internal nodes behind a plane (signed distance < 0) are mirrored back, their velocity reflected and -- for a
+// reflecting plane -- their H tensor as well: PlanarBoundary::updateViolationNodes (PlanarBoundary.cc:179-195) calls
+// enforceBoundary on the position, the velocity AND the H field; ReflectingBoundary::enforceBoundary(Field<SymTensor>)
+// (ReflectingBoundary.cc:493-501) maps H -> (R H R).Symmetric(), which only matters for anisotropic (ASPH) tensors.
 template <int DIM>
-__global__ void __launch_bounds__(RB) k_reflect_enforce(double* __restrict__ pos, double* __restrict__ vel, size_t nInt, Plane pl,
+__global__ void __launch_bounds__(RB) k_reflect_enforce(double* __restrict__ pos, double* __restrict__ vel, double* __restrict__ H, size_t nInt, Plane pl,
                                                         unsigned long long* __restrict__ nViolations) {
   const size_t i = (size_t)blockIdx.x*RB + threadIdx.x;
   if (i >= nInt) return;
@@ -197,6 +200,26 @@ __global__ void __launch_bounds__(RB) k_reflect_enforce(double* __restrict__ pos
   if (!pl.periodic) {                                // ReflectingBoundary::enforceBoundary(velocity): v -> R v
 #pragma unroll
     for (int q = 0; q < DIM; ++q) vel[i*DIM + q] -= 2.0*vn*pl.n[q];
+    if (H) {                                         // H -> (R H R).Symmetric(), R = I - 2 n (x) n
+      constexpr int NS = Dm<DIM>::NS;
+      double T[DIM][DIM], O[DIM][DIM], Hn[DIM], nHn = 0.0;
+      const double* s = H + i*NS;
+      if (DIM == 3) { T[0][0] = s[0]; T[0][1] = T[1][0] = s[1]; T[0][DIM - 1] = T[DIM - 1][0] = s[2]; T[1][1] = s[3]; T[1][DIM - 1] = T[DIM - 1][1] = s[4]; T[DIM - 1][DIM - 1] = s[5]; }
+      else { T[0][0] = s[0]; T[0][1] = T[1][0] = s[1]; T[1][1] = s[2]; }
+#pragma unroll
+      for (int a = 0; a < DIM; ++a) { double t = 0.0;
+#pragma unroll
+        for (int b = 0; b < DIM; ++b) t += T[a][b]*pl.n[b];
+        Hn[a] = t; nHn += pl.n[a]*t; }
+      // R H R = H - 2 n (Hn)^T - 2 (Hn) n^T + 4 (n.Hn) n n^T   (H symmetric: the result is symmetric up to round-off)
+#pragma unroll
+      for (int a = 0; a < DIM; ++a)
+#pragma unroll
+        for (int b = 0; b < DIM; ++b) O[a][b] = T[a][b] - 2.0*pl.n[a]*Hn[b] - 2.0*Hn[a]*pl.n[b] + 4.0*nHn*pl.n[a]*pl.n[b];
+      double* d = H + i*NS;
+      if (DIM == 3) { d[0] = O[0][0]; d[1] = 0.5*(O[0][1] + O[1][0]); d[2] = 0.5*(O[0][DIM - 1] + O[DIM - 1][0]); d[3] = O[1][1]; d[4] = 0.5*(O[1][DIM - 1] + O[DIM - 1][1]); d[5] = O[DIM - 1][DIM - 1]; }
+      else { d[0] = O[0][0]; d[1] = 0.5*(O[0][1] + O[1][0]); d[2] = O[1][1]; }
+    }
   }
   atomicAdd(nViolations, 1ull);
 }
@@ -381,8 +404,8 @@ int sphb200_reflect_enforce(sphb200_ctx* c, size_t* nViolations) {
   const unsigned nb = (unsigned)((c->nInt + RB - 1)/RB);
   for (int p = 0; p < c->nPlanes; ++p) {
     const Plane pl = plane_of(c, p);
-    if (c->ndim == 3) k_reflect_enforce<3><<<nb, RB, 0, c->stream>>>(c->api[S_POS], c->api[S_VEL], c->nInt, pl, c->counters + 7);
-    else              k_reflect_enforce<2><<<nb, RB, 0, c->stream>>>(c->api[S_POS], c->api[S_VEL], c->nInt, pl, c->counters + 7);
+    if (c->ndim == 3) k_reflect_enforce<3><<<nb, RB, 0, c->stream>>>(c->api[S_POS], c->api[S_VEL], c->have[S_H] ? c->api[S_H] : nullptr, c->nInt, pl, c->counters + 7);
+    else              k_reflect_enforce<2><<<nb, RB, 0, c->stream>>>(c->api[S_POS], c->api[S_VEL], c->have[S_H] ? c->api[S_H] : nullptr, c->nInt, pl, c->counters + 7);
     KERNEL_CHECK(c, "k_reflect_enforce");
   }
   c->rowsValid = false;

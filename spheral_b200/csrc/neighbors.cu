@@ -1080,9 +1080,9 @@ static int build_grid(sphb200_ctx* c, const double* bb /*lo3 hi3 ext3 sumext3*/)
   return 0;
 }
 
-static bool sphb200_nbr_v2_wanted() {
-  static const bool v = [] { const char* e = std::getenv("SPHB200_NBR_V2"); return !(e && e[0] == '0'); }();
-  return v;
+static bool sphb200_nbr_v2_wanted() {          // read at every build: the tests switch between the two builders inside one process
+  const char* e = std::getenv("SPHB200_NBR_V2");
+  return !(e && e[0] == '0');
 }
 
 int sphb200_pack_rows(sphb200_ctx* c) {

@@ -540,8 +540,14 @@ int sphb200_iterate_ideal_h(sphb200_ctx* c, int firstSweep, double tolerance, do
   if (!c->derivsValid || !c->pairsValid) return sphb200_fail(c, "iterate_ideal_h: needs the derivatives ('new H') of the current connectivity");
   if (maxDeltaH) *maxDeltaH = 0.0;
   if (c->nInt == 0) return 0;
-  if (sphb200_ensure(c, c->hDone, c->hDoneCap, c->cap)) return 1;
-  if (firstSweep) CU_CHECK(c, cudaMemsetAsync(c->hDone, 0, c->cap*sizeof(uint32_t), c->stream));
+  // one flag per INTERNAL node (the only entries used); the number of internal nodes cannot change between the sweeps of one
+  // relaxation, so the flags of earlier sweeps survive whatever the ghost set does to the node capacity
+  if (!firstSweep && (!c->hDone || c->hDoneCap < c->nInt))
+    return sphb200_fail(c, "iterate_ideal_h: the number of internal nodes grew since the first sweep (start again with firstSweep = 1)");
+  if (firstSweep) {
+    if (sphb200_ensure(c, c->hDone, c->hDoneCap, c->nInt)) return 1;
+    CU_CHECK(c, cudaMemsetAsync(c->hDone, 0, c->nInt*sizeof(uint32_t), c->stream));
+  }
   CU_CHECK(c, cudaMemsetAsync(c->counters + 9, 0, sizeof(unsigned long long), c->stream));
   const unsigned nb = (unsigned)((c->n + RB - 1)/RB);
   if (c->ndim == 3) k_iterate_h<3><<<nb, RB, 0, c->stream>>>(c->perm, c->n, c->cap, (uint32_t)c->nInt, c->deriv[DV_HIDEAL], c->api[S_H], c->hDone, tolerance, c->counters + 9);

@@ -146,6 +146,8 @@ class OracleRK2:
             bad = np.nonzero(sd < 0.0)[0]
             self.s["pos"][bad] -= 2.0*np.outer(sd[bad], nhat)
             self.s["vel"][bad] -= 2.0*np.outer(self.s["vel"][bad] @ nhat, nhat)
+            if len(bad):      # PlanarBoundary::updateViolationNodes also enforces the boundary on H (PlanarBoundary.cc:193-195)
+                self.s["H"][bad] = ng.reflect_map(self.ndim, "H", self.s["H"][bad], sd[bad], nhat)
 
     # -- pieces ------------------------------------------------------------------------------------------------------------
     def _pairs(self):

@@ -124,6 +124,37 @@ def test_enforce_maps_violators_back(mods):
     assert e.reflect_enforce(count=True) == 0
 
 
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_enforce_reflects_the_H_tensor_of_violation_nodes(mods, ndim):
+    """PlanarBoundary::updateViolationNodes (PlanarBoundary.cc:179-195) enforces the boundary on position, velocity AND H;
+    ReflectingBoundary::enforceBoundary(Field<SymTensor>) (ReflectingBoundary.cc:493-501) maps H -> (R H R).Symmetric().  An oblique
+    plane and anisotropic (ASPH) tensors make the difference visible."""
+    engine, _ = mods
+    st, nInt, _ = common.make_problem(ndim, 7 if ndim == 3 else 12, nPerh=1.51, kind="aniso", seed=5)
+    nrm = np.array([1.0, 0.7, -0.4][:ndim]); nrm /= np.linalg.norm(nrm)
+    point = np.full(ndim, 0.5)
+    e = engine.Engine(ndim, nPerh=1.51, hEvolution=1)
+    e.set_kernel_table(K.TableKernel(K.BSplineKernel(ndim), 1000))
+    e.set_nodes(nInt, 0)
+    e.upload_state(**st)
+    e.reflect_configure([(point, nrm)])
+    sd = (st["position"] - point) @ nrm
+    bad = np.nonzero(sd < 0.0)[0]
+    assert 0 < len(bad) < nInt
+    assert e.reflect_enforce(count=True) == len(bad)
+    got = e.download_state("position", "velocity", "H")
+    ref = {k: st[k].copy() for k in ("position", "velocity", "H")}
+    ref["position"][bad] -= 2.0*np.outer(sd[bad], nrm)
+    ref["velocity"][bad] -= 2.0*np.outer(st["velocity"][bad] @ nrm, nrm)
+    ref["H"][bad] = ng.reflect_map(ndim, "H", st["H"][bad], sd[bad], nrm)
+    for k in ref:
+        assert np.abs(got[k] - ref[k]).max() <= 1e-13*np.abs(ref[k]).max(), k
+    # the reflected tensors really differ from the originals (the old behaviour), and untouched nodes keep theirs bit for bit
+    assert np.abs(got["H"][bad] - st["H"][bad]).max() > 1e-3*np.abs(st["H"]).max()
+    good = np.setdiff1d(np.arange(nInt), bad)
+    assert np.array_equal(got["H"][good], st["H"][good])
+
+
 def noh_2d(nRadial, nPerh):
     pos, mass, H = ng.constant_dtheta_2d(nRadial, nPerh=nPerh)
     N = len(pos)
