@@ -454,7 +454,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="noh8m")
-    ap.add_argument("--n", type=int, default=0, help="override lattice points per side (debug)")
+    ap.add_argument("--nside", type=int, default=0, help="override lattice points per side (debug)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="lattice points per side of the bounded CPU sample (default: per workload)")
     ap.add_argument("--xsph", type=int, default=0, help="1: XSPH on (the round-1 bench setting; the stock scripts run with XSPH=False)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -465,7 +465,7 @@ def main():
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     spec = workload_spec(args.workload)
-    n = args.n or spec["n"]
+    n = args.nside or spec["n"]
     threads = os.cpu_count() or 1
     world_env = int(os.environ.get("WORLD_SIZE", "1"))
     config = bench_config(spec, max(world_env, 1) if args.impl == "ours" else max(args.gpus, 1), n)
@@ -588,7 +588,7 @@ def main():
         traffic, traffic_src = None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            ent = tj.get(args.workload if (not args.n and world == 1 and not args.xsph) else "", {})
+            ent = tj.get(args.workload if (not args.nside and world == 1 and not args.xsph) else "", {})
             key = "k_crk_derivs" if crk else "k_sph_derivs"
             if key in ent:
                 traffic = float(ent[key]["dram_bytes_read"]) + float(ent[key]["dram_bytes_write"])

@@ -129,6 +129,11 @@ int  sphb200_table_kernel_build(int kind, int ndim, size_t numPoints, double min
    Integrator stages until re-uploaded). */
 int  sphb200_set_nodes(sphb200_ctx* ctx, size_t nInternal, size_t nGhost);
 int  sphb200_upload_state(sphb200_ctx* ctx, unsigned fieldMask, const sphb200_host_state* s);
+/* The same copy, but the pair lists on the device stay valid even if positions / H are among the fields: a package evaluated
+   in the middle of a step works on the ConnectivityMap of the step start although the nodes have moved since
+   (CheapSynchronousRK2.cc:76-99: state.update, then evaluateDerivatives, no neighbour update in between).
+   replaces: the State<Dim>::fields(name) reads of a mid-step evaluateDerivatives / postStateUpdate. */
+int  sphb200_upload_state_values(sphb200_ctx* ctx, unsigned fieldMask, const sphb200_host_state* s);
 int  sphb200_download_state(sphb200_ctx* ctx, unsigned fieldMask, double* const* fields /* same order as struct */);
 
 /* ---- neighbour pairs ---------------------------------------------------------------------------------------
@@ -139,6 +144,11 @@ int  sphb200_build_pairs(sphb200_ctx* ctx, size_t* npairs);
 /* 1 if the pair lists on the device match the positions / H there (no upload or halo landing of either since the last build);
    the role of DataBase::connectivityMap() being current.  No device work. */
 int  sphb200_connectivity_valid(const sphb200_ctx* ctx);
+/* Mask (SPHB200_STATE_* bits) of the state fields that currently hold values on the device, whether uploaded, received as ghosts or
+   produced there (sphb200_copy_DvDx_to_Q, the CRKSPH volumes ...).  The boundary conditions apply to every field REGISTERED in the
+   State (Integrator::applyGhostBoundaries, Integrator.cc:530-570; ArtificialViscosityHandle.cc:105-119 registers the Q's velocity
+   gradient and Cl / Cq multipliers): a halo exchange asks here which fields must travel.  No device work. */
+unsigned sphb200_state_fields_present(const sphb200_ctx* ctx);
 /* NodePairList in the reference order (NodePairIdxType::operator<, NodePairIdxType.hh:34-58): sorted (i,j), i<j. */
 int  sphb200_download_pairs(sphb200_ctx* ctx, uint32_t* i, uint32_t* j, size_t cap);
 /* ConnectivityMap::numNeighborsForNode for internal nodes (ConnectivityMapInline.hh) */

@@ -20,5 +20,5 @@ echo "== ncu launch list (default bench)"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_list.log 2>&1; echo "rc=$?"
 echo "== ncu full"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_sph_derivs|k_nbr_build|k_tile_runs|k_pack' -s 8 -c 4 -f -o $OUT/prof python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1; echo "rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_crk_derivs|k_crk_corrections|k_crk_volume' -s 9 -c 3 -f -o $OUT/prof_crk python bench.py --workload crksph4m --n 100 --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_crk.log 2>&1; echo "rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_crk_derivs|k_crk_corrections|k_crk_volume' -s 9 -c 3 -f -o $OUT/prof_crk python bench.py --workload crksph4m --nside 100 --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_crk.log 2>&1; echo "rc=$?"
 ls -la $OUT | head -30

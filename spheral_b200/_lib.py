@@ -91,7 +91,7 @@ class Stats(C.Structure):
 
 EXPORTS = ("sphb200_abi_version", "sphb200_create", "sphb200_destroy", "sphb200_set_options", "sphb200_last_error",
            "sphb200_sync", "sphb200_set_kernel_table", "sphb200_table_ncoef", "sphb200_table_kernel_build",
-           "sphb200_set_nodes", "sphb200_upload_state", "sphb200_download_state", "sphb200_build_pairs",
+           "sphb200_set_nodes", "sphb200_upload_state", "sphb200_upload_state_values", "sphb200_download_state", "sphb200_build_pairs",
            "sphb200_download_pairs", "sphb200_download_neighbor_counts", "sphb200_evaluate_derivatives",
            "sphb200_download_derivs", "sphb200_download_pair_accelerations", "sphb200_copy_DvDx_to_Q",
            "sphb200_update_energy_compatible", "sphb200_halo_bytes_per_node", "sphb200_halo_pack",
@@ -102,7 +102,7 @@ EXPORTS = ("sphb200_abi_version", "sphb200_create", "sphb200_destroy", "sphb200_
            "sphb200_state_assign", "sphb200_state_update", "sphb200_compute_dt",
            "sphb200_reflect_configure", "sphb200_reflect_set_ghost_nodes", "sphb200_reflect_apply_ghosts", "sphb200_reflect_enforce",
            "sphb200_reflect_finalize_derivatives", "sphb200_halo_unpack_values", "sphb200_halo_pack_derivs",
-           "sphb200_halo_unpack_derivs", "sphb200_upload_derivs", "sphb200_boundary_configure", "sphb200_iterate_ideal_h", "sphb200_connectivity_valid")
+           "sphb200_halo_unpack_derivs", "sphb200_upload_derivs", "sphb200_boundary_configure", "sphb200_iterate_ideal_h", "sphb200_connectivity_valid", "sphb200_state_fields_present")
 
 _lib = None
 
@@ -134,6 +134,7 @@ def lib():
                                              _dp, _dp, C.POINTER(C.c_size_t), _dp, _dp, _dp, _dp, _dp, _dp, _dp]
     L.sphb200_set_nodes.argtypes = [vp, C.c_size_t, C.c_size_t]
     L.sphb200_upload_state.argtypes = [vp, C.c_uint, C.POINTER(HostState)]
+    L.sphb200_upload_state_values.argtypes = [vp, C.c_uint, C.POINTER(HostState)]
     L.sphb200_download_state.argtypes = [vp, C.c_uint, C.POINTER(_dp)]
     L.sphb200_build_pairs.argtypes = [vp, C.POINTER(C.c_size_t)]
     L.sphb200_download_pairs.argtypes = [vp, _u32p, _u32p, C.c_size_t]
@@ -178,5 +179,7 @@ def lib():
     L.sphb200_boundary_configure.argtypes = [vp, C.c_int, C.POINTER(C.c_int), _dp, _dp, _dp, _dp]
     L.sphb200_iterate_ideal_h.argtypes = [vp, C.c_int, C.c_double, _dp]
     L.sphb200_connectivity_valid.argtypes = [vp]
+    L.sphb200_state_fields_present.argtypes = [vp]
+    L.sphb200_state_fields_present.restype = C.c_uint
     _lib = L
     return L

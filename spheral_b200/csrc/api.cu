@@ -382,7 +382,11 @@ static const double* state_ptr(const sphb200_host_state* s, int slot) {
   return nullptr;
 }
 
-int sphb200_upload_state(sphb200_ctx* c, unsigned mask, const sphb200_host_state* s) {
+static int upload_state_impl(sphb200_ctx* c, unsigned mask, const sphb200_host_state* s, bool keepConnectivity);
+int sphb200_upload_state(sphb200_ctx* c, unsigned mask, const sphb200_host_state* s) { return upload_state_impl(c, mask, s, false); }
+int sphb200_upload_state_values(sphb200_ctx* c, unsigned mask, const sphb200_host_state* s) { return upload_state_impl(c, mask, s, true); }
+
+static int upload_state_impl(sphb200_ctx* c, unsigned mask, const sphb200_host_state* s, bool keepConnectivity) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
   if (!s) return sphb200_fail(c, "upload_state: null state");
   CU_CHECK(c, cudaSetDevice(c->device));
@@ -404,7 +408,7 @@ int sphb200_upload_state(sphb200_ctx* c, unsigned mask, const sphb200_host_state
       if (bytes) CU_CHECK(c, cudaMemcpyAsync(c->api[slot], src, bytes, cudaMemcpyHostToDevice, c->copyStream));
       any = true;
       c->have[slot] = true;
-      if (geom) { c->sortValid = false; c->pairsValid = false; }
+      if (geom && !keepConnectivity) { c->sortValid = false; c->pairsValid = false; }
       if (slot != S_EPS && slot != S_VOLUME && slot != S_RKCORR) c->rowsValid = false;
     }
     if (any && pass == 0) { CU_CHECK(c, cudaEventRecord(c->evGeomUp, c->copyStream)); c->pendGeomUp = true; }
@@ -457,6 +461,12 @@ int sphb200_build_pairs(sphb200_ctx* c, size_t* npairs) {
 }
 
 int sphb200_connectivity_valid(const sphb200_ctx* c) { return (c && c->pairsValid) ? 1 : 0; }
+
+unsigned sphb200_state_fields_present(const sphb200_ctx* c) {
+  unsigned m = 0;
+  if (c) for (int s = 0; s < S_COUNT; ++s) if (c->have[s] && c->api[s]) m |= 1u << s;
+  return m;
+}
 
 int sphb200_download_pairs(sphb200_ctx* c, uint32_t* i, uint32_t* j, size_t cap) {
   if (!c) return sphb200_fail(nullptr, "null ctx");

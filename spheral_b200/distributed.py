@@ -24,6 +24,9 @@ from . import _lib as L
 
 PHASE_A = ("position", "H")
 PHASE_B = ("velocity", "mass", "massDensity", "specificThermalEnergy", "pressure", "soundSpeed", "omegaGradh")
+# State fields owned by the artificial viscosity (ArtificialViscosityHandle.cc:105-119): they travel with the halo from the moment they
+# hold values on the device -- LimitedMonaghanGingold and the Balsara switch read the neighbour's velocity gradient, ghosts included
+OPTIONAL_B = ("DvDxQ", "fCl", "fCq")
 
 
 def slab_edges(xmin, xmax, world):
@@ -157,9 +160,10 @@ class DistributedSPH:
         # the exchange from the moment the integrator reports them ready (mark_ready); the staging is sized for all of them.
         self.extra = tuple(extra_fields)
         self.ready = set()
-        self.maskB = field_mask(PHASE_B)
+        self._maskB_base = field_mask(PHASE_B)
+        self._maskB_opt = field_mask(OPTIONAL_B)
         self.bytesA = engine.halo_bytes_per_node(self.maskA)
-        self.bytesB = engine.halo_bytes_per_node(field_mask(PHASE_B + self.extra))
+        self.bytesB = engine.halo_bytes_per_node(field_mask(PHASE_B + OPTIONAL_B + self.extra))
         self._cap = 0
         self.nInternal = engine.nInternal
         # ghosts of the boundaries that come before the slab halo in the boundary list (reflecting / periodic planes generated on
@@ -171,12 +175,18 @@ class DistributedSPH:
         self.width = 0.0
         self.last = {}
 
+    @property
+    def maskB(self):
+        """Every field but positions and H that travels: the hydro's state, the extra fields declared ready, and the artificial
+        viscosity's fields once they hold values on the device (every rank runs the same call sequence, so all agree)."""
+        m = self._maskB_base | field_mask(tuple(x for x in self.extra if x in self.ready))
+        return m | (self._maskB_opt & self.e.state_fields_present())
+
     def mark_ready(self, *names):
         """A package has computed these extra fields on the internal nodes: from now on they travel with the halo."""
         for k in names:
-            if k in self.extra and k not in self.ready:
+            if k in self.extra:
                 self.ready.add(k)
-                self.maskB = field_mask(PHASE_B + tuple(x for x in self.extra if x in self.ready))
 
     def _ensure(self, cap, keep_lists=False):
         """Capacity (in nodes) of the send lists and of the four staging buffers.  keep_lists: the send lists have just been
@@ -253,10 +263,11 @@ class DistributedSPH:
             self._ensure(max(nLow, nHigh, nFL, nFU), keep_lists=True)
             self.nFromLower, self.nFromUpper = nFL, nFU
             e.set_nodes(nInt, nBG + nFL + nFU)
-            wA, wB = self.bytesA//8, e.halo_bytes_per_node(self.maskB)//8
+            maskB = self.maskB                                  # evaluated once per refresh: landing ghosts must not change it mid-way
+            wA, wB = self.bytesA//8, e.halo_bytes_per_node(maskB)//8
             if not self.two_phase or not build:
                 wAB = wA + wB
-                mask = self.maskA | self.maskB
+                mask = self.maskA | maskB
                 e.halo_pack(mask, self.idxLow.data_ptr(), nLow, self.sLowB.data_ptr())
                 e.halo_pack(mask, self.idxHigh.data_ptr(), nHigh, self.sHighB.data_ptr())
                 works = h.start(self.sLowB[:nLow*wAB], self.sHighB[:nHigh*wAB], self.rLowB[:nFL*wAB], self.rHighB[:nFU*wAB])
@@ -268,8 +279,8 @@ class DistributedSPH:
                 # pack both phases, then post A and B; K1+K2 only wait for A
                 e.halo_pack(self.maskA, self.idxLow.data_ptr(), nLow, self.sLowA.data_ptr())
                 e.halo_pack(self.maskA, self.idxHigh.data_ptr(), nHigh, self.sHighA.data_ptr())
-                e.halo_pack(self.maskB, self.idxLow.data_ptr(), nLow, self.sLowB.data_ptr())
-                e.halo_pack(self.maskB, self.idxHigh.data_ptr(), nHigh, self.sHighB.data_ptr())
+                e.halo_pack(maskB, self.idxLow.data_ptr(), nLow, self.sLowB.data_ptr())
+                e.halo_pack(maskB, self.idxHigh.data_ptr(), nHigh, self.sHighB.data_ptr())
                 worksA = h.start(self.sLowA[:nLow*wA], self.sHighA[:nHigh*wA], self.rLowA[:nFL*wA], self.rHighA[:nFU*wA])
                 worksB = h.start(self.sLowB[:nLow*wB], self.sHighB[:nHigh*wB], self.rLowB[:nFL*wB], self.rHighB[:nFU*wB])
                 h.finish(worksA)
@@ -277,10 +288,10 @@ class DistributedSPH:
                 e.halo_unpack(self.maskA, nOwn + nFL, nFU, self.rHighA.data_ptr())
                 npairs = e.build_pairs()                      # phase B is in flight on the NCCL stream meanwhile
                 h.finish(worksB)
-                e.halo_unpack(self.maskB, nOwn, nFL, self.rLowB.data_ptr())
-                e.halo_unpack(self.maskB, nOwn + nFL, nFU, self.rHighB.data_ptr())
+                e.halo_unpack(maskB, nOwn, nFL, self.rLowB.data_ptr())
+                e.halo_unpack(maskB, nOwn + nFL, nFU, self.rHighB.data_ptr())
         self.last = dict(nSendLow=nLow, nSendHigh=nHigh, nFromLower=nFL, nFromUpper=nFU, nBoundaryGhost=nBG,
-                         h2h_bytes=(nLow + nHigh)*(self.bytesA + self.bytesB), two_phase=bool(self.two_phase))
+                         h2h_bytes=(nLow + nHigh)*(self.bytesA + 8*wB), two_phase=bool(self.two_phase))
         return npairs
 
     def apply_ghosts(self, names=None):

@@ -120,8 +120,9 @@ class Engine:
         self._check(self._lib.sphb200_set_nodes(self._h, nInternal, nGhost))
         self.nInternal, self.nGhost = nInternal, nGhost
 
-    def upload_state(self, **fields):
-        """fields: name -> array in the reference AoS layout; names from _lib.STATE_FIELDS."""
+    def upload_state(self, _keep_connectivity=False, **fields):
+        """fields: name -> array in the reference AoS layout; names from _lib.STATE_FIELDS.  _keep_connectivity: the pair lists
+        stay valid although positions / H are refreshed (a mid-step evaluation on the step-start ConnectivityMap)."""
         hs = L.HostState()
         mask = 0
         keep = []
@@ -136,7 +137,8 @@ class Engine:
             keep.append(a)
             setattr(hs, k, _dp(a))
             mask |= L.STATE_BITS[k]
-        self._check(self._lib.sphb200_upload_state(self._h, mask, C.byref(hs)))
+        fn = self._lib.sphb200_upload_state_values if _keep_connectivity else self._lib.sphb200_upload_state
+        self._check(fn(self._h, mask, C.byref(hs)))
         self.sync()          # the numpy temporaries must outlive the async copies
 
     def upload_state_pinned(self, mask, hs):
@@ -164,6 +166,10 @@ class Engine:
 
     def connectivity_valid(self):
         return bool(self._lib.sphb200_connectivity_valid(self._h))
+
+    def state_fields_present(self):
+        """Mask (_lib.STATE_BITS) of the state fields holding values on the device."""
+        return int(self._lib.sphb200_state_fields_present(self._h))
 
     def download_pairs(self):
         pi = np.zeros(max(self.npairs, 1), dtype=np.uint32)

@@ -330,8 +330,6 @@ class SPHB200(Physics):
         self._device = device
         self._engine = None
         self._own = {}                     # package-owned fields (SPHBase.hh:223-251), name -> array
-        self._uploaded = {}                # abi name -> (id(array), nodelist version) last uploaded
-        self._pairsKey = None
         self._pairAccelerations = PairAccelerationsView(self)
         nl = dataBase.nodeLists[0]
         self._ndim = nl.ndim
@@ -435,40 +433,35 @@ class SPHB200(Physics):
         """What Integrator::setGhostNodes asks for because requireConnectivity() is true (Integrator.cc:372-445):
         Neighbor::updateNodes + DataBase::updateConnectivityMap, on the device."""
         nl = dataBase.nodeLists[0]
-        self._sync_state(nl, state, ("position", "H"))
+        self._sync_state(nl, state, ("position", "H"), keep_connectivity=False)
         self._engine.build_pairs()
-        self._pairsKey = self._uploaded.get("position"), self._uploaded.get("H")
         dataBase.connectivityValid = True
         return self._engine.npairs
 
-    def _sync_state(self, nl, state, names):
-        """Upload the state fields whose host arrays changed identity or content version since the last upload.  Content
-        changes made in place are declared with markDirty()."""
+    def _sync_state(self, nl, state, names, keep_connectivity=True):
+        """Copy the named state fields from the host State to the device -- always, whatever happened to the host arrays since the
+        last call: the State hands out references, so an in-place update by another package is indistinguishable from no update.
+        keep_connectivity: the device keeps its pair lists although positions / H are refreshed, which is what the reference does
+        between the neighbour update of a step and its mid-step evaluateDerivatives (CheapSynchronousRK2.cc:76-99); only
+        updateConnectivity invalidates them."""
         e = self._engine
         if (nl.numInternalNodes, nl.numGhostNodes) != (e.nInternal, e.nGhost):
-            e.set_nodes(nl.numInternalNodes, nl.numGhostNodes)
-            self._uploaded.clear()
+            e.set_nodes(nl.numInternalNodes, nl.numGhostNodes)       # a changed node count invalidates the connectivity
         todo = {}
         for abi in names:
             key = _key(STATE_KEYS[abi], nl.name)
-            if key not in state:
-                continue
-            a = state[key]
-            tag = (id(a), self._dirty.get(abi, 0))
-            if self._uploaded.get(abi) != tag:
-                todo[abi] = a
-                self._uploaded[abi] = tag
+            if key in state:
+                todo[abi] = state[key]
         if todo:
-            e.upload_state(**todo)
-
-    _dirty = {}
+            e.upload_state(_keep_connectivity=keep_connectivity, **todo)
 
     def markDirty(self, *abiNames):
-        """Declare in-place host modifications of state fields (all when no name is given)."""
-        if self._dirty is SPHB200._dirty:
-            self._dirty = {}
-        for k in (abiNames or STATE_KEYS):
-            self._dirty[k] = self._dirty.get(k, 0) + 1
+        """Kept for source compatibility with round 1: every call of this package now re-reads the State's fields."""
+        return None
+
+    def _require_connectivity(self, dataBase, who):
+        if not (self._engine.connectivity_valid() and dataBase.connectivityValid):
+            raise SPHB200Error("SPH::%s: no valid connectivity (call updateConnectivity after the node set or the ghost nodes changed)" % who)
 
     def evaluateDerivatives(self, time, dt, dataBase, state, derivs):
         """SPH<Dim>::evaluateDerivatives (SPH.cc:141-555) followed by the post sub-package's evaluateDerivatives
@@ -481,8 +474,7 @@ class SPHB200(Physics):
             if state.registered(STATE_KEYS[abi], nl.name):
                 needed.append(abi)
         self._sync_state(nl, state, needed)
-        if (self._uploaded.get("position"), self._uploaded.get("H")) != self._pairsKey or not dataBase.connectivityValid:
-            raise SPHB200Error("SPH::evaluateDerivatives: connectivity is stale (positions/H changed since updateConnectivity)")
+        self._require_connectivity(dataBase, "evaluateDerivatives")
         self._engine.evaluate_derivatives(time, dt)
         got = self._engine.download_derivs()
         for abi, key in DERIV_KEYS.items():
@@ -497,12 +489,10 @@ class SPHB200(Physics):
             return
         nl = dataBase.nodeLists[0]
         self._sync_state(nl, state, ("position", "H", "mass", "massDensity"))
-        if (self._uploaded.get("position"), self._uploaded.get("H")) != self._pairsKey or not dataBase.connectivityValid:
-            raise SPHB200Error("SPH::preStepInitialize: connectivity is stale (positions/H changed since updateConnectivity)")
+        self._require_connectivity(dataBase, "preStepInitialize")
         self._engine.sum_mass_density()
         k = _key(HydroFieldNames.massDensity, nl.name)
         state[k][...] = self._engine.download_state("massDensity")["massDensity"]
-        self._uploaded["massDensity"] = (id(state[k]), self._dirty.get("massDensity", 0))
 
     def postStateUpdate(self, time, dt, dataBase, state, derivs):
         """ArtificialViscosityHandle::postStateUpdate copies DvDx into the Q's velocity gradient
@@ -515,23 +505,19 @@ class SPHB200(Physics):
         if HydroFieldNames.ArtificialViscosityVelocityGradient in self._own:
             self._engine.copy_DvDx_to_Q()
             k = _key(HydroFieldNames.ArtificialViscosityVelocityGradient, nl.name)
-            self._uploaded["DvDxQ"] = (id(state[k]), self._dirty.get("DvDxQ", 0)) if k in state else None
+            if k in state:                                # the State's copy follows the device (every later call re-reads the State)
+                state[k][...] = self._engine.download_state("DvDxQ")["DvDxQ"].reshape(state[k].shape)
         if not self.gradhCorrection:
             return False
-        self._sync_state(nl, state, ("position", "H"))
         # the reference evaluates the corrections on the connectivity of the step start although positions moved
-        # (CheapSynchronousRK2.cc:76-84): the device keeps its pair lists unless build_pairs is called again
-        if not self._engine_pairs_usable():
-            self._engine.build_pairs()
+        # (CheapSynchronousRK2.cc:76-84): the refresh of positions and H keeps the device's pair lists
+        self._sync_state(nl, state, ("position", "H"))
+        self._require_connectivity(dataBase, "postStateUpdate")
         self._engine.compute_omega_gradh()
         k = _key(HydroFieldNames.omegaGradh, nl.name)
         if k in state:
             state[k][...] = self._engine.download_state("omegaGradh")["omegaGradh"]
-            self._uploaded["omegaGradh"] = (id(state[k]), self._dirty.get("omegaGradh", 0))
         return True
-
-    def _engine_pairs_usable(self):
-        return self._engine.connectivity_valid()
 
     def dt(self, dataBase, state, derivs, currentTime=0.0):
         """GenericHydro::dt (Physics/GenericHydro.cc:112-381) -> (dt, reason), from the state on the host and the derivatives
@@ -550,7 +536,6 @@ class SPHB200(Physics):
         eps = self._engine.download_state("specificThermalEnergy")["specificThermalEnergy"]
         k = _key(HydroFieldNames.specificThermalEnergy, nl.name)
         state[k][...] = eps
-        self._uploaded["specificThermalEnergy"] = (id(state[k]), self._dirty.get("specificThermalEnergy", 0))
 
 
 class CRKSPHB200(SPHB200):
@@ -607,13 +592,11 @@ class CRKSPHB200(SPHB200):
         got = self._engine.download_state(abi)[abi]
         k = _key(STATE_KEYS[abi], nl.name)
         state[k][...] = got.reshape(state[k].shape)
-        self._uploaded[abi] = (id(state[k]), self._dirty.get(abi, 0))
 
     def preStepInitialize(self, dataBase, state, derivs):
         nl = dataBase.nodeLists[0]
-        if (self._uploaded.get("position"), self._uploaded.get("H")) != self._pairsKey or not dataBase.connectivityValid:
-            raise SPHB200Error("CRKSPH::preStepInitialize: connectivity is stale (call updateConnectivity first)")
-        self._sync_state(nl, state, ("mass", "volume"))
+        self._sync_state(nl, state, ("position", "H", "mass", "volume"))
+        self._require_connectivity(dataBase, "preStepInitialize")
         self._engine.crk_compute_volume()
         self._pull(nl, state, "volume")
         if self.densityUpdate == RigorousSumDensity:

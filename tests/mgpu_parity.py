@@ -44,11 +44,18 @@ def main():
             Rm = ng.random_rotation(ndim, rng)
             F[q] = Rm @ (F[q] @ np.diag(rng.uniform(0.75, 1.25, size=ndim))) @ Rm.T
         G["H"] = np.ascontiguousarray(ng.full_to_sym(ndim, 0.5*(F + np.swapaxes(F, 1, 2))))
+    # MGPU_QKIND=1: LimitedMonaghanGingold with Balsara switch and Cl / Cq multipliers -- the pair loop then reads the velocity
+    # gradient and the multipliers of GHOST neighbours, so all three must travel with the halo
+    qkind = int(os.environ.get("MGPU_QKIND", "0"))
+    if qkind:
+        G = common.add_q_fields(G, ndim, seed=31)
     N = n**3
     mine = slice(rank*N, (rank + 1)*N)
     WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
     crk = os.environ.get("MGPU_CRK", "0") == "1"          # CRKSPH: volumes and RK corrections travel with the halo
     kw = dict(nPerh=nPerh, Cl=2.0, Cq=2.0, hEvolution=1 if asph else 0)
+    if qkind:
+        kw.update(Qkind=1, balsara=1)
     if crk:
         kw = dict(nPerh=nPerh, Cl=1.0, Cq=0.25, Qkind=0, correctVelocityGradient=0)
         G["velocity"] = 0.3*G["velocity"]
@@ -80,7 +87,7 @@ def main():
         worst[k] = float(np.abs(a - b).max()/max(np.abs(b).max(), f))
     w = max(worst.values())
     res = dict(rank=rank, world=world, nodes=N, ghosts=e.nGhost, pairs=int(npairs), counts_equal=ok, worst_field_error=w,
-               halo=d.info(), asph=asph)
+               halo=d.info(), asph=asph, qkind=qkind)
     print(json.dumps(res), flush=True)
     flag = torch.tensor([1.0 if (ok and w <= 1.0e-10) else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -60,7 +60,7 @@ def test_evaluate_derivatives_through_physics_interface(sphlib, oracle):
     state.field("pressure", "nodes")[...] = st["pressure"]
     state.field("sound speed", "nodes")[...] = st["soundSpeed"]
     state.field("grad h corrections", "nodes")[...] = st["omegaGradh"]
-    with pytest.raises(P.SPHB200Error, match="connectivity is stale"):
+    with pytest.raises(P.SPHB200Error, match="no valid connectivity"):
         hydro.evaluateDerivatives(0.0, 1.0, db, state, derivs)
     npairs = hydro.updateConnectivity(db, state)
     derivs.Zero()
@@ -197,3 +197,42 @@ def test_step_hooks_through_physics_interface(sphlib, oracle):
     ref_dt, why, node = oracle.hydro_dt(oo, oracle.default_step_options(cfl=hydro.cfl), nInt, s2["vel"], s2["H"], s2["rho"], s2["cs"], d, pi, pj)
     vote, reason = hydro.dt(db, state, derivs, 0.0)
     assert abs(vote - ref_dt) <= 1e-11*ref_dt and reason.lower().startswith(why)
+
+
+@pytest.mark.gpu
+def test_mid_step_refresh_keeps_the_step_start_connectivity(sphlib, oracle):
+    """CheapSynchronousRK2.cc:76-99: state.update moves the nodes, postStateUpdate and evaluateDerivatives then run on the
+    ConnectivityMap of the step start.  The package re-reads the State's (moved) positions without rebuilding the pair lists, sees
+    host arrays that were modified IN PLACE (no markDirty, no new array identity), and evaluates on the old pairs -- the oracle does
+    the same with the step-start pair list and the moved state."""
+    P, st, nodes, db, WT, hydro = _setup(Q=None)
+    hydro.Q = P.MonaghanGingoldViscosity(2.0, 2.0)
+    hydro.initializeProblemStartup(db)
+    state, derivs = P.State(db, [hydro]), P.StateDerivatives(db, [hydro])
+    state.field("pressure", "nodes")[...] = st["pressure"]
+    state.field("sound speed", "nodes")[...] = st["soundSpeed"]
+    state.field("grad h corrections", "nodes")[...] = st["omegaGradh"]
+    npairs = hydro.updateConnectivity(db, state)
+    nInt = nodes.numInternalNodes
+    s = common.to_oracle_state(st)
+    pi, pj, cnt = oracle.pairs(3, nInt, 0, s["pos"], s["H"], WT.kernelExtent)
+    assert npairs == len(pi)
+    # the trial advance: positions and velocities change in place
+    pos = state.field("position", "nodes")
+    pos += 0.02*st["velocity"]/np.abs(st["velocity"]).max()*(1.0/9.0)
+    state.field("velocity", "nodes")[...] *= 1.01
+    assert hydro.postStateUpdate(0.0, 1.0, db, state, derivs) is True
+    assert hydro._engine.connectivity_valid() and hydro._engine.npairs == npairs          # no rebuild happened
+    OT = common.oracle_table(oracle, WT)
+    s2 = dict(s, pos=np.ascontiguousarray(pos), vel=np.ascontiguousarray(state.field("velocity", "nodes")))
+    om_ref = oracle.omega_gradh(3, OT, nInt, 0, s2["pos"], s2["H"], pi, pj, cnt)
+    om = state.field("grad h corrections", "nodes")
+    assert np.abs(om - om_ref).max() <= 1e-10*np.abs(om_ref).max()
+    derivs.Zero()
+    hydro.evaluateDerivatives(0.0, 1.0, db, state, derivs)                                # must not raise: connectivity is still the step-start one
+    oo = oracle.default_options(3, nPerh=1.51, Cl=2.0, Cq=2.0)
+    ref = oracle.evaluate_derivatives(oo, OT, dict(s2, omega=om_ref), nInt, 0, pi, pj, cnt)
+    floors = common.physical_floors(st, nInt, 3)
+    for abi in ("DvDt", "DepsDt", "DrhoDt", "DvDx"):
+        got = derivs.field(P.DERIV_KEYS[abi], "nodes")
+        assert common.field_err(got, np.asarray(ref[abi]).reshape(got.shape), nInt, floors[abi]) <= 1e-10, abi
