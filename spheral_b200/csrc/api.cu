@@ -653,6 +653,9 @@ static int halo_unpack_impl(sphb200_ctx* c, unsigned mask, size_t firstGhost, si
   if (!c) return sphb200_fail(nullptr, "null ctx");
   CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (firstGhost + count > c->n) return sphb200_fail(c, "halo_unpack: ghost range exceeds node count");
+  // Late fields of a two-phase exchange (everything but positions and H, landing after the neighbour build): the sorted rows are
+  // current except for these ghosts, so only their rows are packed again instead of all of them
+  const bool patchRows = c->sortValid && c->rowsValid && !(mask & ((1u << S_POS) | (1u << S_H)));
   HaloFields f{};
   for (int s = 0; s < S_COUNT; ++s) {
     if (!(mask & (1u << s))) continue;
@@ -668,6 +671,10 @@ static int halo_unpack_impl(sphb200_ctx* c, unsigned mask, size_t firstGhost, si
   if (f.total) {
     k_halo_unpack_all<<<(unsigned)((f.total + RB - 1)/RB), RB, 0, c->stream>>>(f, firstGhost, (const double*)staging);
     KERNEL_CHECK(c, "k_halo_unpack_all");
+  }
+  if (patchRows && !c->rowsValid) {
+    if (sphb200_pack_rows_range(c, firstGhost, count)) return 1;
+    c->rowsValid = true;
   }
   return 0;
 }

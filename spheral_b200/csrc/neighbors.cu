@@ -206,21 +206,25 @@ struct PackArgs {
   float* frows; GridDev g; double kext; double csmax;   // csmax: largest cell width x (3 rad + 4)/7 (FP32 error of k*cs + rel, |k| <= rad)
   int rawP;                       // CRKSPH: the row carries P itself (CRKSPH.cc:376 uses Pi + Pj), not safeInv(omega)*P/rho^2
   unsigned long long* aniso;      // set to 1 if any H is not a multiple of the identity (selects the isotropic pair loop)
+  const uint32_t* invPerm; size_t first, count;   // RANGE mode: re-pack the rows of the nodes [first, first + count) only
 };
-template <int DIM>
+// RANGE: only the nodes [first, first + count) of the host order (ghosts whose non-geometric fields have just landed, with positions
+// and H -- hence the sort, the FP32 rows and the isotropy flag -- unchanged) are packed again, through the inverse permutation.
+template <int DIM, bool RANGE>
 __global__ void __launch_bounds__(RB) k_pack(PackArgs a) {
   using D = Dm<DIM>;
-  const size_t s = (size_t)blockIdx.x*RB + threadIdx.x;
-  if (s >= a.n) return;
-  const size_t o = a.perm[s];
+  const size_t t = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (t >= (RANGE ? a.count : a.n)) return;
+  const size_t s = RANGE ? (size_t)a.invPerm[a.first + t] : t;
+  const size_t o = RANGE ? a.first + t : (size_t)a.perm[s];
   double* r = a.rows + s*D::ROW;
 #pragma unroll
   for (int k = 0; k < DIM; ++k) { r[D::R_POS + k] = a.pos[o*DIM + k]; r[D::R_VEL + k] = a.vel ? a.vel[o*DIM + k] : 0.0; }
   double Hn[D::NS];                                              // this node's H, read once
 #pragma unroll
   for (int k = 0; k < D::NS; ++k) { Hn[k] = a.H[o*D::NS + k]; r[D::R_H + k] = Hn[k]; }
-  { const bool iso = (DIM == 3) ? (Hn[1] == 0.0 && Hn[2] == 0.0 && Hn[4] == 0.0 && Hn[3] == Hn[0] && Hn[5] == Hn[0])
-                                : (Hn[1] == 0.0 && Hn[2] == Hn[0]);
+  if (!RANGE) { const bool iso = (DIM == 3) ? (Hn[1] == 0.0 && Hn[2] == 0.0 && Hn[4] == 0.0 && Hn[3] == Hn[0] && Hn[5] == Hn[0])
+                                             : (Hn[1] == 0.0 && Hn[2] == Hn[0]);
     if (!iso) *a.aniso = 1ull; }
   const double m = a.mass ? a.mass[o] : 0.0, rho = a.rho ? a.rho[o] : 1.0, P = a.P ? a.P[o] : 0.0;
   const double om = a.omega ? a.omega[o] : 1.0, cs = a.cs ? a.cs[o] : 0.0;
@@ -235,8 +239,8 @@ __global__ void __launch_bounds__(RB) k_pack(PackArgs a) {
     for (int k = 0; k < D::NT; ++k) a.auxDvDxQ[s*D::NT + k] = a.DvDxQ[o*D::NT + k];
   }
   if (a.auxfCl) { a.auxfCl[s] = a.fCl[o]; a.auxfCq[s] = a.fCq[o]; }
-  if (a.skey) a.skey[s] = a.keyApi[o];
-  if (a.frows) {
+  if (!RANGE && a.skey) a.skey[s] = a.keyApi[o];
+  if (!RANGE && a.frows) {
     // FP32 pre-filter row (layout: struct Fr).  Error model (DESIGN.md "K2 error bands"): every relative-position component
     // is reconstructed in FP32 as k*cs + rel_i - rel_j with |error| <= 7*2^-24*cs, so for a pair at true distance <= R
     //   | |r|^2_f32 - |r|^2 | <= 2e-6*R*cs + 1e-6*R^2 + 1e-11*cs^2 =: margin(R)            (spheres)
@@ -1085,7 +1089,7 @@ static bool sphb200_nbr_v2_wanted() {          // read at every build: the tests
   return !(e && e[0] == '0');
 }
 
-int sphb200_pack_rows(sphb200_ctx* c) {
+static int pack_rows_impl(sphb200_ctx* c, bool range, size_t first, size_t count) {
   if (!c->sortValid) return sphb200_fail(c, "internal: pack_rows before sort");
   const bool tens = c->opt.epsTensile != 0.0;
   const bool needQ = (c->opt.Qkind == SPHB200_Q_LIMITED_MG) || c->opt.balsara;
@@ -1106,6 +1110,16 @@ int sphb200_pack_rows(sphb200_ctx* c) {
   a.perm = c->perm; a.keyApi = c->cellKeyApi; a.skey = c->skey; a.n = c->n;
   a.rawP = (c->opt.hydro == SPHB200_HYDRO_CRKSPH) ? 1 : 0;
   a.aniso = c->counters + 8;
+  if (range) {
+    if (first + count > c->n) return sphb200_fail(c, "internal: pack_rows range exceeds the node count");
+    if (count == 0) return 0;
+    if (sphb200_inverse_perm(c)) return 1;
+    a.invPerm = c->invPerm; a.first = first; a.count = count;
+    const unsigned nbr = (unsigned)((count + RB - 1)/RB);
+    if (c->ndim == 3) k_pack<3, true><<<nbr, RB, 0, c->stream>>>(a); else k_pack<2, true><<<nbr, RB, 0, c->stream>>>(a);
+    KERNEL_CHECK(c, "k_pack(range)");
+    return 0;
+  }
   CU_CHECK(c, cudaMemsetAsync(c->counters + 8, 0, sizeof(unsigned long long), c->stream));
   { size_t fcap = c->frows ? c->frowsCap : 0;
     if (sphb200_ensure(c, c->frows, fcap, c->cap*(size_t)Fr::ROW)) return 1;
@@ -1117,11 +1131,15 @@ int sphb200_pack_rows(sphb200_ctx* c) {
   c->nbrV2 = sphb200_nbr_v2_wanted() && c->stencilR == 1 && !c->fineWalk;
   a.csmax = std::max(c->grid.cs[0], std::max(c->grid.cs[1], c->ndim == 3 ? c->grid.cs[2] : 0.0))*(c->nbrV2 ? 2.0 : (3.0*c->stencilR + 4.0)/7.0);
   const unsigned nb = (unsigned)((c->n + RB - 1)/RB);
-  if (c->ndim == 3) k_pack<3><<<nb, RB, 0, c->stream>>>(a); else k_pack<2><<<nb, RB, 0, c->stream>>>(a);
+  if (c->ndim == 3) k_pack<3, false><<<nb, RB, 0, c->stream>>>(a); else k_pack<2, false><<<nb, RB, 0, c->stream>>>(a);
   KERNEL_CHECK(c, "k_pack");
   c->rowsValid = true;
   return 0;
 }
+
+int sphb200_pack_rows(sphb200_ctx* c) { return pack_rows_impl(c, false, 0, 0); }
+// Re-pack the rows of the nodes [first, first + count) of the host order after their non-geometric fields changed (late halo fields)
+int sphb200_pack_rows_range(sphb200_ctx* c, size_t first, size_t count) { return pack_rows_impl(c, true, first, count); }
 
 int sphb200_bounds_reduce(sphb200_ctx* c, size_t count) {
   const double kext = std::max(c->W.kext, c->WQ.set ? c->WQ.kext : 0.0);

@@ -184,6 +184,7 @@ int sphb200_sort_and_pack(sphb200_ctx* c);
 extern "C" int sphb200_inverse_perm(sphb200_ctx* c);        // (re)builds c->invPerm from the current sort (api.cu)
 int sphb200_bounds_reduce(sphb200_ctx* c, size_t count);   // bbox + max extents of nodes [0,count) -> reduceHost[0..8] (async copy)
 int sphb200_pack_rows(sphb200_ctx* c);
+int sphb200_pack_rows_range(sphb200_ctx* c, size_t first, size_t count);   // rows of the nodes [first, first + count) only (sort unchanged)
 int sphb200_neighbors(sphb200_ctx* c);
 int sphb200_launch_derivs(sphb200_ctx* c);
 int sphb200_launch_energy(sphb200_ctx* c, double multiplier);

@@ -16,6 +16,8 @@ internal nodes.  The exchange is split in two so that only positi
     phase A  position, H            -> needed by the neighbour build (K1 + K2)
     phase B  every other state field -> needed by the pair loop (K3); in flight while K1 + K2 run.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -148,9 +150,10 @@ class DistributedSPH:
     slabs.  `step_connectivity_and_derivatives()` is what Integrator::setGhostNodes + evaluateDerivatives do per stage
     (Integrator.cc:372-445, 217-229): ghost selection, exchange, neighbour build, derivative evaluation."""
 
-    def __init__(self, engine, axis, lo, hi, halo=None, extra_fields=(), two_phase=False):
+    def __init__(self, engine, axis, lo, hi, halo=None, extra_fields=(), two_phase=None):
         self.e = engine
-        self.two_phase = two_phase
+        # default: split exchange (SPHB200_HALO_TWO_PHASE=0 selects the single batch, for A/B measurements)
+        self.two_phase = (os.environ.get("SPHB200_HALO_TWO_PHASE", "1") != "0") if two_phase is None else bool(two_phase)
         self.axis, self.lo, self.hi = axis, float(lo), float(hi)
         self.halo = halo if halo is not None else SlabHalo()
         self.dev = torch.device("cuda", engine_device(engine))
@@ -214,13 +217,13 @@ class DistributedSPH:
         """Ghost selection + exchange (+ neighbour build).  Returns the number of node pairs of this slab (None without the build).
         `boundary_ghosts`: number of plane ghosts already generated behind the internal nodes (see nBoundaryGhost).
 
-        Default path: ONE host round trip before the neighbour build.  The bounds reduction, the all-reduce(MAX) of the
-        halo width, the send-node selection and the all-gather of the counts are chained on the device
-        (sphb200_node_bounds_device / sphb200_halo_select_device); only the gathered counts come back to the host (NCCL
-        needs the message sizes there).  All fields then travel in one batch of send/recv, so the node rows are packed
-        once (with two phases the rows have to be re-packed when the late fields land: +0.19 ms per step at 1 M nodes,
-        which is more than the ~10 us the second message spends on NVLink).  `two_phase=True` keeps the split exchange
-        (positions + H first, the rest in flight during the neighbour build)."""
+        ONE host round trip before the neighbour build: the bounds reduction, the all-reduce(MAX) of the halo width, the
+        send-node selection and the all-gather of the counts are chained on the device (sphb200_node_bounds_device /
+        sphb200_halo_select_device); only the gathered counts come back to the host (NCCL needs the message sizes there).
+        Default (two_phase): positions + H travel first and the neighbour build (K1 + K2) starts as soon as they have landed;
+        every other field is in flight on the NCCL stream meanwhile and lands before the pair loop, where only the rows of the
+        ghosts it touched are packed again (sphb200_halo_unpack -> k_pack range mode; round 1 re-packed all rows, which cost more
+        than the overlap saved).  two_phase=False sends everything in one batch before the build."""
         e, h = self.e, self.halo
         nInt = self.nInternal
         if nInt == 0:
