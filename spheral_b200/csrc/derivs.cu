@@ -52,17 +52,19 @@ __device__ __forceinline__ void cp_async16_s(unsigned smemDst, const void* gmemS
 #ifndef SPHB200_PAIR_STAGES
 #define SPHB200_PAIR_STAGES 4
 #endif
+// One CTA of 8 warps per SM (register-limited to 8 warps either way): the TableKernel table is staged once per SM instead of twice,
+// which leaves 24 KB more L1 for the neighbour-row gather (noh8m pair kernel 16.75 -> 16.44 ms; profiles/r02_notes.md).
 #ifndef SPHB200_PAIR_WARPS
-#define SPHB200_PAIR_WARPS 4
+#define SPHB200_PAIR_WARPS 8
 #endif
 #ifndef SPHB200_PAIR_CTAS
-#define SPHB200_PAIR_CTAS 2
+#define SPHB200_PAIR_CTAS 1
 #endif
 // 1: stream the per-node {det H, 1/rho} record of every neighbour through the ring as well; 0: recompute both from the row.
 // The per-lane 16-byte copy costs 32 shared-memory wavefronts per iteration, as many as the 32 rows together, and the LSU data
 // pipe is the unit this kernel saturates first (profiles/r01_notes.md); 23 extra FP64 instructions per edge are cheaper.
 #ifndef SPHB200_PAIR_CTAS_ISO
-#define SPHB200_PAIR_CTAS_ISO 2
+#define SPHB200_PAIR_CTAS_ISO 1
 #endif
 #ifndef SPHB200_PAIR_AUX
 #define SPHB200_PAIR_AUX 0
@@ -282,7 +284,8 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
       const double r = r2*rinv;
       e2i = hi2*r2; e2j = (hjInv*hjInv)*r2;
       table_eval_raw(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, hiInv*r, Wi, gWi);
-      table_eval_raw(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, hjInv*r, Wj, gWj);
+      if (xsph) table_eval_raw(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, hjInv*r, Wj, gWj);
+      else { Wj = 0.0; table_eval_grad(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, hjInv*r, gWj); }
       gWiRaw = gWi;
       Wi *= Hdeti; Wj *= Hdetj;
       gi = (gWi*Hdeti)*(hiInv*rinv);                       // gWi * Hi * etaiUnit = gWi * hiInv * rij/r
@@ -301,9 +304,11 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
     const double invj = fast_rsqrt(e2j + 1.0e-300);
     const double etaMagi = e2i*invi, etaMagj = e2j*invj;
 
-    // SPH.cc:374-377 : W, gradW (table values carry no Hdet yet)
+    // SPH.cc:374-377 : W, gradW (table values carry no Hdet yet).  W_j only enters the XSPH weight and the tensile term: without
+    // them the j side reads the gradient coefficients only (two of the record's three 16-byte chunks)
     table_eval_raw(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, etaMagi, Wi, gWi);
-    table_eval_raw(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, etaMagj, Wj, gWj);
+    if (GEN || xsph) table_eval_raw(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, etaMagj, Wj, gWj);
+    else { Wj = 0.0; table_eval_grad(tW, a.kextW, a.xminW, a.xstepW, rxW, a.n1W, etaMagj, gWj); }
     gWiRaw = gWi;
     Wi *= Hdeti; gWi *= Hdeti; Wj *= Hdetj; gWj *= Hdetj;
     double Hei[DIM], Hej[DIM];

@@ -78,6 +78,20 @@ __device__ __forceinline__ void table_eval_raw(unsigned tab, double kext, double
 #endif
 }
 
+// The gradient half of table_eval_raw (same interval selection, same coefficients): for the side of a pair whose W is not needed.
+__device__ __forceinline__ void table_eval_grad(unsigned tab, double kext, double xmin, double xstep, double rxstep,
+                                                uint32_t n1, double eta, double& gW) {
+  const double x = eta - xmin;
+  const double q = x*rxstep;
+  int k = __double2int_rz(q);
+  const double fr = q - (double)k;
+  if (fr < 1.0e-9 || fr > 1.0 - 1.0e-9) k = (int)(fmax(x, 0.0)/xstep);
+  k = max(min(k, (int)n1), 0);
+  const unsigned c = tab + 48u*(unsigned)k;
+  const double2 c23 = lds128(c + 16u), c45 = lds128(c + 32u);
+  gW = (eta < kext) ? fma(fma(c45.y, eta, c45.x), eta, c23.y) : 0.0;
+}
+
 template <int DIM> __device__ __forceinline__ double rootnu(double x) {
   if (DIM == 3) return d_sgn(x)*pow(fabs(x), 0.3333333333333333);   // Dimension.hh:94, FastMath.hh:152-163
   return sqrt(x);

@@ -218,8 +218,10 @@ template <int DIM> __device__ __forceinline__ double eta2_exact(const double* H,
   }
 }
 
+// det H by cofactors of the first row: 9 FP64 instructions instead of the 17 of the six-term form (GeomSymmetricTensorInline.hh:
+// 1740-1749); the two agree to round-off, which is all the 1e-10 bar asks of a pair-loop factor.
 template <int DIM> __device__ __forceinline__ double sym_det(const double* H) {
-  if (DIM == 3) return (H[0]*H[3]*H[5] + H[1]*H[4]*H[2] + H[2]*H[1]*H[4] - H[0]*H[4]*H[4] - H[1]*H[1]*H[5] - H[2]*H[3]*H[2]);
+  if (DIM == 3) return fma(H[0], fma(H[3], H[5], -H[4]*H[4]), fma(H[2], fma(H[1], H[4], -H[2]*H[3]), -H[1]*fma(H[1], H[5], -H[2]*H[4])));
   return H[0]*H[2] - H[1]*H[1];
 }
 template <int DIM> __device__ __forceinline__ void sym_dot(const double* H, const double* r, double* o) {
