@@ -470,8 +470,58 @@ __global__ void __launch_bounds__(128) k_tile_runs(NbrArgs a) {
       }
     }
   };
-  if constexpr (FINE) walk_cells_coarse<DIM>(a.g, leaders, ci, rad, [&](int sx, int sy, int sz) { emit_fine(sx, sy, sz, 0u, true); });
-  else walk_cells<DIM>(a.g, a.dilTab, a.cellStart, leaders, ci, rad, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) { emit(jb, je, sx, sy, sz, 0u, true); });
+  // Box walk (the common case: stencil radius 1, the tile's cells within a small box): the lanes share out the cells of the box
+  // [cmin - 1, cmax + 1], keep those inside the 3^DIM stencil of at least one leader and look their ranges up in parallel; the
+  // runs come out in box order (z, y, x), a fixed function of the input.  ~150 instructions per tile against ~3.8 k for the
+  // serial walk with its leader-by-leader duplicate test (k_tile_runs was 1.1 ms of the 8 M step: profiles/r02_notes.md).
+  bool boxed = false;
+  if constexpr (!FINE) {
+    int bl[3] = {0, 0, 0}, be[3] = {1, 1, 1};
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+      const int lo = __reduce_min_sync(0xffffffffu, leader ? ci[k] : 0x7fffffff), hi = __reduce_max_sync(0xffffffffu, leader ? ci[k] : -0x7fffffff);
+      bl[k] = max(lo - 1, 0);
+      be[k] = min(hi + 1, a.g.nc[k] - 1) - bl[k] + 1;
+    }
+    const int ncell = be[0]*be[1]*be[2];
+    if (rad == 1 && leaders != 0u && ncell <= 128) {
+      boxed = true;
+      for (int base = 0; base < ncell; base += 32) {
+        const int idx = base + lane;
+        int sx = 0, sy = 0, sz = 0;
+        bool want = idx < ncell;
+        if (want) {
+          sx = bl[0] + idx % be[0]; const int t = idx/be[0];
+          sy = bl[1] + t % be[1]; sz = bl[2] + t/be[1];
+        }
+        bool inSt = false;                                   // within one cell of some leader's cell?
+        for (unsigned lm = leaders; lm; lm &= lm - 1) {
+          const int L = __ffs(lm) - 1;
+          const int lx = __shfl_sync(0xffffffffu, ci[0], L), ly = __shfl_sync(0xffffffffu, ci[1], L), lz = __shfl_sync(0xffffffffu, ci[2], L);
+          inSt = inSt || (abs(lx - sx) <= 1 && abs(ly - sy) <= 1 && (DIM == 2 || abs(lz - sz) <= 1));
+        }
+        uint32_t jb = 0, je = 0;
+        if (want && inSt) {
+          const uint32_t key = a.dilTab[sx] | a.dilTab[SPHB200_DIL + sy] | ((DIM == 3) ? a.dilTab[2*SPHB200_DIL + sz] : 0u);
+          jb = a.cellStart[key]; je = a.cellStart[key + 1];
+        }
+        const uint32_t nr = (je - jb + 31u) >> 5;            // a cell with more than 32 nodes becomes several runs
+        uint32_t pre = nr;                                   // inclusive prefix sum over the lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, pre, d); if (lane >= d) pre += t; }
+        const uint32_t tot = __shfl_sync(0xffffffffu, pre, 31);
+        uint32_t at = R + pre - nr;
+        for (uint32_t b = jb; b < je; b += 32u, ++at)
+          if (at < (uint32_t)RUN_CAP) sruns[w][at] = make_uint4(b, min(32u, je - b), (uint32_t)sx | ((uint32_t)sy << 16), (uint32_t)sz);
+        R += tot;
+      }
+      if (R > (uint32_t)RUN_CAP) { boxed = false; R = 0; }   // more runs than the table holds: the serial walk (it spills to global memory)
+    }
+  }
+  if (!boxed) {
+    if constexpr (FINE) walk_cells_coarse<DIM>(a.g, leaders, ci, rad, [&](int sx, int sy, int sz) { emit_fine(sx, sy, sz, 0u, true); });
+    else walk_cells<DIM>(a.g, a.dilTab, a.cellStart, leaders, ci, rad, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) { emit(jb, je, sx, sy, sz, 0u, true); });
+  }
   __syncwarp();
   const uint32_t Rtot = R;
   if (Rtot >= 2048u && lane == 0) atomicAdd(&a.counters[5], 1ull);      // list codes are run << 5 | candidate in 16 bits
