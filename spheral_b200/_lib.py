@@ -15,6 +15,7 @@ _u32p = C.POINTER(C.c_uint32)
 Q_MG, Q_LIMITED_MG = 0, 1
 H_SPH, H_ASPH, H_NONE = 0, 1, 2
 KERNEL_BSPLINE, KERNEL_WENDLANDC4, KERNEL_WENDLANDC2 = 0, 1, 2
+KERNEL_NBSPLINE = 100        # + order: NBSplineKernel(order)
 TABLE_W, TABLE_WPI = 0, 1
 HYDRO_SPH, HYDRO_CRKSPH = 0, 1
 

@@ -12,14 +12,54 @@
 
 namespace {
 
+// NBSplineKernel(order) (Kernel/NBSplineKernel.cc:17-122): Schoenberg's B-spline of order k = order + 1,
+//   W(eta) = A/(k-1)! sum_{i=0..k} (-1)^i C(k,i) (eta - i + k/2)_+^(k-1),
+// its derivatives by lowering the exponent and the factorial; kernel extent (order + 1)/2 in integer arithmetic (:116); the volume
+// normalisation A by composite Simpson integration of W over the kernel volume with 10000 bins (:119-121,
+// Kernel/VolumeIntegrationFunctions.cc:22-70, Utilities/simpsonsIntegration.hh:20-53) -- not the closed form, so that the table
+// carries the reference's own normalisation error (~1e-9).
+struct NBSpline {
+  int order, ndim; double A = 1.0;
+  static double fact(int n) { double r = 1.0; for (int i = 2; i <= n; ++i) r *= i; return r; }
+  double extent() const { return double((order + 1)/2); }
+  double sum(double eta, int lower) const {           // lower = 1, 2, 3: value, first, second derivative (unnormalised)
+    const int k = order + 1, e = std::max(1 - lower, k - lower);
+    double r = 0.0;
+    for (int i = 0; i <= k; ++i) {
+      const double x = eta - i + 0.5*k;
+      const double binom = fact(k)/(fact(k - i)*fact(i));
+      if (x >= 0.0) r += ((i & 1) ? -1.0 : 1.0)*binom*std::pow(x, e);
+    }
+    return r/fact(std::max(e, 0));
+  }
+  void normalise() {
+    const unsigned bins = 10000u;
+    const double kext = extent(), dx = kext/bins;
+    double acc = 0.0;
+    for (unsigned i = 0; i <= bins; ++i) {
+      const double r = i*dx;
+      const double shell = ndim == 1 ? 2.0 : (ndim == 2 ? 2.0*M_PI*r : 4.0*M_PI*r*r);
+      const double f = shell*(r >= kext ? 0.0 : sum(r, 1));
+      acc += (i == 0 || i == bins) ? f : ((i % 2 == 0) ? 2.0*f : 4.0*f);
+    }
+    A = 1.0/(acc*dx/3.0);
+  }
+};
+
 struct Analytic {
   int kind, ndim;
-  double extent() const { return kind == SPHB200_KERNEL_BSPLINE ? 2.0 : 1.0; }
+  NBSpline nbs{0, 0};
+  Analytic(int k, int d) : kind(k), ndim(d) {
+    if (kind >= SPHB200_KERNEL_NBSPLINE) { nbs = NBSpline{kind - SPHB200_KERNEL_NBSPLINE, ndim}; nbs.normalise(); }
+  }
+  double extent() const { return kind >= SPHB200_KERNEL_NBSPLINE ? nbs.extent() : (kind == SPHB200_KERNEL_BSPLINE ? 2.0 : 1.0); }
   // value / first / second derivative at eta with Hdet = 1 (Kernel/BSplineKernelInline.hh:38-90,
   // WendlandC4KernelInline.hh:38-95, WendlandC2KernelInline.hh:36-90)
   void eval(double eta, double& w, double& g, double& g2) const {
     w = g = g2 = 0.0;
-    if (kind == SPHB200_KERNEL_BSPLINE) {
+    if (kind >= SPHB200_KERNEL_NBSPLINE) {
+      if (eta < nbs.extent()) { w = nbs.sum(eta, 1)*nbs.A; g = nbs.sum(eta, 2)*nbs.A; g2 = nbs.sum(eta, 3)*nbs.A; }
+    } else if (kind == SPHB200_KERNEL_BSPLINE) {
       const double A = ndim == 1 ? 2.0/3.0 : (ndim == 2 ? 10.0/(7.0*M_PI) : 1.0/M_PI);
       if (eta < 1.0) {
         const double e2 = eta*eta;
@@ -159,8 +199,9 @@ extern "C" int sphb200_table_kernel_build(int kind, int ndim, size_t numPoints, 
                                           double* kextOut, double* xstepOut, size_t* n1Out,
                                           double* Wcoef, double* gradWcoef, double* grad2Wcoef,
                                           double* nperhVals, double* nperhRange, double* wsumVals, double* wsumRange) {
-  if (kind < 0 || kind > SPHB200_KERNEL_WENDLANDC2 || ndim < 1 || ndim > 3 || numPoints < 3) return 1;
-  const Analytic K{kind, ndim};
+  const bool nbspline = kind >= SPHB200_KERNEL_NBSPLINE + 1 && kind <= SPHB200_KERNEL_NBSPLINE + 11;      // orders 1 .. 11 (kernel extent >= 1)
+  if (((kind < 0 || kind > SPHB200_KERNEL_WENDLANDC2) && !nbspline) || ndim < 1 || ndim > 3 || numPoints < 3) return 1;
+  const Analytic K(kind, ndim);
   const double kext = K.extent();
   const size_t n = (numPoints % 2 == 0) ? numPoints + 1 : numPoints;
   const double step = kext/double(n - 1);

@@ -19,6 +19,8 @@ class _AnalyticKernel:
 
     @property
     def kernelExtent(self):
+        if self.kind >= L.KERNEL_NBSPLINE:
+            return float((self.kind - L.KERNEL_NBSPLINE + 1)//2)      # NBSplineKernel.cc:116, integer arithmetic
         return 2.0 if self.kind == L.KERNEL_BSPLINE else 1.0
 
 
@@ -34,12 +36,36 @@ class WendlandC2Kernel(_AnalyticKernel):
     kind = L.KERNEL_WENDLANDC2
 
 
+class NBSplineKernel(_AnalyticKernel):
+    """NBSplineKernel(order) -- PYB11/Kernel/Kernel.py; Kernel/NBSplineKernel.cc.  The stock Noh scripts build their TableKernel from
+    NBSplineKernel(5) (tests/functional/Hydro/Noh/Noh-spherical-3d.py:25,205)."""
+
+    def __init__(self, ndim=3, order=5):
+        super().__init__(ndim)
+        if not 1 <= int(order) <= 11:
+            raise ValueError("NBSplineKernel: order must be in 1..11")
+        self.order = int(order)
+        self.kind = L.KERNEL_NBSPLINE + self.order
+
+
 def BSplineKernel2d():
     return BSplineKernel(2)
 
 
 def BSplineKernel3d():
     return BSplineKernel(3)
+
+
+def NBSplineKernel1d(order=5):
+    return NBSplineKernel(1, order)
+
+
+def NBSplineKernel2d(order=5):
+    return NBSplineKernel(2, order)
+
+
+def NBSplineKernel3d(order=5):
+    return NBSplineKernel(3, order)
 
 
 def WendlandC4Kernel2d():

@@ -48,6 +48,30 @@ def test_host_table_builder_matches_oracle(sphlib, oracle, ndim, kind):
         assert np.allclose(WT.wsumVals, OT.wsumVals, rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("ndim,order", [(1, 5), (2, 3), (3, 5), (3, 7)])
+def test_nbspline_table_matches_oracle(sphlib, oracle, ndim, order):
+    """NBSplineKernel(order) in the PRODUCT's host table builder (missing 4) against the oracle's restatement of
+    Kernel/NBSplineKernel.cc -- the kernel the stock Noh scripts use, and the one the reference's stored golden was produced with."""
+    WT = K.TableKernel(K.NBSplineKernel(ndim, order), 1000)
+    OT = oracle.TableKernel(oracle.KERNEL_NBSPLINE + order, ndim, 1000)
+    assert WT.kernelExtent == OT.kext == float((order + 1)//2) and WT.n1 == OT.n1 and WT.xstep == OT.xstep
+    sW, sG = np.abs(OT.Wcoef).max(), np.abs(OT.gradWcoef).max()
+    assert np.abs(WT.Wcoef - OT.Wcoef).max() <= 1e-8*sW and np.abs(WT.gradWcoef - OT.gradWcoef).max() <= 1e-8*sG
+    for eta in np.linspace(0, WT.kernelExtent*0.999, 200):
+        a, b = WT.kernelAndGradValue(float(eta)), OT.kernelAndGradValue(float(eta))
+        # the alternating sum cancels ~(k/2)^(k-1) : 1, so two orderings of the same formula differ by that much round-off
+        assert abs(a[0] - b[0]) < 2e-11*sW and abs(a[1] - b[1]) < 2e-11*sG
+    assert np.allclose(WT.nperhVals, OT.nperhVals, rtol=1e-8, atol=1e-10)
+    # unit volume integral in ndim dimensions (the normalisation is Simpson's, 10000 bins: ~1e-9)
+    x = np.linspace(0.0, WT.kernelExtent, 20001)
+    w = np.array([WT.kernelValue(float(e)) for e in x])
+    shell = {1: 2.0*np.ones_like(x), 2: 2.0*np.pi*x, 3: 4.0*np.pi*x*x}[ndim]
+    f = shell*w
+    assert abs(float(np.sum(0.5*(f[1:] + f[:-1])*np.diff(x))) - 1.0) < 2e-6
+    with pytest.raises(ValueError):
+        K.NBSplineKernel(3, 0)
+
+
 def test_table_kernel_python_face(sphlib):
     WT = K.TableKernel(K.BSplineKernel3d(), 1000)
     assert WT.kernelExtent == 2.0
