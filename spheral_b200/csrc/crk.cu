@@ -750,6 +750,7 @@ int sphb200_launch_crk_derivs(sphb200_ctx* c) {
     KERNEL_CHECK(c, "k_crk_qrec");
   }
   a.aux2 = c->crkAux;
+  c->paccMode = PACC_FULL; c->paccWidth = c->ndim;      // the RK-corrected pair force has no two-scalar form
   if (c->opt.compatibleEnergy && sphb200_ensure(c, c->pacc, c->paccCap, c->nSlots*(size_t)c->ndim)) return 1;
   a.pacc = c->pacc;
   if (c->opt.hEvolution == SPHB200_H_SPH && (!a.nperhVals || a.nperhN < 2))

@@ -179,7 +179,9 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
   const uint32_t rows = a.tileRows[tile];
   const unsigned long long base = a.tileOff[tile] + lane;
 
-  double* const paccTile = compat ? a.pacc + (size_t)DIM*a.tileOff[tile] + lane : nullptr;     // pacc_index<DIM>(slot, c)
+  // storage mode of the pair force (sphb200_internal.cuh): one scalar on the scalar-factor isotropic path, two on the tensor paths
+  constexpr int PW = ISC ? 1 : (ISO ? DIM : 2);
+  double* const paccTile = compat ? a.pacc + (size_t)PW*a.tileOff[tile] + lane : nullptr;      // pacc_at(PW, slot, word)
   // ---- software pipeline over the neighbour list: indices one iteration ahead of the row copies, row copies
   //      PAIR_STAGES-1 iterations ahead of the arithmetic.  The copy of the 32 rows of one iteration is warp-cooperative:
   //      CH lanes fetch the CH 16-byte chunks of one row, so a LDGSTS instruction touches 32/CH full lines instead of 32
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
       issue_rows(p, jn);
       jn = load_idx(p + 1u);
     }
-    double* const paccRow = paccTile + (size_t)k*(DIM*32);
+    double* const paccRow = paccTile + (size_t)k*(PW*32);
     if (k < cnt) {
     const unsigned long long slot = base + (unsigned long long)k*SPHB200_TILE;
     const uint32_t j = GEN ? a.nbr[slot] : 0u;
@@ -276,6 +278,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
     double e2i, e2j, Wi, gWi, Wj, gWj, gWiRaw;
     double gradWi[DIM], gradWj[DIM];
     double gi = 0.0, gj = 0.0, hjInv = 0.0;               // ISO: gradW_i = gi * rij, gradW_j = gj * rij
+    double sWi = 0.0, sWj = 0.0, sQi = 0.0, sQj = 0.0;    // tensor paths: gradW_x = sW_x H_x.eta_x, gradWQ_x = sQ_x H_x.eta_x
     if constexpr (ISO) {
       hjInv = Hj[0];
       const double r2 = vdot<DIM>(rij, rij);
@@ -315,6 +318,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
     sym_dot<DIM>(Hi, etai, Hei);                 // gWi*Hi*etaiUnit == (gWi/|etai|) * (Hi.etai)
     sym_dot<DIM>(Hj, etaj, Hej);
     { const double si = gWi*invi, sj = gWj*invj;
+      sWi = sQi = si; sWj = sQj = sj;
 #pragma unroll
       for (int q = 0; q < DIM; ++q) { gradWi[q] = si*Hei[q]; gradWj[q] = sj*Hej[q]; } }
     }
@@ -332,6 +336,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
       table_eval_raw(tQ, a.kextQ, a.xminQ, a.xstepQ, rxQ, a.n1Q, e2j*invj, WQj, gWQj);
       WQi *= Hdeti; WQj *= Hdetj;
       const double si = gWQi*Hdeti*invi, sj = gWQj*Hdetj*invj;
+      sQi = si; sQj = sj;
 #pragma unroll
       for (int q = 0; q < DIM; ++q) { gradWQi[q] = si*Hei[q]; gradWQj[q] = sj*Hej[q]; }
     }
@@ -391,10 +396,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
       const double msd = mj*sd;
 #pragma unroll
       for (int q = 0; q < DIM; ++q) DvDt[q] = fma(-msd, rij[q], DvDt[q]);
-      if (compat) {
-#pragma unroll
-        for (int q = 0; q < DIM; ++q) paccRow[32*q] = sd*rij[q];
-      }
+      if (compat) paccRow[0] = sd;                                           // delta = sd r_ij, expanded by the readers
       // SPH.cc:434 : mj (Prho_i vij.gradW_i + workQ_i) = mj gi (vij.rij) (Prho_i + QPi_ij/2)
       const double mg = mj*gi;
       DepsDt = fma(mg*vr, ai, DepsDt);
@@ -468,8 +470,14 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
 #pragma unroll
     for (int q = 0; q < DIM; ++q) DvDt[q] = fma(-mj, delta[q], DvDt[q]);
     if (compat) {
+      if constexpr (ISO) {
 #pragma unroll
-      for (int q = 0; q < DIM; ++q) paccRow[32*q] = delta[q];
+        for (int q = 0; q < DIM; ++q) paccRow[32*q] = delta[q];
+      } else {
+        // delta = (Prho_i sW_i + QPi_ij/2 sQ_i) H_i.eta_i + (Prho_j sW_j + QPi_ji/2 sQ_j) H_j.eta_j: two scalars, expanded by the readers
+        paccRow[0] = fma(Prhoi, sWi, hQPiij*sQi);
+        paccRow[32] = fma(Prhoj, sWj, hQPiji*sQj);
+      }
     }
 
     // SPH.cc:434
@@ -667,8 +675,12 @@ int sphb200_launch_derivs(sphb200_ctx* c) {
   a.WnPerh = host_table_eval(c->W, 1.0/c->opt.nPerh, false);      // SPH.cc:264-266
   a.n = c->n; a.cap = c->cap; a.nInt = (uint32_t)c->nInt; a.o = c->opt;
   for (int s = 0; s < DV_COUNT; ++s) a.deriv[s] = c->deriv[s];
+  const bool isoPath0 = c->allIsotropic && c->opt.hEvolution != SPHB200_H_ASPH;
+  const bool gen0 = (c->opt.Qkind != SPHB200_Q_MG) || c->opt.balsara || mult || tens || !c->oneKernel || c->opt.linearInExpansion || c->opt.quadraticInExpansion;
+  c->paccMode = (isoPath0 && !gen0) ? (SPHB200_ISO_SCALAR ? PACC_ISO : PACC_FULL) : PACC_TENSOR;
+  c->paccWidth = pacc_width(c->paccMode, c->ndim);
   if (c->opt.compatibleEnergy) {
-    if (sphb200_ensure(c, c->pacc, c->paccCap, c->nSlots*(size_t)c->ndim)) return 1;
+    if (sphb200_ensure(c, c->pacc, c->paccCap, c->nSlots*(size_t)c->paccWidth)) return 1;
   }
   a.pacc = c->pacc; a.nSlots = c->nSlots;
   const int wpb = PAIR_WARPS;
@@ -686,5 +698,6 @@ int sphb200_launch_derivs(sphb200_ctx* c) {
   else              { if (launch_dim<2>(c, a, nb, wpb*32, shm, gen)) return 1; }
   KERNEL_CHECK(c, "k_sph_derivs");
   c->derivsValid = true;
+  c->rowsAtEval = true;
   return 0;
 }

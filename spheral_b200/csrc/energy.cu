@@ -10,13 +10,21 @@ namespace {
 
 constexpr int RB = 256;
 
-// erow[s] = { v + DvDt*hdt (DIM), DepsDt0, m, original index }   stride DIM+3
-template <int DIM>
+// erow[s] = { v + DvDt*hdt (DIM), DepsDt0, m, original index | position (DIM), H (NS) }   stride ES<DIM, MODE>
+// The geometry tail exists only for the compressed pair-force modes (PACC_ISO: position and 1/h; PACC_TENSOR: position and H), which are
+// expanded here from the node rows the evaluation read: delta = sd r_ij, or a H_i.(H_i.r_ij) + b H_j.(H_j.r_ij).
+template <int DIM, int MODE> struct ERow {
+  static constexpr int GEOM = (MODE == PACC_FULL) ? 0 : (MODE == PACC_ISO ? DIM + 1 : DIM + Dm<DIM>::NS);
+  static constexpr int ES = DIM + 3 + GEOM;
+};
+
+template <int DIM, int MODE>
 __global__ void __launch_bounds__(RB) k_energy_prep(const double* __restrict__ velApi, const double* __restrict__ massApi,
                                                     const uint32_t* __restrict__ perm, const double* __restrict__ DvDt,
-                                                    const double* __restrict__ DepsDt, size_t n, size_t cap, double hdt,
+                                                    const double* __restrict__ DepsDt, const double* __restrict__ rows, size_t n, size_t cap, double hdt,
                                                     double* __restrict__ erow) {
-  constexpr int ES = DIM + 3;
+  using D = Dm<DIM>;
+  constexpr int ES = ERow<DIM, MODE>::ES;
   const size_t s = (size_t)blockIdx.x*RB + threadIdx.x;
   if (s >= n) return;
   const size_t o = perm[s];
@@ -25,15 +33,50 @@ __global__ void __launch_bounds__(RB) k_energy_prep(const double* __restrict__ v
   erow[s*ES + DIM] = DepsDt[s];
   erow[s*ES + DIM + 1] = massApi[o];
   erow[s*ES + DIM + 2] = (double)o;            // original index: orients the pair (i_node < j_node, NodePairIdxType.hh:34-58)
+  if (MODE != PACC_FULL) {
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) erow[s*ES + DIM + 3 + q] = rows[s*D::ROW + D::R_POS + q];
+    if (MODE == PACC_ISO) erow[s*ES + 2*DIM + 3] = rows[s*D::ROW + D::R_H];
+    else {
+#pragma unroll
+      for (int q = 0; q < D::NS; ++q) erow[s*ES + 2*DIM + 3 + q] = rows[s*D::ROW + D::R_H + q];
+    }
+  }
 }
 
-template <int DIM>
+// the pair force of a directed edge in i's orientation, expanded from its stored words
+template <int DIM, int MODE>
+__device__ __forceinline__ void pacc_expand(const double* __restrict__ pacc, unsigned long long slot, const double* gi, const double* gj, double* d) {
+  constexpr int W = (MODE == PACC_ISO) ? 1 : (MODE == PACC_TENSOR ? 2 : DIM);
+  if (MODE == PACC_FULL) {
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) d[q] = pacc[pacc_at(W, slot, q)];
+    return;
+  }
+  double rij[DIM];
+#pragma unroll
+  for (int q = 0; q < DIM; ++q) rij[q] = gi[q] - gj[q];
+  if (MODE == PACC_ISO) {
+    const double sd = pacc[pacc_at(W, slot, 0)];
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) d[q] = sd*rij[q];
+  } else {
+    const double a = pacc[pacc_at(W, slot, 0)], b = pacc[pacc_at(W, slot, 1)];
+    double ei[DIM], ej[DIM], hi[DIM], hj[DIM];
+    sym_dot<DIM>(gi + DIM, rij, ei); sym_dot<DIM>(gi + DIM, ei, hi);
+    sym_dot<DIM>(gj + DIM, rij, ej); sym_dot<DIM>(gj + DIM, ej, hj);
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) d[q] = fma(a, hi[q], b*hj[q]);
+  }
+}
+
+template <int DIM, int MODE>
 __global__ void __launch_bounds__(128) k_energy(const double* __restrict__ erow, const uint32_t* __restrict__ perm,
                                                 const uint32_t* __restrict__ nbrCount, const uint32_t* __restrict__ tileRows,
                                                 const unsigned long long* __restrict__ tileOff, const uint32_t* __restrict__ nbr,
                                                 const double* __restrict__ pacc, size_t nSlots, size_t n, uint32_t nInt,
                                                 double multiplier, double* __restrict__ epsApi) {
-  constexpr int ES = DIM + 3;
+  constexpr int ES = ERow<DIM, MODE>::ES, GEOM = ERow<DIM, MODE>::GEOM;
   const int lane = threadIdx.x & 31;
   const size_t tile = (size_t)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
   const size_t i = tile*SPHB200_TILE + lane;
@@ -41,14 +84,18 @@ __global__ void __launch_bounds__(128) k_energy(const double* __restrict__ erow,
   const bool inRange = i < n;
   const uint32_t o = inRange ? perm[i] : 0xffffffffu;
   const bool active = inRange && o < nInt;
-  double vi[DIM], Di = 0, mi = 1;
+  double vi[DIM], Di = 0, mi = 1, gi[GEOM > 0 ? GEOM : 1];
   if (inRange) {
 #pragma unroll
     for (int q = 0; q < DIM; ++q) vi[q] = erow[i*ES + q];
     Di = erow[i*ES + DIM]; mi = erow[i*ES + DIM + 1];
+#pragma unroll
+    for (int q = 0; q < GEOM; ++q) gi[q] = erow[i*ES + DIM + 3 + q];
   } else {
 #pragma unroll
     for (int q = 0; q < DIM; ++q) vi[q] = 0;
+#pragma unroll
+    for (int q = 0; q < (GEOM > 0 ? GEOM : 1); ++q) gi[q] = 0;
   }
   const uint32_t cnt = active ? nbrCount[i] : 0u;
   const uint32_t rows = tileRows[tile];
@@ -58,9 +105,12 @@ __global__ void __launch_bounds__(128) k_energy(const double* __restrict__ erow,
     if (k >= cnt) continue;
     const unsigned long long slot = base + (unsigned long long)k*SPHB200_TILE + lane;
     const uint32_t j = nbr[slot];
-    double vj[DIM], d[DIM];
+    double vj[DIM], d[DIM], gj[GEOM > 0 ? GEOM : 1];
 #pragma unroll
-    for (int q = 0; q < DIM; ++q) { vj[q] = erow[(size_t)j*ES + q]; d[q] = pacc[pacc_index<DIM>(slot, q)]; }
+    for (int q = 0; q < DIM; ++q) vj[q] = erow[(size_t)j*ES + q];
+#pragma unroll
+    for (int q = 0; q < GEOM; ++q) gj[q] = erow[(size_t)j*ES + DIM + 3 + q];
+    pacc_expand<DIM, MODE>(pacc, slot, gi, gj, d);
     const double Dj = erow[(size_t)j*ES + DIM], mj = erow[(size_t)j*ES + DIM + 1];
     const bool up = erow[(size_t)j*ES + DIM + 2] > (double)o;         // original index of j > original index of i
     if (up) {
@@ -126,16 +176,27 @@ __global__ void __launch_bounds__(128) k_emit_pairs(const uint32_t* __restrict__
   }
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(RB) k_emit_pacc(const uint32_t* __restrict__ outJ, const unsigned long long* __restrict__ outSlot,
-                                                  const double* __restrict__ massApi, const double* __restrict__ pacc, size_t nSlots,
-                                                  size_t npairs, double* __restrict__ out) {
+template <int DIM, int MODE>
+__global__ void __launch_bounds__(RB) k_emit_pacc(const uint32_t* __restrict__ outI, const uint32_t* __restrict__ outJ,
+                                                  const unsigned long long* __restrict__ outSlot, const uint32_t* __restrict__ invPerm,
+                                                  const double* __restrict__ rows, const double* __restrict__ massApi,
+                                                  const double* __restrict__ pacc, size_t nSlots, size_t npairs, double* __restrict__ out) {
+  using D = Dm<DIM>;
   const size_t k = (size_t)blockIdx.x*RB + threadIdx.x;
   if (k >= npairs) return;
   const double mj = massApi[outJ[k]];
   const unsigned long long slot = outSlot[k];
+  double d[DIM], gi[DIM + D::NS], gj[DIM + D::NS];
+  if (MODE != PACC_FULL) {                       // geometry of both ends from the node rows the evaluation read
+    const double* ri = rows + (size_t)invPerm[outI[k]]*D::ROW; const double* rj = rows + (size_t)invPerm[outJ[k]]*D::ROW;
 #pragma unroll
-  for (int q = 0; q < DIM; ++q) out[k*DIM + q] = -mj*pacc[pacc_index<DIM>(slot, q)];    // SPH.cc:430
+    for (int q = 0; q < DIM; ++q) { gi[q] = ri[D::R_POS + q]; gj[q] = rj[D::R_POS + q]; }
+#pragma unroll
+    for (int q = 0; q < D::NS; ++q) { gi[DIM + q] = ri[D::R_H + q]; gj[DIM + q] = rj[D::R_H + q]; }
+  }
+  pacc_expand<DIM, MODE>(pacc, slot, gi, gj, d);
+#pragma unroll
+  for (int q = 0; q < DIM; ++q) out[k*DIM + q] = -mj*d[q];    // SPH.cc:430
 }
 
 // u32 counts -> u64 exclusive offsets (single block serial-by-chunks; export path only, not on the hot path)
@@ -166,9 +227,10 @@ __global__ void k_scan64_small(const uint32_t* __restrict__ in, unsigned long lo
 
 }  // namespace
 
-int sphb200_launch_energy(sphb200_ctx* c, double multiplier) {
+template <int DIM, int MODE>
+static int launch_energy_mode(sphb200_ctx* c, double multiplier) {
   const size_t n = c->n;
-  const int ES = c->ndim + 3;
+  constexpr int ES = ERow<DIM, MODE>::ES;
   size_t need = n*ES*sizeof(double);
   if (need > c->stageBytes) {
     if (c->stage) cudaFree(c->stage);
@@ -179,17 +241,25 @@ int sphb200_launch_energy(sphb200_ctx* c, double multiplier) {
   const double hdt = 0.5*multiplier;
   const unsigned nb = (unsigned)((n + RB - 1)/RB);
   const unsigned nbt = (unsigned)((c->nTiles + 3)/4);
-  if (c->ndim == 3) {
-    k_energy_prep<3><<<nb, RB, 0, c->stream>>>(c->api[S_VEL], c->api[S_MASS], c->perm, c->deriv[DV_DVDT], c->deriv[DV_DEPSDT], n, c->cap, hdt, c->stage);
-    KERNEL_CHECK(c, "k_energy_prep");
-    k_energy<3><<<nbt, 128, 0, c->stream>>>(c->stage, c->perm, c->nbrCount, c->tileRows, c->tileOff, c->nbr, c->pacc, c->nSlots, n, (uint32_t)c->nInt, multiplier, c->api[S_EPS]);
-  } else {
-    k_energy_prep<2><<<nb, RB, 0, c->stream>>>(c->api[S_VEL], c->api[S_MASS], c->perm, c->deriv[DV_DVDT], c->deriv[DV_DEPSDT], n, c->cap, hdt, c->stage);
-    KERNEL_CHECK(c, "k_energy_prep");
-    k_energy<2><<<nbt, 128, 0, c->stream>>>(c->stage, c->perm, c->nbrCount, c->tileRows, c->tileOff, c->nbr, c->pacc, c->nSlots, n, (uint32_t)c->nInt, multiplier, c->api[S_EPS]);
-  }
+  k_energy_prep<DIM, MODE><<<nb, RB, 0, c->stream>>>(c->api[S_VEL], c->api[S_MASS], c->perm, c->deriv[DV_DVDT], c->deriv[DV_DEPSDT], c->rows, n, c->cap, hdt, c->stage);
+  KERNEL_CHECK(c, "k_energy_prep");
+  k_energy<DIM, MODE><<<nbt, 128, 0, c->stream>>>(c->stage, c->perm, c->nbrCount, c->tileRows, c->tileOff, c->nbr, c->pacc, c->nSlots, n, (uint32_t)c->nInt, multiplier, c->api[S_EPS]);
   KERNEL_CHECK(c, "k_energy");
   return 0;
+}
+
+int sphb200_launch_energy(sphb200_ctx* c, double multiplier) {
+  if (c->paccMode != PACC_FULL && !c->rowsAtEval)
+    return sphb200_fail(c, "update_energy_compatible: the node rows of the evaluation were re-packed since (a derivative-consuming call on new state came "
+                           "first); evaluate the derivatives again before the compatible energy update");
+  if (c->ndim == 3) {
+    if (c->paccMode == PACC_ISO) return launch_energy_mode<3, PACC_ISO>(c, multiplier);
+    if (c->paccMode == PACC_TENSOR) return launch_energy_mode<3, PACC_TENSOR>(c, multiplier);
+    return launch_energy_mode<3, PACC_FULL>(c, multiplier);
+  }
+  if (c->paccMode == PACC_ISO) return launch_energy_mode<2, PACC_ISO>(c, multiplier);
+  if (c->paccMode == PACC_TENSOR) return launch_energy_mode<2, PACC_TENSOR>(c, multiplier);
+  return launch_energy_mode<2, PACC_FULL>(c, multiplier);
 }
 
 int sphb200_pairs_to_host(sphb200_ctx* c, uint32_t* pi, uint32_t* pj, size_t cap, double* paccOut, size_t paccCap) {
@@ -220,8 +290,14 @@ int sphb200_pairs_to_host(sphb200_ctx* c, uint32_t* pi, uint32_t* pj, size_t cap
   if (paccOut && np) {
     PCHK(cudaMalloc((void**)&dP, np*(size_t)c->ndim*sizeof(double)));
     const unsigned nbp = (unsigned)((np + RB - 1)/RB);
-    if (c->ndim == 3) k_emit_pacc<3><<<nbp, RB, 0, c->stream>>>(dJ, dS, c->api[S_MASS], c->pacc, c->nSlots, np, dP);
-    else              k_emit_pacc<2><<<nbp, RB, 0, c->stream>>>(dJ, dS, c->api[S_MASS], c->pacc, c->nSlots, np, dP);
+    if (c->paccMode != PACC_FULL) {
+      if (!c->rowsAtEval) { cleanup(); return sphb200_fail(c, "download_pair_accelerations: the node rows of the evaluation were re-packed since; evaluate the derivatives again"); }
+      if (sphb200_inverse_perm(c)) { cleanup(); return 1; }
+    }
+#define SPHB200_EMIT(D, M) k_emit_pacc<D, M><<<nbp, RB, 0, c->stream>>>(dI, dJ, dS, c->invPerm, c->rows, c->api[S_MASS], c->pacc, c->nSlots, np, dP)
+    if (c->ndim == 3) { if (c->paccMode == PACC_ISO) SPHB200_EMIT(3, PACC_ISO); else if (c->paccMode == PACC_TENSOR) SPHB200_EMIT(3, PACC_TENSOR); else SPHB200_EMIT(3, PACC_FULL); }
+    else              { if (c->paccMode == PACC_ISO) SPHB200_EMIT(2, PACC_ISO); else if (c->paccMode == PACC_TENSOR) SPHB200_EMIT(2, PACC_TENSOR); else SPHB200_EMIT(2, PACC_FULL); }
+#undef SPHB200_EMIT
     c->stats.launches++;
     PCHK(cudaMemcpyAsync(paccOut, dP, np*(size_t)c->ndim*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   }

@@ -1141,6 +1141,7 @@ static bool sphb200_nbr_v2_wanted() {          // read at every build: the tests
 
 static int pack_rows_impl(sphb200_ctx* c, bool range, size_t first, size_t count) {
   if (!c->sortValid) return sphb200_fail(c, "internal: pack_rows before sort");
+  c->rowsAtEval = false;                       // the rows are about to change: compressed pair forces can no longer be expanded
   const bool tens = c->opt.epsTensile != 0.0;
   const bool needQ = (c->opt.Qkind == SPHB200_Q_LIMITED_MG) || c->opt.balsara;
   const bool mult = c->have[S_FCL] && c->have[S_FCQ];

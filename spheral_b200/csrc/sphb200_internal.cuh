@@ -10,8 +10,11 @@
 //   nbr        : neighbour lists of internal nodes, sliced-ELL: tile t = sorted slots [32t,32t+32),
 //                entry k of lane l at nbr[tileOff[t] + 32*k + l] = sorted slot of the neighbour.
 //   d_*        : derivative fields, SoA per component, sorted order.
-//   pacc       : deltaDvDt of every directed edge, blocked like nbr: component c of edge `slot` at pacc_index<DIM>(slot, c)
-//                = DIM*(slot & ~31) + 32*c + (slot & 31), i.e. one 32-lane line per (list row, component).
+//   pacc       : the pair force of every directed edge (deltaDvDt of SPH.cc:427 in i's orientation), blocked like nbr: word c of edge
+//                `slot` at pacc_at(W, slot, c) = W*(slot & ~31) + 32*c + (slot & 31), one 32-lane line per (list row, word).  W words per
+//                edge, by storage mode (ctx::paccMode): FULL the DIM components; ISO one scalar sd with delta = sd r_ij (every H a
+//                multiple of the identity); TENSOR two scalars (a, b) with delta = a H_i.(H_i.r_ij) + b H_j.(H_j.r_ij).  The compressed
+//                modes are expanded by their readers (k_energy, k_emit_pacc) from the node rows of the evaluation.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -141,7 +144,9 @@ struct sphb200_ctx {
 
   // derivatives (sorted, SoA per component): deriv[slot] points at width*cap doubles, component c at + c*cap
   double* deriv[DV_COUNT] = {nullptr};
-  double* pacc = nullptr; size_t paccCap = 0;   // ndim * nSlots
+  double* pacc = nullptr; size_t paccCap = 0;   // paccWidth * nSlots
+  int paccMode = 0, paccWidth = 0;              // PACC_FULL | PACC_ISO | PACC_TENSOR of the last evaluation, words per directed edge
+  bool rowsAtEval = false;                      // `rows` still hold what the last evaluation read (the compressed modes expand against them)
   bool derivsValid = false;
   // node-wise derivatives outlive the connectivity they were computed on (CheapSynchronousRK2 advances the next step's trial
   // state with them after the neighbour update): the sorted order of the evaluation is kept beside them
@@ -196,8 +201,10 @@ template <int DIM> struct Dm;
 template <> struct Dm<3> { static constexpr int NS = 6, NT = 9, ROW = 16, R_POS = 0, R_VEL = 3, R_H = 6, R_M = 12, R_RHO = 13, R_PRHO = 14, R_CS = 15; };
 template <> struct Dm<2> { static constexpr int NS = 3, NT = 4, ROW = 12, R_POS = 0, R_VEL = 2, R_H = 4, R_M = 7, R_RHO = 8, R_PRHO = 9, R_CS = 10; };
 
-template <int DIM> __host__ __device__ __forceinline__ unsigned long long pacc_index(unsigned long long slot, int comp) {
-  return (unsigned long long)DIM*(slot & ~31ull) + 32ull*(unsigned)comp + (slot & 31ull);
+enum { PACC_FULL = 0, PACC_ISO = 1, PACC_TENSOR = 2 };
+__host__ __device__ __forceinline__ int pacc_width(int mode, int ndim) { return mode == PACC_ISO ? 1 : (mode == PACC_TENSOR ? 2 : ndim); }
+__host__ __device__ __forceinline__ unsigned long long pacc_at(int width, unsigned long long slot, int word) {
+  return (unsigned long long)width*(slot & ~31ull) + 32ull*(unsigned)word + (slot & 31ull);
 }
 
 __device__ __forceinline__ double d_sgn(double x) { return x < 0.0 ? -1.0 : 1.0; }
