@@ -285,6 +285,122 @@ __global__ void __launch_bounds__(RB) k_pack(PackArgs a) {
   }
 }
 
+// ---- K1d': the same rows, written the other way round (round 2) -----------------------------------------------------------------
+// k_pack walks the SORTED slots: every field is gathered through perm (32 different lines per load instruction) and every thread
+// writes its own 128-byte row eight bytes at a time (32 different lines per store instruction); the ncu profile of the 8 M step shows
+// it LSU-bound at 2 TB/s of DRAM traffic (1.7 ms).  k_pack_scatter walks the nodes in HOST order instead: a warp reads the fields of
+// 32 consecutive nodes (coalesced), builds their rows in shared memory and then writes each row to its sorted slot with one full
+// 128-byte line per 8 lanes (64 bytes per 4 lanes for the FP32 rows).  Same values bit for bit (the arithmetic is shared).
+template <int DIM>
+__device__ __forceinline__ void pack_one(const PackArgs& a, size_t o, double* r, float* f, double* aux, bool& aniso) {
+  using D = Dm<DIM>;
+#pragma unroll
+  for (int k = 0; k < DIM; ++k) { r[D::R_POS + k] = a.pos[o*DIM + k]; r[D::R_VEL + k] = a.vel ? a.vel[o*DIM + k] : 0.0; }
+  double Hn[D::NS];
+#pragma unroll
+  for (int k = 0; k < D::NS; ++k) { Hn[k] = a.H[o*D::NS + k]; r[D::R_H + k] = Hn[k]; }
+  aniso = !((DIM == 3) ? (Hn[1] == 0.0 && Hn[2] == 0.0 && Hn[4] == 0.0 && Hn[3] == Hn[0] && Hn[5] == Hn[0]) : (Hn[1] == 0.0 && Hn[2] == Hn[0]));
+  const double m = a.mass ? a.mass[o] : 0.0, rho = a.rho ? a.rho[o] : 1.0, P = a.P ? a.P[o] : 0.0;
+  const double om = a.omega ? a.omega[o] : 1.0, cs = a.cs ? a.cs[o] : 0.0;
+  const double safeOmega = om/(om*om + 1.0e-30);                 // safeInv, Utilities/safeInv.hh:13-19 (SPH.cc:310)
+  r[D::R_M] = m; r[D::R_RHO] = rho; r[D::R_CS] = cs;
+  r[D::R_PRHO] = a.rawP ? P : safeOmega*P/(rho*rho);             // SPH.cc:425 with Peff == P
+  if (DIM == 2) r[11] = 0.0;
+  aux[0] = sym_det<DIM>(Hn); aux[1] = 1.0/rho; aux[2] = (P < 0.0 ? -P : 0.0); aux[3] = safeOmega/(rho*rho);
+  // FP32 pre-filter row: see k_pack for the error model
+  double hf = 0.0;
+#pragma unroll
+  for (int k = 0; k < D::NS; ++k) hf += Hn[k]*Hn[k];
+  if (DIM == 3) hf += Hn[1]*Hn[1] + Hn[2]*Hn[2] + Hn[4]*Hn[4]; else hf += Hn[1]*Hn[1];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float rel = 0.f;
+    if (k < DIM) {
+      const double x = a.pos[o*DIM + k];
+      const int c = cell_coord(x, a.g.lo[k], a.g.cs[k], a.g.nc[k]);
+      rel = (float)(x - (a.g.lo[k] + (double)c*a.g.cs[k]));
+    }
+    f[k] = rel;
+  }
+  const double csw = a.csmax;
+  double lmin, lmax;
+  sym_eig_bounds<DIM>(Hn, lmin, lmax);
+  lmin -= 1.0e-9*lmax; lmax *= 1.0 + 1.0e-9;
+  float r2lo = -1.f, r2hi = 3.0e38f;
+  if (lmin > 0.0) {
+    const double Rmax = a.kext/lmin, Rmin = a.kext/lmax;
+    const double mhi = 2.0e-6*Rmax*csw + 1.0e-6*Rmax*Rmax + 1.0e-11*csw*csw;
+    const double mlo = 2.0e-6*Rmin*csw + 1.0e-6*Rmin*Rmin + 1.0e-11*csw*csw;
+    const double hi = (Rmax*Rmax + mhi)*(1.0 + 1.0e-7);
+    if (hi < 3.0e38) r2hi = __double2float_ru(hi);
+    if (Rmin > 1.0e-3*csw) r2lo = __double2float_rd((Rmin*Rmin - mlo)*(1.0 - 1.0e-7));
+  }
+  f[Fr::R_R2LO] = r2lo; f[Fr::R_R2HI] = r2hi;
+  const double B = sqrt(hf)*csw*7.62939453125e-06;       // 2^-17
+  const double lo = fmax(a.kext - B, 0.0), hi2 = a.kext + B;
+  f[Fr::R_E2LO] = __double2float_rd(lo*lo*(1.0 - 1.0e-6));
+  f[Fr::R_E2HI] = __double2float_ru(hi2*hi2*(1.0 + 1.0e-6));
+  f[7] = __uint_as_float((uint32_t)o);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) f[Fr::R_H + k] = (k < D::NS) ? (float)Hn[k] : 0.f;
+  f[14] = 0.f; f[15] = 0.f;
+}
+
+constexpr int PS_WARPS = 4;
+template <int DIM>
+__global__ void __launch_bounds__(32*PS_WARPS) k_pack_scatter(PackArgs a) {
+  using D = Dm<DIM>;
+  constexpr int ROW = D::ROW, RS = ROW + 2;                      // +2 doubles: conflict-free 128-bit reads of a row's chunks
+  __shared__ __align__(16) double srow[PS_WARPS][32*RS];
+  __shared__ __align__(16) float sfr[PS_WARPS][32*(Fr::ROW + 4)];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const size_t o0 = ((size_t)blockIdx.x*PS_WARPS + w)*32;
+  if (o0 >= a.n) return;
+  const size_t o = o0 + lane;
+  const bool in = o < a.n;
+  uint32_t s = 0;
+  if (in) {
+    double r[ROW], aux[4]; float f[Fr::ROW]; bool aniso;
+    pack_one<DIM>(a, o, r, f, aux, aniso);
+    s = a.invPerm[o];
+    if (aniso) *a.aniso = 1ull;
+#pragma unroll
+    for (int k = 0; k < ROW; ++k) srow[w][lane*RS + k] = r[k];
+#pragma unroll
+    for (int k = 0; k < Fr::ROW; ++k) sfr[w][lane*(Fr::ROW + 4) + k] = f[k];
+    a.aux2[2*(size_t)s] = aux[0]; a.aux2[2*(size_t)s + 1] = aux[1];
+    if (a.auxPneg) { a.auxPneg[s] = aux[2]; a.auxSomr2[s] = aux[3]; }
+    if (a.auxDvDxQ) {
+#pragma unroll
+      for (int k = 0; k < D::NT; ++k) a.auxDvDxQ[(size_t)s*D::NT + k] = a.DvDxQ[o*D::NT + k];
+    }
+    if (a.auxfCl) { a.auxfCl[s] = a.fCl[o]; a.auxfCq[s] = a.fCq[o]; }
+    if (a.skey) a.skey[s] = a.keyApi[o];
+  }
+  __syncwarp();
+  const int nhere = (int)min((size_t)32, a.n - o0);
+  // node rows: CH 16-byte chunks each; 32/CH... lanes are dealt (row, chunk) pairs in order, so consecutive lanes fill one line
+  constexpr int CH = ROW/2;
+  for (int t = lane; t < 32*CH; t += 32) {
+    const int rr = t/CH, ch = t - rr*CH;
+    const uint32_t sr = __shfl_sync(0xffffffffu, s, rr);
+    if (rr < nhere) {
+      const double2 v = *reinterpret_cast<const double2*>(&srow[w][rr*RS + 2*ch]);
+      *reinterpret_cast<double2*>(a.rows + (size_t)sr*ROW + 2*ch) = v;
+    }
+  }
+  if (a.frows) {
+    for (int t = lane; t < 32*4; t += 32) {
+      const int rr = t >> 2, ch = t & 3;
+      const uint32_t sr = __shfl_sync(0xffffffffu, s, rr);
+      if (rr < nhere) {
+        const float4 v = *reinterpret_cast<const float4*>(&sfr[w][rr*(Fr::ROW + 4) + 4*ch]);
+        *reinterpret_cast<float4*>(a.frows + (size_t)sr*Fr::ROW + 4*ch) = v;
+      }
+    }
+  }
+}
+
 // ---- K2: neighbour build ----------------------------------------------------------------------------------------------------
 // One warp per tile of 32 consecutive Morton-sorted nodes; lane <-> node i.  The candidates of a tile are the nodes of the
 // union of the 3^DIM cell stencils of the distinct cells its nodes live in, visited in a fixed order, so every candidate j
@@ -1181,9 +1297,18 @@ static int pack_rows_impl(sphb200_ctx* c, bool range, size_t first, size_t count
   // k_nbr_build; k_nbr_build2 places both nodes in the frame of the tile (|k_i| <= 1, |k_j| <= 2): 12 * 2^-24, budgeted as 14
   c->nbrV2 = sphb200_nbr_v2_wanted() && c->stencilR == 1 && !c->fineWalk;
   a.csmax = std::max(c->grid.cs[0], std::max(c->grid.cs[1], c->ndim == 3 ? c->grid.cs[2] : 0.0))*(c->nbrV2 ? 2.0 : (3.0*c->stencilR + 4.0)/7.0);
-  const unsigned nb = (unsigned)((c->n + RB - 1)/RB);
-  if (c->ndim == 3) k_pack<3, false><<<nb, RB, 0, c->stream>>>(a); else k_pack<2, false><<<nb, RB, 0, c->stream>>>(a);
-  KERNEL_CHECK(c, "k_pack");
+  static const bool gatherPack = [] { const char* e = std::getenv("SPHB200_PACK_GATHER"); return e && e[0] == '1'; }();     // A/B switch: the round-1 kernel
+  if (gatherPack) {
+    const unsigned nb = (unsigned)((c->n + RB - 1)/RB);
+    if (c->ndim == 3) k_pack<3, false><<<nb, RB, 0, c->stream>>>(a); else k_pack<2, false><<<nb, RB, 0, c->stream>>>(a);
+    KERNEL_CHECK(c, "k_pack");
+  } else {
+    if (sphb200_inverse_perm(c)) return 1;
+    a.invPerm = c->invPerm;
+    const unsigned nb = (unsigned)((c->n + 32*PS_WARPS - 1)/(32*PS_WARPS));
+    if (c->ndim == 3) k_pack_scatter<3><<<nb, 32*PS_WARPS, 0, c->stream>>>(a); else k_pack_scatter<2><<<nb, 32*PS_WARPS, 0, c->stream>>>(a);
+    KERNEL_CHECK(c, "k_pack_scatter");
+  }
   c->rowsValid = true;
   return 0;
 }
