@@ -197,6 +197,9 @@ def dist_setup():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
+        # keep NCCL's own account of the communicator (ranks, transport: P2P / NVLS over NVLink) in the run's stderr
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         import torch
         import torch.distributed as dist_
         torch.cuda.set_device(local)
