@@ -198,8 +198,10 @@ def dist_setup():
     dist = None
     if world > 1:
         # keep NCCL's own account of the communicator (ranks, transport: P2P / NVLS over NVLink) in the run's stderr
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ["NCCL_DEBUG_SUBSYS"] = "INIT"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")          # stdout carries the JSON line only
         import torch
         import torch.distributed as dist_
         torch.cuda.set_device(local)
