@@ -379,7 +379,9 @@ class HotPath:
         up = ["position", "velocity", "H", "mass", "massDensity", "specificThermalEnergy", "pressure", "soundSpeed", "omegaGradh"]
         if crk:
             up[-1] = "DvDxQ"
-        self.down_names = ("DxDt", "DrhoDt", "DvDt", "DepsDt", "DvDx", "DHDt", "Hideal")
+        # what a host-side integrator reads back: the derivatives State::update consumes; "new H" only where the path computes it (the
+        # ASPH ideal H is not part of evaluateDerivatives -- ASPHSmoothingScale.cc:110-147 -- so the field would be 48 B/node of zeros)
+        self.down_names = ("DxDt", "DrhoDt", "DvDt", "DepsDt", "DvDx", "DHDt") + (() if spec["asph"] else ("Hideal",))
         self.hs, self.pinned, self.up_mask, self.h2d = L.HostState(), [], 0, 0
         dp = self.dp = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
         for k in up:

@@ -210,6 +210,13 @@ int alloc_nodes(sphb200_ctx* c, size_t n) {
 int sphb200_join_uploads(sphb200_ctx* c, bool all) {
   if (c->pendGeomUp) { CU_CHECK(c, cudaStreamWaitEvent(c->stream, c->evGeomUp, 0)); c->pendGeomUp = false; }
   if (all && c->pendRestUp) { CU_CHECK(c, cudaStreamWaitEvent(c->stream, c->evRestUp, 0)); c->pendRestUp = false; }
+  if (all && c->ghostRefillPending) {
+    // plane ghosts were generated while the non-geometric fields of their control nodes were still on their way from the host
+    // (sphb200_reflect_set_ghost_nodes waits for positions and H only, so that the neighbour build overlaps the rest of the upload):
+    // now that everything has landed, give those ghosts the values of their controls
+    c->ghostRefillPending = false;
+    if (sphb200_reflect_apply_ghosts(c, ~((1u << S_POS) | (1u << S_H)))) return 1;
+  }
   return 0;
 }
 
@@ -361,10 +368,16 @@ int sphb200_set_kernel_table(sphb200_ctx* c, int which, double kext, double xmin
 
 int sphb200_set_nodes(sphb200_ctx* c, size_t nInternal, size_t nGhost) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
+  CU_CHECK(c, cudaSetDevice(c->device));
   const size_t n = nInternal + nGhost;
   if (n >= 0x7fffffffull) return sphb200_fail(c, "set_nodes: more than 2^31-1 nodes per GPU is not supported");
-  if (n > c->cap) CU_CHECK(c, cudaStreamSynchronize(c->stream));      // reallocation frees arrays in-flight work may use
+  if (n > c->cap) {      // reallocation frees arrays that in-flight kernels AND in-flight uploads may use: drain both streams first
+    const bool refill = c->ghostRefillPending; c->ghostRefillPending = false;     // the ghosts are being redefined anyway
+    if (sphb200_join_uploads(c, true)) return 1;
+    c->ghostRefillPending = refill;
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->copyStream));
+  }   // otherwise only the node counts change: uploads still in flight on the copy stream keep landing in the same arrays
   if (alloc_nodes(c, n)) return 1;
   if (n != c->n || nInternal != c->nInt) { c->sortValid = c->rowsValid = c->pairsValid = c->derivsValid = false; }
   c->nInt = nInternal; c->nGhost = nGhost; c->n = n;

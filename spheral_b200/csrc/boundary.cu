@@ -309,7 +309,11 @@ int sphb200_reflect_configure(sphb200_ctx* c, int nPlanes, const double* points,
 
 int sphb200_reflect_set_ghost_nodes(sphb200_ctx* c, size_t* nGhostOut) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
-  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
+  // Which nodes become control nodes, and where their ghosts go, depends on positions and H alone: only those uploads are waited for.
+  // If other fields are still in flight on the copy stream the ghosts get whatever values are on the device now and are refilled when
+  // the first call that needs every field joins the uploads (sphb200_join_uploads) -- the neighbour build in between needs geometry only.
+  const bool restInFlight = c->pendRestUp;
+  CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, false)) return 1;
   if (!c->have[S_POS] || !c->have[S_H]) return sphb200_fail(c, "reflect_set_ghost_nodes: position and H must be on the device");
   if (!c->W.set) return sphb200_fail(c, "reflect_set_ghost_nodes: kernel table not set (need the kernel extent)");
   const double kext = std::max(c->W.kext, c->WQ.set ? c->WQ.kext : 0.0);
@@ -355,6 +359,7 @@ int sphb200_reflect_set_ghost_nodes(sphb200_ctx* c, size_t* nGhostOut) {
     if (fill_plane(c, p, mask)) return 1;
   }
   c->sortValid = c->rowsValid = c->pairsValid = false;
+  c->ghostRefillPending = restInFlight && c->nGhost > 0;
   if (nGhostOut) *nGhostOut = c->nGhost;
   return 0;
 }

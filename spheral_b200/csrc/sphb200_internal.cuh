@@ -79,6 +79,7 @@ struct sphb200_ctx {
   cudaStream_t copyStream = nullptr;
   cudaEvent_t evGeomUp = nullptr, evRestUp = nullptr, evMainMark = nullptr;
   bool pendGeomUp = false, pendRestUp = false;
+  bool ghostRefillPending = false;  // plane ghosts exist whose non-geometric values predate an upload still in flight (sphb200_join_uploads refills them)
   std::string err;
 
   size_t nInt = 0, nGhost = 0, n = 0, cap = 0;
