@@ -357,8 +357,6 @@ class HotPath:
         self.torch, self.L, self.C = torch, L, C
         self.spec, self.rank, self.world, self.local = spec, rank, world, local
         crk = self.crk = spec.get("hydro") == "crksph"
-        if crk and world > 1:
-            raise SystemExit("the CRKSPH workload is single-GPU in bench.py (tests/mgpu_parity.py covers its decomposed run)")
         if weak:      # one full cube per rank, side by side along x (round-1 measurement)
             st, N = make_inputs(spec, seed=14892042 + rank, n=n, shift=float(rank))
             self.lo, self.hi = float(rank), float(rank + 1)
@@ -397,7 +395,8 @@ class HotPath:
         self.dsph = None
         if world > 1:
             from spheral_b200 import distributed as D
-            self.dsph = D.DistributedSPH(e, 0, self.lo, self.hi)
+            # CRKSPH: the volumes and the RK coefficients are state fields too and travel once the package has computed them
+            self.dsph = D.DistributedSPH(e, 0, self.lo, self.hi, extra_fields=("volume", "rkCorrections") if crk else ())
 
     def step(self):
         e = self.e
@@ -406,9 +405,13 @@ class HotPath:
             self.dsph.refresh_ghosts(build=True, boundary_ghosts=nPG)    # ... then the slab halo over NVLink, then K1 + K2
         else:
             e.build_pairs()
-        if self.crk:                                                     # RKCorrections::preStepInitialize / initialize
-            e.crk_compute_volume()
+        if self.crk:                                                     # RKCorrections::preStepInitialize / initialize, each followed
+            e.crk_compute_volume()                                       # by applyGhostBoundaries (RKCorrections.cc:298-372)
+            if self.dsph is not None:
+                self.dsph.mark_ready("volume"); self.dsph.apply_ghosts(("volume",))
             e.crk_compute_corrections()
+            if self.dsph is not None:
+                self.dsph.mark_ready("rkCorrections"); self.dsph.apply_ghosts(("rkCorrections",))
         e.evaluate_derivatives(0.0, 1.0)
 
     def download(self):
