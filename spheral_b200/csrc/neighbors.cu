@@ -897,7 +897,10 @@ constexpr int Q2_CHUNKB = 32*4 + 32*2; // per chunk of 32 survivors: one hit mas
 // STAGEH: the H tensors of the survivors are staged in the ring for stage 2.  When the previous build saw only isotropic H, stage 2
 // is a rarity (a 1e-5-wide shell) and fetches its two rows from global memory instead: 16 of ~31 LSU wavefronts per run less.
 template <int DIM, bool STAGEH>
-__global__ void __launch_bounds__(32*NB_WARPS) k_nbr_build2(NbrArgs a, int maxChunks) {
+#ifndef SPHB200_NB2_CTAS
+#define SPHB200_NB2_CTAS 4
+#endif
+__global__ void __launch_bounds__(32*NB_WARPS, SPHB200_NB2_CTAS) k_nbr_build2(NbrArgs a, int maxChunks) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int w = threadIdx.x >> 5;
   const size_t perWarp = (size_t)Q2_FIXED + (size_t)maxChunks*Q2_CHUNKB;

@@ -180,10 +180,11 @@ class DistributedSPH:
 
     @property
     def maskB(self):
-        """Every field but positions and H that travels: the hydro's state, the extra fields declared ready, and the artificial
-        viscosity's fields once they hold values on the device (every rank runs the same call sequence, so all agree)."""
-        m = self._maskB_base | field_mask(tuple(x for x in self.extra if x in self.ready))
-        return m | (self._maskB_opt & self.e.state_fields_present())
+        """Every field but positions and H that travels: the hydro's state, the artificial viscosity's fields and the extra fields
+        declared ready -- each only if it holds values on the device (CRKSPH, for one, has no grad-h correction field; every rank runs
+        the same call sequence, so all ranks agree on the set)."""
+        m = self._maskB_base | self._maskB_opt | field_mask(tuple(x for x in self.extra if x in self.ready))
+        return m & self.e.state_fields_present()
 
     def mark_ready(self, *names):
         """A package has computed these extra fields on the internal nodes: from now on they travel with the halo."""
