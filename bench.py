@@ -191,6 +191,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def claim_stdout():
+    """stdout carries the ONE JSON line and nothing else: file descriptor 1 is pointed at stderr for the duration of the run (libraries
+    that write to it directly -- NCCL's version banner, a compiler invoked by a build step -- land in the log) and the returned file
+    object, a duplicate of the original descriptor, receives the line at the end."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def dist_setup():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -485,6 +495,7 @@ def main():
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return 0
+        out = claim_stdout()
         val, tmed, N, npairs, sample = cpu_port_run(spec, cpu_sample, max(args.steps, 1), min(warmup, 2), threads, args.xsph)
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": tmed*1e3, "higher_is_better": True,
@@ -492,10 +503,11 @@ def main():
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                                  "note": "oracle restatement on host cores -- not the Spheral MPI build (unbuildable here)"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
         return 0
 
     # ------------------------------------------------------------------ our arm (GPU) ---------------------------------------
+    out = claim_stdout()
     rank, world, local, dist = dist_setup()
     affinity = pin_to_gpu_numa(local)
     hp = HotPath(spec, n, rank, world, local, dist, args.xsph)
@@ -643,7 +655,7 @@ def main():
                 val, tmed, Ns, npairs, sample = cpu_port_run(spec, cpu_sample, 3, 1, threads, args.xsph)
                 line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                                         "note": "oracle restatement on host cores -- not the Spheral MPI build (unbuildable here)"}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0
