@@ -556,6 +556,11 @@ def main():
         rk2 = {"ms_per_step": rk_s/nrk*1e3, "value": hp.N*nrk/rk_s, "unit": UNIT, "steps": nrk, "last_dt": rk.lastDt, "dt_reason": rk.lastDtReason,
                "what": "CheapSynchronousRK2 step with the state resident in HBM (ghosts, build_pairs, sum density, dt, State::update x2, grad-h x2, "
                        "evaluateDerivatives, compatible energy); one 16-byte read-back (dt) per step"}
+        # the same with the end-of-step grad-h correction computed on demand only (integrator.lazyOmega: no evaluation reads it)
+        rk.lazyOmega = True
+        rk_l, _ = hp.timed(rk.step, nrk, dist)
+        rk.ensureOmega()
+        rk2["ms_per_step_lazy_omega"] = rk_l/nrk*1e3
         e.set_nodes(hp.N, 0)
         e.upload_state_pinned(hp.up_mask, hp.hs)
         e.sync()

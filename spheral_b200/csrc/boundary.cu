@@ -57,9 +57,17 @@ __global__ void __launch_bounds__(RB) k_reflect_hmax(const double* __restrict__ 
     for (int q = 0; q < NS; ++q) Hi[q] = H[i*NS + q];
 #pragma unroll
     for (int q = 0; q < DIM; ++q) r[q] = pos[i*DIM + q];
-    const double hi = 1.0/sym_min_eigenvalue<DIM>(Hi);
     const double dmin = fmin(fabs(signed_distance<DIM>(pl, r)), fabs(signed_distance_exit<DIM>(pl, r)));
-    if (dmin < kext*hi) v = hi;
+    // Gershgorin: lambda_min >= min over rows of (diagonal - sum |off-diagonal|).  Where that bound is positive it caps h_i from
+    // above, and a node farther from the plane than kext times the cap cannot pass the test below: the eigenvalue (the expensive
+    // part of this pass: 0.17 ms per plane at 8 M nodes) is only computed for the few layers of nodes next to the plane.
+    double glo;
+    if (DIM == 3) glo = fmin(Hi[0] - fabs(Hi[1]) - fabs(Hi[2]), fmin(Hi[3] - fabs(Hi[1]) - fabs(Hi[4]), Hi[5] - fabs(Hi[2]) - fabs(Hi[4])));
+    else glo = fmin(Hi[0] - fabs(Hi[1]), Hi[2] - fabs(Hi[1]));
+    if (!(glo > 0.0) || dmin*glo < kext*(1.0 + 1.0e-12)) {
+      const double hi = 1.0/sym_min_eigenvalue<DIM>(Hi);
+      if (dmin < kext*hi) v = hi;
+    }
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, off));

@@ -18,8 +18,14 @@ INTEGRATE_DENSITY, RIGOROUS_SUM_DENSITY = 0, 1      # MassDensityType (Hydro/Gen
 class CheapSynchronousRK2:
     def __init__(self, engine, step_options=None, densityUpdate=RIGOROUS_SUM_DENSITY, gradhCorrection=True, cfl=0.25,
                  useVelocityMagnitudeForDt=False, dtMin=0.0, dtMax=1.0e100, dtGrowth=2.0, allowDtCheck=False,
-                 ghostRefresh=None, reflectingPlanes=None, distributed=None, boundaries=None):
+                 ghostRefresh=None, reflectingPlanes=None, distributed=None, boundaries=None, lazyOmega=False):
         self.engine = engine
+        # lazyOmega: the grad-h correction recomputed at the END of a step (SPHBase::postStateUpdate after the full update,
+        # CheapSynchronousRK2.cc:115) is never read by an evaluation -- the next step recomputes it on its trial state before
+        # evaluateDerivatives and the dt vote does not use it.  With lazyOmega it is computed only when somebody looks
+        # (ensureOmega(), dumpState()), on the connectivity of the step that produced the state, as the reference does.  Off by
+        # default: engine.download_state("omegaGradh") between steps then needs ensureOmega() first.
+        self.lazyOmega, self._omegaStale = bool(lazyOmega), False
         self.so = step_options if step_options is not None else E.make_step_options()
         self.densityUpdate, self.gradhCorrection = densityUpdate, gradhCorrection
         self.cfl, self.useVelocityMagnitudeForDt = cfl, useVelocityMagnitudeForDt
@@ -79,13 +85,25 @@ class CheapSynchronousRK2:
         if self.ghostRefresh is not None:
             self.ghostRefresh()
 
-    def _post_state_update(self):
+    def _post_state_update(self, endOfStep=False):
         """Integrator::postStateUpdate (Integrator.cc:252-271)."""
         e = self.engine
         if self._needQ:
             e.copy_DvDx_to_Q()                       # ArtificialViscosityHandle.cc:165-180
         if self.gradhCorrection:
+            if endOfStep and self.lazyOmega:
+                self._omegaStale = True
+                return
             e.compute_omega_gradh()                  # SPHBase.cc:539-547
+            self._omegaStale = False
+            self._ghosts()
+
+    def ensureOmega(self):
+        """lazyOmega: bring the grad-h correction of the current state up to date (no-op otherwise).  Must be called before the
+        next step rebuilds the connectivity to reproduce the reference's end-of-step value."""
+        if self._omegaStale:
+            self.engine.compute_omega_gradh()
+            self._omegaStale = False
             self._ghosts()
 
     def _pre_step_initialize(self):
@@ -171,7 +189,7 @@ class CheapSynchronousRK2:
         e.state_update(so, dt, False)
         self.currentTime = t + dt
         self._ghosts()
-        self._post_state_update()
+        self._post_state_update(endOfStep=True)
         if self.reflectingPlanes:
             e.reflect_enforce()                       # enforceBoundaries (CheapSynchronousRK2.cc:121-123)
         self.currentCycle += 1
@@ -180,6 +198,7 @@ class CheapSynchronousRK2:
 
     def step(self, maxTime=1.0e100):
         """Integrator::step(maxTime) (Integrator.cc:66-111): neighbour update, then up to 10 attempts with a halved dt."""
+        self._omegaStale = False                      # a stale end-of-step grad-h correction dies here, unread (lazyOmega)
         self._set_ghost_nodes()                       # setGhostNodes
         self.engine.build_pairs()                     # Neighbor::updateNodes + ConnectivityMap::computeConnectivity
         ok, count = False, 0
@@ -203,6 +222,7 @@ class CheapSynchronousRK2:
         advance and dt vote read (SPHBase.cc:714-735 dumps them for the same reason), and the integrator's counters
         (Integrator.cc dumpState: time, cycle, lastDt)."""
         e = self.engine
+        self.ensureOmega()
         names = [k for k in L.STATE_FIELDS if k not in ("fCl", "fCq", "volume", "rkCorrections") or (self._crk and k in ("volume", "rkCorrections"))]
         have = []
         for k in names:

@@ -311,3 +311,38 @@ def test_iterate_ideal_h(oracle, mods, ndim, n, nPerh):
     e.build_pairs(); e.evaluate_derivatives()
     hid = e.download_derivs("Hideal")["Hideal"]
     assert np.abs(hid[:, 0]/got[:, 0] - 1.0).max() <= 10*tol
+
+
+@pytest.mark.gpu
+def test_lazy_omega_is_the_eager_omega_when_asked_for(oracle, mods):
+    """integrator.lazyOmega: the end-of-step grad-h correction is computed only on demand (ensureOmega / dumpState); the state it
+    then shows, and every later step, are bit-identical to the eager integrator's."""
+    engine, integrator = mods
+    ndim, nPerh = 3, 1.51
+    st, nInt, _ = common.make_problem(ndim, 10, nPerh=nPerh)
+    st["velocity"] = 0.3*st["velocity"]
+    WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    _, po = common.opts_pair(oracle, engine, ndim, nPerh=nPerh)
+    outs = []
+    for lazy in (False, True):
+        e = engine.Engine(ndim, options=po)
+        e.set_kernel_table(WT)
+        e.set_nodes(nInt, 0)
+        e.upload_state(**st)
+        rk = integrator.CheapSynchronousRK2(e, engine.make_step_options(), densityUpdate=1, lazyOmega=lazy)
+        rk.initializeDerivatives()
+        for _ in range(2):
+            assert rk.step()
+        if lazy:
+            stale = e.download_state("omegaGradh")["omegaGradh"].copy()
+            rk.ensureOmega()
+        a = e.download_state("omegaGradh", "position", "velocity", "specificThermalEnergy", "H")
+        assert rk.step()
+        rk.ensureOmega()
+        b = e.download_state("omegaGradh", "position", "velocity", "specificThermalEnergy", "H")
+        outs.append((a, b, rk.lastDt))
+    for k in outs[0][0]:
+        assert np.array_equal(outs[0][0][k], outs[1][0][k]), k
+        assert np.array_equal(outs[0][1][k], outs[1][1][k]), k
+    assert outs[0][2] == outs[1][2]
+    assert not np.array_equal(stale, outs[1][0]["omegaGradh"])        # the lazy integrator really had skipped it
