@@ -4,19 +4,27 @@
 // pair list once and scatters the discrete pair work into both nodes; here node i walks its own directed edges
 // (which hold deltaDvDt of SPH.cc:427 in i's orientation) and gathers only its own share, so no atomics are needed.
 #include "sphb200_internal.cuh"
+#include "nbr_ring.cuh"
+#include <algorithm>
 #include <cfloat>
 
 namespace {
 
 constexpr int RB = 256;
 
-// erow[s] = { v + DvDt*hdt (DIM), DepsDt0, m, original index | position (DIM), H (NS) }   stride ES<DIM, MODE>
+// erow[s] = { v + DvDt*hdt (DIM), DepsDt0, m, original index | position (DIM), H (NS) }, one record per sorted node with the stride of a node
+// row (so that the record ring of nbr_ring.cuh streams it like one); USED doubles of it are filled.
 // The geometry tail exists only for the compressed pair-force modes (PACC_ISO: position and 1/h; PACC_TENSOR: position and H), which are
 // expanded here from the node rows the evaluation read: delta = sd r_ij, or a H_i.(H_i.r_ij) + b H_j.(H_j.r_ij).
 template <int DIM, int MODE> struct ERow {
   static constexpr int GEOM = (MODE == PACC_FULL) ? 0 : (MODE == PACC_ISO ? DIM + 1 : DIM + Dm<DIM>::NS);
-  static constexpr int ES = DIM + 3 + GEOM;
+  static constexpr int USED = DIM + 3 + GEOM;
+  static constexpr int ES = Dm<DIM>::ROW;
+  static constexpr int COPY = (USED*8 + 15)/16*16;          // bytes of a record the ring copies
+  static_assert(USED <= ES, "the energy record must fit a node row");
 };
+constexpr int EW = 8, ESTAGES = 4;                           // warps per CTA and ring depth of k_energy
+template <int DIM, int MODE> using ERing = NbrRing<DIM, 0, 0, ESTAGES, ERow<DIM, MODE>::COPY, false>;
 
 template <int DIM, int MODE>
 __global__ void __launch_bounds__(RB) k_energy_prep(const double* __restrict__ velApi, const double* __restrict__ massApi,
@@ -70,70 +78,79 @@ __device__ __forceinline__ void pacc_expand(const double* __restrict__ pacc, uns
   }
 }
 
+// One warp per tile, lane <-> node i, persistent CTAs; the neighbours' records arrive through the warp-cooperative ring (a per-lane
+// gather of the 120-byte record was L1-wavefront bound: 14.1 ms of the 83 ms RK2 step at 8 M, profiles/r02_launches_rk2_step_8m_summary.txt).
 template <int DIM, int MODE>
-__global__ void __launch_bounds__(128) k_energy(const double* __restrict__ erow, const uint32_t* __restrict__ perm,
-                                                const uint32_t* __restrict__ nbrCount, const uint32_t* __restrict__ tileRows,
-                                                const unsigned long long* __restrict__ tileOff, const uint32_t* __restrict__ nbr,
-                                                const double* __restrict__ pacc, size_t nSlots, size_t n, uint32_t nInt,
-                                                double multiplier, double* __restrict__ epsApi) {
-  constexpr int ES = ERow<DIM, MODE>::ES, GEOM = ERow<DIM, MODE>::GEOM;
-  const int lane = threadIdx.x & 31;
-  const size_t tile = (size_t)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
-  const size_t i = tile*SPHB200_TILE + lane;
-  if (tile*SPHB200_TILE >= n) return;
-  const bool inRange = i < n;
-  const uint32_t o = inRange ? perm[i] : 0xffffffffu;
-  const bool active = inRange && o < nInt;
-  double vi[DIM], Di = 0, mi = 1, gi[GEOM > 0 ? GEOM : 1];
-  if (inRange) {
+__global__ void __launch_bounds__(32*EW, 1) k_energy(const double* __restrict__ erow, const uint32_t* __restrict__ perm,
+                                                     const uint32_t* __restrict__ nbrCount, const uint32_t* __restrict__ tileRows,
+                                                     const unsigned long long* __restrict__ tileOff, const uint32_t* __restrict__ nbr,
+                                                     const double* __restrict__ pacc, size_t nSlots, size_t n, uint32_t nInt,
+                                                     double multiplier, double* __restrict__ epsApi) {
+  constexpr int ES = ERow<DIM, MODE>::ES, GEOM = ERow<DIM, MODE>::GEOM, NREC = ERow<DIM, MODE>::COPY/8;
+  using Ring = ERing<DIM, MODE>;
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Ring ring;
+  ring.base = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)warp*(unsigned)Ring::WARPB;
+  ring.rows = reinterpret_cast<const unsigned char*>(erow);
+  ring.x1 = nullptr; ring.x2 = nullptr; ring.aux2 = nullptr;
+  const size_t nTiles = (n + SPHB200_TILE - 1)/SPHB200_TILE;
+  for (size_t tile = (size_t)blockIdx.x*EW + warp; tile < nTiles; tile += (size_t)gridDim.x*EW) {
+    const size_t i = tile*SPHB200_TILE + lane;
+    const bool inRange = i < n;
+    const uint32_t o = inRange ? perm[i] : 0xffffffffu;
+    const bool active = inRange && o < nInt;
+    double vi[DIM], Di = 0, mi = 1, gi[GEOM > 0 ? GEOM : 1];
+    if (inRange) {
 #pragma unroll
-    for (int q = 0; q < DIM; ++q) vi[q] = erow[i*ES + q];
-    Di = erow[i*ES + DIM]; mi = erow[i*ES + DIM + 1];
+      for (int q = 0; q < DIM; ++q) vi[q] = erow[i*ES + q];
+      Di = erow[i*ES + DIM]; mi = erow[i*ES + DIM + 1];
 #pragma unroll
-    for (int q = 0; q < GEOM; ++q) gi[q] = erow[i*ES + DIM + 3 + q];
-  } else {
-#pragma unroll
-    for (int q = 0; q < DIM; ++q) vi[q] = 0;
-#pragma unroll
-    for (int q = 0; q < (GEOM > 0 ? GEOM : 1); ++q) gi[q] = 0;
-  }
-  const uint32_t cnt = active ? nbrCount[i] : 0u;
-  const uint32_t rows = tileRows[tile];
-  const unsigned long long base = tileOff[tile];
-  double acc = 0.0;
-  for (uint32_t k = 0; k < rows; ++k) {
-    if (k >= cnt) continue;
-    const unsigned long long slot = base + (unsigned long long)k*SPHB200_TILE + lane;
-    const uint32_t j = nbr[slot];
-    double vj[DIM], d[DIM], gj[GEOM > 0 ? GEOM : 1];
-#pragma unroll
-    for (int q = 0; q < DIM; ++q) vj[q] = erow[(size_t)j*ES + q];
-#pragma unroll
-    for (int q = 0; q < GEOM; ++q) gj[q] = erow[(size_t)j*ES + DIM + 3 + q];
-    pacc_expand<DIM, MODE>(pacc, slot, gi, gj, d);
-    const double Dj = erow[(size_t)j*ES + DIM], mj = erow[(size_t)j*ES + DIM + 1];
-    const bool up = erow[(size_t)j*ES + DIM + 2] > (double)o;         // original index of j > original index of i
-    if (up) {
-      // i is the pair's i-node: paccij = -mj*deltaDvDt (SPH.cc:430); duij = (vj12 - vi12).paccij
-      double du = 0.0;
-#pragma unroll
-      for (int q = 0; q < DIM; ++q) du += (vj[q] - vi[q])*(-mj*d[q]);
-      const double sg = du < 0.0 ? -1.0 : 1.0;
-      const double wti = fmax(DBL_EPSILON, Di*sg), wtj = fmax(DBL_EPSILON, Dj*sg);
-      const double wi = wti/(wti + wtj);
-      acc += wi*du;
+      for (int q = 0; q < GEOM; ++q) gi[q] = erow[i*ES + DIM + 3 + q];
     } else {
-      // i is the pair's j-node; the stored delta is in i's orientation, so pacc(j<-i) = mi*delta
-      double du = 0.0;
 #pragma unroll
-      for (int q = 0; q < DIM; ++q) du += (vi[q] - vj[q])*(mi*d[q]);
-      const double sg = du < 0.0 ? -1.0 : 1.0;
-      const double wtj = fmax(DBL_EPSILON, Dj*sg), wti = fmax(DBL_EPSILON, Di*sg);
-      const double wj = wtj/(wtj + wti);
-      acc += (1.0 - wj)*du*mj/mi;
+      for (int q = 0; q < DIM; ++q) vi[q] = 0;
+#pragma unroll
+      for (int q = 0; q < (GEOM > 0 ? GEOM : 1); ++q) gi[q] = 0;
     }
+    const uint32_t cnt = active ? nbrCount[i] : 0u;
+    const uint32_t rows = tileRows[tile];
+    const unsigned long long base = tileOff[tile] + lane;
+    double acc = 0.0;
+    ring_walk<Ring, ESTAGES>(ring, lane, rows, cnt,
+      [&](uint32_t p) -> uint32_t { return (p < cnt) ? nbr[base + (unsigned long long)p*SPHB200_TILE] : 0u; },
+      [&](uint32_t k, uint32_t) {
+        const unsigned long long slot = base + (unsigned long long)k*SPHB200_TILE;
+        double rj[NREC];
+        ring.read_row(k, lane, rj);
+        const double* vj = rj;
+        const double* gj = rj + DIM + 3;
+        double d[DIM];
+        pacc_expand<DIM, MODE>(pacc, slot, gi, gj, d);
+        const double Dj = rj[DIM], mj = rj[DIM + 1];
+        const bool up = rj[DIM + 2] > (double)o;                          // original index of j > original index of i
+        if (up) {
+          // i is the pair's i-node: paccij = -mj*deltaDvDt (SPH.cc:430); duij = (vj12 - vi12).paccij
+          double du = 0.0;
+#pragma unroll
+          for (int q = 0; q < DIM; ++q) du += (vj[q] - vi[q])*(-mj*d[q]);
+          const double sg = du < 0.0 ? -1.0 : 1.0;
+          const double wti = fmax(DBL_EPSILON, Di*sg), wtj = fmax(DBL_EPSILON, Dj*sg);
+          const double wi = wti/(wti + wtj);
+          acc += wi*du;
+        } else {
+          // i is the pair's j-node; the stored delta is in i's orientation, so pacc(j<-i) = mi*delta
+          double du = 0.0;
+#pragma unroll
+          for (int q = 0; q < DIM; ++q) du += (vi[q] - vj[q])*(mi*d[q]);
+          const double sg = du < 0.0 ? -1.0 : 1.0;
+          const double wtj = fmax(DBL_EPSILON, Dj*sg), wti = fmax(DBL_EPSILON, Di*sg);
+          const double wj = wtj/(wtj + wti);
+          acc += (1.0 - wj)*du*mj/mi;
+        }
+      });
+    if (active) epsApi[o] += acc*multiplier;
   }
-  if (active) epsApi[o] += acc*multiplier;
 }
 
 // ---- exporters: NodePairList (sorted (i,j), i<j in ORIGINAL numbering) and PairwiseField --------------------------------
@@ -240,10 +257,15 @@ static int launch_energy_mode(sphb200_ctx* c, double multiplier) {
   }
   const double hdt = 0.5*multiplier;
   const unsigned nb = (unsigned)((n + RB - 1)/RB);
-  const unsigned nbt = (unsigned)((c->nTiles + 3)/4);
   k_energy_prep<DIM, MODE><<<nb, RB, 0, c->stream>>>(c->api[S_VEL], c->api[S_MASS], c->perm, c->deriv[DV_DVDT], c->deriv[DV_DEPSDT], c->rows, n, c->cap, hdt, c->stage);
   KERNEL_CHECK(c, "k_energy_prep");
-  k_energy<DIM, MODE><<<nbt, 128, 0, c->stream>>>(c->stage, c->perm, c->nbrCount, c->tileRows, c->tileOff, c->nbr, c->pacc, c->nSlots, n, (uint32_t)c->nInt, multiplier, c->api[S_EPS]);
+  const size_t shm = (size_t)EW*ERing<DIM, MODE>::WARPB;
+  CU_CHECK(c, cudaFuncSetAttribute(k_energy<DIM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+  int nsm = 148, perSM = 1;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_energy<DIM, MODE>, 32*EW, shm) != cudaSuccess || perSM < 1) perSM = 1;
+  const unsigned nbt = (unsigned)std::min<size_t>((c->nTiles + EW - 1)/EW, (size_t)nsm*perSM);
+  k_energy<DIM, MODE><<<nbt, 32*EW, shm, c->stream>>>(c->stage, c->perm, c->nbrCount, c->tileRows, c->tileOff, c->nbr, c->pacc, c->nSlots, n, (uint32_t)c->nInt, multiplier, c->api[S_EPS]);
   KERNEL_CHECK(c, "k_energy");
   return 0;
 }

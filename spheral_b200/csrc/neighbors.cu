@@ -119,24 +119,28 @@ __global__ void k_bbox_final(const double* __restrict__ partial, int nb, double*
 }
 
 // ---- K1b: cell key + histogram --------------------------------------------------------------------------------------
+// Ghost split (ghostBase = table size, 0 = off): ghost nodes (i >= nInt) are counted in a second copy of the cell table that follows
+// the first, so the sorted order is [internal nodes in Morton order | ghost nodes in Morton order].  Ghosts build no lists; mixed
+// among the internal nodes they leave lanes of the tiles next to a boundary idle in every pair loop (a tile costs what its longest
+// list costs).  The key stored per node stays the plain cell key; a cell is then two ranges of the sorted order.
 template <int DIM>
 __global__ void __launch_bounds__(RB) k_cell_count(const double* __restrict__ pos, size_t n, GridDev g, const uint32_t* __restrict__ dilTab,
-                                                   uint32_t* __restrict__ keyOut, uint32_t* __restrict__ cellCount) {
+                                                   uint32_t* __restrict__ keyOut, uint32_t* __restrict__ cellCount, size_t nInt, uint32_t ghostBase) {
   const size_t i = (size_t)blockIdx.x*RB + threadIdx.x;
   if (i >= n) return;
   uint32_t key = 0;
 #pragma unroll
   for (int a = 0; a < DIM; ++a) key |= dilTab[a*SPHB200_DIL + cell_coord(pos[i*DIM + a], g.lo[a], g.cs[a], g.nc[a])];
   keyOut[i] = key;
-  atomicAdd(&cellCount[key], 1u);
+  atomicAdd(&cellCount[key + (i >= nInt ? ghostBase : 0u)], 1u);
 }
 
 // ---- K1c: scatter into cells, then order each cell by original index (deterministic layout) ------------------------------
 __global__ void __launch_bounds__(RB) k_cell_scatter(const uint32_t* __restrict__ key, size_t n, uint32_t* __restrict__ cursor,
-                                                     uint32_t* __restrict__ perm) {
+                                                     uint32_t* __restrict__ perm, size_t nInt, uint32_t ghostBase) {
   const size_t i = (size_t)blockIdx.x*RB + threadIdx.x;
   if (i >= n) return;
-  const uint32_t s = atomicAdd(&cursor[key[i]], 1u);
+  const uint32_t s = atomicAdd(&cursor[key[i] + (i >= nInt ? ghostBase : 0u)], 1u);
   perm[s] = (uint32_t)i;
 }
 __global__ void __launch_bounds__(RB) k_cell_order(const uint32_t* __restrict__ cellStart, uint32_t tableSize, uint32_t* __restrict__ perm) {
@@ -419,6 +423,7 @@ __global__ void __launch_bounds__(32*PS_WARPS) k_pack_scatter(PackArgs a) {
 struct NbrArgs {
   const double* rows; const float* frows; const uint32_t* perm; const uint32_t* skey; const uint32_t* cellStart;
   const uint32_t* dilTab;
+  uint32_t ghostBase;                // ghost split: the ghost nodes of cell k are cellStart[ghostBase + k] .. cellStart[ghostBase + k + 1] (0: off)
   size_t n; uint32_t nInt; double kext2; GridDev g;
   uint32_t* nbrCount; uint32_t* tileRows; unsigned long long* tileOff; uint32_t* nbr; unsigned long long nbrCap;
   uint4* runs; unsigned long long runsCap; uint32_t* tileRunStart; uint32_t* tileRunCount;
@@ -431,7 +436,7 @@ struct NbrArgs {
 // Per-warp candidate walk: calls f(jb, je, sx, sy, sz) for every non-empty stencil cell, warp-uniformly.
 template <int DIM, typename F>
 __device__ __forceinline__ void walk_cells(const GridDev& g, const uint32_t* __restrict__ dilTab,
-                                           const uint32_t* __restrict__ cellStart, unsigned leaders, const int* ci, int rad, F&& f) {
+                                           const uint32_t* __restrict__ cellStart, uint32_t ghostBase, unsigned leaders, const int* ci, int rad, F&& f) {
   for (unsigned lm = leaders; lm; lm &= lm - 1) {
     const int L = __ffs(lm) - 1;
     int lc[3];
@@ -458,6 +463,10 @@ __device__ __forceinline__ void walk_cells(const GridDev& g, const uint32_t* __r
           const uint32_t key = dilTab[sx] | kyz;
           const uint32_t jb = cellStart[key], je = cellStart[key + 1];
           if (je > jb) f(jb, je, sx, sy, sz);
+          if (ghostBase) {
+            const uint32_t gb = cellStart[ghostBase + key], ge = cellStart[ghostBase + key + 1];
+            if (ge > gb) f(gb, ge, sx, sy, sz);
+          }
         }
       }
     }
@@ -616,12 +625,13 @@ __global__ void __launch_bounds__(128) k_tile_runs(NbrArgs a) {
           const int lx = __shfl_sync(0xffffffffu, ci[0], L), ly = __shfl_sync(0xffffffffu, ci[1], L), lz = __shfl_sync(0xffffffffu, ci[2], L);
           inSt = inSt || (abs(lx - sx) <= 1 && abs(ly - sy) <= 1 && (DIM == 2 || abs(lz - sz) <= 1));
         }
-        uint32_t jb = 0, je = 0;
+        uint32_t jb = 0, je = 0, gb = 0, ge = 0;             // the cell's internal nodes, then (ghost split) its ghost nodes
         if (want && inSt) {
           const uint32_t key = a.dilTab[sx] | a.dilTab[SPHB200_DIL + sy] | ((DIM == 3) ? a.dilTab[2*SPHB200_DIL + sz] : 0u);
           jb = a.cellStart[key]; je = a.cellStart[key + 1];
+          if (a.ghostBase) { gb = a.cellStart[a.ghostBase + key]; ge = a.cellStart[a.ghostBase + key + 1]; }
         }
-        const uint32_t nr = (je - jb + 31u) >> 5;            // a cell with more than 32 nodes becomes several runs
+        const uint32_t nr = ((je - jb + 31u) >> 5) + ((ge - gb + 31u) >> 5);     // a range of more than 32 nodes becomes several runs
         uint32_t pre = nr;                                   // inclusive prefix sum over the lanes
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, pre, d); if (lane >= d) pre += t; }
@@ -629,6 +639,8 @@ __global__ void __launch_bounds__(128) k_tile_runs(NbrArgs a) {
         uint32_t at = R + pre - nr;
         for (uint32_t b = jb; b < je; b += 32u, ++at)
           if (at < (uint32_t)RUN_CAP) sruns[w][at] = make_uint4(b, min(32u, je - b), (uint32_t)sx | ((uint32_t)sy << 16), (uint32_t)sz);
+        for (uint32_t b = gb; b < ge; b += 32u, ++at)
+          if (at < (uint32_t)RUN_CAP) sruns[w][at] = make_uint4(b, min(32u, ge - b), (uint32_t)sx | ((uint32_t)sy << 16), (uint32_t)sz);
         R += tot;
       }
       if (R > (uint32_t)RUN_CAP) { boxed = false; R = 0; }   // more runs than the table holds: the serial walk (it spills to global memory)
@@ -636,7 +648,7 @@ __global__ void __launch_bounds__(128) k_tile_runs(NbrArgs a) {
   }
   if (!boxed) {
     if constexpr (FINE) walk_cells_coarse<DIM>(a.g, leaders, ci, rad, [&](int sx, int sy, int sz) { emit_fine(sx, sy, sz, 0u, true); });
-    else walk_cells<DIM>(a.g, a.dilTab, a.cellStart, leaders, ci, rad, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) { emit(jb, je, sx, sy, sz, 0u, true); });
+    else walk_cells<DIM>(a.g, a.dilTab, a.cellStart, a.ghostBase, leaders, ci, rad, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) { emit(jb, je, sx, sy, sz, 0u, true); });
   }
   __syncwarp();
   const uint32_t Rtot = R;
@@ -650,7 +662,7 @@ __global__ void __launch_bounds__(128) k_tile_runs(NbrArgs a) {
   if (Rtot > RUN_CAP) {                              // rare: very ragged tile, walk again for the tail
     R = 0;
     if constexpr (FINE) walk_cells_coarse<DIM>(a.g, leaders, ci, rad, [&](int sx, int sy, int sz) { emit_fine(sx, sy, sz, (uint32_t)start, false); });
-    else walk_cells<DIM>(a.g, a.dilTab, a.cellStart, leaders, ci, rad, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) { emit(jb, je, sx, sy, sz, (uint32_t)start, false); });
+    else walk_cells<DIM>(a.g, a.dilTab, a.cellStart, a.ghostBase, leaders, ci, rad, [&](uint32_t jb, uint32_t je, int sx, int sy, int sz) { emit(jb, je, sx, sy, sz, (uint32_t)start, false); });
   }
 }
 
@@ -1253,6 +1265,10 @@ static int build_grid(sphb200_ctx* c, const double* bb /*lo3 hi3 ext3 sumext3*/)
   return 0;
 }
 
+static bool sphb200_ghost_split_wanted() {      // SPHB200_GHOST_SPLIT=0 in the environment: ghosts sorted among the internal nodes (A/B, tests)
+  const char* e = std::getenv("SPHB200_GHOST_SPLIT");
+  return !(e && e[0] == '0');
+}
 static bool sphb200_nbr_v2_wanted() {          // read at every build: the tests switch between the two builders inside one process
   const char* e = std::getenv("SPHB200_NBR_V2");
   return !(e && e[0] == '0');
@@ -1347,7 +1363,10 @@ int sphb200_sort_and_pack(sphb200_ctx* c) {
   if (build_grid(c, c->reduceHost)) return 1;
 
   const GridDev& gs = c->fineWalk ? c->gridFine : c->grid;          // the grid the nodes are sorted by
-  const size_t tbl = (size_t)gs.tableSize + 1;
+  // ghost split: a second copy of the cell table for the ghost nodes (see k_cell_count); not with the experimental two-level walk
+  c->ghostBase = (c->nGhost > 0 && !c->fineWalk && sphb200_ghost_split_wanted() && 2ull*gs.tableSize < 0x7fffffffull) ? gs.tableSize : 0u;
+  const uint32_t cells = gs.tableSize + c->ghostBase;
+  const size_t tbl = (size_t)cells + 1;
   if (sphb200_ensure(c, c->cellStart, c->cellCap, tbl)) return 1;
   if (sphb200_ensure(c, c->cellCursor, c->cellCursorCap, tbl)) return 1;
   CU_CHECK(c, cudaMemsetAsync(c->cellStart, 0, tbl*sizeof(uint32_t), c->stream));
@@ -1357,14 +1376,14 @@ int sphb200_sort_and_pack(sphb200_ctx* c) {
     k_dilate_table<<<dim3((unsigned)((ncmax + RB - 1)/RB), (unsigned)c->ndim), RB, 0, c->stream>>>(gs, c->dilTab);
     KERNEL_CHECK(c, "k_dilate_table");
   }
-  if (c->ndim == 3) k_cell_count<3><<<nb, RB, 0, c->stream>>>(c->api[S_POS], n, gs, c->dilTab, c->cellKeyApi, c->cellStart);
-  else              k_cell_count<2><<<nb, RB, 0, c->stream>>>(c->api[S_POS], n, gs, c->dilTab, c->cellKeyApi, c->cellStart);
+  if (c->ndim == 3) k_cell_count<3><<<nb, RB, 0, c->stream>>>(c->api[S_POS], n, gs, c->dilTab, c->cellKeyApi, c->cellStart, c->nInt, c->ghostBase);
+  else              k_cell_count<2><<<nb, RB, 0, c->stream>>>(c->api[S_POS], n, gs, c->dilTab, c->cellKeyApi, c->cellStart, c->nInt, c->ghostBase);
   KERNEL_CHECK(c, "k_cell_count");
-  if (sphb200_scan_u32(c, c->cellStart, c->cellStart, gs.tableSize)) return 1;
-  CU_CHECK(c, cudaMemcpyAsync(c->cellCursor, c->cellStart, (size_t)gs.tableSize*sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
-  k_cell_scatter<<<nb, RB, 0, c->stream>>>(c->cellKeyApi, n, c->cellCursor, c->perm);
+  if (sphb200_scan_u32(c, c->cellStart, c->cellStart, cells)) return 1;
+  CU_CHECK(c, cudaMemcpyAsync(c->cellCursor, c->cellStart, (size_t)cells*sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+  k_cell_scatter<<<nb, RB, 0, c->stream>>>(c->cellKeyApi, n, c->cellCursor, c->perm, c->nInt, c->ghostBase);
   KERNEL_CHECK(c, "k_cell_scatter");
-  k_cell_order<<<(gs.tableSize + RB - 1)/RB, RB, 0, c->stream>>>(c->cellStart, gs.tableSize, c->perm);
+  k_cell_order<<<(cells + RB - 1)/RB, RB, 0, c->stream>>>(c->cellStart, cells, c->perm);
   KERNEL_CHECK(c, "k_cell_order");
   c->sortValid = true;
   if (c->stencilR > 1) {
@@ -1406,6 +1425,7 @@ int sphb200_neighbors(sphb200_ctx* c) {
   for (int attempt = 0; attempt < 5; ++attempt) {
     NbrArgs a{};
     a.rows = c->rows; a.frows = c->frows; a.perm = c->perm; a.skey = c->skey; a.cellStart = c->cellStart; a.dilTab = c->dilTab;
+    a.ghostBase = c->ghostBase;
     a.n = n; a.nInt = (uint32_t)c->nInt; a.kext2 = kext*kext; a.g = c->grid;
     a.nbrCount = c->nbrCount; a.tileRows = c->tileRows; a.tileOff = c->tileOff; a.nbr = c->nbr; a.nbrCap = c->nbrCap;
     a.runs = c->runs; a.runsCap = c->runsCap; a.tileRunStart = c->tileRunStart; a.tileRunCount = c->tileRunCount;

@@ -96,6 +96,7 @@ struct sphb200_ctx {
   bool fineWalk = false;            // the current sort used gridFine (keys, cellStart, dilTab refer to it; coarse key = fine key >> ndim)
   uint32_t* dilTab = nullptr;       // 3*SPHB200_DIL dilated cell coordinates
   uint32_t* cellKeyApi = nullptr;   // key per node, original order
+  uint32_t ghostBase = 0;           // ghost split of the current sort: offset of the ghost copy of the cell table (0: ghosts sorted among the internal nodes)
   uint32_t* cellStart = nullptr;    // tableSize+1
   uint32_t* cellCursor = nullptr;
   size_t cellCap = 0, cellCursorCap = 0;
