@@ -23,7 +23,16 @@ template <int DIM, int MODE> struct ERow {
   static constexpr int COPY = (USED*8 + 15)/16*16;          // bytes of a record the ring copies
   static_assert(USED <= ES, "the energy record must fit a node row");
 };
-constexpr int EW = 8, ESTAGES = 4;                           // warps per CTA and ring depth of k_energy
+// Ring depth x resident CTAs per SM, measured at 8 M (tensor mode) / 1 M (isotropic mode), per-lane gather before: 14.85 / 1.71 ms:
+//   4 x 1: 18.85 / 1.66    3 x 2: 11.75 / 1.67    2 x 3: 10.95 / 1.27 ms -- this loop has little arithmetic per edge to overlap with
+// and an IEEE division in its chain, so warps (24 per SM at 80 registers) hide more than ring depth does.
+#ifndef SPHB200_ENERGY_STAGES
+#define SPHB200_ENERGY_STAGES 2
+#endif
+#ifndef SPHB200_ENERGY_CTAS
+#define SPHB200_ENERGY_CTAS 3
+#endif
+constexpr int EW = 8, ESTAGES = SPHB200_ENERGY_STAGES;        // warps per CTA and ring depth of k_energy
 template <int DIM, int MODE> using ERing = NbrRing<DIM, 0, 0, ESTAGES, ERow<DIM, MODE>::COPY, false>;
 
 template <int DIM, int MODE>
@@ -81,7 +90,7 @@ __device__ __forceinline__ void pacc_expand(const double* __restrict__ pacc, uns
 // One warp per tile, lane <-> node i, persistent CTAs; the neighbours' records arrive through the warp-cooperative ring (a per-lane
 // gather of the 120-byte record was L1-wavefront bound: 14.1 ms of the 83 ms RK2 step at 8 M, profiles/r02_launches_rk2_step_8m_summary.txt).
 template <int DIM, int MODE>
-__global__ void __launch_bounds__(32*EW, 1) k_energy(const double* __restrict__ erow, const uint32_t* __restrict__ perm,
+__global__ void __launch_bounds__(32*EW, SPHB200_ENERGY_CTAS) k_energy(const double* __restrict__ erow, const uint32_t* __restrict__ perm,
                                                      const uint32_t* __restrict__ nbrCount, const uint32_t* __restrict__ tileRows,
                                                      const unsigned long long* __restrict__ tileOff, const uint32_t* __restrict__ nbr,
                                                      const double* __restrict__ pacc, size_t nSlots, size_t n, uint32_t nInt,
