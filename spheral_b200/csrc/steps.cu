@@ -22,7 +22,16 @@
 namespace {
 
 constexpr int RB = 256;
-constexpr int SW = 8, SS = 4;                      // warps per CTA and ring depth of the light pair loops
+// Warps per CTA x ring depth, measured at 8 M (ms: dt vote / grad-h correction / sum density): 8 x 4: 5.07 / 8.14 / 11.63,
+// 16 x 2: 3.86 / 7.37 / 9.77, 16 x 3: 4.03 / 7.45 / 10.44, 24 x 2: 3.77 / 7.32 / 10.72 -- these loops have little arithmetic per
+// edge, so resident warps hide the gather better than a deeper ring, and a larger CTA shares one staged kernel table.
+#ifndef SPHB200_STEP_WARPS
+#define SPHB200_STEP_WARPS 16
+#endif
+#ifndef SPHB200_STEP_STAGES
+#define SPHB200_STEP_STAGES 2
+#endif
+constexpr int SW = SPHB200_STEP_WARPS, SS = SPHB200_STEP_STAGES;     // warps per CTA and ring depth of the light pair loops
 
 template <int DIM> struct StepPrefix { static constexpr int MASS = ((Dm<DIM>::R_M + 1)*8 + 15)/16*16; };    // position .. mass
 template <int DIM> using MassRing = NbrRing<DIM, 0, 0, SS, StepPrefix<DIM>::MASS, false>;
