@@ -402,13 +402,15 @@ class HotPath:
         self.down_bufs = {}
         e.upload_state_pinned(self.up_mask, self.hs)
         e.sync()
+        # SPHB200_E2E_FUSED=0: evaluate_derivatives + download_derivs as two calls (A/B)
+        self.fused_e2e = os.environ.get("SPHB200_E2E_FUSED", "1") != "0"
         self.dsph = None
         if world > 1:
             from spheral_b200 import distributed as D
             # CRKSPH: the volumes and the RK coefficients are state fields too and travel once the package has computed them
             self.dsph = D.DistributedSPH(e, 0, self.lo, self.hi, extra_fields=("volume", "rkCorrections") if crk else ())
 
-    def step(self):
+    def step(self, evaluate=True):
         e = self.e
         nPG = e.reflect_set_ghost_nodes() if self.planes else 0          # Integrator::setGhostNodes: plane ghosts first ...
         if self.dsph is not None:
@@ -422,9 +424,13 @@ class HotPath:
             e.crk_compute_corrections()
             if self.dsph is not None:
                 self.dsph.mark_ready("rkCorrections"); self.dsph.apply_ghosts(("rkCorrections",))
-        e.evaluate_derivatives(0.0, 1.0)
+        if evaluate:
+            e.evaluate_derivatives(0.0, 1.0)
 
-    def download(self):
+    def download(self, fused=False):
+        """Derivative fields to the pinned host buffers.  fused: evaluateDerivatives and the download in one C-ABI call
+        (sphb200_evaluate_derivatives_to_host: the pair loop runs in chunks of the host index range and the download of one chunk
+        overlaps the computation of the next)."""
         e, L, torch = self.e, self.L, self.torch
         n = e.nInternal + e.nGhost      # the C ABI writes every node; ghost entries are zeros
         if self.down_bufs.get("n", 0) < n:
@@ -433,15 +439,22 @@ class HotPath:
                 t = torch.empty((n + n//16)*L.deriv_width(3, k), dtype=torch.float64).pin_memory()
                 keep.append(t); setattr(hd, k, self.dp(t))
             self.down_bufs.update(n=n + n//16, hd=hd, keep=keep)
-        e._check(e._lib.sphb200_download_derivs(e._h, self.down_mask, self.C.byref(self.down_bufs["hd"])))
+        if fused:
+            e._check(e._lib.sphb200_evaluate_derivatives_to_host(e._h, 0.0, 1.0, self.down_mask, self.C.byref(self.down_bufs["hd"])))
+        else:
+            e._check(e._lib.sphb200_download_derivs(e._h, self.down_mask, self.C.byref(self.down_bufs["hd"])))
 
     def step_e2e(self):
         e = self.e
         if e.nGhost:
             e.set_nodes(self.N, 0)
         e.upload_state_pinned(self.up_mask, self.hs)
-        self.step()
-        self.download()
+        if self.fused_e2e:
+            self.step(evaluate=False)
+            self.download(fused=True)
+        else:
+            self.step()
+            self.download()
 
     def timed(self, fn, k, dist):
         torch = self.torch
@@ -566,7 +579,7 @@ def main():
         e.sync()
 
     # e2e leg: host buffers in, host buffers out, every step
-    for _ in range(2):
+    for _ in range(3):
         hp.step_e2e()
     e.sync()
     _, e2e_wall = hp.timed(hp.step_e2e, args.steps, dist)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPHB200_ABI_VERSION 3
+#define SPHB200_ABI_VERSION 4
 
 typedef struct sphb200_ctx sphb200_ctx;
 
@@ -161,6 +161,15 @@ int  sphb200_download_neighbor_counts(sphb200_ctx* ctx, uint32_t* counts);
    evaluateDerivatives; derivatives are zeroed first (CheapSynchronousRK2.cc:87 derivs.Zero()). Asynchronous. */
 int  sphb200_evaluate_derivatives(sphb200_ctx* ctx, double time, double dt);
 int  sphb200_download_derivs(sphb200_ctx* ctx, unsigned fieldMask, const sphb200_host_derivs* d);
+/* evaluateDerivatives as the reference's caller sees it -- SPH<Dim>::evaluateDerivatives(time, dt, dataBase, state, derivs) fills
+   HOST fields (SPH.cc:141-163; Integrator.cc:217-229 evaluateDerivatives) -- in one call: sphb200_evaluate_derivatives followed by
+   sphb200_download_derivs of fieldMask, with the two overlapped.  The pair loop runs in chunks of the HOST index range (4 by default,
+   SPHB200_E2H_CHUNKS; each chunk = the tiles that hold its nodes); while chunk q+1 is computed, chunk q's slice of every selected
+   field is un-permuted and copied to the host on the copy stream.  Results are bit-identical to the two separate calls (a node's
+   sums do not depend on the launch that forms them).  Falls back to the two calls when the host order has no spatial coherence (a
+   tile would be visited by every chunk), below 256 k internal nodes, and for CRKSPH.  Synchronises (the host fields are complete on
+   return); the derivatives also stay on the device as after sphb200_evaluate_derivatives. */
+int  sphb200_evaluate_derivatives_to_host(sphb200_ctx* ctx, double time, double dt, unsigned fieldMask, const sphb200_host_derivs* d);
 /* Restart: SPHBase::restoreState (SPH/SPHBase.cc:741-765) reads the package-owned derivative fields back, because
    CheapSynchronousRK2 advances the first trial state after a restart with them.  Uploads node-wise derivative fields (host AoS,
    original order); sphb200_state_update / sphb200_compute_dt / sphb200_copy_DvDx_to_Q then work as after an evaluation.  Pair-wise

@@ -103,7 +103,8 @@ EXPORTS = ("sphb200_abi_version", "sphb200_create", "sphb200_destroy", "sphb200_
            "sphb200_state_assign", "sphb200_state_update", "sphb200_compute_dt",
            "sphb200_reflect_configure", "sphb200_reflect_set_ghost_nodes", "sphb200_reflect_apply_ghosts", "sphb200_reflect_enforce",
            "sphb200_reflect_finalize_derivatives", "sphb200_halo_unpack_values", "sphb200_halo_pack_derivs",
-           "sphb200_halo_unpack_derivs", "sphb200_upload_derivs", "sphb200_boundary_configure", "sphb200_iterate_ideal_h", "sphb200_connectivity_valid", "sphb200_state_fields_present")
+           "sphb200_halo_unpack_derivs", "sphb200_upload_derivs", "sphb200_boundary_configure", "sphb200_iterate_ideal_h", "sphb200_connectivity_valid", "sphb200_state_fields_present",
+           "sphb200_evaluate_derivatives_to_host")
 
 _lib = None
 
@@ -142,6 +143,7 @@ def lib():
     L.sphb200_download_neighbor_counts.argtypes = [vp, _u32p]
     L.sphb200_evaluate_derivatives.argtypes = [vp, C.c_double, C.c_double]
     L.sphb200_download_derivs.argtypes = [vp, C.c_uint, C.POINTER(HostDerivs)]
+    L.sphb200_evaluate_derivatives_to_host.argtypes = [vp, C.c_double, C.c_double, C.c_uint, C.POINTER(HostDerivs)]
     L.sphb200_download_pair_accelerations.argtypes = [vp, _dp, C.c_size_t]
     L.sphb200_copy_DvDx_to_Q.argtypes = [vp]
     L.sphb200_update_energy_compatible.argtypes = [vp, C.c_double]

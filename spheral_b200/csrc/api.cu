@@ -2,8 +2,10 @@
 // string the kernels of neighbors.cu / derivs.cu / energy.cu together.  No CPU fallback exists: every compute entry
 // point runs CUDA kernels on the context's device or fails with an error.
 #include "sphb200_internal.cuh"
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -280,6 +282,9 @@ int sphb200_create(sphb200_ctx** out, int device, const sphb200_options* opts) {
   cudaMemset(c->counters, 0, 16*sizeof(unsigned long long));
   cudaMalloc((void**)&c->dilTab, 3*SPHB200_DIL*sizeof(uint32_t));
   cudaMallocHost((void**)&c->countersHost, 16*sizeof(unsigned long long));
+  cudaMalloc((void**)&c->chunkCount, SPHB200_MAX_CHUNKS*sizeof(uint32_t));
+  cudaMallocHost((void**)&c->chunkCountHost, SPHB200_MAX_CHUNKS*sizeof(uint32_t));
+  for (auto& ev : c->evChunk) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   if (cudaGetLastError() != cudaSuccess) { sphb200_destroy(c); return sphb200_fail(nullptr, "context allocation failed"); }
   *out = c;
   return 0;
@@ -305,6 +310,10 @@ void sphb200_destroy(sphb200_ctx* c) {
   if (c->cellReach) cudaFree(c->cellReach);
   if (c->tileRadius) cudaFree(c->tileRadius);
   cudaFreeHost(c->reduceHost); cudaFreeHost(c->countersHost);
+  if (c->chunkList) cudaFree(c->chunkList);
+  if (c->chunkCount) cudaFree(c->chunkCount);
+  if (c->chunkCountHost) cudaFreeHost(c->chunkCountHost);
+  for (auto& ev : c->evChunk) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -511,11 +520,11 @@ int sphb200_download_neighbor_counts(sphb200_ctx* c, uint32_t* counts) {
   return 0;
 }
 
-int sphb200_evaluate_derivatives(sphb200_ctx* c, double /*time*/, double /*dt*/) {
-  if (!c) return sphb200_fail(nullptr, "null ctx");
+// checks of evaluateDerivatives + the row pack; returns 2 when there is nothing to evaluate (no nodes)
+static int evaluate_prepare(sphb200_ctx* c) {
   CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
   if (!c->pairsValid) return sphb200_fail(c, "evaluateDerivatives: connectivity is stale or missing (requireConnectivity: call build_pairs first)");
-  if (c->n == 0) { c->derivsValid = true; return 0; }
+  if (c->n == 0) { c->derivsValid = true; return 2; }
   const bool crk = c->opt.hydro == SPHB200_HYDRO_CRKSPH;
   for (int s : {S_POS, S_VEL, S_H, S_MASS, S_RHO, S_P, S_CS})
     if (!c->have[s]) return sphb200_fail(c, "evaluateDerivatives: required state field missing on device (position, velocity, H, mass, mass density, pressure, sound speed)");
@@ -526,13 +535,23 @@ int sphb200_evaluate_derivatives(sphb200_ctx* c, double /*time*/, double /*dt*/)
   cudaEventRecord(c->ev[3], c->stream);
   if (!c->rowsValid && sphb200_pack_rows(c)) return 1;
   cudaEventRecord(c->ev[4], c->stream);
-  if (crk ? sphb200_launch_crk_derivs(c) : sphb200_launch_derivs(c)) return 1;
+  return 0;
+}
+static int evaluate_finish(sphb200_ctx* c) {
   cudaEventRecord(c->ev[5], c->stream);
   // keep the sorted order these node-wise derivatives are stored in (see permEval)
   if (sphb200_ensure(c, c->permEval, c->permEvalCap, c->cap)) return 1;
   CU_CHECK(c, cudaMemcpyAsync(c->permEval, c->perm, c->n*sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
   c->nEval = c->n; c->capEval = c->cap; c->nIntEval = c->nInt; c->derivNodeValid = true;
   return 0;
+}
+
+int sphb200_evaluate_derivatives(sphb200_ctx* c, double /*time*/, double /*dt*/) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  const int rc = evaluate_prepare(c);
+  if (rc) return rc == 2 ? 0 : 1;
+  if ((c->opt.hydro == SPHB200_HYDRO_CRKSPH) ? sphb200_launch_crk_derivs(c) : sphb200_launch_derivs(c)) return 1;
+  return evaluate_finish(c);
 }
 
 static double* deriv_ptr(const sphb200_host_derivs* d, int slot) {
@@ -570,6 +589,121 @@ int sphb200_download_derivs(sphb200_ctx* c, unsigned mask, const sphb200_host_de
   }
   CU_CHECK(c, cudaStreamSynchronize(c->stream));
   return 0;
+}
+
+// Tiles of each chunk of the host index range: chunk q = internal nodes with original index in [q*chunkSize, (q+1)*chunkSize) (the
+// last chunk takes the remainder and the ghost nodes, whose derivative entries are zeros).  A tile that holds nodes of several chunks
+// is listed in each of them.  The order inside a list is whatever the atomics give (roughly ascending); results do not depend on it.
+__global__ void __launch_bounds__(RB) k_chunk_lists(const uint32_t* __restrict__ perm, size_t n, uint32_t nInt, uint32_t chunkSize, int Q,
+                                                    size_t nTiles, uint32_t* __restrict__ lists, uint32_t* __restrict__ counts) {
+  const size_t tile = ((size_t)blockIdx.x*RB + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (tile >= nTiles) return;
+  const size_t i = tile*SPHB200_TILE + lane;
+  unsigned m = 0u;
+  if (i < n) {
+    const uint32_t o = perm[i];
+    const uint32_t q = (o < nInt) ? min((uint32_t)(Q - 1), o/chunkSize) : (uint32_t)(Q - 1);
+    m = 1u << q;
+  }
+  m = __reduce_or_sync(0xffffffffu, m);
+  if (lane == 0)
+    for (; m; m &= m - 1u) {
+      const int q = __ffs(m) - 1;
+      lists[(size_t)q*nTiles + atomicAdd(&counts[q], 1u)] = (uint32_t)tile;
+    }
+}
+// sorted SoA (component-major) -> host AoS order for the original indices [lo, hi): one thread per output element (coalesced writes)
+__global__ void __launch_bounds__(RB) k_unpermute_range(const double* __restrict__ src, size_t cap, const uint32_t* __restrict__ invPerm,
+                                                        size_t lo, size_t hi, int width, double* __restrict__ dst) {
+  const size_t t = (size_t)blockIdx.x*RB + threadIdx.x;
+  if (t >= (hi - lo)*(size_t)width) return;
+  const size_t o = lo + t/(size_t)width;
+  const int q = (int)(t - (o - lo)*(size_t)width);
+  dst[o*(size_t)width + q] = src[(size_t)q*cap + invPerm[o]];
+}
+
+// SPHB200_E2H_CHUNKS: 1 = no pipelining; default 4 chunks, 8 from 4 M internal nodes on (measured: 1 M 9.49 -> 8.45 ms with 4, 9.01
+// with 8; 8 M 68.2 -> 59.2 with 4, 57.9 with 8 -- the download of the last chunk is what cannot be hidden)
+static int e2h_chunks_wanted(size_t nInt) {
+  const char* e = getenv("SPHB200_E2H_CHUNKS");
+  const int q = e ? atoi(e) : (nInt >= ((size_t)1 << 22) ? 8 : 4);
+  return q < 1 ? 1 : (q > SPHB200_MAX_CHUNKS ? SPHB200_MAX_CHUNKS : q);
+}
+
+int sphb200_evaluate_derivatives_to_host(sphb200_ctx* c, double time, double dt, unsigned mask, const sphb200_host_derivs* d) {
+  if (!c) return sphb200_fail(nullptr, "null ctx");
+  if (!d) return sphb200_fail(c, "evaluate_derivatives_to_host: null destination struct");
+  for (int s = 0; s < DV_COUNT; ++s)
+    if ((mask & (1u << s)) && !deriv_ptr(d, s)) return sphb200_fail(c, "evaluate_derivatives_to_host: field selected in mask but pointer is null");
+  int Q = e2h_chunks_wanted(c->nInt);
+  const char* force = getenv("SPHB200_E2H_FORCE");          // tests: chunk whatever the size / the coherence of the host order
+  const bool forced = force && atoi(force) != 0;
+  if (c->opt.hydro == SPHB200_HYDRO_CRKSPH || (!forced && c->nInt < (size_t)262144) || c->nInt < (size_t)Q) Q = 1;
+  if (Q > 1) {
+    const int rc = evaluate_prepare(c);
+    if (rc == 1) return 1;
+    if (rc == 2) return 0;
+    const uint32_t chunkSize = (uint32_t)(c->nInt/(size_t)Q);
+    if (!c->chunkListsValid || c->chunkQ != Q) {
+      if (sphb200_ensure(c, c->chunkList, c->chunkListCap, (size_t)SPHB200_MAX_CHUNKS*(c->cap/SPHB200_TILE + 2))) return 1;
+      CU_CHECK(c, cudaMemsetAsync(c->chunkCount, 0, SPHB200_MAX_CHUNKS*sizeof(uint32_t), c->stream));
+      k_chunk_lists<<<(unsigned)((c->nTiles*32 + RB - 1)/RB), RB, 0, c->stream>>>(c->perm, c->n, (uint32_t)c->nInt, chunkSize, Q, c->nTiles, c->chunkList, c->chunkCount);
+      KERNEL_CHECK(c, "k_chunk_lists");
+      CU_CHECK(c, cudaMemcpyAsync(c->chunkCountHost, c->chunkCount, SPHB200_MAX_CHUNKS*sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+      CU_CHECK(c, cudaStreamSynchronize(c->stream));
+      c->chunkListsValid = true; c->chunkQ = Q;
+    }
+    size_t listed = 0;
+    for (int q = 0; q < Q; ++q) listed += c->chunkCountHost[q];
+    // a host order without spatial coherence puts every tile into every list: Q times the work.  Then one launch and one download.
+    if (!forced && listed > c->nTiles + c->nTiles/4 + (size_t)Q) Q = 1;
+    if (Q == 1) {
+      if (sphb200_launch_derivs(c)) return 1;
+      if (evaluate_finish(c)) return 1;
+      return sphb200_download_derivs(c, mask, d);
+    }
+    if (sphb200_inverse_perm(c)) return 1;
+    size_t total = 0;
+    for (int s = 0; s < DV_COUNT; ++s) if (mask & (1u << s)) total += c->n*(size_t)sphb200_deriv_width(c->ndim, s);
+    if (ensure_stage(c, total*sizeof(double))) return 1;
+    // Without XSPH DxDt of an internal node IS its velocity (SPH.cc:503-509), which sits on the device in host order already: it
+    // leaves first, while the first chunk is computed (the ghost entries -- zeros -- follow with the last chunk)
+    const bool dxdtEarly = (mask & (1u << DV_DXDT)) && !c->opt.XSPH && c->have[S_VEL];
+    if (dxdtEarly) {
+      CU_CHECK(c, cudaEventRecord(c->evMainMark, c->stream));
+      CU_CHECK(c, cudaStreamWaitEvent(c->copyStream, c->evMainMark, 0));
+      CU_CHECK(c, cudaMemcpyAsync(deriv_ptr(d, DV_DXDT), c->api[S_VEL], c->nInt*(size_t)c->ndim*sizeof(double), cudaMemcpyDeviceToHost, c->copyStream));
+    }
+    for (int q = 0; q < Q; ++q) {
+      const uint32_t lo = (uint32_t)q*chunkSize, hi = (q == Q - 1) ? 0xffffffffu : (uint32_t)(q + 1)*chunkSize;
+      if (sphb200_launch_derivs_chunk(c, c->chunkList + (size_t)q*c->nTiles, c->chunkCountHost[q], lo, hi)) return 1;
+      CU_CHECK(c, cudaEventRecord(c->evChunk[q], c->stream));
+      CU_CHECK(c, cudaStreamWaitEvent(c->copyStream, c->evChunk[q], 0));
+      // this chunk's slice of every selected field: un-permute into the staging area and copy, while the next chunk is computed
+      const size_t olo = lo, ohi = (q == Q - 1) ? c->n : (size_t)hi;          // the last chunk carries the ghost entries (zeros)
+      size_t off = 0;
+      for (int s = 0; s < DV_COUNT; ++s) {
+        if (!(mask & (1u << s))) continue;
+        const int w = sphb200_deriv_width(c->ndim, s);
+        size_t flo = olo;
+        if (s == DV_DXDT && dxdtEarly) flo = std::max(olo, std::min(ohi, c->nInt));     // internal entries already left
+        const size_t cnt = (ohi - flo)*(size_t)w;
+        if (cnt) {
+          k_unpermute_range<<<(unsigned)((cnt + RB - 1)/RB), RB, 0, c->copyStream>>>(c->deriv[s], c->cap, c->invPerm, flo, ohi, w, c->stage + off);
+          KERNEL_CHECK(c, "k_unpermute_range");
+          CU_CHECK(c, cudaMemcpyAsync(deriv_ptr(d, s) + flo*(size_t)w, c->stage + off + flo*(size_t)w, cnt*sizeof(double), cudaMemcpyDeviceToHost, c->copyStream));
+        }
+        off += c->n*(size_t)w;
+      }
+    }
+    c->derivsValid = true;
+    if (evaluate_finish(c)) return 1;
+    CU_CHECK(c, cudaStreamSynchronize(c->copyStream));
+    return 0;
+  }
+  if (sphb200_evaluate_derivatives(c, time, dt)) return 1;
+  return sphb200_download_derivs(c, mask, d);
 }
 
 int sphb200_upload_derivs(sphb200_ctx* c, unsigned mask, const sphb200_host_derivs* d) {

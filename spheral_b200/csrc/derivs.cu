@@ -30,6 +30,10 @@ struct DerivArgs {
   int oneKernel;
   double* deriv[DV_COUNT];
   double* pacc; size_t nSlots;
+  // chunked evaluation (sphb200_evaluate_derivatives_to_host): this launch visits the tiles of `tileList` only and evaluates the
+  // internal nodes whose ORIGINAL index lies in [origLo, origHi); nodes of other chunks are left untouched.  tileList == nullptr:
+  // every tile, every internal node.
+  const uint32_t* tileList; uint32_t nList; uint32_t origLo, origHi;
 };
 
 // Asynchronous global->shared copies (LDGSTS): a warp streams the 128-byte rows of its lanes' upcoming neighbours into a
@@ -122,11 +126,14 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
   constexpr int STAGEB = RingGeom<DIM>::STAGEB;
   const unsigned warpRing = tW + 8u*(nW + nQ) + (unsigned)warp*(PAIR_STAGES*STAGEB);
   const sphb200_options& o = a.o;
-  const size_t nTiles = (a.n + SPHB200_TILE - 1)/SPHB200_TILE;
-  for (size_t tile = (size_t)blockIdx.x*PAIR_WARPS + warp; tile < nTiles; tile += (size_t)gridDim.x*PAIR_WARPS) {
+  const size_t nTiles = a.tileList ? (size_t)a.nList : (a.n + SPHB200_TILE - 1)/SPHB200_TILE;
+  for (size_t tl = (size_t)blockIdx.x*PAIR_WARPS + warp; tl < nTiles; tl += (size_t)gridDim.x*PAIR_WARPS) {
+  const size_t tile = a.tileList ? (size_t)a.tileList[tl] : tl;
   const size_t i = tile*SPHB200_TILE + lane;
   const bool inRange = i < a.n;
-  const bool active = inRange && a.perm[i] < a.nInt;
+  const uint32_t origi = inRange ? a.perm[i] : 0xffffffffu;
+  const bool internal = inRange && origi < a.nInt;
+  const bool active = internal && origi >= a.origLo && origi < a.origHi;
   const double tiny = 1.0e-30;
   const bool xsph = GEN ? (o.XSPH != 0) : XSPH_;
   const bool hsph = GEN ? (o.hEvolution == SPHB200_H_SPH) : HSPH_;
@@ -535,6 +542,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
   const size_t cap = a.cap;
   auto put = [&](int slot, int comp, double v) { a.deriv[slot][(size_t)comp*cap + i] = v; };
   if (!active) {
+    if (internal) continue;                          // a node of another chunk: its launch writes it
     for (int s = 0; s < DV_COUNT; ++s) { const int w = sphb200_deriv_width(DIM, s); for (int q = 0; q < w; ++q) put(s, q, 0.0); }
     continue;
   }
@@ -656,8 +664,12 @@ static double host_table_eval(const TableDev& t, double eta, bool grad) {
   return c[3*k] + (c[3*k + 1] + c[3*k + 2]*eta)*eta;
 }
 
-int sphb200_launch_derivs(sphb200_ctx* c) {
+int sphb200_launch_derivs(sphb200_ctx* c) { return sphb200_launch_derivs_chunk(c, nullptr, 0u, 0u, 0xffffffffu); }
+
+// One launch of the pair loop over the tiles of `tileList` (nullptr: all), internal nodes with original index in [origLo, origHi).
+int sphb200_launch_derivs_chunk(sphb200_ctx* c, const uint32_t* tileList, uint32_t nList, uint32_t origLo, uint32_t origHi) {
   DerivArgs a{};
+  a.tileList = tileList; a.nList = nList; a.origLo = origLo; a.origHi = origHi;
   a.rows = c->rows; a.aux2 = c->aux2; a.perm = c->perm; a.nbrCount = c->nbrCount; a.tileRows = c->tileRows; a.tileOff = c->tileOff; a.nbr = c->nbr;
   const bool tens = c->opt.epsTensile != 0.0;
   const bool needQ = (c->opt.Qkind == SPHB200_Q_LIMITED_MG) || c->opt.balsara;
@@ -691,7 +703,9 @@ int sphb200_launch_derivs(sphb200_ctx* c) {
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
   const bool isoPath = c->allIsotropic && c->opt.hEvolution != SPHB200_H_ASPH;
-  const unsigned nb = (unsigned)std::min<size_t>((c->nTiles + wpb - 1)/wpb, (size_t)nsm*(isoPath ? SPHB200_PAIR_CTAS_ISO : PAIR_CTAS));
+  const size_t tilesHere = tileList ? (size_t)nList : c->nTiles;
+  if (tilesHere == 0) return 0;
+  const unsigned nb = (unsigned)std::min<size_t>((tilesHere + wpb - 1)/wpb, (size_t)nsm*(isoPath ? SPHB200_PAIR_CTAS_ISO : PAIR_CTAS));
   const bool gen = (c->opt.Qkind != SPHB200_Q_MG) || c->opt.balsara || mult || tens || !c->oneKernel ||
                    c->opt.linearInExpansion || c->opt.quadraticInExpansion;
   if (c->ndim == 3) { if (launch_dim<3>(c, a, nb, wpb*32, shm, gen)) return 1; }

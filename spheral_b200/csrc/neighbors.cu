@@ -1386,6 +1386,7 @@ int sphb200_sort_and_pack(sphb200_ctx* c) {
   k_cell_order<<<(cells + RB - 1)/RB, RB, 0, c->stream>>>(c->cellStart, cells, c->perm);
   KERNEL_CHECK(c, "k_cell_order");
   c->sortValid = true;
+  c->chunkListsValid = false;
   if (c->stencilR > 1) {
     if (sphb200_ensure(c, c->cellReach, c->cellReachCap, tbl)) return 1;
     CU_CHECK(c, cudaMemsetAsync(c->cellReach, 0, tbl*sizeof(uint32_t), c->stream));

@@ -167,6 +167,12 @@ struct sphb200_ctx {
   unsigned long long* dtCand = nullptr; size_t dtCandCap = 0;
   double* dtAux = nullptr; size_t dtAuxCap = 0;
   double* stage = nullptr; size_t stageBytes = 0;   // download staging (device)
+  // chunked evaluation with pipelined download (sphb200_evaluate_derivatives_to_host): per chunk of the host index range the tiles that
+  // hold its nodes; valid for the current sort
+  uint32_t* chunkList = nullptr; size_t chunkListCap = 0;     // SPHB200_MAX_CHUNKS lists of nTiles entries
+  uint32_t* chunkCount = nullptr; uint32_t* chunkCountHost = nullptr;   // device / pinned
+  bool chunkListsValid = false; int chunkQ = 0;
+  cudaEvent_t evChunk[8] = {nullptr};
 
   // instrumentation
   sphb200_stats stats{};
@@ -174,6 +180,7 @@ struct sphb200_ctx {
 };
 
 int  sphb200_fail(sphb200_ctx* c, const std::string& msg);
+constexpr int SPHB200_MAX_CHUNKS = 8;
 #define CU_CHECK(c, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
   return sphb200_fail((c), std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
 #define KERNEL_CHECK(c, name) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) \
@@ -194,6 +201,7 @@ int sphb200_pack_rows(sphb200_ctx* c);
 int sphb200_pack_rows_range(sphb200_ctx* c, size_t first, size_t count);   // rows of the nodes [first, first + count) only (sort unchanged)
 int sphb200_neighbors(sphb200_ctx* c);
 int sphb200_launch_derivs(sphb200_ctx* c);
+int sphb200_launch_derivs_chunk(sphb200_ctx* c, const uint32_t* tileList, uint32_t nList, uint32_t origLo, uint32_t origHi);
 int sphb200_launch_energy(sphb200_ctx* c, double multiplier);
 int sphb200_launch_crk_derivs(sphb200_ctx* c);
 int sphb200_pairs_to_host(sphb200_ctx* c, uint32_t* pi, uint32_t* pj, size_t cap, double* pacc, size_t paccCap);

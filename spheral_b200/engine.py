@@ -200,6 +200,21 @@ class Engine:
         self._check(self._lib.sphb200_download_derivs(self._h, mask, C.byref(hd)))
         return out
 
+    def evaluate_derivatives_to_host(self, *names, time=0.0, dt=1.0):
+        """evaluateDerivatives with the selected derivative fields delivered to host arrays, the download of one chunk of the host
+        index range overlapped with the pair loop of the next (sphb200_evaluate_derivatives_to_host)."""
+        names = names or L.DERIV_FIELDS
+        hd = L.HostDerivs()
+        out = {}
+        mask = 0
+        for k in names:
+            w = L.deriv_width(self.ndim, k)
+            out[k] = np.zeros((self.n, w) if w > 1 else self.n)
+            setattr(hd, k, _dp(out[k]))
+            mask |= L.DERIV_BITS[k]
+        self._check(self._lib.sphb200_evaluate_derivatives_to_host(self._h, time, dt, mask, C.byref(hd)))
+        return out
+
     def upload_derivs(self, **fields):
         """Restart (SPHBase::restoreState): node-wise derivative fields back onto the device; names from _lib.DERIV_FIELDS."""
         hd = L.HostDerivs()

@@ -475,8 +475,7 @@ class SPHB200(Physics):
                 needed.append(abi)
         self._sync_state(nl, state, needed)
         self._require_connectivity(dataBase, "evaluateDerivatives")
-        self._engine.evaluate_derivatives(time, dt)
-        got = self._engine.download_derivs()
+        got = self._engine.evaluate_derivatives_to_host(time=time, dt=dt)      # pair loop and download overlapped, same bits
         for abi, key in DERIV_KEYS.items():
             k = _key(key, nl.name)
             if k in derivs:

@@ -113,3 +113,53 @@ def test_morton_jump_tiles_and_ragged_sizes(oracle, mods, nbr_version):
     e.set_nodes(N, 0)
     e.upload_state(**both)
     _pairs_equal(oracle, e, both, N, 0, WT.kernelExtent)
+
+
+@pytest.mark.parametrize("order", ["lattice", "shuffled"])
+@pytest.mark.parametrize("workload,n", [("noh8m", 40), ("sedov1m", 36)])
+def test_evaluate_derivatives_to_host_is_bit_identical(mods, monkeypatch, workload, n, order):
+    """sphb200_evaluate_derivatives_to_host (pair loop in chunks of the host index range, each chunk's download overlapped with the next
+    chunk's computation) against evaluate_derivatives + download_derivs: every field bit-identical, pair accelerations included.
+    `lattice`: the generator's order (chunks are slabs, few tiles straddle two chunks).  `shuffled`: a random host order with the
+    chunking forced (SPHB200_E2H_FORCE=1) -- every tile holds nodes of every chunk and is visited by all of them -- and, unforced, the
+    fallback to the two separate calls."""
+    bench, engine = mods
+    spec = bench.workload_spec(workload)
+    st, N = bench.make_inputs(spec, n=n)
+    if order == "shuffled":
+        p = np.random.default_rng(5).permutation(N)
+        st = {k: np.ascontiguousarray(v[p]) for k, v in st.items()}
+    planes = bench.plane_list(spec) if spec.get("planes") else []
+
+    def run(fused, env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        e = engine.Engine(3, **bench.options_kwargs(spec, 0))
+        e.set_kernel_table(K.TableKernel(K.BSplineKernel(3), 1000))
+        e.set_nodes(N, 0)
+        if planes:
+            e.reflect_configure(planes)
+        e.upload_state(**st)
+        if planes:
+            e.reflect_set_ghost_nodes()
+        e.build_pairs()
+        if fused:
+            d = e.evaluate_derivatives_to_host()
+            again = e.download_derivs()                # the derivatives also stay on the device
+            for k in d:
+                assert np.array_equal(d[k], again[k]), k
+        else:
+            e.evaluate_derivatives(0.0, 1.0)
+            d = e.download_derivs()
+        pacc = e.download_pair_accelerations()
+        launches = e.stats()["launches"]
+        e.close()
+        return d, pacc, launches
+
+    ref, paccRef, _ = run(False, {})
+    for env in ({"SPHB200_E2H_FORCE": "1", "SPHB200_E2H_CHUNKS": "4"}, {"SPHB200_E2H_FORCE": "1", "SPHB200_E2H_CHUNKS": "7"},
+                {"SPHB200_E2H_FORCE": "0", "SPHB200_E2H_CHUNKS": "4"}):
+        got, pacc, _ = run(True, env)
+        for k in ref:
+            assert np.array_equal(got[k], ref[k]), (k, env)
+        assert np.array_equal(pacc, paccRef), env
