@@ -36,7 +36,7 @@ enum { SPHB200_Q_MG = 0, SPHB200_Q_LIMITED_MG = 1 };
 /* smoothing-scale sub-package run after the hydro (SPH/SPHHydros.py:129-140):
    SPHSmoothingScale.cc:101-275 | ASPHSmoothingScale.cc:110-147 | none */
 enum { SPHB200_H_SPH = 0, SPHB200_H_ASPH = 1, SPHB200_H_NONE = 2 };
-/* analytic kernels for sphb200_table_kernel_build (Kernel/*KernelInline.hh) */
+/* analytic kernels for sphb200_table_kernel_build (Kernel/<name>KernelInline.hh) */
 enum { SPHB200_KERNEL_BSPLINE = 0, SPHB200_KERNEL_WENDLANDC4 = 1, SPHB200_KERNEL_WENDLANDC2 = 2,
        SPHB200_KERNEL_NBSPLINE = 100 /* + order (1..11): NBSplineKernel(order), Kernel/NBSplineKernel.cc:17-122 -- the kernel of the stock
                                         Noh scripts (Noh-planar-1d.py, Noh-spherical-3d.py: NBSplineKernel(5)) */ };

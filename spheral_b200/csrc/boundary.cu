@@ -97,9 +97,12 @@ __global__ void __launch_bounds__(RB) k_reflect_scatter(const uint32_t* __restri
 //   kind 5 RK coefficients of linear order {A, B_k | dA/dx_d, dB_k/dx_d}: ReflectingBoundary::applyGhostBoundary(Field<RKCoefficients>)
 //          (Boundary/ReflectingBoundary.cc:403-432) applies RKUtilities::getTransformationMatrix(R) (RK/RKUtilities.cc:637-715):
 //          A' = A, B' = R.B, (grad A)' = R.grad A, (grad B)' = R.(grad B).R; periodic boundaries copy
+// all selected fields of a plane's ghosts in ONE launch (blockIdx.y = field): a launch per field made plane-ghost generation
+// launch-bound on small ranks (9 fields x 3 planes per step)
+struct FillSet { double* f[S_COUNT]; int kind[S_COUNT]; int width[S_COUNT]; int n; };
 template <int DIM>
-__global__ void __launch_bounds__(RB) k_reflect_fill(double* __restrict__ f, int kind, int width, const uint32_t* __restrict__ ctl,
-                                                     size_t first, size_t count, Plane pl) {
+__device__ __forceinline__ void reflect_fill_one(double* __restrict__ f, int kind, int width, const uint32_t* __restrict__ ctl,
+                                                 size_t first, size_t count, const Plane& pl) {
   const size_t k = (size_t)blockIdx.x*RB + threadIdx.x;
   if (k >= count) return;
   const size_t c = ctl[k], g = first + k;
@@ -185,6 +188,11 @@ __global__ void __launch_bounds__(RB) k_reflect_fill(double* __restrict__ f, int
     }
   }
 }
+template <int DIM>
+__global__ void __launch_bounds__(RB) k_reflect_fill(FillSet fs, const uint32_t* __restrict__ ctl, size_t first, size_t count, Plane pl) {
+  const int q = blockIdx.y;
+  reflect_fill_one<DIM>(fs.f[q], fs.kind[q], fs.width[q], ctl, first, count, pl);
+}
 
 // enforceBoundary: internal nodes behind a plane (signed distance < 0) are mirrored back, their velocity reflected and -- for a
 // reflecting plane -- their H tensor as well: PlanarBoundary::updateViolationNodes (PlanarBoundary.cc:179-195) calls
@@ -266,13 +274,16 @@ int fill_plane(sphb200_ctx* c, int p, unsigned mask) {
   if (count == 0) return 0;
   const Plane pl = plane_of(c, p);
   const unsigned nb = (unsigned)((count + RB - 1)/RB);
+  FillSet fs{};
   for (int s = 0; s < S_COUNT; ++s) {
     if (!(mask & (1u << s)) || !c->have[s] || !c->api[s]) continue;
-    const int kind = field_kind(c->ndim, s), w = sphb200_state_width(c->ndim, s);
-    if (c->ndim == 3) k_reflect_fill<3><<<nb, RB, 0, c->stream>>>(c->api[s], kind, w, c->planeCtl[p], first, count, pl);
-    else              k_reflect_fill<2><<<nb, RB, 0, c->stream>>>(c->api[s], kind, w, c->planeCtl[p], first, count, pl);
-    KERNEL_CHECK(c, "k_reflect_fill");
+    fs.f[fs.n] = c->api[s]; fs.kind[fs.n] = field_kind(c->ndim, s); fs.width[fs.n] = sphb200_state_width(c->ndim, s); ++fs.n;
   }
+  if (fs.n == 0) return 0;
+  const dim3 grid(nb, (unsigned)fs.n);
+  if (c->ndim == 3) k_reflect_fill<3><<<grid, RB, 0, c->stream>>>(fs, c->planeCtl[p], first, count, pl);
+  else              k_reflect_fill<2><<<grid, RB, 0, c->stream>>>(fs, c->planeCtl[p], first, count, pl);
+  KERNEL_CHECK(c, "k_reflect_fill");
   return 0;
 }
 

@@ -85,6 +85,10 @@ __device__ __forceinline__ const unsigned char* mad_wide(uint32_t a, uint32_t b,
   return reinterpret_cast<const unsigned char*>(r);
 }
 
+#ifndef SPHB200_PAIR_UNROLL
+#define SPHB200_PAIR_UNROLL 1
+#endif
+constexpr int PAIR_UNROLL = SPHB200_PAIR_UNROLL;   // unroll factor of the neighbour loop (1: measured best, see profiles/r02_notes.md)
 constexpr int PAIR_STAGES = SPHB200_PAIR_STAGES;   // depth of the neighbour-row ring
 constexpr int PAIR_WARPS = SPHB200_PAIR_WARPS;     // warps (= tiles in flight) per CTA
 constexpr int PAIR_CTAS = SPHB200_PAIR_CTAS;       // resident CTAs per SM the register budget is sized for
@@ -245,6 +249,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
     jn = load_idx(p + 1u);
   }
 
+#pragma unroll PAIR_UNROLL
   for (uint32_t k = 0; k < rows; ++k) {
     cp_async_wait<PAIR_STAGES - 2>();                 // this lane's copies for position k have landed ...
     __syncwarp();                                     // ... and so have every other lane's

@@ -112,6 +112,18 @@ int main(int argc, char** argv) {
   check(sphb200_download_derivs(ctx, SPHB200_D_ALL, &hd), "download_derivs");
   std::vector<double> pacc(3*npairs);
   check(sphb200_download_pair_accelerations(ctx, pacc.data(), pacc.size()), "download_pair_accelerations");
+  // the same evaluation delivered to host fields by the one-call form (chunked pair loop, download overlapped): identical bits
+  { std::vector<double> DvDt2(3*N), DvDx2(9*N), DHDt2(6*N), DxDt2(3*N);
+    sphb200_host_derivs h2{};
+    h2.DvDt = DvDt2.data(); h2.DvDx = DvDx2.data(); h2.DHDt = DHDt2.data(); h2.DxDt = DxDt2.data();
+    setenv("SPHB200_E2H_FORCE", "1", 1);                                       // chunk although the problem is small
+    check(sphb200_evaluate_derivatives_to_host(ctx, 0.0, 1.0, SPHB200_D_DVDT | SPHB200_D_DVDX | SPHB200_D_DHDT | SPHB200_D_DXDT, &h2), "evaluate_derivatives_to_host");
+    unsetenv("SPHB200_E2H_FORCE");
+    require(std::memcmp(DvDt2.data(), DvDt.data(), 3*N*sizeof(double)) == 0 && std::memcmp(DvDx2.data(), DvDx.data(), 9*N*sizeof(double)) == 0 &&
+            std::memcmp(DHDt2.data(), DHDt.data(), 6*N*sizeof(double)) == 0 && std::memcmp(DxDt2.data(), DxDt.data(), 3*N*sizeof(double)) == 0,
+            "evaluate_derivatives_to_host delivers the bits of evaluate_derivatives + download_derivs");
+    sphb200_host_derivs none2{};
+    require(sphb200_evaluate_derivatives_to_host(ctx, 0.0, 1.0, SPHB200_D_DVDT, &none2) != 0, "a selected field without a destination is an error"); }
 
   // sum_i m_i DvDt_i = 0 (pairwise antisymmetric forces) and DvDt_i = sum over its pairs of the pair accelerations (SPH.cc:427-430)
   { double mom[3] = {0, 0, 0}, scale = 0.0;
