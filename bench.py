@@ -653,7 +653,10 @@ def main():
                             "grid_stencil_radius": int(st_["stencil_radius"]), "xsph": int(args.xsph), "cpu_affinity": affinity},
                 "clocks": clocks,
                 "e2e": {"value": float(Ntot)*args.steps/e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "timing": "host wall clock around synchronised C-ABI calls (pinned host buffers), max over ranks"},
+                        "timing": "host wall clock around synchronised C-ABI calls (pinned host buffers), max over ranks",
+                        "calls": ("upload_state, reflect_set_ghost_nodes, [halo], build_pairs, evaluate_derivatives_to_host (pair loop in chunks of the host index "
+                                  "range, each chunk's download overlapped with the next chunk's computation)") if hp.fused_e2e else
+                                 "upload_state, reflect_set_ghost_nodes, [halo], build_pairs, evaluate_derivatives, download_derivs"},
                 "gpu_launches": int(launches),
                 "breakdown_ms": {"build_pairs": float(np.mean(build_ms)), "neighbor_kernels": float(np.mean(nbr_ms)),
                                  "evaluate": float(np.mean(eval_ms)), "pair_kernel": float(np.mean(pair_ms)),

@@ -308,7 +308,8 @@ int  sphb200_halo_select(sphb200_ctx* ctx, int axis, size_t count, double lo, do
 /* Stream-ordered variants with NO host synchronisation, so that a whole ghost refresh costs one host round trip (the
    counts): the bounds land in a 9-double device buffer {lo[3], hi[3], maxExtent[3]} (which the plumbing all-reduces in place
    over NCCL), the selection reads the halo width maxExtent[axis]*(1+1e-9) from that device buffer and leaves
-   {nLow, nHigh} (int64) in countsDevice.  Lists longer than cap are truncated; the caller checks the counts.
+   {nLow, nHigh, cap} (int64) in countsDevice (the table a rank all-gathers).  Lists longer than cap are truncated; the caller
+   checks the counts.
    `count` may exceed the number of internal nodes: with reflecting / periodic planes the plane ghosts generated by
    sphb200_reflect_set_ghost_nodes sit right behind the internal nodes and are selected like them (the reference's
    DistributedBoundary comes last in the boundary list and exchanges the ghosts of the other boundaries too); the halo is then
@@ -316,7 +317,7 @@ int  sphb200_halo_select(sphb200_ctx* ctx, int axis, size_t count, double lo, do
    working on the leading part of the ghost tail. */
 int sphb200_node_bounds_device(sphb200_ctx* ctx, size_t count, double* boundsDevice /*[9]*/);
 int sphb200_halo_select_device(sphb200_ctx* ctx, int axis, size_t count, double lo, double hi, const double* maxExtentDevice /*[3]*/,
-                               uint32_t* sendLowDevice, uint32_t* sendHighDevice, long long* countsDevice /*[2]*/, size_t cap);
+                               uint32_t* sendLowDevice, uint32_t* sendHighDevice, long long* countsDevice /*[3]*/, size_t cap);
 /* raw stream handle (cudaStream_t) so the plumbing can order NCCL calls after pack / before unpack */
 void* sphb200_stream(sphb200_ctx* ctx);
 

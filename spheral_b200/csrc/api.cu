@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(RB) k_halo_flags_dev(const double* __restrict_
   fLow[i] = (x < lo + w) ? 1u : 0u;
   fHigh[i] = (x >= hi - w) ? 1u : 0u;
 }
-__global__ void k_halo_counts(const uint32_t* __restrict__ offLow, const uint32_t* __restrict__ offHigh, size_t count, long long* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = (long long)offLow[count]; out[1] = (long long)offHigh[count]; }
+__global__ void k_halo_counts(const uint32_t* __restrict__ offLow, const uint32_t* __restrict__ offHigh, size_t count, size_t cap, long long* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = (long long)offLow[count]; out[1] = (long long)offHigh[count]; out[2] = (long long)cap; }
 }
 __global__ void __launch_bounds__(RB) k_halo_scatter(const uint32_t* __restrict__ offLow, const uint32_t* __restrict__ offHigh, size_t count,
                                                      size_t cap, uint32_t* __restrict__ outLow, uint32_t* __restrict__ outHigh) {
@@ -933,7 +933,7 @@ int sphb200_halo_select_device(sphb200_ctx* c, int axis, size_t count, double lo
   if (sphb200_scan_u32(c, fHigh, fHigh, count)) return 1;
   k_halo_scatter<<<nb, RB, 0, c->stream>>>(fLow, fHigh, count, cap, sendLow, sendHigh);
   KERNEL_CHECK(c, "k_halo_scatter");
-  k_halo_counts<<<1, 32, 0, c->stream>>>(fLow, fHigh, count, countsDevice);
+  k_halo_counts<<<1, 32, 0, c->stream>>>(fLow, fHigh, count, cap, countsDevice);
   KERNEL_CHECK(c, "k_halo_counts");
   return 0;
 }

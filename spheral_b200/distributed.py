@@ -152,12 +152,26 @@ class DistributedSPH:
 
     def __init__(self, engine, axis, lo, hi, halo=None, extra_fields=(), two_phase=None):
         self.e = engine
-        # default: split exchange (SPHB200_HALO_TWO_PHASE=0 selects the single batch, for A/B measurements)
-        self.two_phase = (os.environ.get("SPHB200_HALO_TWO_PHASE", "1") != "0") if two_phase is None else bool(two_phase)
+        # default: split exchange (positions + H first, the rest in flight during the neighbour build) from 2 M internal nodes per rank on,
+        # one batch below -- the split costs two more pack / unpack launches, a second NCCL batch and a partial re-pack of the rows, which a
+        # small slab does not win back (2 ranks x 1 M: 4.31 ms split, 4.20 ms single batch; 2 ranks x 4 M: 16.61 / 16.53 ms).
+        # SPHB200_HALO_TWO_PHASE=0 / 1 forces one or the other (A/B measurements)
+        env = os.environ.get("SPHB200_HALO_TWO_PHASE")
+        if two_phase is not None:
+            self.two_phase = bool(two_phase)
+        elif env is not None:
+            self.two_phase = env != "0"
+        else:
+            self.two_phase = None                    # decided below from the smallest slab, identically on every rank
         self.axis, self.lo, self.hi = axis, float(lo), float(hi)
         self.halo = halo if halo is not None else SlabHalo()
         self.dev = torch.device("cuda", engine_device(engine))
         self.stream = torch.cuda.ExternalStream(engine.stream, device=self.dev)
+        if self.two_phase is None:
+            t = torch.tensor([engine.nInternal], dtype=torch.int64, device=self.dev)
+            if self.halo.world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.halo.group)
+            self.two_phase = int(t.item()) >= (1 << 21)
         self.maskA = field_mask(PHASE_A)
         # extra_fields: state fields that only exist once a package has computed them (CRKSPH: "volume", "rkCorrections").  They join
         # the exchange from the moment the integrator reports them ready (mark_ready); the staging is sized for all of them.
@@ -244,7 +258,6 @@ class DistributedSPH:
                 h.allreduce_max(ext)
                 e.halo_select_device(self.axis, self.lo, self.hi, ext.data_ptr(), self.idxLow.data_ptr(), self.idxHigh.data_ptr(),
                                      self._counts.data_ptr(), self._cap, nOwn)
-                self._counts[2] = self._cap
                 if h.world > 1:
                     dist.all_gather_into_tensor(self._allc, self._counts, group=h.group)
                 else:
