@@ -594,24 +594,30 @@ int sphb200_download_derivs(sphb200_ctx* c, unsigned mask, const sphb200_host_de
 // Tiles of each chunk of the host index range: chunk q = internal nodes with original index in [q*chunkSize, (q+1)*chunkSize) (the
 // last chunk takes the remainder and the ghost nodes, whose derivative entries are zeros).  A tile that holds nodes of several chunks
 // is listed in each of them.  The order inside a list is whatever the atomics give (roughly ascending); results do not depend on it.
-__global__ void __launch_bounds__(RB) k_chunk_lists(const uint32_t* __restrict__ perm, size_t n, uint32_t nInt, uint32_t chunkSize, int Q,
-                                                    size_t nTiles, uint32_t* __restrict__ lists, uint32_t* __restrict__ counts) {
-  const size_t tile = ((size_t)blockIdx.x*RB + threadIdx.x) >> 5;
+constexpr int CL_THREADS = 1024;                 // 32 tiles per block: one global atomic per (block, chunk) instead of one per (tile, chunk)
+__global__ void __launch_bounds__(CL_THREADS) k_chunk_lists(const uint32_t* __restrict__ perm, size_t n, uint32_t nInt, uint32_t chunkSize, int Q,
+                                                            size_t nTiles, uint32_t* __restrict__ lists, uint32_t* __restrict__ counts) {
+  __shared__ uint32_t cnt[SPHB200_MAX_CHUNKS], base[SPHB200_MAX_CHUNKS];
+  if (threadIdx.x < SPHB200_MAX_CHUNKS) cnt[threadIdx.x] = 0u;
+  __syncthreads();
+  const size_t tile = ((size_t)blockIdx.x*CL_THREADS + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (tile >= nTiles) return;
   const size_t i = tile*SPHB200_TILE + lane;
   unsigned m = 0u;
-  if (i < n) {
+  if (tile < nTiles && i < n) {
     const uint32_t o = perm[i];
     const uint32_t q = (o < nInt) ? min((uint32_t)(Q - 1), o/chunkSize) : (uint32_t)(Q - 1);
     m = 1u << q;
   }
   m = __reduce_or_sync(0xffffffffu, m);
+  uint32_t pos[SPHB200_MAX_CHUNKS];
   if (lane == 0)
-    for (; m; m &= m - 1u) {
-      const int q = __ffs(m) - 1;
-      lists[(size_t)q*nTiles + atomicAdd(&counts[q], 1u)] = (uint32_t)tile;
-    }
+    for (unsigned r = m; r; r &= r - 1u) { const int q = __ffs(r) - 1; pos[q] = atomicAdd(&cnt[q], 1u); }
+  __syncthreads();
+  if (threadIdx.x < (unsigned)Q && cnt[threadIdx.x]) base[threadIdx.x] = atomicAdd(&counts[threadIdx.x], cnt[threadIdx.x]);
+  __syncthreads();
+  if (lane == 0)
+    for (unsigned r = m; r; r &= r - 1u) { const int q = __ffs(r) - 1; lists[(size_t)q*nTiles + base[q] + pos[q]] = (uint32_t)tile; }
 }
 // sorted SoA (component-major) -> host AoS order for the original indices [lo, hi): one thread per output element (coalesced writes)
 __global__ void __launch_bounds__(RB) k_unpermute_range(const double* __restrict__ src, size_t cap, const uint32_t* __restrict__ invPerm,
@@ -648,7 +654,7 @@ int sphb200_evaluate_derivatives_to_host(sphb200_ctx* c, double time, double dt,
     if (!c->chunkListsValid || c->chunkQ != Q) {
       if (sphb200_ensure(c, c->chunkList, c->chunkListCap, (size_t)SPHB200_MAX_CHUNKS*(c->cap/SPHB200_TILE + 2))) return 1;
       CU_CHECK(c, cudaMemsetAsync(c->chunkCount, 0, SPHB200_MAX_CHUNKS*sizeof(uint32_t), c->stream));
-      k_chunk_lists<<<(unsigned)((c->nTiles*32 + RB - 1)/RB), RB, 0, c->stream>>>(c->perm, c->n, (uint32_t)c->nInt, chunkSize, Q, c->nTiles, c->chunkList, c->chunkCount);
+      k_chunk_lists<<<(unsigned)((c->nTiles*32 + CL_THREADS - 1)/CL_THREADS), CL_THREADS, 0, c->stream>>>(c->perm, c->n, (uint32_t)c->nInt, chunkSize, Q, c->nTiles, c->chunkList, c->chunkCount);
       KERNEL_CHECK(c, "k_chunk_lists");
       CU_CHECK(c, cudaMemcpyAsync(c->chunkCountHost, c->chunkCount, SPHB200_MAX_CHUNKS*sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
       CU_CHECK(c, cudaStreamSynchronize(c->stream));
