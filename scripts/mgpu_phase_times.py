@@ -26,4 +26,20 @@ for _ in range(K):
     tick("evaluate_derivatives", lambda: e.evaluate_derivatives(0.0, 1.0))
 if rank == 0:
     print(json.dumps({k: round(v/K*1e3, 3) for k, v in T.items()}, indent=1))
+# host-side enqueue times of the un-synchronised loop (SPHB200_HALO_TIMING=1)
+if d is not None and d._timing:
+    d.cpu_ms.clear()
+    tp = {}
+    e.sync(); t00 = time.perf_counter()
+    for _ in range(20):
+        t0 = time.perf_counter(); nPG = e.reflect_set_ghost_nodes(); t1 = time.perf_counter()
+        d.refresh_ghosts(build=True, boundary_ghosts=nPG); t2 = time.perf_counter()
+        e.evaluate_derivatives(0.0, 1.0); t3 = time.perf_counter()
+        for k, v in (("plane ghosts (3 syncs; waits for the previous pair kernel)", t1 - t0), ("refresh_ghosts", t2 - t1), ("evaluate_derivatives (enqueue)", t3 - t2)):
+            tp[k] = tp.get(k, 0.0) + v*1e3
+    e.sync(); tot = (time.perf_counter() - t00)*1e3/20
+    if rank == 0:
+        print("host timeline, un-synchronised loop, ms per step: total %.3f" % tot)
+        print(json.dumps({k: round(v/20, 3) for k, v in tp.items()}, indent=1))
+        print(json.dumps({k: round(v/20, 3) for k, v in d.cpu_ms.items()}, indent=1))
 if dist is not None: dist.destroy_process_group()

@@ -172,6 +172,7 @@ class DistributedSPH:
             if self.halo.world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.halo.group)
             self.two_phase = int(t.item()) >= (1 << 21)
+        self._timing, self.cpu_ms, self._t = os.environ.get("SPHB200_HALO_TIMING", "0") != "0", {}, 0.0
         self.maskA = field_mask(PHASE_A)
         # extra_fields: state fields that only exist once a package has computed them (CRKSPH: "volume", "rkCorrections").  They join
         # the exchange from the moment the integrator reports them ready (mark_ready); the staging is sized for all of them.
@@ -228,6 +229,17 @@ class DistributedSPH:
     def refresh_ghosts_and_build(self):
         return self.refresh_ghosts(build=True)
 
+    def _tick(self, name):
+        """SPHB200_HALO_TIMING=1: host-side time between the marks of refresh_ghosts, accumulated in self.cpu_ms (diagnostic: on small
+        slabs the host enqueue path, not the GPU, bounds the ghost refresh)."""
+        if not self._timing:
+            return
+        import time
+        now = time.perf_counter()
+        if name is not None:
+            self.cpu_ms[name] = self.cpu_ms.get(name, 0.0) + (now - self._t)*1e3
+        self._t = now
+
     def refresh_ghosts(self, build=True, boundary_ghosts=0):
         """Ghost selection + exchange (+ neighbour build).  Returns the number of node pairs of this slab (None without the build).
         `boundary_ghosts`: number of plane ghosts already generated behind the internal nodes (see nBoundaryGhost).
@@ -243,6 +255,8 @@ class DistributedSPH:
         nInt = self.nInternal
         if nInt == 0:
             raise RuntimeError("DistributedSPH: a slab without internal nodes is not supported")
+        tick = self._tick
+        tick(None)
         nBG = self.nBoundaryGhost = int(boundary_ghosts)
         nOwn = nInt + nBG                                  # nodes this slab can send: internal + its own plane ghosts
         with torch.cuda.stream(self.stream):
@@ -256,13 +270,16 @@ class DistributedSPH:
                 e.node_bounds_device(nOwn, self._bounds.data_ptr())
                 ext = self._bounds[6:9]
                 h.allreduce_max(ext)
+                tick("bounds + all-reduce enqueued")
                 e.halo_select_device(self.axis, self.lo, self.hi, ext.data_ptr(), self.idxLow.data_ptr(), self.idxHigh.data_ptr(),
                                      self._counts.data_ptr(), self._cap, nOwn)
                 if h.world > 1:
                     dist.all_gather_into_tensor(self._allc, self._counts, group=h.group)
                 else:
                     self._allc.copy_(self._counts)
+                tick("select + all-gather enqueued")
                 allc = self._allc.cpu().numpy().reshape(h.world, 3)          # the one host round trip
+                tick("counts on the host (sync)")
                 nLow, nHigh = int(allc[h.rank, 0]), int(allc[h.rank, 1])
                 # Redo the selection if ANY rank truncated a send list it will use.  The decision is taken from the gathered table,
                 # identically on every rank: a rank-local test would let one slab repeat the all-gather while its neighbour moves
@@ -287,11 +304,15 @@ class DistributedSPH:
                 mask = self.maskA | maskB
                 e.halo_pack(mask, self.idxLow.data_ptr(), nLow, self.sLowB.data_ptr())
                 e.halo_pack(mask, self.idxHigh.data_ptr(), nHigh, self.sHighB.data_ptr())
+                tick("packs enqueued")
                 works = h.start(self.sLowB[:nLow*wAB], self.sHighB[:nHigh*wAB], self.rLowB[:nFL*wAB], self.rHighB[:nFU*wAB])
+                tick("send/recv batch enqueued")
                 h.finish(works)
                 e.halo_unpack(mask, nOwn, nFL, self.rLowB.data_ptr())
                 e.halo_unpack(mask, nOwn + nFL, nFU, self.rHighB.data_ptr())
+                tick("wait + unpacks enqueued")
                 npairs = e.build_pairs() if build else None
+                tick("build_pairs (sync)")
             else:
                 # pack both phases, then post A and B; K1+K2 only wait for A
                 e.halo_pack(self.maskA, self.idxLow.data_ptr(), nLow, self.sLowA.data_ptr())
