@@ -774,6 +774,7 @@ int sphb200_update_energy_compatible(sphb200_ctx* c, double multiplier) {
   cudaEventRecord(c->ev[6], c->stream);
   if (sphb200_launch_energy(c, multiplier)) return 1;
   cudaEventRecord(c->ev[7], c->stream);
+  c->energyTimed = true;
   return 0;
 }
 
@@ -952,7 +953,7 @@ int sphb200_get_stats(sphb200_ctx* c, sphb200_stats* out) {
     if (cudaEventElapsedTime(&c->stats.ms_evaluate, c->ev[3], c->ev[5]) != cudaSuccess) c->stats.ms_evaluate = 0;
     if (cudaEventElapsedTime(&c->stats.ms_pair_kernel, c->ev[4], c->ev[5]) != cudaSuccess) c->stats.ms_pair_kernel = 0;
   }
-  if (cudaEventElapsedTime(&c->stats.ms_energy, c->ev[6], c->ev[7]) != cudaSuccess) c->stats.ms_energy = 0;
+  if (!c->energyTimed || cudaEventElapsedTime(&c->stats.ms_energy, c->ev[6], c->ev[7]) != cudaSuccess) c->stats.ms_energy = 0;   // events never recorded: no API error
   cudaGetLastError();
   c->stats.stencil_radius = (uint32_t)c->stencilR;
   c->stats.fine_walk = c->fineWalk ? 1u : 0u;

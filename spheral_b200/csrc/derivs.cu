@@ -85,6 +85,9 @@ __device__ __forceinline__ const unsigned char* mad_wide(uint32_t a, uint32_t b,
   return reinterpret_cast<const unsigned char*>(r);
 }
 
+#ifndef SPHB200_TILE_SYNC
+#define SPHB200_TILE_SYNC 5     // 0: none (formally a race), 1 / 4: warp barrier after the tile's loop, 2 / 3: before the next tile's prologue, 5: rotating ring base (no barrier)
+#endif
 #ifndef SPHB200_PAIR_UNROLL
 #define SPHB200_PAIR_UNROLL 1
 #endif
@@ -131,6 +134,12 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
   const unsigned warpRing = tW + 8u*(nW + nQ) + (unsigned)warp*(PAIR_STAGES*STAGEB);
   const sphb200_options& o = a.o;
   const size_t nTiles = a.tileList ? (size_t)a.nList : (a.n + SPHB200_TILE - 1)/SPHB200_TILE;
+  // Ring stage of list position 0 of the current tile.  It rotates from tile to tile so that the prologue of a tile never refills the
+  // stage the previous tile read LAST: a lane that leaves a tile early (ghost, node of another chunk, short list) may issue the next
+  // prologue while a slower lane is still reading that stage, and the first __syncwarp both have passed orders every earlier read only
+  // (compute-sanitizer racecheck reports this tile-to-tile write-after-read).  A warp barrier between tiles cures it too but costs
+  // 2 % of the kernel (15.27 -> 15.6-15.9 ms at 8 M, profiles/r02_notes.md); the rotation costs nothing.
+  uint32_t stageBase = 0u;
   for (size_t tl = (size_t)blockIdx.x*PAIR_WARPS + warp; tl < nTiles; tl += (size_t)gridDim.x*PAIR_WARPS) {
   const size_t tile = a.tileList ? (size_t)a.tileList[tl] : tl;
   const size_t i = tile*SPHB200_TILE + lane;
@@ -203,7 +212,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
   const unsigned char* const srcLane = rowsB + 16*(lane & (SPHB200_COPY_LANES - 1));
   auto issue_rows = [&](uint32_t p, uint32_t jraw) {  // jraw: this lane's list entry at position p (0 if none)
     const uint32_t jrow = jraw;
-    const unsigned stage = warpRing + (p % PAIR_STAGES)*(unsigned)STAGEB;
+    const unsigned stage = warpRing + ((p + stageBase) % PAIR_STAGES)*(unsigned)STAGEB;
 #if SPHB200_PAIR_AUX
     cp_async16_s(stage + 32u*ROWB + 16u*lane, a.aux2 + 2*(size_t)jrow);        // this lane's own neighbour: {det H, 1/rho}
 #endif
@@ -243,6 +252,14 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
     return (p < cnt) ? a.nbr[base + (unsigned long long)p*SPHB200_TILE] : 0u;
   };
   uint32_t jn = load_idx(0u);
+  // every lane is past its reads of the previous tile's ring stages before this tile's prologue refills them (a lane that left the
+  // previous tile early -- a ghost, a node of another chunk -- must not run ahead of the others' last reads; racecheck reports the
+  // tile-to-tile write-after-read otherwise)
+#if SPHB200_TILE_SYNC == 2
+  __syncwarp();
+#elif SPHB200_TILE_SYNC == 3
+  asm volatile("bar.warp.sync 0xffffffff;");      // execution barrier only: no compiler memory fence (the ring accesses are volatile asm themselves)
+#endif
 #pragma unroll
   for (uint32_t p = 0; p < (uint32_t)PAIR_STAGES - 1u; ++p) {
     issue_rows(p, jn);
@@ -257,7 +274,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
     double rw[ROW];
     double2 aux;
     {
-      const unsigned st = warpRing + (k % PAIR_STAGES)*(unsigned)STAGEB;
+      const unsigned st = warpRing + ((k + stageBase) % PAIR_STAGES)*(unsigned)STAGEB;
       const unsigned rp = st + (unsigned)lane*ROWB;
 #pragma unroll
       for (int q = 0; q < ROW/2; ++q) { const double2 v = lds128v(rp + 16u*q); rw[2*q] = v.x; rw[2*q + 1] = v.y; }
@@ -542,6 +559,13 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
   }
 
   cp_async_wait<0>();
+#if SPHB200_TILE_SYNC == 1
+  __syncwarp();
+#elif SPHB200_TILE_SYNC == 4
+  asm volatile("bar.warp.sync 0xffffffff;");
+#elif SPHB200_TILE_SYNC == 5
+  stageBase = (stageBase + rows) % (uint32_t)PAIR_STAGES;      // the next prologue fills every stage but (rows - 1 + old base) % PAIR_STAGES
+#endif
   if (!inRange) continue;
   // ---- K4: per-node finalize (SPH.cc:480-552); ghost nodes get zeros
   const size_t cap = a.cap;

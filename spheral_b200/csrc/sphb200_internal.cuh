@@ -177,6 +177,7 @@ struct sphb200_ctx {
   // instrumentation
   sphb200_stats stats{};
   cudaEvent_t ev[8] = {nullptr};
+  bool energyTimed = false;          // ev[6], ev[7] have been recorded (sphb200_update_energy_compatible ran)
 };
 
 int  sphb200_fail(sphb200_ctx* c, const std::string& msg);
