@@ -34,6 +34,9 @@ __device__ __forceinline__ double2 ring_lds128(unsigned addr) {
   return v;
 }
 
+#ifndef SPHB200_RING_ROTATE
+#define SPHB200_RING_ROTATE 1
+#endif
 constexpr int ring_pad(int bytes) { return bytes == 0 ? 0 : (((bytes/16) & 1) ? bytes : bytes + 16); }
 
 // the leading BYTES of 32 records (STRIDE bytes apart in memory, record index jrow of every lane) -> rows of stride RB at dst0
@@ -85,8 +88,9 @@ struct NbrRing {
 
   unsigned base;                                  // 32-bit shared address of this warp's ring
   const unsigned char *rows, *x1, *x2, *aux2;
+  mutable unsigned rot = 0u;                      // stage of list position 0 of the current walk (ring_walk rotates it from walk to walk)
 
-  __device__ __forceinline__ unsigned stage(uint32_t p) const { return base + (p % STAGES)*(unsigned)STAGEB; }
+  __device__ __forceinline__ unsigned stage(uint32_t p) const { return base + ((p + rot) % STAGES)*(unsigned)STAGEB; }
   // jrow: this lane's list entry at position p (0 past the end of the lane's list: row 0 is fetched and never read back)
   __device__ __forceinline__ void issue(uint32_t p, uint32_t jrow, int lane) const {
     const unsigned st = stage(p);
@@ -147,7 +151,16 @@ __device__ __forceinline__ void ring_walk(const Ring& ring, int lane, uint32_t r
     if (k < cnt) body(k, j);
   }
   ring_wait<0>();
+#if SPHB200_RING_ROTATE
+  // The next walk of this warp (next tile, or the next pass over the same tile) must not refill a stage a slower lane still reads.
+  // Every read but those of the last iteration precedes a __syncwarp all lanes have passed; the last iteration read stage
+  // (rot + rowsT - 1) % STAGES.  Advancing rot by rowsT makes that the one stage the next prologue (positions 0 .. STAGES-2) leaves
+  // alone, and its refill in iteration 0 of the next walk comes after that iteration's __syncwarp.  A __syncwarp here does the same
+  // at +3 % kernel time (measured on k_sph_derivs, profiles/r02_notes.md 11e).
+  ring.rot = (ring.rot + rowsT) % (unsigned)STAGES;
+#else
   __syncwarp();
+#endif
 }
 
 }  // namespace

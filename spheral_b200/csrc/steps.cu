@@ -40,7 +40,8 @@ template <int DIM> using PosRing = NbrRing<DIM, 0, 0, SS, (DIM == 3 ? 32 : 16), 
 struct DtRing {
   static constexpr int REC = 32, RB = ring_pad(REC), STAGEB = 32*RB, WARPB = SS*STAGEB;
   unsigned base; const unsigned char* recs;
-  __device__ __forceinline__ unsigned stage(uint32_t p) const { return base + (p % SS)*(unsigned)STAGEB; }
+  mutable unsigned rot = 0u;                         // see NbrRing::rot
+  __device__ __forceinline__ unsigned stage(uint32_t p) const { return base + ((p + rot) % SS)*(unsigned)STAGEB; }
   __device__ __forceinline__ void issue(uint32_t p, uint32_t jrow, int lane) const {
     ring_copy_records<REC, RB, REC>(stage(p), recs, jrow, lane);
     ring_commit();
