@@ -676,15 +676,22 @@ int sphb200_evaluate_derivatives_to_host(sphb200_ctx* c, double time, double dt,
     // Without XSPH DxDt of an internal node IS its velocity (SPH.cc:503-509), which sits on the device in host order already: it
     // leaves first, while the first chunk is computed (the ghost entries -- zeros -- follow with the last chunk)
     const bool dxdtEarly = (mask & (1u << DV_DXDT)) && !c->opt.XSPH && c->have[S_VEL];
+    if (dxdtEarly) CU_CHECK(c, cudaEventRecord(c->evMainMark, c->stream));      // the velocity is final here (uploads joined, no kernel of this call writes it)
+    // every chunk is enqueued before the first copy: a copy into pageable host memory blocks the calling thread until it is done, and
+    // must not keep the next chunk from being launched
+    for (int q = 0; q < Q; ++q) {
+      const uint32_t lo = (uint32_t)q*chunkSize, hi = (q == Q - 1) ? 0xffffffffu : (uint32_t)(q + 1)*chunkSize;
+      if (sphb200_launch_derivs_chunk(c, c->chunkList + (size_t)q*c->nTiles, c->chunkCountHost[q], lo, hi)) return 1;
+      CU_CHECK(c, cudaEventRecord(c->evChunk[q], c->stream));
+    }
+    c->derivsValid = true;
+    if (evaluate_finish(c)) return 1;
     if (dxdtEarly) {
-      CU_CHECK(c, cudaEventRecord(c->evMainMark, c->stream));
       CU_CHECK(c, cudaStreamWaitEvent(c->copyStream, c->evMainMark, 0));
       CU_CHECK(c, cudaMemcpyAsync(deriv_ptr(d, DV_DXDT), c->api[S_VEL], c->nInt*(size_t)c->ndim*sizeof(double), cudaMemcpyDeviceToHost, c->copyStream));
     }
     for (int q = 0; q < Q; ++q) {
       const uint32_t lo = (uint32_t)q*chunkSize, hi = (q == Q - 1) ? 0xffffffffu : (uint32_t)(q + 1)*chunkSize;
-      if (sphb200_launch_derivs_chunk(c, c->chunkList + (size_t)q*c->nTiles, c->chunkCountHost[q], lo, hi)) return 1;
-      CU_CHECK(c, cudaEventRecord(c->evChunk[q], c->stream));
       CU_CHECK(c, cudaStreamWaitEvent(c->copyStream, c->evChunk[q], 0));
       // this chunk's slice of every selected field: un-permute into the staging area and copy, while the next chunk is computed
       const size_t olo = lo, ohi = (q == Q - 1) ? c->n : (size_t)hi;          // the last chunk carries the ghost entries (zeros)
@@ -703,8 +710,6 @@ int sphb200_evaluate_derivatives_to_host(sphb200_ctx* c, double time, double dt,
         off += c->n*(size_t)w;
       }
     }
-    c->derivsValid = true;
-    if (evaluate_finish(c)) return 1;
     CU_CHECK(c, cudaStreamSynchronize(c->copyStream));
     return 0;
   }
