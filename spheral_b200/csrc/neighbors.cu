@@ -295,7 +295,10 @@ __global__ void __launch_bounds__(RB) k_pack(PackArgs a) {
 // it LSU-bound at 2 TB/s of DRAM traffic (1.7 ms).  k_pack_scatter walks the nodes in HOST order instead: a warp reads the fields of
 // 32 consecutive nodes (coalesced), builds their rows in shared memory and then writes each row to its sorted slot with one full
 // 128-byte line per 8 lanes (64 bytes per 4 lanes for the FP32 rows).  Same values bit for bit (the arithmetic is shared).
-template <int DIM>
+// FROWS: also build the FP32 pre-filter row of the neighbour build (cell-relative position, Jacobi eigenvalue bounds of H, band
+// thresholds).  A re-pack on a valid connectivity (values changed: sum density, EOS, a state update on the step-start pair lists,
+// fields that landed after the build) leaves it out: only K2 reads those rows, and the next sort packs them again.
+template <int DIM, bool FROWS = true>
 __device__ __forceinline__ void pack_one(const PackArgs& a, size_t o, double* r, float* f, double* aux, bool& aniso) {
   using D = Dm<DIM>;
 #pragma unroll
@@ -311,6 +314,7 @@ __device__ __forceinline__ void pack_one(const PackArgs& a, size_t o, double* r,
   r[D::R_PRHO] = a.rawP ? P : safeOmega*P/(rho*rho);             // SPH.cc:425 with Peff == P
   if (DIM == 2) r[11] = 0.0;
   aux[0] = sym_det<DIM>(Hn); aux[1] = 1.0/rho; aux[2] = (P < 0.0 ? -P : 0.0); aux[3] = safeOmega/(rho*rho);
+  if constexpr (!FROWS) return;
   // FP32 pre-filter row: see k_pack for the error model
   double hf = 0.0;
 #pragma unroll
@@ -351,7 +355,7 @@ __device__ __forceinline__ void pack_one(const PackArgs& a, size_t o, double* r,
 }
 
 constexpr int PS_WARPS = 4;
-template <int DIM>
+template <int DIM, bool FROWS>
 __global__ void __launch_bounds__(32*PS_WARPS) k_pack_scatter(PackArgs a) {
   using D = Dm<DIM>;
   constexpr int ROW = D::ROW, RS = ROW + 2;                      // +2 doubles: conflict-free 128-bit reads of a row's chunks
@@ -365,13 +369,15 @@ __global__ void __launch_bounds__(32*PS_WARPS) k_pack_scatter(PackArgs a) {
   uint32_t s = 0;
   if (in) {
     double r[ROW], aux[4]; float f[Fr::ROW]; bool aniso;
-    pack_one<DIM>(a, o, r, f, aux, aniso);
+    pack_one<DIM, FROWS>(a, o, r, f, aux, aniso);
     s = a.invPerm[o];
     if (aniso) *a.aniso = 1ull;
 #pragma unroll
     for (int k = 0; k < ROW; ++k) srow[w][lane*RS + k] = r[k];
+    if constexpr (FROWS) {
 #pragma unroll
-    for (int k = 0; k < Fr::ROW; ++k) sfr[w][lane*(Fr::ROW + 4) + k] = f[k];
+      for (int k = 0; k < Fr::ROW; ++k) sfr[w][lane*(Fr::ROW + 4) + k] = f[k];
+    }
     a.aux2[2*(size_t)s] = aux[0]; a.aux2[2*(size_t)s + 1] = aux[1];
     if (a.auxPneg) { a.auxPneg[s] = aux[2]; a.auxSomr2[s] = aux[3]; }
     if (a.auxDvDxQ) {
@@ -393,7 +399,7 @@ __global__ void __launch_bounds__(32*PS_WARPS) k_pack_scatter(PackArgs a) {
       *reinterpret_cast<double2*>(a.rows + (size_t)sr*ROW + 2*ch) = v;
     }
   }
-  if (a.frows) {
+  if (FROWS && a.frows) {
     for (int t = lane; t < 32*4; t += 32) {
       const int rr = t >> 2, ch = t & 3;
       const uint32_t sr = __shfl_sync(0xffffffffu, s, rr);
@@ -1274,7 +1280,7 @@ static bool sphb200_nbr_v2_wanted() {          // read at every build: the tests
   return !(e && e[0] == '0');
 }
 
-static int pack_rows_impl(sphb200_ctx* c, bool range, size_t first, size_t count) {
+static int pack_rows_impl(sphb200_ctx* c, bool range, size_t first, size_t count, bool withFrows = true) {
   if (!c->sortValid) return sphb200_fail(c, "internal: pack_rows before sort");
   c->rowsAtEval = false;                       // the rows are about to change: compressed pair forces can no longer be expanded
   const bool tens = c->opt.epsTensile != 0.0;
@@ -1314,7 +1320,7 @@ static int pack_rows_impl(sphb200_ctx* c, bool range, size_t first, size_t count
   a.kext = std::max(c->W.kext, c->WQ.set ? c->WQ.kext : 0.0);
   // FP32 error of a reconstructed relative position, in units of 7 * 2^-24 cell widths: k*cs + rel_i - rel_j with |k| <= rad in
   // k_nbr_build; k_nbr_build2 places both nodes in the frame of the tile (|k_i| <= 1, |k_j| <= 2): 12 * 2^-24, budgeted as 14
-  c->nbrV2 = sphb200_nbr_v2_wanted() && c->stencilR == 1 && !c->fineWalk;
+  if (withFrows) c->nbrV2 = sphb200_nbr_v2_wanted() && c->stencilR == 1 && !c->fineWalk;      // a values-only re-pack leaves the FP32 rows, hence their error model, alone
   a.csmax = std::max(c->grid.cs[0], std::max(c->grid.cs[1], c->ndim == 3 ? c->grid.cs[2] : 0.0))*(c->nbrV2 ? 2.0 : (3.0*c->stencilR + 4.0)/7.0);
   static const bool gatherPack = [] { const char* e = std::getenv("SPHB200_PACK_GATHER"); return e && e[0] == '1'; }();     // A/B switch: the round-1 kernel
   if (gatherPack) {
@@ -1325,14 +1331,21 @@ static int pack_rows_impl(sphb200_ctx* c, bool range, size_t first, size_t count
     if (sphb200_inverse_perm(c)) return 1;
     a.invPerm = c->invPerm;
     const unsigned nb = (unsigned)((c->n + 32*PS_WARPS - 1)/(32*PS_WARPS));
-    if (c->ndim == 3) k_pack_scatter<3><<<nb, 32*PS_WARPS, 0, c->stream>>>(a); else k_pack_scatter<2><<<nb, 32*PS_WARPS, 0, c->stream>>>(a);
+    if (withFrows) { if (c->ndim == 3) k_pack_scatter<3, true><<<nb, 32*PS_WARPS, 0, c->stream>>>(a); else k_pack_scatter<2, true><<<nb, 32*PS_WARPS, 0, c->stream>>>(a); }
+    else           { if (c->ndim == 3) k_pack_scatter<3, false><<<nb, 32*PS_WARPS, 0, c->stream>>>(a); else k_pack_scatter<2, false><<<nb, 32*PS_WARPS, 0, c->stream>>>(a); }
     KERNEL_CHECK(c, "k_pack_scatter");
   }
   c->rowsValid = true;
   return 0;
 }
 
-int sphb200_pack_rows(sphb200_ctx* c) { return pack_rows_impl(c, false, 0, 0); }
+// Every caller but the sort re-packs on a valid connectivity (it checked pairsValid): the FP32 rows of the neighbour build are left alone.
+// SPHB200_PACK_VALUES_ONLY=0 packs them all the same (A/B).
+int sphb200_pack_rows(sphb200_ctx* c) {
+  static const bool valuesOnly = [] { const char* e = std::getenv("SPHB200_PACK_VALUES_ONLY"); return !(e && e[0] == '0'); }();
+  return pack_rows_impl(c, false, 0, 0, !(valuesOnly && c->pairsValid));
+}
+int sphb200_pack_rows_all(sphb200_ctx* c) { return pack_rows_impl(c, false, 0, 0, true); }
 // Re-pack the rows of the nodes [first, first + count) of the host order after their non-geometric fields changed (late halo fields)
 int sphb200_pack_rows_range(sphb200_ctx* c, size_t first, size_t count) { return pack_rows_impl(c, true, first, count); }
 
@@ -1411,7 +1424,7 @@ int sphb200_sort_and_pack(sphb200_ctx* c) {
       return sphb200_sort_and_pack(c);
     }
   }
-  return sphb200_pack_rows(c);
+  return sphb200_pack_rows_all(c);
 }
 
 int sphb200_neighbors(sphb200_ctx* c) {
