@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPHB200_ABI_VERSION 4
+#define SPHB200_ABI_VERSION 5
 
 typedef struct sphb200_ctx sphb200_ctx;
 
@@ -35,7 +35,9 @@ typedef struct sphb200_ctx sphb200_ctx;
 enum { SPHB200_Q_MG = 0, SPHB200_Q_LIMITED_MG = 1 };
 /* smoothing-scale sub-package run after the hydro (SPH/SPHHydros.py:129-140):
    SPHSmoothingScale.cc:101-275 | ASPHSmoothingScale.cc:110-147 | none */
-enum { SPHB200_H_SPH = 0, SPHB200_H_ASPH = 1, SPHB200_H_NONE = 2 };
+enum { SPHB200_H_SPH = 0, SPHB200_H_ASPH = 1, SPHB200_H_NONE = 2,
+       SPHB200_H_ASPH_CLASSIC = 3 /* ASPHClassicSmoothingScale (SmoothingScale/ASPHClassicSmoothingScale.cc; SPHHydros.py:133-134, ASPH = "Classic"):
+                                     the ASPH tensor derivative plus the second-moment ideal H; SPH hydro only */ };
 /* analytic kernels for sphb200_table_kernel_build (Kernel/<name>KernelInline.hh) */
 enum { SPHB200_KERNEL_BSPLINE = 0, SPHB200_KERNEL_WENDLANDC4 = 1, SPHB200_KERNEL_WENDLANDC2 = 2,
        SPHB200_KERNEL_NBSPLINE = 100 /* + order (1..11): NBSplineKernel(order), Kernel/NBSplineKernel.cc:17-122 -- the kernel of the stock
@@ -65,6 +67,7 @@ typedef struct {
   int    hEvolution;                /* SPHB200_H_* */
   double hmin, hmax;
   int    hydro;                     /* SPHB200_HYDRO_* (0 = SPH) */
+  double hminratio;                 /* NodeList::hminratio; read by SPHB200_H_ASPH_CLASSIC only (ASPHClassicSmoothingScale.cc:254, 302, 372) */
 } sphb200_options;
 
 /* State fields read by the path (SPH.cc:206-216; Appendix B of SURVEY.md). Bits for fieldMask. */

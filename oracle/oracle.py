@@ -15,7 +15,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "libsph_oracle.so")
 KERNEL_BSPLINE, KERNEL_WENDLANDC4, KERNEL_WENDLANDC2 = 0, 1, 2
 KERNEL_NBSPLINE = 100        # + order: NBSplineKernel(order)
 Q_MG, Q_LIMITED_MG = 0, 1
-H_SPH, H_ASPH, H_NONE = 0, 1, 2
+H_SPH, H_ASPH, H_NONE, H_ASPH_CLASSIC = 0, 1, 2, 3
 
 
 def build(force=False):
@@ -33,7 +33,7 @@ class Options(C.Structure):
                 ("negligibleSoundSpeed", C.c_double),
                 ("balsara", C.c_int), ("linearInExpansion", C.c_int), ("quadraticInExpansion", C.c_int),
                 ("etaCritFrac", C.c_double), ("etaFoldFrac", C.c_double),
-                ("hEvolution", C.c_int), ("hmin", C.c_double), ("hmax", C.c_double)]
+                ("hEvolution", C.c_int), ("hmin", C.c_double), ("hmax", C.c_double), ("hminratio", C.c_double)]
 
 
 _dp = C.POINTER(C.c_double)
@@ -248,7 +248,7 @@ def default_options(ndim, **kw):
     o.Qkind, o.Cl, o.Cq, o.eps2, o.negligibleSoundSpeed = Q_MG, 1.0, 1.0, 1.0e-2, 1.0e-10
     o.balsara = o.linearInExpansion = o.quadraticInExpansion = 0
     o.etaCritFrac, o.etaFoldFrac = 1.0, 0.2
-    o.hEvolution, o.hmin, o.hmax = H_SPH, 1.0e-20, 1.0e20
+    o.hEvolution, o.hmin, o.hmax, o.hminratio = H_SPH, 1.0e-20, 1.0e20, 0.1
     for k, v in kw.items():
         if not hasattr(o, k):
             raise KeyError(k)

@@ -42,7 +42,7 @@ enum { ORC_KERNEL_BSPLINE = 0, ORC_KERNEL_WENDLANDC4 = 1, ORC_KERNEL_WENDLANDC2 
 /* artificial viscosity ids */
 enum { ORC_Q_MG = 0, ORC_Q_LIMITED_MG = 1 };
 /* smoothing scale package */
-enum { ORC_H_SPH = 0, ORC_H_ASPH = 1, ORC_H_NONE = 2 };
+enum { ORC_H_SPH = 0, ORC_H_ASPH = 1, ORC_H_NONE = 2, ORC_H_ASPH_CLASSIC = 3 /* ASPHClassicSmoothingScale (SPHHydros.py:133-134, ASPH = "Classic") */ };
 
 typedef struct {
   int    ndim;                      /* 2 | 3 */
@@ -59,8 +59,9 @@ typedef struct {
   int    balsara, linearInExpansion, quadraticInExpansion;
   double etaCritFrac, etaFoldFrac;  /* LimitedMonaghanGingoldViscosity */
   /* smoothing scale */
-  int    hEvolution;                /* ORC_H_SPH | ORC_H_ASPH | ORC_H_NONE */
+  int    hEvolution;                /* ORC_H_SPH | ORC_H_ASPH | ORC_H_NONE | ORC_H_ASPH_CLASSIC */
   double hmin, hmax;
+  double hminratio;                 /* NodeList::hminratio: ASPHClassicSmoothingScale.cc:254, 296, 355 */
 } orc_options;
 
 /* TableKernel payload: three QuadraticInterpolators sharing xmin/xstep/n1

@@ -13,7 +13,7 @@ _dp = C.POINTER(C.c_double)
 _u32p = C.POINTER(C.c_uint32)
 
 Q_MG, Q_LIMITED_MG = 0, 1
-H_SPH, H_ASPH, H_NONE = 0, 1, 2
+H_SPH, H_ASPH, H_NONE, H_ASPH_CLASSIC = 0, 1, 2, 3
 KERNEL_BSPLINE, KERNEL_WENDLANDC4, KERNEL_WENDLANDC2 = 0, 1, 2
 KERNEL_NBSPLINE = 100        # + order: NBSplineKernel(order)
 TABLE_W, TABLE_WPI = 0, 1
@@ -58,7 +58,7 @@ class Options(C.Structure):
                 ("negligibleSoundSpeed", C.c_double),
                 ("balsara", C.c_int), ("linearInExpansion", C.c_int), ("quadraticInExpansion", C.c_int),
                 ("etaCritFrac", C.c_double), ("etaFoldFrac", C.c_double),
-                ("hEvolution", C.c_int), ("hmin", C.c_double), ("hmax", C.c_double), ("hydro", C.c_int)]
+                ("hEvolution", C.c_int), ("hmin", C.c_double), ("hmax", C.c_double), ("hydro", C.c_int), ("hminratio", C.c_double)]
 
 
 class HostState(C.Structure):

@@ -252,7 +252,11 @@ static int check_options(sphb200_ctx* c, const sphb200_options* o) {
     return sphb200_fail(c, "SPH error : you cannot simultaneously use both compatibleEnergyEvolution and evolveTotalEnergy");
   if (!(o->nPerh > 0.0)) return sphb200_fail(c, "nPerh must be positive");
   if (o->Qkind != SPHB200_Q_MG && o->Qkind != SPHB200_Q_LIMITED_MG) return sphb200_fail(c, "unknown Qkind");
-  if (o->hEvolution < SPHB200_H_SPH || o->hEvolution > SPHB200_H_NONE) return sphb200_fail(c, "unknown hEvolution");
+  if (o->hEvolution < SPHB200_H_SPH || o->hEvolution > SPHB200_H_ASPH_CLASSIC) return sphb200_fail(c, "unknown hEvolution");
+  if (o->hEvolution == SPHB200_H_ASPH_CLASSIC) {
+    if (o->hydro != SPHB200_HYDRO_SPH) return sphb200_fail(c, "the classic ASPH ideal H (SPHB200_H_ASPH_CLASSIC) is implemented for the SPH hydro only");
+    if (!(o->hminratio > 0.0) || !(o->hmin > 0.0) || !(o->hmax > 0.0)) return sphb200_fail(c, "SPHB200_H_ASPH_CLASSIC needs positive hmin, hmax and hminratio");
+  }
   if (o->hydro != SPHB200_HYDRO_SPH && o->hydro != SPHB200_HYDRO_CRKSPH) return sphb200_fail(c, "unknown hydro");
   return 0;
 }
@@ -551,6 +555,7 @@ int sphb200_evaluate_derivatives(sphb200_ctx* c, double /*time*/, double /*dt*/)
   const int rc = evaluate_prepare(c);
   if (rc) return rc == 2 ? 0 : 1;
   if ((c->opt.hydro == SPHB200_HYDRO_CRKSPH) ? sphb200_launch_crk_derivs(c) : sphb200_launch_derivs(c)) return 1;
+  if (c->opt.hEvolution == SPHB200_H_ASPH_CLASSIC && sphb200_launch_asph_classic(c)) return 1;
   return evaluate_finish(c);
 }
 
@@ -645,7 +650,8 @@ int sphb200_evaluate_derivatives_to_host(sphb200_ctx* c, double time, double dt,
   int Q = e2h_chunks_wanted(c->nInt);
   const char* force = getenv("SPHB200_E2H_FORCE");          // tests: chunk whatever the size / the coherence of the host order
   const bool forced = force && atoi(force) != 0;
-  if (c->opt.hydro == SPHB200_HYDRO_CRKSPH || (!forced && c->nInt < (size_t)262144) || c->nInt < (size_t)Q) Q = 1;
+  // (the classic ASPH ideal H is a second loop over all nodes after the pair loop: no chunk is complete before it has run)
+  if (c->opt.hydro == SPHB200_HYDRO_CRKSPH || c->opt.hEvolution == SPHB200_H_ASPH_CLASSIC || (!forced && c->nInt < (size_t)262144) || c->nInt < (size_t)Q) Q = 1;
   if (Q > 1) {
     const int rc = evaluate_prepare(c);
     if (rc == 1) return 1;

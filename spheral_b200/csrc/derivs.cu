@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(32*PAIR_WARPS, ISO ? SPHB200_PAIR_CTAS_ISO : P
 #pragma unroll
     for (int q = 0; q < DIM; ++q) put(DV_M1, q, 0.0);
     double dh[NS];
-    if (o.hEvolution == SPHB200_H_ASPH) asph_DHDt<DIM>(Hi, DvDxF, dh);
+    if (o.hEvolution == SPHB200_H_ASPH || o.hEvolution == SPHB200_H_ASPH_CLASSIC) asph_DHDt<DIM>(Hi, DvDxF, dh);   // the classic package's ideal H follows in k_asph_classic
     else {
 #pragma unroll
       for (int q = 0; q < NS; ++q) dh[q] = 0.0;
@@ -659,7 +659,7 @@ int launch_dim(sphb200_ctx* c, const DerivArgs& a, unsigned nb, int threads, siz
   const bool x = a.o.XSPH != 0, h = a.o.hEvolution == SPHB200_H_SPH, p = a.o.compatibleEnergy != 0;
   if (gen) return launch_one<DIM, true, true, true, true>(c, a, nb, threads, shm);
   const int code = (x ? 4 : 0) | (h ? 2 : 0) | (p ? 1 : 0);
-  if (c->allIsotropic && a.o.hEvolution != SPHB200_H_ASPH) {      // every H = h^-1 I (k_pack checked the rows this launch reads)
+  if (c->allIsotropic && !sphb200_is_asph(a.o.hEvolution)) {      // every H = h^-1 I (k_pack checked the rows this launch reads)
     switch (code) {
       case 0: return launch_one<DIM, false, false, false, false, true>(c, a, nb, threads, shm);
       case 1: return launch_one<DIM, false, false, false, true, true>(c, a, nb, threads, shm);
@@ -716,7 +716,7 @@ int sphb200_launch_derivs_chunk(sphb200_ctx* c, const uint32_t* tileList, uint32
   a.WnPerh = host_table_eval(c->W, 1.0/c->opt.nPerh, false);      // SPH.cc:264-266
   a.n = c->n; a.cap = c->cap; a.nInt = (uint32_t)c->nInt; a.o = c->opt;
   for (int s = 0; s < DV_COUNT; ++s) a.deriv[s] = c->deriv[s];
-  const bool isoPath0 = c->allIsotropic && c->opt.hEvolution != SPHB200_H_ASPH;
+  const bool isoPath0 = c->allIsotropic && !sphb200_is_asph(c->opt.hEvolution);
   const bool gen0 = (c->opt.Qkind != SPHB200_Q_MG) || c->opt.balsara || mult || tens || !c->oneKernel || c->opt.linearInExpansion || c->opt.quadraticInExpansion;
   c->paccMode = (isoPath0 && !gen0) ? (SPHB200_ISO_SCALAR ? PACC_ISO : PACC_FULL) : PACC_TENSOR;
   c->paccWidth = pacc_width(c->paccMode, c->ndim);
@@ -731,7 +731,7 @@ int sphb200_launch_derivs_chunk(sphb200_ctx* c, const uint32_t* tileList, uint32
   // persistent CTAs: 2 per SM (register-limited), each striding over the tiles
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
-  const bool isoPath = c->allIsotropic && c->opt.hEvolution != SPHB200_H_ASPH;
+  const bool isoPath = c->allIsotropic && !sphb200_is_asph(c->opt.hEvolution);
   const size_t tilesHere = tileList ? (size_t)nList : c->nTiles;
   if (tilesHere == 0) return 0;
   const unsigned nb = (unsigned)std::min<size_t>((tilesHere + wpb - 1)/wpb, (size_t)nsm*(isoPath ? SPHB200_PAIR_CTAS_ISO : PAIR_CTAS));

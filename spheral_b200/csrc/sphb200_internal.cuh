@@ -204,6 +204,7 @@ int sphb200_neighbors(sphb200_ctx* c);
 int sphb200_launch_derivs(sphb200_ctx* c);
 int sphb200_launch_derivs_chunk(sphb200_ctx* c, const uint32_t* tileList, uint32_t nList, uint32_t origLo, uint32_t origHi);
 int sphb200_launch_energy(sphb200_ctx* c, double multiplier);
+int sphb200_launch_asph_classic(sphb200_ctx* c);        // steps.cu: ASPHClassicSmoothingScale ideal H, after the pair loop
 int sphb200_launch_crk_derivs(sphb200_ctx* c);
 int sphb200_pairs_to_host(sphb200_ctx* c, uint32_t* pi, uint32_t* pj, size_t cap, double* pacc, size_t paccCap);
 
@@ -212,6 +213,7 @@ template <int DIM> struct Dm;
 template <> struct Dm<3> { static constexpr int NS = 6, NT = 9, ROW = 16, R_POS = 0, R_VEL = 3, R_H = 6, R_M = 12, R_RHO = 13, R_PRHO = 14, R_CS = 15; };
 template <> struct Dm<2> { static constexpr int NS = 3, NT = 4, ROW = 12, R_POS = 0, R_VEL = 2, R_H = 4, R_M = 7, R_RHO = 8, R_PRHO = 9, R_CS = 10; };
 
+__host__ __device__ __forceinline__ bool sphb200_is_asph(int hEvolution) { return hEvolution == SPHB200_H_ASPH || hEvolution == SPHB200_H_ASPH_CLASSIC; }
 enum { PACC_FULL = 0, PACC_ISO = 1, PACC_TENSOR = 2 };
 __host__ __device__ __forceinline__ int pacc_width(int mode, int ndim) { return mode == PACC_ISO ? 1 : (mode == PACC_TENSOR ? 2 : ndim); }
 __host__ __device__ __forceinline__ unsigned long long pacc_at(int width, unsigned long long slot, int word) {

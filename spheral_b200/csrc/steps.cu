@@ -58,6 +58,10 @@ struct LoopArgs {
   const double* tabW; double kext, xmin, xstep; uint32_t n1; double W0;
   size_t n; uint32_t nInt;
   double* out;                                       // api-order destination (rho / omega)
+  // classic ASPH ideal H: sorted component-major derivative arrays (component c of slot i at [c*cap + i]) and the nperh look-up
+  double *dM0, *dM1, *dHideal; size_t cap;
+  const double* nperhVals; uint32_t nperhN; double nperhXmin, nperhXmax, nperhXstep;
+  double nPerh, hminInv, hmaxInv, hminratio;
   // dt
   unsigned long long* best;                          // {dt bits, tag} pairs per CTA
 };
@@ -166,6 +170,131 @@ __global__ void __launch_bounds__(32*SW, 1) k_sph_omega(LoopArgs a) {
       }
       a.out[t.o] = om;
     }
+  }
+}
+
+// ---- ASPHClassicSmoothingScale::evaluateDerivatives (SmoothingScale/ASPHClassicSmoothingScale.cc:130-378), general case -------------------
+// The pair part needs the node's own H only (W_SPH,i = |gradW(|H_i x_ij|)|), so the neighbours' positions are all that is streamed:
+//   m0_i = sum W_SPH,i ; m1_i = -sum W_SPH,i eta_i ; psi_i = sum W_SPH,i^2 x_ij (x) x_ij / |x_ij|^5            (:206-214)
+// and the per-node part turns the second moment into the unit-determinant shape of the ideal H (eigenvalues 1/sqrt(lambda), bounded
+// below by hminratio times the largest, :289-312), scales it to the target neighbour count like the SPH ideal H (:339-367) and bounds
+// the eigenvalues (:371-375).  Every tensor function is of the form R f(lambda) R^T, so one eigen-decomposition of psi carries the
+// chain the reference evaluates with three (eigenVectors, sqrt, eigenVectors): the rotations coincide.  DHDt is the ASPH tensor
+// derivative k_sph_derivs has already stored.  Not exported: the second moment itself (the reference enrolls it as a derivative field
+// only for its own use and restart).
+template <int DIM>
+__global__ void __launch_bounds__(32*SW, 1) k_asph_classic(LoopArgs a) {
+  using D = Dm<DIM>;
+  constexpr int NS = D::NS;
+  extern __shared__ __align__(16) double smem[];
+  const unsigned tW = stage_table(smem, a.tabW, a.n1);
+  const double rx = 1.0/a.xstep;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const PosRing<DIM> ring = make_ring<PosRing<DIM>>(a, tW + 48u*(a.n1 + 2u), warp);
+  const size_t nTiles = (a.n + SPHB200_TILE - 1)/SPHB200_TILE;
+  const double tiny = 1.0e-50;
+  for (size_t tile = (size_t)blockIdx.x*SW + warp; tile < nTiles; tile += (size_t)gridDim.x*SW) {
+    const TileLane t = tile_lane(a, tile, lane);
+    double ri[DIM], Hi[NS];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) ri[k] = t.inRange ? a.rows[t.i*D::ROW + D::R_POS + k] : 0.0;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) Hi[k] = t.inRange ? a.rows[t.i*D::ROW + D::R_H + k] : 0.0;
+    double m0 = 0.0, m1[DIM], psi[NS];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) m1[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) psi[k] = 0.0;
+    ring_walk<PosRing<DIM>, SS>(ring, lane, t.rowsT, t.cnt,
+      [&](uint32_t p) -> uint32_t { return (p < t.cnt) ? a.nbr[t.base + (unsigned long long)p*SPHB200_TILE] : 0u; },
+      [&](uint32_t k, uint32_t) {
+        double rj[DIM == 3 ? 4 : 2];
+        ring.read_row(k, lane, rj);
+        double rij[DIM], eta[DIM];
+#pragma unroll
+        for (int q = 0; q < DIM; ++q) rij[q] = ri[q] - rj[q];
+        sym_dot<DIM>(Hi, rij, eta);
+        const double e2 = vdot<DIM>(eta, eta);
+        double gW;
+        table_eval_grad(tW, a.kext, a.xmin, a.xstep, rx, a.n1, e2*fast_rsqrt(e2 + 1.0e-300), gW);
+        const double W = fabs(gW);                             // kernelValueSPH (TableKernelViewInline.hh:118-127)
+        m0 += W;
+#pragma unroll
+        for (int q = 0; q < DIM; ++q) m1[q] = fma(-W, eta[q], m1[q]);
+        const double r2 = vdot<DIM>(rij, rij);
+        // safeInvVar(|x_ij|^5): coincident nodes give 1e30 times an exactly zero dyad
+        const double rinv = (r2 > 0.0) ? fast_rsqrt(r2) : 0.0;
+        const double w5 = (W*W)*((rinv*rinv)*(rinv*rinv)*rinv);
+        int c = 0;
+#pragma unroll
+        for (int r = 0; r < DIM; ++r)
+#pragma unroll
+          for (int q = r; q < DIM; ++q) { psi[c] = fma(w5, rij[r]*rij[q], psi[c]); ++c; }
+      });
+    if (!t.active) continue;
+    const size_t cap = a.cap, i = t.i;
+    const double z0 = rootnu<DIM>(fmax(0.0, m0));                                             // :269
+    a.dM0[i] = z0;
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) a.dM1[(size_t)q*cap + i] = m1[q];
+    const bool isolated = fabs(z0) <= 1.0e-15*fmax(1.0, fabs(z0));                             // fuzzyEqual(z0, 0)
+    const double cur = isolated ? 0.5*a.nPerh : fmax(0.0, hermite_eval(a.nperhVals, a.nperhN, a.nperhXmin, a.nperhXmax, a.nperhXstep, z0));
+    const double sv = fmin(4.0, fmax(0.25, a.nPerh/cur));                                      // :279
+    const double psiweight = fmax(0.0, fmin(1.0, 2.0/sv - 1.0));                               // :285
+    double lam[DIM], V[DIM*DIM];
+    bool shaped = false;
+    if (psiweight > 0.0 && sym_det<DIM>(psi) > 0.0) {
+      double mx = 0.0;
+#pragma unroll
+      for (int k = 0; k < NS; ++k) mx = fmax(mx, fabs(psi[k]));
+      const double mi = 1.0/mx;
+#pragma unroll
+      for (int k = 0; k < NS; ++k) psi[k] *= mi;                                                // :291 (a positive scale: same eigenvectors, same sign tests)
+      sym_eigen<DIM>(psi, lam, V);
+      double lmin = lam[0];
+#pragma unroll
+      for (int k = 1; k < DIM; ++k) lmin = fmin(lmin, lam[k]);
+      shaped = lmin > 0.0;                                                                      // :289
+    }
+    if (shaped) {
+      const double dpsi = sym_det<DIM>(psi);
+      if (dpsi > 1.0e-10) {                                                                     // :292-293
+        const double f = 1.0/rootnu<DIM>(fabs(dpsi) + tiny);
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) lam[k] *= f;
+      } else {                                                                                  // :295 psi = one
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) lam[k] = 1.0;
+      }
+      double vmax = 0.0, prod = 1.0;
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) { lam[k] = 1.0/sqrt(lam[k]); vmax = fmax(vmax, lam[k]); }  // :301
+      const double psimin = vmax*a.hminratio;
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) { lam[k] = fmax(psimin, lam[k]); prod *= lam[k]; }          // :303 constructSymTensorWithMaxDiagonal
+      const double g = 1.0/rootnu<DIM>(prod + tiny);                                            // :307
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) lam[k] = 1.0/sqrt(fmax(0.0, lam[k]*g));                     // :312 psi.sqrt().Inverse()
+    } else {
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) lam[k] = 1.0;                                               // :334 SymTensor::one()
+#pragma unroll
+      for (int k = 0; k < DIM*DIM; ++k) V[k] = 0.0;
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) V[k*DIM + k] = 1.0;
+    }
+    const double aa = (sv < 1.0 ? 0.4*(1.0 + sv*sv) : 0.4*(1.0 + 1.0/(sv*sv*sv + tiny)));       // :339-344
+    const double f = rootnu<DIM>(sym_det<DIM>(Hi))/(1.0 - aa + aa*sv);                          // :367 general case
+    double lmin = 1.0e300;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) { lam[k] *= f; lmin = fmin(lmin, lam[k]); }
+    const double hminEffInv = fmin(a.hminInv, fmax(a.hmaxInv, lmin)/a.hminratio);               // :372
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) lam[k] = fmax(a.hmaxInv, fmin(hminEffInv, lam[k]));           // :373 constructSymTensorWithBoundedDiagonal
+    double Hid[NS];
+    sym_rebuild<DIM>(lam, V, Hid);
+#pragma unroll
+    for (int k = 0; k < NS; ++k) a.dHideal[(size_t)k*cap + i] = Hid[k];
   }
 }
 
@@ -430,6 +559,22 @@ int loop_ready(sphb200_ctx* c, const char* who) {
 
 }  // namespace
 
+extern "C" {
+
+}  // extern "C"
+// Called by sphb200_evaluate_derivatives after the pair loop when opt.hEvolution == SPHB200_H_ASPH_CLASSIC
+int sphb200_launch_asph_classic(sphb200_ctx* c) {
+  if (c->n == 0) return 0;
+  if (!c->W.nperhVals || c->W.nperhN < 2)
+    return sphb200_fail(c, "evaluateDerivatives: ASPHClassicSmoothingScale needs the TableKernel nperh lookup (nperhVals) but none was set");
+  LoopArgs a; fill_loop_args(c, a);
+  a.dM0 = c->deriv[DV_M0]; a.dM1 = c->deriv[DV_M1]; a.dHideal = c->deriv[DV_HIDEAL]; a.cap = c->cap;
+  a.nperhVals = c->W.nperhVals; a.nperhN = c->W.nperhN; a.nperhXmin = c->W.nperhXmin; a.nperhXmax = c->W.nperhXmax; a.nperhXstep = c->W.nperhXstep;
+  a.nPerh = c->opt.nPerh; a.hminInv = 1.0/c->opt.hmin; a.hmaxInv = 1.0/c->opt.hmax; a.hminratio = c->opt.hminratio;
+  if (c->ndim == 3) { if (launch_loop(c, k_asph_classic<3>, a, "k_asph_classic", PosRing<3>::WARPB, true)) return 1; }
+  else              { if (launch_loop(c, k_asph_classic<2>, a, "k_asph_classic", PosRing<2>::WARPB, true)) return 1; }
+  return 0;
+}
 extern "C" {
 
 int sphb200_sum_mass_density(sphb200_ctx* c) {

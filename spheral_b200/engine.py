@@ -24,6 +24,7 @@ def make_options(ndim, **kw):
     o.etaCritFrac, o.etaFoldFrac = 1.0, 0.2
     o.hEvolution, o.hmin, o.hmax = L.H_SPH, 1.0e-20, 1.0e20
     o.hydro = L.HYDRO_SPH
+    o.hminratio = 0.1                        # NodeList default
     for k, v in kw.items():
         if not hasattr(o, k):
             raise KeyError(k)

@@ -259,6 +259,12 @@ class ASPHSmoothingScale(SPHSmoothingScale):
     hEvolution = L.H_ASPH
 
 
+class ASPHClassicSmoothingScale(SPHSmoothingScale):
+    """ASPHClassicSmoothingScale(HUpdate, W) -- SmoothingScale/ASPHClassicSmoothingScale.cc: the ASPH tensor derivative plus the
+    second-moment ideal H (the factories select it with ASPH = "Classic", SPHHydros.py:133-134)"""
+    hEvolution = L.H_ASPH_CLASSIC
+
+
 IdealH, IntegrateH, FixedH = "IdealH", "IntegrateH", "FixedH"
 RigorousSumDensity, IntegrateDensity = "RigorousSumDensity", "IntegrateDensity"
 
@@ -365,7 +371,7 @@ class SPHB200(Physics):
                             balsara=int(Q.balsaraShearCorrection), linearInExpansion=int(Q.linearInExpansion),
                             quadraticInExpansion=int(Q.quadraticInExpansion), etaCritFrac=Q.etaCritFrac,
                             etaFoldFrac=Q.etaFoldFrac, hEvolution=(sm.hEvolution if sm is not None else L.H_NONE),
-                            hmin=nl.hmin, hmax=nl.hmax, hydro=self._hydro)
+                            hmin=nl.hmin, hmax=nl.hmax, hydro=self._hydro, hminratio=getattr(nl, "hminratio", 0.1))
 
     def _push_options(self):
         if self._engine is not None:
@@ -639,7 +645,10 @@ def SPH(W, WPi=None, WGrad=None, dataBase=None, Q=None, filter=None, cfl=0.25, u
                      epsTensile=epsTensile, nTensile=nTensile, xmin=xmin, xmax=xmax, device=device)
     result.prependSubPackage(Q)                                   # SPHHydros.py:125-127
     if smoothingScaleMethod is None:                              # SPHHydros.py:129-140
-        smoothingScaleMethod = ASPHSmoothingScale(HUpdate, W) if ASPH else SPHSmoothingScale(HUpdate, W)
+        if isinstance(ASPH, str) and ASPH.upper() == "CLASSIC":
+            smoothingScaleMethod = ASPHClassicSmoothingScale(HUpdate, W)
+        else:
+            smoothingScaleMethod = ASPHSmoothingScale(HUpdate, W) if ASPH else SPHSmoothingScale(HUpdate, W)
     result._smoothingScaleMethod = smoothingScaleMethod
     result.appendSubPackage(smoothingScaleMethod)
     return result

@@ -85,6 +85,29 @@ def test_asph_random_rotated_anisotropic_H(oracle, eng_mod, ndim, n):
     assert_parity(r, st, nInt, ndim)
 
 
+@pytest.mark.parametrize("ndim,n,kind", [(3, 11, "aniso"), (2, 36, "aniso"), (3, 12, "lattice"), (2, 40, "lattice")])
+def test_asph_classic_ideal_H(oracle, eng_mod, ndim, n, kind):
+    """ASPHClassicSmoothingScale (hEvolution = 3): zeroth / first moments, the ASPH tensor derivative and the second-moment ideal H of
+    k_asph_classic against the oracle restatement of SmoothingScale/ASPHClassicSmoothingScale.cc, on random rotated anisotropic H and
+    on a jittered lattice; every other derivative field is the ASPH run's."""
+    nPerh = 2.01 if ndim == 2 else (1.3 if kind == "aniso" else 1.51)
+    st, nInt, nGhost = common.make_problem(ndim, n, nPerh=nPerh, kind=kind, seed=23)
+    WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    hb = 1.0/st["H"][:nInt, 0].mean()
+    r = run_both(oracle, eng_mod, ndim, st, nInt, nGhost, WT, nPerh=2.01 if kind == "aniso" else nPerh, hEvolution=3,
+                 hmin=0.02*hb, hmax=50.0*hb, hminratio=0.1)
+    worst = assert_parity(r, st, nInt, ndim)
+    Hid = r["got"]["Hideal"][:nInt]
+    assert np.all(np.isfinite(Hid)) and np.abs(Hid).max() > 0.0
+    if kind == "aniso":                                   # the ideal H is a genuine tensor here
+        off = np.abs(Hid[:, 1]).max()
+        assert off > 1.0e-3*np.abs(Hid[:, 0]).max()
+    # the same state evaluated as plain ASPH: identical hydro derivatives (the classic package only adds its own fields)
+    r1 = run_both(oracle, eng_mod, ndim, st, nInt, nGhost, WT, nPerh=2.01 if kind == "aniso" else nPerh, hEvolution=1)
+    for k in ("DvDt", "DepsDt", "DrhoDt", "DvDx", "DHDt"):
+        assert np.array_equal(r["got"][k], r1["got"][k]), k
+
+
 @pytest.mark.parametrize("flags", [
     dict(XSPH=0), dict(compatibleEnergy=0), dict(compatibleEnergy=0, evolveTotalEnergy=1),
     dict(correctVelocityGradient=0), dict(hEvolution=2), dict(linearInExpansion=1, quadraticInExpansion=1),

@@ -134,7 +134,10 @@ def test_compute_dt(oracle, mods, ndim, n, nPerh, kind, okw):
 @pytest.mark.parametrize("ndim,n,nPerh,okw,rho_update", [(3, 12, 1.51, dict(Cl=1.0, Cq=1.0), 1), (2, 32, 2.01, dict(Cl=1.0, Cq=1.0), 0),
                                                           (3, 10, 1.51, dict(Qkind=1, Cl=1.0, Cq=1.0), 1),
                                                           (3, 10, 1.51, dict(hEvolution=1, Cl=1.0, Cq=1.0, hmin=1e-3, hmax=1e3), 1),
-                                                          (2, 28, 2.01, dict(hEvolution=1, Cl=1.0, Cq=1.0, hmin=1e-3, hmax=1e3), 0)])
+                                                          (2, 28, 2.01, dict(hEvolution=1, Cl=1.0, Cq=1.0, hmin=1e-3, hmax=1e3), 0),
+                                                          # ASPHClassicSmoothingScale with IdealH: H is replaced by the second-moment ideal H
+                                                          (3, 10, 1.51, dict(hEvolution=3, Cl=1.0, Cq=1.0, hmin=1e-3, hmax=1e3), 1),
+                                                          (2, 28, 2.01, dict(hEvolution=3, Cl=1.0, Cq=1.0, hmin=1e-3, hmax=1e3), 0)])
 def test_rk2_steps_device_resident(oracle, mods, ndim, n, nPerh, okw, rho_update):
     """Whole CheapSynchronousRK2 steps: device-resident integrator vs the oracle-driven one."""
     engine, integrator = mods

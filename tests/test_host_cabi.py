@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol(sphlib):
     for name in declared:
         assert hasattr(sphlib, name), "missing export " + name
     assert declared == set(_lib.EXPORTS)
-    assert sphlib.sphb200_abi_version() == 4
+    assert sphlib.sphb200_abi_version() == 5
 
 
 def test_struct_layouts_match_header(sphlib):
