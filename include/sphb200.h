@@ -241,7 +241,7 @@ int  sphb200_state_update(sphb200_ctx* ctx, const sphb200_step_options* so, doub
    not converged yet takes the "new H" of the last sphb200_evaluate_derivatives call; maxDeltaH = max over those nodes of
    max|phi - 1|, phi the eigenvalues of H1^(1/2) H^-1 H1^(1/2); nodes with deltaH <= tolerance are frozen.  The caller loops
    build_pairs -> evaluate_derivatives -> iterate_ideal_h until maxDeltaH <= tolerance (firstSweep != 0 clears the frozen set).
-   SPH smoothing scale only (isotropic ideal H). */
+   SPH smoothing scale (isotropic ideal H: phi = h1/lambda(H)) and the classic ASPH one (tensor ideal H: the general formula). */
 int  sphb200_iterate_ideal_h(sphb200_ctx* ctx, int firstSweep, double tolerance, double* maxDeltaH);
 int  sphb200_compute_dt(sphb200_ctx* ctx, double cfl, int useVelocityMagnitudeForDt, double* dt, int* reason, uint32_t* node);
 

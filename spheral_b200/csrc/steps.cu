@@ -396,9 +396,54 @@ __global__ void __launch_bounds__(RB) k_iterate_h(const uint32_t* __restrict__ p
 #pragma unroll
       for (int q = 0; q < NS; ++q) { Hi[q] = H[o*NS + q]; H1[q] = Hideal[(size_t)q*cap + s]; }
       double lo, hi;
-      sym_eigenvalue_range<DIM>(Hi, lo, hi);
-      const double h1 = H1[0];
-      delta = fmax(fabs(h1/hi - 1.0), fabs(h1/lo - 1.0));
+      const bool iso1 = (DIM == 3) ? (H1[1] == 0.0 && H1[2] == 0.0 && H1[4] == 0.0 && H1[3] == H1[0] && H1[5] == H1[0]) : (H1[1] == 0.0 && H1[2] == H1[0]);
+      if (iso1) {
+        sym_eigenvalue_range<DIM>(Hi, lo, hi);
+        const double h1 = H1[0];
+        delta = fmax(fabs(h1/hi - 1.0), fabs(h1/lo - 1.0));
+      } else {
+        // a tensor ideal H (the classic ASPH package): phi = eigenvalues of (H1^(1/2) H^-1 H1^(1/2)).Symmetric(), iterateIdealH.cc:188-192
+        double lam[DIM], V[DIM*DIM], S[NS], Sf[DIM][DIM], Hf[DIM][DIM], Hv[DIM][DIM], T[DIM][DIM], P[DIM][DIM], Ps[NS];
+        sym_eigen<DIM>(H1, lam, V);
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) lam[k] = sqrt(fmax(0.0, lam[k]));
+        sym_rebuild<DIM>(lam, V, S);
+        if (DIM == 3) {
+          Sf[0][0] = S[0]; Sf[0][1] = Sf[1][0] = S[1]; Sf[0][DIM - 1] = Sf[DIM - 1][0] = S[2]; Sf[1][1] = S[3]; Sf[1][DIM - 1] = Sf[DIM - 1][1] = S[4]; Sf[DIM - 1][DIM - 1] = S[5];
+          Hf[0][0] = Hi[0]; Hf[0][1] = Hf[1][0] = Hi[1]; Hf[0][DIM - 1] = Hf[DIM - 1][0] = Hi[2]; Hf[1][1] = Hi[3]; Hf[1][DIM - 1] = Hf[DIM - 1][1] = Hi[4]; Hf[DIM - 1][DIM - 1] = Hi[5];
+        } else {
+          Sf[0][0] = S[0]; Sf[0][1] = Sf[1][0] = S[1]; Sf[1][1] = S[2];
+          Hf[0][0] = Hi[0]; Hf[0][1] = Hf[1][0] = Hi[1]; Hf[1][1] = Hi[2];
+        }
+        { double Tin[DIM*DIM], Tout[DIM*DIM];
+#pragma unroll
+          for (int r = 0; r < DIM; ++r)
+#pragma unroll
+            for (int q = 0; q < DIM; ++q) Tin[r*DIM + q] = Hf[r][q];
+          ten_inverse<DIM>(Tin, Tout);
+#pragma unroll
+          for (int r = 0; r < DIM; ++r)
+#pragma unroll
+            for (int q = 0; q < DIM; ++q) Hv[r][q] = Tout[r*DIM + q]; }
+#pragma unroll
+        for (int r = 0; r < DIM; ++r)
+#pragma unroll
+          for (int q = 0; q < DIM; ++q) { double t = 0.0;
+#pragma unroll
+            for (int m = 0; m < DIM; ++m) t += Sf[r][m]*Hv[m][q];
+            T[r][q] = t; }
+#pragma unroll
+        for (int r = 0; r < DIM; ++r)
+#pragma unroll
+          for (int q = 0; q < DIM; ++q) { double t = 0.0;
+#pragma unroll
+            for (int m = 0; m < DIM; ++m) t += T[r][m]*Sf[m][q];
+            P[r][q] = t; }
+        if (DIM == 3) { Ps[0] = P[0][0]; Ps[1] = 0.5*(P[0][1] + P[1][0]); Ps[2] = 0.5*(P[0][DIM - 1] + P[DIM - 1][0]); Ps[3] = P[1][1]; Ps[4] = 0.5*(P[1][DIM - 1] + P[DIM - 1][1]); Ps[5] = P[DIM - 1][DIM - 1]; }
+        else { Ps[0] = P[0][0]; Ps[1] = 0.5*(P[0][1] + P[1][0]); Ps[2] = P[1][1]; }
+        sym_eigenvalue_range<DIM>(Ps, lo, hi);
+        delta = fmax(fabs(lo - 1.0), fabs(hi - 1.0));
+      }
       if (delta <= tolerance) done[o] = 1u;
 #pragma unroll
       for (int q = 0; q < NS; ++q) H[o*NS + q] = H1[q];
@@ -691,7 +736,8 @@ int sphb200_state_assign(sphb200_ctx* c) {
 int sphb200_iterate_ideal_h(sphb200_ctx* c, int firstSweep, double tolerance, double* maxDeltaH) {
   if (!c) return sphb200_fail(nullptr, "null ctx");
   CU_CHECK(c, cudaSetDevice(c->device)); if (sphb200_join_uploads(c, true)) return 1;
-  if (c->opt.hEvolution != SPHB200_H_SPH) return sphb200_fail(c, "iterate_ideal_h: only the SPH smoothing scale computes an ideal H on the device (the ASPH ideal H needs the Voronoi second moment, out of scope)");
+  if (c->opt.hEvolution != SPHB200_H_SPH && c->opt.hEvolution != SPHB200_H_ASPH_CLASSIC)
+    return sphb200_fail(c, "iterate_ideal_h: the SPH and the classic ASPH smoothing scale compute an ideal H on the device (the Voronoi-cell ideal H of ASPHSmoothingScale is out of scope)");
   if (!c->derivsValid || !c->pairsValid) return sphb200_fail(c, "iterate_ideal_h: needs the derivatives ('new H') of the current connectivity");
   if (maxDeltaH) *maxDeltaH = 0.0;
   if (c->nInt == 0) return 0;

@@ -261,7 +261,7 @@ def iterateIdealH(engine, maxIterations=100, tolerance=1.0e-10, setGhostNodes=No
     """Utilities/iterateIdealH.cc: the start-up relaxation of the smoothing scales, with the state on the device.  Every
     iteration regenerates the ghost nodes (setGhostNodes: e.g. engine.reflect_set_ghost_nodes), rebuilds the connectivity,
     evaluates the smoothing-scale derivatives and replaces H by the ideal H on the nodes that have not converged.
-    Returns (iterations, maxDeltaH).  SPH smoothing scale only."""
+    Returns (iterations, maxDeltaH).  SPH and classic ASPH (hEvolution = H_ASPH_CLASSIC) smoothing scales."""
     it, maxDeltaH = 0, 2.0*tolerance
     while it < maxIterations and maxDeltaH > tolerance:
         it += 1

@@ -272,8 +272,8 @@ def test_restart_is_bit_exact(oracle, mods, ndim, n, nPerh, Qkind, planes):
         assert np.array_equal(a[k][:nInt], b[k][:nInt]), k
 
 
-@pytest.mark.parametrize("ndim,n,nPerh", [(3, 11, 1.51), (2, 30, 2.01)])
-def test_iterate_ideal_h(oracle, mods, ndim, n, nPerh):
+@pytest.mark.parametrize("ndim,n,nPerh,hev", [(3, 11, 1.51, 0), (2, 30, 2.01, 0), (3, 10, 1.51, 3), (2, 28, 2.01, 3)])
+def test_iterate_ideal_h(oracle, mods, ndim, n, nPerh, hev):
     """iterateIdealH (Utilities/iterateIdealH.cc) on the device against the same loop driven through the oracle: same number of
     sweeps, same maxDeltaH history, H within 1e-10; and the fixed point property H == 'new H' at the end."""
     engine, integrator = mods
@@ -282,18 +282,27 @@ def test_iterate_ideal_h(oracle, mods, ndim, n, nPerh):
     st["H"] = st["H"]*(1.0 + 0.3*rng.uniform(-1.0, 1.0, size=(nInt, 1)))
     WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
     OT = common.oracle_table(oracle, WT)
-    oo, po = common.opts_pair(oracle, engine, ndim, nPerh=nPerh)
+    hb = 1.0/st["H"][:, 0].mean()
+    oo, po = common.opts_pair(oracle, engine, ndim, nPerh=nPerh, hEvolution=hev, hmin=0.01*hb, hmax=100.0*hb)
     tol, maxIt = 1.0e-4, 50
-    # oracle-driven loop (iterateIdealH.cc:120-190 for an isotropic ideal H: phi = h1/lambda(H))
+    # oracle-driven loop (iterateIdealH.cc:120-190): phi = eigenvalues of H1^(1/2) H^-1 H1^(1/2); hev = 3: the classic ASPH tensor ideal H
     s = common.to_oracle_state(st)
     done = np.zeros(nInt, dtype=bool)
     hist = []
     for it in range(maxIt):
         pi, pj, cnt = oracle.pairs(ndim, nInt, 0, s["pos"], s["H"], OT.kext)
         d = oracle.evaluate_derivatives(oo, OT, s, nInt, 0, pi, pj, cnt)
-        lam = np.linalg.eigvalsh(common.ng.sym_to_full(ndim, s["H"]))
-        h1 = d["Hideal"][:, 0]
-        delta = np.maximum(np.abs(h1/lam[:, -1] - 1.0), np.abs(h1/lam[:, 0] - 1.0))
+        if hev == 0:
+            lam = np.linalg.eigvalsh(common.ng.sym_to_full(ndim, s["H"]))
+            h1 = d["Hideal"][:, 0]
+            delta = np.maximum(np.abs(h1/lam[:, -1] - 1.0), np.abs(h1/lam[:, 0] - 1.0))
+        else:
+            H1f, Hf = common.ng.sym_to_full(ndim, np.asarray(d["Hideal"])[:nInt]), common.ng.sym_to_full(ndim, s["H"])
+            w, V = np.linalg.eigh(H1f)
+            S = np.einsum("kab,kb,kcb->kac", V, np.sqrt(w), V)
+            P = S @ np.linalg.inv(Hf) @ S
+            phi = np.linalg.eigvalsh(0.5*(P + np.swapaxes(P, 1, 2)))
+            delta = np.maximum(np.abs(phi[:, 0] - 1.0), np.abs(phi[:, -1] - 1.0))
         act = ~done
         hist.append(float(delta[act].max()) if act.any() else 0.0)
         done |= act & (delta <= tol)
@@ -306,14 +315,26 @@ def test_iterate_ideal_h(oracle, mods, ndim, n, nPerh):
     e.set_nodes(nInt, 0)
     e.upload_state(**st)
     its, dmax = integrator.iterateIdealH(e, maxIterations=maxIt, tolerance=tol)
-    assert its == len(hist) and abs(dmax - hist[-1]) <= 1e-6*max(hist[-1], 1e-300) + 1e-12, (its, len(hist), dmax, hist[-1])
+    # tensor ideal H: the device restates the reference's closed-form 3x3 eigenvalues (GeomSymmetricTensorInline.hh:2210-2256), which resolve
+    # phi - 1 of a nearly isotropic H1^(1/2) H^-1 H1^(1/2) to ~1e-8 only; numpy's eigvalsh above is exact (measured difference 5e-8)
+    slack = 2.0e-7 if hev == 3 else 1.0e-12
+    assert its == len(hist) and abs(dmax - hist[-1]) <= 1e-6*max(hist[-1], 1e-300) + slack, (its, len(hist), dmax, hist[-1])
     assert hist[-1] <= tol < hist[0]
     got = e.download_state("H")["H"]
-    assert np.abs(got - s["H"]).max() <= 1e-10*np.abs(s["H"]).max()
+    if hev == 0:
+        assert np.abs(got - s["H"]).max() <= 1e-10*np.abs(s["H"]).max()
+    else:
+        # A node is frozen in the sweep its deltaH drops below the tolerance.  With deltaH resolved to ~1e-8 (see above) a node whose
+        # deltaH passes within that distance of the tolerance may be frozen one sweep earlier or later than here -- in the reference
+        # as much as on the device; such a node then differs by about the tolerance, every other node agrees to round-off.
+        err = np.abs(got - s["H"]).max(axis=1)/np.abs(s["H"]).max()
+        assert np.mean(err <= 1e-9) >= 0.99 and err.max() <= 5.0*tol, (float(np.mean(err <= 1e-9)), float(err.max()))
     # fixed point: one more evaluation reproduces H to the tolerance
     e.build_pairs(); e.evaluate_derivatives()
     hid = e.download_derivs("Hideal")["Hideal"]
     assert np.abs(hid[:, 0]/got[:, 0] - 1.0).max() <= 10*tol
+    if hev == 3:
+        assert np.abs(got[:, 1]).max() > 0.0            # the relaxed H is a genuine tensor
 
 
 @pytest.mark.gpu
