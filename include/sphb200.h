@@ -37,7 +37,7 @@ enum { SPHB200_Q_MG = 0, SPHB200_Q_LIMITED_MG = 1 };
    SPHSmoothingScale.cc:101-275 | ASPHSmoothingScale.cc:110-147 | none */
 enum { SPHB200_H_SPH = 0, SPHB200_H_ASPH = 1, SPHB200_H_NONE = 2,
        SPHB200_H_ASPH_CLASSIC = 3 /* ASPHClassicSmoothingScale (SmoothingScale/ASPHClassicSmoothingScale.cc; SPHHydros.py:133-134, ASPH = "Classic"):
-                                     the ASPH tensor derivative plus the second-moment ideal H; SPH hydro only */ };
+                                     the ASPH tensor derivative plus the second-moment ideal H, behind either hydro */ };
 /* analytic kernels for sphb200_table_kernel_build (Kernel/<name>KernelInline.hh) */
 enum { SPHB200_KERNEL_BSPLINE = 0, SPHB200_KERNEL_WENDLANDC4 = 1, SPHB200_KERNEL_WENDLANDC2 = 2,
        SPHB200_KERNEL_NBSPLINE = 100 /* + order (1..11): NBSplineKernel(order), Kernel/NBSplineKernel.cc:17-122 -- the kernel of the stock

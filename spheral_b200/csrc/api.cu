@@ -254,7 +254,6 @@ static int check_options(sphb200_ctx* c, const sphb200_options* o) {
   if (o->Qkind != SPHB200_Q_MG && o->Qkind != SPHB200_Q_LIMITED_MG) return sphb200_fail(c, "unknown Qkind");
   if (o->hEvolution < SPHB200_H_SPH || o->hEvolution > SPHB200_H_ASPH_CLASSIC) return sphb200_fail(c, "unknown hEvolution");
   if (o->hEvolution == SPHB200_H_ASPH_CLASSIC) {
-    if (o->hydro != SPHB200_HYDRO_SPH) return sphb200_fail(c, "the classic ASPH ideal H (SPHB200_H_ASPH_CLASSIC) is implemented for the SPH hydro only");
     if (!(o->hminratio > 0.0) || !(o->hmin > 0.0) || !(o->hmax > 0.0)) return sphb200_fail(c, "SPHB200_H_ASPH_CLASSIC needs positive hmin, hmax and hminratio");
   }
   if (o->hydro != SPHB200_HYDRO_SPH && o->hydro != SPHB200_HYDRO_CRKSPH) return sphb200_fail(c, "unknown hydro");

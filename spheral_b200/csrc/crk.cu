@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(32*CW, 1) k_crk_derivs(CrkArgs a) {
 #pragma unroll
     for (int q = 0; q < DIM; ++q) put(DV_M1, q, 0.0);
     double dh[NS];
-    if (GEN && op.hEvolution == SPHB200_H_ASPH) asph_DHDt<DIM>(Hi, DvDx, dh);
+    if (GEN && sphb200_is_asph(op.hEvolution)) asph_DHDt<DIM>(Hi, DvDx, dh);      // classic ASPH: the ideal H follows in k_asph_classic
     else {
 #pragma unroll
       for (int q = 0; q < NS; ++q) dh[q] = 0.0;

@@ -680,7 +680,10 @@ def CRKSPH(dataBase, W, Q=None, order=RKOrder.LinearOrder, filter=0.0, cfl=0.25,
                         device=device)
     result.prependSubPackage(Q)                                   # CRKSPHHydros.py:91
     if smoothingScaleMethod is None:                              # CRKSPHHydros.py:94-103
-        smoothingScaleMethod = ASPHSmoothingScale(HUpdate, W) if ASPH else SPHSmoothingScale(HUpdate, W)
+        if isinstance(ASPH, str) and ASPH.upper() == "CLASSIC":
+            smoothingScaleMethod = ASPHClassicSmoothingScale(HUpdate, W)
+        else:
+            smoothingScaleMethod = ASPHSmoothingScale(HUpdate, W) if ASPH else SPHSmoothingScale(HUpdate, W)
     result._smoothingScaleMethod = smoothingScaleMethod
     result.appendSubPackage(smoothingScaleMethod)
     return result

@@ -121,6 +121,17 @@ def test_crk_anisotropic_H(oracle, eng_mod):
     assert_crk_parity(r, st, nInt, nGhost, 3)
 
 
+@pytest.mark.parametrize("ndim,n", [(3, 11), (2, 30)])
+def test_crk_classic_asph_ideal_H(oracle, eng_mod, ndim, n):
+    """ASPHClassicSmoothingScale behind the CRKSPH hydro (CRKSPHHydros.py with ASPH = "Classic"): k_crk_derivs followed by k_asph_classic."""
+    st, nInt, nGhost = common.make_problem(ndim, n, nPerh=1.3 if ndim == 3 else 2.01, kind="aniso", seed=47)
+    WT = K.TableKernel(K.BSplineKernel(ndim), 1000)
+    hb = 1.0/st["H"][:nInt, 0].mean()
+    r = run_crk(oracle, eng_mod, ndim, st, nInt, nGhost, WT, nPerh=2.01, hEvolution=3, hmin=0.02*hb, hmax=50.0*hb, hminratio=0.1)
+    assert_crk_parity(r, st, nInt, nGhost, ndim)
+    assert np.abs(r["got"]["Hideal"][:nInt, 1]).max() > 0.0
+
+
 def test_crk_with_ghosts(oracle, eng_mod):
     st, nInt, nGhost = common.make_problem(2, 24, nPerh=2.01, seed=47, ghosts=True)
     assert nGhost > 0

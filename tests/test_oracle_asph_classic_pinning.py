@@ -133,3 +133,20 @@ def test_size_follows_the_sph_rule_and_shape_follows_the_stretch(oracle, ndim, n
     assert interior.sum() > 0
     yy = 2 if ndim == 2 else 3
     assert np.median(Hid[:, 0]/Hid[:, yy]) < 0.9                              # H_xx < H_yy: the smoothing length is longer along x
+
+
+@pytest.mark.parametrize("ndim,n", [(2, 16), (3, 7)])
+def test_the_package_is_the_same_behind_either_hydro(oracle, ndim, n):
+    """The smoothing-scale sub-package does not know which hydro it follows: except for DHDt (which reads the hydro's DvDx) its outputs
+    behind the CRKSPH restatement equal those behind the SPH one."""
+    st, nInt, nGhost = common.make_problem(ndim, n, nPerh=2.01 if ndim == 2 else 1.3, kind="aniso", seed=33)
+    hb = 1.0/st["H"][:nInt, 0].mean()
+    kw = dict(hmin=0.05*hb, hmax=20.0*hb, hminratio=0.1)
+    dS, OT, s, (pi, pj) = _run(oracle, ndim, st, nInt, nGhost, 2.01, oracle.H_ASPH_CLASSIC, **kw)
+    vol = oracle.crk_sum_volume(ndim, OT, nInt, nGhost, s["pos"], s["H"], pi, pj)
+    corr = oracle.crk_corrections(ndim, OT, nInt, nGhost, s["pos"], s["H"], vol, pi, pj)
+    oo = oracle.default_options(ndim, nPerh=2.01, hEvolution=oracle.H_ASPH_CLASSIC, **kw)
+    dC = oracle.crk_evaluate_derivatives(oo, OT, s, vol, corr, nInt, nGhost, pi, pj)
+    for k in ("Hideal", "massZerothMoment", "massFirstMoment"):
+        a, b = np.asarray(dS[k])[:nInt], np.asarray(dC[k])[:nInt]
+        assert np.abs(a - b).max() <= 1e-13*max(np.abs(a).max(), 1e-300), k
