@@ -480,6 +480,19 @@ class HotPath:
         return {"sum_abs_DvDt": vals[0], "sum_DepsDt": vals[1], "sum_abs_DrhoDt": vals[2], "directed_edges": int(vals[3]), "particles": int(vals[4])}
 
 
+    def e2e_sums(self, dist):
+        """The same sums as checksum(), taken from the HOST buffers the end-to-end leg filled (the derivative fields delivered by
+        sphb200_evaluate_derivatives_to_host / sphb200_download_derivs): equal to the device-resident run's to the last bit."""
+        try:
+            got = {k: t.numpy() for k, t in zip(self.down_names, self.down_bufs["keep"])}
+            N = self.N
+            vals = [float(np.abs(got["DvDt"].reshape(-1, 3)[:N]).sum()), float(got["DepsDt"][:N].sum()), float(np.abs(got["DrhoDt"][:N]).sum())]
+        except Exception:
+            vals = [float("nan")]*3
+        vals = [reduce_over_ranks(dist, v, self.local, "sum") for v in vals]
+        return {"sum_abs_DvDt": vals[0], "sum_DepsDt": vals[1], "sum_abs_DrhoDt": vals[2]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -586,6 +599,8 @@ def main():
     e2e_s = reduce_over_ranks(dist, e2e_wall, local)
     h2d = reduce_over_ranks(dist, float(hp.h2d), local, "sum")
     d2h = reduce_over_ranks(dist, float(hp.d2h), local, "sum")
+    e2e_sums = hp.e2e_sums(dist)
+    e2e_same = all(e2e_sums[k] == checksum[k] for k in e2e_sums)
 
     # weak-scaling extra (N > 1): one 100^3 cube of the same workload per GPU, the round-1 measurement
     weak = None
@@ -654,6 +669,7 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": float(Ntot)*args.steps/e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "timing": "host wall clock around synchronised C-ABI calls (pinned host buffers), max over ranks",
+                        "host_results_equal_device_resident": bool(e2e_same),
                         "calls": ("upload_state, reflect_set_ghost_nodes, [halo], build_pairs, evaluate_derivatives_to_host (pair loop in chunks of the host index "
                                   "range, each chunk's download overlapped with the next chunk's computation)") if hp.fused_e2e else
                                  "upload_state, reflect_set_ghost_nodes, [halo], build_pairs, evaluate_derivatives, download_derivs"},
