@@ -1,4 +1,4 @@
-"""World-size-2 CPU (gloo) test of the multi-GPU host logic: slab decomposition, ghost selection, count exchange and the
+"""World-size-2 and -3 CPU (gloo) tests of the multi-GPU host logic: slab decomposition, ghost selection, count exchange and the
 two-phase point-to-point halo exchange of spheral_b200/distributed.py.  Each rank assembles its slab (internal + received
 ghosts), runs the ORACLE on it, and the internal-node derivatives must equal the oracle's on the undecomposed problem
 (the pair loop needs no communication once the ghosts are in place)."""
@@ -86,7 +86,7 @@ def _worker(rank, world, port, ndim, n, nPerh, aniso, planes=False):
             stg, NG = st, 0
 
         halo = D.SlabHalo()
-        assert (halo.lower, halo.upper) == ((None, 1) if rank == 0 else (0, None))
+        assert (halo.lower, halo.upper) == (rank - 1 if rank > 0 else None, rank + 1 if rank < world - 1 else None)
         ext = D.kernel_extent_axis(local["H"], ndim, kext, axis).max()
         nOwn = nInt + nBG
         width = float(halo.allreduce_max(torch.tensor([ext], dtype=torch.float64)).item())*(1.0 + 1e-9)
@@ -138,6 +138,17 @@ def test_two_slab_halo_exchange_reproduces_global_derivatives(ndim, n, nPerh, an
     from spheral_b200 import build as b
     b.build()
     mp.spawn(_worker, args=(2, _free_port(), ndim, n, nPerh, aniso, planes), nprocs=2, join=True)
+
+
+@pytest.mark.parametrize("ndim,n,nPerh,aniso,planes", [(3, 12, 1.51, False, False), (2, 30, 2.01, True, True)])
+def test_three_slab_halo_exchange_with_a_two_peer_rank(ndim, n, nPerh, aniso, planes):
+    """World size 3: the middle slab exchanges with two peers (both send lists used, ghosts from below and from above), the end slabs
+    with one; same criterion as the two-slab test."""
+    from oracle import oracle as orc
+    orc.build()
+    from spheral_b200 import build as b
+    b.build()
+    mp.spawn(_worker, args=(3, _free_port(), ndim, n, nPerh, aniso, planes), nprocs=3, join=True)
 
 
 def test_send_list_redo_decision_is_the_same_on_every_rank():
