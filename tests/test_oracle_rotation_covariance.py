@@ -134,3 +134,25 @@ def test_step_loops_and_state_update_are_rotationally_covariant(oracle, ndim, n)
         oracle.sym_bound(ndim, a, lo, hi); oracle.sym_bound(ndim, b, lo, hi)
         Fa, Fb = ng.sym_to_full(ndim, a[None])[0], ng.sym_to_full(ndim, b[None])[0]
         assert np.abs(Fb - R @ Fa @ R.T).max() <= 1e-11*np.abs(Fa).max()
+
+
+@pytest.mark.parametrize("ndim,n", [(2, 22), (3, 8)])
+def test_translation_and_galilean_invariance(oracle, ndim, n):
+    """Only differences of positions and velocities enter the pair loop: a shifted, uniformly moving copy of the problem has the same
+    derivatives (DxDt moves with the frame)."""
+    st, nInt, nGhost = common.make_problem(ndim, n, nPerh=2.01 if ndim == 2 else 1.3, kind="aniso", seed=43)
+    s0 = common.to_oracle_state(st)
+    WT = oracle.TableKernel(oracle.KERNEL_BSPLINE, ndim, 1000)
+    o = oracle.default_options(ndim, nPerh=2.01, hEvolution=oracle.H_ASPH, Cl=1.0, Cq=1.5)
+    shift, boost = np.array([0.375, -1.25, 2.5][:ndim]), np.array([0.5, -0.25, 0.125][:ndim])      # exactly representable: differences stay exact to an ulp
+    s1 = dict(s0, pos=np.ascontiguousarray(s0["pos"] + shift), vel=np.ascontiguousarray(s0["vel"] + boost))
+    res = []
+    for s in (s0, s1):
+        pi, pj, cnt = oracle.pairs(ndim, nInt, nGhost, s["pos"], s["H"], WT.kext)
+        res.append((oracle.evaluate_derivatives(o, WT, s, nInt, nGhost, pi, pj, cnt), pi, pj))
+    (d0, pi0, pj0), (d1, pi1, pj1) = res
+    assert np.array_equal(pi0, pi1) and np.array_equal(pj0, pj1)
+    for k in SCALARS + ("DvDt", "gradRho", "XSPHDeltaV") + TENSORS + ("DHDt",):
+        a, b = np.asarray(d1[k])[:nInt], np.asarray(d0[k])[:nInt]
+        assert np.abs(a - b).max() <= 1e-11*max(np.abs(b).max(), 1e-300), k
+    assert np.abs(np.asarray(d1["DxDt"])[:nInt] - (np.asarray(d0["DxDt"])[:nInt] + boost)).max() <= 1e-12
